@@ -1,0 +1,210 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU oracle for the YOLOv8n body + Detect head (FP32, torch CPU).
+
+Restates the network the reference runs through TensorRT
+(/root/reference/src/yolo_engine.cpp:100-105, README.md:9-16,24-25).  The model file is not in the
+reference tree (CMakeLists.txt:114), so the architecture is the published ultralytics YOLOv8n
+(`yolov8.yaml` scale n, modules Conv/C2f/Bottleneck/SPPF/Detect/DFL) at nc = 14
+(/root/reference/include/irmv_detection/armor.hpp:7) with BN already folded into conv weight+bias.
+Parity status: "parity unpinned" -- the reference holds no golden vector for the network
+(test/yolo_test.cpp:36 only bounds the count); the second opinion is OpenCV-DNN running the ONNX
+export of this same module (see oracle/export_onnx.py, tests/test_oracle_cpu.py).
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this module.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+REG_MAX = 16
+STRIDES = (8, 16, 32)
+
+
+class Conv(nn.Module):
+    """Conv2d(bias) [+ SiLU]: the BN-folded form of ultralytics `Conv`."""
+
+    def __init__(self, c1, c2, k=1, s=1, act=True):
+        super().__init__()
+        self.conv = nn.Conv2d(c1, c2, k, s, k // 2, bias=True)
+        self.act = act
+
+    def forward(self, x):
+        y = self.conv(x)
+        return F.silu(y) if self.act else y
+
+
+class Bottleneck(nn.Module):
+    def __init__(self, c, shortcut):
+        super().__init__()
+        self.cv1 = Conv(c, c, 3, 1)
+        self.cv2 = Conv(c, c, 3, 1)
+        self.add = shortcut
+
+    def forward(self, x):
+        y = self.cv2(self.cv1(x))
+        return x + y if self.add else y
+
+
+class C2f(nn.Module):
+    def __init__(self, c1, c2, n, shortcut):
+        super().__init__()
+        self.c = c2 // 2
+        self.cv1 = Conv(c1, 2 * self.c, 1, 1)
+        self.m = nn.ModuleList(Bottleneck(self.c, shortcut) for _ in range(n))
+        self.cv2 = Conv((2 + n) * self.c, c2, 1, 1)
+
+    def forward(self, x):
+        y = list(self.cv1(x).chunk(2, 1))
+        for m in self.m:
+            y.append(m(y[-1]))
+        return self.cv2(torch.cat(y, 1))
+
+
+class SPPF(nn.Module):
+    def __init__(self, c1, c2):
+        super().__init__()
+        self.cv1 = Conv(c1, c1 // 2, 1, 1)
+        self.cv2 = Conv(c1 * 2, c2, 1, 1)
+
+    def forward(self, x):
+        x = self.cv1(x)
+        y1 = F.max_pool2d(x, 5, 1, 2)
+        y2 = F.max_pool2d(y1, 5, 1, 2)
+        y3 = F.max_pool2d(y2, 5, 1, 2)
+        return self.cv2(torch.cat((x, y1, y2, y3), 1))
+
+
+class YoloV8n(nn.Module):
+    """Module order matches irmv_detection_b200.weights.conv_specs()."""
+
+    def __init__(self, nc=14):
+        super().__init__()
+        self.nc = nc
+        self.m0 = Conv(3, 16, 3, 2)
+        self.m1 = Conv(16, 32, 3, 2)
+        self.m2 = C2f(32, 32, 1, True)
+        self.m3 = Conv(32, 64, 3, 2)
+        self.m4 = C2f(64, 64, 2, True)
+        self.m5 = Conv(64, 128, 3, 2)
+        self.m6 = C2f(128, 128, 2, True)
+        self.m7 = Conv(128, 256, 3, 2)
+        self.m8 = C2f(256, 256, 1, True)
+        self.m9 = SPPF(256, 256)
+        self.m12 = C2f(384, 128, 1, False)
+        self.m15 = C2f(192, 64, 1, False)
+        self.m16 = Conv(64, 64, 3, 2)
+        self.m18 = C2f(192, 128, 1, False)
+        self.m19 = Conv(128, 128, 3, 2)
+        self.m21 = C2f(384, 256, 1, False)
+        c3 = max(64, min(nc, 100))
+        self.box = nn.ModuleList(
+            nn.Sequential(Conv(ch, 64, 3), Conv(64, 64, 3), Conv(64, 4 * REG_MAX, 1, 1, act=False))
+            for ch in (64, 128, 256))
+        self.cls = nn.ModuleList(
+            nn.Sequential(Conv(ch, c3, 3), Conv(c3, c3, 3), Conv(c3, nc, 1, 1, act=False))
+            for ch in (64, 128, 256))
+
+    def convs_in_order(self):
+        out = [self.m0.conv, self.m1.conv]
+
+        def c2f(m):
+            r = [m.cv1.conv]
+            for b in m.m:
+                r += [b.cv1.conv, b.cv2.conv]
+            return r + [m.cv2.conv]
+
+        out += c2f(self.m2) + [self.m3.conv] + c2f(self.m4) + [self.m5.conv] + c2f(self.m6)
+        out += [self.m7.conv] + c2f(self.m8) + [self.m9.cv1.conv, self.m9.cv2.conv]
+        out += c2f(self.m12) + c2f(self.m15) + [self.m16.conv] + c2f(self.m18)
+        out += [self.m19.conv] + c2f(self.m21)
+        for i in range(3):
+            out += [self.box[i][0].conv, self.box[i][1].conv, self.box[i][2].conv]
+            out += [self.cls[i][0].conv, self.cls[i][1].conv, self.cls[i][2].conv]
+        return out
+
+    def load_irmw(self, path):
+        from irmv_detection_b200 import weights as W
+        nc, tensors = W.load(path)
+        assert nc == self.nc
+        convs = self.convs_in_order()
+        assert len(convs) == len(tensors)
+        with torch.no_grad():
+            for conv, (spec, w, b) in zip(convs, tensors):
+                assert tuple(conv.weight.shape) == w.shape, spec.name
+                conv.weight.copy_(torch.from_numpy(w))
+                conv.bias.copy_(torch.from_numpy(b))
+        return self
+
+    def features(self, x, taps=None):
+        """Returns per-scale raw head tensors [(box[B,64,H,W], cls[B,nc,H,W])]."""
+        def tap(name, t):
+            if taps is not None:
+                taps[name] = t
+            return t
+        x0 = tap("m0", self.m0(x))
+        x1 = tap("m1", self.m1(x0))
+        x2 = tap("m2", self.m2(x1))
+        x3 = tap("m3", self.m3(x2))
+        x4 = tap("m4", self.m4(x3))
+        x5 = tap("m5", self.m5(x4))
+        x6 = tap("m6", self.m6(x5))
+        x7 = tap("m7", self.m7(x6))
+        x8 = tap("m8", self.m8(x7))
+        x9 = tap("m9", self.m9(x8))
+        u = F.interpolate(x9, scale_factor=2, mode="nearest")
+        x12 = tap("m12", self.m12(torch.cat((u, x6), 1)))
+        u = F.interpolate(x12, scale_factor=2, mode="nearest")
+        x15 = tap("m15", self.m15(torch.cat((u, x4), 1)))
+        x16 = tap("m16", self.m16(x15))
+        x18 = tap("m18", self.m18(torch.cat((x16, x12), 1)))
+        x19 = tap("m19", self.m19(x18))
+        x21 = tap("m21", self.m21(torch.cat((x19, x9), 1)))
+        outs = []
+        for i, f in enumerate((x15, x18, x21)):
+            outs.append((self.box[i](f), self.cls[i](f)))
+        return outs
+
+    def forward(self, x):
+        """x f32[B,3,640,640] -> boxes xyxy f32[B,8400,4] (net px), scores f32[B,8400,nc]."""
+        return decode_heads(self.features(x))
+
+
+def make_anchors(sizes=(80, 40, 20)):
+    pts, strides = [], []
+    for hw, s in zip(sizes, STRIDES):
+        ys, xs = np.meshgrid(np.arange(hw, dtype=np.float32) + 0.5,
+                             np.arange(hw, dtype=np.float32) + 0.5, indexing="ij")
+        pts.append(np.stack((xs.reshape(-1), ys.reshape(-1)), 1))
+        strides.append(np.full((hw * hw,), s, np.float32))
+    return np.concatenate(pts), np.concatenate(strides)
+
+
+def decode_heads(outs):
+    """DFL expectation + dist2bbox(xyxy) * stride, sigmoid class scores (ultralytics Detect/DFL).
+
+    Anchor order: scale-major (80x80, 40x40, 20x20), row-major inside a scale.
+    """
+    B = outs[0][0].shape[0]
+    box = torch.cat([o[0].reshape(B, 4 * REG_MAX, -1) for o in outs], 2)   # [B,64,A]
+    cls = torch.cat([o[1].reshape(B, o[1].shape[1], -1) for o in outs], 2)  # [B,nc,A]
+    A = box.shape[2]
+    p = box.view(B, 4, REG_MAX, A).softmax(2)
+    proj = torch.arange(REG_MAX, dtype=torch.float32).view(1, 1, REG_MAX, 1)
+    dist = (p * proj).sum(2)                                               # [B,4,A] l,t,r,b
+    anchors, strides = make_anchors(tuple(int(o[0].shape[2]) for o in outs))
+    a = torch.from_numpy(anchors).t().unsqueeze(0)                         # [1,2,A]
+    s = torch.from_numpy(strides).view(1, 1, A)
+    x1y1 = (a - dist[:, :2]) * s
+    x2y2 = (a + dist[:, 2:]) * s
+    boxes = torch.cat((x1y1, x2y2), 1).permute(0, 2, 1).contiguous()       # [B,A,4]
+    scores = cls.sigmoid().permute(0, 2, 1).contiguous()                   # [B,A,nc]
+    return boxes, scores
+
+
+def build(weights_path, nc=14):
+    torch.manual_seed(0)
+    m = YoloV8n(nc).eval()
+    m.load_irmw(weights_path)
+    return m
