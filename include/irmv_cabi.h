@@ -1,0 +1,151 @@
+/*
+ * irmv_cabi.h -- C ABI of the B200-native per-frame armor pipeline (libirmv_b200.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  The C++ classes in
+ * include/irmv_detection/{yolo_engine,pnp_solver}.hpp keep the reference's signatures and call
+ * these functions; the Python mirror (irmv_detection_b200/) binds the same symbols with ctypes.
+ * Every function returns 0 on success and a non-zero code on failure (irmv_last_error() then
+ * holds a message); nothing throws across this boundary and nothing falls back to the CPU.
+ *
+ * Reference interfaces replaced (paths into the reference tree, illini-robomaster/irmv_detection):
+ *   irmv_engine_create        <- YoloEngine::YoloEngine          src/yolo_engine.cpp:24-117
+ *   irmv_engine_destroy       <- YoloEngine::~YoloEngine         src/yolo_engine.cpp:119-135
+ *   irmv_engine_src_buffer    <- get_src_image_buffer()          include/irmv_detection/yolo_engine.hpp:35
+ *   irmv_engine_rotated_image <- get_rotated_image()             include/irmv_detection/yolo_engine.hpp:34
+ *   irmv_engine_detect        <- YoloEngine::detect()            src/yolo_engine.cpp:153-177
+ *                                (graph launch :164, sync :165, parse_output :202-220)
+ *   irmv_engine_profile_ms    <- get_profiling_time()            include/irmv_detection/yolo_engine.hpp:33
+ *   irmv_preprocess           <- YoloEngine::preprocess()        src/yolo_engine.cpp:179-200 (NPP K1-K4)
+ *   irmv_nms                  <- EfficientNMS_TRT inside the engine  src/yolo_engine.cpp:33,53-57
+ *   irmv_pnp_create           <- PnPSolver::PnPSolver            src/pnp_solver.cpp:7-34
+ *   irmv_pnp_solve            <- PnPSolver::solvePnP             src/pnp_solver.cpp:36-52
+ *   irmv_pnp_distance_to_center <- calculateDistanceToCenter     src/pnp_solver.cpp:54-59
+ *   irmv_engine_detect_batch / irmv_pnp_solve_batch: batch forms of the same calls for the
+ *   multi-frame configs of BASELINE.json (the reference is batch-1 only).
+ */
+#ifndef IRMV_CABI_H_
+#define IRMV_CABI_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IRMV_NET_SIZE 640      /* src/yolo_engine.cpp:98-99,189-198 */
+#define IRMV_NUM_CLASSES 14    /* include/irmv_detection/armor.hpp:7 */
+#define IRMV_CLASS_UNKNOWN 14
+
+/* channel order of the source buffer */
+enum {
+  IRMV_CH_PASSTHROUGH = 0, /* reference: bytes go to the net in buffer order */
+  IRMV_CH_SWAP_RB = 1,
+  IRMV_CH_BAYER_RGGB = 2,
+  IRMV_CH_BAYER_BGGR = 3,
+  IRMV_CH_BAYER_GRBG = 4,
+  IRMV_CH_BAYER_GBRG = 5
+};
+
+enum { IRMV_RESIZE_STRETCH = 0 /* reference */, IRMV_RESIZE_LETTERBOX = 1 };
+enum { IRMV_CONV_TCGEN05 = 0, IRMV_CONV_DIRECT = 1 /* CUDA-core bring-up kernel */ };
+
+/* Same layout as YoloEngine::bbox (include/irmv_detection/yolo_engine.hpp:19-26): 24 bytes. */
+typedef struct irmv_bbox {
+  float xyxy[4];    /* source-frame pixels (already multiplied by W/640, H/640) */
+  float score;
+  int32_t class_id; /* 0..13, 14 = UNKNOWN */
+} irmv_bbox;
+
+typedef struct irmv_engine_config {
+  int32_t src_width;        /* 1280 in the reference node, src/irm_detector.cpp:142-143 */
+  int32_t src_height;       /* 1024 */
+  int32_t chan_order;       /* IRMV_CH_* */
+  int32_t rotate180;        /* 1 = reference (nppiMirror both axes, src/yolo_engine.cpp:182-184) */
+  int32_t resize_mode;      /* IRMV_RESIZE_* */
+  int32_t quantize_u8;      /* 1 = keep the reference's 8-bit intermediate after the resize */
+  int32_t max_batch;        /* frames per detect_batch call; 1 = reference */
+  int32_t sub_batch;        /* frames per graph replay (<= max_batch); 0 = pick */
+  int32_t num_lanes;        /* concurrent streams replaying sub-batches; 0 = pick */
+  int32_t num_slots;        /* pinned source slots for detect(); 3 = the reference's triple buffer */
+  int32_t device;           /* CUDA device ordinal */
+  int32_t conv_impl;        /* IRMV_CONV_* */
+  int32_t max_det;          /* EfficientNMS max_output_boxes, 100 */
+  float score_thr;          /* 0.25 */
+  float iou_thr;            /* 0.45 */
+  int32_t use_graph;        /* 1 = replay captured CUDA graphs (reference behaviour) */
+  int32_t reserved[8];
+} irmv_engine_config;
+
+typedef struct irmv_engine irmv_engine;
+typedef struct irmv_pnp irmv_pnp;
+
+const char *irmv_last_error(void);
+int irmv_version(void);
+
+/* ---- engine -------------------------------------------------------------------------------- */
+int irmv_engine_config_default(irmv_engine_config *cfg);
+int irmv_engine_create(const char *weights_path, const irmv_engine_config *cfg, irmv_engine **out);
+void irmv_engine_destroy(irmv_engine *e);
+
+/* Borrowed, address-stable pinned-host frame slot the camera writes (src_w*src_h*channels bytes). */
+uint8_t *irmv_engine_src_buffer(irmv_engine *e, int slot);
+/* Rotated frame of `slot` as left by the last detect() on it, copied into dst (packed u8x3). */
+int irmv_engine_rotated_image(irmv_engine *e, int slot, uint8_t *dst);
+
+/* One frame from pinned slot `slot`: H2D + graph(preprocess, net, decode, NMS) + D2H + parse. */
+int irmv_engine_detect(irmv_engine *e, int slot, irmv_bbox *out, int cap, int *n);
+/* nframes <= max_batch contiguous frames; frames_on_device != 0 means a device pointer.
+ * out holds nframes*max_det boxes, counts nframes entries. */
+int irmv_engine_detect_batch(irmv_engine *e, const uint8_t *frames, int frames_on_device,
+                             int nframes, irmv_bbox *out, int *counts);
+/* Same, but leaves results on the device and does not synchronise (bench: inputs resident). */
+int irmv_engine_enqueue_batch(irmv_engine *e, const uint8_t *frames_dev, int nframes);
+int irmv_engine_sync(irmv_engine *e);
+int irmv_engine_fetch(irmv_engine *e, int nframes, irmv_bbox *out, int *counts);
+double irmv_engine_profile_ms(irmv_engine *e);
+/* Device time of the last enqueue/detect (CUDA events on the engine's streams), ms. */
+double irmv_engine_last_device_ms(irmv_engine *e);
+int irmv_engine_kernel_launches(irmv_engine *e, int nframes);
+void *irmv_engine_stream(irmv_engine *e);
+
+/* Parity taps: raw activations of the last run.  name: "input" (preprocessed, NHWC8 FP16),
+ * "box0".."box2" (NHWC64), "cls0".."cls2" (NHWC16), "boxes" (f32 [A,4]), or a module tap
+ * ("m0".."m21").  Copies up to cap_bytes to dst (host); dims receives {B,H,W,C,elem_size}. */
+int irmv_engine_read_tensor(irmv_engine *e, const char *name, void *dst, int64_t cap_bytes,
+                            int32_t dims[5]);
+/* Kept flat indices (anchor*nc+class) of frame i of the last run, for bit-exact NMS parity. */
+int irmv_engine_read_kept_indices(irmv_engine *e, int frame, int32_t *idx, int cap, int *n);
+
+/* ---- stage entry points (each is what the engine runs, exposed for parity tests) ------------ */
+/* src: host u8 frames [n][H][W][3] (or [n][H][W] Bayer); dst: host FP16 [n][640][640][8] NHWC. */
+int irmv_preprocess(const uint8_t *src, int n, int src_w, int src_h, int chan_order,
+                    int rotate180, int resize_mode, int quantize_u8, uint16_t *dst_nhwc8,
+                    uint8_t *rotated_or_null, int device);
+/* boxes f32[n][A][4] xyxy, scores f32[n][A][nc] (host).  Outputs per frame: max_det entries. */
+int irmv_nms(const float *boxes, const float *scores, int n, int anchors, int nc, float score_thr,
+             float iou_thr, int max_det, int32_t *num_dets, float *det_boxes, float *det_scores,
+             int32_t *det_classes, int32_t *det_index, int device);
+/* head tensors (host FP16): box [n][A][64], cls [n][A][16] in anchor order -> decoded boxes and
+ * scores (host f32), the decode half of the fused decode+NMS kernel. */
+int irmv_decode(const uint16_t *box_nhwc, const uint16_t *cls_nhwc, int n, float *boxes,
+                float *scores, int device);
+
+/* ---- PnP ----------------------------------------------------------------------------------- */
+int irmv_pnp_create(const double K[9], const double D[5], int device, irmv_pnp **out);
+void irmv_pnp_destroy(irmv_pnp *p);
+/* img_pts: {LB.x,LB.y, LT.x,LT.y, RT.x,RT.y, RB.x,RB.y} (src/pnp_solver.cpp:41-44). ok=1 solved. */
+int irmv_pnp_solve(irmv_pnp *p, const float img_pts[8], double rvec[3], double tvec[3], int *ok);
+int irmv_pnp_solve_batch(irmv_pnp *p, const float *img_pts, int n, int on_device, int large_armor,
+                         double *rvecs, double *tvecs, uint8_t *ok);
+/* Extended output: quaternion (x,y,z,w) as tf2::Matrix3x3::getRotation gives
+ * (src/irm_detector.cpp:218-226) and both IPPE solutions' RMSE; any pointer may be NULL. */
+int irmv_pnp_solve_batch_ex(irmv_pnp *p, const float *img_pts, int n, int on_device,
+                            int large_armor, double *rvecs, double *tvecs, uint8_t *ok,
+                            double *quats, double *rvecs2, double *tvecs2, double *rmse2);
+double irmv_pnp_last_device_ms(irmv_pnp *p);
+float irmv_pnp_distance_to_center(irmv_pnp *p, float x, float y);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IRMV_CABI_H_ */

@@ -1,0 +1,10 @@
+"""irmv_detection_b200 -- B200-native (sm_100a) per-frame armor pipeline behind the reference's
+YoloEngine / PnPSolver interfaces.  All compute is in libirmv_b200.so (hand-written CUDA); see
+DESIGN.md and include/irmv_cabi.h."""
+from ._lib import (CH_BAYER_BGGR, CH_BAYER_GBRG, CH_BAYER_GRBG, CH_BAYER_RGGB, CH_PASSTHROUGH,
+                   CH_SWAP_RB, CONV_DIRECT, CONV_TCGEN05, IrmvError)
+from .engine import ArmorClass, PnPSolver, YoloEngine, bbox, decode, nms, preprocess
+
+__all__ = ["YoloEngine", "PnPSolver", "ArmorClass", "bbox", "preprocess", "nms", "decode", "IrmvError",
+           "CH_PASSTHROUGH", "CH_SWAP_RB", "CH_BAYER_RGGB", "CH_BAYER_BGGR", "CH_BAYER_GRBG",
+           "CH_BAYER_GBRG", "CONV_TCGEN05", "CONV_DIRECT"]

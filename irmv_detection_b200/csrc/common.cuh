@@ -1,0 +1,121 @@
+// Shared declarations for the sm_100a kernels and the host engine.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+namespace irmv {
+
+constexpr int kNet = 640;           // network input side (reference: src/yolo_engine.cpp:98-99)
+constexpr int kInC = 8;             // conv0 input is NHWC8: RGB + 5 zero channels (16-byte pixels)
+constexpr int kRegMax = 16;
+constexpr int kNumAnchors = 8400;   // 80*80 + 40*40 + 20*20
+constexpr int kClsPad = 16;         // class-logit channels padded 14 -> 16
+constexpr int kMaxCand = 4096;      // pre-NMS top-k (oracle/nms_ref.py MAX_CAND)
+
+void set_error(const std::string &msg);
+bool cuda_ok(cudaError_t e, const char *what, const char *file, int line);
+
+#define IRMV_CUDA(call)                                              \
+  do {                                                               \
+    if (!::irmv::cuda_ok((call), #call, __FILE__, __LINE__)) return 1; \
+  } while (0)
+
+// ---------------------------------------------------------------- preprocess
+struct PreprocessParams {
+  const uint8_t *src;          // [n][H][W][3] or [n][H][W] (Bayer); used when src_indirect == null
+  const uint8_t *const *src_indirect;  // device word holding the frame base pointer (batch path)
+  __half *dst;                 // [n][640][640][8]
+  uint8_t *rotated;            // optional [n][H][W][3] rotated RGB image, may be null
+  int n, src_w, src_h;
+  int chan_order, rotate180, resize_mode, quantize_u8;
+};
+cudaError_t launch_preprocess(const PreprocessParams &p, cudaStream_t s);
+
+// ---------------------------------------------------------------- convolution
+struct ConvSeg {
+  const __half *ptr;  // NHWC tensor base
+  int cstride;        // channels per pixel in the buffer
+  int coff;           // first channel of the slice read
+  int c;              // channels read (multiple of 8)
+  int up;             // 1: tensor is half resolution, read with nearest 2x upsampling
+};
+
+struct ConvParams {
+  ConvSeg seg[2];
+  int nseg;
+  int B, H, W;        // input grid (after upsampling)
+  int OH, OW;
+  int k, stride, pad;
+  int cin;            // seg[0].c + seg[1].c
+  int cout;           // stored output channels (multiple of 8)
+  int npad;           // GEMM N (multiple of 16)
+  int K;              // k*k*cin
+  int kpad;           // K rounded up to 64
+  int act;            // 1 = SiLU
+  const __half *w_plain;   // [npad][kpad], k = (ky*k+kx)*cin + c          (direct kernel)
+  const __half *w_tiled;   // [kpad/64][npad][64] with the 128B swizzle     (tcgen05 kernel)
+  const int32_t *ktab;     // [kpad/8] packed tap table                      (tcgen05 kernel)
+  const float *bias;       // [npad]
+  __half *out;
+  int out_cstride, out_coff;
+  const __half *res;       // residual added after the activation, same grid as out; may be null
+  int res_cstride, res_coff;
+  int sync_mode;           // tcgen05 producer hand-off: 0 = cp.async-tracked mbarrier, 1 = wait+fence
+};
+cudaError_t launch_conv_direct(const ConvParams &p, cudaStream_t s);
+cudaError_t launch_conv_tc(const ConvParams &p, int num_sms, cudaStream_t s);
+size_t conv_tc_smem_bytes(const ConvParams &p, int *stages, int *b_resident);
+
+// ktab entry: bits 0-1 ky, 2-3 kx, 4 segment, 5 valid, 8.. channel offset inside the segment
+__host__ __device__ inline int32_t ktab_pack(int ky, int kx, int seg, int valid, int choff) {
+  return ky | (kx << 2) | (seg << 4) | (valid << 5) | (choff << 8);
+}
+
+// ---------------------------------------------------------------- SPPF pooling
+// in: [B][H][W] slice of c channels at coff; writes maxpool5, maxpool5^2, maxpool5^3 to the
+// three following channel slices of the same buffer (ultralytics SPPF).
+cudaError_t launch_sppf_pool(__half *buf, int B, int H, int W, int cstride, int c, cudaStream_t s);
+
+// ---------------------------------------------------------------- decode + NMS
+struct HeadPtrs {
+  const __half *box[3];   // [B][hw][hw][64]
+  const __half *cls[3];   // [B][hw][hw][16]
+};
+struct DetOut {            // per frame, device
+  int32_t *num_dets;      // [B]
+  float *boxes;           // [B][max_det][4]  network pixels
+  float *scores;          // [B][max_det]
+  int32_t *classes;       // [B][max_det]
+  int32_t *index;         // [B][max_det]  flat anchor*nc+class
+};
+struct NmsScratch {
+  float *boxes;                    // [B][A][4]
+  unsigned long long *keys;        // [B][A*nc]
+  int32_t *counts;                 // [B]
+};
+cudaError_t launch_decode(const HeadPtrs &h, int B, int nc, float score_thr, NmsScratch sc,
+                          float *scores_or_null, cudaStream_t s);
+cudaError_t launch_score_filter(const float *scores, int B, int A, int nc, float score_thr,
+                                NmsScratch sc, cudaStream_t s);
+cudaError_t launch_nms(NmsScratch sc, int B, int A, int nc, float iou_thr, int max_det, DetOut out,
+                       cudaStream_t s);
+
+// ---------------------------------------------------------------- PnP
+struct PnpConsts {
+  double fx, fy, cx, cy;
+  double k1, k2, p1, p2, k3;
+  double half_w[2], half_h[2];   // small, large armor half extents (m)
+};
+struct PnpOut {
+  double *rvec, *tvec;           // [n][3]
+  uint8_t *ok;                   // [n]
+  double *quat;                  // [n][4] or null
+  double *rvec2, *tvec2, *rmse;  // second solution / [n][2] rmse, or null
+};
+cudaError_t launch_pnp(const PnpConsts &c, const float *pts, int n, int large, PnpOut out,
+                       cudaStream_t s);
+
+}  // namespace irmv

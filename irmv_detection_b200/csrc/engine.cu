@@ -1,0 +1,942 @@
+// Host side of libirmv_b200.so: weight loading and re-layout, the YOLOv8n layer program, CUDA
+// graphs on per-lane streams, pinned source slots, and the C ABI of include/irmv_cabi.h.
+//
+// Reference behaviour mirrored here (reference src/yolo_engine.cpp):
+//   :24-117  constructor: allocate buffers, bind, capture {preprocess, network} into a graph
+//   :153-177 detect(): graph launch, stream sync, parse_output
+//   :202-220 parse_output(): scale boxes by (W/640, H/640), class id -> ArmorClass/UNKNOWN
+// What changed: unified memory -> pinned host slots + device buffers; TensorRT/NPP -> the kernels
+// in this directory; batch-1 -> sub-batches replayed on several lanes (streams).
+#include <cstdio>
+#include <cstring>
+#include <chrono>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/irmv_cabi.h"
+#include "common.cuh"
+
+namespace irmv {
+
+static thread_local std::string g_err;
+void set_error(const std::string &msg) { g_err = msg; }
+bool cuda_ok(cudaError_t e, const char *what, const char *file, int line) {
+  if (e == cudaSuccess) return true;
+  char buf[512];
+  snprintf(buf, sizeof buf, "%s:%d: %s -> %s", file, line, what, cudaGetErrorString(e));
+  set_error(buf);
+  return false;
+}
+
+namespace {
+
+struct HostConv {   // one GEMM as the kernels see it (possibly several reference convs merged)
+  int cin_eff = 0, cout = 0, k = 1, stride = 1, act = 1;
+  int npad = 0, K = 0, kpad = 0;
+  std::vector<int> seg_c;            // channels per input segment (sum = cin_eff)
+  std::vector<__half> w_plain;       // [npad][kpad]
+  std::vector<__half> w_tiled;       // [kpad/64][npad][64] swizzled
+  std::vector<float> bias;           // [npad]
+  std::vector<int32_t> ktab;         // [kpad/8]
+  __half *d_plain = nullptr, *d_tiled = nullptr;
+  float *d_bias = nullptr;
+  int32_t *d_ktab = nullptr;
+};
+
+struct FileConv {
+  int cin, cout, k, stride, act;
+  std::vector<float> w, b;   // w [cout][cin][k][k]
+};
+
+bool read_weights(const char *path, int &nc, std::vector<FileConv> &out) {
+  FILE *f = fopen(path, "rb");
+  if (!f) { set_error(std::string("cannot open weight file ") + path); return false; }
+  char magic[4];
+  uint32_t hdr[3];
+  if (fread(magic, 1, 4, f) != 4 || memcmp(magic, "IRMW", 4) != 0 || fread(hdr, 4, 3, f) != 3 ||
+      hdr[0] != 1) {
+    fclose(f);
+    set_error(std::string(path) + ": not an IRMW v1 weight file");
+    return false;
+  }
+  nc = (int)hdr[1];
+  out.resize(hdr[2]);
+  for (auto &c : out) {
+    uint32_t h[5];
+    if (fread(h, 4, 5, f) != 5) { fclose(f); set_error("truncated weight file"); return false; }
+    c.cin = h[0]; c.cout = h[1]; c.k = h[2]; c.stride = h[3]; c.act = h[4];
+    c.w.resize((size_t)c.cout * c.cin * c.k * c.k);
+    c.b.resize(c.cout);
+    if (fread(c.w.data(), 4, c.w.size(), f) != c.w.size() ||
+        fread(c.b.data(), 4, c.b.size(), f) != c.b.size()) {
+      fclose(f); set_error("truncated weight file"); return false;
+    }
+  }
+  fclose(f);
+  return true;
+}
+
+// Build the GEMM operand images.  `parts` are reference convs sharing input/k/stride whose
+// outputs are concatenated along N (the Detect head's box.0 | cls.0 pair); cin_pad >= cin.
+HostConv make_conv(const std::vector<const FileConv *> &parts, int cin_pad,
+                   const std::vector<int> &seg_c) {
+  HostConv h;
+  const FileConv &f0 = *parts[0];
+  h.cin_eff = cin_pad; h.k = f0.k; h.stride = f0.stride; h.act = f0.act;
+  int cout_real = 0;
+  for (auto *p : parts) cout_real += p->cout;
+  h.cout = (cout_real + 7) / 8 * 8;
+  h.npad = (cout_real + 15) / 16 * 16;
+  if (h.cout < h.npad) h.cout = h.npad;   // stored channels == GEMM N (cls head: 14 -> 16)
+  h.K = h.k * h.k * cin_pad;
+  h.kpad = (h.K + 63) / 64 * 64;
+  h.seg_c = seg_c;
+  h.w_plain.assign((size_t)h.npad * h.kpad, __float2half(0.f));
+  h.bias.assign(h.npad, 0.f);
+  int n0 = 0;
+  for (auto *p : parts) {
+    for (int n = 0; n < p->cout; ++n) {
+      h.bias[n0 + n] = p->b[n];
+      for (int c = 0; c < p->cin; ++c)
+        for (int ky = 0; ky < p->k; ++ky)
+          for (int kx = 0; kx < p->k; ++kx) {
+            float v = p->w[(((size_t)n * p->cin + c) * p->k + ky) * p->k + kx];
+            size_t kk = (size_t)(ky * p->k + kx) * cin_pad + c;
+            h.w_plain[(size_t)(n0 + n) * h.kpad + kk] = __float2half(v);
+          }
+    }
+    n0 += p->cout;
+  }
+  // tensor-core image: [kb][n][64] with the 16-byte chunk index XORed by (n & 7)
+  const int KB = h.kpad / 64;
+  h.w_tiled.assign((size_t)KB * h.npad * 64, __float2half(0.f));
+  for (int kb = 0; kb < KB; ++kb)
+    for (int n = 0; n < h.npad; ++n)
+      for (int kk = 0; kk < 64; ++kk) {
+        int chunk = (kk >> 3) ^ (n & 7);
+        h.w_tiled[((size_t)kb * h.npad + n) * 64 + chunk * 8 + (kk & 7)] =
+            h.w_plain[(size_t)n * h.kpad + kb * 64 + kk];
+      }
+  // tap table: one entry per 8-channel chunk of K
+  h.ktab.assign(h.kpad / 8, ktab_pack(0, 0, 0, 0, 0));
+  for (int q = 0; q < h.K / 8; ++q) {
+    int kk = q * 8, tap = kk / cin_pad, c = kk % cin_pad;
+    int sg = 0, off = c;
+    if (seg_c.size() > 1 && c >= seg_c[0]) { sg = 1; off = c - seg_c[0]; }
+    h.ktab[q] = ktab_pack(tap / h.k, tap % h.k, sg, 1, off);
+  }
+  return h;
+}
+
+bool upload(HostConv &h) {
+  auto up = [](void **d, const void *src, size_t bytes) {
+    if (!cuda_ok(cudaMalloc(d, bytes), "cudaMalloc(weights)", __FILE__, __LINE__)) return false;
+    return cuda_ok(cudaMemcpy(*d, src, bytes, cudaMemcpyHostToDevice), "cudaMemcpy(weights)",
+                   __FILE__, __LINE__);
+  };
+  return up((void **)&h.d_plain, h.w_plain.data(), h.w_plain.size() * 2) &&
+         up((void **)&h.d_tiled, h.w_tiled.data(), h.w_tiled.size() * 2) &&
+         up((void **)&h.d_bias, h.bias.data(), h.bias.size() * 4) &&
+         up((void **)&h.d_ktab, h.ktab.data(), h.ktab.size() * 4);
+}
+
+struct Tensor {
+  __half *p = nullptr;
+  int H = 0, W = 0, C = 0;
+};
+
+struct Op {
+  enum Kind { CONV, POOL } kind = CONV;
+  ConvParams cp{};
+  __half *pool_buf = nullptr;
+  int pH = 0, pW = 0, pC = 0, pStride = 0;
+};
+
+struct DetPack {           // one contiguous device block per lane, mirrored in pinned memory
+  size_t bytes = 0;
+  uint8_t *dev = nullptr;
+  int S = 0, max_det = 0;
+  int32_t *num() const { return reinterpret_cast<int32_t *>(dev); }
+  float *boxes() const { return reinterpret_cast<float *>(dev + off_boxes()); }
+  float *scores() const { return reinterpret_cast<float *>(dev + off_scores()); }
+  int32_t *classes() const { return reinterpret_cast<int32_t *>(dev + off_classes()); }
+  int32_t *index() const { return reinterpret_cast<int32_t *>(dev + off_index()); }
+  size_t off_boxes() const { return ((size_t)S * 4 + 15) & ~(size_t)15; }   // float4 stores
+  size_t off_scores() const { return off_boxes() + (size_t)S * max_det * 16; }
+  size_t off_classes() const { return off_scores() + (size_t)S * max_det * 4; }
+  size_t off_index() const { return off_classes() + (size_t)S * max_det * 4; }
+  void init(int s, int md) { S = s; max_det = md; bytes = off_index() + (size_t)S * max_det * 4; }
+};
+
+struct Lane {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
+  std::vector<void *> allocs;
+  std::map<std::string, Tensor> taps;
+  std::vector<Op> ops;
+  Tensor in8;
+  HeadPtrs heads{};
+  NmsScratch nms{};
+  DetPack det;
+  const uint8_t **src_word = nullptr;      // device word: base pointer of the frames of this replay
+  uint8_t *rotated = nullptr;
+  std::map<int, cudaGraphExec_t> graphs;   // keyed by frames in the replay
+  int launches_per_replay = 0;
+};
+
+__global__ void set_src_kernel(const uint8_t **word, const uint8_t *ptr) { *word = ptr; }
+
+}  // namespace
+}  // namespace irmv
+
+using namespace irmv;
+
+struct irmv_engine {
+  irmv_engine_config cfg{};
+  int nc = IRMV_NUM_CLASSES;
+  int num_sms = 148;
+  int S = 1, L = 1;
+  size_t frame_bytes = 0;
+  std::vector<std::unique_ptr<HostConv>> convs;
+  std::vector<Lane> lanes;
+  cudaStream_t main_stream = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+  std::vector<uint8_t *> slots_host;      // pinned
+  uint8_t *slot_dev = nullptr;            // device copy of the frame being detected
+  uint8_t *batch_dev = nullptr;           // staging for host-resident batches
+  uint8_t *res_host = nullptr;            // pinned results: max_batch frames
+  size_t res_frame_stride = 0;
+  double profile_ms = 0.0, device_ms = 0.0;
+  int last_slot = -1;
+  int last_n = 0;
+};
+
+namespace {
+
+bool lane_alloc(Lane &ln, void **p, size_t bytes) {
+  if (!cuda_ok(cudaMalloc(p, bytes), "cudaMalloc(activation)", __FILE__, __LINE__)) return false;
+  ln.allocs.push_back(*p);
+  return cuda_ok(cudaMemset(*p, 0, bytes), "cudaMemset", __FILE__, __LINE__);
+}
+
+bool new_tensor(Lane &ln, int S, int H, int W, int C, Tensor &t, const char *tap = nullptr) {
+  t.H = H; t.W = W; t.C = C;
+  if (!lane_alloc(ln, (void **)&t.p, (size_t)S * H * W * C * 2)) return false;
+  if (tap) ln.taps[tap] = t;
+  return true;
+}
+
+struct SegRef { const Tensor *t; int coff; int c; int up; };
+
+void add_conv(irmv_engine *e, Lane &ln, HostConv &hc, std::vector<SegRef> in, int H, int W,
+              const Tensor &out, int out_coff, const Tensor *res = nullptr, int res_coff = 0) {
+  Op op;
+  op.kind = Op::CONV;
+  ConvParams &p = op.cp;
+  p.nseg = (int)in.size();
+  int cin = 0;
+  for (int i = 0; i < p.nseg; ++i) {
+    p.seg[i].ptr = in[i].t->p; p.seg[i].cstride = in[i].t->C; p.seg[i].coff = in[i].coff;
+    p.seg[i].c = in[i].c; p.seg[i].up = in[i].up;
+    cin += in[i].c;
+  }
+  if (p.nseg == 1) p.seg[1] = p.seg[0];
+  p.B = e->S; p.H = H; p.W = W;
+  p.k = hc.k; p.stride = hc.stride; p.pad = hc.k / 2;
+  p.OH = (H + 2 * p.pad - hc.k) / hc.stride + 1;
+  p.OW = (W + 2 * p.pad - hc.k) / hc.stride + 1;
+  p.cin = cin; p.cout = hc.cout; p.npad = hc.npad; p.K = hc.K; p.kpad = hc.kpad; p.act = hc.act;
+  p.w_plain = hc.d_plain; p.w_tiled = hc.d_tiled; p.ktab = hc.d_ktab; p.bias = hc.d_bias;
+  p.out = out.p; p.out_cstride = out.C; p.out_coff = out_coff;
+  p.res = res ? res->p : nullptr; p.res_cstride = res ? res->C : 0; p.res_coff = res_coff;
+  p.sync_mode = 0;
+  ln.ops.push_back(op);
+}
+
+// C2f (ultralytics): cv1 -> split -> n bottlenecks chained on the last chunk -> cv2 over all chunks.
+// All chunks live in one buffer so split and concat are channel offsets.
+bool add_c2f(irmv_engine *e, Lane &ln, size_t &ci, std::vector<SegRef> in, int H, int W, int c2,
+             int n, bool shortcut, Tensor &out, const char *tap) {
+  const int c = c2 / 2;
+  Tensor buf, tmp;
+  if (!new_tensor(ln, e->S, H, W, (2 + n) * c, buf) || !new_tensor(ln, e->S, H, W, c, tmp) ||
+      !new_tensor(ln, e->S, H, W, c2, out, tap))
+    return false;
+  add_conv(e, ln, *e->convs[ci++], in, H, W, buf, 0);
+  for (int i = 0; i < n; ++i) {
+    add_conv(e, ln, *e->convs[ci++], {{&buf, (1 + i) * c, c, 0}}, H, W, tmp, 0);
+    add_conv(e, ln, *e->convs[ci++], {{&tmp, 0, c, 0}}, H, W, buf, (2 + i) * c,
+             shortcut ? &buf : nullptr, (1 + i) * c);
+  }
+  add_conv(e, ln, *e->convs[ci++], {{&buf, 0, (2 + n) * c, 0}}, H, W, out, 0);
+  return true;
+}
+
+bool build_lane(irmv_engine *e, Lane &ln) {
+  const int S = e->S;
+  if (!cuda_ok(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking), "cudaStreamCreate",
+               __FILE__, __LINE__) ||
+      !cuda_ok(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming), "cudaEventCreate",
+               __FILE__, __LINE__))
+    return false;
+  if (!new_tensor(ln, S, kNet, kNet, kInC, ln.in8, "input")) return false;
+  size_t ci = 0;
+  Tensor t0, t1, x2, t3, x4, t5, x6, t7, x8, sp, x9, x12, x15, t16, x18, t19, x21;
+  if (!new_tensor(ln, S, 320, 320, 16, t0, "m0")) return false;
+  add_conv(e, ln, *e->convs[ci++], {{&ln.in8, 0, kInC, 0}}, 640, 640, t0, 0);
+  if (!new_tensor(ln, S, 160, 160, 32, t1, "m1")) return false;
+  add_conv(e, ln, *e->convs[ci++], {{&t0, 0, 16, 0}}, 320, 320, t1, 0);
+  if (!add_c2f(e, ln, ci, {{&t1, 0, 32, 0}}, 160, 160, 32, 1, true, x2, "m2")) return false;
+  if (!new_tensor(ln, S, 80, 80, 64, t3, "m3")) return false;
+  add_conv(e, ln, *e->convs[ci++], {{&x2, 0, 32, 0}}, 160, 160, t3, 0);
+  if (!add_c2f(e, ln, ci, {{&t3, 0, 64, 0}}, 80, 80, 64, 2, true, x4, "m4")) return false;
+  if (!new_tensor(ln, S, 40, 40, 128, t5, "m5")) return false;
+  add_conv(e, ln, *e->convs[ci++], {{&x4, 0, 64, 0}}, 80, 80, t5, 0);
+  if (!add_c2f(e, ln, ci, {{&t5, 0, 128, 0}}, 40, 40, 128, 2, true, x6, "m6")) return false;
+  if (!new_tensor(ln, S, 20, 20, 256, t7, "m7")) return false;
+  add_conv(e, ln, *e->convs[ci++], {{&x6, 0, 128, 0}}, 40, 40, t7, 0);
+  if (!add_c2f(e, ln, ci, {{&t7, 0, 256, 0}}, 20, 20, 256, 1, true, x8, "m8")) return false;
+  // SPPF: cv1 -> [pool x3 into the next slices] -> cv2
+  if (!new_tensor(ln, S, 20, 20, 512, sp) || !new_tensor(ln, S, 20, 20, 256, x9, "m9")) return false;
+  add_conv(e, ln, *e->convs[ci++], {{&x8, 0, 256, 0}}, 20, 20, sp, 0);
+  {
+    Op op; op.kind = Op::POOL; op.pool_buf = sp.p; op.pH = 20; op.pW = 20; op.pC = 128; op.pStride = 512;
+    ln.ops.push_back(op);
+  }
+  add_conv(e, ln, *e->convs[ci++], {{&sp, 0, 512, 0}}, 20, 20, x9, 0);
+  // neck: upsample and concat happen in the consumers' gathers
+  if (!add_c2f(e, ln, ci, {{&x9, 0, 256, 1}, {&x6, 0, 128, 0}}, 40, 40, 128, 1, false, x12, "m12")) return false;
+  if (!add_c2f(e, ln, ci, {{&x12, 0, 128, 1}, {&x4, 0, 64, 0}}, 80, 80, 64, 1, false, x15, "m15")) return false;
+  if (!new_tensor(ln, S, 40, 40, 64, t16, "m16")) return false;
+  add_conv(e, ln, *e->convs[ci++], {{&x15, 0, 64, 0}}, 80, 80, t16, 0);
+  if (!add_c2f(e, ln, ci, {{&t16, 0, 64, 0}, {&x12, 0, 128, 0}}, 40, 40, 128, 1, false, x18, "m18")) return false;
+  if (!new_tensor(ln, S, 20, 20, 128, t19, "m19")) return false;
+  add_conv(e, ln, *e->convs[ci++], {{&x18, 0, 128, 0}}, 40, 40, t19, 0);
+  if (!add_c2f(e, ln, ci, {{&t19, 0, 128, 0}, {&x9, 0, 256, 0}}, 20, 20, 256, 1, false, x21, "m21")) return false;
+  // Detect head: box.0|cls.0 merged (N=128), then the two towers
+  const Tensor *feat[3] = {&x15, &x18, &x21};
+  const int hw[3] = {80, 40, 20};
+  for (int i = 0; i < 3; ++i) {
+    Tensor h0, hb, hc, bo, co;
+    char nb[8], ncn[8];
+    snprintf(nb, sizeof nb, "box%d", i);
+    snprintf(ncn, sizeof ncn, "cls%d", i);
+    if (!new_tensor(ln, S, hw[i], hw[i], 128, h0) || !new_tensor(ln, S, hw[i], hw[i], 64, hb) ||
+        !new_tensor(ln, S, hw[i], hw[i], 64, hc) || !new_tensor(ln, S, hw[i], hw[i], 64, bo, nb) ||
+        !new_tensor(ln, S, hw[i], hw[i], kClsPad, co, ncn))
+      return false;
+    add_conv(e, ln, *e->convs[ci++], {{feat[i], 0, feat[i]->C, 0}}, hw[i], hw[i], h0, 0);
+    add_conv(e, ln, *e->convs[ci++], {{&h0, 0, 64, 0}}, hw[i], hw[i], hb, 0);
+    add_conv(e, ln, *e->convs[ci++], {{&hb, 0, 64, 0}}, hw[i], hw[i], bo, 0);
+    add_conv(e, ln, *e->convs[ci++], {{&h0, 64, 64, 0}}, hw[i], hw[i], hc, 0);
+    add_conv(e, ln, *e->convs[ci++], {{&hc, 0, 64, 0}}, hw[i], hw[i], co, 0);
+    ln.heads.box[i] = bo.p;
+    ln.heads.cls[i] = co.p;
+  }
+  if (ci != e->convs.size()) { set_error("internal: conv count mismatch"); return false; }
+  // decode / NMS scratch and outputs
+  if (!lane_alloc(ln, (void **)&ln.nms.boxes, (size_t)S * kNumAnchors * 16) ||
+      !lane_alloc(ln, (void **)&ln.nms.keys, (size_t)S * kNumAnchors * e->nc * 8) ||
+      !lane_alloc(ln, (void **)&ln.nms.counts, (size_t)S * 4))
+    return false;
+  ln.det.init(S, e->cfg.max_det);
+  if (!lane_alloc(ln, (void **)&ln.det.dev, ln.det.bytes)) return false;
+  if (!lane_alloc(ln, (void **)&ln.src_word, sizeof(void *))) return false;
+  Tensor bt; bt.p = reinterpret_cast<__half *>(ln.nms.boxes); bt.H = 1; bt.W = kNumAnchors; bt.C = 4;
+  ln.taps["boxes"] = bt;
+  return true;
+}
+
+// Enqueue one replay (n frames) of the whole pipeline on the lane stream.
+int issue_replay(irmv_engine *e, Lane &ln, int n, cudaStream_t st, int *launches) {
+  int cnt = 0;
+  PreprocessParams pp{};
+  pp.src = nullptr; pp.src_indirect = ln.src_word; pp.dst = ln.in8.p; pp.rotated = ln.rotated;
+  pp.n = n; pp.src_w = e->cfg.src_width; pp.src_h = e->cfg.src_height;
+  pp.chan_order = e->cfg.chan_order; pp.rotate180 = e->cfg.rotate180;
+  pp.resize_mode = e->cfg.resize_mode; pp.quantize_u8 = e->cfg.quantize_u8;
+  IRMV_CUDA(launch_preprocess(pp, st)); cnt += 1 + (ln.rotated ? 1 : 0);
+  for (auto &op : ln.ops) {
+    if (op.kind == Op::CONV) {
+      ConvParams p = op.cp;
+      p.B = n;
+      if (e->cfg.conv_impl == IRMV_CONV_DIRECT) IRMV_CUDA(launch_conv_direct(p, st));
+      else IRMV_CUDA(launch_conv_tc(p, e->num_sms, st));
+    } else {
+      IRMV_CUDA(launch_sppf_pool(op.pool_buf, n, op.pH, op.pW, op.pStride, op.pC, st));
+    }
+    ++cnt;
+  }
+  IRMV_CUDA(launch_decode(ln.heads, n, e->nc, e->cfg.score_thr, ln.nms, nullptr, st)); ++cnt;
+  DetOut out{ln.det.num(), ln.det.boxes(), ln.det.scores(), ln.det.classes(), ln.det.index()};
+  IRMV_CUDA(launch_nms(ln.nms, n, kNumAnchors, e->nc, e->cfg.iou_thr, e->cfg.max_det, out, st)); ++cnt;
+  if (launches) *launches = cnt;
+  return 0;
+}
+
+int run_replay(irmv_engine *e, Lane &ln, int n) {
+  if (!e->cfg.use_graph) return issue_replay(e, ln, n, ln.stream, &ln.launches_per_replay);
+  auto it = ln.graphs.find(n);
+  if (it == ln.graphs.end()) {
+    cudaGraph_t g = nullptr;
+    cudaGraphExec_t ge = nullptr;
+    // one eager pass first (function attributes, module load), like the reference's
+    // enqueueV3 before capture (src/yolo_engine.cpp:100-101)
+    if (int rc0 = issue_replay(e, ln, n, ln.stream, &ln.launches_per_replay)) return rc0;
+    IRMV_CUDA(cudaStreamBeginCapture(ln.stream, cudaStreamCaptureModeThreadLocal));
+    int rc = issue_replay(e, ln, n, ln.stream, &ln.launches_per_replay);
+    cudaError_t ce = cudaStreamEndCapture(ln.stream, &g);
+    if (rc) return rc;
+    IRMV_CUDA(ce);
+    IRMV_CUDA(cudaGraphInstantiate(&ge, g, 0));
+    cudaGraphDestroy(g);
+    it = ln.graphs.emplace(n, ge).first;
+  }
+  IRMV_CUDA(cudaGraphLaunch(it->second, ln.stream));
+  return 0;
+}
+
+// frames_dev: device pointer to n contiguous frames.  Results land in res_host (pinned).
+int enqueue(irmv_engine *e, const uint8_t *frames_dev, int n) {
+  IRMV_CUDA(cudaEventRecord(e->ev_start, e->main_stream));
+  const int S = e->S;
+  const int chunks = (n + S - 1) / S;
+  const int used = chunks < e->L ? chunks : e->L;
+  for (int l = 0; l < used; ++l) IRMV_CUDA(cudaStreamWaitEvent(e->lanes[l].stream, e->ev_start, 0));
+  for (int c = 0; c < chunks; ++c) {
+    Lane &ln = e->lanes[c % e->L];
+    const int f0 = c * S, nf = (n - f0) < S ? (n - f0) : S;
+    set_src_kernel<<<1, 1, 0, ln.stream>>>(ln.src_word, frames_dev + (size_t)f0 * e->frame_bytes);
+    IRMV_CUDA(cudaGetLastError());
+    if (int rc = run_replay(e, ln, nf)) return rc;
+    // results: the lane's packed block -> pinned host, one copy per array so a partial replay
+    // still lands at the frame's slot
+    uint8_t *h = e->res_host;
+    const int md = e->cfg.max_det;
+    const size_t B = e->cfg.max_batch;
+    IRMV_CUDA(cudaMemcpyAsync(h + (size_t)f0 * 4, ln.det.num(), (size_t)nf * 4, cudaMemcpyDeviceToHost, ln.stream));
+    size_t o = B * 4;
+    IRMV_CUDA(cudaMemcpyAsync(h + o + (size_t)f0 * md * 16, ln.det.boxes(), (size_t)nf * md * 16, cudaMemcpyDeviceToHost, ln.stream));
+    o += B * md * 16;
+    IRMV_CUDA(cudaMemcpyAsync(h + o + (size_t)f0 * md * 4, ln.det.scores(), (size_t)nf * md * 4, cudaMemcpyDeviceToHost, ln.stream));
+    o += B * md * 4;
+    IRMV_CUDA(cudaMemcpyAsync(h + o + (size_t)f0 * md * 4, ln.det.classes(), (size_t)nf * md * 4, cudaMemcpyDeviceToHost, ln.stream));
+    o += B * md * 4;
+    IRMV_CUDA(cudaMemcpyAsync(h + o + (size_t)f0 * md * 4, ln.det.index(), (size_t)nf * md * 4, cudaMemcpyDeviceToHost, ln.stream));
+  }
+  for (int l = 0; l < used; ++l) {
+    IRMV_CUDA(cudaEventRecord(e->lanes[l].done, e->lanes[l].stream));
+    IRMV_CUDA(cudaStreamWaitEvent(e->main_stream, e->lanes[l].done, 0));
+  }
+  IRMV_CUDA(cudaEventRecord(e->ev_stop, e->main_stream));
+  e->last_n = n;
+  return 0;
+}
+
+// reference parse_output (src/yolo_engine.cpp:202-220)
+void parse(irmv_engine *e, int n, irmv_bbox *out, int *counts) {
+  const int md = e->cfg.max_det;
+  const size_t B = e->cfg.max_batch;
+  const uint8_t *h = e->res_host;
+  const int32_t *num = reinterpret_cast<const int32_t *>(h);
+  const float *boxes = reinterpret_cast<const float *>(h + B * 4);
+  const float *scores = reinterpret_cast<const float *>(h + B * 4 + B * md * 16);
+  const int32_t *cls = reinterpret_cast<const int32_t *>(h + B * 4 + B * md * 20);
+  const float sx = (float)e->cfg.src_width / 640, sy = (float)e->cfg.src_height / 640;
+  for (int f = 0; f < n; ++f) {
+    int k = num[f];
+    if (counts) counts[f] = k;
+    for (int i = 0; i < k; ++i) {
+      const float *b = boxes + ((size_t)f * md + i) * 4;
+      irmv_bbox &o = out[(size_t)f * md + i];
+      o.xyxy[0] = b[0] * sx; o.xyxy[1] = b[1] * sy; o.xyxy[2] = b[2] * sx; o.xyxy[3] = b[3] * sy;
+      o.score = scores[(size_t)f * md + i];
+      int c = cls[(size_t)f * md + i];
+      o.class_id = (c >= 0 && c < IRMV_NUM_CLASSES) ? c : IRMV_CLASS_UNKNOWN;
+    }
+  }
+}
+
+}  // namespace
+
+// =============================================================================== C ABI
+extern "C" {
+
+const char *irmv_last_error(void) { return g_err.c_str(); }
+int irmv_version(void) { return 100; }
+
+int irmv_engine_config_default(irmv_engine_config *c) {
+  if (!c) return 1;
+  memset(c, 0, sizeof *c);
+  c->src_width = 1280; c->src_height = 1024;
+  c->chan_order = IRMV_CH_PASSTHROUGH; c->rotate180 = 1; c->resize_mode = IRMV_RESIZE_STRETCH;
+  c->quantize_u8 = 1; c->max_batch = 1; c->sub_batch = 0; c->num_lanes = 0; c->num_slots = 3;
+  c->device = 0; c->conv_impl = IRMV_CONV_TCGEN05; c->max_det = 100;
+  c->score_thr = 0.25f; c->iou_thr = 0.45f; c->use_graph = 1;
+  return 0;
+}
+
+int irmv_engine_create(const char *weights_path, const irmv_engine_config *cfg, irmv_engine **out) {
+  if (!weights_path || !cfg || !out) { set_error("null argument"); return 1; }
+  if (cfg->resize_mode != IRMV_RESIZE_STRETCH) { set_error("resize_mode LETTERBOX is not built yet"); return 2; }
+  if (cfg->max_batch < 1 || cfg->src_width < 2 || cfg->src_height < 2 || cfg->max_det < 1 || cfg->max_det > 1024) {
+    set_error("bad engine config"); return 2;
+  }
+  int ndev = 0;
+  IRMV_CUDA(cudaGetDeviceCount(&ndev));
+  if (cfg->device < 0 || cfg->device >= ndev) { set_error("no such CUDA device"); return 3; }
+  IRMV_CUDA(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  IRMV_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) { set_error("libirmv_b200 needs an sm_100 (Blackwell) GPU"); return 3; }
+  std::unique_ptr<irmv_engine> e(new irmv_engine);
+  e->cfg = *cfg;
+  e->num_sms = prop.multiProcessorCount;
+  std::vector<FileConv> fc;
+  if (!read_weights(weights_path, e->nc, fc)) return 4;
+  if (fc.size() != 63 || e->nc != IRMV_NUM_CLASSES) { set_error("weight file is not YOLOv8n nc=14"); return 4; }
+  // 63 reference convs -> 60 GEMMs (Detect box.0|cls.0 merged per scale)
+  auto single = [&](size_t i, int cin_pad, std::vector<int> seg) {
+    e->convs.emplace_back(new HostConv(make_conv({&fc[i]}, cin_pad, seg)));
+  };
+  size_t i = 0;
+  single(i++, kInC, {kInC});                                   // m0: 3 -> 8 input channels
+  for (; i < 45; ++i) {
+    int cin = fc[i].cin;
+    std::vector<int> seg{cin};
+    // concat-on-read layers: first conv of m12, m15, m18, m21 (cv1 over two sources)
+    if (i == 27) seg = {256, 128};
+    if (i == 31) seg = {128, 64};
+    if (i == 36) seg = {64, 128};
+    if (i == 41) seg = {128, 256};
+    single(i, cin, seg);
+  }
+  for (int s = 0; s < 3; ++s) {
+    size_t b = 45 + (size_t)s * 6;
+    e->convs.emplace_back(new HostConv(make_conv({&fc[b + 0], &fc[b + 3]}, fc[b].cin, {fc[b].cin})));
+    single(b + 1, 64, {64});
+    single(b + 2, 64, {64});
+    single(b + 4, 64, {64});
+    single(b + 5, 64, {64});
+  }
+  for (auto &c : e->convs) if (!upload(*c)) return 5;
+
+  const bool bayer = cfg->chan_order >= 2;
+  e->frame_bytes = (size_t)cfg->src_width * cfg->src_height * (bayer ? 1 : 3);
+  e->S = cfg->sub_batch > 0 ? cfg->sub_batch : (cfg->max_batch < 8 ? cfg->max_batch : 8);
+  if (e->S > cfg->max_batch) e->S = cfg->max_batch;
+  int chunks = (cfg->max_batch + e->S - 1) / e->S;
+  e->L = cfg->num_lanes > 0 ? cfg->num_lanes : (chunks < 4 ? chunks : 4);
+  if (e->L > chunks) e->L = chunks;
+  e->lanes.resize(e->L);
+  IRMV_CUDA(cudaStreamCreateWithFlags(&e->main_stream, cudaStreamNonBlocking));
+  IRMV_CUDA(cudaEventCreate(&e->ev_start));
+  IRMV_CUDA(cudaEventCreate(&e->ev_stop));
+  for (auto &ln : e->lanes) if (!build_lane(e.get(), ln)) return 6;
+  int nslots = cfg->num_slots > 0 ? cfg->num_slots : 1;
+  e->slots_host.resize(nslots, nullptr);
+  for (auto &s : e->slots_host) {
+    IRMV_CUDA(cudaHostAlloc((void **)&s, e->frame_bytes, cudaHostAllocDefault));
+    memset(s, 0, e->frame_bytes);
+  }
+  IRMV_CUDA(cudaMalloc((void **)&e->slot_dev, e->frame_bytes));
+  const size_t md = cfg->max_det, B = cfg->max_batch;
+  size_t res_bytes = B * 4 + B * md * (16 + 4 + 4 + 4);
+  IRMV_CUDA(cudaHostAlloc((void **)&e->res_host, res_bytes, cudaHostAllocDefault));
+  memset(e->res_host, 0, res_bytes);
+  IRMV_CUDA(cudaDeviceSynchronize());
+  *out = e.release();
+  return 0;
+}
+
+void irmv_engine_destroy(irmv_engine *e) {
+  if (!e) return;
+  cudaSetDevice(e->cfg.device);
+  cudaDeviceSynchronize();
+  for (auto &ln : e->lanes) {
+    for (auto &g : ln.graphs) cudaGraphExecDestroy(g.second);
+    for (void *p : ln.allocs) cudaFree(p);
+    if (ln.rotated) cudaFree(ln.rotated);
+    if (ln.stream) cudaStreamDestroy(ln.stream);
+    if (ln.done) cudaEventDestroy(ln.done);
+  }
+  for (auto &c : e->convs) {
+    cudaFree(c->d_plain); cudaFree(c->d_tiled); cudaFree(c->d_bias); cudaFree(c->d_ktab);
+  }
+  for (auto s : e->slots_host) cudaFreeHost(s);
+  cudaFree(e->slot_dev);
+  if (e->batch_dev) cudaFree(e->batch_dev);
+  cudaFreeHost(e->res_host);
+  cudaEventDestroy(e->ev_start); cudaEventDestroy(e->ev_stop);
+  cudaStreamDestroy(e->main_stream);
+  delete e;
+}
+
+uint8_t *irmv_engine_src_buffer(irmv_engine *e, int slot) {
+  if (!e || slot < 0 || slot >= (int)e->slots_host.size()) { set_error("bad slot"); return nullptr; }
+  return e->slots_host[slot];
+}
+
+int irmv_engine_detect(irmv_engine *e, int slot, irmv_bbox *out, int cap, int *n) {
+  if (!e || !n || slot < 0 || slot >= (int)e->slots_host.size()) { set_error("bad argument"); return 1; }
+  auto t0 = std::chrono::high_resolution_clock::now();
+  IRMV_CUDA(cudaSetDevice(e->cfg.device));
+  Lane &ln = e->lanes[0];
+  IRMV_CUDA(cudaMemcpyAsync(e->slot_dev, e->slots_host[slot], e->frame_bytes, cudaMemcpyHostToDevice, e->main_stream));
+  if (int rc = enqueue(e, e->slot_dev, 1)) return rc;
+  IRMV_CUDA(cudaStreamSynchronize(e->main_stream));
+  (void)ln;
+  std::vector<irmv_bbox> tmp(e->cfg.max_det);
+  int k = 0;
+  parse(e, 1, tmp.data(), &k);
+  *n = k < cap ? k : cap;
+  if (out) memcpy(out, tmp.data(), sizeof(irmv_bbox) * (size_t)*n);
+  e->last_slot = slot;
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e->ev_start, e->ev_stop);
+  e->device_ms = ms;
+  auto t1 = std::chrono::high_resolution_clock::now();
+  e->profile_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+  return 0;
+}
+
+int irmv_engine_enqueue_batch(irmv_engine *e, const uint8_t *frames_dev, int nframes) {
+  if (!e || !frames_dev || nframes < 1 || nframes > e->cfg.max_batch) { set_error("bad argument"); return 1; }
+  IRMV_CUDA(cudaSetDevice(e->cfg.device));
+  return enqueue(e, frames_dev, nframes);
+}
+
+int irmv_engine_sync(irmv_engine *e) {
+  if (!e) return 1;
+  IRMV_CUDA(cudaStreamSynchronize(e->main_stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e->ev_start, e->ev_stop);
+  e->device_ms = ms;
+  return 0;
+}
+
+int irmv_engine_fetch(irmv_engine *e, int nframes, irmv_bbox *out, int *counts) {
+  if (!e || !out || nframes < 1 || nframes > e->cfg.max_batch) { set_error("bad argument"); return 1; }
+  parse(e, nframes, out, counts);
+  return 0;
+}
+
+int irmv_engine_detect_batch(irmv_engine *e, const uint8_t *frames, int on_device, int nframes,
+                             irmv_bbox *out, int *counts) {
+  if (!e || !frames || !out || nframes < 1 || nframes > e->cfg.max_batch) { set_error("bad argument"); return 1; }
+  auto t0 = std::chrono::high_resolution_clock::now();
+  IRMV_CUDA(cudaSetDevice(e->cfg.device));
+  const uint8_t *dev = frames;
+  if (!on_device) {
+    if (!e->batch_dev) IRMV_CUDA(cudaMalloc((void **)&e->batch_dev, e->frame_bytes * (size_t)e->cfg.max_batch));
+    IRMV_CUDA(cudaMemcpyAsync(e->batch_dev, frames, e->frame_bytes * (size_t)nframes, cudaMemcpyHostToDevice, e->main_stream));
+    dev = e->batch_dev;
+  }
+  if (int rc = enqueue(e, dev, nframes)) return rc;
+  if (int rc = irmv_engine_sync(e)) return rc;
+  parse(e, nframes, out, counts);
+  auto t1 = std::chrono::high_resolution_clock::now();
+  e->profile_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+  return 0;
+}
+
+double irmv_engine_profile_ms(irmv_engine *e) { return e ? e->profile_ms : 0.0; }
+double irmv_engine_last_device_ms(irmv_engine *e) { return e ? e->device_ms : 0.0; }
+void *irmv_engine_stream(irmv_engine *e) { return e ? (void *)e->main_stream : nullptr; }
+
+int irmv_engine_kernel_launches(irmv_engine *e, int nframes) {
+  if (!e) return 0;
+  int chunks = (nframes + e->S - 1) / e->S;
+  return chunks * (e->lanes[0].launches_per_replay + 1);
+}
+
+int irmv_engine_rotated_image(irmv_engine *e, int slot, uint8_t *dst) {
+  if (!e || !dst || slot < 0 || slot >= (int)e->slots_host.size()) { set_error("bad argument"); return 1; }
+  IRMV_CUDA(cudaSetDevice(e->cfg.device));
+  const size_t bytes = (size_t)e->cfg.src_width * e->cfg.src_height * 3;
+  uint8_t *d = nullptr;
+  IRMV_CUDA(cudaMalloc((void **)&d, bytes));
+  IRMV_CUDA(cudaMemcpyAsync(e->slot_dev, e->slots_host[slot], e->frame_bytes, cudaMemcpyHostToDevice, e->main_stream));
+  PreprocessParams pp{};
+  pp.src = e->slot_dev; pp.dst = e->lanes[0].in8.p; pp.rotated = d; pp.n = 1;
+  pp.src_w = e->cfg.src_width; pp.src_h = e->cfg.src_height; pp.chan_order = e->cfg.chan_order;
+  pp.rotate180 = e->cfg.rotate180; pp.resize_mode = e->cfg.resize_mode; pp.quantize_u8 = e->cfg.quantize_u8;
+  cudaError_t ce = launch_preprocess(pp, e->main_stream);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(dst, d, bytes, cudaMemcpyDeviceToHost, e->main_stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->main_stream);
+  cudaFree(d);
+  IRMV_CUDA(ce);
+  return 0;
+}
+
+int irmv_engine_read_tensor(irmv_engine *e, const char *name, void *dst, int64_t cap, int32_t dims[5]) {
+  if (!e || !name || !dims) { set_error("bad argument"); return 1; }
+  IRMV_CUDA(cudaSetDevice(e->cfg.device));
+  Lane &ln = e->lanes[0];
+  auto it = ln.taps.find(name);
+  if (it == ln.taps.end()) { set_error(std::string("no tensor named ") + name); return 2; }
+  const Tensor &t = it->second;
+  int es = strcmp(name, "boxes") == 0 ? 4 : 2;
+  int nb = e->last_n < e->S ? (e->last_n > 0 ? e->last_n : 1) : e->S;
+  dims[0] = nb; dims[1] = t.H; dims[2] = t.W; dims[3] = t.C; dims[4] = es;
+  int64_t bytes = (int64_t)nb * t.H * t.W * t.C * es;
+  if (dst) {
+    if (bytes > cap) { set_error("destination too small"); return 3; }
+    IRMV_CUDA(cudaDeviceSynchronize());
+    IRMV_CUDA(cudaMemcpy(dst, t.p, (size_t)bytes, cudaMemcpyDeviceToHost));
+  }
+  return 0;
+}
+
+int irmv_engine_read_kept_indices(irmv_engine *e, int frame, int32_t *idx, int cap, int *n) {
+  if (!e || !idx || !n || frame < 0 || frame >= e->cfg.max_batch) { set_error("bad argument"); return 1; }
+  const size_t md = e->cfg.max_det, B = e->cfg.max_batch;
+  const int32_t *num = reinterpret_cast<const int32_t *>(e->res_host);
+  const int32_t *index = reinterpret_cast<const int32_t *>(e->res_host + B * 4 + B * md * 24);
+  int k = num[frame];
+  *n = k < cap ? k : cap;
+  memcpy(idx, index + (size_t)frame * md, (size_t)*n * 4);
+  return 0;
+}
+
+// ------------------------------------------------------------------ stage entry points
+int irmv_preprocess(const uint8_t *src, int n, int src_w, int src_h, int chan_order, int rotate180,
+                    int resize_mode, int quantize_u8, uint16_t *dst, uint8_t *rotated, int device) {
+  if (!src || !dst || n < 1) { set_error("bad argument"); return 1; }
+  if (resize_mode != IRMV_RESIZE_STRETCH) { set_error("resize_mode LETTERBOX is not built yet"); return 2; }
+  IRMV_CUDA(cudaSetDevice(device));
+  const size_t fb = (size_t)src_w * src_h * (chan_order >= 2 ? 1 : 3);
+  const size_t ob = (size_t)kNet * kNet * kInC * 2;
+  uint8_t *ds = nullptr, *dr = nullptr;
+  __half *dd = nullptr;
+  IRMV_CUDA(cudaMalloc((void **)&ds, fb * n));
+  IRMV_CUDA(cudaMalloc((void **)&dd, ob * n));
+  if (rotated) IRMV_CUDA(cudaMalloc((void **)&dr, (size_t)src_w * src_h * 3 * n));
+  IRMV_CUDA(cudaMemcpy(ds, src, fb * n, cudaMemcpyHostToDevice));
+  PreprocessParams pp{};
+  pp.src = ds; pp.dst = dd; pp.rotated = dr; pp.n = n; pp.src_w = src_w; pp.src_h = src_h;
+  pp.chan_order = chan_order; pp.rotate180 = rotate180; pp.resize_mode = resize_mode; pp.quantize_u8 = quantize_u8;
+  cudaError_t ce = launch_preprocess(pp, 0);
+  if (ce == cudaSuccess) ce = cudaDeviceSynchronize();
+  if (ce == cudaSuccess) ce = cudaMemcpy(dst, dd, ob * n, cudaMemcpyDeviceToHost);
+  if (ce == cudaSuccess && rotated) ce = cudaMemcpy(rotated, dr, (size_t)src_w * src_h * 3 * n, cudaMemcpyDeviceToHost);
+  cudaFree(ds); cudaFree(dd); if (dr) cudaFree(dr);
+  IRMV_CUDA(ce);
+  return 0;
+}
+
+static int alloc_nms(int n, int A, int nc, int max_det, NmsScratch &sc, DetPack &dp) {
+  IRMV_CUDA(cudaMalloc((void **)&sc.boxes, (size_t)n * A * 16));
+  IRMV_CUDA(cudaMalloc((void **)&sc.keys, (size_t)n * A * nc * 8));
+  IRMV_CUDA(cudaMalloc((void **)&sc.counts, (size_t)n * 4));
+  IRMV_CUDA(cudaMemset(sc.counts, 0, (size_t)n * 4));
+  dp.init(n, max_det);
+  IRMV_CUDA(cudaMalloc((void **)&dp.dev, dp.bytes));
+  IRMV_CUDA(cudaMemset(dp.dev, 0, dp.bytes));
+  return 0;
+}
+
+int irmv_nms(const float *boxes, const float *scores, int n, int A, int nc, float score_thr,
+             float iou_thr, int max_det, int32_t *num_dets, float *det_boxes, float *det_scores,
+             int32_t *det_classes, int32_t *det_index, int device) {
+  if (!boxes || !scores || !num_dets || n < 1 || A < 1 || nc < 1 || max_det < 1) { set_error("bad argument"); return 1; }
+  IRMV_CUDA(cudaSetDevice(device));
+  NmsScratch sc{};
+  DetPack dp;
+  if (int rc = alloc_nms(n, A, nc, max_det, sc, dp)) return rc;
+  float *ds = nullptr;
+  IRMV_CUDA(cudaMalloc((void **)&ds, (size_t)n * A * nc * 4));
+  IRMV_CUDA(cudaMemcpy(sc.boxes, boxes, (size_t)n * A * 16, cudaMemcpyHostToDevice));
+  IRMV_CUDA(cudaMemcpy(ds, scores, (size_t)n * A * nc * 4, cudaMemcpyHostToDevice));
+  cudaError_t ce = launch_score_filter(ds, n, A, nc, score_thr, sc, 0);
+  DetOut out{dp.num(), dp.boxes(), dp.scores(), dp.classes(), dp.index()};
+  if (ce == cudaSuccess) ce = launch_nms(sc, n, A, nc, iou_thr, max_det, out, 0);
+  if (ce == cudaSuccess) ce = cudaDeviceSynchronize();
+  std::vector<uint8_t> host(dp.bytes);
+  if (ce == cudaSuccess) ce = cudaMemcpy(host.data(), dp.dev, dp.bytes, cudaMemcpyDeviceToHost);
+  cudaFree(sc.boxes); cudaFree(sc.keys); cudaFree(sc.counts); cudaFree(dp.dev); cudaFree(ds);
+  IRMV_CUDA(ce);
+  memcpy(num_dets, host.data(), (size_t)n * 4);
+  if (det_boxes) memcpy(det_boxes, host.data() + dp.off_boxes(), (size_t)n * max_det * 16);
+  if (det_scores) memcpy(det_scores, host.data() + dp.off_scores(), (size_t)n * max_det * 4);
+  if (det_classes) memcpy(det_classes, host.data() + dp.off_classes(), (size_t)n * max_det * 4);
+  if (det_index) memcpy(det_index, host.data() + dp.off_index(), (size_t)n * max_det * 4);
+  return 0;
+}
+
+int irmv_decode(const uint16_t *box, const uint16_t *cls, int n, float *boxes, float *scores, int device) {
+  if (!box || !cls || !boxes || !scores || n < 1) { set_error("bad argument"); return 1; }
+  IRMV_CUDA(cudaSetDevice(device));
+  const int nc = IRMV_NUM_CLASSES;
+  NmsScratch sc{};
+  DetPack dp;
+  if (int rc = alloc_nms(n, kNumAnchors, nc, 1, sc, dp)) return rc;
+  // inputs arrive in anchor order [n][A][C]; the kernel wants one tensor per scale [n][hw*hw][C]
+  const int cnt[3] = {6400, 1600, 400}, off[3] = {0, 6400, 8000};
+  HeadPtrs h{};
+  __half *db[3], *dc[3];
+  float *dscores = nullptr;
+  IRMV_CUDA(cudaMalloc((void **)&dscores, (size_t)n * kNumAnchors * nc * 4));
+  for (int s = 0; s < 3; ++s) {
+    IRMV_CUDA(cudaMalloc((void **)&db[s], (size_t)n * cnt[s] * 64 * 2));
+    IRMV_CUDA(cudaMalloc((void **)&dc[s], (size_t)n * cnt[s] * kClsPad * 2));
+    for (int f = 0; f < n; ++f) {
+      IRMV_CUDA(cudaMemcpy(db[s] + (size_t)f * cnt[s] * 64, box + ((size_t)f * kNumAnchors + off[s]) * 64,
+                           (size_t)cnt[s] * 64 * 2, cudaMemcpyHostToDevice));
+      IRMV_CUDA(cudaMemcpy(dc[s] + (size_t)f * cnt[s] * kClsPad, cls + ((size_t)f * kNumAnchors + off[s]) * kClsPad,
+                           (size_t)cnt[s] * kClsPad * 2, cudaMemcpyHostToDevice));
+    }
+    h.box[s] = db[s]; h.cls[s] = dc[s];
+  }
+  cudaError_t ce = launch_decode(h, n, nc, 2.0f /* no candidates */, sc, dscores, 0);
+  if (ce == cudaSuccess) ce = cudaDeviceSynchronize();
+  if (ce == cudaSuccess) ce = cudaMemcpy(boxes, sc.boxes, (size_t)n * kNumAnchors * 16, cudaMemcpyDeviceToHost);
+  if (ce == cudaSuccess) ce = cudaMemcpy(scores, dscores, (size_t)n * kNumAnchors * nc * 4, cudaMemcpyDeviceToHost);
+  for (int s = 0; s < 3; ++s) { cudaFree(db[s]); cudaFree(dc[s]); }
+  cudaFree(sc.boxes); cudaFree(sc.keys); cudaFree(sc.counts); cudaFree(dp.dev); cudaFree(dscores);
+  IRMV_CUDA(ce);
+  return 0;
+}
+
+}  // extern "C"
+
+// =============================================================================== PnP
+struct irmv_pnp {
+  PnpConsts c{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double last_ms = 0.0;
+  // small persistent buffers for the single-armor call
+  float *d_pts1 = nullptr;
+  double *d_out1 = nullptr;   // rvec[3] tvec[3]
+  uint8_t *d_ok1 = nullptr;
+  float *h_pts1 = nullptr;    // pinned
+  double *h_out1 = nullptr;
+  uint8_t *h_ok1 = nullptr;
+};
+
+extern "C" {
+
+int irmv_pnp_create(const double K[9], const double D[5], int device, irmv_pnp **out) {
+  if (!K || !D || !out) { set_error("null argument"); return 1; }
+  int ndev = 0;
+  IRMV_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) { set_error("no such CUDA device"); return 3; }
+  IRMV_CUDA(cudaSetDevice(device));
+  std::unique_ptr<irmv_pnp> p(new irmv_pnp);
+  p->device = device;
+  // reference src/pnp_solver.cpp:10-15: K row-major 3x3, D first five coefficients
+  p->c.fx = K[0]; p->c.cx = K[2]; p->c.fy = K[4]; p->c.cy = K[5];
+  p->c.k1 = D[0]; p->c.k2 = D[1]; p->c.p1 = D[2]; p->c.p2 = D[3]; p->c.k3 = D[4];
+  // reference include/irmv_detection/pnp_solver.hpp:30-33 (mm) and src/pnp_solver.cpp:18-21
+  p->c.half_w[0] = 135.0 / 2.0 / 1000.0; p->c.half_h[0] = 55.0 / 2.0 / 1000.0;
+  p->c.half_w[1] = 225.0 / 2.0 / 1000.0; p->c.half_h[1] = 55.0 / 2.0 / 1000.0;
+  IRMV_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+  IRMV_CUDA(cudaEventCreate(&p->ev0));
+  IRMV_CUDA(cudaEventCreate(&p->ev1));
+  IRMV_CUDA(cudaMalloc((void **)&p->d_pts1, 32));
+  IRMV_CUDA(cudaMalloc((void **)&p->d_out1, 48));
+  IRMV_CUDA(cudaMalloc((void **)&p->d_ok1, 4));
+  IRMV_CUDA(cudaHostAlloc((void **)&p->h_pts1, 32, cudaHostAllocDefault));
+  IRMV_CUDA(cudaHostAlloc((void **)&p->h_out1, 48, cudaHostAllocDefault));
+  IRMV_CUDA(cudaHostAlloc((void **)&p->h_ok1, 4, cudaHostAllocDefault));
+  *out = p.release();
+  return 0;
+}
+
+void irmv_pnp_destroy(irmv_pnp *p) {
+  if (!p) return;
+  cudaSetDevice(p->device);
+  cudaStreamSynchronize(p->stream);
+  cudaFree(p->d_pts1); cudaFree(p->d_out1); cudaFree(p->d_ok1);
+  cudaFreeHost(p->h_pts1); cudaFreeHost(p->h_out1); cudaFreeHost(p->h_ok1);
+  cudaEventDestroy(p->ev0); cudaEventDestroy(p->ev1);
+  cudaStreamDestroy(p->stream);
+  delete p;
+}
+
+int irmv_pnp_solve(irmv_pnp *p, const float img_pts[8], double rvec[3], double tvec[3], int *ok) {
+  if (!p || !img_pts || !rvec || !tvec) { set_error("null argument"); return 1; }
+  IRMV_CUDA(cudaSetDevice(p->device));
+  memcpy(p->h_pts1, img_pts, 32);
+  IRMV_CUDA(cudaMemcpyAsync(p->d_pts1, p->h_pts1, 32, cudaMemcpyHostToDevice, p->stream));
+  PnpOut o{p->d_out1, p->d_out1 + 3, p->d_ok1, nullptr, nullptr, nullptr, nullptr};
+  IRMV_CUDA(launch_pnp(p->c, p->d_pts1, 1, 0 /* reference: small_armor = true, src/pnp_solver.cpp:47 */, o, p->stream));
+  IRMV_CUDA(cudaMemcpyAsync(p->h_out1, p->d_out1, 48, cudaMemcpyDeviceToHost, p->stream));
+  IRMV_CUDA(cudaMemcpyAsync(p->h_ok1, p->d_ok1, 1, cudaMemcpyDeviceToHost, p->stream));
+  IRMV_CUDA(cudaStreamSynchronize(p->stream));
+  memcpy(rvec, p->h_out1, 24);
+  memcpy(tvec, p->h_out1 + 3, 24);
+  if (ok) *ok = p->h_ok1[0];
+  return 0;
+}
+
+int irmv_pnp_solve_batch_ex(irmv_pnp *p, const float *img_pts, int n, int on_device, int large,
+                            double *rvecs, double *tvecs, uint8_t *ok, double *quats,
+                            double *rvecs2, double *tvecs2, double *rmse2) {
+  if (!p || !img_pts || !rvecs || !tvecs || n < 1) { set_error("bad argument"); return 1; }
+  IRMV_CUDA(cudaSetDevice(p->device));
+  const bool want2 = rvecs2 && tvecs2 && rmse2;
+  float *dp = nullptr;
+  double *dr = nullptr, *dt = nullptr, *dq = nullptr, *dr2 = nullptr, *dt2 = nullptr, *de = nullptr;
+  uint8_t *dk = nullptr;
+  if (on_device) dp = const_cast<float *>(img_pts);
+  else {
+    IRMV_CUDA(cudaMalloc((void **)&dp, (size_t)n * 32));
+    IRMV_CUDA(cudaMemcpyAsync(dp, img_pts, (size_t)n * 32, cudaMemcpyHostToDevice, p->stream));
+  }
+  IRMV_CUDA(cudaMalloc((void **)&dr, (size_t)n * 24));
+  IRMV_CUDA(cudaMalloc((void **)&dt, (size_t)n * 24));
+  IRMV_CUDA(cudaMalloc((void **)&dk, (size_t)n));
+  if (quats) IRMV_CUDA(cudaMalloc((void **)&dq, (size_t)n * 32));
+  if (want2) {
+    IRMV_CUDA(cudaMalloc((void **)&dr2, (size_t)n * 24));
+    IRMV_CUDA(cudaMalloc((void **)&dt2, (size_t)n * 24));
+    IRMV_CUDA(cudaMalloc((void **)&de, (size_t)n * 16));
+  }
+  PnpOut o{dr, dt, dk, dq, dr2, dt2, de};
+  IRMV_CUDA(cudaEventRecord(p->ev0, p->stream));
+  IRMV_CUDA(launch_pnp(p->c, dp, n, large, o, p->stream));
+  IRMV_CUDA(cudaEventRecord(p->ev1, p->stream));
+  IRMV_CUDA(cudaMemcpyAsync(rvecs, dr, (size_t)n * 24, cudaMemcpyDeviceToHost, p->stream));
+  IRMV_CUDA(cudaMemcpyAsync(tvecs, dt, (size_t)n * 24, cudaMemcpyDeviceToHost, p->stream));
+  if (ok) IRMV_CUDA(cudaMemcpyAsync(ok, dk, (size_t)n, cudaMemcpyDeviceToHost, p->stream));
+  if (quats) IRMV_CUDA(cudaMemcpyAsync(quats, dq, (size_t)n * 32, cudaMemcpyDeviceToHost, p->stream));
+  if (want2) {
+    IRMV_CUDA(cudaMemcpyAsync(rvecs2, dr2, (size_t)n * 24, cudaMemcpyDeviceToHost, p->stream));
+    IRMV_CUDA(cudaMemcpyAsync(tvecs2, dt2, (size_t)n * 24, cudaMemcpyDeviceToHost, p->stream));
+    IRMV_CUDA(cudaMemcpyAsync(rmse2, de, (size_t)n * 16, cudaMemcpyDeviceToHost, p->stream));
+  }
+  IRMV_CUDA(cudaStreamSynchronize(p->stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, p->ev0, p->ev1);
+  p->last_ms = ms;
+  if (!on_device) cudaFree(dp);
+  cudaFree(dr); cudaFree(dt); cudaFree(dk);
+  if (dq) cudaFree(dq);
+  if (want2) { cudaFree(dr2); cudaFree(dt2); cudaFree(de); }
+  return 0;
+}
+
+int irmv_pnp_solve_batch(irmv_pnp *p, const float *img_pts, int n, int on_device, int large,
+                         double *rvecs, double *tvecs, uint8_t *ok) {
+  return irmv_pnp_solve_batch_ex(p, img_pts, n, on_device, large, rvecs, tvecs, ok, nullptr, nullptr,
+                                 nullptr, nullptr);
+}
+
+double irmv_pnp_last_device_ms(irmv_pnp *p) { return p ? p->last_ms : 0.0; }
+
+// The reference reads its CV_64F camera matrix with .at<float> (src/pnp_solver.cpp:56-57), which
+// yields garbage principal-point values.  This implements the intended
+// computation: distance from the image point to (cx, cy).
+float irmv_pnp_distance_to_center(irmv_pnp *p, float x, float y) {
+  if (!p) return 0.f;
+  float dx = x - (float)p->c.cx, dy = y - (float)p->c.cy;
+  return sqrtf(dx * dx + dy * dy);
+}
+
+}  // extern "C"

@@ -1,0 +1,264 @@
+// Fused preprocess for sm_100a: one kernel replaces the reference's four NPP calls
+// (nppiMirror -> nppiResize LINEAR -> nppiScale /255 -> nppiCopy HWC->CHW,
+// reference src/yolo_engine.cpp:179-200) and the camera ISP's Bayer->RGB step
+// (reference src/mv_camera.cpp:96).  HBM-bound: each source byte is read once with 128-bit
+// loads into shared memory, each output pixel is written once as one 16-byte NHWC8 FP16 store.
+//
+// Arithmetic is written with explicitly rounded FP32 intrinsics so it is bit-identical to
+// oracle/preprocess_ref.py (no FMA contraction).
+#include "common.cuh"
+
+namespace irmv {
+namespace {
+
+constexpr int TH = 8;     // output rows per CTA
+constexpr int TW = 64;    // output cols per CTA
+constexpr int NT = 256;
+
+struct Taps { int i0, i1; float f; };
+
+__device__ __forceinline__ Taps axis_taps(int d, float scale, int n_src) {
+  float s = __fsub_rn(__fmul_rn(__fadd_rn((float)d, 0.5f), scale), 0.5f);
+  float fl = floorf(s);
+  Taps t;
+  t.f = __fsub_rn(s, fl);
+  int i0 = (int)fl;
+  t.i0 = min(max(i0, 0), n_src - 1);
+  t.i1 = min(max(i0 + 1, 0), n_src - 1);
+  return t;
+}
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * n - 2 - i;
+  return i;
+}
+
+struct Region {
+  const uint8_t *frame;   // frame base (global)
+  const uint8_t *smem;    // staged rows
+  int row_lo;             // first staged source row
+  int pitch_s;            // bytes per staged row
+  int col_byte_lo;        // first needed byte inside a source row
+  int src_pitch;          // bytes per source row
+};
+
+// byte of source row `sy`, byte column `bx` (already inside the staged window)
+__device__ __forceinline__ int rd(const Region &r, int sy, int bx) {
+  size_t row_addr = (size_t)(r.frame + (size_t)sy * r.src_pitch + r.col_byte_lo);
+  int shift = (int)(row_addr & 15);
+  return r.smem[(sy - r.row_lo) * r.pitch_s + shift + (bx - r.col_byte_lo)];
+}
+
+// RGB at source pixel (sy,sx) of a Bayer mosaic, bilinear demosaic (oracle demosaic_bilinear)
+__device__ __forceinline__ void bayer_rgb(const Region &r, int sy, int sx, int H, int W, int red_y,
+                                          int red_x, int &R, int &G, int &B) {
+  int ym = reflect101(sy - 1, H), yp = reflect101(sy + 1, H);
+  int xm = reflect101(sx - 1, W), xp = reflect101(sx + 1, W);
+  int c = rd(r, sy, sx);
+  int py = sy & 1, px = sx & 1;
+  bool is_r = (py == red_y) && (px == red_x);
+  bool is_b = (py != red_y) && (px != red_x);
+  if (is_r || is_b) {
+    int cross = (rd(r, ym, sx) + rd(r, yp, sx) + rd(r, sy, xm) + rd(r, sy, xp) + 2) >> 2;
+    int diag = (rd(r, ym, xm) + rd(r, ym, xp) + rd(r, yp, xm) + rd(r, yp, xp) + 2) >> 2;
+    G = cross;
+    if (is_r) { R = c; B = diag; } else { B = c; R = diag; }
+  } else {
+    int horiz = (rd(r, sy, xm) + rd(r, sy, xp) + 1) >> 1;
+    int vert = (rd(r, ym, sx) + rd(r, yp, sx) + 1) >> 1;
+    G = c;
+    bool on_red_row = (py == red_y);
+    R = on_red_row ? horiz : vert;
+    B = on_red_row ? vert : horiz;
+  }
+}
+
+__device__ __forceinline__ float lerp4(float p00, float p01, float p10, float p11, float fx,
+                                       float fy) {
+  float ofx = __fsub_rn(1.0f, fx), ofy = __fsub_rn(1.0f, fy);
+  float top = __fadd_rn(__fmul_rn(p00, ofx), __fmul_rn(p01, fx));
+  float bot = __fadd_rn(__fmul_rn(p10, ofx), __fmul_rn(p11, fx));
+  return __fadd_rn(__fmul_rn(top, ofy), __fmul_rn(bot, fy));
+}
+
+__device__ __forceinline__ float finish(float v, int quantize) {
+  if (quantize) v = fminf(fmaxf(floorf(__fadd_rn(v, 0.5f)), 0.0f), 255.0f);
+  return __fdiv_rn(v, 255.0f);
+}
+
+__global__ void __launch_bounds__(NT)
+preprocess_kernel(PreprocessParams p, int rows_cap, int pitch_s) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int n = blockIdx.z;
+  const int oy0 = blockIdx.y * TH, ox0 = blockIdx.x * TW;
+  const bool bayer = p.chan_order >= 2;
+  const int bpp = bayer ? 1 : 3;
+  const int H = p.src_h, W = p.src_w;
+  const int src_pitch = W * bpp;
+  const size_t frame_bytes = (size_t)H * src_pitch;
+  const uint8_t *base = p.src_indirect ? *p.src_indirect : p.src;
+  const uint8_t *frame = base + (size_t)n * frame_bytes;
+  const float scale_x = __fdiv_rn((float)W, (float)kNet);
+  const float scale_y = __fdiv_rn((float)H, (float)kNet);
+
+  // window of rotated-space taps needed by this tile
+  Taps ty0 = axis_taps(oy0, scale_y, H), ty1 = axis_taps(min(oy0 + TH, kNet) - 1, scale_y, H);
+  Taps tx0 = axis_taps(ox0, scale_x, W), tx1 = axis_taps(min(ox0 + TW, kNet) - 1, scale_x, W);
+  int ry_lo = ty0.i0, ry_hi = ty1.i1, rx_lo = tx0.i0, rx_hi = tx1.i1;
+  int sy_lo = p.rotate180 ? H - 1 - ry_hi : ry_lo, sy_hi = p.rotate180 ? H - 1 - ry_lo : ry_hi;
+  int sx_lo = p.rotate180 ? W - 1 - rx_hi : rx_lo, sx_hi = p.rotate180 ? W - 1 - rx_lo : rx_hi;
+  if (bayer) {
+    sy_lo = max(sy_lo - 2, 0); sy_hi = min(sy_hi + 2, H - 1);
+    sx_lo = max(sx_lo - 2, 0); sx_hi = min(sx_hi + 2, W - 1);
+  }
+  const int nrows = sy_hi - sy_lo + 1;
+  const int col_byte_lo = sx_lo * bpp;
+  const int nbytes = (sx_hi - sx_lo + 1) * bpp;
+
+  // stage: 16-byte chunks, aligned on absolute addresses, per source row
+  const int chunks_per_row = pitch_s >> 4;
+  const uint8_t *alloc_end = base + (size_t)p.n * frame_bytes;
+  for (int i = threadIdx.x; i < nrows * chunks_per_row; i += NT) {
+    int r = i / chunks_per_row, c = i - r * chunks_per_row;
+    const uint8_t *row = frame + (size_t)(sy_lo + r) * src_pitch + col_byte_lo;
+    const uint8_t *a = (const uint8_t *)((size_t)row & ~(size_t)15) + (size_t)c * 16;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (a < row + nbytes && a < alloc_end) v = __ldg((const uint4 *)a);
+    *(uint4 *)(smem + (size_t)r * pitch_s + c * 16) = v;
+  }
+  __syncthreads();
+  (void)rows_cap;
+
+  Region reg{frame, smem, sy_lo, pitch_s, col_byte_lo, src_pitch};
+  int red_y = 0, red_x = 0;
+  if (p.chan_order == 3) { red_y = 1; red_x = 1; }       // BGGR
+  else if (p.chan_order == 4) { red_y = 0; red_x = 1; }  // GRBG
+  else if (p.chan_order == 5) { red_y = 1; red_x = 0; }  // GBRG
+  const bool swap = (p.chan_order == 1);
+
+  for (int q = threadIdx.x; q < TH * TW; q += NT) {
+    int oy = oy0 + q / TW, ox = ox0 + q % TW;
+    if (oy >= kNet || ox >= kNet) continue;
+    Taps ty = axis_taps(oy, scale_y, H), tx = axis_taps(ox, scale_x, W);
+    int ys[2] = {ty.i0, ty.i1}, xs[2] = {tx.i0, tx.i1};
+    float pix[2][2][3];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        int sy = p.rotate180 ? H - 1 - ys[a] : ys[a];
+        int sx = p.rotate180 ? W - 1 - xs[b] : xs[b];
+        int R, G, B;
+        if (bayer) {
+          bayer_rgb(reg, sy, sx, H, W, red_y, red_x, R, G, B);
+        } else {
+          R = rd(reg, sy, sx * 3 + 0);
+          G = rd(reg, sy, sx * 3 + 1);
+          B = rd(reg, sy, sx * 3 + 2);
+          if (swap) { int t = R; R = B; B = t; }
+        }
+        pix[a][b][0] = (float)R; pix[a][b][1] = (float)G; pix[a][b][2] = (float)B;
+      }
+    }
+    float v[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      v[c] = finish(lerp4(pix[0][0][c], pix[0][1][c], pix[1][0][c], pix[1][1][c], tx.f, ty.f),
+                    p.quantize_u8);
+    __half2 h01 = __halves2half2(__float2half_rn(v[0]), __float2half_rn(v[1]));
+    __half2 h23 = __halves2half2(__float2half_rn(v[2]), __float2half_rn(0.0f));
+    uint4 o;
+    o.x = *reinterpret_cast<uint32_t *>(&h01);
+    o.y = *reinterpret_cast<uint32_t *>(&h23);
+    o.z = 0u; o.w = 0u;
+    size_t pix_idx = ((size_t)n * kNet + oy) * kNet + ox;
+    *reinterpret_cast<uint4 *>(p.dst + pix_idx * kInC) = o;
+  }
+}
+
+// Optional: materialise the rotated RGB frame (what get_rotated_image() exposes in the reference,
+// include/irmv_detection/yolo_engine.hpp:34) for consumers of the rotated source image.
+__global__ void rotate_kernel(PreprocessParams p) {
+  const bool bayer = p.chan_order >= 2;
+  const int H = p.src_h, W = p.src_w, bpp = bayer ? 1 : 3;
+  const size_t frame_bytes = (size_t)H * W * bpp;
+  const uint8_t *base = p.src_indirect ? *p.src_indirect : p.src;
+  size_t total = (size_t)p.n * H * W;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    int n = (int)(i / ((size_t)H * W));
+    int rem = (int)(i - (size_t)n * H * W);
+    int y = rem / W, x = rem - y * W;
+    int sy = p.rotate180 ? H - 1 - y : y, sx = p.rotate180 ? W - 1 - x : x;
+    const uint8_t *frame = base + (size_t)n * frame_bytes;
+    int R, G, B;
+    if (bayer) {
+      Region reg{frame, frame, 0, W, 0, W};
+      // direct global reads: shift term must vanish, so index manually
+      auto g = [&](int yy, int xx) { return (int)frame[(size_t)yy * W + xx]; };
+      int red_y = 0, red_x = 0;
+      if (p.chan_order == 3) { red_y = 1; red_x = 1; }
+      else if (p.chan_order == 4) { red_y = 0; red_x = 1; }
+      else if (p.chan_order == 5) { red_y = 1; red_x = 0; }
+      int ym = reflect101(sy - 1, H), yp = reflect101(sy + 1, H);
+      int xm = reflect101(sx - 1, W), xp = reflect101(sx + 1, W);
+      int c = g(sy, sx), py = sy & 1, px = sx & 1;
+      bool is_r = (py == red_y) && (px == red_x), is_b = (py != red_y) && (px != red_x);
+      if (is_r || is_b) {
+        int cross = (g(ym, sx) + g(yp, sx) + g(sy, xm) + g(sy, xp) + 2) >> 2;
+        int diag = (g(ym, xm) + g(ym, xp) + g(yp, xm) + g(yp, xp) + 2) >> 2;
+        G = cross;
+        if (is_r) { R = c; B = diag; } else { B = c; R = diag; }
+      } else {
+        int horiz = (g(sy, xm) + g(sy, xp) + 1) >> 1, vert = (g(ym, sx) + g(yp, sx) + 1) >> 1;
+        G = c;
+        bool on_red_row = (py == red_y);
+        R = on_red_row ? horiz : vert;
+        B = on_red_row ? vert : horiz;
+      }
+      (void)reg;
+    } else {
+      const uint8_t *s = frame + ((size_t)sy * W + sx) * 3;
+      R = s[0]; G = s[1]; B = s[2];
+      if (p.chan_order == 1) { int t = R; R = B; B = t; }
+    }
+    uint8_t *d = p.rotated + i * 3;
+    d[0] = (uint8_t)R; d[1] = (uint8_t)G; d[2] = (uint8_t)B;
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_preprocess(const PreprocessParams &p, cudaStream_t s) {
+  if (p.n <= 0) return cudaSuccess;
+  const bool bayer = p.chan_order >= 2;
+  const int bpp = bayer ? 1 : 3;
+  const float sx = (float)p.src_w / kNet, sy = (float)p.src_h / kNet;
+  int rows_cap = (int)(TH * sy) + 4 + (bayer ? 4 : 0);
+  int cols_cap = (int)(TW * sx) + 4 + (bayer ? 4 : 0);
+  int pitch_s = ((cols_cap * bpp + 15) / 16 + 2) * 16;   // +1 chunk for the alignment shift
+  size_t smem = (size_t)rows_cap * pitch_s;
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(preprocess_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  dim3 grid((kNet + TW - 1) / TW, (kNet + TH - 1) / TH, p.n);
+  preprocess_kernel<<<grid, NT, smem, s>>>(p, rows_cap, pitch_s);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if (p.rotated) {
+    size_t total = (size_t)p.n * p.src_h * p.src_w;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    rotate_kernel<<<blocks, 256, 0, s>>>(p);
+    e = cudaGetLastError();
+  }
+  return e;
+}
+
+}  // namespace irmv

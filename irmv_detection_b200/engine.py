@@ -1,0 +1,279 @@
+"""Python mirror of the reference's YoloEngine / PnPSolver interfaces over the C ABI.
+
+Names, argument meaning and error behaviour follow the reference classes
+(/root/reference/include/irmv_detection/yolo_engine.hpp:16-73, pnp_solver.hpp:12-38); the
+arithmetic is entirely in libirmv_b200.so (CUDA, sm_100a).  numpy is used for host buffers only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import os
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib as L
+
+
+class ArmorClass(enum.IntEnum):
+    """/root/reference/include/irmv_detection/armor.hpp:7"""
+    B1 = 0; B2 = 1; B3 = 2; B4 = 3; B5 = 4; BO = 5; BS = 6
+    R1 = 7; R2 = 8; R3 = 9; R4 = 10; R5 = 11; RO = 12; RS = 13
+    UNKNOWN = 14
+
+
+@dataclass
+class bbox:
+    """YoloEngine::bbox, /root/reference/include/irmv_detection/yolo_engine.hpp:19-26"""
+    xyxy: Tuple[float, float, float, float]
+    score: float
+    class_id: ArmorClass
+
+
+def weights_path_for(onnx_file_path: str) -> str:
+    """The reference swaps the .onnx extension for .engine (src/yolo_engine.cpp:28-31); the
+    B200 engine swaps it for .irmw."""
+    root, _ = os.path.splitext(onnx_file_path)
+    return root + ".irmw"
+
+
+class YoloEngine:
+    """YoloEngine(onnx_file_path, src_image_size=(W,H), enable_profiling=False)
+
+    Extra keyword arguments expose what the reference hard-codes: channel order, rotation,
+    batch size and the bring-up convolution kernel.
+    """
+
+    def __init__(self, onnx_file_path: str, src_image_size: Tuple[int, int] = (1280, 1024),
+                 enable_profiling: bool = False, *, chan_order: int = L.CH_PASSTHROUGH,
+                 rotate180: bool = True, quantize_u8: bool = True, max_batch: int = 1,
+                 sub_batch: int = 0, num_lanes: int = 0, num_slots: int = 3, device: int = 0,
+                 conv_impl: int = L.CONV_TCGEN05, score_thr: float = 0.25, iou_thr: float = 0.45,
+                 max_det: int = 100, use_graph: bool = True):
+        lib = L.lib()
+        wpath = onnx_file_path if onnx_file_path.endswith(".irmw") else weights_path_for(onnx_file_path)
+        if not os.path.exists(wpath):
+            # reference: prints and exit(0)s (src/yolo_engine.cpp:37-40); raising is the Python form
+            raise FileNotFoundError(f"weight file {wpath} not found (build it with "
+                                    "irmv_detection_b200.weights.write_random or convert a checkpoint)")
+        cfg = L.EngineConfig()
+        L.check(lib.irmv_engine_config_default(C.byref(cfg)), "irmv_engine_config_default")
+        cfg.src_width, cfg.src_height = int(src_image_size[0]), int(src_image_size[1])
+        cfg.chan_order = chan_order
+        cfg.rotate180 = int(rotate180)
+        cfg.quantize_u8 = int(quantize_u8)
+        cfg.max_batch, cfg.sub_batch, cfg.num_lanes, cfg.num_slots = max_batch, sub_batch, num_lanes, num_slots
+        cfg.device, cfg.conv_impl = device, conv_impl
+        cfg.score_thr, cfg.iou_thr, cfg.max_det = score_thr, iou_thr, max_det
+        cfg.use_graph = int(use_graph)
+        self._cfg = cfg
+        self._h = C.c_void_p()
+        self._lib = lib
+        L.check(lib.irmv_engine_create(wpath.encode(), C.byref(cfg), C.byref(self._h)), "irmv_engine_create")
+        self.src_image_size = (cfg.src_width, cfg.src_height)
+        self.enable_profiling = enable_profiling
+        self.channels = 1 if chan_order >= L.CH_BAYER_RGGB else 3
+        self.frame_bytes = cfg.src_width * cfg.src_height * self.channels
+        self.max_batch, self.max_det = max_batch, max_det
+        self._slot = 0
+        self._out = (L.Bbox * (max_batch * max_det))()
+        self._counts = (C.c_int * max_batch)()
+
+    # -- reference surface ---------------------------------------------------------------
+    def get_src_image_buffer(self, slot: int = 0) -> np.ndarray:
+        """Pinned-host frame slot as a writable numpy view (reference returns uint8_t*)."""
+        p = self._lib.irmv_engine_src_buffer(self._h, slot)
+        if not p:
+            raise L.IrmvError("bad slot")
+        buf = (C.c_uint8 * self.frame_bytes).from_address(p)
+        shape = (self.src_image_size[1], self.src_image_size[0]) + ((3,) if self.channels == 3 else ())
+        return np.frombuffer(buf, np.uint8).reshape(shape)
+
+    def detect(self, slot: int = 0) -> List[bbox]:
+        n = C.c_int(0)
+        L.check(self._lib.irmv_engine_detect(self._h, slot, self._out, self.max_det, C.byref(n)), "irmv_engine_detect")
+        self._slot = slot
+        return self._to_list(0, n.value)
+
+    def get_rotated_image(self, slot: Optional[int] = None) -> np.ndarray:
+        slot = self._slot if slot is None else slot
+        out = np.empty((self.src_image_size[1], self.src_image_size[0], 3), np.uint8)
+        L.check(self._lib.irmv_engine_rotated_image(self._h, slot, out.ctypes.data), "irmv_engine_rotated_image")
+        return out
+
+    def get_profiling_time(self) -> float:
+        return float(self._lib.irmv_engine_profile_ms(self._h))
+
+    # -- batch extension -----------------------------------------------------------------
+    def detect_batch(self, frames: np.ndarray) -> List[List[bbox]]:
+        """frames u8 [n,H,W,3] (or [n,H,W] Bayer) in host memory."""
+        frames = np.ascontiguousarray(frames, np.uint8)
+        n = frames.shape[0]
+        if frames[0].size != self.frame_bytes:
+            raise ValueError("frame size does not match the engine's src_image_size")
+        L.check(self._lib.irmv_engine_detect_batch(self._h, frames.ctypes.data, 0, n, self._out, self._counts),
+                "irmv_engine_detect_batch")
+        return [self._to_list(f, self._counts[f]) for f in range(n)]
+
+    def detect_batch_device(self, dev_ptr: int, n: int) -> List[List[bbox]]:
+        L.check(self._lib.irmv_engine_detect_batch(self._h, C.c_void_p(dev_ptr), 1, n, self._out, self._counts),
+                "irmv_engine_detect_batch")
+        return [self._to_list(f, self._counts[f]) for f in range(n)]
+
+    def enqueue_batch_device(self, dev_ptr: int, n: int) -> None:
+        L.check(self._lib.irmv_engine_enqueue_batch(self._h, C.c_void_p(dev_ptr), n), "irmv_engine_enqueue_batch")
+
+    def sync(self) -> float:
+        L.check(self._lib.irmv_engine_sync(self._h), "irmv_engine_sync")
+        return float(self._lib.irmv_engine_last_device_ms(self._h))
+
+    def fetch(self, n: int) -> List[List[bbox]]:
+        L.check(self._lib.irmv_engine_fetch(self._h, n, self._out, self._counts), "irmv_engine_fetch")
+        return [self._to_list(f, self._counts[f]) for f in range(n)]
+
+    def last_device_ms(self) -> float:
+        return float(self._lib.irmv_engine_last_device_ms(self._h))
+
+    def kernel_launches(self, n: int) -> int:
+        return int(self._lib.irmv_engine_kernel_launches(self._h, n))
+
+    # -- parity taps ---------------------------------------------------------------------
+    def read_tensor(self, name: str) -> np.ndarray:
+        dims = (C.c_int32 * 5)()
+        L.check(self._lib.irmv_engine_read_tensor(self._h, name.encode(), None, 0, C.byref(dims)), "read_tensor")
+        b, h, w, c, es = list(dims)
+        out = np.empty((b, h, w, c), np.float32 if es == 4 else np.float16)
+        L.check(self._lib.irmv_engine_read_tensor(self._h, name.encode(), out.ctypes.data, out.nbytes, C.byref(dims)),
+                "read_tensor")
+        return out
+
+    def kept_indices(self, frame: int = 0) -> np.ndarray:
+        idx = np.empty(self.max_det, np.int32)
+        n = C.c_int(0)
+        L.check(self._lib.irmv_engine_read_kept_indices(self._h, frame, idx.ctypes.data, self.max_det, C.byref(n)),
+                "read_kept_indices")
+        return idx[: n.value].copy()
+
+    def _to_list(self, frame: int, k: int) -> List[bbox]:
+        out = []
+        base = frame * self.max_det
+        for i in range(k):
+            b = self._out[base + i]
+            out.append(bbox(tuple(b.xyxy), float(b.score), ArmorClass(int(b.class_id))))
+        return out
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.irmv_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class PnPSolver:
+    """PnPSolver(camera_matrix[9], dist_coeffs[>=5]); solvePnP(points) -> (ok, rvec, tvec).
+
+    `points` stands for the reference's Armor: the four image points in the order
+    left_light.bottom, left_light.top, right_light.top, right_light.bottom
+    (/root/reference/src/pnp_solver.cpp:41-44).
+    """
+
+    def __init__(self, camera_matrix: Sequence[float], dist_coeffs: Sequence[float], device: int = 0):
+        self._lib = L.lib()
+        K = (C.c_double * 9)(*[float(v) for v in camera_matrix])
+        D = (C.c_double * 5)(*[float(v) for v in list(dist_coeffs)[:5]])
+        self._h = C.c_void_p()
+        L.check(self._lib.irmv_pnp_create(K, D, device, C.byref(self._h)), "irmv_pnp_create")
+
+    def solvePnP(self, points) -> Tuple[bool, np.ndarray, np.ndarray]:
+        pts = (C.c_float * 8)(*np.asarray(points, np.float32).reshape(8))
+        r = (C.c_double * 3)()
+        t = (C.c_double * 3)()
+        ok = C.c_int(0)
+        L.check(self._lib.irmv_pnp_solve(self._h, pts, r, t, C.byref(ok)), "irmv_pnp_solve")
+        return bool(ok.value), np.array(r[:]).reshape(3, 1), np.array(t[:]).reshape(3, 1)
+
+    def solve_batch(self, points: np.ndarray, large_armor: bool = False, extended: bool = False):
+        pts = np.ascontiguousarray(points, np.float32).reshape(-1, 8)
+        n = pts.shape[0]
+        rv = np.empty((n, 3)); tv = np.empty((n, 3)); ok = np.empty(n, np.uint8)
+        if not extended:
+            L.check(self._lib.irmv_pnp_solve_batch(self._h, pts.ctypes.data, n, 0, int(large_armor),
+                                                   rv.ctypes.data, tv.ctypes.data, ok.ctypes.data), "irmv_pnp_solve_batch")
+            return rv, tv, ok.astype(bool)
+        q = np.empty((n, 4)); rv2 = np.empty((n, 3)); tv2 = np.empty((n, 3)); e = np.empty((n, 2))
+        L.check(self._lib.irmv_pnp_solve_batch_ex(self._h, pts.ctypes.data, n, 0, int(large_armor), rv.ctypes.data,
+                                                  tv.ctypes.data, ok.ctypes.data, q.ctypes.data, rv2.ctypes.data,
+                                                  tv2.ctypes.data, e.ctypes.data), "irmv_pnp_solve_batch_ex")
+        return rv, tv, ok.astype(bool), q, rv2, tv2, e
+
+    def solve_batch_device(self, dev_ptr: int, n: int, rv: np.ndarray, tv: np.ndarray, ok: np.ndarray,
+                           large_armor: bool = False) -> float:
+        L.check(self._lib.irmv_pnp_solve_batch(self._h, C.c_void_p(dev_ptr), n, 1, int(large_armor),
+                                               rv.ctypes.data, tv.ctypes.data, ok.ctypes.data), "irmv_pnp_solve_batch")
+        return float(self._lib.irmv_pnp_last_device_ms(self._h))
+
+    def last_device_ms(self) -> float:
+        return float(self._lib.irmv_pnp_last_device_ms(self._h))
+
+    def calculateDistanceToCenter(self, image_point) -> float:
+        return float(self._lib.irmv_pnp_distance_to_center(self._h, float(image_point[0]), float(image_point[1])))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.irmv_pnp_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---- stage-level wrappers (parity tests) ------------------------------------------------------
+def preprocess(frames: np.ndarray, chan_order: int = L.CH_PASSTHROUGH, rotate180: bool = True,
+               quantize_u8: bool = True, want_rotated: bool = False, device: int = 0):
+    """frames u8 [n,H,W,3] or [n,H,W] -> FP16 [n,640,640,8] NHWC (+ rotated u8 [n,H,W,3])."""
+    frames = np.ascontiguousarray(frames, np.uint8)
+    n, H, W = frames.shape[:3]
+    out = np.empty((n, L.NET, L.NET, 8), np.float16)
+    rot = np.empty((n, H, W, 3), np.uint8) if want_rotated else None
+    L.check(L.lib().irmv_preprocess(frames.ctypes.data, n, W, H, chan_order, int(rotate180), L.RESIZE_STRETCH,
+                                    int(quantize_u8), out.ctypes.data, rot.ctypes.data if want_rotated else None,
+                                    device), "irmv_preprocess")
+    return (out, rot) if want_rotated else out
+
+
+def nms(boxes: np.ndarray, scores: np.ndarray, score_thr: float = 0.25, iou_thr: float = 0.45,
+        max_det: int = 100, device: int = 0):
+    """boxes f32 [n,A,4], scores f32 [n,A,nc] -> per frame (index, boxes, scores, classes)."""
+    boxes = np.ascontiguousarray(boxes, np.float32)
+    scores = np.ascontiguousarray(scores, np.float32)
+    n, A, nc = scores.shape
+    num = np.zeros(n, np.int32)
+    db = np.zeros((n, max_det, 4), np.float32); ds = np.zeros((n, max_det), np.float32)
+    dc = np.zeros((n, max_det), np.int32); di = np.zeros((n, max_det), np.int32)
+    L.check(L.lib().irmv_nms(boxes.ctypes.data, scores.ctypes.data, n, A, nc, score_thr, iou_thr, max_det,
+                             num.ctypes.data, db.ctypes.data, ds.ctypes.data, dc.ctypes.data, di.ctypes.data, device),
+            "irmv_nms")
+    return [(di[f, :num[f]].copy(), db[f, :num[f]].copy(), ds[f, :num[f]].copy(), dc[f, :num[f]].copy())
+            for f in range(n)]
+
+
+def decode(box: np.ndarray, cls: np.ndarray, device: int = 0):
+    """box f16 [n,8400,64], cls f16 [n,8400,16] -> boxes f32 [n,8400,4], scores f32 [n,8400,14]."""
+    box = np.ascontiguousarray(box, np.float16)
+    cls = np.ascontiguousarray(cls, np.float16)
+    n = box.shape[0]
+    boxes = np.empty((n, L.NUM_ANCHORS, 4), np.float32)
+    scores = np.empty((n, L.NUM_ANCHORS, L.NUM_CLASSES), np.float32)
+    L.check(L.lib().irmv_decode(box.ctypes.data, cls.ctypes.data, n, boxes.ctypes.data, scores.ctypes.data, device),
+            "irmv_decode")
+    return boxes, scores
