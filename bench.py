@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s of the per-frame armor pipeline (preprocess -> YOLOv8n -> decode+NMS -> PnP).
+
+Contract: `python bench.py --gpus N --steps K --warmup W` (N>1 under torch.distributed.run, one rank
+per GPU).  One step = one pass of the hot path over one batch of synthetic frames per GPU.
+Workload = BASELINE.json configs[3]: 1280x1024 8-bit Bayer camera frames, batch 256 per GPU, full
+preprocess + YOLOv8n (nc=14, seeded random-init FP16) + decode/NMS + PnP; frames are independent,
+so ranks share nothing (weak scaling, no data-path collective).  Rank 0 prints ONE JSON line.
+
+`--impl reference` times the reference path's CPU form (cv2 flip/resize, OpenCV-DNN on the ONNX
+export of the same weights, numpy NMS, cv2.solvePnP) on the box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "frames/s (640^2 YOLOv8n+NMS+PnP)"
+SRC_W, SRC_H = 1280, 1024
+FLOPS_PER_FRAME = 8.0956416e9          # SURVEY.md section 8d, 63 convs
+K_CAM = [957.669211, 0.0, 345.943891, 0.0, 969.127115, 284.057302, 0.0, 0.0, 1.0]
+D_CAM = [-0.405274, 0.126058, -0.026939, -0.006503, 0.0]
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------- inputs
+def make_bayer_frames_device(n: int, seed: int, device):
+    """n synthetic RGGB frames on the device (torch used as plumbing): rm_test.jpg with per-frame
+    circular shift, gain and sensor noise (irmv_detection_b200.synth, vectorised)."""
+    import torch
+    from irmv_detection_b200 import synth
+    base = torch.from_numpy(synth.load_base()[..., ::-1].copy()).to(device)        # RGB u8 [H,W,3]
+    g = torch.Generator(device=device)
+    g.manual_seed(1234 + seed)
+    out = torch.empty((n, SRC_H, SRC_W), dtype=torch.uint8, device=device)
+    yy = (torch.arange(SRC_H, device=device) & 1)[:, None]
+    xx = (torch.arange(SRC_W, device=device) & 1)[None, :]
+    chan = torch.where((yy == 0) & (xx == 0), 0, torch.where((yy == 1) & (xx == 1), 2, 1))      # RGGB
+    rng = np.random.default_rng(seed)
+    for i in range(n):
+        dx, dy = rng.integers(-96, 97, 2)
+        gain = float(rng.uniform(0.9, 1.2))
+        f = torch.roll(base, (int(dy), int(dx)), (0, 1)).float() * gain
+        f = f + torch.randn(f.shape, generator=g, device=device) * 3.0
+        f = f.round().clamp_(0, 255).to(torch.uint8)
+        out[i] = torch.gather(f, 2, chan[..., None]).squeeze(2)
+    return out
+
+
+def weights_file(seed: int = 0) -> str:
+    from irmv_detection_b200 import weights
+    path = f"/tmp/irmv_bench_seed{seed}_{os.getpid()}.irmw"
+    weights.write_random(path, seed)
+    return path
+
+
+# ---------------------------------------------------------------------------------- CPU reference
+class CpuReference:
+    """The reference path's CPU form, through the oracle modules."""
+
+    def __init__(self, wpath: str, threads: int):
+        import cv2
+        import torch
+        from oracle import export_onnx, yolov8n_ref as Y
+        cv2.setNumThreads(threads)
+        torch.set_num_threads(threads)
+        self.threads = threads
+        self.model = Y.build(wpath)
+        self.kind_net = "torch-cpu"
+        self.net = None
+        try:
+            onnx_path = wpath.replace(".irmw", ".onnx")
+            export_onnx.export(self.model, onnx_path)
+            self.net = cv2.dnn.readNetFromONNX(onnx_path)
+            self.kind_net = "opencv-dnn"
+        except Exception:
+            self.net = None
+
+    def frame(self, bayer: np.ndarray):
+        import cv2
+        import torch
+        from oracle import nms_ref as N, pnp_ref as P
+        rgb = cv2.cvtColor(bayer, cv2.COLOR_BayerRGGB2RGB)              # camera ISP step (mv_camera.cpp:96)
+        img = cv2.flip(rgb, -1)
+        r = cv2.resize(img, (640, 640), interpolation=cv2.INTER_LINEAR)
+        x = np.ascontiguousarray((r.astype(np.float32) / 255.0).transpose(2, 0, 1))[None]
+        if self.net is not None:
+            self.net.setInput(x)
+            out = self.net.forward()[0]
+            boxes, scores = out[:, :4], out[:, 4:]
+        else:
+            with torch.no_grad():
+                b, s = self.model(torch.from_numpy(x))
+            boxes, scores = b[0].numpy(), s[0].numpy()
+        # class-aware NMS in C++ (cv2.dnn.NMSBoxesBatched == the oracle's rule, tests/test_oracle_cpu.py)
+        a, c = np.nonzero(scores > N.SCORE_THR)
+        if a.size:
+            sc = scores[a, c]
+            top = np.argsort(-sc, kind="stable")[:N.MAX_CAND]
+            a, c, sc = a[top], c[top], sc[top]
+            bb = boxes[a]
+            xywh = np.concatenate((bb[:, :2], bb[:, 2:] - bb[:, :2]), 1)
+            sel = np.asarray(cv2.dnn.NMSBoxesBatched(xywh.tolist(), sc.tolist(), c.tolist(), N.SCORE_THR, N.IOU_THR)).ravel()
+            sel = sel[np.argsort(-sc[sel], kind="stable")][:N.MAX_DET]
+            kb, ks, kc = bb[sel], sc[sel], c[sel]
+        else:
+            kb, ks, kc = np.zeros((0, 4), np.float32), np.zeros(0, np.float32), np.zeros(0, np.int32)
+        ob, _, _ = N.parse_output(kb, ks, kc, SRC_W, SRC_H)
+        n = 0
+        if len(ob):
+            sx, sy = 640.0 / SRC_W, 480.0 / SRC_H
+            pts = np.stack([np.stack([ob[:, 0] * sx, ob[:, 3] * sy], 1), np.stack([ob[:, 0] * sx, ob[:, 1] * sy], 1),
+                            np.stack([ob[:, 2] * sx, ob[:, 1] * sy], 1), np.stack([ob[:, 2] * sx, ob[:, 3] * sy], 1)], 1)
+            P.solve_cv2(pts.astype(np.float32))
+            n = len(ob)
+        return n
+
+    def run(self, frames: np.ndarray, budget_s: float, min_frames: int = 4):
+        self.frame(frames[0])                      # warm-up
+        t0 = time.perf_counter()
+        n = 0
+        while n < len(frames) and (n < min_frames or time.perf_counter() - t0 < budget_s):
+            self.frame(frames[n])
+            n += 1
+        dt = time.perf_counter() - t0
+        return n / dt, n, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from irmv_detection_b200 import synth
+    threads = os.cpu_count() or 1
+    wpath = weights_file(0)
+    ref = CpuReference(wpath, threads)
+    base = synth.load_base()
+    per_step = args.ref_frames
+    frames = synth.bayer_from_rgb(synth.frames_from_base(base, per_step, seed=0)[..., ::-1], "RGGB")
+    for _ in range(max(args.warmup, 1)):
+        ref.frame(frames[0])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for f in frames:
+            ref.frame(f)
+    dt = time.perf_counter() - t0
+    fps = args.steps * per_step / dt
+    sample = (f"{per_step} frames/step x {args.steps} steps of the same 1280x1024 Bayer workload; "
+              f"cv2 demosaic+flip+resize, {ref.kind_net} YOLOv8n FP32, numpy NMS, cv2.solvePnP(IPPE)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "1280x1024 Bayer frames, full preprocess+YOLOv8n+NMS+PnP (BASELINE.json configs[3])",
+                   "frames_per_step": per_step, "note": "reference CPU path on host cores; TensorRT unavailable offline"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------- ours
+def run_ours(args):
+    import torch
+    import irmv_detection_b200 as irmv
+    from irmv_detection_b200 import sharding
+    rank, world, local_rank = sharding.env_rank_world()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback exists for the product path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        sharding.init_process_group("nccl")
+    B = args.batch
+    wpath = weights_file(0)
+    frames_dev = make_bayer_frames_device(B, seed=rank, device=dev)
+    torch.cuda.synchronize()
+    eng = irmv.YoloEngine(wpath, (SRC_W, SRC_H), chan_order=irmv.CH_BAYER_RGGB, max_batch=B,
+                          sub_batch=args.sub_batch, num_lanes=args.lanes, device=local_rank)
+    eng.enable_pnp(K_CAM, D_CAM, (640.0 / SRC_W, 480.0 / SRC_H))
+    ptr = frames_dev.data_ptr()
+
+    # ---- device-resident throughput (`value`) ------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()                               # nvidia-smi needs ~0.3 s to come up: start before warm-up
+    t_w = time.perf_counter()
+    n_warm = 0
+    while n_warm < max(args.warmup, 3) or time.perf_counter() - t_w < 1.0:
+        eng.enqueue_batch_device(ptr, B)
+        eng.sync()
+        n_warm += 1
+    if world > 1:
+        torch.distributed.barrier(device_ids=[local_rank])
+    torch.cuda.synchronize()
+    dev_ms = 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.enqueue_batch_device(ptr, B)
+        dev_ms += eng.sync()                      # CUDA events on the engine's own streams
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop()
+    dets = eng.fetch(B)
+    n_dets = sum(len(d) for d in dets)
+    if world > 1:
+        torch.distributed.barrier(device_ids=[local_rank])
+    step_ms_local = dev_ms / args.steps
+    step_ms, frames_per_step = sharding.reduce_max_sum(step_ms_local, float(B), device=str(dev))
+    value = frames_per_step / (step_ms * 1e-3)
+
+    # ---- end to end through the public API with host buffers (`e2e`) ---------------------------
+    host = torch.empty((B, SRC_H, SRC_W), dtype=torch.uint8, pin_memory=True)
+    host.copy_(frames_dev)
+    torch.cuda.synchronize()
+    host_np = host.numpy()
+    eng.detect_batch(host_np)
+    if world > 1:
+        torch.distributed.barrier(device_ids=[local_rank])
+    e2e_steps = max(2, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.detect_batch(host_np)                 # H2D + pipeline + D2H of results + parse
+        eng.fetch_poses(B)
+    e2e_ms_local = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    e2e_ms, _ = sharding.reduce_max_sum(e2e_ms_local, 0.0, device=str(dev))
+    e2e_value = frames_per_step / (e2e_ms * 1e-3)
+    h2d = B * SRC_W * SRC_H
+    d2h = B * 4 + B * eng.max_det * (16 + 4 + 4 + 4 + 24 + 24 + 1)
+
+    if rank != 0:
+        eng.close()
+        return
+
+    # ---- roofline of the dominant kernel (the tcgen05 convolution) ---------------------------
+    peaks, peak_kind = measured_peaks()
+    k, st = None, None
+    conv_ms = []
+    for _ in range(5):
+        k, st = eng.profile_stages(ptr, B)
+        conv_ms.append(st["conv"])
+    conv_t = statistics.median(conv_ms) * 1e-3
+    n_conv = 60
+    achieved = FLOPS_PER_FRAME * k / conv_t / 1e12
+    peak = float(peaks.get("bf16_tflops", 1590.0))
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "conv_tc_kernel (60 launches per replay, timed as a group)",
+                "frames_per_replay": k, "peak_source": f"{peak_kind} bf16_tflops (burst: stage timed alone)",
+                "stage_ms": st,
+                "hbm_frac_preprocess": (3768320.0 * k / (st["preprocess"] * 1e-3) / 1e9) / float(peaks.get("hbm_gbs", 6650.0))
+                if st["preprocess"] > 0 else None}
+
+    # ---- batch-1 latency (BASELINE.json metric's second half) ----------------------------------
+    lat = None
+    try:
+        e1 = irmv.YoloEngine(wpath, (SRC_W, SRC_H), chan_order=irmv.CH_BAYER_RGGB, max_batch=1, device=local_rank)
+        e1.enable_pnp(K_CAM, D_CAM, (640.0 / SRC_W, 480.0 / SRC_H))
+        e1.get_src_image_buffer(0)[...] = host_np[0]
+        for _ in range(20):
+            e1.detect(0)
+        wall, devt = [], []
+        for _ in range(200):
+            t0 = time.perf_counter()
+            e1.detect(0)
+            wall.append((time.perf_counter() - t0) * 1e6)
+            devt.append(e1.last_device_ms() * 1e3)
+        lat = {"p50_us_e2e_host_frame": statistics.median(wall), "p99_us_e2e_host_frame": sorted(wall)[197],
+               "p50_us_device_graph": statistics.median(devt), "iters": 200,
+               "note": "detect(): H2D of one 1.31 MB Bayer frame + CUDA graph + D2H + parse, single stream"}
+        e1.close()
+    except Exception as ex:                              # latency is a secondary key; never lose the line
+        lat = {"error": str(ex)}
+
+    # ---- CPU baseline on a bounded sample (rank 0, N=1 only) ------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            threads = os.cpu_count() or 1
+            ref = CpuReference(wpath, threads)
+            fps, n, dt = ref.run(host_np[:64], budget_s=args.cpu_budget)
+            cpu = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                   "sample": f"{n} of the step's 256 Bayer frames in {dt:.1f} s; cv2 demosaic+flip+resize, "
+                             f"{ref.kind_net} YOLOv8n FP32, numpy NMS, cv2.solvePnP(IPPE)"}
+        except Exception as ex:
+            cpu = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": n_warm, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": {"workload": "1280x1024 8-bit Bayer RGGB frames, batch 256/GPU, fused demosaic+rot180+resize -> "
+                               "YOLOv8n nc=14 (seeded random-init, FP16 tcgen05) -> decode+NMS -> PnP "
+                               "(BASELINE.json configs[3])",
+                   "frames_per_gpu_per_step": B, "sub_batch": eng._cfg.sub_batch or min(B, 8), "lanes": args.lanes,
+                   "l2": "inputs larger than L2 (335 MB of frames per step per GPU, activations cycled per replay)",
+                   "timing": "CUDA events on the engine's streams, summed over steps, max over ranks",
+                   "detections_per_step": n_dets, "wall_ms_per_step": wall_ms / args.steps},
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms, "note": "detect_batch() on pinned host frames: H2D + pipeline + D2H + parse"},
+        "gpu_launches": eng.kernel_launches(B) * args.steps,
+        "clocks": clocks, "roofline": roofline, "latency_batch1": lat,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    eng.close()
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--sub-batch", type=int, default=0)
+    ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--ref-frames", type=int, default=8, help="frames per step of the reference arm")
+    ap.add_argument("--cpu-budget", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -46,7 +46,10 @@ enum {
   IRMV_CH_BAYER_GBRG = 5
 };
 
-enum { IRMV_RESIZE_STRETCH = 0 /* reference */, IRMV_RESIZE_LETTERBOX = 1 };
+/* STRETCH = the reference: independent x/y scale, NPP's measured corner-aligned bilinear map
+ * (src = dst * src_size/640, no half-pixel offset; pinned in tests/golden/npp_rm_golden.npz).
+ * STRETCH_HALF_PIXEL = same stretch with OpenCV-style pixel centres.  LETTERBOX: not built yet. */
+enum { IRMV_RESIZE_STRETCH = 0, IRMV_RESIZE_LETTERBOX = 1, IRMV_RESIZE_STRETCH_HALF_PIXEL = 2 };
 enum { IRMV_CONV_TCGEN05 = 0, IRMV_CONV_DIRECT = 1 /* CUDA-core bring-up kernel */ };
 
 /* Same layout as YoloEngine::bbox (include/irmv_detection/yolo_engine.hpp:19-26): 24 bytes. */
@@ -107,6 +110,18 @@ double irmv_engine_profile_ms(irmv_engine *e);
 double irmv_engine_last_device_ms(irmv_engine *e);
 int irmv_engine_kernel_launches(irmv_engine *e, int nframes);
 void *irmv_engine_stream(irmv_engine *e);
+
+/* Fuse the pose stage into the replay: after NMS, the four corners of every kept box (scaled by
+ * corner_sx/sy from source pixels to the calibration frame) go through the IPPE kernel on the
+ * device; poses come back with the detections.  Replaces the per-armor host loop of
+ * IrmDetector::message_callback (src/irm_detector.cpp:204-208). */
+int irmv_engine_enable_pnp(irmv_engine *e, const double K[9], const double D[5], float corner_sx,
+                           float corner_sy);
+/* rvecs/tvecs: nframes*max_det*3 doubles; slot i of frame f is valid when i < counts[f]. */
+int irmv_engine_fetch_poses(irmv_engine *e, int nframes, double *rvecs, double *tvecs, uint8_t *ok);
+/* One eager replay of min(nframes, sub_batch) device-resident frames with CUDA events between
+ * stages: ms = {preprocess, convolutions, decode+NMS, PnP, total}.  Returns frames profiled. */
+int irmv_engine_profile_stages(irmv_engine *e, const uint8_t *frames_dev, int nframes, float ms[5]);
 
 /* Parity taps: raw activations of the last run.  name: "input" (preprocessed, NHWC8 FP16),
  * "box0".."box2" (NHWC64), "cls0".."cls2" (NHWC16), "boxes" (f32 [A,4]), or a module tap

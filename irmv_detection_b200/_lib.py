@@ -14,7 +14,7 @@ CLASS_UNKNOWN = 14
 NUM_ANCHORS = 8400
 
 CH_PASSTHROUGH, CH_SWAP_RB, CH_BAYER_RGGB, CH_BAYER_BGGR, CH_BAYER_GRBG, CH_BAYER_GBRG = range(6)
-RESIZE_STRETCH, RESIZE_LETTERBOX = 0, 1
+RESIZE_STRETCH, RESIZE_LETTERBOX, RESIZE_STRETCH_HALF_PIXEL = 0, 1, 2
 CONV_TCGEN05, CONV_DIRECT = 0, 1
 
 
@@ -52,6 +52,9 @@ SYMBOLS = {
     "irmv_engine_last_device_ms": (C.c_double, [_P]),
     "irmv_engine_kernel_launches": (C.c_int, [_P, C.c_int]),
     "irmv_engine_stream": (_P, [_P]),
+    "irmv_engine_enable_pnp": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_float, C.c_float]),
+    "irmv_engine_fetch_poses": (C.c_int, [_P, C.c_int, _P, _P, _P]),
+    "irmv_engine_profile_stages": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_float * 5)]),
     "irmv_engine_read_tensor": (C.c_int, [_P, C.c_char_p, _P, C.c_int64, C.POINTER(C.c_int32 * 5)]),
     "irmv_engine_read_kept_indices": (C.c_int, [_P, C.c_int, _P, C.c_int, C.POINTER(C.c_int)]),
     "irmv_preprocess": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int]),

@@ -185,9 +185,29 @@ struct Lane {
   uint8_t *rotated = nullptr;
   std::map<int, cudaGraphExec_t> graphs;   // keyed by frames in the replay
   int launches_per_replay = 0;
+  float *pnp_pts = nullptr;                // [S*max_det][8]
+  double *pnp_rvec = nullptr, *pnp_tvec = nullptr;
+  uint8_t *pnp_ok = nullptr;
+  cudaEvent_t stage_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 __global__ void set_src_kernel(const uint8_t **word, const uint8_t *ptr) { *word = ptr; }
+
+// Detections -> PnP corner quads {LB, LT, RT, RB} (reference order, src/pnp_solver.cpp:41-44).
+// Until the light-bar extractor (reference src/irm_detector.cpp:292-355) is on the GPU the four
+// corners are the box corners, scaled from network pixels to the calibration frame.
+__global__ void quads_from_dets_kernel(const int32_t *num, const float *boxes, int n, int max_det,
+                                       float sx, float sy, float *pts) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * max_det) return;
+  int f = i / max_det, k = i - f * max_det;
+  float4 b = make_float4(150.f, 140.f, 200.f, 160.f);     // inactive slots: a fixed valid quad
+  if (k < num[f]) b = reinterpret_cast<const float4 *>(boxes)[i];
+  float x1 = b.x * sx, y1 = b.y * sy, x2 = b.z * sx, y2 = b.w * sy;
+  float4 *o = reinterpret_cast<float4 *>(pts + (size_t)i * 8);
+  o[0] = make_float4(x1, y2, x1, y1);
+  o[1] = make_float4(x2, y1, x2, y2);
+}
 
 }  // namespace
 }  // namespace irmv
@@ -210,6 +230,9 @@ struct irmv_engine {
   uint8_t *res_host = nullptr;            // pinned results: max_batch frames
   size_t res_frame_stride = 0;
   double profile_ms = 0.0, device_ms = 0.0;
+  bool pnp_on = false;
+  PnpConsts pnp_c{};
+  float pnp_sx = 1.f, pnp_sy = 1.f;
   int last_slot = -1;
   int last_n = 0;
 };
@@ -345,20 +368,34 @@ bool build_lane(irmv_engine *e, Lane &ln) {
   ln.det.init(S, e->cfg.max_det);
   if (!lane_alloc(ln, (void **)&ln.det.dev, ln.det.bytes)) return false;
   if (!lane_alloc(ln, (void **)&ln.src_word, sizeof(void *))) return false;
+  const size_t slots = (size_t)S * e->cfg.max_det;
+  if (!lane_alloc(ln, (void **)&ln.pnp_pts, slots * 32) || !lane_alloc(ln, (void **)&ln.pnp_rvec, slots * 24) ||
+      !lane_alloc(ln, (void **)&ln.pnp_tvec, slots * 24) || !lane_alloc(ln, (void **)&ln.pnp_ok, slots))
+    return false;
+  for (auto &ev : ln.stage_ev)
+    if (!cuda_ok(cudaEventCreate(&ev), "cudaEventCreate", __FILE__, __LINE__)) return false;
   Tensor bt; bt.p = reinterpret_cast<__half *>(ln.nms.boxes); bt.H = 1; bt.W = kNumAnchors; bt.C = 4;
   ln.taps["boxes"] = bt;
   return true;
 }
 
-// Enqueue one replay (n frames) of the whole pipeline on the lane stream.
-int issue_replay(irmv_engine *e, Lane &ln, int n, cudaStream_t st, int *launches) {
+// Enqueue one replay (n frames) of the whole pipeline on the lane stream.  With `stage_events`
+// the lane's events are recorded between stages (profiling pass, never inside a graph).
+int issue_replay(irmv_engine *e, Lane &ln, int n, cudaStream_t st, int *launches,
+                 bool stage_events = false) {
   int cnt = 0;
+  auto mark = [&](int i) -> int {
+    if (stage_events) IRMV_CUDA(cudaEventRecord(ln.stage_ev[i], st));
+    return 0;
+  };
+  if (mark(0)) return 1;
   PreprocessParams pp{};
   pp.src = nullptr; pp.src_indirect = ln.src_word; pp.dst = ln.in8.p; pp.rotated = ln.rotated;
   pp.n = n; pp.src_w = e->cfg.src_width; pp.src_h = e->cfg.src_height;
   pp.chan_order = e->cfg.chan_order; pp.rotate180 = e->cfg.rotate180;
   pp.resize_mode = e->cfg.resize_mode; pp.quantize_u8 = e->cfg.quantize_u8;
   IRMV_CUDA(launch_preprocess(pp, st)); cnt += 1 + (ln.rotated ? 1 : 0);
+  if (mark(1)) return 1;
   for (auto &op : ln.ops) {
     if (op.kind == Op::CONV) {
       ConvParams p = op.cp;
@@ -370,9 +407,21 @@ int issue_replay(irmv_engine *e, Lane &ln, int n, cudaStream_t st, int *launches
     }
     ++cnt;
   }
+  if (mark(2)) return 1;
   IRMV_CUDA(launch_decode(ln.heads, n, e->nc, e->cfg.score_thr, ln.nms, nullptr, st)); ++cnt;
   DetOut out{ln.det.num(), ln.det.boxes(), ln.det.scores(), ln.det.classes(), ln.det.index()};
   IRMV_CUDA(launch_nms(ln.nms, n, kNumAnchors, e->nc, e->cfg.iou_thr, e->cfg.max_det, out, st)); ++cnt;
+  if (mark(3)) return 1;
+  if (e->pnp_on) {
+    const int total = n * e->cfg.max_det;
+    quads_from_dets_kernel<<<(total + 127) / 128, 128, 0, st>>>(ln.det.num(), ln.det.boxes(), n, e->cfg.max_det,
+                                                               e->pnp_sx, e->pnp_sy, ln.pnp_pts);
+    IRMV_CUDA(cudaGetLastError());
+    PnpOut po{ln.pnp_rvec, ln.pnp_tvec, ln.pnp_ok, nullptr, nullptr, nullptr, nullptr};
+    IRMV_CUDA(launch_pnp(e->pnp_c, ln.pnp_pts, total, 0, po, st));
+    cnt += 2;
+  }
+  if (mark(4)) return 1;
   if (launches) *launches = cnt;
   return 0;
 }
@@ -426,6 +475,14 @@ int enqueue(irmv_engine *e, const uint8_t *frames_dev, int n) {
     IRMV_CUDA(cudaMemcpyAsync(h + o + (size_t)f0 * md * 4, ln.det.classes(), (size_t)nf * md * 4, cudaMemcpyDeviceToHost, ln.stream));
     o += B * md * 4;
     IRMV_CUDA(cudaMemcpyAsync(h + o + (size_t)f0 * md * 4, ln.det.index(), (size_t)nf * md * 4, cudaMemcpyDeviceToHost, ln.stream));
+    o += B * md * 4;
+    if (e->pnp_on) {
+      IRMV_CUDA(cudaMemcpyAsync(h + o + (size_t)f0 * md * 24, ln.pnp_rvec, (size_t)nf * md * 24, cudaMemcpyDeviceToHost, ln.stream));
+      o += B * md * 24;
+      IRMV_CUDA(cudaMemcpyAsync(h + o + (size_t)f0 * md * 24, ln.pnp_tvec, (size_t)nf * md * 24, cudaMemcpyDeviceToHost, ln.stream));
+      o += B * md * 24;
+      IRMV_CUDA(cudaMemcpyAsync(h + o + (size_t)f0 * md, ln.pnp_ok, (size_t)nf * md, cudaMemcpyDeviceToHost, ln.stream));
+    }
   }
   for (int l = 0; l < used; ++l) {
     IRMV_CUDA(cudaEventRecord(e->lanes[l].done, e->lanes[l].stream));
@@ -481,7 +538,7 @@ int irmv_engine_config_default(irmv_engine_config *c) {
 
 int irmv_engine_create(const char *weights_path, const irmv_engine_config *cfg, irmv_engine **out) {
   if (!weights_path || !cfg || !out) { set_error("null argument"); return 1; }
-  if (cfg->resize_mode != IRMV_RESIZE_STRETCH) { set_error("resize_mode LETTERBOX is not built yet"); return 2; }
+  if (cfg->resize_mode == IRMV_RESIZE_LETTERBOX) { set_error("resize_mode LETTERBOX is not built yet"); return 2; }
   if (cfg->max_batch < 1 || cfg->src_width < 2 || cfg->src_height < 2 || cfg->max_det < 1 || cfg->max_det > 1024) {
     set_error("bad engine config"); return 2;
   }
@@ -544,7 +601,7 @@ int irmv_engine_create(const char *weights_path, const irmv_engine_config *cfg, 
   }
   IRMV_CUDA(cudaMalloc((void **)&e->slot_dev, e->frame_bytes));
   const size_t md = cfg->max_det, B = cfg->max_batch;
-  size_t res_bytes = B * 4 + B * md * (16 + 4 + 4 + 4);
+  size_t res_bytes = B * 4 + B * md * (16 + 4 + 4 + 4) + B * md * (24 + 24 + 1) + 64;
   IRMV_CUDA(cudaHostAlloc((void **)&e->res_host, res_bytes, cudaHostAllocDefault));
   memset(e->res_host, 0, res_bytes);
   IRMV_CUDA(cudaDeviceSynchronize());
@@ -562,6 +619,7 @@ void irmv_engine_destroy(irmv_engine *e) {
     if (ln.rotated) cudaFree(ln.rotated);
     if (ln.stream) cudaStreamDestroy(ln.stream);
     if (ln.done) cudaEventDestroy(ln.done);
+    for (auto ev : ln.stage_ev) if (ev) cudaEventDestroy(ev);
   }
   for (auto &c : e->convs) {
     cudaFree(c->d_plain); cudaFree(c->d_tiled); cudaFree(c->d_bias); cudaFree(c->d_ktab);
@@ -702,11 +760,59 @@ int irmv_engine_read_kept_indices(irmv_engine *e, int frame, int32_t *idx, int c
   return 0;
 }
 
+int irmv_engine_enable_pnp(irmv_engine *e, const double K[9], const double D[5], float corner_sx, float corner_sy) {
+  if (!e || !K || !D) { set_error("bad argument"); return 1; }
+  e->pnp_c.fx = K[0]; e->pnp_c.cx = K[2]; e->pnp_c.fy = K[4]; e->pnp_c.cy = K[5];
+  e->pnp_c.k1 = D[0]; e->pnp_c.k2 = D[1]; e->pnp_c.p1 = D[2]; e->pnp_c.p2 = D[3]; e->pnp_c.k3 = D[4];
+  e->pnp_c.half_w[0] = 135.0 / 2.0 / 1000.0; e->pnp_c.half_h[0] = 55.0 / 2.0 / 1000.0;
+  e->pnp_c.half_w[1] = 225.0 / 2.0 / 1000.0; e->pnp_c.half_h[1] = 55.0 / 2.0 / 1000.0;
+  // boxes are in network pixels: first to the source frame (parse_output's scale), then to the calibration frame
+  e->pnp_sx = corner_sx * (float)e->cfg.src_width / 640.f;
+  e->pnp_sy = corner_sy * (float)e->cfg.src_height / 640.f;
+  e->pnp_on = true;
+  IRMV_CUDA(cudaSetDevice(e->cfg.device));
+  IRMV_CUDA(cudaDeviceSynchronize());
+  for (auto &ln : e->lanes) {             // the pipeline changed: drop captured graphs
+    for (auto &g : ln.graphs) cudaGraphExecDestroy(g.second);
+    ln.graphs.clear();
+  }
+  return 0;
+}
+
+int irmv_engine_fetch_poses(irmv_engine *e, int nframes, double *rvecs, double *tvecs, uint8_t *ok) {
+  if (!e || !rvecs || !tvecs || nframes < 1 || nframes > e->cfg.max_batch) { set_error("bad argument"); return 1; }
+  if (!e->pnp_on) { set_error("PnP stage not enabled"); return 2; }
+  const size_t md = e->cfg.max_det, B = e->cfg.max_batch;
+  const uint8_t *h = e->res_host + B * 4 + B * md * 28;
+  memcpy(rvecs, h, (size_t)nframes * md * 24);
+  memcpy(tvecs, h + B * md * 24, (size_t)nframes * md * 24);
+  if (ok) memcpy(ok, h + B * md * 48, (size_t)nframes * md);
+  return 0;
+}
+
+// One eager (non-graph) replay of up to sub_batch frames on lane 0 with CUDA events between the
+// stages: ms[0] preprocess, ms[1] convolutions (+SPPF pool), ms[2] decode+NMS, ms[3] PnP, ms[4] total.
+int irmv_engine_profile_stages(irmv_engine *e, const uint8_t *frames_dev, int nframes, float ms[5]) {
+  if (!e || !frames_dev || !ms || nframes < 1) { set_error("bad argument"); return 1; }
+  IRMV_CUDA(cudaSetDevice(e->cfg.device));
+  Lane &ln = e->lanes[0];
+  const int n = nframes < e->S ? nframes : e->S;
+  IRMV_CUDA(cudaDeviceSynchronize());
+  set_src_kernel<<<1, 1, 0, ln.stream>>>(ln.src_word, frames_dev);
+  IRMV_CUDA(cudaGetLastError());
+  int launches = 0;
+  if (int rc = issue_replay(e, ln, n, ln.stream, &launches, true)) return rc;
+  IRMV_CUDA(cudaStreamSynchronize(ln.stream));
+  for (int i = 0; i < 4; ++i) IRMV_CUDA(cudaEventElapsedTime(&ms[i], ln.stage_ev[i], ln.stage_ev[i + 1]));
+  IRMV_CUDA(cudaEventElapsedTime(&ms[4], ln.stage_ev[0], ln.stage_ev[4]));
+  return n;
+}
+
 // ------------------------------------------------------------------ stage entry points
 int irmv_preprocess(const uint8_t *src, int n, int src_w, int src_h, int chan_order, int rotate180,
                     int resize_mode, int quantize_u8, uint16_t *dst, uint8_t *rotated, int device) {
   if (!src || !dst || n < 1) { set_error("bad argument"); return 1; }
-  if (resize_mode != IRMV_RESIZE_STRETCH) { set_error("resize_mode LETTERBOX is not built yet"); return 2; }
+  if (resize_mode == IRMV_RESIZE_LETTERBOX) { set_error("resize_mode LETTERBOX is not built yet"); return 2; }
   IRMV_CUDA(cudaSetDevice(device));
   const size_t fb = (size_t)src_w * src_h * (chan_order >= 2 ? 1 : 3);
   const size_t ob = (size_t)kNet * kNet * kInC * 2;

@@ -17,8 +17,11 @@ constexpr int NT = 256;
 
 struct Taps { int i0, i1; float f; };
 
-__device__ __forceinline__ Taps axis_taps(int d, float scale, int n_src) {
-  float s = __fsub_rn(__fmul_rn(__fadd_rn((float)d, 0.5f), scale), 0.5f);
+// half_pixel = 0: NPP's measured convention (corner-aligned, src = dst * scale), reference-exact;
+// half_pixel = 1: OpenCV-style pixel centres.
+__device__ __forceinline__ Taps axis_taps(int d, float scale, int n_src, int half_pixel) {
+  float s = half_pixel ? __fsub_rn(__fmul_rn(__fadd_rn((float)d, 0.5f), scale), 0.5f)
+                       : __fmul_rn((float)d, scale);
   float fl = floorf(s);
   Taps t;
   t.f = __fsub_rn(s, fl);
@@ -101,10 +104,11 @@ preprocess_kernel(PreprocessParams p, int rows_cap, int pitch_s) {
   const uint8_t *frame = base + (size_t)n * frame_bytes;
   const float scale_x = __fdiv_rn((float)W, (float)kNet);
   const float scale_y = __fdiv_rn((float)H, (float)kNet);
+  const int hp = (p.resize_mode == 2);
 
   // window of rotated-space taps needed by this tile
-  Taps ty0 = axis_taps(oy0, scale_y, H), ty1 = axis_taps(min(oy0 + TH, kNet) - 1, scale_y, H);
-  Taps tx0 = axis_taps(ox0, scale_x, W), tx1 = axis_taps(min(ox0 + TW, kNet) - 1, scale_x, W);
+  Taps ty0 = axis_taps(oy0, scale_y, H, hp), ty1 = axis_taps(min(oy0 + TH, kNet) - 1, scale_y, H, hp);
+  Taps tx0 = axis_taps(ox0, scale_x, W, hp), tx1 = axis_taps(min(ox0 + TW, kNet) - 1, scale_x, W, hp);
   int ry_lo = ty0.i0, ry_hi = ty1.i1, rx_lo = tx0.i0, rx_hi = tx1.i1;
   int sy_lo = p.rotate180 ? H - 1 - ry_hi : ry_lo, sy_hi = p.rotate180 ? H - 1 - ry_lo : ry_hi;
   int sx_lo = p.rotate180 ? W - 1 - rx_hi : rx_lo, sx_hi = p.rotate180 ? W - 1 - rx_lo : rx_hi;
@@ -140,7 +144,7 @@ preprocess_kernel(PreprocessParams p, int rows_cap, int pitch_s) {
   for (int q = threadIdx.x; q < TH * TW; q += NT) {
     int oy = oy0 + q / TW, ox = ox0 + q % TW;
     if (oy >= kNet || ox >= kNet) continue;
-    Taps ty = axis_taps(oy, scale_y, H), tx = axis_taps(ox, scale_x, W);
+    Taps ty = axis_taps(oy, scale_y, H, hp), tx = axis_taps(ox, scale_x, W, hp);
     int ys[2] = {ty.i0, ty.i1}, xs[2] = {tx.i0, tx.i1};
     float pix[2][2][3];
 #pragma unroll

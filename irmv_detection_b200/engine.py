@@ -48,7 +48,7 @@ class YoloEngine:
 
     def __init__(self, onnx_file_path: str, src_image_size: Tuple[int, int] = (1280, 1024),
                  enable_profiling: bool = False, *, chan_order: int = L.CH_PASSTHROUGH,
-                 rotate180: bool = True, quantize_u8: bool = True, max_batch: int = 1,
+                 rotate180: bool = True, quantize_u8: bool = True, half_pixel: bool = False, max_batch: int = 1,
                  sub_batch: int = 0, num_lanes: int = 0, num_slots: int = 3, device: int = 0,
                  conv_impl: int = L.CONV_TCGEN05, score_thr: float = 0.25, iou_thr: float = 0.45,
                  max_det: int = 100, use_graph: bool = True):
@@ -64,6 +64,7 @@ class YoloEngine:
         cfg.chan_order = chan_order
         cfg.rotate180 = int(rotate180)
         cfg.quantize_u8 = int(quantize_u8)
+        cfg.resize_mode = L.RESIZE_STRETCH_HALF_PIXEL if half_pixel else L.RESIZE_STRETCH
         cfg.max_batch, cfg.sub_batch, cfg.num_lanes, cfg.num_slots = max_batch, sub_batch, num_lanes, num_slots
         cfg.device, cfg.conv_impl = device, conv_impl
         cfg.score_thr, cfg.iou_thr, cfg.max_det = score_thr, iou_thr, max_det
@@ -138,6 +139,27 @@ class YoloEngine:
 
     def kernel_launches(self, n: int) -> int:
         return int(self._lib.irmv_engine_kernel_launches(self._h, n))
+
+    def enable_pnp(self, camera_matrix, dist_coeffs, corner_scale=(1.0, 1.0)) -> None:
+        """Fuse the pose stage (box corners -> IPPE) into every replay."""
+        K = (C.c_double * 9)(*[float(v) for v in camera_matrix])
+        D = (C.c_double * 5)(*[float(v) for v in list(dist_coeffs)[:5]])
+        L.check(self._lib.irmv_engine_enable_pnp(self._h, K, D, float(corner_scale[0]), float(corner_scale[1])),
+                "irmv_engine_enable_pnp")
+
+    def fetch_poses(self, n: int):
+        rv = np.empty((n, self.max_det, 3)); tv = np.empty((n, self.max_det, 3))
+        ok = np.empty((n, self.max_det), np.uint8)
+        L.check(self._lib.irmv_engine_fetch_poses(self._h, n, rv.ctypes.data, tv.ctypes.data, ok.ctypes.data),
+                "irmv_engine_fetch_poses")
+        return rv, tv, ok.astype(bool)
+
+    def profile_stages(self, dev_ptr: int, n: int):
+        ms = (C.c_float * 5)()
+        k = self._lib.irmv_engine_profile_stages(self._h, C.c_void_p(dev_ptr), n, C.byref(ms))
+        if k <= 0:
+            L.check(1, "irmv_engine_profile_stages")
+        return k, dict(zip(("preprocess", "conv", "decode_nms", "pnp", "total"), [float(v) for v in ms]))
 
     # -- parity taps ---------------------------------------------------------------------
     def read_tensor(self, name: str) -> np.ndarray:
@@ -239,13 +261,15 @@ class PnPSolver:
 
 # ---- stage-level wrappers (parity tests) ------------------------------------------------------
 def preprocess(frames: np.ndarray, chan_order: int = L.CH_PASSTHROUGH, rotate180: bool = True,
-               quantize_u8: bool = True, want_rotated: bool = False, device: int = 0):
+               quantize_u8: bool = True, want_rotated: bool = False, device: int = 0,
+               half_pixel: bool = False):
     """frames u8 [n,H,W,3] or [n,H,W] -> FP16 [n,640,640,8] NHWC (+ rotated u8 [n,H,W,3])."""
     frames = np.ascontiguousarray(frames, np.uint8)
     n, H, W = frames.shape[:3]
     out = np.empty((n, L.NET, L.NET, 8), np.float16)
     rot = np.empty((n, H, W, 3), np.uint8) if want_rotated else None
-    L.check(L.lib().irmv_preprocess(frames.ctypes.data, n, W, H, chan_order, int(rotate180), L.RESIZE_STRETCH,
+    L.check(L.lib().irmv_preprocess(frames.ctypes.data, n, W, H, chan_order, int(rotate180),
+                                    L.RESIZE_STRETCH_HALF_PIXEL if half_pixel else L.RESIZE_STRETCH,
                                     int(quantize_u8), out.ctypes.data, rot.ctypes.data if want_rotated else None,
                                     device), "irmv_preprocess")
     return (out, rot) if want_rotated else out

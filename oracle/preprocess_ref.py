@@ -7,10 +7,13 @@ Restates /root/reference/src/yolo_engine.cpp:179-200:
     K4 nppiCopy_32f_C3P3R                  -> packed HWC -> planar CHW   (:197-199)
 The reference does NOT letterbox and does NOT swap channels on the device.
 
-NPP's bilinear convention is not documented; `resize_bilinear_u8` is the restatement used by the
-CUDA kernel (half-pixel centres, FP32 lerp, round-half-up to u8), and oracle/npp_ref.cpp is the
-reference's literal NPP chain, compiled to oracle/_ref/ and run on the GPU box to pin it
-(tests/golden/npp_*.npz hold its outputs).  Bayer input (config 4) is demosaiced first;
+NPP's bilinear convention is not documented, so it was measured: oracle/npp_ref.cpp (the
+reference's literal NPP chain, built into oracle/_ref/) was run on a B200 with NPP 12.4.1 and its
+output for test/rm_test.jpg is pinned in tests/golden/npp_rm_golden.npz.  Result: nppiResize
+LINEAR maps corner-aligned, src = dst * (src_size/dst_size) with NO half-pixel offset (so the
+1280->640 axis simply picks every second pixel), and rounds to nearest.  `resize_bilinear_u8`
+with half_pixel=False restates exactly that (bit-identical to the NPP output on the fixture);
+half_pixel=True is the OpenCV/ultralytics convention kept as a non-reference mode.  Bayer input (config 4) is demosaiced first;
 its oracle is cv2.cvtColor(COLOR_Bayer*2RGB) restated in `demosaic_bilinear`.
 
 Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this module.
@@ -34,11 +37,15 @@ def rot180(img: np.ndarray) -> np.ndarray:
     return np.ascontiguousarray(img[::-1, ::-1])
 
 
-def _axis_taps(n_dst: int, n_src: int):
-    """Half-pixel-centre source taps in FP32, the exact arithmetic the kernel uses."""
+def _axis_taps(n_dst: int, n_src: int, half_pixel: bool = False):
+    """Source taps in FP32, the exact arithmetic the kernel uses.  half_pixel=False is NPP's
+    measured corner-aligned map (reference-exact); True is the OpenCV-style pixel-centre map."""
     scale = np.float32(n_src) / np.float32(n_dst)
     d = np.arange(n_dst, dtype=np.float32)
-    s = (d + np.float32(0.5)) * scale - np.float32(0.5)
+    if half_pixel:
+        s = (d + np.float32(0.5)) * scale - np.float32(0.5)
+    else:
+        s = d * scale
     i0 = np.floor(s)
     f = (s - i0).astype(np.float32)
     i0 = i0.astype(np.int64)
@@ -48,11 +55,11 @@ def _axis_taps(n_dst: int, n_src: int):
     return i0c, i1c, f
 
 
-def resize_bilinear_f32(img: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
+def resize_bilinear_f32(img: np.ndarray, out_h: int, out_w: int, half_pixel: bool = False) -> np.ndarray:
     """Bilinear stretch, FP32 result (no u8 rounding). img u8 [H,W,C]."""
     H, W, _ = img.shape
-    y0, y1, fy = _axis_taps(out_h, H)
-    x0, x1, fx = _axis_taps(out_w, W)
+    y0, y1, fy = _axis_taps(out_h, H, half_pixel)
+    x0, x1, fx = _axis_taps(out_w, W, half_pixel)
     p = img.astype(np.float32)
     fx_ = fx[None, :, None]
     fy_ = fy[:, None, None]
@@ -62,8 +69,8 @@ def resize_bilinear_f32(img: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
     return (top * (one - fy_) + bot * fy_).astype(np.float32)
 
 
-def resize_bilinear_u8(img: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
-    v = resize_bilinear_f32(img, out_h, out_w)
+def resize_bilinear_u8(img: np.ndarray, out_h: int, out_w: int, half_pixel: bool = False) -> np.ndarray:
+    v = resize_bilinear_f32(img, out_h, out_w, half_pixel)
     return np.clip(np.floor(v + np.float32(0.5)), 0, 255).astype(np.uint8)
 
 
@@ -122,7 +129,7 @@ def to_rgb(src: np.ndarray, chan: int) -> np.ndarray:
 
 
 def preprocess(src: np.ndarray, chan: int = CH_PASSTHROUGH, rotate: bool = True,
-               quantize_u8: bool = True):
+               quantize_u8: bool = True, half_pixel: bool = False):
     """Returns (input f32[3,640,640], rotated u8 image [H,W,3]) as the reference's graph leaves them.
 
     quantize_u8=True keeps the reference's 8-bit intermediate (K2 writes u8 before K3 scales it);
@@ -132,16 +139,16 @@ def preprocess(src: np.ndarray, chan: int = CH_PASSTHROUGH, rotate: bool = True,
     if rotate:
         img = rot180(img)
     if quantize_u8:
-        r = resize_bilinear_u8(img, NET, NET).astype(np.float32)
+        r = resize_bilinear_u8(img, NET, NET, half_pixel).astype(np.float32)
     else:
-        r = resize_bilinear_f32(img, NET, NET)
+        r = resize_bilinear_f32(img, NET, NET, half_pixel)
     x = (r / np.float32(255.0)).astype(np.float32)
     return np.ascontiguousarray(x.transpose(2, 0, 1)), img
 
 
-def preprocess_fp16(src, chan=CH_PASSTHROUGH, rotate=True, quantize_u8=True):
+def preprocess_fp16(src, chan=CH_PASSTHROUGH, rotate=True, quantize_u8=True, half_pixel=False):
     """What the CUDA kernel stores: the FP32 result rounded to FP16 (round-to-nearest-even)."""
-    x, img = preprocess(src, chan, rotate, quantize_u8)
+    x, img = preprocess(src, chan, rotate, quantize_u8, half_pixel)
     return x.astype(np.float16), img
 
 

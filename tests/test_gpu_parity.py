@@ -30,14 +30,15 @@ def frames(base_image):
 
 
 # ------------------------------------------------------------------------------- preprocess
-@pytest.mark.parametrize("chan,rotate,quant", [(0, True, True), (1, True, True), (0, False, True),
-                                               (0, True, False), (1, False, False)])
-def test_preprocess_packed_bit_exact(frames, chan, rotate, quant):
+@pytest.mark.parametrize("chan,rotate,quant,hp", [(0, True, True, False), (1, True, True, False),
+                                                  (0, False, True, False), (0, True, False, False),
+                                                  (1, False, False, True), (0, True, True, True)])
+def test_preprocess_packed_bit_exact(frames, chan, rotate, quant, hp):
     import irmv_detection_b200 as irmv
     from oracle import preprocess_ref as PR
-    got, rot = irmv.preprocess(frames, chan, rotate, quant, want_rotated=True)
+    got, rot = irmv.preprocess(frames, chan, rotate, quant, want_rotated=True, half_pixel=hp)
     for i, f in enumerate(frames):
-        ref, ref_rot = PR.preprocess_fp16(f, chan, rotate, quant)
+        ref, ref_rot = PR.preprocess_fp16(f, chan, rotate, quant, hp)
         assert np.array_equal(got[i, :, :, :3].view(np.uint16), ref.transpose(1, 2, 0).view(np.uint16)), f"frame {i}"
         assert not got[i, :, :, 3:].any()
         assert np.array_equal(rot[i], ref_rot)
@@ -53,6 +54,34 @@ def test_preprocess_bayer_bit_exact(frames, chan):
         ref, ref_rot = PR.preprocess_fp16(raw[i], chan, True, True)
         assert np.array_equal(got[i, :, :, :3].view(np.uint16), ref.transpose(1, 2, 0).view(np.uint16))
         assert np.array_equal(rot[i], ref_rot)
+
+
+def test_preprocess_matches_reference_npp_chain(base_image):
+    """The reference's own NPP calls (oracle/_ref/npp_ref, run on this GPU) and the golden capture
+    of them: the CUDA kernel must reproduce their 8-bit result exactly."""
+    import hashlib
+    import os
+    import subprocess
+    import irmv_detection_b200 as irmv
+    _cuda()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    got = irmv.preprocess(base_image[None])[0, :, :, :3].astype(np.float32).transpose(2, 0, 1)
+    u8 = np.rint(got * 255.0).astype(np.uint8)
+    g = np.load(os.path.join(root, "tests", "golden", "npp_rm_golden.npz"))
+    sha = np.frombuffer(hashlib.sha256(np.ascontiguousarray(u8).tobytes()).digest(), np.uint8)
+    assert np.array_equal(u8[:, 288:352, 288:352], g["crop"])
+    assert np.array_equal(sha, g["sha"])
+    exe = os.path.join(root, "oracle", "_ref", "npp_ref")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/npp_ref not built")
+    rnd = np.random.default_rng(21).integers(0, 256, base_image.shape, dtype=np.uint8)
+    rnd.tofile("/tmp/_npp_in.raw")
+    r = subprocess.run([exe, "/tmp/_npp_in.raw", "1280", "1024", "/tmp/_npp_out.f32"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    npp = np.fromfile("/tmp/_npp_out.f32", np.float32).reshape(3, 640, 640)
+    ours = irmv.preprocess(rnd[None])[0, :, :, :3].astype(np.float32).transpose(2, 0, 1)
+    assert np.array_equal(np.rint(ours * 255.0), np.rint(npp * 255.0))
+    assert np.abs(ours - npp).max() < 1e-3           # FP16 storage of k/255
 
 
 def test_preprocess_odd_source_size():

@@ -102,13 +102,24 @@ def test_preprocess_oracle_golden(base_image):
         assert np.array_equal(x[:, 300:316, 300:316], g[key + "_crop"])
 
 
+def test_preprocess_oracle_matches_reference_npp_capture(base_image):
+    """tests/golden/npp_rm_golden.npz = output of the reference's own NPP chain (oracle/npp_ref.cpp)
+    for test/rm_test.jpg on a B200: the restatement must equal it bit for bit."""
+    from oracle import preprocess_ref as PR
+    g = np.load(os.path.join(GOLD, "npp_rm_golden.npz"))
+    x, _ = PR.preprocess(base_image)
+    u8 = np.rint(x * 255.0).astype(np.uint8)
+    assert np.array_equal(u8[:, 288:352, 288:352], g["crop"])
+    assert np.array_equal(np.frombuffer(hashlib.sha256(np.ascontiguousarray(u8).tobytes()).digest(), np.uint8), g["sha"])
+
+
 def test_preprocess_oracle_vs_cv2(base_image):
     """BASELINE.md section 3 CPU form (cv2.flip + cv2.resize LINEAR): same half-pixel convention;
     OpenCV's 11-bit fixed-point lerp may differ by one 8-bit step."""
     from oracle import preprocess_ref as PR
     rnd = np.random.default_rng(1).integers(0, 256, base_image.shape, dtype=np.uint8)
     for img in (base_image, rnd):
-        a, rot_a = PR.preprocess(img)
+        a, rot_a = PR.preprocess(img, half_pixel=True)
         b, rot_b = PR.preprocess_cv2(img)
         assert np.array_equal(rot_a, rot_b)
         d = np.abs(a - b) * 255.0
