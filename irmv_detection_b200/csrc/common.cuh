@@ -57,7 +57,7 @@ struct ConvParams {
   int act;            // 1 = SiLU
   const __half *w_plain;   // [npad][kpad], k = (ky*k+kx)*cin + c          (direct kernel)
   const __half *w_tiled;   // [kpad/64][npad][64] with the 128B swizzle     (tcgen05 kernel)
-  const int32_t *ktab;     // [kpad/8] packed tap table                      (tcgen05 kernel)
+  const int32_t *ktab;     // [kpad/8][2] {element offset from the row's base pixel, meta} (tcgen05 kernel)
   const float *bias;       // [npad]
   __half *out;
   int out_cstride, out_coff;
@@ -69,9 +69,11 @@ cudaError_t launch_conv_direct(const ConvParams &p, cudaStream_t s);
 cudaError_t launch_conv_tc(const ConvParams &p, int num_sms, cudaStream_t s);
 size_t conv_tc_smem_bytes(const ConvParams &p, int *stages, int *b_resident);
 
-// ktab entry: bits 0-1 ky, 2-3 kx, 4 segment, 5 valid, 8.. channel offset inside the segment
-__host__ __device__ inline int32_t ktab_pack(int ky, int kx, int seg, int valid, int choff) {
-  return ky | (kx << 2) | (seg << 4) | (valid << 5) | (choff << 8);
+// ktab meta: bits 0-3 tap bit index (ky*k+kx), 4 segment, 5 valid.  The element offset is
+// ((ky-pad)*W + (kx-pad))*cstride + coff + choff relative to pixel (oy*stride, ox*stride); for an
+// upsample-on-read segment (1x1 convs only) it is just coff + choff.
+__host__ __device__ inline int32_t ktab_meta(int tap, int seg, int valid) {
+  return tap | (seg << 4) | (valid << 5);
 }
 
 // ---------------------------------------------------------------- SPPF pooling

@@ -114,12 +114,13 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   return d;
 }
 
-__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 struct TcArgs {
   ConvParams p;
   int M, num_tiles, KB, ksteps_last, stages, b_resident, tmem_cols;
   uint32_t idesc;
+  uint32_t mul_ow, mul_oh;      // ceil(2^34 / OW), ceil(2^34 / OH): q = (n * mul) >> 34, exact for n < 2^25
   uint32_t off_b, off_ktab, off_bias, off_bars;
 };
 
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
   const int npad = p.npad;
   const uint32_t b_block_bytes = (uint32_t)npad * 128u;
 
-  for (int i = tid; i < a.KB * 8; i += NTHREADS) s_ktab[i] = p.ktab[i];
+  for (int i = tid; i < a.KB * 16; i += NTHREADS) s_ktab[i] = p.ktab[i];
   for (int i = tid; i < npad; i += NTHREADS) s_bias[i] = p.bias[i];
   if (tid == 0) {
     for (int s = 0; s < a.stages; ++s) {
@@ -161,44 +162,62 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
 
   if (warp < EPI_WARP0) {
     // ===================================================================== A producers
+    // Per tile: decode the thread's 4 rows once (magic-number division), keep one 32-bit element
+    // offset per (segment, row) and a bitmask of the taps that fall inside the image.  Per
+    // k-block: one table lookup gives the tap's element offset, so a row costs a bit test, one
+    // add and the cp.async.
     const int chunk = tid & 7;
     const int rbase = tid >> 3;                       // 0..31, rows rbase + 32*i
     const uint32_t dst_off = (uint32_t)rbase * 128u + (uint32_t)((chunk ^ (rbase & 7)) << 4);
-    const int H = p.H, W = p.W;
+    const int H = p.H, W = p.W, ksz = p.k;
+    const __half *sp0 = p.seg[0].ptr, *sp1 = p.seg[1].ptr;
+    const int cs0 = p.seg[0].cstride, cs1 = p.seg[1].cstride;
+    const int up0 = p.seg[0].up, up1 = p.seg[1].up;
+    const int two = p.nseg > 1;
     int g = 0;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-      int iy0[4], ix0[4], bi[4];
+      int off0[4], off1[4];
+      uint32_t mask[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        int m = tile * BM + rbase + 32 * i;
+        const int m = tile * BM + rbase + 32 * i;
+        off0[i] = 0; off1[i] = 0; mask[i] = 0u;
         if (m < a.M) {
-          int ox = m % p.OW, t = m / p.OW;
-          int oy = t % p.OH;
-          bi[i] = t / p.OH;
-          iy0[i] = oy * p.stride - p.pad;
-          ix0[i] = ox * p.stride - p.pad;
-        } else {
-          bi[i] = -1; iy0[i] = 0; ix0[i] = 0;
+          const uint32_t t = (uint32_t)(((uint64_t)(uint32_t)m * a.mul_ow) >> 34);      // m / OW
+          const int ox = m - (int)t * p.OW;
+          const uint32_t bimg = (uint32_t)(((uint64_t)t * a.mul_oh) >> 34);             // t / OH
+          const int oy = (int)t - (int)bimg * p.OH;
+          const int iy0 = oy * p.stride, ix0 = ox * p.stride;
+          off0[i] = up0 ? (((int)bimg * (H >> 1) + (iy0 >> 1)) * (W >> 1) + (ix0 >> 1)) * cs0
+                        : (((int)bimg * H + iy0) * W + ix0) * cs0;
+          if (two)
+            off1[i] = up1 ? (((int)bimg * (H >> 1) + (iy0 >> 1)) * (W >> 1) + (ix0 >> 1)) * cs1
+                          : (((int)bimg * H + iy0) * W + ix0) * cs1;
+          uint32_t mk = 0u;
+          for (int ky = 0; ky < ksz; ++ky) {
+            const int iy = iy0 - p.pad + ky;
+            const bool yok = iy >= 0 && iy < H;
+            for (int kx = 0; kx < ksz; ++kx) {
+              const int ix = ix0 - p.pad + kx;
+              if (yok && ix >= 0 && ix < W) mk |= 1u << (ky * ksz + kx);
+            }
+          }
+          mask[i] = mk;
         }
       }
       for (int kb = 0; kb < a.KB; ++kb, ++g) {
         const int s = g % a.stages;
         const uint32_t ph = (uint32_t)(g / a.stages) & 1u;
-        mbar_wait(&bars->empty[s], ph ^ 1u);
-        const int32_t e = s_ktab[kb * 8 + chunk];
-        const int ky = e & 3, kx = (e >> 2) & 3, sg = (e >> 4) & 1, kvalid = (e >> 5) & 1;
-        const int choff = e >> 8;
-        const ConvSeg seg = p.seg[sg];
-        const int up = seg.up;
-        const int Hs = H >> up, Ws = W >> up;
-        const __half *sbase = seg.ptr + seg.coff + choff;
+        const int2 e = *reinterpret_cast<const int2 *>(&s_ktab[(kb * 8 + chunk) * 2]);
+        const int tapbit = e.y & 15, sg = (e.y >> 4) & 1;
+        const uint32_t kvalid = (uint32_t)(e.y >> 5) & 1u;
+        const __half *sbase = (sg ? sp1 : sp0) + e.x;
         const uint32_t dst0 = smem_u32(sA + (size_t)s * A_STAGE) + dst_off;
+        mbar_wait(&bars->empty[s], ph ^ 1u);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          int iy = iy0[i] + ky, ix = ix0[i] + kx;
-          bool ok = kvalid && bi[i] >= 0 && iy >= 0 && iy < H && ix >= 0 && ix < W;
-          const __half *src = seg.ptr;
-          if (ok) src = sbase + (((size_t)bi[i] * Hs + (iy >> up)) * Ws + (ix >> up)) * seg.cstride;
+          const uint32_t ok = kvalid & (mask[i] >> tapbit);
+          const __half *src = ok ? sbase + (sg ? off1[i] : off0[i]) : sp0;
           cp_async16(dst0 + (uint32_t)i * (32u * 128u), src, ok ? 16u : 0u);
         }
         if (p.sync_mode == 0) {
@@ -326,7 +345,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
 size_t conv_tc_smem_bytes(const ConvParams &p, int *stages_out, int *b_resident_out) {
   const int KB = p.kpad / BK;
   const size_t b_block = (size_t)p.npad * 128;
-  const size_t misc = (size_t)KB * 8 * 4 + (size_t)p.npad * 4 + sizeof(Bars) + 256;
+  const size_t misc = (size_t)KB * 16 * 4 + (size_t)p.npad * 4 + sizeof(Bars) + 256;
   int resident = 0, stages = 0;
   if ((size_t)KB * b_block + 3 * (size_t)A_STAGE + misc <= (size_t)SMEM_BUDGET) {
     resident = 1;
@@ -364,7 +383,9 @@ cudaError_t launch_conv_tc(const ConvParams &p, int num_sms, cudaStream_t s) {
   a.off_b = (uint32_t)((size_t)a.stages * A_STAGE);
   size_t b_bytes = a.b_resident ? (size_t)a.KB * b_block : (size_t)a.stages * b_block;
   a.off_ktab = (uint32_t)(a.off_b + b_bytes);
-  a.off_bias = a.off_ktab + (uint32_t)a.KB * 8 * 4;
+  a.off_bias = a.off_ktab + (uint32_t)a.KB * 16 * 4;
+  a.mul_ow = (uint32_t)(((1ull << 34) + (uint64_t)p.OW - 1) / (uint64_t)p.OW);
+  a.mul_oh = (uint32_t)(((1ull << 34) + (uint64_t)p.OH - 1) / (uint64_t)p.OH);
   a.off_bars = (a.off_bias + (uint32_t)p.npad * 4 + 15u) & ~15u;
   static size_t configured = 0;
   if (smem > configured) {

@@ -120,13 +120,14 @@ HostConv make_conv(const std::vector<const FileConv *> &parts, int cin_pad,
         h.w_tiled[((size_t)kb * h.npad + n) * 64 + chunk * 8 + (kk & 7)] =
             h.w_plain[(size_t)n * h.kpad + kb * 64 + kk];
       }
-  // tap table: one entry per 8-channel chunk of K
-  h.ktab.assign(h.kpad / 8, ktab_pack(0, 0, 0, 0, 0));
+  // chunk table (one entry per 8-channel chunk of K): {tap, segment, channel offset}; the
+  // device tap table is derived per layer instance in add_conv (it needs W and the pixel strides)
+  h.ktab.assign((size_t)(h.kpad / 8) * 3, -1);
   for (int q = 0; q < h.K / 8; ++q) {
     int kk = q * 8, tap = kk / cin_pad, c = kk % cin_pad;
     int sg = 0, off = c;
     if (seg_c.size() > 1 && c >= seg_c[0]) { sg = 1; off = c - seg_c[0]; }
-    h.ktab[q] = ktab_pack(tap / h.k, tap % h.k, sg, 1, off);
+    h.ktab[q * 3 + 0] = tap; h.ktab[q * 3 + 1] = sg; h.ktab[q * 3 + 2] = off;
   }
   return h;
 }
@@ -139,8 +140,7 @@ bool upload(HostConv &h) {
   };
   return up((void **)&h.d_plain, h.w_plain.data(), h.w_plain.size() * 2) &&
          up((void **)&h.d_tiled, h.w_tiled.data(), h.w_tiled.size() * 2) &&
-         up((void **)&h.d_bias, h.bias.data(), h.bias.size() * 4) &&
-         up((void **)&h.d_ktab, h.ktab.data(), h.ktab.size() * 4);
+         up((void **)&h.d_bias, h.bias.data(), h.bias.size() * 4);
 }
 
 struct Tensor {
@@ -272,7 +272,27 @@ void add_conv(irmv_engine *e, Lane &ln, HostConv &hc, std::vector<SegRef> in, in
   p.OH = (H + 2 * p.pad - hc.k) / hc.stride + 1;
   p.OW = (W + 2 * p.pad - hc.k) / hc.stride + 1;
   p.cin = cin; p.cout = hc.cout; p.npad = hc.npad; p.K = hc.K; p.kpad = hc.kpad; p.act = hc.act;
-  p.w_plain = hc.d_plain; p.w_tiled = hc.d_tiled; p.ktab = hc.d_ktab; p.bias = hc.d_bias;
+  p.w_plain = hc.d_plain; p.w_tiled = hc.d_tiled; p.bias = hc.d_bias;
+  {
+    // device tap table for this layer instance
+    const int nq = hc.kpad / 8;
+    std::vector<int32_t> tab((size_t)nq * 2, 0);
+    for (int q = 0; q < nq; ++q) {
+      int tap = hc.ktab[q * 3 + 0], sg = hc.ktab[q * 3 + 1], off = hc.ktab[q * 3 + 2];
+      if (tap < 0) { tab[q * 2 + 0] = 0; tab[q * 2 + 1] = ktab_meta(0, 0, 0); continue; }
+      const ConvSeg &g = p.seg[sg];
+      int ky = tap / hc.k, kx = tap % hc.k;
+      int delta = g.coff + off;
+      if (!g.up) delta += ((ky - p.pad) * W + (kx - p.pad)) * g.cstride;
+      tab[q * 2 + 0] = delta;
+      tab[q * 2 + 1] = ktab_meta(tap, sg, 1);
+    }
+    int32_t *d = nullptr;
+    cudaMalloc((void **)&d, tab.size() * 4);
+    cudaMemcpy(d, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice);
+    ln.allocs.push_back(d);
+    p.ktab = d;
+  }
   p.out = out.p; p.out_cstride = out.C; p.out_coff = out_coff;
   p.res = res ? res->p : nullptr; p.res_cstride = res ? res->C : 0; p.res_coff = res_coff;
   p.sync_mode = 0;
@@ -622,7 +642,7 @@ void irmv_engine_destroy(irmv_engine *e) {
     for (auto ev : ln.stage_ev) if (ev) cudaEventDestroy(ev);
   }
   for (auto &c : e->convs) {
-    cudaFree(c->d_plain); cudaFree(c->d_tiled); cudaFree(c->d_bias); cudaFree(c->d_ktab);
+    cudaFree(c->d_plain); cudaFree(c->d_tiled); cudaFree(c->d_bias);
   }
   for (auto s : e->slots_host) cudaFreeHost(s);
   cudaFree(e->slot_dev);
