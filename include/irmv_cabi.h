@@ -123,6 +123,10 @@ int irmv_engine_fetch_poses(irmv_engine *e, int nframes, double *rvecs, double *
  * stages: ms = {preprocess, convolutions, decode+NMS, PnP, total}.  Returns frames profiled. */
 int irmv_engine_profile_stages(irmv_engine *e, const uint8_t *frames_dev, int nframes, float ms[5]);
 
+/* Debug/tuning: per-tile clock64 stamps of CTA 0 for GEMM `op_index` (see engine.cu). */
+int irmv_engine_trace_conv(irmv_engine *e, int op_index, int nframes, long long *out, int cap_tiles,
+                           float *kernel_ms);
+
 /* Parity taps: raw activations of the last run.  name: "input" (preprocessed, NHWC8 FP16),
  * "box0".."box2" (NHWC64), "cls0".."cls2" (NHWC16), "boxes" (f32 [A,4]), or a module tap
  * ("m0".."m21").  Copies up to cap_bytes to dst (host); dims receives {B,H,W,C,elem_size}. */

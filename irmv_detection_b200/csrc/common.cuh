@@ -64,6 +64,8 @@ struct ConvParams {
   const __half *res;       // residual added after the activation, same grid as out; may be null
   int res_cstride, res_coff;
   int sync_mode;           // tcgen05 producer hand-off: 0 = cp.async-tracked mbarrier, 1 = wait+fence
+  long long *trace;        // debug: CTA 0 writes per-tile clock64 stamps [tile][8]; null in production
+  int trace_cap;
 };
 cudaError_t launch_conv_direct(const ConvParams &p, cudaStream_t s);
 cudaError_t launch_conv_tc(const ConvParams &p, int num_sms, cudaStream_t s);

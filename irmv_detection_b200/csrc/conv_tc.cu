@@ -28,8 +28,8 @@ constexpr int EPI_WARP0 = 8;
 constexpr int MMA_WARP = 12;
 constexpr int BLD_WARP = 13;
 constexpr int NTHREADS = 14 * 32;
-constexpr int MAX_STAGES = 6;
-constexpr int SMEM_BUDGET = 160 * 1024;       // leave L1 room for the 3x3 tap re-reads
+constexpr int MAX_STAGES = 12;
+constexpr int SMEM_BUDGET = 220 * 1024;       // the ring depth hides HBM latency; L1 is not relied on
 
 struct Bars {
   uint64_t full[MAX_STAGES];
@@ -47,16 +47,39 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) {
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+// try_wait with a suspend-time hint: the polling lane sleeps in hardware until the phase
+// completes (or the hint expires) instead of re-issuing try_wait every few cycles -- measured:
+// un-hinted spinning by the epilogue lanes was 35% of all executed instructions and slowed every
+// other mbarrier operation on the SM.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred P1;\n"
       "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
       "@P1 bra DONE;\n"
       "bra LAB_WAIT;\n"
       "DONE:\n"
-      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+      "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
+}
+// One lane polls, the warp is released by __syncwarp: 32 lanes spinning on try_wait saturate the
+// shared-memory sync unit (measured: ~600 cycles to return from an already-completed barrier).
+__device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, uint32_t parity, int lane) {
+  if (lane == 0) mbar_wait(bar, parity);
+  __syncwarp();
+}
+// elect.sync: ptxas knows exactly one lane runs the guarded region, so tcgen05 operands can live in
+// uniform registers without the per-lane "waterfall" loop that `if (lane == 0)` produces.
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .b32 %%rx;\n"
+      ".reg .pred %%px;\n"
+      "elect.sync %%rx|%%px, %1;\n"
+      "@%%px mov.s32 %0, 1;\n"
+      "}" : "+r"(pred) : "r"(0xffffffffu));
+  return pred;
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -71,11 +94,24 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
       ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes)
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes)
                : "memory");
 }
 __device__ __forceinline__ void cp_async_mbar_arrive(uint64_t *bar) {
   asm volatile("cp.async.mbarrier.arrive.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// wait until at most n of this thread's cp.async groups are still in flight (n is an immediate)
+__device__ __forceinline__ void cp_async_wait_lag(int n) {
+  switch (n) {
+    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+    case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+    case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+    case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+    case 6: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
+    default: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
+  }
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -114,7 +150,14 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   return d;
 }
 
-__device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// SiLU with one MUFU op per element: x*sigmoid(x) = h + h*tanh(h), h = x/2 (tanh.approx.f32,
+// relative error ~2^-11, the size of the FP16 rounding that follows).
+__device__ __forceinline__ float silu(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 
 struct TcArgs {
   ConvParams p;
@@ -140,12 +183,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
   for (int i = tid; i < npad; i += NTHREADS) s_bias[i] = p.bias[i];
   if (tid == 0) {
     for (int s = 0; s < a.stages; ++s) {
-      mbar_init(&bars->full[s], NPROD + (a.b_resident ? 0 : 1));
+      mbar_init(&bars->full[s], 128 + (a.b_resident ? 0 : 1));   // the 128 threads of the owning producer group
       mbar_init(&bars->empty[s], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->tmem_full[i], 1);
-      mbar_init(&bars->tmem_empty[i], 128);
+      mbar_init(&bars->tmem_empty[i], 4);                                // one arrive per epilogue warp
     }
     mbar_init(&bars->bfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -162,73 +205,89 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
 
   if (warp < EPI_WARP0) {
     // ===================================================================== A producers
-    // Per tile: decode the thread's 4 rows once (magic-number division), keep one 32-bit element
-    // offset per (segment, row) and a bitmask of the taps that fall inside the image.  Per
-    // k-block: one table lookup gives the tap's element offset, so a row costs a bit test, one
-    // add and the cp.async.
-    const int chunk = tid & 7;
-    const int rbase = tid >> 3;                       // 0..31, rows rbase + 32*i
+    // Two groups of 4 warps alternate k-blocks (group = k-block parity), so the serial latency of
+    // one warp's loop body (barrier wait, table lookup, issue) is paid once per TWO k-blocks.
+    // Per tile a thread decodes its 8 rows once (magic-number division) into a 32-bit element
+    // offset per (segment, row) and a bitmask of the taps that fall inside the image; per
+    // k-block one table lookup gives the tap's element offset, so a row costs a bit test, an
+    // add and the cp.async.  Hand-off: each thread tracks its copies with cp.async groups and ONE
+    // lane per warp arrives on the stage's mbarrier, `lag` of the group's k-blocks behind the
+    // issue front (256 per-thread arrives per stage serialise on one smem word).
+    const int grp = warp >> 2;
+    const int ptid = tid & 127;
+    const int chunk = ptid & 7;
+    const int rbase = ptid >> 3;                      // 0..15, rows rbase + 16*i
     const uint32_t dst_off = (uint32_t)rbase * 128u + (uint32_t)((chunk ^ (rbase & 7)) << 4);
-    const int H = p.H, W = p.W, ksz = p.k;
+    const int H = p.H, W = p.W, OW = p.OW, OH = p.OH, cstr = p.stride, M = a.M;
+    const bool k3 = p.k == 3;
+    const uint32_t mul_ow = a.mul_ow, mul_oh = a.mul_oh;
     const __half *sp0 = p.seg[0].ptr, *sp1 = p.seg[1].ptr;
     const int cs0 = p.seg[0].cstride, cs1 = p.seg[1].cstride;
     const int up0 = p.seg[0].up, up1 = p.seg[1].up;
     const int two = p.nseg > 1;
-    int g = 0;
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-      int off0[4], off1[4];
-      uint32_t mask[4];
+    const int Hh = H >> 1, Wh = W >> 1;
+    const int stages = a.stages, KB = a.KB;
+    const int lag = (stages - 1) / 2 < 7 ? (stages - 1) / 2 : 7;   // own k-blocks in flight = lag + 1
+    const bool nozero = !(p.sync_mode & 2);
+    int s = 0;                 // ring slot of the current k-block
+    uint32_t ph = 0;           // its phase
+    int par = 0;               // its parity (which group owns it)
+    int own = 0;               // k-blocks this group has issued
+    int s_pub = grp % stages;  // ring slot of the next k-block this group publishes
+    int itp = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++itp) {
+      const bool tr = p.trace && blockIdx.x == 0 && tid == 0 && itp < p.trace_cap;
+      if (tr) p.trace[itp * 8 + 0] = clock64();
+      int off0[8], off1[8];
+      uint32_t mask[8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int m = tile * BM + rbase + 32 * i;
-        off0[i] = 0; off1[i] = 0; mask[i] = 0u;
-        if (m < a.M) {
-          const uint32_t t = (uint32_t)(((uint64_t)(uint32_t)m * a.mul_ow) >> 34);      // m / OW
-          const int ox = m - (int)t * p.OW;
-          const uint32_t bimg = (uint32_t)(((uint64_t)t * a.mul_oh) >> 34);             // t / OH
-          const int oy = (int)t - (int)bimg * p.OH;
-          const int iy0 = oy * p.stride, ix0 = ox * p.stride;
-          off0[i] = up0 ? (((int)bimg * (H >> 1) + (iy0 >> 1)) * (W >> 1) + (ix0 >> 1)) * cs0
-                        : (((int)bimg * H + iy0) * W + ix0) * cs0;
-          if (two)
-            off1[i] = up1 ? (((int)bimg * (H >> 1) + (iy0 >> 1)) * (W >> 1) + (ix0 >> 1)) * cs1
-                          : (((int)bimg * H + iy0) * W + ix0) * cs1;
-          uint32_t mk = 0u;
-          for (int ky = 0; ky < ksz; ++ky) {
-            const int iy = iy0 - p.pad + ky;
-            const bool yok = iy >= 0 && iy < H;
-            for (int kx = 0; kx < ksz; ++kx) {
-              const int ix = ix0 - p.pad + kx;
-              if (yok && ix >= 0 && ix < W) mk |= 1u << (ky * ksz + kx);
-            }
-          }
-          mask[i] = mk;
+      for (int i = 0; i < 8; ++i) {
+        const int m = tile * BM + rbase + 16 * i;
+        const uint32_t t = (uint32_t)(((uint64_t)(uint32_t)m * mul_ow) >> 34);      // m / OW
+        const int ox = m - (int)t * OW;
+        const uint32_t bimg = (uint32_t)(((uint64_t)t * mul_oh) >> 34);             // t / OH
+        const int oy = (int)t - (int)bimg * OH;
+        const int iy0 = oy * cstr, ix0 = ox * cstr;
+        const int full = ((int)bimg * H + iy0) * W + ix0;
+        const int half = ((int)bimg * Hh + (iy0 >> 1)) * Wh + (ix0 >> 1);
+        off0[i] = (up0 ? half : full) * cs0;
+        off1[i] = two ? (up1 ? half : full) * cs1 : 0;
+        // taps inside the image (k = 1: the pixel itself; k = 3, pad 1: closed form)
+        uint32_t mk = 1u;
+        if (k3) {
+          const uint32_t xb = (ix0 >= 1 ? 1u : 0u) | 2u | (ix0 + 1 < W ? 4u : 0u);
+          mk = (iy0 >= 1 ? xb : 0u) | (xb << 3) | (iy0 + 1 < H ? xb << 6 : 0u);
         }
+        mask[i] = (m < M && nozero) ? mk : 0u;
       }
-      for (int kb = 0; kb < a.KB; ++kb, ++g) {
-        const int s = g % a.stages;
-        const uint32_t ph = (uint32_t)(g / a.stages) & 1u;
-        const int2 e = *reinterpret_cast<const int2 *>(&s_ktab[(kb * 8 + chunk) * 2]);
-        const int tapbit = e.y & 15, sg = (e.y >> 4) & 1;
-        const uint32_t kvalid = (uint32_t)(e.y >> 5) & 1u;
-        const __half *sbase = (sg ? sp1 : sp0) + e.x;
-        const uint32_t dst0 = smem_u32(sA + (size_t)s * A_STAGE) + dst_off;
-        mbar_wait(&bars->empty[s], ph ^ 1u);
+      if (tr) p.trace[itp * 8 + 1] = clock64();
+      for (int kb = 0; kb < KB; ++kb) {
+        if (par == grp) {
+          const int2 e = *reinterpret_cast<const int2 *>(&s_ktab[(kb * 8 + chunk) * 2]);
+          const int tapbit = e.y & 15, sg = (e.y >> 4) & 1;
+          const uint32_t kvalid = (uint32_t)(e.y >> 5) & 1u;
+          const __half *sbase = (sg ? sp1 : sp0) + e.x;
+          const uint32_t dst0 = smem_u32(sA + (size_t)s * A_STAGE) + dst_off;
+          const bool tk = p.trace && blockIdx.x == 0 && ptid == 0 && itp == 3 && kb < 16;
+          if (tk) p.trace[p.trace_cap * 8 + kb * 8 + 0] = clock64();
+          mbar_wait_warp(&bars->empty[s], ph ^ 1u, lane);
+          if (tk) p.trace[p.trace_cap * 8 + kb * 8 + 1] = clock64();
+          if (tr && kb == 0) p.trace[itp * 8 + 2] = clock64();
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint32_t ok = kvalid & (mask[i] >> tapbit);
-          const __half *src = ok ? sbase + (sg ? off1[i] : off0[i]) : sp0;
-          cp_async16(dst0 + (uint32_t)i * (32u * 128u), src, ok ? 16u : 0u);
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t ok = kvalid & (mask[i] >> tapbit);
+            const __half *src = ok ? sbase + (sg ? off1[i] : off0[i]) : sp0;
+            cp_async16(dst0 + (uint32_t)i * (16u * 128u), src, ok ? 16u : 0u);
+          }
+          // each thread's copies arrive on the stage barrier when they land (no thread blocks on
+          // memory latency); .noinc: the arrival is one of the 128 the barrier was initialised with
+          asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&bars->full[s])) : "memory");
+          if (tk) p.trace[p.trace_cap * 8 + kb * 8 + 2] = clock64();
+          ++own;
+          if (tr && kb >= KB - 2) p.trace[itp * 8 + 3] = clock64();
         }
-        if (p.sync_mode == 0) {
-          cp_async_mbar_arrive(&bars->full[s]);
-          mbar_arrive(&bars->full[s]);
-        } else {
-          asm volatile("cp.async.commit_group;" ::: "memory");
-          asm volatile("cp.async.wait_group 0;" ::: "memory");
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          mbar_arrive(&bars->full[s]);
-        }
+        par ^= 1;
+        if (++s == stages) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp < MMA_WARP) {
@@ -239,8 +298,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t aph = (uint32_t)(it >> 1) & 1u;
-      mbar_wait(&bars->tmem_full[acc], aph);
+      const bool tr = p.trace && blockIdx.x == 0 && tid == EPI_WARP0 * 32 && it < p.trace_cap;
+      mbar_wait_warp(&bars->tmem_full[acc], aph, lane);
       tc_fence_after();
+      if (tr) p.trace[it * 8 + 6] = clock64();
       const int m = tile * BM + row;
       const bool mok = m < a.M;
       __half *orow = p.out + (size_t)(mok ? m : 0) * p.out_cstride + p.out_coff;
@@ -252,9 +313,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
         tc_ld_wait();
         if (c0 + 16 >= npad) {           // accumulator fully read: hand it back to the MMA warp
           tc_fence_before();
-          mbar_arrive(&bars->tmem_empty[acc]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
         }
-        if (!mok || c0 >= p.cout) continue;
+        if (!mok || c0 >= p.cout || (p.sync_mode & 16)) continue;
         float v[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -276,56 +338,68 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
         __half2 hv[8];
 #pragma unroll
         for (int t = 0; t < 8; ++t) hv[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
+        if (p.sync_mode & 8) continue;
         *reinterpret_cast<uint4 *>(orow + c0) = *reinterpret_cast<uint4 *>(&hv[0]);
         if (c0 + 8 < p.cout) *reinterpret_cast<uint4 *>(orow + c0 + 8) = *reinterpret_cast<uint4 *>(&hv[4]);
       }
+      if (tr) p.trace[it * 8 + 7] = clock64();
     }
   } else if (warp == MMA_WARP) {
     // ===================================================================== MMA issuer
-    if (a.b_resident) mbar_wait(&bars->bfull, 0);
-    int g = 0, it = 0;
+    if (a.b_resident) mbar_wait_warp(&bars->bfull, 0, lane);
+    int it = 0, s = 0;
+    uint32_t ph = 0;
+    const int stages = a.stages, KB = a.KB;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t aph = (uint32_t)(it >> 1) & 1u;
-      mbar_wait(&bars->tmem_empty[acc], aph ^ 1u);
+      mbar_wait_warp(&bars->tmem_empty[acc], aph ^ 1u, lane);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * npad);
-      for (int kb = 0; kb < a.KB; ++kb, ++g) {
-        const int s = g % a.stages;
-        const uint32_t ph = (uint32_t)(g / a.stages) & 1u;
-        mbar_wait(&bars->full[s], ph);
+      for (int kb = 0; kb < KB; ++kb) {
+        const bool tk = p.trace && blockIdx.x == 0 && lane == 0 && it == 3 && kb < 16;
+        if (tk) p.trace[p.trace_cap * 8 + kb * 8 + 5] = clock64();
+        mbar_wait_warp(&bars->full[s], ph, lane);
         tc_fence_after();
-        if (lane == 0) {
+        if (tk) p.trace[p.trace_cap * 8 + kb * 8 + 6] = clock64();
+        if (p.trace && blockIdx.x == 0 && lane == 0 && it < p.trace_cap) {
+          if (kb == 0) p.trace[it * 8 + 4] = clock64();
+          if (kb == KB - 1) p.trace[it * 8 + 5] = clock64();
+        }
+        if (elect_one()) {
           const uint64_t adesc = make_desc(smem_u32(sA + (size_t)s * A_STAGE));
           const uint64_t bdesc = make_desc(smem_u32(sB + (size_t)(a.b_resident ? kb : s) * b_block_bytes));
-          const int nks = (kb == a.KB - 1) ? a.ksteps_last : 4;
+          const int nks = (kb == KB - 1) ? a.ksteps_last : 4;
+          if (!(p.sync_mode & 4))
           for (int ks = 0; ks < nks; ++ks)
             tc_mma_f16(tmem_d, adesc + (uint64_t)(ks * 2), bdesc + (uint64_t)(ks * 2), a.idesc,
                        (uint32_t)((kb | ks) != 0));
           tc_commit(&bars->empty[s]);
-          if (kb == a.KB - 1) tc_commit(&bars->tmem_full[acc]);
+          if (kb == KB - 1) tc_commit(&bars->tmem_full[acc]);
+          if (tk) p.trace[p.trace_cap * 8 + kb * 8 + 7] = clock64();
         }
         __syncwarp();
+        if (++s == stages) { s = 0; ph ^= 1u; }
       }
     }
   } else {
     // ===================================================================== weight loader
-    if (lane == 0) {
+    if (elect_one()) {
       if (a.b_resident) {
         mbar_expect_tx(&bars->bfull, (uint32_t)a.KB * b_block_bytes);
         for (int kb = 0; kb < a.KB; ++kb)
           bulk_g2s(sB + (size_t)kb * b_block_bytes, p.w_tiled + (size_t)kb * npad * BK,
                    b_block_bytes, &bars->bfull);
       } else {
-        int g = 0;
+        int s = 0;
+        uint32_t ph = 0;
         for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-          for (int kb = 0; kb < a.KB; ++kb, ++g) {
-            const int s = g % a.stages;
-            const uint32_t ph = (uint32_t)(g / a.stages) & 1u;
+          for (int kb = 0; kb < a.KB; ++kb) {
             mbar_wait(&bars->empty[s], ph ^ 1u);
             mbar_expect_tx(&bars->full[s], b_block_bytes);
             bulk_g2s(sB + (size_t)s * b_block_bytes, p.w_tiled + (size_t)kb * npad * BK,
                      b_block_bytes, &bars->full[s]);
+            if (++s == a.stages) { s = 0; ph ^= 1u; }
           }
         }
       }
@@ -347,16 +421,13 @@ size_t conv_tc_smem_bytes(const ConvParams &p, int *stages_out, int *b_resident_
   const size_t b_block = (size_t)p.npad * 128;
   const size_t misc = (size_t)KB * 16 * 4 + (size_t)p.npad * 4 + sizeof(Bars) + 256;
   int resident = 0, stages = 0;
-  if ((size_t)KB * b_block + 3 * (size_t)A_STAGE + misc <= (size_t)SMEM_BUDGET) {
+  if ((size_t)KB * b_block + 4 * (size_t)A_STAGE + misc + 1024 <= (size_t)SMEM_BUDGET) {
     resident = 1;
-    stages = (int)(((size_t)SMEM_BUDGET - (size_t)KB * b_block - misc) / A_STAGE);
-    if (stages > 4) stages = 4;
+    stages = (int)(((size_t)SMEM_BUDGET - (size_t)KB * b_block - misc - 1024) / A_STAGE);
   } else {
-    size_t budget = 200 * 1024;
-    stages = (int)((budget - misc) / (A_STAGE + b_block));
-    if (stages > 4) stages = 4;
+    stages = (int)(((size_t)SMEM_BUDGET - misc - 1024) / (A_STAGE + b_block));
   }
-  if (stages > KB + 1) stages = KB + 1;   // no point in more slots than one tile can fill twice
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) stages = 2;
   if (stages_out) *stages_out = stages;
   if (b_resident_out) *b_resident_out = resident;

@@ -8,6 +8,7 @@
 // What changed: unified memory -> pinned host slots + device buffers; TensorRT/NPP -> the kernels
 // in this directory; batch-1 -> sub-batches replayed on several lanes (streams).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <chrono>
 #include <map>
@@ -296,6 +297,7 @@ void add_conv(irmv_engine *e, Lane &ln, HostConv &hc, std::vector<SegRef> in, in
   p.out = out.p; p.out_cstride = out.C; p.out_coff = out_coff;
   p.res = res ? res->p : nullptr; p.res_cstride = res ? res->C : 0; p.res_coff = res_coff;
   p.sync_mode = 0;
+  p.trace = nullptr; p.trace_cap = 0;
   ln.ops.push_back(op);
 }
 
@@ -826,6 +828,38 @@ int irmv_engine_profile_stages(irmv_engine *e, const uint8_t *frames_dev, int nf
   for (int i = 0; i < 4; ++i) IRMV_CUDA(cudaEventElapsedTime(&ms[i], ln.stage_ev[i], ln.stage_ev[i + 1]));
   IRMV_CUDA(cudaEventElapsedTime(&ms[4], ln.stage_ev[0], ln.stage_ev[4]));
   return n;
+}
+
+// Debug: re-run GEMM number `op_index` of lane 0 on whatever its input buffers hold, with CTA 0
+// writing clock64 stamps per tile: {tile start, before empty wait, after, last k-block issued,
+// MMA first full, MMA last full, epilogue start, epilogue end}.  Returns tiles traced.
+int irmv_engine_trace_conv(irmv_engine *e, int op_index, int nframes, long long *out, int cap_tiles, float *kernel_ms) {
+  if (!e || !out || cap_tiles < 1) { set_error("bad argument"); return -1; }
+  cudaSetDevice(e->cfg.device);
+  Lane &ln = e->lanes[0];
+  int ci = -1;
+  Op *op = nullptr;
+  for (auto &o : ln.ops) if (o.kind == Op::CONV && ++ci == op_index) { op = &o; break; }
+  if (!op) { set_error("no such conv"); return -1; }
+  long long *d = nullptr;
+  cudaMalloc((void **)&d, (size_t)(cap_tiles + 16) * 64);
+  cudaMemset(d, 0, (size_t)(cap_tiles + 16) * 64);
+  ConvParams p = op->cp;
+  p.B = nframes < e->S ? nframes : e->S;
+  p.trace = d; p.trace_cap = cap_tiles;
+  if (const char *dbg = getenv("IRMV_TC_DEBUG")) p.sync_mode = atoi(dbg);
+  cudaDeviceSynchronize();
+  cudaEventRecord(ln.stage_ev[0], ln.stream);
+  launch_conv_tc(p, e->num_sms, ln.stream);
+  cudaEventRecord(ln.stage_ev[1], ln.stream);
+  cudaError_t ce = cudaStreamSynchronize(ln.stream);
+  if (kernel_ms) cudaEventElapsedTime(kernel_ms, ln.stage_ev[0], ln.stage_ev[1]);
+  cudaMemcpy(out, d, (size_t)(cap_tiles + 16) * 64, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (ce != cudaSuccess) { set_error(cudaGetErrorString(ce)); return -1; }
+  int M = p.B * p.OH * p.OW, tiles = (M + 127) / 128;
+  int per_cta = (tiles + (tiles < e->num_sms ? tiles : e->num_sms) - 1) / (tiles < e->num_sms ? tiles : e->num_sms);
+  return per_cta < cap_tiles ? per_cta : cap_tiles;
 }
 
 // ------------------------------------------------------------------ stage entry points

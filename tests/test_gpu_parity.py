@@ -352,3 +352,21 @@ def test_bayer_pipeline_batch_invariance(base_image, weights_seed0):
         assert res2[i] == res[p]
     assert sum(len(r) for r in res) > 0
     eng.close()
+
+
+def test_large_sub_batch_matches_single_frames(base_image, weights_seed0):
+    """Many tiles per persistent CTA (smem ring wraps, TMEM ping-pong): a 32-frame replay must give
+    each frame exactly what it gets alone, and frame 0 must still match the FP32 oracle."""
+    import irmv_detection_b200 as irmv
+    from irmv_detection_b200 import synth
+    _cuda()
+    fr = synth.frames_from_base(base_image, 32, seed=5)
+    big = irmv.YoloEngine(weights_seed0, (1280, 1024), max_batch=32, sub_batch=32, num_lanes=1)
+    res = big.detect_batch(fr)
+    box_big = big.read_tensor("box0")
+    one = irmv.YoloEngine(weights_seed0, (1280, 1024))
+    for i in (0, 7, 19, 31):
+        r = one.detect_batch(fr[i:i + 1])[0]
+        assert r == res[i], f"frame {i}"
+        assert np.array_equal(one.read_tensor("box0")[0], box_big[i]), f"frame {i} head tensor"
+    big.close(); one.close()
