@@ -15,6 +15,21 @@ constexpr int kNumAnchors = 8400;   // 80*80 + 40*40 + 20*20
 constexpr int kClsPad = 16;         // class-logit channels padded 14 -> 16
 constexpr int kMaxCand = 4096;      // pre-NMS top-k (oracle/nms_ref.py MAX_CAND)
 
+// ---------------------------------------------------------------- activation layout
+// Every NHWC activation is stored as a zero-padded raster ("PR" layout): row pitch Wp = W + 1
+// (one zero pixel after each row -- it is the right neighbour of x = W-1 and the left neighbour of
+// x = 0 of the next row), H + 1 rows per image (one zero row before each image -- it is the bottom
+// neighbour of the previous image and the top neighbour of this one) and one trailing zero row.
+// A 3x3 / pad-1 tap is then a constant raster offset (ky-1)*Wp + (kx-1) with no bounds test, which
+// is what lets the raster convolution kernel feed all 9 taps from one shared-memory halo tile.
+// Buffers carry pr_guard() zero pixels in front and behind so halo reads never leave them.
+__host__ __device__ inline int pr_wp(int W) { return W + 1; }
+__host__ __device__ inline long long pr_pixels(int B, int H, int W) { return ((long long)B * (H + 1) + 1) * (W + 1); }
+__host__ __device__ inline long long pr_index(int b, int y, int x, int H, int W) {
+  return ((long long)b * (H + 1) + 1 + y) * (W + 1) + x;
+}
+__host__ __device__ inline int pr_guard(int W) { return W + 1 + 8; }
+
 void set_error(const std::string &msg);
 bool cuda_ok(cudaError_t e, const char *what, const char *file, int line);
 
@@ -27,7 +42,7 @@ bool cuda_ok(cudaError_t e, const char *what, const char *file, int line);
 struct PreprocessParams {
   const uint8_t *src;          // [n][H][W][3] or [n][H][W] (Bayer); used when src_indirect == null
   const uint8_t *const *src_indirect;  // device word holding the frame base pointer (batch path)
-  __half *dst;                 // [n][640][640][8]
+  __half *dst;                 // PR layout of [n][640][640][8]
   uint8_t *rotated;            // optional [n][H][W][3] rotated RGB image, may be null
   int n, src_w, src_h;
   int chan_order, rotate180, resize_mode, quantize_u8;
@@ -56,7 +71,8 @@ struct ConvParams {
   int kpad;           // K rounded up to 64
   int act;            // 1 = SiLU
   const __half *w_plain;   // [npad][kpad], k = (ky*k+kx)*cin + c          (direct kernel)
-  const __half *w_tiled;   // [kpad/64][npad][64] with the 128B swizzle     (tcgen05 kernel)
+  const __half *w_tiled;   // [kpad/64][npad][64] with the 128B swizzle     (tcgen05 gather kernel)
+  const __half *w_raster;  // [k*k][cin/8][npad][8]                          (tcgen05 raster kernel)
   const int32_t *ktab;     // [kpad/8][2] {element offset from the row's base pixel, meta} (tcgen05 kernel)
   const float *bias;       // [npad]
   __half *out;
@@ -70,6 +86,11 @@ struct ConvParams {
 cudaError_t launch_conv_direct(const ConvParams &p, cudaStream_t s);
 cudaError_t launch_conv_tc(const ConvParams &p, int num_sms, cudaStream_t s);
 size_t conv_tc_smem_bytes(const ConvParams &p, int *stages, int *b_resident);
+// Raster (halo-tile) kernel: 3x3/stride-1/pad-1 and 1x1 convolutions whose weights fit in shared
+// memory.  w_raster: [tap][cin/8][npad][8] (no swizzle).  Returns false from the fit test when the
+// layer has to take the gather kernel instead.
+bool conv_raster_fits(const ConvParams &p);
+cudaError_t launch_conv_raster(const ConvParams &p, int num_sms, cudaStream_t s);
 
 // ktab meta: bits 0-3 tap bit index (ky*k+kx), 4 segment, 5 valid.  The element offset is
 // ((ky-pad)*W + (kx-pad))*cstride + coff + choff relative to pixel (oy*stride, ox*stride); for an
@@ -79,14 +100,15 @@ __host__ __device__ inline int32_t ktab_meta(int tap, int seg, int valid) {
 }
 
 // ---------------------------------------------------------------- SPPF pooling
-// in: [B][H][W] slice of c channels at coff; writes maxpool5, maxpool5^2, maxpool5^3 to the
+// in: PR-layout [B][H][W] slice of c channels at coff; writes maxpool5, maxpool5^2, maxpool5^3 to the
 // three following channel slices of the same buffer (ultralytics SPPF).
 cudaError_t launch_sppf_pool(__half *buf, int B, int H, int W, int cstride, int c, cudaStream_t s);
 
 // ---------------------------------------------------------------- decode + NMS
 struct HeadPtrs {
-  const __half *box[3];   // [B][hw][hw][64]
-  const __half *cls[3];   // [B][hw][hw][16]
+  const __half *box[3];   // PR layout of [B][hw][hw][64]
+  const __half *cls[3];   // PR layout of [B][hw][hw][16]
+  int padded;             // 1: PR layout (engine); 0: dense [B][hw*hw][C] (irmv_decode stage entry)
 };
 struct DetOut {            // per frame, device
   int32_t *num_dets;      // [B]

@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(ConvParams p) {
         const ConvSeg sg = p.seg[s];
         int hs = sg.up ? p.H >> 1 : p.H, ws = sg.up ? p.W >> 1 : p.W;
         int sy = sg.up ? iy >> 1 : iy, sx = sg.up ? ix >> 1 : ix;
-        const __half *ip = sg.ptr + (((size_t)b * hs + sy) * ws + sx) * sg.cstride + sg.coff;
+        const __half *ip = sg.ptr + (size_t)pr_index(b, sy, sx, hs, ws) * sg.cstride + sg.coff;
         for (int c = 0; c < sg.c; c += 8) {
           uint4 iv = *reinterpret_cast<const uint4 *>(ip + c);
           const __half2 *ih = reinterpret_cast<const __half2 *>(&iv);
@@ -65,8 +65,9 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(ConvParams p) {
   }
   __half outv[8];
   float r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const size_t opix = (size_t)pr_index(b, oy, ox, p.OH, p.OW);
   if (p.res) {
-    uint4 rv = *reinterpret_cast<const uint4 *>(p.res + (size_t)m * p.res_cstride + p.res_coff + g * 8);
+    uint4 rv = *reinterpret_cast<const uint4 *>(p.res + opix * p.res_cstride + p.res_coff + g * 8);
     const __half2 *rh = reinterpret_cast<const __half2 *>(&rv);
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
@@ -79,7 +80,7 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(ConvParams p) {
     float v = p.act ? silu(acc[j]) : acc[j];
     outv[j] = __float2half_rn(v + r[j]);
   }
-  *reinterpret_cast<uint4 *>(p.out + (size_t)m * p.out_cstride + p.out_coff + g * 8) =
+  *reinterpret_cast<uint4 *>(p.out + opix * p.out_cstride + p.out_coff + g * 8) =
       *reinterpret_cast<uint4 *>(outv);
 }
 
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(128) sppf_pool_kernel(__half *buf, int B, int 
     for (int dx = -6; dx <= 6; ++dx) {
       int xx = x + dx;
       if (xx < 0 || xx >= W) continue;
-      uint4 v = *reinterpret_cast<const uint4 *>(buf + (((size_t)b * H + yy) * W + xx) * cstride + g * 8);
+      uint4 v = *reinterpret_cast<const uint4 *>(buf + (size_t)pr_index(b, yy, xx, H, W) * cstride + g * 8);
       const __half2 *h = reinterpret_cast<const __half2 *>(&v);
       int r = max(abs(dy), abs(dx));
 #pragma unroll
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(128) sppf_pool_kernel(__half *buf, int B, int 
       }
     }
   }
-  __half *o = buf + (((size_t)b * H + y) * W + x) * cstride + g * 8;
+  __half *o = buf + (size_t)pr_index(b, y, x, H, W) * cstride + g * 8;
   *reinterpret_cast<uint4 *>(o + c) = *reinterpret_cast<uint4 *>(m1);
   *reinterpret_cast<uint4 *>(o + 2 * c) = *reinterpret_cast<uint4 *>(m2);
   *reinterpret_cast<uint4 *>(o + 3 * c) = *reinterpret_cast<uint4 *>(m3);

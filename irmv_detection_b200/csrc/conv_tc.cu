@@ -248,17 +248,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
         const uint32_t bimg = (uint32_t)(((uint64_t)t * mul_oh) >> 34);             // t / OH
         const int oy = (int)t - (int)bimg * OH;
         const int iy0 = oy * cstr, ix0 = ox * cstr;
-        const int full = ((int)bimg * H + iy0) * W + ix0;
-        const int half = ((int)bimg * Hh + (iy0 >> 1)) * Wh + (ix0 >> 1);
+        const int full = ((int)bimg * (H + 1) + 1 + iy0) * (W + 1) + ix0;                       // PR layout
+        const int half = ((int)bimg * (Hh + 1) + 1 + (iy0 >> 1)) * (Wh + 1) + (ix0 >> 1);
         off0[i] = (up0 ? half : full) * cs0;
         off1[i] = two ? (up1 ? half : full) * cs1 : 0;
-        // taps inside the image (k = 1: the pixel itself; k = 3, pad 1: closed form)
-        uint32_t mk = 1u;
-        if (k3) {
-          const uint32_t xb = (ix0 >= 1 ? 1u : 0u) | 2u | (ix0 + 1 < W ? 4u : 0u);
-          mk = (iy0 >= 1 ? xb : 0u) | (xb << 3) | (iy0 + 1 < H ? xb << 6 : 0u);
-        }
-        mask[i] = (m < M && nozero) ? mk : 0u;
+        // the PR layout's zero row/column make every tap of a real output pixel readable
+        mask[i] = (m < M && nozero) ? (k3 ? 0x1FFu : 1u) : 0u;
       }
       if (tr) p.trace[itp * 8 + 1] = clock64();
       for (int kb = 0; kb < KB; ++kb) {
@@ -304,8 +299,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
       if (tr) p.trace[it * 8 + 6] = clock64();
       const int m = tile * BM + row;
       const bool mok = m < a.M;
-      __half *orow = p.out + (size_t)(mok ? m : 0) * p.out_cstride + p.out_coff;
-      const __half *rrow = p.res ? p.res + (size_t)(mok ? m : 0) * p.res_cstride + p.res_coff : nullptr;
+      size_t opix = 0;
+      if (mok) {
+        const uint32_t t = (uint32_t)(((uint64_t)(uint32_t)m * a.mul_ow) >> 34);
+        const uint32_t bimg = (uint32_t)(((uint64_t)t * a.mul_oh) >> 34);
+        opix = (size_t)pr_index((int)bimg, (int)t - (int)bimg * p.OH, m - (int)t * p.OW, p.OH, p.OW);
+      }
+      __half *orow = p.out + opix * p.out_cstride + p.out_coff;
+      const __half *rrow = p.res ? p.res + opix * p.res_cstride + p.res_coff : nullptr;
       const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * npad);
       for (int c0 = 0; c0 < npad; c0 += 16) {
         uint32_t r[16];

@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(256) decode_kernel(HeadPtrs h, int B, int nc, 
   if (a < 6400) { scale = 0; local = a; hw = 80; stride = 8.0f; }
   else if (a < 8000) { scale = 1; local = a - 6400; hw = 40; stride = 16.0f; }
   else { scale = 2; local = a - 8000; hw = 20; stride = 32.0f; }
-  const size_t pix = (size_t)b * hw * hw + local;
+  const size_t pix = h.padded ? (size_t)pr_index(b, local / hw, local % hw, hw, hw) : (size_t)b * hw * hw + local;
 
   // DFL expectation of this lane's side
   const uint4 *bp = reinterpret_cast<const uint4 *>(h.box[scale] + pix * 64 + lane4 * 16);

@@ -40,9 +40,10 @@ struct HostConv {   // one GEMM as the kernels see it (possibly several referenc
   std::vector<int> seg_c;            // channels per input segment (sum = cin_eff)
   std::vector<__half> w_plain;       // [npad][kpad]
   std::vector<__half> w_tiled;       // [kpad/64][npad][64] swizzled
+  std::vector<__half> w_raster;      // [k*k][cin/8][npad][8] unswizzled (raster kernel)
   std::vector<float> bias;           // [npad]
   std::vector<int32_t> ktab;         // [kpad/8]
-  __half *d_plain = nullptr, *d_tiled = nullptr;
+  __half *d_plain = nullptr, *d_tiled = nullptr, *d_raster = nullptr;
   float *d_bias = nullptr;
   int32_t *d_ktab = nullptr;
 };
@@ -121,6 +122,17 @@ HostConv make_conv(const std::vector<const FileConv *> &parts, int cin_pad,
         h.w_tiled[((size_t)kb * h.npad + n) * 64 + chunk * 8 + (kk & 7)] =
             h.w_plain[(size_t)n * h.kpad + kb * 64 + kk];
       }
+  // raster-kernel image: [tap][cin/8][npad][8]
+  {
+    const int taps = h.k * h.k, nch = cin_pad / 8;
+    h.w_raster.assign((size_t)taps * nch * h.npad * 8, __float2half(0.f));
+    for (int t = 0; t < taps; ++t)
+      for (int c = 0; c < nch; ++c)
+        for (int n = 0; n < h.npad; ++n)
+          for (int e = 0; e < 8; ++e)
+            h.w_raster[(((size_t)t * nch + c) * h.npad + n) * 8 + e] =
+                h.w_plain[(size_t)n * h.kpad + (size_t)t * cin_pad + c * 8 + e];
+  }
   // chunk table (one entry per 8-channel chunk of K): {tap, segment, channel offset}; the
   // device tap table is derived per layer instance in add_conv (it needs W and the pixel strides)
   h.ktab.assign((size_t)(h.kpad / 8) * 3, -1);
@@ -141,6 +153,7 @@ bool upload(HostConv &h) {
   };
   return up((void **)&h.d_plain, h.w_plain.data(), h.w_plain.size() * 2) &&
          up((void **)&h.d_tiled, h.w_tiled.data(), h.w_tiled.size() * 2) &&
+         up((void **)&h.d_raster, h.w_raster.data(), h.w_raster.size() * 2) &&
          up((void **)&h.d_bias, h.bias.data(), h.bias.size() * 4);
 }
 
@@ -152,6 +165,7 @@ struct Tensor {
 struct Op {
   enum Kind { CONV, POOL } kind = CONV;
   ConvParams cp{};
+  bool raster = false;       // raster (halo-tile) kernel, else the per-tap gather kernel
   __half *pool_buf = nullptr;
   int pH = 0, pW = 0, pC = 0, pStride = 0;
 };
@@ -248,7 +262,11 @@ bool lane_alloc(Lane &ln, void **p, size_t bytes) {
 
 bool new_tensor(Lane &ln, int S, int H, int W, int C, Tensor &t, const char *tap = nullptr) {
   t.H = H; t.W = W; t.C = C;
-  if (!lane_alloc(ln, (void **)&t.p, (size_t)S * H * W * C * 2)) return false;
+  // PR layout, zeroed, with 8 zero guard pixels in front and behind: the top-left tap of pixel
+  // (0,0) of image 0 is raster index -1
+  __half *base = nullptr;
+  if (!lane_alloc(ln, (void **)&base, ((size_t)pr_pixels(S, H, W) + 16) * C * 2)) return false;
+  t.p = base + (size_t)8 * C;
   if (tap) ln.taps[tap] = t;
   return true;
 }
@@ -273,7 +291,7 @@ void add_conv(irmv_engine *e, Lane &ln, HostConv &hc, std::vector<SegRef> in, in
   p.OH = (H + 2 * p.pad - hc.k) / hc.stride + 1;
   p.OW = (W + 2 * p.pad - hc.k) / hc.stride + 1;
   p.cin = cin; p.cout = hc.cout; p.npad = hc.npad; p.K = hc.K; p.kpad = hc.kpad; p.act = hc.act;
-  p.w_plain = hc.d_plain; p.w_tiled = hc.d_tiled; p.bias = hc.d_bias;
+  p.w_plain = hc.d_plain; p.w_tiled = hc.d_tiled; p.w_raster = hc.d_raster; p.bias = hc.d_bias;
   {
     // device tap table for this layer instance
     const int nq = hc.kpad / 8;
@@ -284,7 +302,7 @@ void add_conv(irmv_engine *e, Lane &ln, HostConv &hc, std::vector<SegRef> in, in
       const ConvSeg &g = p.seg[sg];
       int ky = tap / hc.k, kx = tap % hc.k;
       int delta = g.coff + off;
-      if (!g.up) delta += ((ky - p.pad) * W + (kx - p.pad)) * g.cstride;
+      if (!g.up) delta += ((ky - p.pad) * (W + 1) + (kx - p.pad)) * g.cstride;   // PR layout pitch
       tab[q * 2 + 0] = delta;
       tab[q * 2 + 1] = ktab_meta(tap, sg, 1);
     }
@@ -298,6 +316,7 @@ void add_conv(irmv_engine *e, Lane &ln, HostConv &hc, std::vector<SegRef> in, in
   p.res = res ? res->p : nullptr; p.res_cstride = res ? res->C : 0; p.res_coff = res_coff;
   p.sync_mode = 0;
   p.trace = nullptr; p.trace_cap = 0;
+  op.raster = conv_raster_fits(p) && !getenv("IRMV_NO_RASTER");
   ln.ops.push_back(op);
 }
 
@@ -380,6 +399,7 @@ bool build_lane(irmv_engine *e, Lane &ln) {
     add_conv(e, ln, *e->convs[ci++], {{&hc, 0, 64, 0}}, hw[i], hw[i], co, 0);
     ln.heads.box[i] = bo.p;
     ln.heads.cls[i] = co.p;
+    ln.heads.padded = 1;
   }
   if (ci != e->convs.size()) { set_error("internal: conv count mismatch"); return false; }
   // decode / NMS scratch and outputs
@@ -423,11 +443,23 @@ int issue_replay(irmv_engine *e, Lane &ln, int n, cudaStream_t st, int *launches
       ConvParams p = op.cp;
       p.B = n;
       if (e->cfg.conv_impl == IRMV_CONV_DIRECT) IRMV_CUDA(launch_conv_direct(p, st));
+      else if (op.raster) IRMV_CUDA(launch_conv_raster(p, e->num_sms, st));
       else IRMV_CUDA(launch_conv_tc(p, e->num_sms, st));
     } else {
       IRMV_CUDA(launch_sppf_pool(op.pool_buf, n, op.pH, op.pW, op.pStride, op.pC, st));
     }
     ++cnt;
+    if (getenv("IRMV_SYNC_EACH")) {
+      cudaError_t ce = cudaStreamSynchronize(st);
+      if (ce != cudaSuccess) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "op %d (%s k=%d s=%d cin=%d cout=%d H=%d) failed: %s", cnt - 2,
+                 op.kind == Op::POOL ? "pool" : (op.raster ? "raster" : "gather"), op.cp.k, op.cp.stride, op.cp.cin,
+                 op.cp.cout, op.cp.H, cudaGetErrorString(ce));
+        set_error(buf);
+        return 1;
+      }
+    }
   }
   if (mark(2)) return 1;
   IRMV_CUDA(launch_decode(ln.heads, n, e->nc, e->cfg.score_thr, ln.nms, nullptr, st)); ++cnt;
@@ -644,7 +676,7 @@ void irmv_engine_destroy(irmv_engine *e) {
     for (auto ev : ln.stage_ev) if (ev) cudaEventDestroy(ev);
   }
   for (auto &c : e->convs) {
-    cudaFree(c->d_plain); cudaFree(c->d_tiled); cudaFree(c->d_bias);
+    cudaFree(c->d_plain); cudaFree(c->d_tiled); cudaFree(c->d_raster); cudaFree(c->d_bias);
   }
   for (auto s : e->slots_host) cudaFreeHost(s);
   cudaFree(e->slot_dev);
@@ -759,14 +791,27 @@ int irmv_engine_read_tensor(irmv_engine *e, const char *name, void *dst, int64_t
   auto it = ln.taps.find(name);
   if (it == ln.taps.end()) { set_error(std::string("no tensor named ") + name); return 2; }
   const Tensor &t = it->second;
-  int es = strcmp(name, "boxes") == 0 ? 4 : 2;
+  const bool is_boxes = strcmp(name, "boxes") == 0;
+  int es = is_boxes ? 4 : 2;
   int nb = e->last_n < e->S ? (e->last_n > 0 ? e->last_n : 1) : e->S;
   dims[0] = nb; dims[1] = t.H; dims[2] = t.W; dims[3] = t.C; dims[4] = es;
   int64_t bytes = (int64_t)nb * t.H * t.W * t.C * es;
   if (dst) {
     if (bytes > cap) { set_error("destination too small"); return 3; }
     IRMV_CUDA(cudaDeviceSynchronize());
-    IRMV_CUDA(cudaMemcpy(dst, t.p, (size_t)bytes, cudaMemcpyDeviceToHost));
+    if (is_boxes) {
+      IRMV_CUDA(cudaMemcpy(dst, t.p, (size_t)bytes, cudaMemcpyDeviceToHost));
+    } else {
+      // device tensors are in the padded raster layout: copy out and drop the zero row/column
+      const size_t px = (size_t)pr_pixels(nb, t.H, t.W);
+      std::vector<uint16_t> tmp(px * t.C);
+      IRMV_CUDA(cudaMemcpy(tmp.data(), t.p, tmp.size() * 2, cudaMemcpyDeviceToHost));
+      uint16_t *o = static_cast<uint16_t *>(dst);
+      for (int b = 0; b < nb; ++b)
+        for (int y = 0; y < t.H; ++y)
+          memcpy(o + (((size_t)b * t.H + y) * t.W) * t.C, tmp.data() + (size_t)pr_index(b, y, 0, t.H, t.W) * t.C,
+                 (size_t)t.W * t.C * 2);
+    }
   }
   return 0;
 }
@@ -869,11 +914,12 @@ int irmv_preprocess(const uint8_t *src, int n, int src_w, int src_h, int chan_or
   if (resize_mode == IRMV_RESIZE_LETTERBOX) { set_error("resize_mode LETTERBOX is not built yet"); return 2; }
   IRMV_CUDA(cudaSetDevice(device));
   const size_t fb = (size_t)src_w * src_h * (chan_order >= 2 ? 1 : 3);
-  const size_t ob = (size_t)kNet * kNet * kInC * 2;
+  const size_t ob = (size_t)pr_pixels(n, kNet, kNet) * kInC * 2;     // kernel writes the PR layout
   uint8_t *ds = nullptr, *dr = nullptr;
   __half *dd = nullptr;
   IRMV_CUDA(cudaMalloc((void **)&ds, fb * n));
-  IRMV_CUDA(cudaMalloc((void **)&dd, ob * n));
+  IRMV_CUDA(cudaMalloc((void **)&dd, ob));
+  IRMV_CUDA(cudaMemset(dd, 0, ob));
   if (rotated) IRMV_CUDA(cudaMalloc((void **)&dr, (size_t)src_w * src_h * 3 * n));
   IRMV_CUDA(cudaMemcpy(ds, src, fb * n, cudaMemcpyHostToDevice));
   PreprocessParams pp{};
@@ -881,10 +927,15 @@ int irmv_preprocess(const uint8_t *src, int n, int src_w, int src_h, int chan_or
   pp.chan_order = chan_order; pp.rotate180 = rotate180; pp.resize_mode = resize_mode; pp.quantize_u8 = quantize_u8;
   cudaError_t ce = launch_preprocess(pp, 0);
   if (ce == cudaSuccess) ce = cudaDeviceSynchronize();
-  if (ce == cudaSuccess) ce = cudaMemcpy(dst, dd, ob * n, cudaMemcpyDeviceToHost);
+  std::vector<uint16_t> tmp(ob / 2);
+  if (ce == cudaSuccess) ce = cudaMemcpy(tmp.data(), dd, ob, cudaMemcpyDeviceToHost);
   if (ce == cudaSuccess && rotated) ce = cudaMemcpy(rotated, dr, (size_t)src_w * src_h * 3 * n, cudaMemcpyDeviceToHost);
   cudaFree(ds); cudaFree(dd); if (dr) cudaFree(dr);
   IRMV_CUDA(ce);
+  for (int b = 0; b < n; ++b)
+    for (int y = 0; y < kNet; ++y)
+      memcpy(dst + (((size_t)b * kNet + y) * kNet) * kInC, tmp.data() + (size_t)pr_index(b, y, 0, kNet, kNet) * kInC,
+             (size_t)kNet * kInC * 2);
   return 0;
 }
 
@@ -951,6 +1002,7 @@ int irmv_decode(const uint16_t *box, const uint16_t *cls, int n, float *boxes, f
     }
     h.box[s] = db[s]; h.cls[s] = dc[s];
   }
+  h.padded = 0;
   cudaError_t ce = launch_decode(h, n, nc, 2.0f /* no candidates */, sc, dscores, 0);
   if (ce == cudaSuccess) ce = cudaDeviceSynchronize();
   if (ce == cudaSuccess) ce = cudaMemcpy(boxes, sc.boxes, (size_t)n * kNumAnchors * 16, cudaMemcpyDeviceToHost);

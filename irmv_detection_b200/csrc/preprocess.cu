@@ -176,7 +176,7 @@ preprocess_kernel(PreprocessParams p, int rows_cap, int pitch_s) {
     o.x = *reinterpret_cast<uint32_t *>(&h01);
     o.y = *reinterpret_cast<uint32_t *>(&h23);
     o.z = 0u; o.w = 0u;
-    size_t pix_idx = ((size_t)n * kNet + oy) * kNet + ox;
+    size_t pix_idx = (size_t)pr_index(n, oy, ox, kNet, kNet);
     *reinterpret_cast<uint4 *>(p.dst + pix_idx * kInC) = o;
   }
 }
