@@ -895,7 +895,7 @@ int irmv_engine_trace_conv(irmv_engine *e, int op_index, int nframes, long long 
   if (const char *dbg = getenv("IRMV_TC_DEBUG")) p.sync_mode = atoi(dbg);
   cudaDeviceSynchronize();
   cudaEventRecord(ln.stage_ev[0], ln.stream);
-  launch_conv_tc(p, e->num_sms, ln.stream);
+  if (op->raster) launch_conv_raster(p, e->num_sms, ln.stream); else launch_conv_tc(p, e->num_sms, ln.stream);
   cudaEventRecord(ln.stage_ev[1], ln.stream);
   cudaError_t ce = cudaStreamSynchronize(ln.stream);
   if (kernel_ms) cudaEventElapsedTime(kernel_ms, ln.stage_ev[0], ln.stage_ev[1]);
@@ -903,6 +903,7 @@ int irmv_engine_trace_conv(irmv_engine *e, int op_index, int nframes, long long 
   cudaFree(d);
   if (ce != cudaSuccess) { set_error(cudaGetErrorString(ce)); return -1; }
   int M = p.B * p.OH * p.OW, tiles = (M + 127) / 128;
+  if (op->raster) return cap_tiles < 12 ? cap_tiles : 12;
   int per_cta = (tiles + (tiles < e->num_sms ? tiles : e->num_sms) - 1) / (tiles < e->num_sms ? tiles : e->num_sms);
   return per_cta < cap_tiles ? per_cta : cap_tiles;
 }

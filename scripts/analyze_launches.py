@@ -1,0 +1,55 @@
+"""Per-layer table from an ncu launch list (gpu__time_duration) of scripts/profile_replay.py."""
+import csv
+import re
+import sys
+
+
+def layers():
+    def c2f(name, c1, c2, n, hw):
+        c = c2 // 2
+        out = [(f"{name}.cv1", hw, c1, 2 * c, 1, 1)]
+        for i in range(n):
+            out += [(f"{name}.m{i}.cv1", hw, c, c, 3, 1), (f"{name}.m{i}.cv2", hw, c, c, 3, 1)]
+        out.append((f"{name}.cv2", hw, (2 + n) * c, c2, 1, 1))
+        return out
+    d = [("m0", 320, 8, 16, 3, 2), ("m1", 160, 16, 32, 3, 2)] + c2f("m2", 32, 32, 1, 160)
+    d += [("m3", 80, 32, 64, 3, 2)] + c2f("m4", 64, 64, 2, 80) + [("m5", 40, 64, 128, 3, 2)] + c2f("m6", 128, 128, 2, 40)
+    d += [("m7", 20, 128, 256, 3, 2)] + c2f("m8", 256, 256, 1, 20) + [("m9.cv1", 20, 256, 128, 1, 1), ("POOL", 20, 0, 0, 0, 0), ("m9.cv2", 20, 512, 256, 1, 1)]
+    d += c2f("m12", 384, 128, 1, 40) + c2f("m15", 192, 64, 1, 80) + [("m16", 40, 64, 64, 3, 2)] + c2f("m18", 192, 128, 1, 40)
+    d += [("m19", 20, 128, 128, 3, 2)] + c2f("m21", 384, 256, 1, 20)
+    for i, (hw, ch) in enumerate(((80, 64), (40, 128), (20, 256))):
+        d += [(f"h{i}.01", hw, ch, 128, 3, 1), (f"h{i}.box1", hw, 64, 64, 3, 1), (f"h{i}.box2", hw, 64, 64, 1, 1),
+              (f"h{i}.cls1", hw, 64, 64, 3, 1), (f"h{i}.cls2", hw, 64, 16, 1, 1)]
+    return d
+
+
+def main():
+    path, B = sys.argv[1], int(sys.argv[2])
+    with open(path) as f:
+        lines = [l for l in f if not l.startswith("==")]
+    rows = list(csv.DictReader(lines))
+    names = [(r["Kernel Name"], float(r["Metric Value"])) for r in rows]
+    idx = [i for i, n in enumerate(names) if "preprocess_kernel" in n[0]]
+    seq = names[idx[-1]:idx[-1] + 66]
+    out, tot = [], 0.0
+    for (n, v), d in zip(seq[1:62], layers()):
+        name, hw, cin, cout, k, s = d
+        kern = re.sub(r"\(.*", "", n).split("::")[-1].replace("_kernel", "")
+        if name == "POOL":
+            out.append((name, kern, v, 0.0, 0.0))
+            tot += v
+            continue
+        M = B * hw * hw
+        fl = 2.0 * M * k * k * cin * cout
+        io = (B * (hw * s) ** 2 * cin + M * cout) * 2.0
+        out.append((name, kern, v, fl / v / 1e3, io / v))
+        tot += v
+    print(f"conv+pool total {tot/1e3:.1f} us for {B} frames = {tot/1e3/B:.2f} us/frame; other:",
+          [(re.sub(r'\(.*', '', n).split('::')[-1], round(v / 1e3, 1)) for n, v in [seq[0]] + seq[62:]])
+    print(f"{'layer':12s} {'kernel':12s} {'us':>8s} {'share':>6s} {'TFLOP/s':>8s} {'GB/s(in+out)':>12s}")
+    for name, kern, v, tf, gb in sorted(out, key=lambda r: -r[2]):
+        print(f"{name:12s} {kern:12s} {v/1e3:8.1f} {100*v/tot:5.1f}% {tf:8.1f} {gb:12.1f}")
+
+
+if __name__ == "__main__":
+    main()

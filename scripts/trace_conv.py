@@ -36,6 +36,7 @@ def main():
         t0 = t[0, 0]
         print(f"== op {op}: kernel {ms.value*1e3:.1f} us, tiles/CTA {k}")
         names = ["start", "pre-wait", "post-wait", "issued", "mma-first", "mma-last", "epi-start", "epi-end"]
+        names = ["ld-start", "ld-gotslot", "ld-issued", "mma-wait", "mma-go", "mma-issued", "epi-start", "epi-end"] if os.environ.get("RASTER") else names
         for i in list(range(min(k, 6))) + list(range(max(6, k - 3), k)):
             print(f"  tile {i:3d} " + " ".join(f"{nm}={int(v - t0):7d}" for nm, v in zip(names, t[i])))
         kb = buf[cap:cap + 16].astype(np.float64)
