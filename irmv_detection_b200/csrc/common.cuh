@@ -16,19 +16,24 @@ constexpr int kClsPad = 16;         // class-logit channels padded 14 -> 16
 constexpr int kMaxCand = 4096;      // pre-NMS top-k (oracle/nms_ref.py MAX_CAND)
 
 // ---------------------------------------------------------------- activation layout
-// Every NHWC activation is stored as a zero-padded raster ("PR" layout): row pitch Wp = W + 1
+// Activations are channel-blocked: a tensor of C channels is C/8 PLANES, each plane holding 8
+// channels (16 bytes) per pixel: plane[q][8].  A channel slice or a concatenation is a list of
+// planes, a tile of one plane is a contiguous byte range (one TMA bulk copy), and 32 lanes storing
+// 32 consecutive pixels of a plane write 512 contiguous bytes.
+// Inside a plane the pixels form a zero-padded raster ("PR" layout): row pitch Wp = W + 1
 // (one zero pixel after each row -- it is the right neighbour of x = W-1 and the left neighbour of
 // x = 0 of the next row), H + 1 rows per image (one zero row before each image -- it is the bottom
 // neighbour of the previous image and the top neighbour of this one) and one trailing zero row.
 // A 3x3 / pad-1 tap is then a constant raster offset (ky-1)*Wp + (kx-1) with no bounds test, which
 // is what lets the raster convolution kernel feed all 9 taps from one shared-memory halo tile.
-// Buffers carry pr_guard() zero pixels in front and behind so halo reads never leave them.
+// Planes carry kGuardFront / kGuardBack zero pixels so halo tiles never leave the allocation.
 __host__ __device__ inline int pr_wp(int W) { return W + 1; }
 __host__ __device__ inline long long pr_pixels(int B, int H, int W) { return ((long long)B * (H + 1) + 1) * (W + 1); }
 __host__ __device__ inline long long pr_index(int b, int y, int x, int H, int W) {
   return ((long long)b * (H + 1) + 1 + y) * (W + 1) + x;
 }
-__host__ __device__ inline int pr_guard(int W) { return W + 1 + 8; }
+constexpr int kGuardFront = 384;    // >= Wp + 1 of the widest raster-kernel layer (320 + 2)
+constexpr int kGuardBack = 1024;    // >= 512-row tile overhang + Wp + 1
 
 void set_error(const std::string &msg);
 bool cuda_ok(cudaError_t e, const char *what, const char *file, int line);
@@ -51,11 +56,10 @@ cudaError_t launch_preprocess(const PreprocessParams &p, cudaStream_t s);
 
 // ---------------------------------------------------------------- convolution
 struct ConvSeg {
-  const __half *ptr;  // NHWC tensor base
-  int cstride;        // channels per pixel in the buffer
-  int coff;           // first channel of the slice read
-  int c;              // channels read (multiple of 8)
-  int up;             // 1: tensor is half resolution, read with nearest 2x upsampling
+  const __half *ptr;    // pixel 0 of the first plane of the slice read
+  long long pstride;    // halfs between consecutive planes
+  int c;                // channels read (multiple of 8)
+  int up;               // 1: tensor is half resolution, read with nearest 2x upsampling
 };
 
 struct ConvParams {
@@ -73,12 +77,12 @@ struct ConvParams {
   const __half *w_plain;   // [npad][kpad], k = (ky*k+kx)*cin + c          (direct kernel)
   const __half *w_tiled;   // [kpad/64][npad][64] with the 128B swizzle     (tcgen05 gather kernel)
   const __half *w_raster;  // [k*k][cin/8][npad][8]                          (tcgen05 raster kernel)
-  const int32_t *ktab;     // [kpad/8][2] {element offset from the row's base pixel, meta} (tcgen05 kernel)
+  const int32_t *ktab;     // [kpad/8][2] {pixel offset of the tap, meta} (tcgen05 gather kernel)
   const float *bias;       // [npad]
-  __half *out;
-  int out_cstride, out_coff;
-  const __half *res;       // residual added after the activation, same grid as out; may be null
-  int res_cstride, res_coff;
+  __half *out;             // pixel 0 of the first output plane
+  long long out_pstride;
+  const __half *res;       // residual added after the activation (same grid as out); may be null
+  long long res_pstride;
   int sync_mode;           // tcgen05 producer hand-off: 0 = cp.async-tracked mbarrier, 1 = wait+fence
   long long *trace;        // debug: CTA 0 writes per-tile clock64 stamps [tile][8]; null in production
   int trace_cap;
@@ -92,23 +96,24 @@ size_t conv_tc_smem_bytes(const ConvParams &p, int *stages, int *b_resident);
 bool conv_raster_fits(const ConvParams &p);
 cudaError_t launch_conv_raster(const ConvParams &p, int num_sms, cudaStream_t s);
 
-// ktab meta: bits 0-3 tap bit index (ky*k+kx), 4 segment, 5 valid.  The element offset is
-// ((ky-pad)*W + (kx-pad))*cstride + coff + choff relative to pixel (oy*stride, ox*stride); for an
-// upsample-on-read segment (1x1 convs only) it is just coff + choff.
-__host__ __device__ inline int32_t ktab_meta(int tap, int seg, int valid) {
-  return tap | (seg << 4) | (valid << 5);
+// ktab meta: bits 0-3 tap index (ky*k+kx), 4 segment, 5 valid, 8.. plane index inside the segment.
+// The pixel offset is (ky-pad)*Wp + (kx-pad) relative to pixel (oy*stride, ox*stride); 0 for an
+// upsample-on-read segment (1x1 convs only).
+__host__ __device__ inline int32_t ktab_meta(int tap, int seg, int valid, int plane) {
+  return tap | (seg << 4) | (valid << 5) | (plane << 8);
 }
 
 // ---------------------------------------------------------------- SPPF pooling
-// in: PR-layout [B][H][W] slice of c channels at coff; writes maxpool5, maxpool5^2, maxpool5^3 to the
-// three following channel slices of the same buffer (ultralytics SPPF).
-cudaError_t launch_sppf_pool(__half *buf, int B, int H, int W, int cstride, int c, cudaStream_t s);
+// in: planes [0, c/8) of `buf`; writes maxpool5, maxpool5^2, maxpool5^3 to the three following
+// groups of c/8 planes of the same tensor (ultralytics SPPF).
+cudaError_t launch_sppf_pool(__half *buf, int B, int H, int W, long long pstride, int c, cudaStream_t s);
 
 // ---------------------------------------------------------------- decode + NMS
 struct HeadPtrs {
-  const __half *box[3];   // PR layout of [B][hw][hw][64]
-  const __half *cls[3];   // PR layout of [B][hw][hw][16]
-  int padded;             // 1: PR layout (engine); 0: dense [B][hw*hw][C] (irmv_decode stage entry)
+  const __half *box[3];   // 8 planes of [B][hw][hw] (PR layout)
+  const __half *cls[3];   // 2 planes
+  long long box_ps[3], cls_ps[3];   // plane strides (halfs)
+  int padded;             // 1: planar PR layout (engine); 0: dense [B][hw*hw][C] (irmv_decode stage entry)
 };
 struct DetOut {            // per frame, device
   int32_t *num_dets;      // [B]

@@ -36,9 +36,9 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(ConvParams p) {
         const ConvSeg sg = p.seg[s];
         int hs = sg.up ? p.H >> 1 : p.H, ws = sg.up ? p.W >> 1 : p.W;
         int sy = sg.up ? iy >> 1 : iy, sx = sg.up ? ix >> 1 : ix;
-        const __half *ip = sg.ptr + (size_t)pr_index(b, sy, sx, hs, ws) * sg.cstride + sg.coff;
+        const __half *ip = sg.ptr + (size_t)pr_index(b, sy, sx, hs, ws) * 8;
         for (int c = 0; c < sg.c; c += 8) {
-          uint4 iv = *reinterpret_cast<const uint4 *>(ip + c);
+          uint4 iv = *reinterpret_cast<const uint4 *>(ip + (size_t)(c >> 3) * sg.pstride);
           const __half2 *ih = reinterpret_cast<const __half2 *>(&iv);
           float xin[8];
 #pragma unroll
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(ConvParams p) {
   float r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const size_t opix = (size_t)pr_index(b, oy, ox, p.OH, p.OW);
   if (p.res) {
-    uint4 rv = *reinterpret_cast<const uint4 *>(p.res + opix * p.res_cstride + p.res_coff + g * 8);
+    uint4 rv = *reinterpret_cast<const uint4 *>(p.res + (size_t)g * p.res_pstride + opix * 8);
     const __half2 *rh = reinterpret_cast<const __half2 *>(&rv);
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(ConvParams p) {
     float v = p.act ? silu(acc[j]) : acc[j];
     outv[j] = __float2half_rn(v + r[j]);
   }
-  *reinterpret_cast<uint4 *>(p.out + opix * p.out_cstride + p.out_coff + g * 8) =
+  *reinterpret_cast<uint4 *>(p.out + (size_t)g * p.out_pstride + opix * 8) =
       *reinterpret_cast<uint4 *>(outv);
 }
 
@@ -99,7 +99,7 @@ namespace {
 // -inf).  One thread: one pixel x 8 channels; separable max would cut reads further, but the
 // whole tensor is 20x20x128 per frame (0.1 MB) and lives in L2.
 __global__ void __launch_bounds__(128) sppf_pool_kernel(__half *buf, int B, int H, int W,
-                                                        int cstride, int c) {
+                                                        long long pstride, int c) {
   int groups = c / 8;
   long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   long long total = (long long)B * H * W * groups;
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(128) sppf_pool_kernel(__half *buf, int B, int 
     for (int dx = -6; dx <= 6; ++dx) {
       int xx = x + dx;
       if (xx < 0 || xx >= W) continue;
-      uint4 v = *reinterpret_cast<const uint4 *>(buf + (size_t)pr_index(b, yy, xx, H, W) * cstride + g * 8);
+      uint4 v = *reinterpret_cast<const uint4 *>(buf + (size_t)g * pstride + (size_t)pr_index(b, yy, xx, H, W) * 8);
       const __half2 *h = reinterpret_cast<const __half2 *>(&v);
       int r = max(abs(dy), abs(dx));
 #pragma unroll
@@ -128,17 +128,18 @@ __global__ void __launch_bounds__(128) sppf_pool_kernel(__half *buf, int B, int 
       }
     }
   }
-  __half *o = buf + (size_t)pr_index(b, y, x, H, W) * cstride + g * 8;
-  *reinterpret_cast<uint4 *>(o + c) = *reinterpret_cast<uint4 *>(m1);
-  *reinterpret_cast<uint4 *>(o + 2 * c) = *reinterpret_cast<uint4 *>(m2);
-  *reinterpret_cast<uint4 *>(o + 3 * c) = *reinterpret_cast<uint4 *>(m3);
+  __half *o = buf + (size_t)g * pstride + (size_t)pr_index(b, y, x, H, W) * 8;
+  const size_t grp = (size_t)(c / 8) * pstride;
+  *reinterpret_cast<uint4 *>(o + grp) = *reinterpret_cast<uint4 *>(m1);
+  *reinterpret_cast<uint4 *>(o + 2 * grp) = *reinterpret_cast<uint4 *>(m2);
+  *reinterpret_cast<uint4 *>(o + 3 * grp) = *reinterpret_cast<uint4 *>(m3);
 }
 }  // namespace
 
-cudaError_t launch_sppf_pool(__half *buf, int B, int H, int W, int cstride, int c, cudaStream_t s) {
+cudaError_t launch_sppf_pool(__half *buf, int B, int H, int W, long long pstride, int c, cudaStream_t s) {
   long long total = (long long)B * H * W * (c / 8);
   int blocks = (int)((total + 127) / 128);
-  sppf_pool_kernel<<<blocks, 128, 0, s>>>(buf, B, H, W, cstride, c);
+  sppf_pool_kernel<<<blocks, 128, 0, s>>>(buf, B, H, W, pstride, c);
   return cudaGetLastError();
 }
 

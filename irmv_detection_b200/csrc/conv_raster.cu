@@ -9,14 +9,16 @@
 // (TM + 2*Wp + 2 of them), and all nine taps are the same shared-memory tile read at nine
 // different row offsets:
 //
-//   loader warps 0-7   copy the halo range once per tile (cp.async.cg, fully coalesced) into
-//                      channel-chunk planes  [cin/8][PP pixels][8 halfs]  -- the K-major, unswizzled
-//                      UMMA operand layout, in which a tap shift is just +16 bytes per pixel on
-//                      the descriptor's start address.  One mbarrier hand-off per TILE.
-//   warp 13            loads the whole weight set once (TMA bulk copy), resident for the CTA.
-//   warp 12            issues R * taps * cin/16 tcgen05.mma per tile back to back.
-//   warps 8-11         epilogue out of double-buffered TMEM: bias, SiLU, residual, FP16 store;
-//                      padding pixels are skipped so the zero border is preserved.
+//   warp 8 (one lane)  TMA producer: the activation planes are [pixel][8 channels] arrays, so the
+//                      halo range of one plane is ONE contiguous byte range and one
+//                      cp.async.bulk per plane fills the tile  [cin/8][PP pixels][8 halfs]  -- the
+//                      K-major, unswizzled UMMA operand layout, in which a tap shift is just
+//                      +16 bytes per pixel on the descriptor's start address.  One mbarrier
+//                      (expect_tx) hand-off per TILE; the weights are loaded once the same way.
+//   warp 9             issues R * taps * cin/16 tcgen05.mma per tile back to back.
+//   warps 0-7          epilogue out of double-buffered TMEM: bias, SiLU, residual, FP16; a warp
+//                      stores 32 consecutive pixels of one plane = 512 contiguous bytes; padding
+//                      pixels are skipped so the zero border is preserved.
 //
 // Against the per-tap gather kernel this cuts L2->SM traffic and load instructions ~4x for 3x3
 // layers and the number of producer/consumer hand-offs 9x.
@@ -25,10 +27,10 @@
 namespace irmv {
 namespace {
 
-constexpr int NLOAD = 256;                  // warps 0-7
-constexpr int EPI_WARP0 = 8;
-constexpr int MMA_WARP = 12;
-constexpr int NTHREADS = 14 * 32;
+constexpr int NEPI_WARPS = 8;               // warps 0-7 (TMEM lane quarter = warp % 4)
+constexpr int TMA_WARP = 8;
+constexpr int MMA_WARP = 9;
+constexpr int NTHREADS = 10 * 32;
 constexpr int MAX_STAGES = 4;
 constexpr int SMEM_BUDGET = 226 * 1024;     // 232448 B is the opt-in maximum per CTA
 
@@ -150,12 +152,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_raster_kernel(const __grid_c
   for (int i = tid; i < npad; i += NTHREADS) s_bias[i] = p.bias[i];
   if (tid == 0) {
     for (int s = 0; s < a.stages; ++s) {
-      mbar_init(&bars->full[s], NLOAD);
+      mbar_init(&bars->full[s], 1);
       mbar_init(&bars->empty[s], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->tmem_full[i], 1);
-      mbar_init(&bars->tmem_empty[i], 4);
+      mbar_init(&bars->tmem_empty[i], NEPI_WARPS);
     }
     mbar_init(&bars->bfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -170,100 +172,99 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_raster_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
-  if (warp < EPI_WARP0) {
-    // ===================================================================== halo loaders
-    int s = 0, itl = 0;
-    uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++itl) {
-      const bool tr = p.trace && blockIdx.x == 0 && tid == 0 && itl < p.trace_cap;
-      if (tr) p.trace[itl * 8 + 0] = clock64();
-      const long long qlo = (long long)a.q_begin + (long long)tile * a.TM - a.halo_front;
-      mbar_wait_warp(&bars->empty[s], ph ^ 1u, lane);
-      if (tr) p.trace[itl * 8 + 1] = clock64();
-      const uint32_t stage = smem_u32(sA + (size_t)s * a.a_stage_bytes);
-      int plane0 = 0;
-      for (int sg = 0; sg < p.nseg; ++sg) {
-        const ConvSeg seg = p.seg[sg];
-        const int nch = seg.c >> 3;
-        const int total = a.npix_need * nch;
-        // item = pixel * nch + chunk (chunk fastest: a warp reads nch*16 contiguous bytes per pixel)
-        int px = tid / nch, ch = tid - px * nch;
-        const int step_p = NLOAD / nch, step_c = NLOAD - step_p * nch;
-        for (int it = tid; it < total; it += NLOAD) {
-          const long long q = qlo + px;
-          const bool ok = q >= 0 && q < a.npix;
-          const __half *src = ok ? seg.ptr + q * seg.cstride + seg.coff + ch * 8 : seg.ptr;
-          cp_async16(stage + (uint32_t)(((plane0 + ch) * a.PP + px) << 4), src, ok ? 16u : 0u);
-          px += step_p; ch += step_c;
-          if (ch >= nch) { ch -= nch; ++px; }
-        }
-        plane0 += nch;
-      }
-      // arrival on the stage barrier fires when this thread's copies have landed
-      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&bars->full[s])) : "memory");
-      if (tr) p.trace[itl * 8 + 2] = clock64();
-      if (++s == a.stages) { s = 0; ph ^= 1u; }
-    }
-  } else if (warp < MMA_WARP) {
+  if (warp < NEPI_WARPS) {
     // ===================================================================== epilogue
-    const int ew = warp - EPI_WARP0;
+    // warp w reads TMEM lanes 32*(w%4)..+31 (hardware rule); the two warps of a lane quarter split
+    // the (accumulator, 16-column chunk) work items between them.
+    const int ew = warp & 3, half = warp >> 2;
+    const int chunks = npad >> 4;
     int it = 0;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       const uint32_t aph = (uint32_t)(it >> 1) & 1u;
-      const bool tr = p.trace && blockIdx.x == 0 && tid == EPI_WARP0 * 32 && it < p.trace_cap;
+      const bool tr = p.trace && blockIdx.x == 0 && tid == 0 && it < p.trace_cap;
       mbar_wait_warp(&bars->tmem_full[buf], aph, lane);
       tc_fence_after();
       if (tr) p.trace[it * 8 + 6] = clock64();
-      for (int r = 0; r < a.R; ++r) {
+      const int items = a.R * chunks;
+      for (int w = half; w < items; w += 2) {
+        const int r = w / chunks, c0 = (w - r * chunks) << 4;
         const int q = a.q_begin + tile * a.TM + r * 128 + ew * 32 + lane;
         // real pixel? (not the zero column x == W, not a zero row, inside the batch)
         const uint32_t row = (uint32_t)(((uint64_t)(uint32_t)q * a.mul_wp) >> 34);
         const int x = q - (int)row * a.Wp;
         const uint32_t img = (uint32_t)(((uint64_t)row * a.mul_hp1) >> 34);
         const int yrow = (int)row - (int)img * a.Hp1;
-        const bool ok = q < a.q_end && x < p.W && yrow != 0;
-        __half *orow = p.out + (size_t)q * p.out_cstride + p.out_coff;
-        const __half *rrow = p.res ? p.res + (size_t)q * p.res_cstride + p.res_coff : nullptr;
-        const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)((buf * a.R + r) * npad);
-        for (int c0 = 0; c0 < npad; c0 += 16) {
-          uint32_t v32[16];
-          tc_ld16(tbase + (uint32_t)c0, v32);
-          tc_ld_wait();
-          if (r == a.R - 1 && c0 + 16 >= npad) {     // accumulators read: hand the buffer back
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->tmem_empty[buf]);
-          }
-          if (!ok || c0 >= p.cout) continue;
-          float v[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float xv = __uint_as_float(v32[j]) + s_bias[c0 + j];
-            v[j] = p.act ? silu(xv) : xv;
-          }
-          if (rrow) {
-            uint4 q0 = *reinterpret_cast<const uint4 *>(rrow + c0);
-            uint4 q1 = *reinterpret_cast<const uint4 *>(rrow + c0 + 8);
-            const __half2 *h0 = reinterpret_cast<const __half2 *>(&q0);
-            const __half2 *h1 = reinterpret_cast<const __half2 *>(&q1);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              float2 f0 = __half22float2(h0[t]), f1 = __half22float2(h1[t]);
-              v[2 * t] += f0.x; v[2 * t + 1] += f0.y;
-              v[8 + 2 * t] += f1.x; v[8 + 2 * t + 1] += f1.y;
-            }
-          }
-          __half2 hv[8];
-#pragma unroll
-          for (int t = 0; t < 8; ++t) hv[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
-          *reinterpret_cast<uint4 *>(orow + c0) = *reinterpret_cast<uint4 *>(&hv[0]);
-          if (c0 + 8 < p.cout) *reinterpret_cast<uint4 *>(orow + c0 + 8) = *reinterpret_cast<uint4 *>(&hv[4]);
+        const bool ok = q < a.q_end && x < p.W && yrow != 0 && c0 < p.cout;
+        const int pl = c0 >> 3;
+        uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
+        if (ok && p.res) {                                  // residual: issue the loads first
+          q0 = *reinterpret_cast<const uint4 *>(p.res + (size_t)pl * p.res_pstride + (size_t)q * 8);
+          q1 = *reinterpret_cast<const uint4 *>(p.res + (size_t)(pl + 1) * p.res_pstride + (size_t)q * 8);
         }
+        uint32_t v32[16];
+        tc_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)((buf * a.R + r) * npad + c0), v32);
+        tc_ld_wait();
+        if (!ok) continue;
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float xv = __uint_as_float(v32[j]) + s_bias[c0 + j];
+          v[j] = p.act ? silu(xv) : xv;
+        }
+        if (p.res) {
+          const __half2 *h0 = reinterpret_cast<const __half2 *>(&q0);
+          const __half2 *h1 = reinterpret_cast<const __half2 *>(&q1);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            float2 f0 = __half22float2(h0[t]), f1 = __half22float2(h1[t]);
+            v[2 * t] += f0.x; v[2 * t + 1] += f0.y;
+            v[8 + 2 * t] += f1.x; v[8 + 2 * t + 1] += f1.y;
+          }
+        }
+        __half2 hv[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) hv[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
+        *reinterpret_cast<uint4 *>(p.out + (size_t)pl * p.out_pstride + (size_t)q * 8) = *reinterpret_cast<uint4 *>(&hv[0]);
+        *reinterpret_cast<uint4 *>(p.out + (size_t)(pl + 1) * p.out_pstride + (size_t)q * 8) = *reinterpret_cast<uint4 *>(&hv[4]);
       }
+      // all of this warp's TMEM reads of the buffer are done: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->tmem_empty[buf]);
       if (tr) p.trace[it * 8 + 7] = clock64();
     }
-  } else if (warp == MMA_WARP) {
+  } else if (warp == TMA_WARP) {
+    // ===================================================================== TMA producer
+    if (elect_one()) {
+      mbar_expect_tx(&bars->bfull, a.b_bytes);
+      for (uint32_t off = 0; off < a.b_bytes; off += 65536u) {
+        const uint32_t n = a.b_bytes - off < 65536u ? a.b_bytes - off : 65536u;
+        bulk_g2s(sB + off, reinterpret_cast<const uint8_t *>(p.w_raster) + off, n, &bars->bfull);
+      }
+      int s = 0, itl = 0;
+      uint32_t ph = 0;
+      const uint32_t plane_bytes = (uint32_t)a.npix_need * 16u;
+      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++itl) {
+        const bool tr = p.trace && blockIdx.x == 0 && itl < p.trace_cap;
+        if (tr) p.trace[itl * 8 + 0] = clock64();
+        const long long qlo = (long long)a.q_begin + (long long)tile * a.TM - a.halo_front;
+        mbar_wait(&bars->empty[s], ph ^ 1u);
+        if (tr) p.trace[itl * 8 + 1] = clock64();
+        uint8_t *stage = sA + (size_t)s * a.a_stage_bytes;
+        mbar_expect_tx(&bars->full[s], plane_bytes * (uint32_t)a.NCH);
+        int plane = 0;
+        for (int sg = 0; sg < p.nseg; ++sg) {
+          const __half *src = p.seg[sg].ptr + qlo * 8;
+          const long long ps = p.seg[sg].pstride;
+          for (int c = 0; c < (p.seg[sg].c >> 3); ++c, ++plane)
+            bulk_g2s(stage + (size_t)plane * a.PP * 16, src + (long long)c * ps, plane_bytes, &bars->full[s]);
+        }
+        if (tr) p.trace[itl * 8 + 2] = clock64();
+        if (++s == a.stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else {
     // ===================================================================== MMA issuer
     mbar_wait_warp(&bars->bfull, 0, lane);
     int it = 0, s = 0;
@@ -306,17 +307,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_raster_kernel(const __grid_c
       if (tr) p.trace[it * 8 + 5] = clock64();
       if (++s == a.stages) { s = 0; ph ^= 1u; }
     }
-  } else {
-    // ===================================================================== weight loader
-    if (elect_one()) {
-      mbar_expect_tx(&bars->bfull, a.b_bytes);
-      uint32_t off = 0;
-      while (off < a.b_bytes) {                  // bulk copies of at most 64 KB
-        uint32_t n = a.b_bytes - off < 65536u ? a.b_bytes - off : 65536u;
-        bulk_g2s(sB + off, reinterpret_cast<const uint8_t *>(p.w_raster) + off, n, &bars->bfull);
-        off += n;
-      }
-    }
   }
 
   tc_fence_before();
@@ -330,6 +320,7 @@ bool plan(const ConvParams &p, int num_sms, RArgs &a) {
   if (p.stride != 1 || !(p.k == 1 || p.k == 3) || (p.k == 3 && p.pad != 1) || (p.k == 1 && p.pad != 0)) return false;
   if (p.cin % 16 != 0 || p.npad % 16 != 0 || p.npad > 256) return false;
   for (int i = 0; i < p.nseg; ++i) if (p.seg[i].up || p.seg[i].c % 8) return false;
+  if (p.W + 2 > kGuardFront || p.cout % 16 != 0) return false;
   a.p = p;
   a.NCH = p.cin / 8;
   a.taps = p.k * p.k;

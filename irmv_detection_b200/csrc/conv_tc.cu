@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
     const bool k3 = p.k == 3;
     const uint32_t mul_ow = a.mul_ow, mul_oh = a.mul_oh;
     const __half *sp0 = p.seg[0].ptr, *sp1 = p.seg[1].ptr;
-    const int cs0 = p.seg[0].cstride, cs1 = p.seg[1].cstride;
+    const long long ps0 = p.seg[0].pstride, ps1 = p.seg[1].pstride;
     const int up0 = p.seg[0].up, up1 = p.seg[1].up;
     const int two = p.nseg > 1;
     const int Hh = H >> 1, Wh = W >> 1;
@@ -250,8 +250,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
         const int iy0 = oy * cstr, ix0 = ox * cstr;
         const int full = ((int)bimg * (H + 1) + 1 + iy0) * (W + 1) + ix0;                       // PR layout
         const int half = ((int)bimg * (Hh + 1) + 1 + (iy0 >> 1)) * (Wh + 1) + (ix0 >> 1);
-        off0[i] = (up0 ? half : full) * cs0;
-        off1[i] = two ? (up1 ? half : full) * cs1 : 0;
+        off0[i] = (up0 ? half : full) * 8;                 // halfs inside a plane
+        off1[i] = two ? (up1 ? half : full) * 8 : 0;
         // the PR layout's zero row/column make every tap of a real output pixel readable
         mask[i] = (m < M && nozero) ? (k3 ? 0x1FFu : 1u) : 0u;
       }
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
           const int2 e = *reinterpret_cast<const int2 *>(&s_ktab[(kb * 8 + chunk) * 2]);
           const int tapbit = e.y & 15, sg = (e.y >> 4) & 1;
           const uint32_t kvalid = (uint32_t)(e.y >> 5) & 1u;
-          const __half *sbase = (sg ? sp1 : sp0) + e.x;
+          const __half *sbase = (sg ? sp1 : sp0) + (long long)(e.y >> 8) * (sg ? ps1 : ps0) + (long long)e.x * 8;
           const uint32_t dst0 = smem_u32(sA + (size_t)s * A_STAGE) + dst_off;
           const bool tk = p.trace && blockIdx.x == 0 && ptid == 0 && itp == 3 && kb < 16;
           if (tk) p.trace[p.trace_cap * 8 + kb * 8 + 0] = clock64();
@@ -305,8 +305,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
         const uint32_t bimg = (uint32_t)(((uint64_t)t * a.mul_oh) >> 34);
         opix = (size_t)pr_index((int)bimg, (int)t - (int)bimg * p.OH, m - (int)t * p.OW, p.OH, p.OW);
       }
-      __half *orow = p.out + opix * p.out_cstride + p.out_coff;
-      const __half *rrow = p.res ? p.res + opix * p.res_cstride + p.res_coff : nullptr;
+      __half *orow = p.out + opix * 8;                      // + plane * out_pstride
+      const __half *rrow = p.res ? p.res + opix * 8 : nullptr;
       const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * npad);
       for (int c0 = 0; c0 < npad; c0 += 16) {
         uint32_t r[16];
@@ -324,9 +324,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
           float x = __uint_as_float(r[j]) + s_bias[c0 + j];
           v[j] = p.act ? silu(x) : x;
         }
+        const int pl = c0 >> 3;                              // first of the two 8-channel planes
         if (rrow) {
-          uint4 q0 = *reinterpret_cast<const uint4 *>(rrow + c0);
-          uint4 q1 = *reinterpret_cast<const uint4 *>(rrow + c0 + 8);
+          uint4 q0 = *reinterpret_cast<const uint4 *>(rrow + (size_t)pl * p.res_pstride);
+          uint4 q1 = *reinterpret_cast<const uint4 *>(rrow + (size_t)(pl + 1) * p.res_pstride);
           const __half2 *h0 = reinterpret_cast<const __half2 *>(&q0);
           const __half2 *h1 = reinterpret_cast<const __half2 *>(&q1);
 #pragma unroll
@@ -340,8 +341,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
         for (int t = 0; t < 8; ++t) hv[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
         if (p.sync_mode & 8) continue;
-        *reinterpret_cast<uint4 *>(orow + c0) = *reinterpret_cast<uint4 *>(&hv[0]);
-        if (c0 + 8 < p.cout) *reinterpret_cast<uint4 *>(orow + c0 + 8) = *reinterpret_cast<uint4 *>(&hv[4]);
+        *reinterpret_cast<uint4 *>(orow + (size_t)pl * p.out_pstride) = *reinterpret_cast<uint4 *>(&hv[0]);
+        if (c0 + 8 < p.cout)
+          *reinterpret_cast<uint4 *>(orow + (size_t)(pl + 1) * p.out_pstride) = *reinterpret_cast<uint4 *>(&hv[4]);
       }
       if (tr) p.trace[it * 8 + 7] = clock64();
     }

@@ -32,9 +32,16 @@ __global__ void __launch_bounds__(256) decode_kernel(HeadPtrs h, int B, int nc, 
   else { scale = 2; local = a - 8000; hw = 20; stride = 32.0f; }
   const size_t pix = h.padded ? (size_t)pr_index(b, local / hw, local % hw, hw, hw) : (size_t)b * hw * hw + local;
 
-  // DFL expectation of this lane's side
-  const uint4 *bp = reinterpret_cast<const uint4 *>(h.box[scale] + pix * 64 + lane4 * 16);
-  uint4 v0 = __ldg(bp), v1 = __ldg(bp + 1);
+  // DFL expectation of this lane's side (16 bins = planes 2*side, 2*side+1 in the planar layout)
+  uint4 v0, v1;
+  if (h.padded) {
+    const __half *bp = h.box[scale] + (size_t)(2 * lane4) * h.box_ps[scale] + pix * 8;
+    v0 = __ldg(reinterpret_cast<const uint4 *>(bp));
+    v1 = __ldg(reinterpret_cast<const uint4 *>(bp + h.box_ps[scale]));
+  } else {
+    const uint4 *bp = reinterpret_cast<const uint4 *>(h.box[scale] + pix * 64 + lane4 * 16);
+    v0 = __ldg(bp); v1 = __ldg(bp + 1);
+  }
   float x[16];
   {
     const __half2 *p0 = reinterpret_cast<const __half2 *>(&v0);
@@ -71,7 +78,9 @@ __global__ void __launch_bounds__(256) decode_kernel(HeadPtrs h, int B, int nc, 
     *reinterpret_cast<float4 *>(sc.boxes + ((size_t)b * kNumAnchors + a) * 4) = bx;
   }
   // class scores: lane handles classes lane4*4 .. +3
-  uint2 cv = __ldg(reinterpret_cast<const uint2 *>(h.cls[scale] + pix * kClsPad + lane4 * 4));
+  const __half *cp = h.padded ? h.cls[scale] + (size_t)(lane4 >> 1) * h.cls_ps[scale] + pix * 8 + (lane4 & 1) * 4
+                              : h.cls[scale] + pix * kClsPad + lane4 * 4;
+  uint2 cv = __ldg(reinterpret_cast<const uint2 *>(cp));
   const __half2 *ch = reinterpret_cast<const __half2 *>(&cv);
   float lg[4];
   { float2 f = __half22float2(ch[0]); lg[0] = f.x; lg[1] = f.y;

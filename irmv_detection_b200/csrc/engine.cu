@@ -157,8 +157,9 @@ bool upload(HostConv &h) {
          up((void **)&h.d_bias, h.bias.data(), h.bias.size() * 4);
 }
 
-struct Tensor {
-  __half *p = nullptr;
+struct Tensor {            // channel-blocked planar PR layout (common.cuh)
+  __half *p = nullptr;     // pixel 0 of plane 0
+  long long pstride = 0;   // halfs between planes
   int H = 0, W = 0, C = 0;
 };
 
@@ -167,7 +168,8 @@ struct Op {
   ConvParams cp{};
   bool raster = false;       // raster (halo-tile) kernel, else the per-tap gather kernel
   __half *pool_buf = nullptr;
-  int pH = 0, pW = 0, pC = 0, pStride = 0;
+  int pH = 0, pW = 0, pC = 0;
+  long long pStride = 0;
 };
 
 struct DetPack {           // one contiguous device block per lane, mirrored in pinned memory
@@ -262,11 +264,12 @@ bool lane_alloc(Lane &ln, void **p, size_t bytes) {
 
 bool new_tensor(Lane &ln, int S, int H, int W, int C, Tensor &t, const char *tap = nullptr) {
   t.H = H; t.W = W; t.C = C;
-  // PR layout, zeroed, with 8 zero guard pixels in front and behind: the top-left tap of pixel
-  // (0,0) of image 0 is raster index -1
+  // C/8 zeroed planes of [guard | PR raster | guard] pixels x 8 channels
+  const size_t plane_px = (size_t)kGuardFront + (size_t)pr_pixels(S, H, W) + kGuardBack;
+  t.pstride = (long long)plane_px * 8;
   __half *base = nullptr;
-  if (!lane_alloc(ln, (void **)&base, ((size_t)pr_pixels(S, H, W) + 16) * C * 2)) return false;
-  t.p = base + (size_t)8 * C;
+  if (!lane_alloc(ln, (void **)&base, (size_t)(C / 8) * plane_px * 16)) return false;
+  t.p = base + (size_t)kGuardFront * 8;
   if (tap) ln.taps[tap] = t;
   return true;
 }
@@ -281,7 +284,8 @@ void add_conv(irmv_engine *e, Lane &ln, HostConv &hc, std::vector<SegRef> in, in
   p.nseg = (int)in.size();
   int cin = 0;
   for (int i = 0; i < p.nseg; ++i) {
-    p.seg[i].ptr = in[i].t->p; p.seg[i].cstride = in[i].t->C; p.seg[i].coff = in[i].coff;
+    p.seg[i].ptr = in[i].t->p + (long long)(in[i].coff / 8) * in[i].t->pstride;
+    p.seg[i].pstride = in[i].t->pstride;
     p.seg[i].c = in[i].c; p.seg[i].up = in[i].up;
     cin += in[i].c;
   }
@@ -298,13 +302,11 @@ void add_conv(irmv_engine *e, Lane &ln, HostConv &hc, std::vector<SegRef> in, in
     std::vector<int32_t> tab((size_t)nq * 2, 0);
     for (int q = 0; q < nq; ++q) {
       int tap = hc.ktab[q * 3 + 0], sg = hc.ktab[q * 3 + 1], off = hc.ktab[q * 3 + 2];
-      if (tap < 0) { tab[q * 2 + 0] = 0; tab[q * 2 + 1] = ktab_meta(0, 0, 0); continue; }
+      if (tap < 0) { tab[q * 2 + 0] = 0; tab[q * 2 + 1] = ktab_meta(0, 0, 0, 0); continue; }
       const ConvSeg &g = p.seg[sg];
       int ky = tap / hc.k, kx = tap % hc.k;
-      int delta = g.coff + off;
-      if (!g.up) delta += ((ky - p.pad) * (W + 1) + (kx - p.pad)) * g.cstride;   // PR layout pitch
-      tab[q * 2 + 0] = delta;
-      tab[q * 2 + 1] = ktab_meta(tap, sg, 1);
+      tab[q * 2 + 0] = g.up ? 0 : (ky - p.pad) * (W + 1) + (kx - p.pad);   // pixel offset, PR pitch
+      tab[q * 2 + 1] = ktab_meta(tap, sg, 1, off / 8);
     }
     int32_t *d = nullptr;
     cudaMalloc((void **)&d, tab.size() * 4);
@@ -312,8 +314,9 @@ void add_conv(irmv_engine *e, Lane &ln, HostConv &hc, std::vector<SegRef> in, in
     ln.allocs.push_back(d);
     p.ktab = d;
   }
-  p.out = out.p; p.out_cstride = out.C; p.out_coff = out_coff;
-  p.res = res ? res->p : nullptr; p.res_cstride = res ? res->C : 0; p.res_coff = res_coff;
+  p.out = out.p + (long long)(out_coff / 8) * out.pstride; p.out_pstride = out.pstride;
+  p.res = res ? res->p + (long long)(res_coff / 8) * res->pstride : nullptr;
+  p.res_pstride = res ? res->pstride : 0;
   p.sync_mode = 0;
   p.trace = nullptr; p.trace_cap = 0;
   op.raster = conv_raster_fits(p) && !getenv("IRMV_NO_RASTER");
@@ -367,7 +370,7 @@ bool build_lane(irmv_engine *e, Lane &ln) {
   if (!new_tensor(ln, S, 20, 20, 512, sp) || !new_tensor(ln, S, 20, 20, 256, x9, "m9")) return false;
   add_conv(e, ln, *e->convs[ci++], {{&x8, 0, 256, 0}}, 20, 20, sp, 0);
   {
-    Op op; op.kind = Op::POOL; op.pool_buf = sp.p; op.pH = 20; op.pW = 20; op.pC = 128; op.pStride = 512;
+    Op op; op.kind = Op::POOL; op.pool_buf = sp.p; op.pH = 20; op.pW = 20; op.pC = 128; op.pStride = sp.pstride;
     ln.ops.push_back(op);
   }
   add_conv(e, ln, *e->convs[ci++], {{&sp, 0, 512, 0}}, 20, 20, x9, 0);
@@ -397,8 +400,8 @@ bool build_lane(irmv_engine *e, Lane &ln) {
     add_conv(e, ln, *e->convs[ci++], {{&hb, 0, 64, 0}}, hw[i], hw[i], bo, 0);
     add_conv(e, ln, *e->convs[ci++], {{&h0, 64, 64, 0}}, hw[i], hw[i], hc, 0);
     add_conv(e, ln, *e->convs[ci++], {{&hc, 0, 64, 0}}, hw[i], hw[i], co, 0);
-    ln.heads.box[i] = bo.p;
-    ln.heads.cls[i] = co.p;
+    ln.heads.box[i] = bo.p; ln.heads.box_ps[i] = bo.pstride;
+    ln.heads.cls[i] = co.p; ln.heads.cls_ps[i] = co.pstride;
     ln.heads.padded = 1;
   }
   if (ci != e->convs.size()) { set_error("internal: conv count mismatch"); return false; }
@@ -416,7 +419,7 @@ bool build_lane(irmv_engine *e, Lane &ln) {
     return false;
   for (auto &ev : ln.stage_ev)
     if (!cuda_ok(cudaEventCreate(&ev), "cudaEventCreate", __FILE__, __LINE__)) return false;
-  Tensor bt; bt.p = reinterpret_cast<__half *>(ln.nms.boxes); bt.H = 1; bt.W = kNumAnchors; bt.C = 4;
+  Tensor bt; bt.p = reinterpret_cast<__half *>(ln.nms.boxes); bt.H = 1; bt.W = kNumAnchors; bt.C = 4; bt.pstride = 0;
   ln.taps["boxes"] = bt;
   return true;
 }
@@ -802,15 +805,19 @@ int irmv_engine_read_tensor(irmv_engine *e, const char *name, void *dst, int64_t
     if (is_boxes) {
       IRMV_CUDA(cudaMemcpy(dst, t.p, (size_t)bytes, cudaMemcpyDeviceToHost));
     } else {
-      // device tensors are in the padded raster layout: copy out and drop the zero row/column
+      // device tensors are channel-blocked planes in the padded raster layout: gather to dense NHWC
       const size_t px = (size_t)pr_pixels(nb, t.H, t.W);
-      std::vector<uint16_t> tmp(px * t.C);
-      IRMV_CUDA(cudaMemcpy(tmp.data(), t.p, tmp.size() * 2, cudaMemcpyDeviceToHost));
+      const int planes = t.C / 8;
+      std::vector<uint16_t> tmp(px * 8);
       uint16_t *o = static_cast<uint16_t *>(dst);
-      for (int b = 0; b < nb; ++b)
-        for (int y = 0; y < t.H; ++y)
-          memcpy(o + (((size_t)b * t.H + y) * t.W) * t.C, tmp.data() + (size_t)pr_index(b, y, 0, t.H, t.W) * t.C,
-                 (size_t)t.W * t.C * 2);
+      for (int pl = 0; pl < planes; ++pl) {
+        IRMV_CUDA(cudaMemcpy(tmp.data(), t.p + (long long)pl * t.pstride, tmp.size() * 2, cudaMemcpyDeviceToHost));
+        for (int b = 0; b < nb; ++b)
+          for (int y = 0; y < t.H; ++y)
+            for (int x = 0; x < t.W; ++x)
+              memcpy(o + ((((size_t)b * t.H + y) * t.W + x) * t.C + pl * 8),
+                     tmp.data() + (size_t)pr_index(b, y, x, t.H, t.W) * 8, 16);
+      }
     }
   }
   return 0;
