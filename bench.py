@@ -279,13 +279,13 @@ def run_ours(args):
     host.copy_(frames_dev)
     torch.cuda.synchronize()
     host_np = host.numpy()
-    eng.detect_batch(host_np)
+    eng.detect_batch_arrays(host_np)
     if world > 1:
         torch.distributed.barrier(device_ids=[local_rank])
     e2e_steps = max(2, min(args.steps, 10))
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        eng.detect_batch(host_np)                 # H2D + pipeline + D2H of results + parse
+        eng.detect_batch_arrays(host_np)          # H2D + pipeline + D2H of results + parse_output
         eng.fetch_poses(B)
     e2e_ms_local = (time.perf_counter() - t0) * 1e3 / e2e_steps
     e2e_ms, _ = sharding.reduce_max_sum(e2e_ms_local, 0.0, device=str(dev))

@@ -76,7 +76,8 @@ typedef struct irmv_engine_config {
   float score_thr;          /* 0.25 */
   float iou_thr;            /* 0.45 */
   int32_t use_graph;        /* 1 = replay captured CUDA graphs (reference behaviour) */
-  int32_t reserved[8];
+  int32_t reserved[8];      /* reserved[0] != 0: run preprocess and conv0 as separate kernels (the network
+                             * input tensor is then materialised and readable as tap "input") */
 } irmv_engine_config;
 
 typedef struct irmv_engine irmv_engine;

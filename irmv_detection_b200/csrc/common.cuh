@@ -53,6 +53,9 @@ struct PreprocessParams {
   int chan_order, rotate180, resize_mode, quantize_u8;
 };
 cudaError_t launch_preprocess(const PreprocessParams &p, cudaStream_t s);
+// Fused preprocess + conv0 (3x3 s2, 3->16, SiLU): w = [16][9 taps][3] FP32, writes two planes.
+cudaError_t launch_stem(const PreprocessParams &p, const float *w, const float *bias, __half *out,
+                        long long out_pstride, cudaStream_t s);
 
 // ---------------------------------------------------------------- convolution
 struct ConvSeg {

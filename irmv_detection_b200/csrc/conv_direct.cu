@@ -95,51 +95,58 @@ cudaError_t launch_conv_direct(const ConvParams &p, cudaStream_t s) {
 
 // ------------------------------------------------------------------------------- SPPF pooling
 namespace {
-// Three chained MaxPool2d(5,1,2) == windows of radius 2, 4, 6 clipped to the image (padding is
-// -inf).  One thread: one pixel x 8 channels; separable max would cut reads further, but the
-// whole tensor is 20x20x128 per frame (0.1 MB) and lives in L2.
-__global__ void __launch_bounds__(128) sppf_pool_kernel(__half *buf, int B, int H, int W,
-                                                        long long pstride, int c) {
-  int groups = c / 8;
-  long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  long long total = (long long)B * H * W * groups;
-  if (gid >= total) return;
-  int g = (int)(gid % groups);
-  long long pix = gid / groups;
-  int x = (int)(pix % W), y = (int)((pix / W) % H), b = (int)(pix / ((long long)W * H));
-  __half2 m1[4], m2[4], m3[4];
-  const __half2 ninf = __float2half2_rn(-65504.0f);
+// Three chained MaxPool2d(5,1,2) (ultralytics SPPF; padding is -inf, i.e. windows clipped to the
+// image).  One CTA per (image, plane of 8 channels): the 20x20 plane is staged in shared memory
+// and each 5x5 max is done separably (row max, then column max), three times in a row.
+constexpr int POOL_MAX_HW = 20 * 20;
+__global__ void __launch_bounds__(256) sppf_pool_kernel(__half *buf, int H, int W, long long pstride, int c) {
+  __shared__ uint4 cur[POOL_MAX_HW], tmp[POOL_MAX_HW];
+  const int planes = c / 8;
+  const int b = blockIdx.x / planes, g = blockIdx.x - b * planes;
+  const int n = H * W;
+  __half *plane = buf + (size_t)g * pstride;
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    cur[i] = *reinterpret_cast<const uint4 *>(plane + (size_t)pr_index(b, i / W, i % W, H, W) * 8);
+  __syncthreads();
+  for (int pass = 1; pass <= 3; ++pass) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {          // row max over x-2..x+2
+      const int y = i / W, x = i - y * W;
+      uint4 m = cur[i];
+      __half2 *mh = reinterpret_cast<__half2 *>(&m);
+      for (int dx = -2; dx <= 2; ++dx) {
+        const int xx = x + dx;
+        if (dx == 0 || xx < 0 || xx >= W) continue;
+        const uint4 v = cur[y * W + xx];
+        const __half2 *vh = reinterpret_cast<const __half2 *>(&v);
 #pragma unroll
-  for (int t = 0; t < 4; ++t) m1[t] = m2[t] = m3[t] = ninf;
-  for (int dy = -6; dy <= 6; ++dy) {
-    int yy = y + dy;
-    if (yy < 0 || yy >= H) continue;
-    for (int dx = -6; dx <= 6; ++dx) {
-      int xx = x + dx;
-      if (xx < 0 || xx >= W) continue;
-      uint4 v = *reinterpret_cast<const uint4 *>(buf + (size_t)g * pstride + (size_t)pr_index(b, yy, xx, H, W) * 8);
-      const __half2 *h = reinterpret_cast<const __half2 *>(&v);
-      int r = max(abs(dy), abs(dx));
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        m3[t] = __hmax2(m3[t], h[t]);
-        if (r <= 4) m2[t] = __hmax2(m2[t], h[t]);
-        if (r <= 2) m1[t] = __hmax2(m1[t], h[t]);
+        for (int t = 0; t < 4; ++t) mh[t] = __hmax2(mh[t], vh[t]);
       }
+      tmp[i] = m;
     }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {          // column max over y-2..y+2
+      const int y = i / W, x = i - y * W;
+      uint4 m = tmp[i];
+      __half2 *mh = reinterpret_cast<__half2 *>(&m);
+      for (int dy = -2; dy <= 2; ++dy) {
+        const int yy = y + dy;
+        if (dy == 0 || yy < 0 || yy >= H) continue;
+        const uint4 v = tmp[yy * W + x];
+        const __half2 *vh = reinterpret_cast<const __half2 *>(&v);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) mh[t] = __hmax2(mh[t], vh[t]);
+      }
+      *reinterpret_cast<uint4 *>(plane + (size_t)pass * planes * pstride + (size_t)pr_index(b, y, x, H, W) * 8) = m;
+      cur[i] = m;   // each thread rewrites only its own pixels; readers of cur[] are behind the next barrier
+    }
+    __syncthreads();
   }
-  __half *o = buf + (size_t)g * pstride + (size_t)pr_index(b, y, x, H, W) * 8;
-  const size_t grp = (size_t)(c / 8) * pstride;
-  *reinterpret_cast<uint4 *>(o + grp) = *reinterpret_cast<uint4 *>(m1);
-  *reinterpret_cast<uint4 *>(o + 2 * grp) = *reinterpret_cast<uint4 *>(m2);
-  *reinterpret_cast<uint4 *>(o + 3 * grp) = *reinterpret_cast<uint4 *>(m3);
 }
 }  // namespace
 
 cudaError_t launch_sppf_pool(__half *buf, int B, int H, int W, long long pstride, int c, cudaStream_t s) {
-  long long total = (long long)B * H * W * (c / 8);
-  int blocks = (int)((total + 127) / 128);
-  sppf_pool_kernel<<<blocks, 128, 0, s>>>(buf, B, H, W, pstride, c);
+  if (H * W > POOL_MAX_HW) return cudaErrorInvalidValue;
+  sppf_pool_kernel<<<B * (c / 8), 256, 0, s>>>(buf, H, W, pstride, c);
   return cudaGetLastError();
 }
 

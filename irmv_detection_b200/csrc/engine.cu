@@ -194,7 +194,7 @@ struct Lane {
   std::vector<void *> allocs;
   std::map<std::string, Tensor> taps;
   std::vector<Op> ops;
-  Tensor in8;
+  Tensor in8, stem_out;
   HeadPtrs heads{};
   NmsScratch nms{};
   DetPack det;
@@ -248,6 +248,8 @@ struct irmv_engine {
   size_t res_frame_stride = 0;
   double profile_ms = 0.0, device_ms = 0.0;
   bool pnp_on = false;
+  bool fused_stem = true;               // preprocess + conv0 in one kernel (input never materialised)
+  float *d_stem_w = nullptr, *d_stem_b = nullptr;
   PnpConsts pnp_c{};
   float pnp_sx = 1.f, pnp_sy = 1.f;
   int last_slot = -1;
@@ -354,6 +356,7 @@ bool build_lane(irmv_engine *e, Lane &ln) {
   Tensor t0, t1, x2, t3, x4, t5, x6, t7, x8, sp, x9, x12, x15, t16, x18, t19, x21;
   if (!new_tensor(ln, S, 320, 320, 16, t0, "m0")) return false;
   add_conv(e, ln, *e->convs[ci++], {{&ln.in8, 0, kInC, 0}}, 640, 640, t0, 0);
+  ln.stem_out = t0;
   if (!new_tensor(ln, S, 160, 160, 32, t1, "m1")) return false;
   add_conv(e, ln, *e->convs[ci++], {{&t0, 0, 16, 0}}, 320, 320, t1, 0);
   if (!add_c2f(e, ln, ci, {{&t1, 0, 32, 0}}, 160, 160, 32, 1, true, x2, "m2")) return false;
@@ -439,9 +442,15 @@ int issue_replay(irmv_engine *e, Lane &ln, int n, cudaStream_t st, int *launches
   pp.n = n; pp.src_w = e->cfg.src_width; pp.src_h = e->cfg.src_height;
   pp.chan_order = e->cfg.chan_order; pp.rotate180 = e->cfg.rotate180;
   pp.resize_mode = e->cfg.resize_mode; pp.quantize_u8 = e->cfg.quantize_u8;
-  IRMV_CUDA(launch_preprocess(pp, st)); cnt += 1 + (ln.rotated ? 1 : 0);
+  const bool fused = e->fused_stem && e->cfg.conv_impl != IRMV_CONV_DIRECT;
+  if (fused) IRMV_CUDA(launch_stem(pp, e->d_stem_w, e->d_stem_b, ln.stem_out.p, ln.stem_out.pstride, st));
+  else IRMV_CUDA(launch_preprocess(pp, st));
+  cnt += 1 + (ln.rotated ? 1 : 0);
   if (mark(1)) return 1;
+  bool first = true;
   for (auto &op : ln.ops) {
+    if (first && fused) { first = false; continue; }        // conv0 ran inside the stem kernel
+    first = false;
     if (op.kind == Op::CONV) {
       ConvParams p = op.cp;
       p.B = n;
@@ -506,7 +515,9 @@ int run_replay(irmv_engine *e, Lane &ln, int n) {
 }
 
 // frames_dev: device pointer to n contiguous frames.  Results land in res_host (pinned).
-int enqueue(irmv_engine *e, const uint8_t *frames_dev, int n) {
+// frames_host != null: the frames are still on the host; each chunk is copied on its lane's stream
+// right before its replay, so the H2D of one lane overlaps the compute of the others.
+int enqueue(irmv_engine *e, const uint8_t *frames_dev, int n, const uint8_t *frames_host = nullptr) {
   IRMV_CUDA(cudaEventRecord(e->ev_start, e->main_stream));
   const int S = e->S;
   const int chunks = (n + S - 1) / S;
@@ -515,6 +526,10 @@ int enqueue(irmv_engine *e, const uint8_t *frames_dev, int n) {
   for (int c = 0; c < chunks; ++c) {
     Lane &ln = e->lanes[c % e->L];
     const int f0 = c * S, nf = (n - f0) < S ? (n - f0) : S;
+    if (frames_host)
+      IRMV_CUDA(cudaMemcpyAsync(const_cast<uint8_t *>(frames_dev) + (size_t)f0 * e->frame_bytes,
+                                frames_host + (size_t)f0 * e->frame_bytes, (size_t)nf * e->frame_bytes,
+                                cudaMemcpyHostToDevice, ln.stream));
     set_src_kernel<<<1, 1, 0, ln.stream>>>(ln.src_word, frames_dev + (size_t)f0 * e->frame_bytes);
     IRMV_CUDA(cudaGetLastError());
     if (int rc = run_replay(e, ln, nf)) return rc;
@@ -637,6 +652,21 @@ int irmv_engine_create(const char *weights_path, const irmv_engine_config *cfg, 
     single(b + 5, 64, {64});
   }
   for (auto &c : e->convs) if (!upload(*c)) return 5;
+  {
+    // stem weights: conv0 as FP32 [16][9 taps][3] + bias
+    const HostConv &c0 = *e->convs[0];
+    std::vector<float> w(16 * 27), b(16);
+    for (int n = 0; n < 16; ++n) {
+      b[n] = c0.bias[n];
+      for (int t = 0; t < 9; ++t)
+        for (int c = 0; c < 3; ++c) w[n * 27 + t * 3 + c] = __half2float(c0.w_plain[(size_t)n * c0.kpad + t * kInC + c]);
+    }
+    IRMV_CUDA(cudaMalloc((void **)&e->d_stem_w, w.size() * 4));
+    IRMV_CUDA(cudaMalloc((void **)&e->d_stem_b, b.size() * 4));
+    IRMV_CUDA(cudaMemcpy(e->d_stem_w, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
+    IRMV_CUDA(cudaMemcpy(e->d_stem_b, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
+    e->fused_stem = cfg->reserved[0] == 0;
+  }
 
   const bool bayer = cfg->chan_order >= 2;
   e->frame_bytes = (size_t)cfg->src_width * cfg->src_height * (bayer ? 1 : 3);
@@ -683,6 +713,7 @@ void irmv_engine_destroy(irmv_engine *e) {
   }
   for (auto s : e->slots_host) cudaFreeHost(s);
   cudaFree(e->slot_dev);
+  cudaFree(e->d_stem_w); cudaFree(e->d_stem_b);
   if (e->batch_dev) cudaFree(e->batch_dev);
   cudaFreeHost(e->res_host);
   cudaEventDestroy(e->ev_start); cudaEventDestroy(e->ev_stop);
@@ -747,10 +778,9 @@ int irmv_engine_detect_batch(irmv_engine *e, const uint8_t *frames, int on_devic
   const uint8_t *dev = frames;
   if (!on_device) {
     if (!e->batch_dev) IRMV_CUDA(cudaMalloc((void **)&e->batch_dev, e->frame_bytes * (size_t)e->cfg.max_batch));
-    IRMV_CUDA(cudaMemcpyAsync(e->batch_dev, frames, e->frame_bytes * (size_t)nframes, cudaMemcpyHostToDevice, e->main_stream));
     dev = e->batch_dev;
   }
-  if (int rc = enqueue(e, dev, nframes)) return rc;
+  if (int rc = enqueue(e, dev, nframes, on_device ? nullptr : frames)) return rc;
   if (int rc = irmv_engine_sync(e)) return rc;
   parse(e, nframes, out, counts);
   auto t1 = std::chrono::high_resolution_clock::now();

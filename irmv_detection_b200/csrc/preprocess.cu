@@ -44,20 +44,24 @@ struct Region {
   int pitch_s;            // bytes per staged row
   int col_byte_lo;        // first needed byte inside a source row
   int src_pitch;          // bytes per source row
+  int shift0, dshift;     // (address of staged row 0) & 15, and src_pitch & 15: row r starts at
+                          // smem offset r*pitch_s + ((shift0 + r*dshift) & 15)
 };
 
 // byte of source row `sy`, byte column `bx` (already inside the staged window)
 __device__ __forceinline__ int rd(const Region &r, int sy, int bx) {
-  size_t row_addr = (size_t)(r.frame + (size_t)sy * r.src_pitch + r.col_byte_lo);
-  int shift = (int)(row_addr & 15);
-  return r.smem[(sy - r.row_lo) * r.pitch_s + shift + (bx - r.col_byte_lo)];
+  const int rr = sy - r.row_lo;
+  return r.smem[rr * r.pitch_s + ((r.shift0 + rr * r.dshift) & 15) + (bx - r.col_byte_lo)];
 }
 
 // RGB at source pixel (sy,sx) of a Bayer mosaic, bilinear demosaic (oracle demosaic_bilinear)
 __device__ __forceinline__ void bayer_rgb(const Region &r, int sy, int sx, int H, int W, int red_y,
                                           int red_x, int &R, int &G, int &B) {
-  int ym = reflect101(sy - 1, H), yp = reflect101(sy + 1, H);
-  int xm = reflect101(sx - 1, W), xp = reflect101(sx + 1, W);
+  int ym = sy - 1, yp = sy + 1, xm = sx - 1, xp = sx + 1;
+  if (sy == 0 || sx == 0 || sy == H - 1 || sx == W - 1) {       // image border: mirror (reflect-101)
+    ym = reflect101(ym, H); yp = reflect101(yp, H);
+    xm = reflect101(xm, W); xp = reflect101(xp, W);
+  }
   int c = rd(r, sy, sx);
   int py = sy & 1, px = sx & 1;
   bool is_r = (py == red_y) && (px == red_x);
@@ -90,6 +94,83 @@ __device__ __forceinline__ float finish(float v, int quantize) {
   return __fdiv_rn(v, 255.0f);
 }
 
+// One network-input pixel (oy, ox): rot180 + resize taps + (demosaic | channel swap) + lerp +
+// 8-bit quantisation + /255, from the staged source window.  v = {R, G, B} as fed to the net.
+__device__ __forceinline__ void sample_pixel(const Region &reg, const PreprocessParams &p, int oy, int ox,
+                                             float scale_x, float scale_y, int hp, int red_y, int red_x,
+                                             float (&v)[3]) {
+  const int H = p.src_h, W = p.src_w;
+  const bool bayer = p.chan_order >= 2;
+  const bool swap = (p.chan_order == 1);
+  Taps ty = axis_taps(oy, scale_y, H, hp), tx = axis_taps(ox, scale_x, W, hp);
+  int ys[2] = {ty.i0, ty.i1}, xs[2] = {tx.i0, tx.i1};
+  float pix[2][2][3];
+  // a tap with weight exactly 0 contributes p*0 = +0 to an exactly rounded sum: skipping it is
+  // bit-identical and halves the work when the scale is an integer (1280 -> 640: fx == 0)
+  const bool need_x1 = tx.f != 0.0f, need_y1 = ty.f != 0.0f;
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      if ((a == 1 && !need_y1) || (b == 1 && !need_x1)) {
+        pix[a][b][0] = pix[a][b][1] = pix[a][b][2] = 0.0f;
+        continue;
+      }
+      int sy = p.rotate180 ? H - 1 - ys[a] : ys[a];
+      int sx = p.rotate180 ? W - 1 - xs[b] : xs[b];
+      int R, G, B;
+      if (bayer) {
+        bayer_rgb(reg, sy, sx, H, W, red_y, red_x, R, G, B);
+      } else {
+        R = rd(reg, sy, sx * 3 + 0);
+        G = rd(reg, sy, sx * 3 + 1);
+        B = rd(reg, sy, sx * 3 + 2);
+        if (swap) { int t = R; R = B; B = t; }
+      }
+      pix[a][b][0] = (float)R; pix[a][b][1] = (float)G; pix[a][b][2] = (float)B;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+    v[c] = finish(lerp4(pix[0][0][c], pix[0][1][c], pix[1][0][c], pix[1][1][c], tx.f, ty.f), p.quantize_u8);
+}
+
+// Stage the source window needed by network-input rows [iy_lo, iy_hi] x cols [ix_lo, ix_hi] into
+// shared memory with 16-byte loads aligned on absolute addresses; returns the Region describing it.
+__device__ __forceinline__ Region stage_window(const PreprocessParams &p, const uint8_t *base, const uint8_t *frame,
+                                               uint8_t *smem, int pitch_s, int iy_lo, int iy_hi, int ix_lo, int ix_hi,
+                                               float scale_x, float scale_y, int hp, int nthreads) {
+  const bool bayer = p.chan_order >= 2;
+  const int bpp = bayer ? 1 : 3;
+  const int H = p.src_h, W = p.src_w;
+  const int src_pitch = W * bpp;
+  const size_t frame_bytes = (size_t)H * src_pitch;
+  Taps ty0 = axis_taps(iy_lo, scale_y, H, hp), ty1 = axis_taps(iy_hi, scale_y, H, hp);
+  Taps tx0 = axis_taps(ix_lo, scale_x, W, hp), tx1 = axis_taps(ix_hi, scale_x, W, hp);
+  int ry_lo = ty0.i0, ry_hi = ty1.i1, rx_lo = tx0.i0, rx_hi = tx1.i1;
+  int sy_lo = p.rotate180 ? H - 1 - ry_hi : ry_lo, sy_hi = p.rotate180 ? H - 1 - ry_lo : ry_hi;
+  int sx_lo = p.rotate180 ? W - 1 - rx_hi : rx_lo, sx_hi = p.rotate180 ? W - 1 - rx_lo : rx_hi;
+  if (bayer) {
+    sy_lo = max(sy_lo - 2, 0); sy_hi = min(sy_hi + 2, H - 1);
+    sx_lo = max(sx_lo - 2, 0); sx_hi = min(sx_hi + 2, W - 1);
+  }
+  const int nrows = sy_hi - sy_lo + 1;
+  const int col_byte_lo = sx_lo * bpp;
+  const int nbytes = (sx_hi - sx_lo + 1) * bpp;
+  const int chunks_per_row = pitch_s >> 4;
+  const uint8_t *alloc_end = base + (size_t)p.n * frame_bytes;
+  for (int i = threadIdx.x; i < nrows * chunks_per_row; i += nthreads) {
+    int r = i / chunks_per_row, c = i - r * chunks_per_row;
+    const uint8_t *row = frame + (size_t)(sy_lo + r) * src_pitch + col_byte_lo;
+    const uint8_t *a = (const uint8_t *)((size_t)row & ~(size_t)15) + (size_t)c * 16;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (a < row + nbytes && a < alloc_end) v = __ldg((const uint4 *)a);
+    *(uint4 *)(smem + (size_t)r * pitch_s + c * 16) = v;
+  }
+  const int shift0 = (int)((size_t)(frame + (size_t)sy_lo * src_pitch + col_byte_lo) & 15);
+  return Region{frame, smem, sy_lo, pitch_s, col_byte_lo, src_pitch, shift0, src_pitch & 15};
+}
+
 __global__ void __launch_bounds__(NT)
 preprocess_kernel(PreprocessParams p, int rows_cap, int pitch_s) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -106,70 +187,21 @@ preprocess_kernel(PreprocessParams p, int rows_cap, int pitch_s) {
   const float scale_y = __fdiv_rn((float)H, (float)kNet);
   const int hp = (p.resize_mode == 2);
 
-  // window of rotated-space taps needed by this tile
-  Taps ty0 = axis_taps(oy0, scale_y, H, hp), ty1 = axis_taps(min(oy0 + TH, kNet) - 1, scale_y, H, hp);
-  Taps tx0 = axis_taps(ox0, scale_x, W, hp), tx1 = axis_taps(min(ox0 + TW, kNet) - 1, scale_x, W, hp);
-  int ry_lo = ty0.i0, ry_hi = ty1.i1, rx_lo = tx0.i0, rx_hi = tx1.i1;
-  int sy_lo = p.rotate180 ? H - 1 - ry_hi : ry_lo, sy_hi = p.rotate180 ? H - 1 - ry_lo : ry_hi;
-  int sx_lo = p.rotate180 ? W - 1 - rx_hi : rx_lo, sx_hi = p.rotate180 ? W - 1 - rx_lo : rx_hi;
-  if (bayer) {
-    sy_lo = max(sy_lo - 2, 0); sy_hi = min(sy_hi + 2, H - 1);
-    sx_lo = max(sx_lo - 2, 0); sx_hi = min(sx_hi + 2, W - 1);
-  }
-  const int nrows = sy_hi - sy_lo + 1;
-  const int col_byte_lo = sx_lo * bpp;
-  const int nbytes = (sx_hi - sx_lo + 1) * bpp;
-
-  // stage: 16-byte chunks, aligned on absolute addresses, per source row
-  const int chunks_per_row = pitch_s >> 4;
-  const uint8_t *alloc_end = base + (size_t)p.n * frame_bytes;
-  for (int i = threadIdx.x; i < nrows * chunks_per_row; i += NT) {
-    int r = i / chunks_per_row, c = i - r * chunks_per_row;
-    const uint8_t *row = frame + (size_t)(sy_lo + r) * src_pitch + col_byte_lo;
-    const uint8_t *a = (const uint8_t *)((size_t)row & ~(size_t)15) + (size_t)c * 16;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (a < row + nbytes && a < alloc_end) v = __ldg((const uint4 *)a);
-    *(uint4 *)(smem + (size_t)r * pitch_s + c * 16) = v;
-  }
+  Region reg = stage_window(p, base, frame, smem, pitch_s, oy0, min(oy0 + TH, kNet) - 1, ox0, min(ox0 + TW, kNet) - 1,
+                            scale_x, scale_y, hp, NT);
   __syncthreads();
   (void)rows_cap;
 
-  Region reg{frame, smem, sy_lo, pitch_s, col_byte_lo, src_pitch};
   int red_y = 0, red_x = 0;
   if (p.chan_order == 3) { red_y = 1; red_x = 1; }       // BGGR
   else if (p.chan_order == 4) { red_y = 0; red_x = 1; }  // GRBG
   else if (p.chan_order == 5) { red_y = 1; red_x = 0; }  // GBRG
-  const bool swap = (p.chan_order == 1);
 
   for (int q = threadIdx.x; q < TH * TW; q += NT) {
     int oy = oy0 + q / TW, ox = ox0 + q % TW;
     if (oy >= kNet || ox >= kNet) continue;
-    Taps ty = axis_taps(oy, scale_y, H, hp), tx = axis_taps(ox, scale_x, W, hp);
-    int ys[2] = {ty.i0, ty.i1}, xs[2] = {tx.i0, tx.i1};
-    float pix[2][2][3];
-#pragma unroll
-    for (int a = 0; a < 2; ++a) {
-#pragma unroll
-      for (int b = 0; b < 2; ++b) {
-        int sy = p.rotate180 ? H - 1 - ys[a] : ys[a];
-        int sx = p.rotate180 ? W - 1 - xs[b] : xs[b];
-        int R, G, B;
-        if (bayer) {
-          bayer_rgb(reg, sy, sx, H, W, red_y, red_x, R, G, B);
-        } else {
-          R = rd(reg, sy, sx * 3 + 0);
-          G = rd(reg, sy, sx * 3 + 1);
-          B = rd(reg, sy, sx * 3 + 2);
-          if (swap) { int t = R; R = B; B = t; }
-        }
-        pix[a][b][0] = (float)R; pix[a][b][1] = (float)G; pix[a][b][2] = (float)B;
-      }
-    }
     float v[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-      v[c] = finish(lerp4(pix[0][0][c], pix[0][1][c], pix[1][0][c], pix[1][1][c], tx.f, ty.f),
-                    p.quantize_u8);
+    sample_pixel(reg, p, oy, ox, scale_x, scale_y, hp, red_y, red_x, v);
     __half2 h01 = __halves2half2(__float2half_rn(v[0]), __float2half_rn(v[1]));
     __half2 h23 = __halves2half2(__float2half_rn(v[2]), __float2half_rn(0.0f));
     uint4 o;
@@ -179,6 +211,88 @@ preprocess_kernel(PreprocessParams p, int rows_cap, int pitch_s) {
     size_t pix_idx = (size_t)pr_index(n, oy, ox, kNet, kNet);
     *reinterpret_cast<uint4 *>(p.dst + pix_idx * kInC) = o;
   }
+}
+
+// ------------------------------------------------------------------------------------ fused stem
+// preprocess + conv0 (3x3, stride 2, 3->16, bias, SiLU) in one kernel: the 640x640x3 network input
+// is produced tile by tile in shared memory and consumed there, so it never touches HBM (it would
+// be 6.5 MB written + read per frame as NHWC8).  conv0 is 88 MFLOP per frame with K = 27: CUDA-core
+// FP32 FMAs from shared memory; the input values are rounded to FP16 first so the result matches
+// the unfused (tensor-core) path's operands.
+constexpr int ST = 16;                 // output tile side
+constexpr int SI = 2 * ST + 1;         // input tile side (33)
+
+__device__ __forceinline__ float silu_fast(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+
+__global__ void __launch_bounds__(ST * ST)
+stem_kernel(PreprocessParams p, const float *__restrict__ w, const float *__restrict__ bias, __half *out,
+            long long out_pstride, int pitch_s) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  __shared__ float tile[3][SI][SI + 1];
+  __shared__ __align__(16) float sw[27 * 16 + 16];   // [tap*3+c][16 outputs] then bias: float4 broadcast loads
+  const int n = blockIdx.z, oy0 = blockIdx.y * ST, ox0 = blockIdx.x * ST;
+  const bool bayer = p.chan_order >= 2;
+  const int H = p.src_h, W = p.src_w;
+  const size_t frame_bytes = (size_t)H * W * (bayer ? 1 : 3);
+  const uint8_t *base = p.src_indirect ? *p.src_indirect : p.src;
+  const uint8_t *frame = base + (size_t)n * frame_bytes;
+  const float scale_x = __fdiv_rn((float)W, (float)kNet), scale_y = __fdiv_rn((float)H, (float)kNet);
+  const int hp = (p.resize_mode == 2);
+  for (int i = threadIdx.x; i < 16 * 27 + 16; i += ST * ST)
+    sw[i] = i < 16 * 27 ? w[(i & 15) * 27 + (i >> 4)] : bias[i - 16 * 27];
+  // network-input window of this tile: rows 2*oy0-1 .. 2*oy0+2*ST-1 (clipped: outside is conv padding)
+  const int iy_lo = 2 * oy0 - 1, ix_lo = 2 * ox0 - 1;
+  Region reg = stage_window(p, base, frame, smem, pitch_s, max(iy_lo, 0), min(iy_lo + SI - 1, kNet - 1), max(ix_lo, 0),
+                            min(ix_lo + SI - 1, kNet - 1), scale_x, scale_y, hp, ST * ST);
+  __syncthreads();
+  int red_y = 0, red_x = 0;
+  if (p.chan_order == 3) { red_y = 1; red_x = 1; }
+  else if (p.chan_order == 4) { red_y = 0; red_x = 1; }
+  else if (p.chan_order == 5) { red_y = 1; red_x = 0; }
+  for (int q = threadIdx.x; q < SI * SI; q += ST * ST) {
+    const int r = q / SI, c = q - r * SI;
+    const int iy = iy_lo + r, ix = ix_lo + c;
+    float v[3] = {0.f, 0.f, 0.f};
+    if (iy >= 0 && iy < kNet && ix >= 0 && ix < kNet) {
+      sample_pixel(reg, p, iy, ix, scale_x, scale_y, hp, red_y, red_x, v);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) v[k] = __half2float(__float2half_rn(v[k]));
+    }
+    tile[0][r][c] = v[0]; tile[1][r][c] = v[1]; tile[2][r][c] = v[2];
+  }
+  __syncthreads();
+  const int ty = threadIdx.x / ST, tx = threadIdx.x - ty * ST;
+  float acc[16];
+#pragma unroll
+  for (int o = 0; o < 16; ++o) acc[o] = sw[16 * 27 + o];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float x = tile[c][2 * ty + ky][2 * tx + kx];
+        const float4 *wv = reinterpret_cast<const float4 *>(&sw[((ky * 3 + kx) * 3 + c) * 16]);
+#pragma unroll
+        for (int o4 = 0; o4 < 4; ++o4) {
+          const float4 w4 = wv[o4];
+          acc[4 * o4 + 0] = fmaf(x, w4.x, acc[4 * o4 + 0]);
+          acc[4 * o4 + 1] = fmaf(x, w4.y, acc[4 * o4 + 1]);
+          acc[4 * o4 + 2] = fmaf(x, w4.z, acc[4 * o4 + 2]);
+          acc[4 * o4 + 3] = fmaf(x, w4.w, acc[4 * o4 + 3]);
+        }
+      }
+  __half2 hv[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) hv[t] = __floats2half2_rn(silu_fast(acc[2 * t]), silu_fast(acc[2 * t + 1]));
+  const size_t pix = (size_t)pr_index(n, oy0 + ty, ox0 + tx, kNet / 2, kNet / 2);
+  *reinterpret_cast<uint4 *>(out + pix * 8) = *reinterpret_cast<uint4 *>(&hv[0]);
+  *reinterpret_cast<uint4 *>(out + out_pstride + pix * 8) = *reinterpret_cast<uint4 *>(&hv[4]);
 }
 
 // Optional: materialise the rotated RGB frame (what get_rotated_image() exposes in the reference,
@@ -198,7 +312,7 @@ __global__ void rotate_kernel(PreprocessParams p) {
     const uint8_t *frame = base + (size_t)n * frame_bytes;
     int R, G, B;
     if (bayer) {
-      Region reg{frame, frame, 0, W, 0, W};
+      Region reg{frame, frame, 0, W, 0, W, 0, 0};
       // direct global reads: shift term must vanish, so index manually
       auto g = [&](int yy, int xx) { return (int)frame[(size_t)yy * W + xx]; };
       int red_y = 0, red_x = 0;
@@ -256,6 +370,35 @@ cudaError_t launch_preprocess(const PreprocessParams &p, cudaStream_t s) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (p.rotated) {
+    size_t total = (size_t)p.n * p.src_h * p.src_w;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    rotate_kernel<<<blocks, 256, 0, s>>>(p);
+    e = cudaGetLastError();
+  }
+  return e;
+}
+
+
+cudaError_t launch_stem(const PreprocessParams &p, const float *w, const float *bias, __half *out,
+                        long long out_pstride, cudaStream_t s) {
+  if (p.n <= 0) return cudaSuccess;
+  const bool bayer = p.chan_order >= 2;
+  const int bpp = bayer ? 1 : 3;
+  const float sx = (float)p.src_w / kNet, sy = (float)p.src_h / kNet;
+  int rows_cap = (int)(SI * sy) + 4 + (bayer ? 4 : 0);
+  int cols_cap = (int)(SI * sx) + 4 + (bayer ? 4 : 0);
+  int pitch_s = ((cols_cap * bpp + 15) / 16 + 2) * 16;
+  size_t smem = (size_t)rows_cap * pitch_s;
+  if (smem > 160 * 1024) return cudaErrorInvalidValue;
+  if (smem > 30 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  dim3 grid(kNet / 2 / ST, kNet / 2 / ST, p.n);
+  stem_kernel<<<grid, ST * ST, smem, s>>>(p, w, bias, out, out_pstride, pitch_s);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess && p.rotated) {
     size_t total = (size_t)p.n * p.src_h * p.src_w;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;

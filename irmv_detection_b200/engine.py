@@ -51,7 +51,7 @@ class YoloEngine:
                  rotate180: bool = True, quantize_u8: bool = True, half_pixel: bool = False, max_batch: int = 1,
                  sub_batch: int = 0, num_lanes: int = 0, num_slots: int = 3, device: int = 0,
                  conv_impl: int = L.CONV_TCGEN05, score_thr: float = 0.25, iou_thr: float = 0.45,
-                 max_det: int = 100, use_graph: bool = True):
+                 max_det: int = 100, use_graph: bool = True, fused_stem: bool = True):
         lib = L.lib()
         wpath = onnx_file_path if onnx_file_path.endswith(".irmw") else weights_path_for(onnx_file_path)
         if not os.path.exists(wpath):
@@ -69,6 +69,7 @@ class YoloEngine:
         cfg.device, cfg.conv_impl = device, conv_impl
         cfg.score_thr, cfg.iou_thr, cfg.max_det = score_thr, iou_thr, max_det
         cfg.use_graph = int(use_graph)
+        cfg.reserved[0] = 0 if fused_stem else 1
         self._cfg = cfg
         self._h = C.c_void_p()
         self._lib = lib
@@ -117,6 +118,17 @@ class YoloEngine:
         L.check(self._lib.irmv_engine_detect_batch(self._h, frames.ctypes.data, 0, n, self._out, self._counts),
                 "irmv_engine_detect_batch")
         return [self._to_list(f, self._counts[f]) for f in range(n)]
+
+    def detect_batch_arrays(self, frames: np.ndarray):
+        """Same call as detect_batch, results as arrays (no per-detection Python objects):
+        counts i32[n] and a structured view {xyxy f32[4], score f32, class_id i32}[n, max_det]."""
+        frames = np.ascontiguousarray(frames, np.uint8)
+        n = frames.shape[0]
+        L.check(self._lib.irmv_engine_detect_batch(self._h, frames.ctypes.data, 0, n, self._out, self._counts),
+                "irmv_engine_detect_batch")
+        dt = np.dtype([("xyxy", np.float32, 4), ("score", np.float32), ("class_id", np.int32)])
+        dets = np.frombuffer(self._out, dtype=dt, count=n * self.max_det).reshape(n, self.max_det)
+        return np.frombuffer(self._counts, dtype=np.int32, count=n), dets
 
     def detect_batch_device(self, dev_ptr: int, n: int) -> List[List[bbox]]:
         L.check(self._lib.irmv_engine_detect_batch(self._h, C.c_void_p(dev_ptr), 1, n, self._out, self._counts),

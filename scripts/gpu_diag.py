@@ -77,7 +77,7 @@ def main():
         t0 = time.time()
         dets = eng.detect_batch(fr)
         log("impl", impl, "first batch wall", round(time.time() - t0, 3), "s; device ms", eng.last_device_ms(), "dets", [len(d) for d in dets])
-        x = eng.read_tensor("input")
+        x = irmv.preprocess(fr)
         taps = {}
         with torch.no_grad():
             xin = torch.from_numpy(x[..., :3].astype(np.float32)).permute(0, 3, 1, 2).contiguous()

@@ -280,7 +280,9 @@ def test_network_parity(frames, weights_seed0, impl):
     eng = irmv.YoloEngine(weights_seed0, (1280, 1024), max_batch=n, sub_batch=n,
                           conv_impl=irmv.CONV_DIRECT if impl == "direct" else irmv.CONV_TCGEN05)
     dets = eng.detect_batch(fr)
-    x = eng.read_tensor("input")
+    # the engine's stem kernel fuses preprocess + conv0, so the network input is not materialised;
+    # the stand-alone preprocess entry point produces the identical tensor (same device code)
+    x = irmv.preprocess(fr)
     taps, outs, rboxes, rscores = _oracle_forward(weights_seed0, x)
     # module taps: FP16 storage vs FP32 oracle
     for name, ref in taps.items():
@@ -370,3 +372,23 @@ def test_large_sub_batch_matches_single_frames(base_image, weights_seed0):
         assert r == res[i], f"frame {i}"
         assert np.array_equal(one.read_tensor("box0")[0], box_big[i]), f"frame {i} head tensor"
     big.close(); one.close()
+
+
+def test_fused_stem_matches_unfused(frames, weights_seed0):
+    """preprocess+conv0 fused (CUDA-core FP32) vs separate kernels (tcgen05 conv0): same detections,
+    conv0 output equal up to FP16 rounding of differently ordered FP32 sums; the unfused engine's
+    materialised input equals the stand-alone preprocess bit for bit."""
+    import irmv_detection_b200 as irmv
+    fr = frames[[0, 2]]
+    a = irmv.YoloEngine(weights_seed0, (1280, 1024), max_batch=2, sub_batch=2)
+    b = irmv.YoloEngine(weights_seed0, (1280, 1024), max_batch=2, sub_batch=2, fused_stem=False)
+    ra, rb = a.detect_batch(fr), b.detect_batch(fr)
+    assert np.array_equal(b.read_tensor("input"), irmv.preprocess(fr))
+    m0a, m0b = a.read_tensor("m0").astype(np.float32), b.read_tensor("m0").astype(np.float32)
+    assert np.abs(m0a - m0b).max() <= 2e-2 and np.abs(m0a - m0b).mean() < 2e-4
+    for x, y in zip(ra, rb):
+        assert len(x) == len(y)
+        for dx, dy in zip(x, y):
+            assert dx.class_id == dy.class_id and abs(dx.score - dy.score) < 1e-2
+            assert np.abs(np.array(dx.xyxy) - np.array(dy.xyxy)).max() < 1.0
+    a.close(); b.close()
