@@ -356,7 +356,7 @@ def run_ours(args):
         "config": {"workload": "1280x1024 8-bit Bayer RGGB frames, batch 256/GPU, fused demosaic+rot180+resize -> "
                                "YOLOv8n nc=14 (seeded random-init, FP16 tcgen05) -> decode+NMS -> PnP "
                                "(BASELINE.json configs[3])",
-                   "frames_per_gpu_per_step": B, "sub_batch": eng._cfg.sub_batch or min(B, 8), "lanes": args.lanes,
+                   "frames_per_gpu_per_step": B, "sub_batch": eng._cfg.sub_batch or min(B, 128), "lanes": args.lanes or 2,
                    "l2": "inputs larger than L2 (335 MB of frames per step per GPU, activations cycled per replay)",
                    "timing": "CUDA events on the engine's streams, summed over steps, max over ranks",
                    "detections_per_step": n_dets, "wall_ms_per_step": wall_ms / args.steps},

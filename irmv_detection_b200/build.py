@@ -69,5 +69,33 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+HOST_LIB = os.path.join(HERE, "libirmv_detection.so")
+DROP_IN_TEST = os.path.join(HERE, "drop_in_test")
+
+
+def build_host(force: bool = False) -> str:
+    """C++ drop-in classes (YoloEngine / PnPSolver with the reference signatures) + their test."""
+    inc = os.path.join(os.path.dirname(HERE), "include")
+    srcs = [os.path.join(CSRC, "host", "yolo_engine.cpp"), os.path.join(CSRC, "host", "pnp_solver.cpp")]
+    test_src = os.path.join(os.path.dirname(HERE), "tests", "cpp", "drop_in_test.cpp")
+    deps = srcs + [test_src] + [os.path.join(inc, "irmv_detection", h) for h in os.listdir(os.path.join(inc, "irmv_detection"))]
+    if not force and os.path.exists(HOST_LIB) and os.path.exists(DROP_IN_TEST) and \
+            all(os.path.getmtime(d) < min(os.path.getmtime(HOST_LIB), os.path.getmtime(DROP_IN_TEST)) for d in deps) and \
+            os.path.getmtime(LIB) < os.path.getmtime(HOST_LIB):
+        return HOST_LIB
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    common = ["g++", "-O2", "-std=c++20", "-fPIC", f"-I{inc}"]
+    rp = ["-Wl,-rpath,$ORIGIN", "-Wl,-rpath," + HERE]
+    for cmd in (common + ["-shared", "-o", HOST_LIB, *srcs, f"-L{HERE}", "-lirmv_b200", *rp],
+                common + ["-o", DROP_IN_TEST, test_src, f"-L{HERE}", "-lirmv_detection", "-lirmv_b200", "-lpthread",
+                          "-Wl,-rpath," + HERE]):
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout)
+            raise RuntimeError("host C++ build failed: " + " ".join(cmd))
+    return HOST_LIB
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_host(force="--force" in sys.argv))

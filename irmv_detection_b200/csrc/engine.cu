@@ -670,10 +670,11 @@ int irmv_engine_create(const char *weights_path, const irmv_engine_config *cfg, 
 
   const bool bayer = cfg->chan_order >= 2;
   e->frame_bytes = (size_t)cfg->src_width * cfg->src_height * (bayer ? 1 : 3);
-  e->S = cfg->sub_batch > 0 ? cfg->sub_batch : (cfg->max_batch < 8 ? cfg->max_batch : 8);
+  // defaults from the bench sweeps: replays of up to 128 frames on 2 lanes
+  e->S = cfg->sub_batch > 0 ? cfg->sub_batch : (cfg->max_batch < 128 ? cfg->max_batch : 128);
   if (e->S > cfg->max_batch) e->S = cfg->max_batch;
   int chunks = (cfg->max_batch + e->S - 1) / e->S;
-  e->L = cfg->num_lanes > 0 ? cfg->num_lanes : (chunks < 4 ? chunks : 4);
+  e->L = cfg->num_lanes > 0 ? cfg->num_lanes : (chunks < 2 ? chunks : 2);
   if (e->L > chunks) e->L = chunks;
   e->lanes.resize(e->L);
   IRMV_CUDA(cudaStreamCreateWithFlags(&e->main_stream, cudaStreamNonBlocking));

@@ -1,0 +1,90 @@
+// C++ drop-in check, shaped like the reference's own tests (reference test/yolo_test.cpp:53-107,
+// test/triple_buffer_test.cpp): construct YoloEngine / PnPSolver through the reference class
+// interfaces, copy a frame into get_src_image_buffer(), detect(), run the benchmark protocol
+// (warm-ups, 30 runs x 10 iterations, max < 30 ms) and solve one armor pose.
+// usage: drop_in_test <model.onnx (the .irmw sits beside it)> <frame.raw u8 1280x1024x3> [runs]
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <thread>
+#include <vector>
+
+#include "irmv_detection/pnp_solver.hpp"
+#include "irmv_detection/triple_buffer.hpp"
+#include "irmv_detection/yolo_engine.hpp"
+
+using namespace irmv_detection;
+
+int main(int argc, char ** argv)
+{
+  if (argc < 3) { fprintf(stderr, "usage: drop_in_test model.onnx frame.raw [runs]\n"); return 2; }
+  const int runs = argc > 3 ? atoi(argv[3]) : 30;
+  std::vector<uint8_t> frame(1280 * 1024 * 3);
+  FILE * f = fopen(argv[2], "rb");
+  if (!f || fread(frame.data(), 1, frame.size(), f) != frame.size()) { fprintf(stderr, "bad frame file\n"); return 2; }
+  fclose(f);
+
+  YoloEngine engine(argv[1], cv::Size(1280, 1024), true);
+  uint8_t * src = engine.get_src_image_buffer();
+  for (int i = 0; i < 100; i++) {
+    memcpy(src, frame.data(), frame.size());
+    engine.detect();
+  }
+  std::vector<double> avg;
+  std::vector<YoloEngine::bbox> boxes;
+  for (int run = 0; run < runs; run++) {
+    auto t0 = std::chrono::high_resolution_clock::now();
+    for (int i = 0; i < 10; i++) {
+      memcpy(src, frame.data(), frame.size());
+      boxes = engine.detect();
+    }
+    avg.push_back(std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - t0).count() / 10.0);
+  }
+  const double mean = std::accumulate(avg.begin(), avg.end(), 0.0) / avg.size();
+  const double mx = *std::max_element(avg.begin(), avg.end());
+  printf("detections %zu\n", boxes.size());
+  for (size_t i = 0; i < boxes.size() && i < 3; i++)
+    printf("box %.3f %.3f %.3f %.3f score %.4f class %s\n", boxes[i].xyxy[0], boxes[i].xyxy[1], boxes[i].xyxy[2],
+           boxes[i].xyxy[3], boxes[i].score, armor_class_name(boxes[i].class_id));
+  printf("avg_ms %.4f max_ms %.4f profiling_ms %.4f\n", mean, mx, engine.get_profiling_time());
+  if (!(mx < 30.0)) { printf("FAIL: max detection time\n"); return 1; }   // reference bound, test/yolo_test.cpp:106
+  const cv::Mat & rot = engine.get_rotated_image();
+  printf("rotated %dx%d first_byte %d expect %d\n", rot.cols, rot.rows, rot.data[0], frame[frame.size() - 3]);
+  if (rot.data[0] != frame[frame.size() - 3]) { printf("FAIL: rotated image\n"); return 1; }
+
+  // PnP on a known quad (SURVEY.md section 8c known answer)
+  PnPSolver pnp({957.669211, 0, 345.943891, 0, 969.127115, 284.057302, 0, 0, 1}, {-0.405274, 0.126058, -0.026939, -0.006503, 0});
+  Light left(cv::Point2f(302, 280), cv::Point2f(300, 320), 4.0), right(cv::Point2f(400, 282), cv::Point2f(398, 322), 4.0);
+  Armor armor(left, right);
+  cv::Mat rvec, tvec;
+  const bool ok = pnp.solvePnP(armor, rvec, tvec);
+  printf("pnp ok %d rvec %.8f %.8f %.8f tvec %.8f %.8f %.8f dist %.4f\n", ok, rvec.at<double>(0), rvec.at<double>(1),
+         rvec.at<double>(2), tvec.at<double>(0), tvec.at<double>(1), tvec.at<double>(2),
+         pnp.calculateDistanceToCenter(armor.center));
+
+  // triple buffer: producer at full speed, consumer sees strictly newer frames (drops allowed).
+  // The hand-off can lose the wake-up of the very last commit by design (the reference clears its
+  // flag after the exchange too), so the producer keeps re-committing the final value until the
+  // consumer has seen it.
+  std::array<int, 3> slots = {0, 0, 0};
+  TripleBuffer<int> tb(slots);
+  std::atomic<bool> done{false};
+  std::thread prod([&] {
+    for (int i = 1; i <= 2000; i++) { *tb.get_producer_buffer() = i; tb.producer_commit(); }
+    while (!done.load()) { *tb.get_producer_buffer() = 2001; tb.producer_commit(); std::this_thread::yield(); }
+  });
+  int last = 0, seen = 0;
+  while (last < 2000) {
+    int v = *tb.get_consumer_buffer();
+    if (v < last) { printf("FAIL: triple buffer order %d after %d\n", v, last); done = true; prod.join(); return 1; }
+    last = v; seen++;
+  }
+  done = true;
+  prod.join();
+  printf("triple_buffer consumed %d hand-offs, last %d\n", seen, last);
+  printf("DROP_IN_OK\n");
+  return 0;
+}

@@ -4,6 +4,8 @@ Bars (BASELINE.json north_star): kept NMS indices bit-exact on identical inputs;
 0.5 px; scores within 1e-2 (FP16 path vs FP32 oracle); PnP rvec/tvec within 1e-4 relative.
 Integer/byte stages (preprocess, NMS indices) are compared bit-exactly.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -392,3 +394,35 @@ def test_fused_stem_matches_unfused(frames, weights_seed0):
             assert dx.class_id == dy.class_id and abs(dx.score - dy.score) < 1e-2
             assert np.abs(np.array(dx.xyxy) - np.array(dy.xyxy)).max() < 1.0
     a.close(); b.close()
+
+
+def test_cpp_drop_in_classes(base_image, weights_seed0, tmp_path):
+    """The C++ YoloEngine / PnPSolver / TripleBuffer with the reference's class interfaces
+    (include/irmv_detection/*.hpp), exercised by a program shaped like the reference's
+    yolo_engine_benchmark test: same detections as the Python mirror, max time < 30 ms."""
+    import shutil
+    import subprocess
+    import irmv_detection_b200 as irmv
+    from irmv_detection_b200 import build as B
+    _cuda()
+    exe = B.DROP_IN_TEST
+    if not os.path.exists(exe):
+        pytest.skip("drop_in_test not built")
+    shutil.copy(weights_seed0, tmp_path / "yolov7.irmw")          # the reference passes models/yolov7.onnx
+    base_image.tofile(tmp_path / "frame.raw")
+    r = subprocess.run([exe, str(tmp_path / "yolov7.onnx"), str(tmp_path / "frame.raw"), "5"], capture_output=True,
+                       text=True, timeout=240)
+    assert r.returncode == 0 and "DROP_IN_OK" in r.stdout, f"rc={r.returncode}\nstdout:\n{r.stdout[-2000:]}\nstderr:\n{r.stderr[-2000:]}"
+    eng = irmv.YoloEngine(weights_seed0, (1280, 1024))
+    eng.get_src_image_buffer(0)[...] = base_image
+    dets = eng.detect(0)
+    lines = r.stdout.splitlines()
+    assert int(lines[0].split()[1]) == len(dets)
+    for ln, d in zip([l for l in lines if l.startswith("box ")], dets):
+        f = ln.split()
+        np.testing.assert_allclose([float(v) for v in f[1:5]], d.xyxy, atol=2e-3)
+        assert abs(float(f[6]) - d.score) < 1e-4 and f[8] == d.class_id.name
+    pnp = [l for l in lines if l.startswith("pnp ok")][0].split()
+    np.testing.assert_allclose([float(v) for v in pnp[4:7]], [1.14443091, -0.9268353, 1.21457493], rtol=1e-6)
+    np.testing.assert_allclose([float(v) for v in pnp[8:11]], [0.00508322, 0.02282537, 1.30085669], rtol=1e-6)
+    eng.close()
