@@ -308,8 +308,12 @@ def run_ours(args):
     n_conv = 60
     achieved = FLOPS_PER_FRAME * k / conv_t / 1e12
     peak = float(peaks.get("bf16_tflops", 1590.0))
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tpath):                      # dram__bytes_read+write of the GEMM launches, ncu capture
+        traffic = json.load(open(tpath))["conv_group_dram_bytes_per_frame"] * k
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "conv_tc_kernel (60 launches per replay, timed as a group)",
+                "traffic": traffic, "kernel": "conv_tc_kernel (60 launches per replay, timed as a group)",
                 "frames_per_replay": k, "peak_source": f"{peak_kind} bf16_tflops (burst: stage timed alone)",
                 "stage_ms": st,
                 "hbm_frac_preprocess": (3768320.0 * k / (st["preprocess"] * 1e-3) / 1e9) / float(peaks.get("hbm_gbs", 6650.0))

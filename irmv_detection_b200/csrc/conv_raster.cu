@@ -22,6 +22,8 @@
 //
 // Against the per-tap gather kernel this cuts L2->SM traffic and load instructions ~4x for 3x3
 // layers and the number of producer/consumer hand-offs 9x.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace irmv {
@@ -133,13 +135,13 @@ struct RArgs {
   ConvParams p;
   int R, TM, PP, halo_front, npix_need;   // rows = 128*R; PP = plane pitch (pixels); halo before q0
   int NCH, taps, Wp, Hp1;                 // cin/8, 1 or 9, W+1, H+1
-  int q_begin, q_end, num_tiles, stages, tmem_cols;
+  int q_begin, q_end, num_tiles, stages, tmem_cols, ctas_per_sm;
   long long npix;                         // raster pixels of the tensors for this batch
   uint32_t idesc, mul_wp, mul_hp1;        // magic dividers (q / Wp, row / (H+1)), >> 34
   uint32_t a_stage_bytes, b_bytes, off_b, off_bias, off_bars;
 };
 
-__global__ void __launch_bounds__(NTHREADS, 1) conv_raster_kernel(const __grid_constant__ RArgs a) {
+__global__ void __launch_bounds__(NTHREADS) conv_raster_kernel(const __grid_constant__ RArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const ConvParams &p = a.p;
   uint8_t *sA = smem;
@@ -352,12 +354,19 @@ bool plan(const ConvParams &p, int num_sms, RArgs &a) {
   a.npix_need = a.TM + halo;
   a.PP = a.npix_need + ((9 - (a.npix_need & 7)) & 7);
   a.a_stage_bytes = (uint32_t)((((size_t)a.NCH * a.PP * 16) + 127) & ~(size_t)127);
-  a.stages = (int)(((size_t)SMEM_BUDGET - a.b_bytes - misc) / a.a_stage_bytes);
-  if (a.stages > MAX_STAGES) a.stages = MAX_STAGES;
-  a.num_tiles = (int)((Mr + a.TM - 1) / a.TM);
   int cols = 2 * a.R * p.npad, alloc = 32;
   while (alloc < cols) alloc <<= 1;
   a.tmem_cols = alloc;
+  // The per-tile chain load -> MMA -> epilogue is latency-bound (profiles: warps mostly asleep on
+  // barriers), so when two CTAs fit on an SM (shared memory and TMEM halves) run two: their
+  // phases interleave and hide each other's latencies.
+  const size_t half_budget = 112 * 1024;
+  const bool two = !getenv("IRMV_ONE_CTA") && alloc <= 256 && a.b_bytes + 2 * (size_t)a.a_stage_bytes + misc <= half_budget;
+  a.ctas_per_sm = two ? 2 : 1;
+  const size_t budget = two ? half_budget : (size_t)SMEM_BUDGET;
+  a.stages = (int)((budget - a.b_bytes - misc) / a.a_stage_bytes);
+  if (a.stages > MAX_STAGES) a.stages = MAX_STAGES;
+  a.num_tiles = (int)((Mr + a.TM - 1) / a.TM);
   a.idesc = (1u << 4) | ((uint32_t)(p.npad >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   a.mul_wp = (uint32_t)(((1ull << 34) + (uint64_t)a.Wp - 1) / (uint64_t)a.Wp);
   a.mul_hp1 = (uint32_t)(((1ull << 34) + (uint64_t)a.Hp1 - 1) / (uint64_t)a.Hp1);
@@ -384,7 +393,8 @@ cudaError_t launch_conv_raster(const ConvParams &p, int num_sms, cudaStream_t s)
     configured = true;
   }
   size_t smem = (size_t)a.off_bars + sizeof(Bars) + 64;
-  int grid = a.num_tiles < num_sms ? a.num_tiles : num_sms;
+  const int slots = num_sms * a.ctas_per_sm;
+  int grid = a.num_tiles < slots ? a.num_tiles : slots;
   conv_raster_kernel<<<grid, NTHREADS, smem, s>>>(a);
   return cudaGetLastError();
 }
