@@ -54,6 +54,12 @@ __device__ __forceinline__ int rd(const Region &r, int sy, int bx) {
   return r.smem[rr * r.pitch_s + ((r.shift0 + rr * r.dshift) & 15) + (bx - r.col_byte_lo)];
 }
 
+// pointer such that rowp(r, sy)[bx] is byte column bx of source row sy
+__device__ __forceinline__ const uint8_t *rowp(const Region &r, int sy) {
+  const int rr = sy - r.row_lo;
+  return r.smem + rr * r.pitch_s + ((r.shift0 + rr * r.dshift) & 15) - r.col_byte_lo;
+}
+
 // RGB at source pixel (sy,sx) of a Bayer mosaic, bilinear demosaic (oracle demosaic_bilinear)
 __device__ __forceinline__ void bayer_rgb(const Region &r, int sy, int sx, int H, int W, int red_y,
                                           int red_x, int &R, int &G, int &B) {
@@ -62,18 +68,19 @@ __device__ __forceinline__ void bayer_rgb(const Region &r, int sy, int sx, int H
     ym = reflect101(ym, H); yp = reflect101(yp, H);
     xm = reflect101(xm, W); xp = reflect101(xp, W);
   }
-  int c = rd(r, sy, sx);
+  const uint8_t *r0 = rowp(r, ym), *r1 = rowp(r, sy), *r2 = rowp(r, yp);
+  int c = r1[sx];
   int py = sy & 1, px = sx & 1;
   bool is_r = (py == red_y) && (px == red_x);
   bool is_b = (py != red_y) && (px != red_x);
   if (is_r || is_b) {
-    int cross = (rd(r, ym, sx) + rd(r, yp, sx) + rd(r, sy, xm) + rd(r, sy, xp) + 2) >> 2;
-    int diag = (rd(r, ym, xm) + rd(r, ym, xp) + rd(r, yp, xm) + rd(r, yp, xp) + 2) >> 2;
+    int cross = (r0[sx] + r2[sx] + r1[xm] + r1[xp] + 2) >> 2;
+    int diag = (r0[xm] + r0[xp] + r2[xm] + r2[xp] + 2) >> 2;
     G = cross;
     if (is_r) { R = c; B = diag; } else { B = c; R = diag; }
   } else {
-    int horiz = (rd(r, sy, xm) + rd(r, sy, xp) + 1) >> 1;
-    int vert = (rd(r, ym, sx) + rd(r, yp, sx) + 1) >> 1;
+    int horiz = (r1[xm] + r1[xp] + 1) >> 1;
+    int vert = (r0[sx] + r2[sx] + 1) >> 1;
     G = c;
     bool on_red_row = (py == red_y);
     R = on_red_row ? horiz : vert;
@@ -89,20 +96,20 @@ __device__ __forceinline__ float lerp4(float p00, float p01, float p10, float p1
   return __fadd_rn(__fmul_rn(top, ofy), __fmul_rn(bot, fy));
 }
 
-__device__ __forceinline__ float finish(float v, int quantize) {
-  if (quantize) v = fminf(fmaxf(floorf(__fadd_rn(v, 0.5f)), 0.0f), 255.0f);
+// lut[k] = k/255 (FP32, exactly rounded): the 8-bit intermediate makes the final division a lookup
+__device__ __forceinline__ float finish(float v, int quantize, const float *lut) {
+  if (quantize) return lut[(int)fminf(fmaxf(floorf(__fadd_rn(v, 0.5f)), 0.0f), 255.0f)];
   return __fdiv_rn(v, 255.0f);
 }
 
 // One network-input pixel (oy, ox): rot180 + resize taps + (demosaic | channel swap) + lerp +
 // 8-bit quantisation + /255, from the staged source window.  v = {R, G, B} as fed to the net.
-__device__ __forceinline__ void sample_pixel(const Region &reg, const PreprocessParams &p, int oy, int ox,
-                                             float scale_x, float scale_y, int hp, int red_y, int red_x,
+__device__ __forceinline__ void sample_pixel(const Region &reg, const PreprocessParams &p, const Taps &ty,
+                                             const Taps &tx, int red_y, int red_x, const float *lut,
                                              float (&v)[3]) {
   const int H = p.src_h, W = p.src_w;
   const bool bayer = p.chan_order >= 2;
   const bool swap = (p.chan_order == 1);
-  Taps ty = axis_taps(oy, scale_y, H, hp), tx = axis_taps(ox, scale_x, W, hp);
   int ys[2] = {ty.i0, ty.i1}, xs[2] = {tx.i0, tx.i1};
   float pix[2][2][3];
   // a tap with weight exactly 0 contributes p*0 = +0 to an exactly rounded sum: skipping it is
@@ -132,7 +139,7 @@ __device__ __forceinline__ void sample_pixel(const Region &reg, const Preprocess
   }
 #pragma unroll
   for (int c = 0; c < 3; ++c)
-    v[c] = finish(lerp4(pix[0][0][c], pix[0][1][c], pix[1][0][c], pix[1][1][c], tx.f, ty.f), p.quantize_u8);
+    v[c] = finish(lerp4(pix[0][0][c], pix[0][1][c], pix[1][0][c], pix[1][1][c], tx.f, ty.f), p.quantize_u8, lut);
 }
 
 // Stage the source window needed by network-input rows [iy_lo, iy_hi] x cols [ix_lo, ix_hi] into
@@ -187,6 +194,11 @@ preprocess_kernel(PreprocessParams p, int rows_cap, int pitch_s) {
   const float scale_y = __fdiv_rn((float)H, (float)kNet);
   const int hp = (p.resize_mode == 2);
 
+  __shared__ float lut[256];
+  __shared__ Taps ytap[TH], xtap[TW];
+  lut[threadIdx.x & 255] = __fdiv_rn((float)(threadIdx.x & 255), 255.0f);
+  if (threadIdx.x < TH) ytap[threadIdx.x] = axis_taps(min(oy0 + (int)threadIdx.x, kNet - 1), scale_y, H, hp);
+  else if (threadIdx.x < TH + TW) xtap[threadIdx.x - TH] = axis_taps(min(ox0 + (int)threadIdx.x - TH, kNet - 1), scale_x, W, hp);
   Region reg = stage_window(p, base, frame, smem, pitch_s, oy0, min(oy0 + TH, kNet) - 1, ox0, min(ox0 + TW, kNet) - 1,
                             scale_x, scale_y, hp, NT);
   __syncthreads();
@@ -201,7 +213,7 @@ preprocess_kernel(PreprocessParams p, int rows_cap, int pitch_s) {
     int oy = oy0 + q / TW, ox = ox0 + q % TW;
     if (oy >= kNet || ox >= kNet) continue;
     float v[3];
-    sample_pixel(reg, p, oy, ox, scale_x, scale_y, hp, red_y, red_x, v);
+    sample_pixel(reg, p, ytap[q / TW], xtap[q % TW], red_y, red_x, lut, v);
     __half2 h01 = __halves2half2(__float2half_rn(v[0]), __float2half_rn(v[1]));
     __half2 h23 = __halves2half2(__float2half_rn(v[2]), __float2half_rn(0.0f));
     uint4 o;
@@ -243,8 +255,13 @@ stem_kernel(PreprocessParams p, const float *__restrict__ w, const float *__rest
   const uint8_t *frame = base + (size_t)n * frame_bytes;
   const float scale_x = __fdiv_rn((float)W, (float)kNet), scale_y = __fdiv_rn((float)H, (float)kNet);
   const int hp = (p.resize_mode == 2);
+  __shared__ float lut[256];
+  __shared__ Taps ytap[SI], xtap[SI];
   for (int i = threadIdx.x; i < 16 * 27 + 16; i += ST * ST)
     sw[i] = i < 16 * 27 ? w[(i & 15) * 27 + (i >> 4)] : bias[i - 16 * 27];
+  lut[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.0f);                       // ST*ST == 256 threads
+  if (threadIdx.x < SI) ytap[threadIdx.x] = axis_taps(min(max(2 * oy0 - 1 + (int)threadIdx.x, 0), kNet - 1), scale_y, H, hp);
+  else if (threadIdx.x < 2 * SI) xtap[threadIdx.x - SI] = axis_taps(min(max(2 * ox0 - 1 + (int)threadIdx.x - SI, 0), kNet - 1), scale_x, W, hp);
   // network-input window of this tile: rows 2*oy0-1 .. 2*oy0+2*ST-1 (clipped: outside is conv padding)
   const int iy_lo = 2 * oy0 - 1, ix_lo = 2 * ox0 - 1;
   Region reg = stage_window(p, base, frame, smem, pitch_s, max(iy_lo, 0), min(iy_lo + SI - 1, kNet - 1), max(ix_lo, 0),
@@ -259,7 +276,7 @@ stem_kernel(PreprocessParams p, const float *__restrict__ w, const float *__rest
     const int iy = iy_lo + r, ix = ix_lo + c;
     float v[3] = {0.f, 0.f, 0.f};
     if (iy >= 0 && iy < kNet && ix >= 0 && ix < kNet) {
-      sample_pixel(reg, p, iy, ix, scale_x, scale_y, hp, red_y, red_x, v);
+      sample_pixel(reg, p, ytap[r], xtap[c], red_y, red_x, lut, v);
 #pragma unroll
       for (int k = 0; k < 3; ++k) v[k] = __half2float(__float2half_rn(v[k]));
     }
