@@ -68,24 +68,19 @@ __device__ __forceinline__ void bayer_rgb(const Region &r, int sy, int sx, int H
     ym = reflect101(ym, H); yp = reflect101(yp, H);
     xm = reflect101(xm, W); xp = reflect101(xp, W);
   }
+  // branch-free: neighbouring samples sit on different colour sites, so a site-dependent branch
+  // would run both arms for most warps anyway
   const uint8_t *r0 = rowp(r, ym), *r1 = rowp(r, sy), *r2 = rowp(r, yp);
-  int c = r1[sx];
-  int py = sy & 1, px = sx & 1;
-  bool is_r = (py == red_y) && (px == red_x);
-  bool is_b = (py != red_y) && (px != red_x);
-  if (is_r || is_b) {
-    int cross = (r0[sx] + r2[sx] + r1[xm] + r1[xp] + 2) >> 2;
-    int diag = (r0[xm] + r0[xp] + r2[xm] + r2[xp] + 2) >> 2;
-    G = cross;
-    if (is_r) { R = c; B = diag; } else { B = c; R = diag; }
-  } else {
-    int horiz = (r1[xm] + r1[xp] + 1) >> 1;
-    int vert = (r0[sx] + r2[sx] + 1) >> 1;
-    G = c;
-    bool on_red_row = (py == red_y);
-    R = on_red_row ? horiz : vert;
-    B = on_red_row ? vert : horiz;
-  }
+  const int nw = r0[xm], n = r0[sx], ne = r0[xp];
+  const int w = r1[xm], c = r1[sx], e = r1[xp];
+  const int sw = r2[xm], s = r2[sx], se = r2[xp];
+  const int cross = (n + s + w + e + 2) >> 2, diag = (nw + ne + sw + se + 2) >> 2;
+  const int horiz = (w + e + 1) >> 1, vert = (n + s + 1) >> 1;
+  const bool red_row = ((sy & 1) == red_y), red_col = ((sx & 1) == red_x);
+  const bool is_r = red_row && red_col, is_b = !red_row && !red_col;
+  G = (is_r || is_b) ? cross : c;
+  R = is_r ? c : (is_b ? diag : (red_row ? horiz : vert));
+  B = is_b ? c : (is_r ? diag : (red_row ? vert : horiz));
 }
 
 __device__ __forceinline__ float lerp4(float p00, float p01, float p10, float p11, float fx,
