@@ -426,3 +426,27 @@ def test_cpp_drop_in_classes(base_image, weights_seed0, tmp_path):
     np.testing.assert_allclose([float(v) for v in pnp[4:7]], [1.14443091, -0.9268353, 1.21457493], rtol=1e-6)
     np.testing.assert_allclose([float(v) for v in pnp[8:11]], [0.00508322, 0.02282537, 1.30085669], rtol=1e-6)
     eng.close()
+
+
+def test_pnp_stress_one_million_properties():
+    """BASELINE.json configs[4] at full size: properties that do not need the CPU oracle at 1M --
+    every solve succeeds, the returned pose reprojects onto its quad (normalised RMSE of the first
+    IPPE solution <= the second), and results are independent of batch position."""
+    import irmv_detection_b200 as irmv
+    from oracle import pnp_ref as P
+    _cuda()
+    base = P.synth_quads(5000, seed=3)
+    n = 1_000_000
+    q = np.tile(base, (n // len(base), 1, 1))
+    s = irmv.PnPSolver(P.K_DEFAULT, P.D_DEFAULT)
+    rv, tv, ok, quat, rv2, tv2, rmse = s.solve_batch(q, extended=True)
+    assert ok.all() and np.isfinite(rv).all() and np.isfinite(tv).all()
+    assert (rmse[:, 0] <= rmse[:, 1] + 1e-12).all()
+    assert rmse[:, 0].max() < 5e-3                       # 0.5 px noise / f ~ 1e-3 in normalised units
+    assert (tv[:, 2] > 0.3).all() and (tv[:, 2] < 12).all()
+    np.testing.assert_allclose(np.linalg.norm(quat, axis=1), 1.0, atol=1e-9)
+    # tiling: copy k of the base set equals copy 0 bit for bit
+    assert np.array_equal(rv[:5000], rv[-5000:]) and np.array_equal(tv[:5000], tv[-5000:])
+    r1, t1 = P.solve_ippe(base)
+    rel = np.linalg.norm(rv[:5000] - r1, axis=1) / np.linalg.norm(r1, axis=1)
+    assert np.quantile(rel, 0.99) < PNP_REL_TOL
