@@ -14,14 +14,19 @@
 //                      cp.async.bulk per plane fills the tile  [cin/8][PP pixels][8 halfs]  -- the
 //                      K-major, unswizzled UMMA operand layout, in which a tap shift is just
 //                      +16 bytes per pixel on the descriptor's start address.  One mbarrier
-//                      (expect_tx) hand-off per TILE; the weights are loaded once the same way.
-//   warp 9             issues R * taps * cin/16 tcgen05.mma per tile back to back.
+//                      (expect_tx) hand-off per TILE.  Weights: resident (one load per CTA) when
+//                      they fit next to two activation stages, otherwise streamed tap by tap
+//                      through a small ring (layers with cin*cout >= 128*128).
+//   warp 9 (one lane)  issues R * taps * cin/16 tcgen05.mma per tile back to back.  The loop is
+//                      written so that every operand is a warp-uniform add on the previous one
+//                      (descriptor low words, TMEM column): measured with scripts/mma_probe.cu the
+//                      tensor pipe sustains max(N/2, 32 + N/4) cycles per M128 x N x K16 MMA for
+//                      ANY operand layout, but a single thread that rebuilds 64-bit descriptors
+//                      per MMA only issues one every 90-200 cycles.
 //   warps 0-7          epilogue out of double-buffered TMEM: bias, SiLU, residual, FP16; a warp
 //                      stores 32 consecutive pixels of one plane = 512 contiguous bytes; padding
-//                      pixels are skipped so the zero border is preserved.
-//
-// Against the per-tap gather kernel this cuts L2->SM traffic and load instructions ~4x for 3x3
-// layers and the number of producer/consumer hand-offs 9x.
+//                      pixels are skipped so the zero border is preserved.  tcgen05.ld of the
+//                      next 16-column chunk is in flight while the current one is processed.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -29,16 +34,17 @@
 namespace irmv {
 namespace {
 
-constexpr int NEPI_WARPS = 8;               // warps 0-7 (TMEM lane quarter = warp % 4)
-constexpr int TMA_WARP = 8;
-constexpr int MMA_WARP = 9;
-constexpr int NTHREADS = 10 * 32;
+// warps 0..NEPI-1: epilogue (TMEM lane quarter = warp % 4); warp NEPI: TMA producer; warp NEPI+1: MMA issuer.
+// NEPI = 8 when two CTAs share an SM (16 epilogue warps per SM either way), 16 otherwise.
 constexpr int MAX_STAGES = 4;
+constexpr int MAX_BSTAGES = 4;
 constexpr int SMEM_BUDGET = 226 * 1024;     // 232448 B is the opt-in maximum per CTA
 
 struct Bars {
   uint64_t full[MAX_STAGES];
   uint64_t empty[MAX_STAGES];
+  uint64_t bw_full[MAX_BSTAGES];
+  uint64_t bw_empty[MAX_BSTAGES];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint64_t bfull;
@@ -79,29 +85,30 @@ __device__ __forceinline__ uint32_t elect_one() {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                           uint32_t accumulate) {
+// descriptors as (lo, hi) words: only the low word (start address, LBO) ever changes
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi,
+                                           uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+      ".reg .b64 da, db;\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+      "}" ::"r"(tmem_d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
@@ -115,51 +122,125 @@ __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sy
 
 // K-major operand without swizzle: 8x(16 B) core matrices; SBO = bytes between 8-row groups
 // (128, rows are 16 B apart), LBO = bytes between the two 16-byte K halves of one MMA.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)(128 >> 4) << 32;
-  d |= (uint64_t)1 << 46;          // descriptor version (Blackwell); layout type 0 = no swizzle
-  return d;
+// Low word: start address >> 4 | (LBO >> 4) << 16; high word: SBO >> 4, descriptor version 1
+// (bit 46), layout type 0 = no swizzle.
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
 }
-
-__device__ __forceinline__ float silu(float x) {
-  const float h = 0.5f * x;
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
-  return fmaf(h, t, h);
-}
+constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);
 
 struct RArgs {
   ConvParams p;
   int R, TM, PP, halo_front, npix_need;   // rows = 128*R; PP = plane pitch (pixels); halo before q0
   int NCH, taps, Wp, Hp1;                 // cin/8, 1 or 9, W+1, H+1
   int q_begin, q_end, num_tiles, stages, tmem_cols, ctas_per_sm;
+  int b_stream, b_stages;                 // weights streamed chunk by chunk through b_stages ring slots
+  int dbg;                                // debug switches (IRMV_RASTER_DBG)
+  int nchunks, chunk_pairs;               // K chunks (a tap, or 64 channels of a wide 1x1) and K16 steps per chunk
   long long npix;                         // raster pixels of the tensors for this batch
   uint32_t idesc, mul_wp, mul_hp1;        // magic dividers (q / Wp, row / (H+1)), >> 34
-  uint32_t a_stage_bytes, b_bytes, off_b, off_bias, off_bars;
+  uint32_t a_stage_bytes, b_bytes, b_tap_bytes, off_b, off_bias, off_bars;
+  uint32_t tap_a[9];                      // per chunk: A start offset inside a stage, 16-byte units
 };
 
-__global__ void __launch_bounds__(NTHREADS) conv_raster_kernel(const __grid_constant__ RArgs a) {
+// One 16-column chunk of one accumulator: bias, SiLU, residual, FP16, two 16-byte plane stores.
+// hb: bias / 2 (ACT: folded into the SiLU argument) or the bias itself.
+template <bool ACT, bool RES>
+__device__ __forceinline__ void epi_chunk(const uint32_t (&v32)[16], const float *hb, __half *o, long long out_ps,
+                                          const uint4 &r0, const uint4 &r1, int dbg) {
+  float b[16];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 t = *reinterpret_cast<const float4 *>(hb + 4 * j);   // same address in every lane: broadcast
+    b[4 * j] = t.x; b[4 * j + 1] = t.y; b[4 * j + 2] = t.z; b[4 * j + 3] = t.w;
+  }
+  float v[16];
+  if (ACT && (dbg & 4)) {
+    // packed variant: tanh.approx.f16x2, one MUFU per two elements
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float h0 = fmaf(__uint_as_float(v32[2 * j]), 0.5f, b[2 * j]);
+      const float h1 = fmaf(__uint_as_float(v32[2 * j + 1]), 0.5f, b[2 * j + 1]);
+      const __half2 hh = __floats2half2_rn(h0, h1);
+      uint32_t t2;
+      asm("tanh.approx.f16x2 %0, %1;" : "=r"(t2) : "r"(*reinterpret_cast<const uint32_t *>(&hh)));
+      const float2 tf = __half22float2(*reinterpret_cast<const __half2 *>(&t2));
+      v[2 * j] = fmaf(h0, tf.x, h0);
+      v[2 * j + 1] = fmaf(h1, tf.y, h1);
+    }
+  } else if (ACT && (dbg & 1)) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float h = fmaf(__uint_as_float(v32[j]), 0.5f, b[j]);
+      v[j] = fmaf(h, h, h);
+    }
+  } else if (ACT) {
+    // SiLU(x) = x * sigmoid(x) = h + h * tanh(h), h = x / 2: one MUFU per element
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float h = fmaf(__uint_as_float(v32[j]), 0.5f, b[j]);
+      float t;
+      asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+      v[j] = fmaf(h, t, h);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(v32[j]) + b[j];
+  }
+  if (RES) {
+    const __half2 *h0 = reinterpret_cast<const __half2 *>(&r0);
+    const __half2 *h1 = reinterpret_cast<const __half2 *>(&r1);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 f0 = __half22float2(h0[t]), f1 = __half22float2(h1[t]);
+      v[2 * t] += f0.x; v[2 * t + 1] += f0.y;
+      v[8 + 2 * t] += f1.x; v[8 + 2 * t + 1] += f1.y;
+    }
+  }
+  __half2 hv[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) hv[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
+  if (dbg & 2) return;
+  *reinterpret_cast<uint4 *>(o) = *reinterpret_cast<uint4 *>(&hv[0]);
+  *reinterpret_cast<uint4 *>(o + out_ps) = *reinterpret_cast<uint4 *>(&hv[4]);
+}
+
+template <int R, int NEPI, bool ACT, bool RES>
+__global__ void __launch_bounds__((NEPI + 2) * 32) conv_raster_kernel(const __grid_constant__ RArgs a) {
+  constexpr int NTHREADS = (NEPI + 2) * 32;
+  constexpr int TMA_WARP = NEPI, MMA_WARP = NEPI + 1;
   extern __shared__ __align__(1024) uint8_t smem[];
   const ConvParams &p = a.p;
   uint8_t *sA = smem;
   uint8_t *sB = smem + a.off_b;
-  float *s_bias = reinterpret_cast<float *>(smem + a.off_bias);
+  float *s_hb = reinterpret_cast<float *>(smem + a.off_bias);
   Bars *bars = reinterpret_cast<Bars *>(smem + a.off_bars);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int npad = p.npad;
+  // debug trace rows cap+15 (CTA 0) / cap+14 (last CTA): {entry, setup done, exit} clocks + globaltimer ns
+  long long *trow = (p.trace && tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))
+                        ? p.trace + (size_t)(p.trace_cap + (blockIdx.x == 0 ? 15 : 14)) * 8 : nullptr;
+  if (trow) {
+    trow[0] = clock64();
+    unsigned long long g;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    trow[3] = (long long)g;
+  }
 
-  for (int i = tid; i < npad; i += NTHREADS) s_bias[i] = p.bias[i];
+  // act: bias / 2 (folded into the SiLU argument), otherwise the bias itself
+  for (int i = tid; i < npad; i += NTHREADS) s_hb[i] = ACT ? 0.5f * p.bias[i] : p.bias[i];
   if (tid == 0) {
     for (int s = 0; s < a.stages; ++s) {
       mbar_init(&bars->full[s], 1);
       mbar_init(&bars->empty[s], 1);
     }
+    for (int s = 0; s < MAX_BSTAGES; ++s) {
+      mbar_init(&bars->bw_full[s], 1);
+      mbar_init(&bars->bw_empty[s], 1);
+    }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->tmem_full[i], 1);
-      mbar_init(&bars->tmem_empty[i], NEPI_WARPS);
+      mbar_init(&bars->tmem_empty[i], NEPI);
     }
     mbar_init(&bars->bfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -173,106 +254,156 @@ __global__ void __launch_bounds__(NTHREADS) conv_raster_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  if (trow) trow[1] = clock64();
 
-  if (warp < NEPI_WARPS) {
+  if (warp < NEPI) {
     // ===================================================================== epilogue
     // warp w reads TMEM lanes 32*(w%4)..+31 (hardware rule); the two warps of a lane quarter split
-    // the (accumulator, 16-column chunk) work items between them.
-    const int ew = warp & 3, half = warp >> 2;
-    const int chunks = npad >> 4;
+    // the (accumulator, 16-column chunk) work items between them.  Software pipeline: the
+    // tcgen05.ld of item i+1 is issued before item i is processed (tcgen05.wait::ld waits for
+    // every outstanding load, so exactly one load is in flight while the other chunk is computed).
+    // warp w reads TMEM lanes 32*(w%4)..+31 (hardware rule); the NEPI/4 warps of a lane quarter split
+    // the (accumulator, 16-column chunk) work items between them.  Software pipeline: the
+    // tcgen05.ld of the warp's next item is issued before the current one is processed
+    // (tcgen05.wait::ld waits for every outstanding load, so exactly one load is in flight while
+    // the other chunk is computed).
+    constexpr int NSUB = NEPI / 4;
+    const int ew = warp & 3, sub = warp >> 2;
+    const int chunk_shift = 31 - __clz(npad >> 4);          // npad / 16 is a power of two
+    const int chunk_mask = (npad >> 4) - 1;
+    const int items = R << chunk_shift;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(ew * 32) << 16);
+    __half *const out = p.out;
+    const __half *const res = p.res;
+    const long long out_ps = p.out_pstride, res_ps = p.res_pstride;
+    const int cout = p.cout;
+    const int dbg = a.dbg;
+    const int Wp = a.Wp, Hp1 = a.Hp1, W = p.W, q_end = a.q_end, TM = a.TM;
+    const uint32_t mul_wp = a.mul_wp, mul_hp1 = a.mul_hp1;
+    const int q_lane = a.q_begin + ew * 32 + lane;
+    const int num_tiles = a.num_tiles;
+    long long *const trace = p.trace;
+    const int trace_cap = p.trace_cap;
     int it = 0;
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       const uint32_t aph = (uint32_t)(it >> 1) & 1u;
-      const bool tr = p.trace && blockIdx.x == 0 && tid == 0 && it < p.trace_cap;
+      const bool tr = trace && blockIdx.x == 0 && tid == 0 && it < trace_cap;
+      const int q_tile = q_lane + tile * TM;
+      // real pixel? (not the zero column x == W, not a zero row, inside the batch) -- per accumulator
+      uint32_t okmask = 0;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int qi = q_tile + r * 128;
+        const uint32_t row = (uint32_t)(((uint64_t)(uint32_t)qi * mul_wp) >> 34);
+        const int x = qi - (int)row * Wp;
+        const uint32_t img = (uint32_t)(((uint64_t)row * mul_hp1) >> 34);
+        const int yrow = (int)row - (int)img * Hp1;
+        if (qi < q_end && x < W && yrow != 0) okmask |= 1u << r;
+      }
+      __half *const out_q = out + (long long)q_tile * 8;
+      const __half *const res_q = RES ? res + (long long)q_tile * 8 : nullptr;
       mbar_wait_warp(&bars->tmem_full[buf], aph, lane);
       tc_fence_after();
-      if (tr) p.trace[it * 8 + 6] = clock64();
-      const int items = a.R * chunks;
-      for (int w = half; w < items; w += 2) {
-        const int r = w / chunks, c0 = (w - r * chunks) << 4;
-        const int q = a.q_begin + tile * a.TM + r * 128 + ew * 32 + lane;
-        // real pixel? (not the zero column x == W, not a zero row, inside the batch)
-        const uint32_t row = (uint32_t)(((uint64_t)(uint32_t)q * a.mul_wp) >> 34);
-        const int x = q - (int)row * a.Wp;
-        const uint32_t img = (uint32_t)(((uint64_t)row * a.mul_hp1) >> 34);
-        const int yrow = (int)row - (int)img * a.Hp1;
-        const bool ok = q < a.q_end && x < p.W && yrow != 0 && c0 < p.cout;
-        const int pl = c0 >> 3;
-        uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
-        if (ok && p.res) {                                  // residual: issue the loads first
-          q0 = *reinterpret_cast<const uint4 *>(p.res + (size_t)pl * p.res_pstride + (size_t)q * 8);
-          q1 = *reinterpret_cast<const uint4 *>(p.res + (size_t)(pl + 1) * p.res_pstride + (size_t)q * 8);
+      if (tr) trace[it * 8 + 6] = clock64();
+      const uint32_t tcol0 = lane_base + (uint32_t)(buf * R * npad);
+      // item w -> accumulator r = w / chunks, chunk c = w % chunks; this warp takes w = sub, sub+NSUB, ...
+      struct Item { int c0; bool ok; __half *o; uint4 r0, r1; };
+      auto setup = [&](int w, Item &t) -> uint32_t {
+        const int r = w >> chunk_shift;
+        t.c0 = (w & chunk_mask) << 4;
+        t.ok = ((okmask >> r) & 1u) && t.c0 < cout;
+        const long long off = (long long)(t.c0 >> 3) * out_ps + r * 1024;
+        t.o = out_q + off;
+        if (RES && t.ok) {                                  // residual: issue the loads early
+          const __half *rp = res_q + (long long)(t.c0 >> 3) * res_ps + r * 1024;
+          t.r0 = *reinterpret_cast<const uint4 *>(rp);
+          t.r1 = *reinterpret_cast<const uint4 *>(rp + res_ps);
         }
-        uint32_t v32[16];
-        tc_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)((buf * a.R + r) * npad + c0), v32);
-        tc_ld_wait();
-        if (!ok) continue;
-        float v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float xv = __uint_as_float(v32[j]) + s_bias[c0 + j];
-          v[j] = p.act ? silu(xv) : xv;
-        }
-        if (p.res) {
-          const __half2 *h0 = reinterpret_cast<const __half2 *>(&q0);
-          const __half2 *h1 = reinterpret_cast<const __half2 *>(&q1);
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            float2 f0 = __half22float2(h0[t]), f1 = __half22float2(h1[t]);
-            v[2 * t] += f0.x; v[2 * t + 1] += f0.y;
-            v[8 + 2 * t] += f1.x; v[8 + 2 * t + 1] += f1.y;
-          }
-        }
-        __half2 hv[8];
-#pragma unroll
-        for (int t = 0; t < 8; ++t) hv[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
-        *reinterpret_cast<uint4 *>(p.out + (size_t)pl * p.out_pstride + (size_t)q * 8) = *reinterpret_cast<uint4 *>(&hv[0]);
-        *reinterpret_cast<uint4 *>(p.out + (size_t)(pl + 1) * p.out_pstride + (size_t)q * 8) = *reinterpret_cast<uint4 *>(&hv[4]);
+        return tcol0 + (uint32_t)(r * npad + t.c0);
+      };
+      uint32_t va[16], vb[16];
+      Item ia, ib;
+      ia.r0 = ia.r1 = ib.r0 = ib.r1 = make_uint4(0, 0, 0, 0);
+      int w = sub;
+      if (w < items) tc_ld16(setup(w, ia), va);
+      while (w < items) {
+        tc_ld_wait();                                       // va ready
+        const bool more_b = w + NSUB < items;
+        if (more_b) tc_ld16(setup(w + NSUB, ib), vb);
+        if (ia.ok) epi_chunk<ACT, RES>(va, s_hb + ia.c0, ia.o, out_ps, ia.r0, ia.r1, dbg);
+        if (!more_b) break;
+        tc_ld_wait();                                       // vb ready
+        const bool more_a = w + 2 * NSUB < items;
+        if (more_a) tc_ld16(setup(w + 2 * NSUB, ia), va);
+        if (ib.ok) epi_chunk<ACT, RES>(vb, s_hb + ib.c0, ib.o, out_ps, ib.r0, ib.r1, dbg);
+        if (!more_a) break;
+        w += 2 * NSUB;
       }
       // all of this warp's TMEM reads of the buffer are done: hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->tmem_empty[buf]);
-      if (tr) p.trace[it * 8 + 7] = clock64();
+      if (tr) trace[it * 8 + 7] = clock64();
     }
   } else if (warp == TMA_WARP) {
     // ===================================================================== TMA producer
     if (elect_one()) {
-      mbar_expect_tx(&bars->bfull, a.b_bytes);
-      for (uint32_t off = 0; off < a.b_bytes; off += 65536u) {
-        const uint32_t n = a.b_bytes - off < 65536u ? a.b_bytes - off : 65536u;
-        bulk_g2s(sB + off, reinterpret_cast<const uint8_t *>(p.w_raster) + off, n, &bars->bfull);
+      const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+      if (!a.b_stream) {
+        const uint32_t bar = smem_u32(&bars->bfull);
+        mbar_expect_tx(bar, a.b_bytes);
+        for (uint32_t off = 0; off < a.b_bytes; off += 65536u) {
+          const uint32_t n = a.b_bytes - off < 65536u ? a.b_bytes - off : 65536u;
+          bulk_g2s(sB_u + off, reinterpret_cast<const uint8_t *>(p.w_raster) + off, n, bar);
+        }
       }
-      int s = 0, itl = 0;
-      uint32_t ph = 0;
+      int s = 0, itl = 0, bs = 0;
+      uint32_t ph = 0, bph = 0;
       const uint32_t plane_bytes = (uint32_t)a.npix_need * 16u;
+      const uint32_t pitch_bytes = (uint32_t)a.PP * 16u;
+      const uint32_t tile_tx = plane_bytes * (uint32_t)a.NCH;
+      const int n0 = p.seg[0].c >> 3, n1 = p.nseg > 1 ? p.seg[1].c >> 3 : 0;
+      const size_t ps0 = (size_t)p.seg[0].pstride * 2, ps1 = (size_t)p.seg[1].pstride * 2;
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++itl) {
         const bool tr = p.trace && blockIdx.x == 0 && itl < p.trace_cap;
         if (tr) p.trace[itl * 8 + 0] = clock64();
         const long long qlo = (long long)a.q_begin + (long long)tile * a.TM - a.halo_front;
         mbar_wait(&bars->empty[s], ph ^ 1u);
         if (tr) p.trace[itl * 8 + 1] = clock64();
-        uint8_t *stage = sA + (size_t)s * a.a_stage_bytes;
-        mbar_expect_tx(&bars->full[s], plane_bytes * (uint32_t)a.NCH);
-        int plane = 0;
-        for (int sg = 0; sg < p.nseg; ++sg) {
-          const __half *src = p.seg[sg].ptr + qlo * 8;
-          const long long ps = p.seg[sg].pstride;
-          for (int c = 0; c < (p.seg[sg].c >> 3); ++c, ++plane)
-            bulk_g2s(stage + (size_t)plane * a.PP * 16, src + (long long)c * ps, plane_bytes, &bars->full[s]);
-        }
+        const uint32_t bar = smem_u32(&bars->full[s]);
+        mbar_expect_tx(bar, tile_tx);
+        uint32_t dst = sA_u + (uint32_t)s * a.a_stage_bytes;
+        const uint8_t *src = reinterpret_cast<const uint8_t *>(p.seg[0].ptr) + qlo * 16;
+        for (int c = 0; c < n0; ++c, dst += pitch_bytes, src += ps0) bulk_g2s(dst, src, plane_bytes, bar);
+        src = reinterpret_cast<const uint8_t *>(p.seg[1].ptr) + qlo * 16;
+        for (int c = 0; c < n1; ++c, dst += pitch_bytes, src += ps1) bulk_g2s(dst, src, plane_bytes, bar);
         if (tr) p.trace[itl * 8 + 2] = clock64();
         if (++s == a.stages) { s = 0; ph ^= 1u; }
+        if (a.b_stream) {
+          const uint8_t *wsrc = reinterpret_cast<const uint8_t *>(p.w_raster);
+          for (int t = 0; t < a.nchunks; ++t, wsrc += a.b_tap_bytes) {
+            mbar_wait(&bars->bw_empty[bs], bph ^ 1u);
+            const uint32_t bbar = smem_u32(&bars->bw_full[bs]);
+            mbar_expect_tx(bbar, a.b_tap_bytes);
+            bulk_g2s(sB_u + (uint32_t)bs * a.b_tap_bytes, wsrc, a.b_tap_bytes, bbar);
+            if (++bs == a.b_stages) { bs = 0; bph ^= 1u; }
+          }
+        }
       }
     }
   } else {
     // ===================================================================== MMA issuer
-    mbar_wait_warp(&bars->bfull, 0, lane);
-    int it = 0, s = 0;
-    uint32_t ph = 0;
-    const uint32_t lbo_a = (uint32_t)a.PP * 16u, lbo_b = (uint32_t)npad * 16u;
-    const int pairs = a.NCH >> 1;
+    if (!a.b_stream) mbar_wait_warp(&bars->bfull, 0, lane);
+    int it = 0, s = 0, bs = 0;
+    uint32_t ph = 0, bph = 0;
+    const uint32_t a_lo0 = desc_lo(smem_u32(sA), (uint32_t)a.PP * 16u);
+    const uint32_t b_lo0 = desc_lo(smem_u32(sB), (uint32_t)npad * 16u);
+    const uint32_t a_stage_u = a.a_stage_bytes >> 4;       // descriptor address units are 16 bytes
+    const uint32_t a_pair_u = 2u * (uint32_t)a.PP;         // two 8-channel planes per K16 step
+    const uint32_t b_pair_u = 2u * (uint32_t)npad;
+    const uint32_t b_tap_u = a.b_tap_bytes >> 4;
+    const int pairs = a.chunk_pairs, nchunks = a.nchunks;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       const uint32_t aph = (uint32_t)(it >> 1) & 1u;
@@ -282,30 +413,49 @@ __global__ void __launch_bounds__(NTHREADS) conv_raster_kernel(const __grid_cons
       mbar_wait_warp(&bars->full[s], ph, lane);
       tc_fence_after();
       if (tr) p.trace[it * 8 + 4] = clock64();
-      if (elect_one()) {
-        const uint32_t abase = smem_u32(sA + (size_t)s * a.a_stage_bytes);
-        const uint32_t bbase = smem_u32(sB);
-        // Loop order: accumulator index r innermost.  MMAs into the same TMEM tile form a dependent
-        // chain (measured ~260-320 cycles per MMA at N = 16/32, i.e. pipeline latency, not
-        // throughput), so consecutive issues go to the R independent accumulators of the tile.
-        const uint32_t tmem_d0 = tmem_base + (uint32_t)(buf * a.R * npad);
-        for (int t = 0; t < a.taps; ++t) {
-          const int shift = a.taps == 9 ? (t / 3) * a.Wp + (t % 3) : 0;   // tap shift in pixels
-          const uint32_t arow = abase + (uint32_t)(shift << 4);
-          const uint32_t brow = bbase + (uint32_t)(t * a.NCH * npad) * 16u;
-          for (int j = 0; j < pairs; ++j) {
-            const uint64_t bdesc = make_desc(brow + (uint32_t)(2 * j) * lbo_b, lbo_b);
-            const uint32_t acol = arow + (uint32_t)(2 * j) * lbo_a;
-            const uint32_t acc = (uint32_t)((t | j) != 0);
-            for (int r = 0; r < a.R; ++r)
-              tc_mma_f16(tmem_d0 + (uint32_t)(r * npad), make_desc(acol + (uint32_t)(r * 128 * 16), lbo_a), bdesc,
-                         a.idesc, acc);
+      const uint32_t tmem_d0 = tmem_base + (uint32_t)(buf * R * npad);
+      const uint32_t a_stage_lo = a_lo0 + (uint32_t)s * a_stage_u;
+      if (!a.b_stream) {
+        if (elect_one()) {
+          // MMAs into the R accumulators of the tile are interleaved (r innermost); every operand
+          // below is a uniform add.
+          uint32_t acc = 0;
+          uint32_t bl_t = b_lo0;
+          for (int t = 0; t < nchunks; ++t, bl_t += b_tap_u) {
+            uint32_t al = a_stage_lo + a.tap_a[t], bl = bl_t;
+            for (int j = 0; j < pairs; ++j, al += a_pair_u, bl += b_pair_u) {
+#pragma unroll
+              for (int r = 0; r < R; ++r)
+                tc_mma_f16(tmem_d0 + (uint32_t)(r * npad), al + (uint32_t)(r * 128), kDescHi, bl, kDescHi, a.idesc, acc);
+              acc = 1;
+            }
           }
+          tc_commit(&bars->empty[s]);
+          tc_commit(&bars->tmem_full[buf]);
         }
-        tc_commit(&bars->empty[s]);
-        tc_commit(&bars->tmem_full[buf]);
+        __syncwarp();
+      } else {
+        for (int t = 0; t < nchunks; ++t) {
+          mbar_wait_warp(&bars->bw_full[bs], bph, lane);
+          tc_fence_after();
+          if (elect_one()) {
+            uint32_t al = a_stage_lo + a.tap_a[t], bl = b_lo0 + (uint32_t)bs * b_tap_u;
+            for (int j = 0; j < pairs; ++j, al += a_pair_u, bl += b_pair_u) {
+#pragma unroll
+              for (int r = 0; r < R; ++r)
+                tc_mma_f16(tmem_d0 + (uint32_t)(r * npad), al + (uint32_t)(r * 128), kDescHi, bl, kDescHi, a.idesc,
+                           (t | j) != 0 ? 1u : 0u);
+            }
+            tc_commit(&bars->bw_empty[bs]);
+            if (t == nchunks - 1) {
+              tc_commit(&bars->empty[s]);
+              tc_commit(&bars->tmem_full[buf]);
+            }
+          }
+          __syncwarp();
+          if (++bs == a.b_stages) { bs = 0; bph ^= 1u; }
+        }
       }
-      __syncwarp();
       if (tr) p.trace[it * 8 + 5] = clock64();
       if (++s == a.stages) { s = 0; ph ^= 1u; }
     }
@@ -313,6 +463,12 @@ __global__ void __launch_bounds__(NTHREADS) conv_raster_kernel(const __grid_cons
 
   tc_fence_before();
   __syncthreads();
+  if (trow) {
+    trow[2] = clock64();
+    unsigned long long g;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    trow[4] = (long long)g;
+  }
   if (warp == MMA_WARP) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols) : "memory");
   }
@@ -324,6 +480,10 @@ bool plan(const ConvParams &p, int num_sms, RArgs &a) {
   for (int i = 0; i < p.nseg; ++i) if (p.seg[i].up || p.seg[i].c % 8) return false;
   if (p.W + 2 > kGuardFront || p.cout % 16 != 0) return false;
   a.p = p;
+  {
+    static const int dbg = getenv("IRMV_RASTER_DBG") ? atoi(getenv("IRMV_RASTER_DBG")) : 0;
+    a.dbg = dbg;
+  }
   a.NCH = p.cin / 8;
   a.taps = p.k * p.k;
   a.Wp = p.W + 1;
@@ -333,47 +493,112 @@ bool plan(const ConvParams &p, int num_sms, RArgs &a) {
   a.q_end = (p.B * (p.H + 1)) * a.Wp;               // end of the last image row
   const long long Mr = (long long)a.q_end - a.q_begin;
   a.b_bytes = (uint32_t)((size_t)a.taps * p.cin * p.npad * 2);
+  // K chunks: a tap of a 3x3, or (streamed wide 1x1) 64 input channels
+  a.nchunks = a.taps;
+  a.chunk_pairs = a.NCH >> 1;
+  a.b_tap_bytes = (uint32_t)((size_t)p.cin * p.npad * 2);
   const size_t misc = (size_t)p.npad * 4 + sizeof(Bars) + 1024 + 256;
   const int halo = p.k == 3 ? 2 * a.Wp + 2 : 0;
+  // Bulk copies run fastest when source, destination and size are multiples of 128 bytes (8
+  // pixels): the copied range starts `delta` pixels early so that it begins on an 8-pixel boundary
+  // of the plane (delta is the same for every tile because TM is a multiple of 128), and the tap
+  // offsets absorb the shift.
+  const int halo_front = p.k == 3 ? a.Wp + 1 : 0;
+  const int delta = (((a.q_begin - halo_front) % 8) + 8) % 8;
+  auto plane_pixels = [&](int R) { return (128 * R + halo + delta + 7) & ~7; };
+  auto stage_bytes = [&](int R) { return (size_t)a.NCH * plane_pixels(R) * 16; };
   int best_R = 0;
+  a.b_stream = 0;
   for (int R = 4; R >= 1; R >>= 1) {
     if (2 * R * p.npad > 512) continue;
-    int PP = 128 * R + halo;
-    PP += (9 - (PP & 7)) & 7;                        // PP = 1 (mod 8): conflict-free plane writes
-    size_t stage = (((size_t)a.NCH * PP * 16) + 127) & ~(size_t)127;
-    if (a.b_bytes + 2 * stage + misc > (size_t)SMEM_BUDGET) continue;
+    if (a.b_bytes + 2 * stage_bytes(R) + misc > (size_t)SMEM_BUDGET) continue;
     long long tiles = (Mr + 128 * R - 1) / (128 * R);
     if (R > 1 && tiles < 2LL * num_sms) continue;    // keep every SM busy at small batch
     best_R = R;
     break;
   }
+  if (!best_R && !getenv("IRMV_NO_BSTREAM")) {
+    // weights do not fit next to two activation stages: stream them chunk by chunk.  Larger tiles
+    // amortise the weight traffic (all of the weights once per tile), so prefer the largest R that
+    // still leaves one tile per SM.
+    if (p.k == 1) {
+      if (a.NCH % 8 != 0 || a.NCH / 8 > 9) return false;
+      a.nchunks = a.NCH / 8;
+      a.chunk_pairs = 4;
+      a.b_tap_bytes = (uint32_t)((size_t)64 * p.npad * 2);
+    }
+    for (int R = 4; R >= 1; R >>= 1) {
+      if (2 * R * p.npad > 512) continue;
+      if (2 * (size_t)a.b_tap_bytes + stage_bytes(R) + misc > (size_t)SMEM_BUDGET) continue;
+      long long tiles = (Mr + 128 * R - 1) / (128 * R);
+      if (R > 1 && tiles < (long long)num_sms) continue;
+      best_R = R;
+      a.b_stream = 1;
+      break;
+    }
+  }
   if (!best_R) return false;
   a.R = best_R;
   a.TM = 128 * a.R;
-  a.halo_front = p.k == 3 ? a.Wp + 1 : 0;
-  a.npix_need = a.TM + halo;
-  a.PP = a.npix_need + ((9 - (a.npix_need & 7)) & 7);
-  a.a_stage_bytes = (uint32_t)((((size_t)a.NCH * a.PP * 16) + 127) & ~(size_t)127);
+  a.halo_front = halo_front + delta;
+  a.npix_need = plane_pixels(a.R);
+  a.PP = a.npix_need;
+  a.a_stage_bytes = (uint32_t)stage_bytes(a.R);
   int cols = 2 * a.R * p.npad, alloc = 32;
   while (alloc < cols) alloc <<= 1;
   a.tmem_cols = alloc;
-  // The per-tile chain load -> MMA -> epilogue is latency-bound (profiles: warps mostly asleep on
-  // barriers), so when two CTAs fit on an SM (shared memory and TMEM halves) run two: their
-  // phases interleave and hide each other's latencies.
-  const size_t half_budget = 112 * 1024;
-  const bool two = !getenv("IRMV_ONE_CTA") && alloc <= 256 && a.b_bytes + 2 * (size_t)a.a_stage_bytes + misc <= half_budget;
-  a.ctas_per_sm = two ? 2 : 1;
-  const size_t budget = two ? half_budget : (size_t)SMEM_BUDGET;
-  a.stages = (int)((budget - a.b_bytes - misc) / a.a_stage_bytes);
-  if (a.stages > MAX_STAGES) a.stages = MAX_STAGES;
   a.num_tiles = (int)((Mr + a.TM - 1) / a.TM);
+  size_t b_smem = a.b_bytes;
+  if (a.b_stream) {
+    // split what is left between activation stages (at most 2) and weight ring slots (at most 4)
+    a.ctas_per_sm = 1;
+    size_t left = (size_t)SMEM_BUDGET - misc;
+    a.stages = (left >= 2 * (size_t)a.a_stage_bytes + 2 * (size_t)a.b_tap_bytes) ? 2 : 1;
+    left -= (size_t)a.stages * a.a_stage_bytes;
+    a.b_stages = (int)(left / a.b_tap_bytes);
+    if (a.b_stages > MAX_BSTAGES) a.b_stages = MAX_BSTAGES;
+    b_smem = (size_t)a.b_stages * a.b_tap_bytes;
+  } else {
+    // The per-tile chain load -> MMA -> epilogue has latency bubbles, so when two CTAs fit on an SM
+    // (shared memory and TMEM halves) run two: their phases interleave.
+    const size_t half_budget = 112 * 1024;
+    const bool two = !getenv("IRMV_ONE_CTA") && alloc <= 256 && a.b_bytes + 2 * (size_t)a.a_stage_bytes + misc <= half_budget;
+    a.ctas_per_sm = two ? 2 : 1;
+    const size_t budget = two ? half_budget : (size_t)SMEM_BUDGET;
+    a.stages = (int)((budget - a.b_bytes - misc) / a.a_stage_bytes);
+    if (a.stages > MAX_STAGES) a.stages = MAX_STAGES;
+    a.b_stages = 0;
+  }
   a.idesc = (1u << 4) | ((uint32_t)(p.npad >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   a.mul_wp = (uint32_t)(((1ull << 34) + (uint64_t)a.Wp - 1) / (uint64_t)a.Wp);
   a.mul_hp1 = (uint32_t)(((1ull << 34) + (uint64_t)a.Hp1 - 1) / (uint64_t)a.Hp1);
   a.off_b = (uint32_t)((size_t)a.stages * a.a_stage_bytes);
-  a.off_bias = (a.off_b + a.b_bytes + 127u) & ~127u;
+  a.off_bias = (uint32_t)((a.off_b + b_smem + 127u) & ~(size_t)127u);
   a.off_bars = (a.off_bias + (uint32_t)p.npad * 4 + 15u) & ~15u;
+  for (int t = 0; t < 9; ++t) {
+    if (a.taps == 9) a.tap_a[t] = (uint32_t)(delta + (t / 3) * a.Wp + (t % 3));   // tap shift in pixels
+    else a.tap_a[t] = (uint32_t)(delta + t * 8 * a.PP);                             // 64-channel chunk = 8 planes
+  }
   return true;
+}
+
+template <int R, int NEPI, bool ACT, bool RES>
+cudaError_t launch_k(const RArgs &a, int grid, size_t smem, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_raster_kernel<R, NEPI, ACT, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  conv_raster_kernel<R, NEPI, ACT, RES><<<grid, (NEPI + 2) * 32, smem, s>>>(a);
+  return cudaGetLastError();
+}
+
+template <int R, int NEPI>
+cudaError_t launch_r(const RArgs &a, int grid, size_t smem, cudaStream_t s) {
+  const bool act = a.p.act != 0, res = a.p.res != nullptr;
+  if (act) return res ? launch_k<R, NEPI, true, true>(a, grid, smem, s) : launch_k<R, NEPI, true, false>(a, grid, smem, s);
+  return res ? launch_k<R, NEPI, false, true>(a, grid, smem, s) : launch_k<R, NEPI, false, false>(a, grid, smem, s);
 }
 
 }  // namespace
@@ -386,17 +611,21 @@ bool conv_raster_fits(const ConvParams &p) {
 cudaError_t launch_conv_raster(const ConvParams &p, int num_sms, cudaStream_t s) {
   RArgs a;
   if (!plan(p, num_sms, a)) return cudaErrorInvalidValue;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
-  size_t smem = (size_t)a.off_bars + sizeof(Bars) + 64;
+  const size_t smem = (size_t)a.off_bars + sizeof(Bars) + 64;
   const int slots = num_sms * a.ctas_per_sm;
-  int grid = a.num_tiles < slots ? a.num_tiles : slots;
-  conv_raster_kernel<<<grid, NTHREADS, smem, s>>>(a);
-  return cudaGetLastError();
+  const int grid = a.num_tiles < slots ? a.num_tiles : slots;
+  if (a.ctas_per_sm == 2) {
+    switch (a.R) {
+      case 4: return launch_r<4, 8>(a, grid, smem, s);
+      case 2: return launch_r<2, 8>(a, grid, smem, s);
+      default: return launch_r<1, 8>(a, grid, smem, s);
+    }
+  }
+  switch (a.R) {
+    case 4: return launch_r<4, 16>(a, grid, smem, s);
+    case 2: return launch_r<2, 16>(a, grid, smem, s);
+    default: return launch_r<1, 16>(a, grid, smem, s);
+  }
 }
 
 }  // namespace irmv

@@ -267,7 +267,8 @@ bool lane_alloc(Lane &ln, void **p, size_t bytes) {
 bool new_tensor(Lane &ln, int S, int H, int W, int C, Tensor &t, const char *tap = nullptr) {
   t.H = H; t.W = W; t.C = C;
   // C/8 zeroed planes of [guard | PR raster | guard] pixels x 8 channels
-  const size_t plane_px = (size_t)kGuardFront + (size_t)pr_pixels(S, H, W) + kGuardBack;
+  // planes start on 128-byte boundaries (8 pixels): the raster kernel's bulk copies rely on it
+  const size_t plane_px = ((size_t)kGuardFront + (size_t)pr_pixels(S, H, W) + kGuardBack + 7) & ~(size_t)7;
   t.pstride = (long long)plane_px * 8;
   __half *base = nullptr;
   if (!lane_alloc(ln, (void **)&base, (size_t)(C / 8) * plane_px * 16)) return false;
@@ -941,7 +942,7 @@ int irmv_engine_trace_conv(irmv_engine *e, int op_index, int nframes, long long 
   cudaFree(d);
   if (ce != cudaSuccess) { set_error(cudaGetErrorString(ce)); return -1; }
   int M = p.B * p.OH * p.OW, tiles = (M + 127) / 128;
-  if (op->raster) return cap_tiles < 12 ? cap_tiles : 12;
+  if (op->raster) return cap_tiles;   // rows past the CTA's last tile stay zero
   int per_cta = (tiles + (tiles < e->num_sms ? tiles : e->num_sms) - 1) / (tiles < e->num_sms ? tiles : e->num_sms);
   return per_cta < cap_tiles ? per_cta : cap_tiles;
 }
