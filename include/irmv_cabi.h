@@ -125,6 +125,8 @@ int irmv_engine_fetch_poses(irmv_engine *e, int nframes, double *rvecs, double *
 int irmv_engine_profile_stages(irmv_engine *e, const uint8_t *frames_dev, int nframes, float ms[5]);
 
 /* Debug/tuning: per-tile clock64 stamps of CTA 0 for GEMM `op_index` (see engine.cu). */
+/* Debug: per-kernel CUDA-event times (ms) of the network stage of one eager replay. */
+int irmv_engine_profile_ops(irmv_engine *e, const uint8_t *frames_dev, int nframes, float *ms, int cap);
 int irmv_engine_trace_conv(irmv_engine *e, int op_index, int nframes, long long *out, int cap_tiles,
                            float *kernel_ms);
 

@@ -54,8 +54,9 @@ struct PreprocessParams {
 };
 cudaError_t launch_preprocess(const PreprocessParams &p, cudaStream_t s);
 // Fused preprocess + conv0 (3x3 s2, 3->16, SiLU): w = [16][9 taps][3] FP32, writes two planes.
+// out2 (optional): parity-split twin of the output (see ConvParams).
 cudaError_t launch_stem(const PreprocessParams &p, const float *w, const float *bias, __half *out,
-                        long long out_pstride, cudaStream_t s);
+                        long long out_pstride, __half *out2, long long out2_pstride, cudaStream_t s);
 
 // ---------------------------------------------------------------- convolution
 struct ConvSeg {
@@ -82,10 +83,18 @@ struct ConvParams {
   const __half *w_raster;  // [k*k][cin/8][npad][8]                          (tcgen05 raster kernel)
   const int32_t *ktab;     // [kpad/8][2] {pixel offset of the tap, meta} (tcgen05 gather kernel)
   const float *bias;       // [npad]
-  __half *out;             // pixel 0 of the first output plane
+  __half *out;             // pixel 0 of the first output plane (raster kernel: null = only the parity twin is written)
   long long out_pstride;
   const __half *res;       // residual added after the activation (same grid as out); may be null
   long long res_pstride;
+  // Parity-split twin tensors (raster kernel only).  A tensor of C channels on an H x W grid is
+  // stored a second time as 4 * C/8 planes ordered [parity g = (y&1)*2 + (x&1)][C/8], each a padded
+  // raster of the (H/2) x (W/2) pixels of that parity.  A 3x3 / stride-2 / pad-1 tap (ky, kx) then
+  // reads parity ((ky != 1), (kx != 1)) at the constant raster offset (ky == 0 ? -Wp : 0) +
+  // (kx == 0 ? -1 : 0) of the OUTPUT raster, so stride-2 layers run on the halo-tile kernel too.
+  int in_parity;           // 1: seg[0].ptr / pstride describe the parity twin of the input
+  __half *out2;            // parity twin of the output (written in addition to `out`); may be null
+  long long out2_pstride;
   int sync_mode;           // tcgen05 producer hand-off: 0 = cp.async-tracked mbarrier, 1 = wait+fence
   long long *trace;        // debug: CTA 0 writes per-tile clock64 stamps [tile][8]; null in production
   int trace_cap;

@@ -132,7 +132,7 @@ constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);
 struct RArgs {
   ConvParams p;
   int R, TM, PP, halo_front, npix_need;   // rows = 128*R; PP = plane pitch (pixels); halo before q0
-  int NCH, taps, Wp, Hp1;                 // cin/8, 1 or 9, W+1, H+1
+  int NCH, NP, taps, Wp, Hp1;             // cin/8, planes per stage, 1 or 9, OW+1, OH+1
   int q_begin, q_end, num_tiles, stages, tmem_cols, ctas_per_sm;
   int b_stream, b_stages;                 // weights streamed chunk by chunk through b_stages ring slots
   int dbg;                                // debug switches (IRMV_RASTER_DBG)
@@ -147,7 +147,7 @@ struct RArgs {
 // hb: bias / 2 (ACT: folded into the SiLU argument) or the bias itself.
 template <bool ACT, bool RES>
 __device__ __forceinline__ void epi_chunk(const uint32_t (&v32)[16], const float *hb, __half *o, long long out_ps,
-                                          const uint4 &r0, const uint4 &r1, int dbg) {
+                                          __half *o2, long long out2_ps, const uint4 &r0, const uint4 &r1, int dbg) {
   float b[16];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -201,12 +201,18 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v32)[16], const float
 #pragma unroll
   for (int t = 0; t < 8; ++t) hv[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
   if (dbg & 2) return;
-  *reinterpret_cast<uint4 *>(o) = *reinterpret_cast<uint4 *>(&hv[0]);
-  *reinterpret_cast<uint4 *>(o + out_ps) = *reinterpret_cast<uint4 *>(&hv[4]);
+  if (o) {
+    *reinterpret_cast<uint4 *>(o) = *reinterpret_cast<uint4 *>(&hv[0]);
+    *reinterpret_cast<uint4 *>(o + out_ps) = *reinterpret_cast<uint4 *>(&hv[4]);
+  }
+  if (o2) {                                                 // parity-split twin (stride-2 consumer)
+    *reinterpret_cast<uint4 *>(o2) = *reinterpret_cast<uint4 *>(&hv[0]);
+    *reinterpret_cast<uint4 *>(o2 + out2_ps) = *reinterpret_cast<uint4 *>(&hv[4]);
+  }
 }
 
 template <int R, int NEPI, bool ACT, bool RES>
-__global__ void __launch_bounds__((NEPI + 2) * 32) conv_raster_kernel(const __grid_constant__ RArgs a) {
+__global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raster_kernel(const __grid_constant__ RArgs a) {
   constexpr int NTHREADS = (NEPI + 2) * 32;
   constexpr int TMA_WARP = NEPI, MMA_WARP = NEPI + 1;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -278,7 +284,10 @@ __global__ void __launch_bounds__((NEPI + 2) * 32) conv_raster_kernel(const __gr
     const long long out_ps = p.out_pstride, res_ps = p.res_pstride;
     const int cout = p.cout;
     const int dbg = a.dbg;
-    const int Wp = a.Wp, Hp1 = a.Hp1, W = p.W, q_end = a.q_end, TM = a.TM;
+    const int Wp = a.Wp, Hp1 = a.Hp1, W = p.OW, q_end = a.q_end, TM = a.TM;
+    __half *const out2 = p.out2;
+    const long long out2_ps = p.out2_pstride;
+    const int Wp2 = (p.OW >> 1) + 1, Hp2 = (p.OH >> 1) + 1, cpl = cout >> 3;
     const uint32_t mul_wp = a.mul_wp, mul_hp1 = a.mul_hp1;
     const int q_lane = a.q_begin + ew * 32 + lane;
     const int num_tiles = a.num_tiles;
@@ -292,6 +301,7 @@ __global__ void __launch_bounds__((NEPI + 2) * 32) conv_raster_kernel(const __gr
       const int q_tile = q_lane + tile * TM;
       // real pixel? (not the zero column x == W, not a zero row, inside the batch) -- per accumulator
       uint32_t okmask = 0;
+      int pl2[R], px2[R];                                     // parity twin: first plane / pixel of this lane's pixel
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const int qi = q_tile + r * 128;
@@ -300,6 +310,9 @@ __global__ void __launch_bounds__((NEPI + 2) * 32) conv_raster_kernel(const __gr
         const uint32_t img = (uint32_t)(((uint64_t)row * mul_hp1) >> 34);
         const int yrow = (int)row - (int)img * Hp1;
         if (qi < q_end && x < W && yrow != 0) okmask |= 1u << r;
+        const int y = yrow - 1;
+        pl2[r] = ((y & 1) * 2 + (x & 1)) * cpl;
+        px2[r] = ((int)img * Hp2 + 1 + (y >> 1)) * Wp2 + (x >> 1);
       }
       __half *const out_q = out + (long long)q_tile * 8;
       const __half *const res_q = RES ? res + (long long)q_tile * 8 : nullptr;
@@ -308,13 +321,14 @@ __global__ void __launch_bounds__((NEPI + 2) * 32) conv_raster_kernel(const __gr
       if (tr) trace[it * 8 + 6] = clock64();
       const uint32_t tcol0 = lane_base + (uint32_t)(buf * R * npad);
       // item w -> accumulator r = w / chunks, chunk c = w % chunks; this warp takes w = sub, sub+NSUB, ...
-      struct Item { int c0; bool ok; __half *o; uint4 r0, r1; };
+      struct Item { int c0; bool ok; __half *o, *o2; uint4 r0, r1; };
       auto setup = [&](int w, Item &t) -> uint32_t {
         const int r = w >> chunk_shift;
         t.c0 = (w & chunk_mask) << 4;
         t.ok = ((okmask >> r) & 1u) && t.c0 < cout;
         const long long off = (long long)(t.c0 >> 3) * out_ps + r * 1024;
-        t.o = out_q + off;
+        t.o = out ? out_q + off : nullptr;
+        t.o2 = out2 ? out2 + (long long)(pl2[r] + (t.c0 >> 3)) * out2_ps + (long long)px2[r] * 8 : nullptr;
         if (RES && t.ok) {                                  // residual: issue the loads early
           const __half *rp = res_q + (long long)(t.c0 >> 3) * res_ps + r * 1024;
           t.r0 = *reinterpret_cast<const uint4 *>(rp);
@@ -331,12 +345,12 @@ __global__ void __launch_bounds__((NEPI + 2) * 32) conv_raster_kernel(const __gr
         tc_ld_wait();                                       // va ready
         const bool more_b = w + NSUB < items;
         if (more_b) tc_ld16(setup(w + NSUB, ib), vb);
-        if (ia.ok) epi_chunk<ACT, RES>(va, s_hb + ia.c0, ia.o, out_ps, ia.r0, ia.r1, dbg);
+        if (ia.ok) epi_chunk<ACT, RES>(va, s_hb + ia.c0, ia.o, out_ps, ia.o2, out2_ps, ia.r0, ia.r1, dbg);
         if (!more_b) break;
         tc_ld_wait();                                       // vb ready
         const bool more_a = w + 2 * NSUB < items;
         if (more_a) tc_ld16(setup(w + 2 * NSUB, ia), va);
-        if (ib.ok) epi_chunk<ACT, RES>(vb, s_hb + ib.c0, ib.o, out_ps, ib.r0, ib.r1, dbg);
+        if (ib.ok) epi_chunk<ACT, RES>(vb, s_hb + ib.c0, ib.o, out_ps, ib.o2, out2_ps, ib.r0, ib.r1, dbg);
         if (!more_a) break;
         w += 2 * NSUB;
       }
@@ -362,8 +376,8 @@ __global__ void __launch_bounds__((NEPI + 2) * 32) conv_raster_kernel(const __gr
       uint32_t ph = 0, bph = 0;
       const uint32_t plane_bytes = (uint32_t)a.npix_need * 16u;
       const uint32_t pitch_bytes = (uint32_t)a.PP * 16u;
-      const uint32_t tile_tx = plane_bytes * (uint32_t)a.NCH;
-      const int n0 = p.seg[0].c >> 3, n1 = p.nseg > 1 ? p.seg[1].c >> 3 : 0;
+      const uint32_t tile_tx = plane_bytes * (uint32_t)a.NP;
+      const int n0 = p.in_parity ? a.NP : p.seg[0].c >> 3, n1 = p.nseg > 1 ? p.seg[1].c >> 3 : 0;
       const size_t ps0 = (size_t)p.seg[0].pstride * 2, ps1 = (size_t)p.seg[1].pstride * 2;
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++itl) {
         const bool tr = p.trace && blockIdx.x == 0 && itl < p.trace_cap;
@@ -475,22 +489,32 @@ __global__ void __launch_bounds__((NEPI + 2) * 32) conv_raster_kernel(const __gr
 }
 
 bool plan(const ConvParams &p, int num_sms, RArgs &a) {
-  if (p.stride != 1 || !(p.k == 1 || p.k == 3) || (p.k == 3 && p.pad != 1) || (p.k == 1 && p.pad != 0)) return false;
+  const bool s2 = p.stride == 2;
+  if (s2) {
+    // stride 2: 3x3 / pad 1 over the parity-split twin of the input (common.cuh)
+    if (!p.in_parity || p.k != 3 || p.pad != 1 || p.nseg != 1 || (p.H & 1) || (p.W & 1)) return false;
+  } else {
+    if (p.in_parity || p.stride != 1 || !(p.k == 1 || p.k == 3) || (p.k == 3 && p.pad != 1) || (p.k == 1 && p.pad != 0)) return false;
+  }
   if (p.cin % 16 != 0 || p.npad % 16 != 0 || p.npad > 256) return false;
   for (int i = 0; i < p.nseg; ++i) if (p.seg[i].up || p.seg[i].c % 8) return false;
-  if (p.W + 2 > kGuardFront || p.cout % 16 != 0) return false;
+  if (p.OW + 2 + 8 > kGuardFront || p.cout % 16 != 0) return false;
+  if (p.out2 && ((p.OH & 1) || (p.OW & 1))) return false;
   a.p = p;
   {
     static const int dbg = getenv("IRMV_RASTER_DBG") ? atoi(getenv("IRMV_RASTER_DBG")) : 0;
     a.dbg = dbg;
   }
   a.NCH = p.cin / 8;
+  a.NP = s2 ? 4 * a.NCH : a.NCH;                     // planes per activation stage
   a.taps = p.k * p.k;
-  a.Wp = p.W + 1;
-  a.Hp1 = p.H + 1;
-  a.npix = pr_pixels(p.B, p.H, p.W);
+  // raster geometry of the OUTPUT grid (identical to the input grid for stride 1, and to each
+  // parity sub-raster of the input for stride 2)
+  a.Wp = p.OW + 1;
+  a.Hp1 = p.OH + 1;
+  a.npix = pr_pixels(p.B, p.OH, p.OW);
   a.q_begin = a.Wp;                                  // first pixel of raster row 1
-  a.q_end = (p.B * (p.H + 1)) * a.Wp;               // end of the last image row
+  a.q_end = (p.B * (p.OH + 1)) * a.Wp;              // end of the last image row
   const long long Mr = (long long)a.q_end - a.q_begin;
   a.b_bytes = (uint32_t)((size_t)a.taps * p.cin * p.npad * 2);
   // K chunks: a tap of a 3x3, or (streamed wide 1x1) 64 input channels
@@ -498,7 +522,7 @@ bool plan(const ConvParams &p, int num_sms, RArgs &a) {
   a.chunk_pairs = a.NCH >> 1;
   a.b_tap_bytes = (uint32_t)((size_t)p.cin * p.npad * 2);
   const size_t misc = (size_t)p.npad * 4 + sizeof(Bars) + 1024 + 256;
-  const int halo = p.k == 3 ? 2 * a.Wp + 2 : 0;
+  const int halo = p.k == 3 ? (s2 ? a.Wp + 1 : 2 * a.Wp + 2) : 0;
   // Bulk copies run fastest when source, destination and size are multiples of 128 bytes (8
   // pixels): the copied range starts `delta` pixels early so that it begins on an 8-pixel boundary
   // of the plane (delta is the same for every tile because TM is a multiple of 128), and the tap
@@ -506,7 +530,7 @@ bool plan(const ConvParams &p, int num_sms, RArgs &a) {
   const int halo_front = p.k == 3 ? a.Wp + 1 : 0;
   const int delta = (((a.q_begin - halo_front) % 8) + 8) % 8;
   auto plane_pixels = [&](int R) { return (128 * R + halo + delta + 7) & ~7; };
-  auto stage_bytes = [&](int R) { return (size_t)a.NCH * plane_pixels(R) * 16; };
+  auto stage_bytes = [&](int R) { return (size_t)a.NP * plane_pixels(R) * 16; };
   int best_R = 0;
   a.b_stream = 0;
   for (int R = 4; R >= 1; R >>= 1) {
@@ -576,8 +600,16 @@ bool plan(const ConvParams &p, int num_sms, RArgs &a) {
   a.off_bias = (uint32_t)((a.off_b + b_smem + 127u) & ~(size_t)127u);
   a.off_bars = (a.off_bias + (uint32_t)p.npad * 4 + 15u) & ~15u;
   for (int t = 0; t < 9; ++t) {
-    if (a.taps == 9) a.tap_a[t] = (uint32_t)(delta + (t / 3) * a.Wp + (t % 3));   // tap shift in pixels
-    else a.tap_a[t] = (uint32_t)(delta + t * 8 * a.PP);                             // 64-channel chunk = 8 planes
+    const int ky = t / 3, kx = t % 3;
+    if (s2) {
+      // tap (ky, kx) reads parity group g at offset (ky == 0 ? -Wp : 0) + (kx == 0 ? -1 : 0)
+      const int g = (ky != 1) * 2 + (kx != 1);
+      a.tap_a[t] = (uint32_t)(g * a.NCH * a.PP + delta + (ky == 0 ? 0 : a.Wp) + (kx == 0 ? 0 : 1));
+    } else if (a.taps == 9) {
+      a.tap_a[t] = (uint32_t)(delta + ky * a.Wp + kx);                    // tap shift in pixels
+    } else {
+      a.tap_a[t] = (uint32_t)(delta + t * 8 * a.PP);                      // 64-channel chunk = 8 planes
+    }
   }
   return true;
 }

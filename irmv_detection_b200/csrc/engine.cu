@@ -161,6 +161,9 @@ struct Tensor {            // channel-blocked planar PR layout (common.cuh)
   __half *p = nullptr;     // pixel 0 of plane 0
   long long pstride = 0;   // halfs between planes
   int H = 0, W = 0, C = 0;
+  __half *pp = nullptr;    // parity-split twin (4 * C/8 planes of (H/2) x (W/2) rasters), or null
+  long long pp_stride = 0;
+  bool parity_only = false;  // the producer writes only the twin (every consumer reads the twin)
 };
 
 struct Op {
@@ -277,6 +280,18 @@ bool new_tensor(Lane &ln, int S, int H, int W, int C, Tensor &t, const char *tap
   return true;
 }
 
+// Parity-split twin of `t` (written by t's producer next to the normal layout, read by a
+// stride-2 consumer running on the raster kernel; ConvParams in common.cuh).
+bool add_parity_twin(Lane &ln, int S, Tensor &t, bool only) {
+  t.parity_only = only;
+  const size_t plane_px = ((size_t)kGuardFront + (size_t)pr_pixels(S, t.H / 2, t.W / 2) + kGuardBack + 7) & ~(size_t)7;
+  t.pp_stride = (long long)plane_px * 8;
+  __half *base = nullptr;
+  if (!lane_alloc(ln, (void **)&base, (size_t)(4 * (t.C / 8)) * plane_px * 16)) return false;
+  t.pp = base + (size_t)kGuardFront * 8;
+  return true;
+}
+
 struct SegRef { const Tensor *t; int coff; int c; int up; };
 
 void add_conv(irmv_engine *e, Lane &ln, HostConv &hc, std::vector<SegRef> in, int H, int W,
@@ -322,19 +337,39 @@ void add_conv(irmv_engine *e, Lane &ln, HostConv &hc, std::vector<SegRef> in, in
   p.res_pstride = res ? res->pstride : 0;
   p.sync_mode = 0;
   p.trace = nullptr; p.trace_cap = 0;
+  p.in_parity = 0;
+  p.out2 = nullptr; p.out2_pstride = 0;
+  if (out.pp && out_coff == 0 && hc.cout == out.C) {
+    p.out2 = out.pp; p.out2_pstride = out.pp_stride;
+    if (out.parity_only) p.out = nullptr;
+  }
+  if (hc.stride == 2 && p.nseg == 1 && in[0].t->pp && in[0].coff == 0 && in[0].c == in[0].t->C &&
+      !getenv("IRMV_NO_RASTER") && !getenv("IRMV_NO_S2_RASTER")) {
+    ConvParams q = p;                       // try the raster kernel on the parity twin of the input
+    q.in_parity = 1;
+    q.seg[0].ptr = in[0].t->pp; q.seg[0].pstride = in[0].t->pp_stride;
+    q.seg[1] = q.seg[0];
+    if (conv_raster_fits(q)) p = q;
+    else if (in[0].t->parity_only) fprintf(stderr, "irmv: internal: stride-2 consumer of a parity-only tensor does not fit the raster kernel\n");
+  }
   op.raster = conv_raster_fits(p) && !getenv("IRMV_NO_RASTER");
+  if (p.out2 && !op.raster) { p.out2 = nullptr; p.out = out.p; }   // conv0 as a stand-alone op: the stem kernel writes the twin
   ln.ops.push_back(op);
 }
 
 // C2f (ultralytics): cv1 -> split -> n bottlenecks chained on the last chunk -> cv2 over all chunks.
 // All chunks live in one buffer so split and concat are channel offsets.
 bool add_c2f(irmv_engine *e, Lane &ln, size_t &ci, std::vector<SegRef> in, int H, int W, int c2,
-             int n, bool shortcut, Tensor &out, const char *tap) {
+             int n, bool shortcut, Tensor &out, const char *tap, bool parity_out = false) {
   const int c = c2 / 2;
   Tensor buf, tmp;
   if (!new_tensor(ln, e->S, H, W, (2 + n) * c, buf) || !new_tensor(ln, e->S, H, W, c, tmp) ||
       !new_tensor(ln, e->S, H, W, c2, out, tap))
     return false;
+  if (parity_out) {
+    if (!add_parity_twin(ln, e->S, out, true)) return false;
+    if (tap) ln.taps[tap] = out;
+  }
   add_conv(e, ln, *e->convs[ci++], in, H, W, buf, 0);
   for (int i = 0; i < n; ++i) {
     add_conv(e, ln, *e->convs[ci++], {{&buf, (1 + i) * c, c, 0}}, H, W, tmp, 0);
@@ -355,12 +390,19 @@ bool build_lane(irmv_engine *e, Lane &ln) {
   if (!new_tensor(ln, S, kNet, kNet, kInC, ln.in8, "input")) return false;
   size_t ci = 0;
   Tensor t0, t1, x2, t3, x4, t5, x6, t7, x8, sp, x9, x12, x15, t16, x18, t19, x21;
+  // stride-2 3x3 layers whose operands fit run on the raster kernel from parity-split twins of
+  // their inputs (m1, m3, m5, m16); the producers write the twin next to the normal layout
+  const bool par = e->cfg.conv_impl != IRMV_CONV_DIRECT && !getenv("IRMV_NO_RASTER") && !getenv("IRMV_NO_S2_RASTER");
+  const bool fused = e->fused_stem && e->cfg.conv_impl != IRMV_CONV_DIRECT;
   if (!new_tensor(ln, S, 320, 320, 16, t0, "m0")) return false;
+  if (par && fused && !add_parity_twin(ln, S, t0, true)) return false;
+  ln.taps["m0"] = t0;
   add_conv(e, ln, *e->convs[ci++], {{&ln.in8, 0, kInC, 0}}, 640, 640, t0, 0);
+  ln.ops.back().cp.out2 = nullptr;                 // conv0 as a stand-alone op never writes the twin
   ln.stem_out = t0;
   if (!new_tensor(ln, S, 160, 160, 32, t1, "m1")) return false;
   add_conv(e, ln, *e->convs[ci++], {{&t0, 0, 16, 0}}, 320, 320, t1, 0);
-  if (!add_c2f(e, ln, ci, {{&t1, 0, 32, 0}}, 160, 160, 32, 1, true, x2, "m2")) return false;
+  if (!add_c2f(e, ln, ci, {{&t1, 0, 32, 0}}, 160, 160, 32, 1, true, x2, "m2", par)) return false;
   if (!new_tensor(ln, S, 80, 80, 64, t3, "m3")) return false;
   add_conv(e, ln, *e->convs[ci++], {{&x2, 0, 32, 0}}, 160, 160, t3, 0);
   if (!add_c2f(e, ln, ci, {{&t3, 0, 64, 0}}, 80, 80, 64, 2, true, x4, "m4")) return false;
@@ -431,8 +473,15 @@ bool build_lane(irmv_engine *e, Lane &ln) {
 // Enqueue one replay (n frames) of the whole pipeline on the lane stream.  With `stage_events`
 // the lane's events are recorded between stages (profiling pass, never inside a graph).
 int issue_replay(irmv_engine *e, Lane &ln, int n, cudaStream_t st, int *launches,
-                 bool stage_events = false) {
+                 bool stage_events = false, std::vector<cudaEvent_t> *op_events = nullptr) {
   int cnt = 0;
+  auto op_mark = [&]() {
+    if (!op_events) return;
+    cudaEvent_t ev = nullptr;
+    cudaEventCreate(&ev);
+    cudaEventRecord(ev, st);
+    op_events->push_back(ev);
+  };
   auto mark = [&](int i) -> int {
     if (stage_events) IRMV_CUDA(cudaEventRecord(ln.stage_ev[i], st));
     return 0;
@@ -444,10 +493,11 @@ int issue_replay(irmv_engine *e, Lane &ln, int n, cudaStream_t st, int *launches
   pp.chan_order = e->cfg.chan_order; pp.rotate180 = e->cfg.rotate180;
   pp.resize_mode = e->cfg.resize_mode; pp.quantize_u8 = e->cfg.quantize_u8;
   const bool fused = e->fused_stem && e->cfg.conv_impl != IRMV_CONV_DIRECT;
-  if (fused) IRMV_CUDA(launch_stem(pp, e->d_stem_w, e->d_stem_b, ln.stem_out.p, ln.stem_out.pstride, st));
+  if (fused) IRMV_CUDA(launch_stem(pp, e->d_stem_w, e->d_stem_b, ln.stem_out.parity_only ? nullptr : ln.stem_out.p, ln.stem_out.pstride, ln.stem_out.pp, ln.stem_out.pp_stride, st));
   else IRMV_CUDA(launch_preprocess(pp, st));
   cnt += 1 + (ln.rotated ? 1 : 0);
   if (mark(1)) return 1;
+  op_mark();
   bool first = true;
   for (auto &op : ln.ops) {
     if (first && fused) { first = false; continue; }        // conv0 ran inside the stem kernel
@@ -462,6 +512,7 @@ int issue_replay(irmv_engine *e, Lane &ln, int n, cudaStream_t st, int *launches
       IRMV_CUDA(launch_sppf_pool(op.pool_buf, n, op.pH, op.pW, op.pStride, op.pC, st));
     }
     ++cnt;
+    op_mark();
     if (getenv("IRMV_SYNC_EACH")) {
       cudaError_t ce = cudaStreamSynchronize(st);
       if (ce != cudaSuccess) {
@@ -842,13 +893,26 @@ int irmv_engine_read_tensor(irmv_engine *e, const char *name, void *dst, int64_t
       const int planes = t.C / 8;
       std::vector<uint16_t> tmp(px * 8);
       uint16_t *o = static_cast<uint16_t *>(dst);
-      for (int pl = 0; pl < planes; ++pl) {
+      for (int pl = 0; pl < planes && !t.parity_only; ++pl) {
         IRMV_CUDA(cudaMemcpy(tmp.data(), t.p + (long long)pl * t.pstride, tmp.size() * 2, cudaMemcpyDeviceToHost));
         for (int b = 0; b < nb; ++b)
           for (int y = 0; y < t.H; ++y)
             for (int x = 0; x < t.W; ++x)
               memcpy(o + ((((size_t)b * t.H + y) * t.W + x) * t.C + pl * 8),
                      tmp.data() + (size_t)pr_index(b, y, x, t.H, t.W) * 8, 16);
+      }
+      if (t.parity_only) {               // only the parity-split twin exists: planes [g][C/8] of (H/2) x (W/2)
+        const size_t px2 = (size_t)pr_pixels(nb, t.H / 2, t.W / 2);
+        tmp.resize(px2 * 8);
+        for (int g = 0; g < 4; ++g)
+          for (int pl = 0; pl < planes; ++pl) {
+            IRMV_CUDA(cudaMemcpy(tmp.data(), t.pp + (long long)(g * planes + pl) * t.pp_stride, tmp.size() * 2, cudaMemcpyDeviceToHost));
+            for (int b = 0; b < nb; ++b)
+              for (int y = g >> 1; y < t.H; y += 2)
+                for (int x = g & 1; x < t.W; x += 2)
+                  memcpy(o + ((((size_t)b * t.H + y) * t.W + x) * t.C + pl * 8),
+                         tmp.data() + (size_t)pr_index(b, y >> 1, x >> 1, t.H / 2, t.W / 2) * 8, 16);
+          }
       }
     }
   }
@@ -912,6 +976,25 @@ int irmv_engine_profile_stages(irmv_engine *e, const uint8_t *frames_dev, int nf
   for (int i = 0; i < 4; ++i) IRMV_CUDA(cudaEventElapsedTime(&ms[i], ln.stage_ev[i], ln.stage_ev[i + 1]));
   IRMV_CUDA(cudaEventElapsedTime(&ms[4], ln.stage_ev[0], ln.stage_ev[4]));
   return n;
+}
+
+// One eager replay with a CUDA event after every kernel of the network stage: ms[i] = duration of
+// op i (op 0 = conv0 is inside the stem kernel and reported as 0 when fused).  Returns ops timed.
+int irmv_engine_profile_ops(irmv_engine *e, const uint8_t *frames_dev, int nframes, float *ms, int cap) {
+  if (!e || !frames_dev || !ms || nframes < 1) { set_error("bad argument"); return -1; }
+  cudaSetDevice(e->cfg.device);
+  Lane &ln = e->lanes[0];
+  const int n = nframes < e->S ? nframes : e->S;
+  cudaDeviceSynchronize();
+  set_src_kernel<<<1, 1, 0, ln.stream>>>(ln.src_word, frames_dev);
+  std::vector<cudaEvent_t> evs;
+  int launches = 0;
+  if (issue_replay(e, ln, n, ln.stream, &launches, false, &evs)) return -1;
+  if (cudaStreamSynchronize(ln.stream) != cudaSuccess) { set_error("profile_ops: replay failed"); return -1; }
+  int k = 0;
+  for (size_t i = 1; i < evs.size() && k < cap; ++i, ++k) cudaEventElapsedTime(&ms[k], evs[i - 1], evs[i]);
+  for (auto ev : evs) cudaEventDestroy(ev);
+  return k;
 }
 
 // Debug: re-run GEMM number `op_index` of lane 0 on whatever its input buffers hold, with CTA 0

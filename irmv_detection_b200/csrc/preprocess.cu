@@ -238,7 +238,7 @@ __device__ __forceinline__ float silu_fast(float x) {
 
 __global__ void __launch_bounds__(ST * ST)
 stem_kernel(PreprocessParams p, const float *__restrict__ w, const float *__restrict__ bias, __half *out,
-            long long out_pstride, int pitch_s) {
+            long long out_pstride, __half *out2, long long out2_pstride, int pitch_s) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ float tile[3][SI][SI + 1];
   __shared__ __align__(16) float sw[27 * 16 + 16];   // [tap*3+c][16 outputs] then bias: float4 broadcast loads
@@ -303,8 +303,17 @@ stem_kernel(PreprocessParams p, const float *__restrict__ w, const float *__rest
 #pragma unroll
   for (int t = 0; t < 8; ++t) hv[t] = __floats2half2_rn(silu_fast(acc[2 * t]), silu_fast(acc[2 * t + 1]));
   const size_t pix = (size_t)pr_index(n, oy0 + ty, ox0 + tx, kNet / 2, kNet / 2);
-  *reinterpret_cast<uint4 *>(out + pix * 8) = *reinterpret_cast<uint4 *>(&hv[0]);
-  *reinterpret_cast<uint4 *>(out + out_pstride + pix * 8) = *reinterpret_cast<uint4 *>(&hv[4]);
+  if (out) {
+    *reinterpret_cast<uint4 *>(out + pix * 8) = *reinterpret_cast<uint4 *>(&hv[0]);
+    *reinterpret_cast<uint4 *>(out + out_pstride + pix * 8) = *reinterpret_cast<uint4 *>(&hv[4]);
+  }
+  if (out2) {   // parity-split twin for the stride-2 consumer (common.cuh, ConvParams)
+    const int y = oy0 + ty, x = ox0 + tx;
+    const size_t pix2 = (size_t)pr_index(n, y >> 1, x >> 1, kNet / 4, kNet / 4);
+    __half *o2 = out2 + (long long)(((y & 1) * 2 + (x & 1)) * 2) * out2_pstride + pix2 * 8;
+    *reinterpret_cast<uint4 *>(o2) = *reinterpret_cast<uint4 *>(&hv[0]);
+    *reinterpret_cast<uint4 *>(o2 + out2_pstride) = *reinterpret_cast<uint4 *>(&hv[4]);
+  }
 }
 
 // Optional: materialise the rotated RGB frame (what get_rotated_image() exposes in the reference,
@@ -393,7 +402,7 @@ cudaError_t launch_preprocess(const PreprocessParams &p, cudaStream_t s) {
 
 
 cudaError_t launch_stem(const PreprocessParams &p, const float *w, const float *bias, __half *out,
-                        long long out_pstride, cudaStream_t s) {
+                        long long out_pstride, __half *out2, long long out2_pstride, cudaStream_t s) {
   if (p.n <= 0) return cudaSuccess;
   const bool bayer = p.chan_order >= 2;
   const int bpp = bayer ? 1 : 3;
@@ -408,7 +417,7 @@ cudaError_t launch_stem(const PreprocessParams &p, const float *w, const float *
     if (e != cudaSuccess) return e;
   }
   dim3 grid(kNet / 2 / ST, kNet / 2 / ST, p.n);
-  stem_kernel<<<grid, ST * ST, smem, s>>>(p, w, bias, out, out_pstride, pitch_s);
+  stem_kernel<<<grid, ST * ST, smem, s>>>(p, w, bias, out, out_pstride, out2, out2_pstride, pitch_s);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess && p.rotated) {
     size_t total = (size_t)p.n * p.src_h * p.src_w;
