@@ -270,3 +270,14 @@ def test_gloo_world2_reduction():
     res = sorted(q.get(timeout=120) for _ in ps)
     [p.join(60) for p in ps]
     assert res == [(0, 2.0, 10.0), (1, 2.0, 10.0)]
+
+
+def test_triple_buffer_monotonic(tmp_path):
+    """include/irmv_detection/triple_buffer.hpp under a full-speed producer: the consumer never
+    steps back to an older frame (the reference's two-atomic protocol can; see the header)."""
+    import subprocess
+    exe = tmp_path / "tb_test"
+    subprocess.run(["g++", "-std=c++20", "-O2", "-pthread", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cpp", "triple_buffer_test.cpp"), "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "FAIL" not in r.stdout, r.stdout[-500:]
