@@ -120,6 +120,14 @@ int irmv_engine_enable_pnp(irmv_engine *e, const double K[9], const double D[5],
                            float corner_sy);
 /* rvecs/tvecs: nframes*max_det*3 doubles; slot i of frame f is valid when i < counts[f]. */
 int irmv_engine_fetch_poses(irmv_engine *e, int nframes, double *rvecs, double *tvecs, uint8_t *ok);
+/* Pipelined hand-off for host-resident batches -- the B200 form of the overlap the reference gets
+ * from its TripleBuffer (camera thread fills the next slot while detect() runs on the previous one,
+ * reference README.md:60-63, src/irm_detector.cpp:68-72).  submit queues H2D copy (dedicated copy
+ * stream) + pipeline + D2H of the results and returns; collect waits for that batch and parses it
+ * like detect_batch (rvecs/tvecs/ok may be null).  At most two batches in flight; collect in order. */
+int irmv_engine_submit_batch(irmv_engine *e, const uint8_t *frames_host, int nframes, int *ticket);
+int irmv_engine_collect(irmv_engine *e, int ticket, irmv_bbox *out, int *counts, double *rvecs, double *tvecs,
+                        uint8_t *ok);
 /* One eager replay of min(nframes, sub_batch) device-resident frames with CUDA events between
  * stages: ms = {preprocess, convolutions, decode+NMS, PnP, total}.  Returns frames profiled. */
 int irmv_engine_profile_stages(irmv_engine *e, const uint8_t *frames_dev, int nframes, float ms[5]);

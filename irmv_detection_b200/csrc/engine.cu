@@ -247,7 +247,20 @@ struct irmv_engine {
   std::vector<uint8_t *> slots_host;      // pinned
   uint8_t *slot_dev = nullptr;            // device copy of the frame being detected
   uint8_t *batch_dev = nullptr;           // staging for host-resident batches
-  uint8_t *res_host = nullptr;            // pinned results: max_batch frames
+  uint8_t *res_host = nullptr;            // pinned results: max_batch frames (== sets[0].res_host)
+  // Pipelined hand-off (irmv_engine_submit_batch / _collect): two result sets so that the H2D copy
+  // of batch k+1 (copy stream) runs under the kernels of batch k -- the B200 form of the
+  // reference's camera/detector overlap through its TripleBuffer (reference README.md:60-63).
+  struct Set {
+    uint8_t *res_host = nullptr;          // pinned results of this set
+    uint8_t *batch_dev = nullptr;         // device staging of this set's frames
+    cudaEvent_t done = nullptr;           // all lanes finished (results in res_host)
+    std::vector<cudaEvent_t> h2d;         // per chunk: frames arrived on the device
+    int n = 0;
+  } sets[2];
+  cudaStream_t copy_stream = nullptr;
+  long long next_ticket = 0;
+  size_t res_bytes = 0;
   size_t res_frame_stride = 0;
   double profile_ms = 0.0, device_ms = 0.0;
   bool pnp_on = false;
@@ -569,25 +582,42 @@ int run_replay(irmv_engine *e, Lane &ln, int n) {
 // frames_dev: device pointer to n contiguous frames.  Results land in res_host (pinned).
 // frames_host != null: the frames are still on the host; each chunk is copied on its lane's stream
 // right before its replay, so the H2D of one lane overlaps the compute of the others.
-int enqueue(irmv_engine *e, const uint8_t *frames_dev, int n, const uint8_t *frames_host = nullptr) {
+int enqueue(irmv_engine *e, const uint8_t *frames_dev, int n, const uint8_t *frames_host = nullptr, int set = 0,
+            bool copy_stream = false) {
+  irmv_engine::Set &rs = e->sets[set];
   IRMV_CUDA(cudaEventRecord(e->ev_start, e->main_stream));
   const int S = e->S;
   const int chunks = (n + S - 1) / S;
   const int used = chunks < e->L ? chunks : e->L;
-  for (int l = 0; l < used; ++l) IRMV_CUDA(cudaStreamWaitEvent(e->lanes[l].stream, e->ev_start, 0));
+  // (pipelined submissions keep the lanes free-running: stream order already serialises a lane)
+  if (!copy_stream)
+    for (int l = 0; l < used; ++l) IRMV_CUDA(cudaStreamWaitEvent(e->lanes[l].stream, e->ev_start, 0));
   for (int c = 0; c < chunks; ++c) {
     Lane &ln = e->lanes[c % e->L];
     const int f0 = c * S, nf = (n - f0) < S ? (n - f0) : S;
-    if (frames_host)
+    if (frames_host && copy_stream) {
+      // all H2D copies go back to back on the copy stream; the lane only waits for its own chunk
+      while ((int)rs.h2d.size() <= c) {
+        cudaEvent_t ev = nullptr;
+        IRMV_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        rs.h2d.push_back(ev);
+      }
+      IRMV_CUDA(cudaMemcpyAsync(const_cast<uint8_t *>(frames_dev) + (size_t)f0 * e->frame_bytes,
+                                frames_host + (size_t)f0 * e->frame_bytes, (size_t)nf * e->frame_bytes,
+                                cudaMemcpyHostToDevice, e->copy_stream));
+      IRMV_CUDA(cudaEventRecord(rs.h2d[c], e->copy_stream));
+      IRMV_CUDA(cudaStreamWaitEvent(ln.stream, rs.h2d[c], 0));
+    } else if (frames_host) {
       IRMV_CUDA(cudaMemcpyAsync(const_cast<uint8_t *>(frames_dev) + (size_t)f0 * e->frame_bytes,
                                 frames_host + (size_t)f0 * e->frame_bytes, (size_t)nf * e->frame_bytes,
                                 cudaMemcpyHostToDevice, ln.stream));
+    }
     set_src_kernel<<<1, 1, 0, ln.stream>>>(ln.src_word, frames_dev + (size_t)f0 * e->frame_bytes);
     IRMV_CUDA(cudaGetLastError());
     if (int rc = run_replay(e, ln, nf)) return rc;
     // results: the lane's packed block -> pinned host, one copy per array so a partial replay
     // still lands at the frame's slot
-    uint8_t *h = e->res_host;
+    uint8_t *h = rs.res_host;
     const int md = e->cfg.max_det;
     const size_t B = e->cfg.max_batch;
     IRMV_CUDA(cudaMemcpyAsync(h + (size_t)f0 * 4, ln.det.num(), (size_t)nf * 4, cudaMemcpyDeviceToHost, ln.stream));
@@ -613,15 +643,17 @@ int enqueue(irmv_engine *e, const uint8_t *frames_dev, int n, const uint8_t *fra
     IRMV_CUDA(cudaStreamWaitEvent(e->main_stream, e->lanes[l].done, 0));
   }
   IRMV_CUDA(cudaEventRecord(e->ev_stop, e->main_stream));
+  IRMV_CUDA(cudaEventRecord(rs.done, e->main_stream));
+  rs.n = n;
   e->last_n = n;
   return 0;
 }
 
 // reference parse_output (src/yolo_engine.cpp:202-220)
-void parse(irmv_engine *e, int n, irmv_bbox *out, int *counts) {
+void parse(irmv_engine *e, int n, irmv_bbox *out, int *counts, int set = 0) {
   const int md = e->cfg.max_det;
   const size_t B = e->cfg.max_batch;
-  const uint8_t *h = e->res_host;
+  const uint8_t *h = e->sets[set].res_host;
   const int32_t *num = reinterpret_cast<const int32_t *>(h);
   const float *boxes = reinterpret_cast<const float *>(h + B * 4);
   const float *scores = reinterpret_cast<const float *>(h + B * 4 + B * md * 16);
@@ -744,6 +776,10 @@ int irmv_engine_create(const char *weights_path, const irmv_engine_config *cfg, 
   size_t res_bytes = B * 4 + B * md * (16 + 4 + 4 + 4) + B * md * (24 + 24 + 1) + 64;
   IRMV_CUDA(cudaHostAlloc((void **)&e->res_host, res_bytes, cudaHostAllocDefault));
   memset(e->res_host, 0, res_bytes);
+  e->res_bytes = res_bytes;
+  e->sets[0].res_host = e->res_host;
+  IRMV_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+  for (auto &st : e->sets) IRMV_CUDA(cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
   IRMV_CUDA(cudaDeviceSynchronize());
   *out = e.release();
   return 0;
@@ -769,6 +805,13 @@ void irmv_engine_destroy(irmv_engine *e) {
   cudaFree(e->d_stem_w); cudaFree(e->d_stem_b);
   if (e->batch_dev) cudaFree(e->batch_dev);
   cudaFreeHost(e->res_host);
+  if (e->sets[1].res_host) cudaFreeHost(e->sets[1].res_host);
+  if (e->sets[1].batch_dev) cudaFree(e->sets[1].batch_dev);
+  for (auto &st : e->sets) {
+    if (st.done) cudaEventDestroy(st.done);
+    for (auto ev : st.h2d) cudaEventDestroy(ev);
+  }
+  if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   cudaEventDestroy(e->ev_start); cudaEventDestroy(e->ev_stop);
   cudaStreamDestroy(e->main_stream);
   delete e;
@@ -831,6 +874,7 @@ int irmv_engine_detect_batch(irmv_engine *e, const uint8_t *frames, int on_devic
   const uint8_t *dev = frames;
   if (!on_device) {
     if (!e->batch_dev) IRMV_CUDA(cudaMalloc((void **)&e->batch_dev, e->frame_bytes * (size_t)e->cfg.max_batch));
+    e->sets[0].batch_dev = e->batch_dev;
     dev = e->batch_dev;
   }
   if (int rc = enqueue(e, dev, nframes, on_device ? nullptr : frames)) return rc;
@@ -838,6 +882,50 @@ int irmv_engine_detect_batch(irmv_engine *e, const uint8_t *frames, int on_devic
   parse(e, nframes, out, counts);
   auto t1 = std::chrono::high_resolution_clock::now();
   e->profile_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+  return 0;
+}
+
+// Pipelined form of detect_batch for host-resident frames: submit returns as soon as the work is
+// queued (H2D on the copy stream, kernels on the lanes, D2H of the results); collect waits for
+// that batch and parses it.  Two batches may be in flight: submit(k+1) before collect(k) puts the
+// copy of batch k+1 under the kernels of batch k.  Tickets must be collected in order.
+int irmv_engine_submit_batch(irmv_engine *e, const uint8_t *frames_host, int nframes, int *ticket) {
+  if (!e || !frames_host || !ticket || nframes < 1 || nframes > e->cfg.max_batch) { set_error("bad argument"); return 1; }
+  IRMV_CUDA(cudaSetDevice(e->cfg.device));
+  const int set = (int)(e->next_ticket & 1);
+  irmv_engine::Set &rs = e->sets[set];
+  if (!rs.res_host) {
+    IRMV_CUDA(cudaHostAlloc((void **)&rs.res_host, e->res_bytes, cudaHostAllocDefault));
+    memset(rs.res_host, 0, e->res_bytes);
+  }
+  if (!rs.batch_dev) {
+    if (set == 0 && e->batch_dev) rs.batch_dev = e->batch_dev;
+    else IRMV_CUDA(cudaMalloc((void **)&rs.batch_dev, e->frame_bytes * (size_t)e->cfg.max_batch));
+    if (set == 0) e->batch_dev = rs.batch_dev;
+  }
+  // the set's staging buffer and result block are free once its previous batch has finished
+  IRMV_CUDA(cudaStreamWaitEvent(e->copy_stream, rs.done, 0));
+  if (int rc = enqueue(e, rs.batch_dev, nframes, frames_host, set, true)) return rc;
+  *ticket = (int)(e->next_ticket++ & 0x7fffffff);
+  return 0;
+}
+
+int irmv_engine_collect(irmv_engine *e, int ticket, irmv_bbox *out, int *counts, double *rvecs, double *tvecs,
+                        uint8_t *ok) {
+  if (!e || !out) { set_error("bad argument"); return 1; }
+  IRMV_CUDA(cudaSetDevice(e->cfg.device));
+  const int set = ticket & 1;
+  irmv_engine::Set &rs = e->sets[set];
+  if (rs.n < 1) { set_error("nothing was submitted under this ticket"); return 2; }
+  IRMV_CUDA(cudaEventSynchronize(rs.done));
+  parse(e, rs.n, out, counts, set);
+  if (rvecs && tvecs && e->pnp_on) {
+    const size_t md = e->cfg.max_det, B = e->cfg.max_batch;
+    const uint8_t *h = rs.res_host + B * 4 + B * md * 28;
+    memcpy(rvecs, h, (size_t)rs.n * md * 24);
+    memcpy(tvecs, h + B * md * 24, (size_t)rs.n * md * 24);
+    if (ok) memcpy(ok, h + B * md * 48, (size_t)rs.n * md);
+  }
   return 0;
 }
 

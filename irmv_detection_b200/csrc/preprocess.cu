@@ -240,8 +240,8 @@ __global__ void __launch_bounds__(ST * ST)
 stem_kernel(PreprocessParams p, const float *__restrict__ w, const float *__restrict__ bias, __half *out,
             long long out_pstride, __half *out2, long long out2_pstride, int pitch_s) {
   extern __shared__ __align__(16) uint8_t smem[];
-  __shared__ float tile[3][SI][SI + 1];
-  __shared__ __align__(16) float sw[27 * 16 + 16];   // [tap*3+c][16 outputs] then bias: float4 broadcast loads
+  __shared__ __half tile[3][SI][SI + 1];             // network-input tile, already rounded to FP16
+  __shared__ float sw[27 * 16 + 16];                 // w[o][k] (k = tap*3 + c) then bias
   const int n = blockIdx.z, oy0 = blockIdx.y * ST, ox0 = blockIdx.x * ST;
   const bool bayer = p.chan_order >= 2;
   const int H = p.src_h, W = p.src_w;
@@ -252,8 +252,7 @@ stem_kernel(PreprocessParams p, const float *__restrict__ w, const float *__rest
   const int hp = (p.resize_mode == 2);
   __shared__ float lut[256];
   __shared__ Taps ytap[SI], xtap[SI];
-  for (int i = threadIdx.x; i < 16 * 27 + 16; i += ST * ST)
-    sw[i] = i < 16 * 27 ? w[(i & 15) * 27 + (i >> 4)] : bias[i - 16 * 27];
+  for (int i = threadIdx.x; i < 16 * 27 + 16; i += ST * ST) sw[i] = i < 16 * 27 ? w[i] : bias[i - 16 * 27];
   lut[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.0f);                       // ST*ST == 256 threads
   if (threadIdx.x < SI) ytap[threadIdx.x] = axis_taps(min(max(2 * oy0 - 1 + (int)threadIdx.x, 0), kNet - 1), scale_y, H, hp);
   else if (threadIdx.x < 2 * SI) xtap[threadIdx.x - SI] = axis_taps(min(max(2 * ox0 - 1 + (int)threadIdx.x - SI, 0), kNet - 1), scale_x, W, hp);
@@ -270,49 +269,84 @@ stem_kernel(PreprocessParams p, const float *__restrict__ w, const float *__rest
     const int r = q / SI, c = q - r * SI;
     const int iy = iy_lo + r, ix = ix_lo + c;
     float v[3] = {0.f, 0.f, 0.f};
-    if (iy >= 0 && iy < kNet && ix >= 0 && ix < kNet) {
-      sample_pixel(reg, p, ytap[r], xtap[c], red_y, red_x, lut, v);
-#pragma unroll
-      for (int k = 0; k < 3; ++k) v[k] = __half2float(__float2half_rn(v[k]));
-    }
-    tile[0][r][c] = v[0]; tile[1][r][c] = v[1]; tile[2][r][c] = v[2];
+    if (iy >= 0 && iy < kNet && ix >= 0 && ix < kNet) sample_pixel(reg, p, ytap[r], xtap[c], red_y, red_x, lut, v);
+    tile[0][r][c] = __float2half_rn(v[0]); tile[1][r][c] = __float2half_rn(v[1]); tile[2][r][c] = __float2half_rn(v[2]);
   }
+  // conv0 as an implicit GEMM on mma.sync m16n8k16 (FP16 operands, FP32 accumulate): an m-tile is
+  // one output row of the CTA's 16x16 tile (16 pixels), N = 16 = two n-tiles, K = 27 padded to 32.
+  // (K = 27 and N = 16 are too small for a tcgen05 tile to pay for its TMEM round trip; the warp
+  // MMA replaces 432 FP32 FMAs per pixel.)  Fragment layout: PTX ISA, mma.m16n8k16 .f16.
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  int koff[2][4];          // tile offset (halfs) of k = 16*s + {2t, 2t+1, 2t+8, 2t+9}; 0 for the pad columns
+  uint32_t bfrag[2][2][2];  // [n-tile][k-step][2]
+#pragma unroll
+  for (int s2 = 0; s2 < 2; ++s2)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = 16 * s2 + 2 * t + (j & 1) + (j >> 1) * 8;
+      const int tap = k / 3, c = k - tap * 3, ky = tap / 3, kx = tap - ky * 3;
+      koff[s2][j] = k < 27 ? (c * SI + ky) * (SI + 1) + kx : 0;
+    }
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int s2 = 0; s2 < 2; ++s2)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k0 = 16 * s2 + 2 * t + h * 8;
+        const float w0 = k0 < 27 ? sw[(nt * 8 + g) * 27 + k0] : 0.f;
+        const float w1 = k0 + 1 < 27 ? sw[(nt * 8 + g) * 27 + k0 + 1] : 0.f;
+        const __half2 hw = __floats2half2_rn(w0, w1);
+        bfrag[nt][s2][h] = *reinterpret_cast<const uint32_t *>(&hw);
+      }
   __syncthreads();
-  const int ty = threadIdx.x / ST, tx = threadIdx.x - ty * ST;
-  float acc[16];
+  const __half *tl = &tile[0][0][0];
 #pragma unroll
-  for (int o = 0; o < 16; ++o) acc[o] = sw[16 * 27 + o];
+  for (int mt = 0; mt < 2; ++mt) {
+    const int ty = 2 * warp + mt;
+    float acc[2][4];
 #pragma unroll
-  for (int ky = 0; ky < 3; ++ky)
+    for (int nt = 0; nt < 2; ++nt) {
+      acc[nt][0] = acc[nt][2] = sw[16 * 27 + nt * 8 + 2 * t];
+      acc[nt][1] = acc[nt][3] = sw[16 * 27 + nt * 8 + 2 * t + 1];
+    }
+    const int base0 = (2 * ty) * (SI + 1) + 2 * g;          // pixel tx = g; pixel g + 8 is 16 halfs further
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx)
+    for (int s2 = 0; s2 < 2; ++s2) {
+      uint32_t afrag[4];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float x = tile[c][2 * ty + ky][2 * tx + kx];
-        const float4 *wv = reinterpret_cast<const float4 *>(&sw[((ky * 3 + kx) * 3 + c) * 16]);
+      for (int hk = 0; hk < 2; ++hk)        // k pair {2t, 2t+1} / {2t+8, 2t+9}
 #pragma unroll
-        for (int o4 = 0; o4 < 4; ++o4) {
-          const float4 w4 = wv[o4];
-          acc[4 * o4 + 0] = fmaf(x, w4.x, acc[4 * o4 + 0]);
-          acc[4 * o4 + 1] = fmaf(x, w4.y, acc[4 * o4 + 1]);
-          acc[4 * o4 + 2] = fmaf(x, w4.z, acc[4 * o4 + 2]);
-          acc[4 * o4 + 3] = fmaf(x, w4.w, acc[4 * o4 + 3]);
+        for (int hr = 0; hr < 2; ++hr) {    // row g / g + 8
+          const int b0 = base0 + hr * 16;
+          const __half2 v = __halves2half2(tl[b0 + koff[s2][2 * hk]], tl[b0 + koff[s2][2 * hk + 1]]);
+          afrag[hk * 2 + hr] = *reinterpret_cast<const uint32_t *>(&v);
+        }
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(acc[nt][0]), "+f"(acc[nt][1]), "+f"(acc[nt][2]), "+f"(acc[nt][3])
+                     : "r"(afrag[0]), "r"(afrag[1]), "r"(afrag[2]), "r"(afrag[3]), "r"(bfrag[nt][s2][0]), "r"(bfrag[nt][s2][1]));
+    }
+    // thread holds channels {2t, 2t+1} of n-tile 0 (plane 0) and of n-tile 1 (plane 1) for pixels
+    // tx = g and g + 8: 4-byte stores, the four lanes of a quad complete one 16-byte pixel
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) {
+      const int y = oy0 + ty, x = ox0 + g + 8 * hr;
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const __half2 hv = __floats2half2_rn(silu_fast(acc[nt][2 * hr]), silu_fast(acc[nt][2 * hr + 1]));
+        if (out) {
+          const size_t pix = (size_t)pr_index(n, y, x, kNet / 2, kNet / 2);
+          *reinterpret_cast<__half2 *>(out + (long long)nt * out_pstride + pix * 8 + 2 * t) = hv;
+        }
+        if (out2) {   // parity-split twin for the stride-2 consumer (common.cuh, ConvParams)
+          const size_t pix2 = (size_t)pr_index(n, y >> 1, x >> 1, kNet / 4, kNet / 4);
+          *reinterpret_cast<__half2 *>(out2 + (long long)(((y & 1) * 2 + (x & 1)) * 2 + nt) * out2_pstride + pix2 * 8 + 2 * t) = hv;
         }
       }
-  __half2 hv[8];
-#pragma unroll
-  for (int t = 0; t < 8; ++t) hv[t] = __floats2half2_rn(silu_fast(acc[2 * t]), silu_fast(acc[2 * t + 1]));
-  const size_t pix = (size_t)pr_index(n, oy0 + ty, ox0 + tx, kNet / 2, kNet / 2);
-  if (out) {
-    *reinterpret_cast<uint4 *>(out + pix * 8) = *reinterpret_cast<uint4 *>(&hv[0]);
-    *reinterpret_cast<uint4 *>(out + out_pstride + pix * 8) = *reinterpret_cast<uint4 *>(&hv[4]);
-  }
-  if (out2) {   // parity-split twin for the stride-2 consumer (common.cuh, ConvParams)
-    const int y = oy0 + ty, x = ox0 + tx;
-    const size_t pix2 = (size_t)pr_index(n, y >> 1, x >> 1, kNet / 4, kNet / 4);
-    __half *o2 = out2 + (long long)(((y & 1) * 2 + (x & 1)) * 2) * out2_pstride + pix2 * 8;
-    *reinterpret_cast<uint4 *>(o2) = *reinterpret_cast<uint4 *>(&hv[0]);
-    *reinterpret_cast<uint4 *>(o2 + out2_pstride) = *reinterpret_cast<uint4 *>(&hv[4]);
+    }
   }
 }
 

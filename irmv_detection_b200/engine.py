@@ -82,6 +82,7 @@ class YoloEngine:
         self._slot = 0
         self._out = (L.Bbox * (max_batch * max_det))()
         self._counts = (C.c_int * max_batch)()
+        self._ticket_n = [0, 0]
 
     # -- reference surface ---------------------------------------------------------------
     def get_src_image_buffer(self, slot: int = 0) -> np.ndarray:
@@ -129,6 +130,38 @@ class YoloEngine:
         dt = np.dtype([("xyxy", np.float32, 4), ("score", np.float32), ("class_id", np.int32)])
         dets = np.frombuffer(self._out, dtype=dt, count=n * self.max_det).reshape(n, self.max_det)
         return np.frombuffer(self._counts, dtype=np.int32, count=n), dets
+
+    # -- pipelined hand-off (copy of batch k+1 under the kernels of batch k) ---------------
+    def submit_batch(self, frames: np.ndarray) -> int:
+        """Queue H2D + pipeline + D2H for host frames and return a ticket; at most two batches in
+        flight, collect in order.  `frames` must stay alive and unchanged until collected (pinned
+        memory makes the copy asynchronous)."""
+        if not frames.flags.c_contiguous or frames.dtype != np.uint8:
+            raise ValueError("submit_batch needs a C-contiguous uint8 array")
+        n = frames.shape[0]
+        if frames[0].size != self.frame_bytes:
+            raise ValueError("frame size does not match the engine's src_image_size")
+        t = C.c_int(0)
+        L.check(self._lib.irmv_engine_submit_batch(self._h, frames.ctypes.data, n, C.byref(t)), "irmv_engine_submit_batch")
+        self._ticket_n[t.value & 1] = n
+        return t.value
+
+    def collect_arrays(self, ticket: int, poses: bool = False):
+        """Wait for a submitted batch: (counts i32[n], dets structured [n, max_det]) and, with
+        poses=True, (rvec f64[n,max_det,3], tvec, ok).  The arrays are views that the next collect
+        of the same parity overwrites."""
+        n = self._ticket_n[ticket & 1]
+        rv = tv = ok = None
+        if poses:
+            rv = np.empty((n, self.max_det, 3)); tv = np.empty((n, self.max_det, 3))
+            ok = np.empty((n, self.max_det), np.uint8)
+        L.check(self._lib.irmv_engine_collect(self._h, ticket, self._out, self._counts,
+                                              rv.ctypes.data if poses else None, tv.ctypes.data if poses else None,
+                                              ok.ctypes.data if poses else None), "irmv_engine_collect")
+        dt = np.dtype([("xyxy", np.float32, 4), ("score", np.float32), ("class_id", np.int32)])
+        dets = np.frombuffer(self._out, dtype=dt, count=n * self.max_det).reshape(n, self.max_det)
+        counts = np.frombuffer(self._counts, dtype=np.int32, count=n)
+        return (counts, dets, rv, tv, ok.astype(bool)) if poses else (counts, dets)
 
     def detect_batch_device(self, dev_ptr: int, n: int) -> List[List[bbox]]:
         L.check(self._lib.irmv_engine_detect_batch(self._h, C.c_void_p(dev_ptr), 1, n, self._out, self._counts),

@@ -358,6 +358,46 @@ def test_bayer_pipeline_batch_invariance(base_image, weights_seed0):
     eng.close()
 
 
+def test_submit_collect_pipelined_matches_sync(base_image, weights_seed0):
+    """Pipelined hand-off (two batches in flight, H2D on the copy stream): each batch gets exactly
+    the detections and poses of the synchronous call, whatever is queued behind or ahead of it."""
+    import torch
+    import irmv_detection_b200 as irmv
+    from irmv_detection_b200 import synth
+    from oracle import pnp_ref as P
+    _cuda()
+    rgb = synth.frames_from_base(base_image, 12, seed=9)[..., ::-1]
+    raw = synth.bayer_from_rgb(rgb, "RGGB")
+    bufs = []
+    for part in (raw[:6], raw[6:], raw[3:9]):
+        t = torch.empty(part.shape, dtype=torch.uint8, pin_memory=True)
+        t.numpy()[...] = part
+        bufs.append(t.numpy())
+    eng = irmv.YoloEngine(weights_seed0, (1280, 1024), chan_order=irmv.CH_BAYER_RGGB, max_batch=6,
+                          sub_batch=2, num_lanes=2)
+    eng.enable_pnp(P.K_DEFAULT, P.D_DEFAULT, (0.5, 480 / 1024))
+    want = []
+    for b in bufs:
+        c, d = eng.detect_batch_arrays(b)
+        rv, tv, ok = eng.fetch_poses(6)
+        want.append((c.copy(), d.copy(), rv, tv, ok))
+    t0 = eng.submit_batch(bufs[0])
+    t1 = eng.submit_batch(bufs[1])
+    got = [tuple(np.copy(x) for x in eng.collect_arrays(t0, poses=True))]
+    t2 = eng.submit_batch(bufs[2])
+    got.append(tuple(np.copy(x) for x in eng.collect_arrays(t1, poses=True)))
+    got.append(tuple(np.copy(x) for x in eng.collect_arrays(t2, poses=True)))
+    assert sum(int(w[0].sum()) for w in want) > 0
+    for w, g in zip(want, got):
+        assert np.array_equal(w[0], g[0])
+        for f in range(6):
+            k = int(w[0][f])
+            assert np.array_equal(w[1][f, :k], g[1][f, :k])
+            assert np.array_equal(w[2][f, :k], g[2][f, :k]) and np.array_equal(w[3][f, :k], g[3][f, :k])
+            assert np.array_equal(w[4][f, :k], g[4][f, :k])
+    eng.close()
+
+
 def test_large_sub_batch_matches_single_frames(base_image, weights_seed0):
     """Many tiles per persistent CTA (smem ring wraps, TMEM ping-pong): a 32-frame replay must give
     each frame exactly what it gets alone, and frame 0 must still match the FP32 oracle."""
