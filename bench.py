@@ -342,7 +342,7 @@ def run_ours(args):
     try:
         e1 = irmv.YoloEngine(wpath, (SRC_W, SRC_H), chan_order=irmv.CH_BAYER_RGGB, max_batch=1, device=local_rank)
         e1.enable_pnp(K_CAM, D_CAM, (640.0 / SRC_W, 480.0 / SRC_H))
-        e1.get_src_image_buffer(0)[...] = host_np[0]
+        e1.get_src_image_buffer(0)[...] = hosts[0][0]
         for _ in range(20):
             e1.detect(0)
         wall, devt = [], []
@@ -364,7 +364,7 @@ def run_ours(args):
         try:
             threads = os.cpu_count() or 1
             ref = CpuReference(wpath, threads)
-            fps, n, dt = ref.run(host_np[:64], budget_s=args.cpu_budget)
+            fps, n, dt = ref.run(hosts[0][:64], budget_s=args.cpu_budget)
             cpu = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
                    "sample": f"{n} of the step's 256 Bayer frames in {dt:.1f} s; cv2 demosaic+flip+resize, "
                              f"{ref.kind_net} YOLOv8n FP32, numpy NMS, cv2.solvePnP(IPPE)"}
