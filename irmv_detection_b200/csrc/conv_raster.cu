@@ -233,6 +233,9 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
     trow[3] = (long long)g;
   }
 
+  // Programmatic dependent launch: let the next kernel of the stream start its prologue now; its
+  // own griddepcontrol.wait still blocks until this grid has completed and flushed.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // act: bias / 2 (folded into the SiLU argument), otherwise the bias itself
   for (int i = tid; i < npad; i += NTHREADS) s_hb[i] = ACT ? 0.5f * p.bias[i] : p.bias[i];
   if (tid == 0) {
@@ -261,6 +264,18 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
   if (trow) trow[1] = clock64();
+  // Resident weights are constants: start loading them before waiting for the producer kernel.
+  if (warp == TMA_WARP && !a.b_stream && elect_one()) {
+    const uint32_t bar = smem_u32(&bars->bfull), sB_u = smem_u32(sB);
+    mbar_expect_tx(bar, a.b_bytes);
+    for (uint32_t off = 0; off < a.b_bytes; off += 65536u) {
+      const uint32_t n = a.b_bytes - off < 65536u ? a.b_bytes - off : 65536u;
+      bulk_g2s(sB_u + off, reinterpret_cast<const uint8_t *>(p.w_raster) + off, n, bar);
+    }
+  }
+  // Everything above overlapped the tail of the previous kernel (PDL); activations, residuals
+  // and output buffers may only be touched once it has completed.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp < NEPI) {
     // ===================================================================== epilogue
@@ -364,14 +379,6 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
     // ===================================================================== TMA producer
     if (elect_one()) {
       const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
-      if (!a.b_stream) {
-        const uint32_t bar = smem_u32(&bars->bfull);
-        mbar_expect_tx(bar, a.b_bytes);
-        for (uint32_t off = 0; off < a.b_bytes; off += 65536u) {
-          const uint32_t n = a.b_bytes - off < 65536u ? a.b_bytes - off : 65536u;
-          bulk_g2s(sB_u + off, reinterpret_cast<const uint8_t *>(p.w_raster) + off, n, bar);
-        }
-      }
       int s = 0, itl = 0, bs = 0;
       uint32_t ph = 0, bph = 0;
       const uint32_t plane_bytes = (uint32_t)a.npix_need * 16u;
@@ -622,8 +629,18 @@ cudaError_t launch_k(const RArgs &a, int grid, size_t smem, cudaStream_t s) {
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  conv_raster_kernel<R, NEPI, ACT, RES><<<grid, (NEPI + 2) * 32, smem, s>>>(a);
-  return cudaGetLastError();
+  static const bool pdl = !getenv("IRMV_NO_PDL");
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((NEPI + 2) * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, conv_raster_kernel<R, NEPI, ACT, RES>, a);
 }
 
 template <int R, int NEPI>
