@@ -83,6 +83,26 @@ __device__ __forceinline__ void bayer_rgb(const Region &r, int sy, int sx, int H
   B = is_b ? c : (is_r ? diag : (red_row ? vert : horiz));
 }
 
+// Same demosaic with the column part hoisted: oxm / ox0 / oxp are the byte offsets of columns
+// sx-1 / sx / sx+1 (already mirrored at the image border) inside a staged row, red_col is the
+// column's colour-site parity.  Used by the stem's fast path, where one thread walks down a column.
+__device__ __forceinline__ void bayer_rgb_col(const Region &r, int sy, int H, int oxm, int ox0, int oxp,
+                                              bool red_col, int red_y, int &R, int &G, int &B) {
+  int ym = sy - 1, yp = sy + 1;
+  if (sy == 0 || sy == H - 1) { ym = reflect101(ym, H); yp = reflect101(yp, H); }
+  const uint8_t *r0 = rowp(r, ym) + r.col_byte_lo, *r1 = rowp(r, sy) + r.col_byte_lo, *r2 = rowp(r, yp) + r.col_byte_lo;
+  const int nw = r0[oxm], n = r0[ox0], ne = r0[oxp];
+  const int w = r1[oxm], c = r1[ox0], e = r1[oxp];
+  const int sw = r2[oxm], s = r2[ox0], se = r2[oxp];
+  const int cross = (n + s + w + e + 2) >> 2, diag = (nw + ne + sw + se + 2) >> 2;
+  const int horiz = (w + e + 1) >> 1, vert = (n + s + 1) >> 1;
+  const bool red_row = ((sy & 1) == red_y);
+  const bool is_r = red_row && red_col, is_b = !red_row && !red_col;
+  G = (is_r || is_b) ? cross : c;
+  R = is_r ? c : (is_b ? diag : (red_row ? horiz : vert));
+  B = is_b ? c : (is_r ? diag : (red_row ? vert : horiz));
+}
+
 __device__ __forceinline__ float lerp4(float p00, float p01, float p10, float p11, float fx,
                                        float fy) {
   float ofx = __fsub_rn(1.0f, fx), ofy = __fsub_rn(1.0f, fy);
@@ -161,13 +181,22 @@ __device__ __forceinline__ Region stage_window(const PreprocessParams &p, const 
   const int nbytes = (sx_hi - sx_lo + 1) * bpp;
   const int chunks_per_row = pitch_s >> 4;
   const uint8_t *alloc_end = base + (size_t)p.n * frame_bytes;
-  for (int i = threadIdx.x; i < nrows * chunks_per_row; i += nthreads) {
-    int r = i / chunks_per_row, c = i - r * chunks_per_row;
+  auto stage_chunk = [&](int r, int c) {
     const uint8_t *row = frame + (size_t)(sy_lo + r) * src_pitch + col_byte_lo;
     const uint8_t *a = (const uint8_t *)((size_t)row & ~(size_t)15) + (size_t)c * 16;
     uint4 v = make_uint4(0, 0, 0, 0);
     if (a < row + nbytes && a < alloc_end) v = __ldg((const uint4 *)a);
     *(uint4 *)(smem + (size_t)r * pitch_s + c * 16) = v;
+  };
+  if (chunks_per_row <= 8) {                    // 8 threads per staged row, no division
+    const int c = threadIdx.x & 7;
+    if (c < chunks_per_row)
+      for (int r = threadIdx.x >> 3; r < nrows; r += nthreads >> 3) stage_chunk(r, c);
+  } else {
+    for (int i = threadIdx.x; i < nrows * chunks_per_row; i += nthreads) {
+      const int r = i / chunks_per_row;
+      stage_chunk(r, i - r * chunks_per_row);
+    }
   }
   const int shift0 = (int)((size_t)(frame + (size_t)sy_lo * src_pitch + col_byte_lo) & 15);
   return Region{frame, smem, sy_lo, pitch_s, col_byte_lo, src_pitch, shift0, src_pitch & 15};
@@ -238,10 +267,12 @@ __device__ __forceinline__ float silu_fast(float x) {
 
 __global__ void __launch_bounds__(ST * ST)
 stem_kernel(PreprocessParams p, const float *__restrict__ w, const float *__restrict__ bias, __half *out,
-            long long out_pstride, __half *out2, long long out2_pstride, int pitch_s) {
+            long long out_pstride, __half *out2, long long out2_pstride, int pitch_s, int fast_x) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ __half tile[3][SI][SI + 1];             // network-input tile, already rounded to FP16
-  __shared__ float sw[27 * 16 + 16];                 // w[o][k] (k = tap*3 + c) then bias
+  __shared__ uint32_t sbf[16][16];                   // conv0 weights as half2 {w[n][2j], w[n][2j+1]}, K padded to 32
+  __shared__ float sbias[16];
+  __shared__ short skoff[32];                        // tile offset (halfs) of GEMM column k = tap*3 + c
   const int n = blockIdx.z, oy0 = blockIdx.y * ST, ox0 = blockIdx.x * ST;
   const bool bayer = p.chan_order >= 2;
   const int H = p.src_h, W = p.src_w;
@@ -252,7 +283,16 @@ stem_kernel(PreprocessParams p, const float *__restrict__ w, const float *__rest
   const int hp = (p.resize_mode == 2);
   __shared__ float lut[256];
   __shared__ Taps ytap[SI], xtap[SI];
-  for (int i = threadIdx.x; i < 16 * 27 + 16; i += ST * ST) sw[i] = i < 16 * 27 ? w[i] : bias[i - 16 * 27];
+  {
+    const int nn = threadIdx.x >> 4, k0 = 2 * (threadIdx.x & 15);
+    const __half2 hw = __floats2half2_rn(k0 < 27 ? w[nn * 27 + k0] : 0.f, k0 + 1 < 27 ? w[nn * 27 + k0 + 1] : 0.f);
+    sbf[nn][threadIdx.x & 15] = *reinterpret_cast<const uint32_t *>(&hw);
+    if (threadIdx.x < 16) sbias[threadIdx.x] = bias[threadIdx.x];
+    if (threadIdx.x < 32) {
+      const int k = threadIdx.x, tap = k / 3, cc = k - tap * 3, ky = tap / 3, kx = tap - ky * 3;
+      skoff[k] = k < 27 ? (short)((cc * SI + ky) * (SI + 1) + kx) : (short)0;   // pad columns: any finite value
+    }
+  }
   lut[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.0f);                       // ST*ST == 256 threads
   if (threadIdx.x < SI) ytap[threadIdx.x] = axis_taps(min(max(2 * oy0 - 1 + (int)threadIdx.x, 0), kNet - 1), scale_y, H, hp);
   else if (threadIdx.x < 2 * SI) xtap[threadIdx.x - SI] = axis_taps(min(max(2 * ox0 - 1 + (int)threadIdx.x - SI, 0), kNet - 1), scale_x, W, hp);
@@ -265,12 +305,85 @@ stem_kernel(PreprocessParams p, const float *__restrict__ w, const float *__rest
   if (p.chan_order == 3) { red_y = 1; red_x = 1; }
   else if (p.chan_order == 4) { red_y = 0; red_x = 1; }
   else if (p.chan_order == 5) { red_y = 1; red_x = 0; }
-  for (int q = threadIdx.x; q < SI * SI; q += ST * ST) {
-    const int r = q / SI, c = q - r * SI;
-    const int iy = iy_lo + r, ix = ix_lo + c;
-    float v[3] = {0.f, 0.f, 0.f};
-    if (iy >= 0 && iy < kNet && ix >= 0 && ix < kNet) sample_pixel(reg, p, ytap[r], xtap[c], red_y, red_x, lut, v);
-    tile[0][r][c] = __float2half_rn(v[0]); tile[1][r][c] = __float2half_rn(v[1]); tile[2][r][c] = __float2half_rn(v[2]);
+  if (fast_x && bayer) {
+    // Fast path (Bayer source, integer horizontal scale: every x tap has weight 0 on its second
+    // sample, so a network-input pixel is a vertical lerp of two demosaiced source pixels of ONE
+    // column).  7 x 33 threads: a thread owns a column and five consecutive input rows and walks
+    // down its source column with a 3x3 window of raw samples in registers (three byte loads per
+    // source row); column addressing and colour-site parity are loop invariants.  The source rows
+    // an input row needs are monotone in the input row, so the window only ever slides forward.
+    // Bit-identical to sample_pixel().
+    constexpr int RG = 5, NG = (SI + RG - 1) / RG;
+    if (threadIdx.x < NG * SI) {
+      const int grp = threadIdx.x / SI, c = threadIdx.x - grp * SI;
+      const int ix = ix_lo + c;
+      const bool xin = ix >= 0 && ix < kNet;
+      const int sx = p.rotate180 ? W - 1 - xtap[c].i0 : xtap[c].i0;
+      int xm = sx - 1, xp = sx + 1;
+      if (sx == 0 || sx == W - 1) { xm = reflect101(xm, W); xp = reflect101(xp, W); }
+      const bool red_col = ((sx & 1) == red_x);
+      const int dir = p.rotate180 ? -1 : 1;          // source rows move this way as the input row grows
+      // window rows: wa = row cur - dir, wb = row cur, wc = row cur + dir (mirrored at the border);
+      // the demosaic is symmetric in north/south, so the orientation does not matter
+      int cur = -1 << 20;
+      int a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0, c0 = 0, c1 = 0, c2 = 0;
+      auto load_row = [&](int y, int &v0, int &v1, int &v2) {
+        const uint8_t *rp = rowp(reg, reflect101(y, H));
+        v0 = rp[xm]; v1 = rp[sx]; v2 = rp[xp];
+      };
+      auto seek = [&](int sy) {                       // make `sy` the window centre
+        if (sy == cur) return;
+        if (sy == cur + dir) {                        // slide by one row
+          a0 = b0; a1 = b1; a2 = b2; b0 = c0; b1 = c1; b2 = c2;
+        } else if (sy == cur + 2 * dir) {             // slide by two rows
+          a0 = c0; a1 = c1; a2 = c2;
+          load_row(sy, b0, b1, b2);
+        } else {                                      // first use (or a vertical scale above 2)
+          load_row(sy - dir, a0, a1, a2);
+          load_row(sy, b0, b1, b2);
+        }
+        load_row(sy + dir, c0, c1, c2);
+        cur = sy;
+      };
+      auto demosaic = [&](int sy, int &R, int &G, int &B) {
+        const int cross = (a1 + c1 + b0 + b2 + 2) >> 2, diag = (a0 + a2 + c0 + c2 + 2) >> 2;
+        const int horiz = (b0 + b2 + 1) >> 1, vert = (a1 + c1 + 1) >> 1;
+        const bool red_row = ((sy & 1) == red_y);
+        const bool is_r = red_row && red_col, is_b = !red_row && !red_col;
+        G = (is_r || is_b) ? cross : b1;
+        R = is_r ? b1 : (is_b ? diag : (red_row ? horiz : vert));
+        B = is_b ? b1 : (is_r ? diag : (red_row ? vert : horiz));
+      };
+#pragma unroll
+      for (int k = 0; k < RG; ++k) {
+        const int r = grp * RG + k;
+        if (r >= SI) break;
+        const int iy = iy_lo + r;
+        float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+        if (xin && iy >= 0 && iy < kNet) {
+          const Taps ty = ytap[r];
+          const int sy0 = p.rotate180 ? H - 1 - ty.i0 : ty.i0, sy1 = p.rotate180 ? H - 1 - ty.i1 : ty.i1;
+          int R0, G0, B0, R1, G1, B1;
+          seek(sy0);
+          demosaic(sy0, R0, G0, B0);
+          seek(sy1);
+          demosaic(sy1, R1, G1, B1);
+          const float fy = ty.f, ofy = __fsub_rn(1.0f, fy);
+          v0 = finish(__fadd_rn(__fmul_rn((float)R0, ofy), __fmul_rn((float)R1, fy)), p.quantize_u8, lut);
+          v1 = finish(__fadd_rn(__fmul_rn((float)G0, ofy), __fmul_rn((float)G1, fy)), p.quantize_u8, lut);
+          v2 = finish(__fadd_rn(__fmul_rn((float)B0, ofy), __fmul_rn((float)B1, fy)), p.quantize_u8, lut);
+        }
+        tile[0][r][c] = __float2half_rn(v0); tile[1][r][c] = __float2half_rn(v1); tile[2][r][c] = __float2half_rn(v2);
+      }
+    }
+  } else {
+    for (int q = threadIdx.x; q < SI * SI; q += ST * ST) {
+      const int r = q / SI, c = q - r * SI;
+      const int iy = iy_lo + r, ix = ix_lo + c;
+      float v[3] = {0.f, 0.f, 0.f};
+      if (iy >= 0 && iy < kNet && ix >= 0 && ix < kNet) sample_pixel(reg, p, ytap[r], xtap[c], red_y, red_x, lut, v);
+      tile[0][r][c] = __float2half_rn(v[0]); tile[1][r][c] = __float2half_rn(v[1]); tile[2][r][c] = __float2half_rn(v[2]);
+    }
   }
   // conv0 as an implicit GEMM on mma.sync m16n8k16 (FP16 operands, FP32 accumulate): an m-tile is
   // one output row of the CTA's 16x16 tile (16 pixels), N = 16 = two n-tiles, K = 27 padded to 32.
@@ -278,29 +391,19 @@ stem_kernel(PreprocessParams p, const float *__restrict__ w, const float *__rest
   // MMA replaces 432 FP32 FMAs per pixel.)  Fragment layout: PTX ISA, mma.m16n8k16 .f16.
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
-  int koff[2][4];          // tile offset (halfs) of k = 16*s + {2t, 2t+1, 2t+8, 2t+9}; 0 for the pad columns
+  __syncthreads();
+  int koff[2][4];          // tile offset (halfs) of k = 16*s + {2t, 2t+1, 2t+8, 2t+9}
   uint32_t bfrag[2][2][2];  // [n-tile][k-step][2]
 #pragma unroll
   for (int s2 = 0; s2 < 2; ++s2)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int k = 16 * s2 + 2 * t + (j & 1) + (j >> 1) * 8;
-      const int tap = k / 3, c = k - tap * 3, ky = tap / 3, kx = tap - ky * 3;
-      koff[s2][j] = k < 27 ? (c * SI + ky) * (SI + 1) + kx : 0;
-    }
+    for (int j = 0; j < 4; ++j) koff[s2][j] = skoff[16 * s2 + 2 * t + (j & 1) + (j >> 1) * 8];
 #pragma unroll
   for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
     for (int s2 = 0; s2 < 2; ++s2)
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int k0 = 16 * s2 + 2 * t + h * 8;
-        const float w0 = k0 < 27 ? sw[(nt * 8 + g) * 27 + k0] : 0.f;
-        const float w1 = k0 + 1 < 27 ? sw[(nt * 8 + g) * 27 + k0 + 1] : 0.f;
-        const __half2 hw = __floats2half2_rn(w0, w1);
-        bfrag[nt][s2][h] = *reinterpret_cast<const uint32_t *>(&hw);
-      }
-  __syncthreads();
+      for (int h = 0; h < 2; ++h) bfrag[nt][s2][h] = sbf[nt * 8 + g][8 * s2 + t + 4 * h];
   const __half *tl = &tile[0][0][0];
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt) {
@@ -308,8 +411,8 @@ stem_kernel(PreprocessParams p, const float *__restrict__ w, const float *__rest
     float acc[2][4];
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt) {
-      acc[nt][0] = acc[nt][2] = sw[16 * 27 + nt * 8 + 2 * t];
-      acc[nt][1] = acc[nt][3] = sw[16 * 27 + nt * 8 + 2 * t + 1];
+      acc[nt][0] = acc[nt][2] = sbias[nt * 8 + 2 * t];
+      acc[nt][1] = acc[nt][3] = sbias[nt * 8 + 2 * t + 1];
     }
     const int base0 = (2 * ty) * (SI + 1) + 2 * g;          // pixel tx = g; pixel g + 8 is 16 halfs further
 #pragma unroll
@@ -451,7 +554,9 @@ cudaError_t launch_stem(const PreprocessParams &p, const float *w, const float *
     if (e != cudaSuccess) return e;
   }
   dim3 grid(kNet / 2 / ST, kNet / 2 / ST, p.n);
-  stem_kernel<<<grid, ST * ST, smem, s>>>(p, w, bias, out, out_pstride, out2, out2_pstride, pitch_s);
+  // integer horizontal scale without half-pixel centres: every second x tap has weight exactly 0
+  const int fast_x = (p.src_w % kNet == 0) && p.resize_mode != 2;
+  stem_kernel<<<grid, ST * ST, smem, s>>>(p, w, bias, out, out_pstride, out2, out2_pstride, pitch_s, fast_x);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess && p.rotated) {
     size_t total = (size_t)p.n * p.src_h * p.src_w;

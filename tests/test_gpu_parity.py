@@ -436,6 +436,46 @@ def test_fused_stem_matches_unfused(frames, weights_seed0):
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("chan", [0, 2, 3, 4, 5])
+def test_fused_stem_input_pixels_exact(base_image, tmp_path, chan):
+    """The fused stem never materialises the network input, so probe it through conv0: with
+    one-hot weights output channel 3*t + c is SiLU(input[c] at tap t) for the four taps
+    (ky, kx) in {1,2}^2, which together visit every input pixel.  A single 8-bit step of the
+    preprocess (1/255 = 3.9e-3) would move the output by >= 2e-3; tanh.approx + FP16 rounding
+    stay below 1.5e-3.  Covers the Bayer fast path (integer horizontal scale) and packed RGB."""
+    import irmv_detection_b200 as irmv
+    from irmv_detection_b200 import synth, weights
+    from oracle import preprocess_ref as PR
+    _cuda()
+    tens = weights.random_init(0)
+    w0 = np.zeros((16, 3, 3, 3), np.float32)
+    taps = [(1, 1), (1, 2), (2, 1), (2, 2)]
+    for t, (ky, kx) in enumerate(taps):
+        for c in range(3):
+            w0[3 * t + c, c, ky, kx] = 1.0
+    tens[0] = (w0, np.zeros(16, np.float32))
+    wp = str(tmp_path / "probe.irmw")
+    weights.save(wp, tens)
+    rnd = np.random.default_rng(5).integers(0, 256, base_image.shape, dtype=np.uint8)
+    rgb = np.stack([base_image[..., ::-1], rnd])
+    if chan >= 2:
+        src = synth.bayer_from_rgb(rgb, {2: "RGGB", 3: "BGGR", 4: "GRBG", 5: "GBRG"}[chan])
+    else:
+        src = rgb
+    eng = irmv.YoloEngine(wp, (1280, 1024), chan_order=chan, max_batch=2, sub_batch=2)
+    eng.detect_batch(src)
+    m0 = eng.read_tensor("m0").astype(np.float64)                  # [2, 320, 320, 16]
+    for f in range(2):
+        ref, _ = PR.preprocess_fp16(src[f], chan)                   # [3, 640, 640] fp16
+        x = np.pad(ref.astype(np.float64), ((0, 0), (1, 1), (1, 1)))
+        for t, (ky, kx) in enumerate(taps):
+            want = x[:, ky:ky + 640:2, kx:kx + 640:2]                # input (2y + ky - 1, 2x + kx - 1)
+            want = want / (1.0 + np.exp(-want))
+            got = m0[f, :, :, 3 * t:3 * t + 3].transpose(2, 0, 1)
+            assert np.abs(got - want).max() < 1.5e-3, (f, t)
+    eng.close()
+
+
 def test_cpp_drop_in_classes(base_image, weights_seed0, tmp_path):
     """The C++ YoloEngine / PnPSolver / TripleBuffer with the reference's class interfaces
     (include/irmv_detection/*.hpp), exercised by a program shaped like the reference's
