@@ -51,7 +51,26 @@ struct PreprocessParams {
   uint8_t *rotated;            // optional [n][H][W][3] rotated RGB image, may be null
   int n, src_w, src_h;
   int chan_order, rotate180, resize_mode, quantize_u8;
+  // filled by letterbox_geometry(): the resized image is new_w x new_h at (pad_x, pad_y) of the
+  // 640 x 640 network input (stretch modes: 640 x 640 at (0, 0))
+  int pad_x, pad_y, new_w, new_h;
 };
+// Resize geometry of a src_w x src_h frame.  LETTERBOX (resize_mode 1) follows ultralytics'
+// LetterBox: r = min(640/w, 640/h), new = round(size * r), centred, pad value 114, pixel-centre
+// bilinear resize.  (The reference itself stretches, src/yolo_engine.cpp:186-190; north_star and
+// BASELINE configs[0] name the letterboxed form.)
+inline void letterbox_geometry(int src_w, int src_h, int resize_mode, int *pad_x, int *pad_y, int *new_w, int *new_h) {
+  *pad_x = *pad_y = 0; *new_w = *new_h = kNet;
+  if (resize_mode != 1) return;
+  const double rw = (double)kNet / src_w, rh = (double)kNet / src_h, r = rw < rh ? rw : rh;
+  *new_w = (int)(src_w * r + 0.5); *new_h = (int)(src_h * r + 0.5);
+  if (*new_w > kNet) *new_w = kNet;
+  if (*new_h > kNet) *new_h = kNet;
+  const double dw = (kNet - *new_w) / 2.0, dh = (kNet - *new_h) / 2.0;
+  *pad_x = (int)(dw - 0.1 + 0.5); *pad_y = (int)(dh - 0.1 + 0.5);
+  if (*pad_x < 0) *pad_x = 0;
+  if (*pad_y < 0) *pad_y = 0;
+}
 cudaError_t launch_preprocess(const PreprocessParams &p, cudaStream_t s);
 // Fused preprocess + conv0 (3x3 s2, 3->16, SiLU): w = [16][9 taps][3] FP32, writes two planes.
 // out2 (optional): parity-split twin of the output (see ConvParams).

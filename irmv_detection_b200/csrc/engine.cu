@@ -217,13 +217,13 @@ __global__ void set_src_kernel(const uint8_t **word, const uint8_t *ptr) { *word
 // Until the light-bar extractor (reference src/irm_detector.cpp:292-355) is on the GPU the four
 // corners are the box corners, scaled from network pixels to the calibration frame.
 __global__ void quads_from_dets_kernel(const int32_t *num, const float *boxes, int n, int max_det,
-                                       float sx, float sy, float *pts) {
+                                       float sx, float sy, float px, float py, float *pts) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * max_det) return;
   int f = i / max_det, k = i - f * max_det;
-  float4 b = make_float4(150.f, 140.f, 200.f, 160.f);     // inactive slots: a fixed valid quad
+  float4 b = make_float4(150.f + px, 140.f + py, 200.f + px, 160.f + py);     // inactive slots: a fixed valid quad
   if (k < num[f]) b = reinterpret_cast<const float4 *>(boxes)[i];
-  float x1 = b.x * sx, y1 = b.y * sy, x2 = b.z * sx, y2 = b.w * sy;
+  float x1 = (b.x - px) * sx, y1 = (b.y - py) * sy, x2 = (b.z - px) * sx, y2 = (b.w - py) * sy;
   float4 *o = reinterpret_cast<float4 *>(pts + (size_t)i * 8);
   o[0] = make_float4(x1, y2, x1, y1);
   o[1] = make_float4(x2, y1, x2, y2);
@@ -267,7 +267,7 @@ struct irmv_engine {
   bool fused_stem = true;               // preprocess + conv0 in one kernel (input never materialised)
   float *d_stem_w = nullptr, *d_stem_b = nullptr;
   PnpConsts pnp_c{};
-  float pnp_sx = 1.f, pnp_sy = 1.f;
+  float pnp_sx = 1.f, pnp_sy = 1.f, pnp_px = 0.f, pnp_py = 0.f;
   int last_slot = -1;
   int last_n = 0;
 };
@@ -546,7 +546,7 @@ int issue_replay(irmv_engine *e, Lane &ln, int n, cudaStream_t st, int *launches
   if (e->pnp_on) {
     const int total = n * e->cfg.max_det;
     quads_from_dets_kernel<<<(total + 127) / 128, 128, 0, st>>>(ln.det.num(), ln.det.boxes(), n, e->cfg.max_det,
-                                                               e->pnp_sx, e->pnp_sy, ln.pnp_pts);
+                                                               e->pnp_sx, e->pnp_sy, e->pnp_px, e->pnp_py, ln.pnp_pts);
     IRMV_CUDA(cudaGetLastError());
     PnpOut po{ln.pnp_rvec, ln.pnp_tvec, ln.pnp_ok, nullptr, nullptr, nullptr, nullptr};
     IRMV_CUDA(launch_pnp(e->pnp_c, ln.pnp_pts, total, 0, po, st));
@@ -658,14 +658,19 @@ void parse(irmv_engine *e, int n, irmv_bbox *out, int *counts, int set = 0) {
   const float *boxes = reinterpret_cast<const float *>(h + B * 4);
   const float *scores = reinterpret_cast<const float *>(h + B * 4 + B * md * 16);
   const int32_t *cls = reinterpret_cast<const int32_t *>(h + B * 4 + B * md * 20);
-  const float sx = (float)e->cfg.src_width / 640, sy = (float)e->cfg.src_height / 640;
+  // reference parse_output scales by (W/640, H/640) (src/yolo_engine.cpp:211-214); with LETTERBOX the
+  // resized image sits at (pad_x, pad_y) and is new_w x new_h, so boxes are shifted back first
+  int pad_x, pad_y, new_w, new_h;
+  letterbox_geometry(e->cfg.src_width, e->cfg.src_height, e->cfg.resize_mode, &pad_x, &pad_y, &new_w, &new_h);
+  const float sx = (float)e->cfg.src_width / new_w, sy = (float)e->cfg.src_height / new_h;
+  const float px = (float)pad_x, py = (float)pad_y;
   for (int f = 0; f < n; ++f) {
     int k = num[f];
     if (counts) counts[f] = k;
     for (int i = 0; i < k; ++i) {
       const float *b = boxes + ((size_t)f * md + i) * 4;
       irmv_bbox &o = out[(size_t)f * md + i];
-      o.xyxy[0] = b[0] * sx; o.xyxy[1] = b[1] * sy; o.xyxy[2] = b[2] * sx; o.xyxy[3] = b[3] * sy;
+      o.xyxy[0] = (b[0] - px) * sx; o.xyxy[1] = (b[1] - py) * sy; o.xyxy[2] = (b[2] - px) * sx; o.xyxy[3] = (b[3] - py) * sy;
       o.score = scores[(size_t)f * md + i];
       int c = cls[(size_t)f * md + i];
       o.class_id = (c >= 0 && c < IRMV_NUM_CLASSES) ? c : IRMV_CLASS_UNKNOWN;
@@ -694,7 +699,6 @@ int irmv_engine_config_default(irmv_engine_config *c) {
 
 int irmv_engine_create(const char *weights_path, const irmv_engine_config *cfg, irmv_engine **out) {
   if (!weights_path || !cfg || !out) { set_error("null argument"); return 1; }
-  if (cfg->resize_mode == IRMV_RESIZE_LETTERBOX) { set_error("resize_mode LETTERBOX is not built yet"); return 2; }
   if (cfg->max_batch < 1 || cfg->src_width < 2 || cfg->src_height < 2 || cfg->max_det < 1 || cfg->max_det > 1024) {
     set_error("bad engine config"); return 2;
   }
@@ -1025,8 +1029,13 @@ int irmv_engine_enable_pnp(irmv_engine *e, const double K[9], const double D[5],
   e->pnp_c.half_w[0] = 135.0 / 2.0 / 1000.0; e->pnp_c.half_h[0] = 55.0 / 2.0 / 1000.0;
   e->pnp_c.half_w[1] = 225.0 / 2.0 / 1000.0; e->pnp_c.half_h[1] = 55.0 / 2.0 / 1000.0;
   // boxes are in network pixels: first to the source frame (parse_output's scale), then to the calibration frame
-  e->pnp_sx = corner_sx * (float)e->cfg.src_width / 640.f;
-  e->pnp_sy = corner_sy * (float)e->cfg.src_height / 640.f;
+  {
+    int pad_x, pad_y, new_w, new_h;
+    letterbox_geometry(e->cfg.src_width, e->cfg.src_height, e->cfg.resize_mode, &pad_x, &pad_y, &new_w, &new_h);
+    e->pnp_sx = corner_sx * (float)e->cfg.src_width / (float)new_w;
+    e->pnp_sy = corner_sy * (float)e->cfg.src_height / (float)new_h;
+    e->pnp_px = (float)pad_x; e->pnp_py = (float)pad_y;
+  }
   e->pnp_on = true;
   IRMV_CUDA(cudaSetDevice(e->cfg.device));
   IRMV_CUDA(cudaDeviceSynchronize());
@@ -1122,7 +1131,6 @@ int irmv_engine_trace_conv(irmv_engine *e, int op_index, int nframes, long long 
 int irmv_preprocess(const uint8_t *src, int n, int src_w, int src_h, int chan_order, int rotate180,
                     int resize_mode, int quantize_u8, uint16_t *dst, uint8_t *rotated, int device) {
   if (!src || !dst || n < 1) { set_error("bad argument"); return 1; }
-  if (resize_mode == IRMV_RESIZE_LETTERBOX) { set_error("resize_mode LETTERBOX is not built yet"); return 2; }
   IRMV_CUDA(cudaSetDevice(device));
   const size_t fb = (size_t)src_w * src_h * (chan_order >= 2 ? 1 : 3);
   const size_t ob = (size_t)pr_pixels(n, kNet, kNet) * kInC * 2;     // kernel writes the PR layout

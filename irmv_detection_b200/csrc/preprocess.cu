@@ -15,7 +15,7 @@ constexpr int TH = 8;     // output rows per CTA
 constexpr int TW = 64;    // output cols per CTA
 constexpr int NT = 256;
 
-struct Taps { int i0, i1; float f; };
+struct Taps { int i0, i1; float f; int ok; };   // ok = 0: letterbox padding (value 114)
 
 // half_pixel = 0: NPP's measured convention (corner-aligned, src = dst * scale), reference-exact;
 // half_pixel = 1: OpenCV-style pixel centres.
@@ -24,10 +24,19 @@ __device__ __forceinline__ Taps axis_taps(int d, float scale, int n_src, int hal
                        : __fmul_rn((float)d, scale);
   float fl = floorf(s);
   Taps t;
+  t.ok = 1;
   t.f = __fsub_rn(s, fl);
   int i0 = (int)fl;
   t.i0 = min(max(i0, 0), n_src - 1);
   t.i1 = min(max(i0 + 1, 0), n_src - 1);
+  return t;
+}
+
+// Network-input coordinate d of a letterboxed axis: the resized image occupies [pad, pad + n_new).
+__device__ __forceinline__ Taps axis_taps_lb(int d, int pad, int n_new, float scale, int n_src, int half_pixel) {
+  const int dr = d - pad;
+  Taps t = axis_taps(min(max(dr, 0), n_new - 1), scale, n_src, half_pixel);
+  t.ok = dr >= 0 && dr < n_new;
   return t;
 }
 
@@ -167,8 +176,8 @@ __device__ __forceinline__ Region stage_window(const PreprocessParams &p, const 
   const int H = p.src_h, W = p.src_w;
   const int src_pitch = W * bpp;
   const size_t frame_bytes = (size_t)H * src_pitch;
-  Taps ty0 = axis_taps(iy_lo, scale_y, H, hp), ty1 = axis_taps(iy_hi, scale_y, H, hp);
-  Taps tx0 = axis_taps(ix_lo, scale_x, W, hp), tx1 = axis_taps(ix_hi, scale_x, W, hp);
+  Taps ty0 = axis_taps_lb(iy_lo, p.pad_y, p.new_h, scale_y, H, hp), ty1 = axis_taps_lb(iy_hi, p.pad_y, p.new_h, scale_y, H, hp);
+  Taps tx0 = axis_taps_lb(ix_lo, p.pad_x, p.new_w, scale_x, W, hp), tx1 = axis_taps_lb(ix_hi, p.pad_x, p.new_w, scale_x, W, hp);
   int ry_lo = ty0.i0, ry_hi = ty1.i1, rx_lo = tx0.i0, rx_hi = tx1.i1;
   int sy_lo = p.rotate180 ? H - 1 - ry_hi : ry_lo, sy_hi = p.rotate180 ? H - 1 - ry_lo : ry_hi;
   int sx_lo = p.rotate180 ? W - 1 - rx_hi : rx_lo, sx_hi = p.rotate180 ? W - 1 - rx_lo : rx_hi;
@@ -214,15 +223,15 @@ preprocess_kernel(PreprocessParams p, int rows_cap, int pitch_s) {
   const size_t frame_bytes = (size_t)H * src_pitch;
   const uint8_t *base = p.src_indirect ? *p.src_indirect : p.src;
   const uint8_t *frame = base + (size_t)n * frame_bytes;
-  const float scale_x = __fdiv_rn((float)W, (float)kNet);
-  const float scale_y = __fdiv_rn((float)H, (float)kNet);
-  const int hp = (p.resize_mode == 2);
+  const float scale_x = __fdiv_rn((float)W, (float)p.new_w);
+  const float scale_y = __fdiv_rn((float)H, (float)p.new_h);
+  const int hp = (p.resize_mode != 0);
 
   __shared__ float lut[256];
   __shared__ Taps ytap[TH], xtap[TW];
   lut[threadIdx.x & 255] = __fdiv_rn((float)(threadIdx.x & 255), 255.0f);
-  if (threadIdx.x < TH) ytap[threadIdx.x] = axis_taps(min(oy0 + (int)threadIdx.x, kNet - 1), scale_y, H, hp);
-  else if (threadIdx.x < TH + TW) xtap[threadIdx.x - TH] = axis_taps(min(ox0 + (int)threadIdx.x - TH, kNet - 1), scale_x, W, hp);
+  if (threadIdx.x < TH) ytap[threadIdx.x] = axis_taps_lb(min(oy0 + (int)threadIdx.x, kNet - 1), p.pad_y, p.new_h, scale_y, H, hp);
+  else if (threadIdx.x < TH + TW) xtap[threadIdx.x - TH] = axis_taps_lb(min(ox0 + (int)threadIdx.x - TH, kNet - 1), p.pad_x, p.new_w, scale_x, W, hp);
   Region reg = stage_window(p, base, frame, smem, pitch_s, oy0, min(oy0 + TH, kNet) - 1, ox0, min(ox0 + TW, kNet) - 1,
                             scale_x, scale_y, hp, NT);
   __syncthreads();
@@ -237,7 +246,8 @@ preprocess_kernel(PreprocessParams p, int rows_cap, int pitch_s) {
     int oy = oy0 + q / TW, ox = ox0 + q % TW;
     if (oy >= kNet || ox >= kNet) continue;
     float v[3];
-    sample_pixel(reg, p, ytap[q / TW], xtap[q % TW], red_y, red_x, lut, v);
+    if (ytap[q / TW].ok && xtap[q % TW].ok) sample_pixel(reg, p, ytap[q / TW], xtap[q % TW], red_y, red_x, lut, v);
+    else v[0] = v[1] = v[2] = lut[114];                 // letterbox padding: 114 / 255
     __half2 h01 = __halves2half2(__float2half_rn(v[0]), __float2half_rn(v[1]));
     __half2 h23 = __halves2half2(__float2half_rn(v[2]), __float2half_rn(0.0f));
     uint4 o;
@@ -279,8 +289,8 @@ stem_kernel(PreprocessParams p, const float *__restrict__ w, const float *__rest
   const size_t frame_bytes = (size_t)H * W * (bayer ? 1 : 3);
   const uint8_t *base = p.src_indirect ? *p.src_indirect : p.src;
   const uint8_t *frame = base + (size_t)n * frame_bytes;
-  const float scale_x = __fdiv_rn((float)W, (float)kNet), scale_y = __fdiv_rn((float)H, (float)kNet);
-  const int hp = (p.resize_mode == 2);
+  const float scale_x = __fdiv_rn((float)W, (float)p.new_w), scale_y = __fdiv_rn((float)H, (float)p.new_h);
+  const int hp = (p.resize_mode != 0);
   __shared__ float lut[256];
   __shared__ Taps ytap[SI], xtap[SI];
   {
@@ -294,8 +304,8 @@ stem_kernel(PreprocessParams p, const float *__restrict__ w, const float *__rest
     }
   }
   lut[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.0f);                       // ST*ST == 256 threads
-  if (threadIdx.x < SI) ytap[threadIdx.x] = axis_taps(min(max(2 * oy0 - 1 + (int)threadIdx.x, 0), kNet - 1), scale_y, H, hp);
-  else if (threadIdx.x < 2 * SI) xtap[threadIdx.x - SI] = axis_taps(min(max(2 * ox0 - 1 + (int)threadIdx.x - SI, 0), kNet - 1), scale_x, W, hp);
+  if (threadIdx.x < SI) ytap[threadIdx.x] = axis_taps_lb(min(max(2 * oy0 - 1 + (int)threadIdx.x, 0), kNet - 1), p.pad_y, p.new_h, scale_y, H, hp);
+  else if (threadIdx.x < 2 * SI) xtap[threadIdx.x - SI] = axis_taps_lb(min(max(2 * ox0 - 1 + (int)threadIdx.x - SI, 0), kNet - 1), p.pad_x, p.new_w, scale_x, W, hp);
   // network-input window of this tile: rows 2*oy0-1 .. 2*oy0+2*ST-1 (clipped: outside is conv padding)
   const int iy_lo = 2 * oy0 - 1, ix_lo = 2 * ox0 - 1;
   Region reg = stage_window(p, base, frame, smem, pitch_s, max(iy_lo, 0), min(iy_lo + SI - 1, kNet - 1), max(ix_lo, 0),
@@ -381,7 +391,10 @@ stem_kernel(PreprocessParams p, const float *__restrict__ w, const float *__rest
       const int r = q / SI, c = q - r * SI;
       const int iy = iy_lo + r, ix = ix_lo + c;
       float v[3] = {0.f, 0.f, 0.f};
-      if (iy >= 0 && iy < kNet && ix >= 0 && ix < kNet) sample_pixel(reg, p, ytap[r], xtap[c], red_y, red_x, lut, v);
+      if (iy >= 0 && iy < kNet && ix >= 0 && ix < kNet) {
+        if (ytap[r].ok && xtap[c].ok) sample_pixel(reg, p, ytap[r], xtap[c], red_y, red_x, lut, v);
+        else v[0] = v[1] = v[2] = lut[114];             // letterbox padding: 114 / 255
+      }
       tile[0][r][c] = __float2half_rn(v[0]); tile[1][r][c] = __float2half_rn(v[1]); tile[2][r][c] = __float2half_rn(v[2]);
     }
   }
@@ -506,11 +519,13 @@ __global__ void rotate_kernel(PreprocessParams p) {
 
 }  // namespace
 
-cudaError_t launch_preprocess(const PreprocessParams &p, cudaStream_t s) {
+cudaError_t launch_preprocess(const PreprocessParams &p_in, cudaStream_t s) {
+  PreprocessParams p = p_in;
+  letterbox_geometry(p.src_w, p.src_h, p.resize_mode, &p.pad_x, &p.pad_y, &p.new_w, &p.new_h);
   if (p.n <= 0) return cudaSuccess;
   const bool bayer = p.chan_order >= 2;
   const int bpp = bayer ? 1 : 3;
-  const float sx = (float)p.src_w / kNet, sy = (float)p.src_h / kNet;
+  const float sx = (float)p.src_w / p.new_w, sy = (float)p.src_h / p.new_h;
   int rows_cap = (int)(TH * sy) + 4 + (bayer ? 4 : 0);
   int cols_cap = (int)(TW * sx) + 4 + (bayer ? 4 : 0);
   int pitch_s = ((cols_cap * bpp + 15) / 16 + 2) * 16;   // +1 chunk for the alignment shift
@@ -538,12 +553,14 @@ cudaError_t launch_preprocess(const PreprocessParams &p, cudaStream_t s) {
 }
 
 
-cudaError_t launch_stem(const PreprocessParams &p, const float *w, const float *bias, __half *out,
+cudaError_t launch_stem(const PreprocessParams &p_in, const float *w, const float *bias, __half *out,
                         long long out_pstride, __half *out2, long long out2_pstride, cudaStream_t s) {
+  PreprocessParams p = p_in;
+  letterbox_geometry(p.src_w, p.src_h, p.resize_mode, &p.pad_x, &p.pad_y, &p.new_w, &p.new_h);
   if (p.n <= 0) return cudaSuccess;
   const bool bayer = p.chan_order >= 2;
   const int bpp = bayer ? 1 : 3;
-  const float sx = (float)p.src_w / kNet, sy = (float)p.src_h / kNet;
+  const float sx = (float)p.src_w / p.new_w, sy = (float)p.src_h / p.new_h;
   int rows_cap = (int)(SI * sy) + 4 + (bayer ? 4 : 0);
   int cols_cap = (int)(SI * sx) + 4 + (bayer ? 4 : 0);
   int pitch_s = ((cols_cap * bpp + 15) / 16 + 2) * 16;
@@ -555,7 +572,7 @@ cudaError_t launch_stem(const PreprocessParams &p, const float *w, const float *
   }
   dim3 grid(kNet / 2 / ST, kNet / 2 / ST, p.n);
   // integer horizontal scale without half-pixel centres: every second x tap has weight exactly 0
-  const int fast_x = (p.src_w % kNet == 0) && p.resize_mode != 2;
+  const int fast_x = (p.src_w % kNet == 0) && p.resize_mode == 0;
   stem_kernel<<<grid, ST * ST, smem, s>>>(p, w, bias, out, out_pstride, out2, out2_pstride, pitch_s, fast_x);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess && p.rotated) {

@@ -48,7 +48,8 @@ class YoloEngine:
 
     def __init__(self, onnx_file_path: str, src_image_size: Tuple[int, int] = (1280, 1024),
                  enable_profiling: bool = False, *, chan_order: int = L.CH_PASSTHROUGH,
-                 rotate180: bool = True, quantize_u8: bool = True, half_pixel: bool = False, max_batch: int = 1,
+                 rotate180: bool = True, quantize_u8: bool = True, half_pixel: bool = False, letterbox: bool = False,
+                 max_batch: int = 1,
                  sub_batch: int = 0, num_lanes: int = 0, num_slots: int = 3, device: int = 0,
                  conv_impl: int = L.CONV_TCGEN05, score_thr: float = 0.25, iou_thr: float = 0.45,
                  max_det: int = 100, use_graph: bool = True, fused_stem: bool = True):
@@ -64,7 +65,7 @@ class YoloEngine:
         cfg.chan_order = chan_order
         cfg.rotate180 = int(rotate180)
         cfg.quantize_u8 = int(quantize_u8)
-        cfg.resize_mode = L.RESIZE_STRETCH_HALF_PIXEL if half_pixel else L.RESIZE_STRETCH
+        cfg.resize_mode = L.RESIZE_LETTERBOX if letterbox else (L.RESIZE_STRETCH_HALF_PIXEL if half_pixel else L.RESIZE_STRETCH)
         cfg.max_batch, cfg.sub_batch, cfg.num_lanes, cfg.num_slots = max_batch, sub_batch, num_lanes, num_slots
         cfg.device, cfg.conv_impl = device, conv_impl
         cfg.score_thr, cfg.iou_thr, cfg.max_det = score_thr, iou_thr, max_det
@@ -307,14 +308,15 @@ class PnPSolver:
 # ---- stage-level wrappers (parity tests) ------------------------------------------------------
 def preprocess(frames: np.ndarray, chan_order: int = L.CH_PASSTHROUGH, rotate180: bool = True,
                quantize_u8: bool = True, want_rotated: bool = False, device: int = 0,
-               half_pixel: bool = False):
+               half_pixel: bool = False, letterbox: bool = False):
     """frames u8 [n,H,W,3] or [n,H,W] -> FP16 [n,640,640,8] NHWC (+ rotated u8 [n,H,W,3])."""
     frames = np.ascontiguousarray(frames, np.uint8)
     n, H, W = frames.shape[:3]
     out = np.empty((n, L.NET, L.NET, 8), np.float16)
     rot = np.empty((n, H, W, 3), np.uint8) if want_rotated else None
     L.check(L.lib().irmv_preprocess(frames.ctypes.data, n, W, H, chan_order, int(rotate180),
-                                    L.RESIZE_STRETCH_HALF_PIXEL if half_pixel else L.RESIZE_STRETCH,
+                                    L.RESIZE_LETTERBOX if letterbox else
+                                    (L.RESIZE_STRETCH_HALF_PIXEL if half_pixel else L.RESIZE_STRETCH),
                                     int(quantize_u8), out.ctypes.data, rot.ctypes.data if want_rotated else None,
                                     device), "irmv_preprocess")
     return (out, rot) if want_rotated else out

@@ -152,6 +152,51 @@ def preprocess_fp16(src, chan=CH_PASSTHROUGH, rotate=True, quantize_u8=True, hal
     return x.astype(np.float16), img
 
 
+# ---- LETTERBOX mode (not what the reference does: it stretches, src/yolo_engine.cpp:186-190; this is
+# the form BASELINE.json's north_star / configs[0] name).  Restates ultralytics' LetterBox
+# (data/augment.py, the preprocessing every YOLOv8 export expects): r = min(640/h, 640/w),
+# new_unpad = round(size * r), cv2.resize(INTER_LINEAR) = pixel-centre bilinear, centred with
+# top/left = round(d - 0.1), border value 114.  Parity unpinned by the reference.
+LETTERBOX_PAD = 114
+
+
+def letterbox_geometry(src_w: int, src_h: int):
+    r = min(NET / src_w, NET / src_h)
+    new_w, new_h = min(int(src_w * r + 0.5), NET), min(int(src_h * r + 0.5), NET)
+    pad_x = max(int((NET - new_w) / 2.0 - 0.1 + 0.5), 0)
+    pad_y = max(int((NET - new_h) / 2.0 - 0.1 + 0.5), 0)
+    return pad_x, pad_y, new_w, new_h
+
+
+def preprocess_letterbox(src: np.ndarray, chan: int = CH_PASSTHROUGH, rotate: bool = True, quantize_u8: bool = True):
+    """(input f32[3,640,640], geometry) for resize_mode LETTERBOX."""
+    img = to_rgb(src, chan)
+    if rotate:
+        img = rot180(img)
+    H, W, _ = img.shape
+    pad_x, pad_y, new_w, new_h = letterbox_geometry(W, H)
+    if quantize_u8:
+        r = resize_bilinear_u8(img, new_h, new_w, True).astype(np.float32)
+        pad = np.float32(LETTERBOX_PAD)
+    else:
+        r = resize_bilinear_f32(img, new_h, new_w, True)
+        pad = np.float32(LETTERBOX_PAD)
+    out = np.full((NET, NET, 3), pad, np.float32)
+    out[pad_y:pad_y + new_h, pad_x:pad_x + new_w] = r
+    x = out / np.float32(255.0)
+    return np.ascontiguousarray(x.transpose(2, 0, 1)), (pad_x, pad_y, new_w, new_h)
+
+
+def unletterbox_boxes(boxes: np.ndarray, src_w: int, src_h: int) -> np.ndarray:
+    """Network-pixel xyxy -> source pixels (the inverse the engine's parse_output applies)."""
+    pad_x, pad_y, new_w, new_h = letterbox_geometry(src_w, src_h)
+    sx, sy = np.float32(src_w) / np.float32(new_w), np.float32(src_h) / np.float32(new_h)
+    b = np.asarray(boxes, np.float32).copy()
+    b[:, [0, 2]] = (b[:, [0, 2]] - np.float32(pad_x)) * sx
+    b[:, [1, 3]] = (b[:, [1, 3]] - np.float32(pad_y)) * sy
+    return b
+
+
 def preprocess_cv2(src_bgr: np.ndarray):
     """The CPU-baseline form named in BASELINE.md section 3 (cv2.flip + cv2.resize + /255 + CHW)."""
     import cv2

@@ -281,3 +281,23 @@ def test_triple_buffer_monotonic(tmp_path):
                     os.path.join(ROOT, "tests", "cpp", "triple_buffer_test.cpp"), "-o", str(exe)], check=True)
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "FAIL" not in r.stdout, r.stdout[-500:]
+
+
+def test_letterbox_oracle_vs_cv2(base_image):
+    """LETTERBOX oracle vs the ultralytics recipe done with cv2 (resize INTER_LINEAR + copyMakeBorder
+    114): same geometry, pixels within 1 grey level (cv2 resizes u8 in fixed point)."""
+    import cv2
+    from oracle import preprocess_ref as PR
+    for img in (base_image, np.ascontiguousarray(base_image[:700, :900])):
+        H, W = img.shape[:2]
+        x, (px, py, nw, nh) = PR.preprocess_letterbox(img, rotate=False)
+        r = min(640 / H, 640 / W)
+        new_unpad = int(round(W * r)), int(round(H * r))
+        dw, dh = (640 - new_unpad[0]) / 2, (640 - new_unpad[1]) / 2
+        ref = cv2.resize(img, new_unpad, interpolation=cv2.INTER_LINEAR)
+        top, bottom = int(round(dh - 0.1)), int(round(dh + 0.1))
+        left, right = int(round(dw - 0.1)), int(round(dw + 0.1))
+        ref = cv2.copyMakeBorder(ref, top, bottom, left, right, cv2.BORDER_CONSTANT, value=(114, 114, 114))
+        assert ref.shape[:2] == (640, 640) and (px, py, nw, nh) == (left, top, new_unpad[0], new_unpad[1])
+        got = np.rint(x.transpose(1, 2, 0) * 255).astype(np.int32)
+        assert np.abs(got - ref.astype(np.int32)).max() <= 1
