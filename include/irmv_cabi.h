@@ -172,6 +172,11 @@ int irmv_pnp_solve_batch(irmv_pnp *p, const float *img_pts, int n, int on_device
 int irmv_pnp_solve_batch_ex(irmv_pnp *p, const float *img_pts, int n, int on_device,
                             int large_armor, double *rvecs, double *tvecs, uint8_t *ok,
                             double *quats, double *rvecs2, double *tvecs2, double *rmse2);
+/* Optional stage, OFF by default (= reference behaviour: cv::solvePnP(..., SOLVEPNP_IPPE) does not refine,
+ * src/pnp_solver.cpp:49-51): max_iters > 0 adds a Levenberg-Marquardt refinement of the returned pose on the pixel
+ * reprojection error (the north_star's "IPPE + LM"; oracle cv2.solvePnPRefineLM).  Second solution and RMSE outputs of
+ * _ex stay IPPE's. */
+int irmv_pnp_set_refine_lm(irmv_pnp *p, int max_iters);
 double irmv_pnp_last_device_ms(irmv_pnp *p);
 float irmv_pnp_distance_to_center(irmv_pnp *p, float x, float y);
 

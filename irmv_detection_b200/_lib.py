@@ -70,6 +70,7 @@ SYMBOLS = {
     "irmv_pnp_solve_batch": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "irmv_pnp_solve_batch_ex": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P]),
     "irmv_pnp_last_device_ms": (C.c_double, [_P]),
+    "irmv_pnp_set_refine_lm": (C.c_int, [_P, C.c_int]),
     "irmv_pnp_distance_to_center": (C.c_float, [_P, C.c_float, C.c_float]),
 }
 

@@ -179,5 +179,9 @@ struct PnpOut {
 };
 cudaError_t launch_pnp(const PnpConsts &c, const float *pts, int n, int large, PnpOut out,
                        cudaStream_t s);
+// Optional Levenberg-Marquardt refinement of (rvec, tvec) in place on the pixel reprojection error
+// (not in the reference's call; oracle cv2.solvePnPRefineLM).  quat may be null.
+cudaError_t launch_pnp_refine_lm(const PnpConsts &c, const float *pts, int n, int large, int max_iters, double *rvec,
+                                 double *tvec, double *quat, cudaStream_t s);
 
 }  // namespace irmv

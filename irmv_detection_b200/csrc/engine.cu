@@ -1241,6 +1241,7 @@ struct irmv_pnp {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   double last_ms = 0.0;
+  int lm_iters = 0;             // > 0: Levenberg-Marquardt refinement after IPPE (not in the reference's call)
   // small persistent buffers for the single-armor call
   float *d_pts1 = nullptr;
   double *d_out1 = nullptr;   // rvec[3] tvec[3]
@@ -1297,6 +1298,8 @@ int irmv_pnp_solve(irmv_pnp *p, const float img_pts[8], double rvec[3], double t
   IRMV_CUDA(cudaMemcpyAsync(p->d_pts1, p->h_pts1, 32, cudaMemcpyHostToDevice, p->stream));
   PnpOut o{p->d_out1, p->d_out1 + 3, p->d_ok1, nullptr, nullptr, nullptr, nullptr};
   IRMV_CUDA(launch_pnp(p->c, p->d_pts1, 1, 0 /* reference: small_armor = true, src/pnp_solver.cpp:47 */, o, p->stream));
+  if (p->lm_iters > 0)
+    IRMV_CUDA(launch_pnp_refine_lm(p->c, p->d_pts1, 1, 0, p->lm_iters, p->d_out1, p->d_out1 + 3, nullptr, p->stream));
   IRMV_CUDA(cudaMemcpyAsync(p->h_out1, p->d_out1, 48, cudaMemcpyDeviceToHost, p->stream));
   IRMV_CUDA(cudaMemcpyAsync(p->h_ok1, p->d_ok1, 1, cudaMemcpyDeviceToHost, p->stream));
   IRMV_CUDA(cudaStreamSynchronize(p->stream));
@@ -1332,6 +1335,7 @@ int irmv_pnp_solve_batch_ex(irmv_pnp *p, const float *img_pts, int n, int on_dev
   PnpOut o{dr, dt, dk, dq, dr2, dt2, de};
   IRMV_CUDA(cudaEventRecord(p->ev0, p->stream));
   IRMV_CUDA(launch_pnp(p->c, dp, n, large, o, p->stream));
+  if (p->lm_iters > 0) IRMV_CUDA(launch_pnp_refine_lm(p->c, dp, n, large, p->lm_iters, dr, dt, dq, p->stream));
   IRMV_CUDA(cudaEventRecord(p->ev1, p->stream));
   IRMV_CUDA(cudaMemcpyAsync(rvecs, dr, (size_t)n * 24, cudaMemcpyDeviceToHost, p->stream));
   IRMV_CUDA(cudaMemcpyAsync(tvecs, dt, (size_t)n * 24, cudaMemcpyDeviceToHost, p->stream));
@@ -1357,6 +1361,12 @@ int irmv_pnp_solve_batch(irmv_pnp *p, const float *img_pts, int n, int on_device
                          double *rvecs, double *tvecs, uint8_t *ok) {
   return irmv_pnp_solve_batch_ex(p, img_pts, n, on_device, large, rvecs, tvecs, ok, nullptr, nullptr,
                                  nullptr, nullptr);
+}
+
+int irmv_pnp_set_refine_lm(irmv_pnp *p, int max_iters) {
+  if (!p || max_iters < 0 || max_iters > 1000) { set_error("bad argument"); return 1; }
+  p->lm_iters = max_iters;
+  return 0;
 }
 
 double irmv_pnp_last_device_ms(irmv_pnp *p) { return p ? p->last_ms : 0.0; }

@@ -213,6 +213,174 @@ __global__ void __launch_bounds__(128) pnp_kernel(PnpConsts C, const float *__re
   }
 }
 
+// ------------------------------------------------------------------ optional LM refinement
+// Levenberg-Marquardt on the pixel reprojection error of the 4 corners (plumb-bob projection with
+// K and D), 6 parameters, started from the IPPE pose.  NOT part of the reference's call
+// (cv::solvePnP(..., SOLVEPNP_IPPE) has no refinement): this is the
+// north_star's "IPPE + LM" stage, oracle = cv2.solvePnPRefineLM.  The rotation is updated
+// multiplicatively (R <- exp(dw) R), which has the same minimiser as OpenCV's rvec
+// parametrisation; one armor per thread, FP64.
+__device__ __forceinline__ void rodrigues(const double r[3], double R[3][3]) {
+  const double th2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+  const double th = sqrt(th2);
+  double a, b;                       // a = sin(th)/th, b = (1 - cos(th))/th^2
+  if (th < 1e-8) { a = 1.0 - th2 / 6.0; b = 0.5 - th2 / 24.0; }
+  else { a = sin(th) / th; b = (1.0 - cos(th)) / th2; }
+  const double x = r[0], y = r[1], z = r[2];
+  R[0][0] = 1.0 - b * (y * y + z * z); R[0][1] = -a * z + b * x * y;        R[0][2] = a * y + b * x * z;
+  R[1][0] = a * z + b * x * y;         R[1][1] = 1.0 - b * (x * x + z * z); R[1][2] = -a * x + b * y * z;
+  R[2][0] = -a * y + b * x * z;        R[2][1] = a * x + b * y * z;         R[2][2] = 1.0 - b * (x * x + y * y);
+}
+
+// residuals (8) and cost of pose (R, t); optionally the normal equations JtJ (upper, 21) and Jtf (6)
+__device__ __forceinline__ double lm_eval(const PnpConsts &C, const double R[3][3], const double t[3], const double ha,
+                                          const double hb, const double px[4], const double py[4], bool want_j,
+                                          double JtJ[6][6], double Jtf[6]) {
+  double cost = 0.0;
+  if (want_j) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      Jtf[i] = 0.0;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) JtJ[i][j] = 0.0;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    // model-frame corners LB, LT, RT, RB: (0, +-ha, -+hb)  (reference src/pnp_solver.cpp:23-28)
+    const double Y = (k < 2) ? ha : -ha, Z = (k == 1 || k == 2) ? hb : -hb;
+    const double a0 = R[0][1] * Y + R[0][2] * Z, a1 = R[1][1] * Y + R[1][2] * Z, a2 = R[2][1] * Y + R[2][2] * Z;
+    const double Px = a0 + t[0], Py = a1 + t[1], Pz = a2 + t[2];
+    const double iz = 1.0 / Pz, xn = Px * iz, yn = Py * iz;
+    const double r2 = xn * xn + yn * yn;
+    const double rad = 1.0 + ((C.k3 * r2 + C.k2) * r2 + C.k1) * r2;
+    const double xd = xn * rad + 2.0 * C.p1 * xn * yn + C.p2 * (r2 + 2.0 * xn * xn);
+    const double yd = yn * rad + C.p1 * (r2 + 2.0 * yn * yn) + 2.0 * C.p2 * xn * yn;
+    const double fu = C.fx * xd + C.cx - px[k], fv = C.fy * yd + C.cy - py[k];
+    cost += fu * fu + fv * fv;
+    if (want_j) {
+      const double g = (3.0 * C.k3 * r2 + 2.0 * C.k2) * r2 + C.k1;        // d rad / d r2
+      const double dxx = rad + 2.0 * g * xn * xn + 2.0 * C.p1 * yn + 6.0 * C.p2 * xn;
+      const double dxy = 2.0 * g * xn * yn + 2.0 * C.p1 * xn + 2.0 * C.p2 * yn;
+      const double dyy = rad + 2.0 * g * yn * yn + 6.0 * C.p1 * yn + 2.0 * C.p2 * xn;
+      // d(xn, yn)/dP
+      const double nx[3] = {iz, 0.0, -xn * iz}, ny[3] = {0.0, iz, -yn * iz};
+      double gu[3], gv[3];            // d(u, v)/dP
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        gu[c] = C.fx * (dxx * nx[c] + dxy * ny[c]);
+        gv[c] = C.fy * (dxy * nx[c] + dyy * ny[c]);
+      }
+      // dP/d(dw) = -skew(a): columns (0, a2, -a1)... i.e. grad . (dw x a) = dw . (a x grad)
+      const double Ju[6] = {a1 * gu[2] - a2 * gu[1], a2 * gu[0] - a0 * gu[2], a0 * gu[1] - a1 * gu[0], gu[0], gu[1], gu[2]};
+      const double Jv[6] = {a1 * gv[2] - a2 * gv[1], a2 * gv[0] - a0 * gv[2], a0 * gv[1] - a1 * gv[0], gv[0], gv[1], gv[2]};
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        Jtf[i] += Ju[i] * fu + Jv[i] * fv;
+#pragma unroll
+        for (int j = i; j < 6; ++j) JtJ[i][j] += Ju[i] * Ju[j] + Jv[i] * Jv[j];
+      }
+    }
+  }
+  return cost;
+}
+
+__global__ void __launch_bounds__(64) pnp_refine_kernel(PnpConsts C, const float *__restrict__ pts, int n, int large,
+                                                       int max_iters, double *rvec, double *tvec, double *quat) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 *pp = reinterpret_cast<const float4 *>(pts) + (size_t)i * 2;
+  const float4 pa = __ldg(pp), pb = __ldg(pp + 1);
+  const double px[4] = {pa.x, pa.z, pb.x, pb.z}, py[4] = {pa.y, pa.w, pb.y, pb.w};
+  const double ha = C.half_w[large ? 1 : 0], hb = C.half_h[large ? 1 : 0];
+  double r[3] = {rvec[(size_t)i * 3], rvec[(size_t)i * 3 + 1], rvec[(size_t)i * 3 + 2]};
+  double t[3] = {tvec[(size_t)i * 3], tvec[(size_t)i * 3 + 1], tvec[(size_t)i * 3 + 2]};
+  if (!(isfinite(r[0]) && isfinite(r[1]) && isfinite(r[2]) && isfinite(t[0]) && isfinite(t[1]) && isfinite(t[2]))) return;
+  double R[3][3];
+  rodrigues(r, R);
+  double A[6][6], g[6];
+  double lambda = 1e-3;
+  double cost = lm_eval(C, R, t, ha, hb, px, py, true, A, g);
+  for (int it = 0; it < max_iters; ++it) {
+    // (JtJ + lambda diag) d = -Jtf, Cholesky
+    double L[6][6], d[6];
+    bool spd = true;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      double s = A[c][c] * (1.0 + lambda);
+#pragma unroll
+      for (int k = 0; k < c; ++k) s -= L[c][k] * L[c][k];
+      if (!(s > 0.0)) spd = false;
+      const double lc = sqrt(fmax(s, 1e-300));
+      L[c][c] = lc;
+#pragma unroll
+      for (int rr = c + 1; rr < 6; ++rr) {
+        double v = A[c][rr];
+#pragma unroll
+        for (int k = 0; k < c; ++k) v -= L[rr][k] * L[c][k];
+        L[rr][c] = v / lc;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {              // forward: L y = -g
+      double v = -g[c];
+#pragma unroll
+      for (int k = 0; k < c; ++k) v -= L[c][k] * d[k];
+      d[c] = v / L[c][c];
+    }
+#pragma unroll
+    for (int c = 5; c >= 0; --c) {             // backward: L^T d = y
+      double v = d[c];
+#pragma unroll
+      for (int k = c + 1; k < 6; ++k) v -= L[k][c] * d[k];
+      d[c] = v / L[c][c];
+    }
+    double dR[3][3], Rn[3][3], tn[3] = {t[0] + d[3], t[1] + d[4], t[2] + d[5]};
+    const double dw[3] = {d[0], d[1], d[2]};
+    rodrigues(dw, dR);
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) Rn[a][b] = dR[a][0] * R[0][b] + dR[a][1] * R[1][b] + dR[a][2] * R[2][b];
+    double An[6][6], gn[6];
+    const double cn = spd ? lm_eval(C, Rn, tn, ha, hb, px, py, true, An, gn) : cost;
+    const double step2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2] + d[3] * d[3] + d[4] * d[4] + d[5] * d[5];
+    if (spd && cn < cost) {                    // accept
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        t[a] = tn[a];
+#pragma unroll
+        for (int b = 0; b < 3; ++b) R[a][b] = Rn[a][b];
+      }
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        g[a] = gn[a];
+#pragma unroll
+        for (int b = 0; b < 6; ++b) A[a][b] = An[a][b];
+      }
+      const double rel = (cost - cn) / fmax(cost, 1e-300);
+      cost = cn;
+      lambda = fmax(lambda * 0.1, 1e-12);
+      if (step2 < 1e-24 || rel < 1e-14) break;
+    } else {
+      lambda = fmin(lambda * 10.0, 1e12);
+      if (step2 < 1e-24) break;
+    }
+  }
+  rot2vec(R, r);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    rvec[(size_t)i * 3 + k] = r[k];
+    tvec[(size_t)i * 3 + k] = t[k];
+  }
+  if (quat) {
+    double qv[4];
+    rot2quat(R, qv);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) quat[(size_t)i * 4 + k] = qv[k];
+  }
+}
+
 }  // namespace
 
 cudaError_t launch_pnp(const PnpConsts &c, const float *pts, int n, int large, PnpOut out,
@@ -223,4 +391,13 @@ cudaError_t launch_pnp(const PnpConsts &c, const float *pts, int n, int large, P
   return cudaGetLastError();
 }
 
+}  // namespace irmv
+
+namespace irmv {
+cudaError_t launch_pnp_refine_lm(const PnpConsts &c, const float *pts, int n, int large, int max_iters, double *rvec,
+                                 double *tvec, double *quat, cudaStream_t s) {
+  if (n <= 0 || max_iters <= 0) return cudaSuccess;
+  pnp_refine_kernel<<<(n + 63) / 64, 64, 0, s>>>(c, pts, n, large, max_iters, rvec, tvec, quat);
+  return cudaGetLastError();
+}
 }  // namespace irmv

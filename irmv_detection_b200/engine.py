@@ -290,6 +290,10 @@ class PnPSolver:
     def last_device_ms(self) -> float:
         return float(self._lib.irmv_pnp_last_device_ms(self._h))
 
+    def set_refine_lm(self, max_iters: int = 20) -> None:
+        """Optional Levenberg-Marquardt refinement after IPPE (0 = off = reference behaviour)."""
+        L.check(self._lib.irmv_pnp_set_refine_lm(self._h, int(max_iters)), "irmv_pnp_set_refine_lm")
+
     def calculateDistanceToCenter(self, image_point) -> float:
         return float(self._lib.irmv_pnp_distance_to_center(self._h, float(image_point[0]), float(image_point[1])))
 

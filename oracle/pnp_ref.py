@@ -296,3 +296,32 @@ def synth_quads(n: int, seed: int = 0, noise_px: float = 0.5, K=K_DEFAULT, D=D_D
         out[i] = p.astype(np.float32)
         i += 1
     return out
+
+
+def refine_lm_cv2(img_pts: np.ndarray, rvecs: np.ndarray, tvecs: np.ndarray, K=K_DEFAULT, D=D_DEFAULT,
+                  large: bool = False):
+    """Oracle of the optional LM stage (NOT in the reference's call): cv2.solvePnPRefineLM with a
+    tight termination criterion, started from the given poses."""
+    import cv2
+    obj = object_points(large)
+    Km = np.asarray(K, np.float64).reshape(3, 3)
+    Dm = np.asarray(D, np.float64).reshape(-1, 1)
+    out_r, out_t = np.empty_like(rvecs), np.empty_like(tvecs)
+    crit = (cv2.TERM_CRITERIA_EPS + cv2.TERM_CRITERIA_COUNT, 200, 1e-15)
+    for i in range(len(img_pts)):
+        r, t = cv2.solvePnPRefineLM(obj, np.asarray(img_pts[i], np.float64).reshape(4, 1, 2), Km, Dm,
+                                    rvecs[i].reshape(3, 1).copy(), tvecs[i].reshape(3, 1).copy(), crit)
+        out_r[i], out_t[i] = r.ravel(), t.ravel()
+    return out_r, out_t
+
+
+def reprojection_rmse_px(img_pts, rvecs, tvecs, K=K_DEFAULT, D=D_DEFAULT, large=False):
+    import cv2
+    obj = object_points(large)
+    Km = np.asarray(K, np.float64).reshape(3, 3)
+    Dm = np.asarray(D, np.float64).reshape(-1, 1)
+    out = np.empty(len(img_pts))
+    for i in range(len(img_pts)):
+        pr, _ = cv2.projectPoints(obj, rvecs[i].reshape(3, 1), tvecs[i].reshape(3, 1), Km, Dm)
+        out[i] = np.sqrt(np.mean((pr.reshape(4, 2) - np.asarray(img_pts[i], np.float64).reshape(4, 2)) ** 2))
+    return out

@@ -201,6 +201,35 @@ def test_pnp_batch_vs_oracle_and_cv2():
         np.testing.assert_allclose(quat[i], ref, atol=1e-7)
 
 
+def test_pnp_lm_refinement_vs_cv2():
+    """Optional IPPE + LM stage (north_star item 4; the reference's call has no refinement, so it is
+    OFF by default): refined poses equal cv2.solvePnPRefineLM started from the same IPPE poses
+    within 1e-4 relative, never increase the pixel reprojection error, and IPPE-only output is
+    unchanged when the stage is off."""
+    import irmv_detection_b200 as irmv
+    from oracle import pnp_ref as P
+    _cuda()
+    q = P.synth_quads(400, seed=7)
+    s = irmv.PnPSolver(P.K_DEFAULT, P.D_DEFAULT)
+    r0, t0, ok0 = s.solve_batch(q)
+    s.set_refine_lm(30)
+    r1, t1, ok1 = s.solve_batch(q)
+    okb, rs, ts = s.solvePnP(q[5])
+    s.set_refine_lm(0)
+    r2, t2, _ = s.solve_batch(q)
+    assert np.array_equal(r0, r2) and np.array_equal(t0, t2) and ok1.all()
+    assert okb and np.allclose(rs.ravel(), r1[5], rtol=0, atol=1e-12) and np.allclose(ts.ravel(), t1[5], rtol=0, atol=1e-12)
+    rc, tc = P.refine_lm_cv2(q, r0, t0)
+    e0, e1, ec = (P.reprojection_rmse_px(q, a, b) for a, b in ((r0, t0), (r1, t1), (rc, tc)))
+    assert (e1 <= e0 + 1e-9).all()
+    assert (e1 <= ec + 1e-6).all()                      # at least as converged as OpenCV's solver
+    same = np.abs(e1 - ec) < 1e-6                       # both reached the same minimum
+    assert same.mean() > 0.97
+    rel_r = np.linalg.norm(r1 - rc, axis=1) / np.linalg.norm(rc, axis=1)
+    rel_t = np.linalg.norm(t1 - tc, axis=1) / np.linalg.norm(tc, axis=1)
+    assert rel_r[same].max() < PNP_REL_TOL and rel_t[same].max() < PNP_REL_TOL
+
+
 def test_pnp_single_matches_batch():
     import irmv_detection_b200 as irmv
     from oracle import pnp_ref as P
