@@ -373,14 +373,14 @@ void add_conv(irmv_engine *e, Lane &ln, HostConv &hc, std::vector<SegRef> in, in
 // C2f (ultralytics): cv1 -> split -> n bottlenecks chained on the last chunk -> cv2 over all chunks.
 // All chunks live in one buffer so split and concat are channel offsets.
 bool add_c2f(irmv_engine *e, Lane &ln, size_t &ci, std::vector<SegRef> in, int H, int W, int c2,
-             int n, bool shortcut, Tensor &out, const char *tap, bool parity_out = false) {
+             int n, bool shortcut, Tensor &out, const char *tap, int parity_out = 0) {   // 1: twin only, 2: both layouts
   const int c = c2 / 2;
   Tensor buf, tmp;
   if (!new_tensor(ln, e->S, H, W, (2 + n) * c, buf) || !new_tensor(ln, e->S, H, W, c, tmp) ||
       !new_tensor(ln, e->S, H, W, c2, out, tap))
     return false;
   if (parity_out) {
-    if (!add_parity_twin(ln, e->S, out, true)) return false;
+    if (!add_parity_twin(ln, e->S, out, parity_out == 1)) return false;
     if (tap) ln.taps[tap] = out;
   }
   add_conv(e, ln, *e->convs[ci++], in, H, W, buf, 0);
@@ -407,6 +407,8 @@ bool build_lane(irmv_engine *e, Lane &ln) {
   // their inputs (m1, m3, m5, m16); the producers write the twin next to the normal layout
   const bool par = e->cfg.conv_impl != IRMV_CONV_DIRECT && !getenv("IRMV_NO_RASTER") && !getenv("IRMV_NO_S2_RASTER");
   const bool fused = e->fused_stem && e->cfg.conv_impl != IRMV_CONV_DIRECT;
+  // x4 / x15 also feed stride-1 consumers, so their producers would write both layouts (m5, m16)
+  const bool par2 = par && getenv("IRMV_S2_DUAL");
   if (!new_tensor(ln, S, 320, 320, 16, t0, "m0")) return false;
   if (par && fused && !add_parity_twin(ln, S, t0, true)) return false;
   ln.taps["m0"] = t0;
@@ -415,10 +417,10 @@ bool build_lane(irmv_engine *e, Lane &ln) {
   ln.stem_out = t0;
   if (!new_tensor(ln, S, 160, 160, 32, t1, "m1")) return false;
   add_conv(e, ln, *e->convs[ci++], {{&t0, 0, 16, 0}}, 320, 320, t1, 0);
-  if (!add_c2f(e, ln, ci, {{&t1, 0, 32, 0}}, 160, 160, 32, 1, true, x2, "m2", par)) return false;
+  if (!add_c2f(e, ln, ci, {{&t1, 0, 32, 0}}, 160, 160, 32, 1, true, x2, "m2", par ? 1 : 0)) return false;
   if (!new_tensor(ln, S, 80, 80, 64, t3, "m3")) return false;
   add_conv(e, ln, *e->convs[ci++], {{&x2, 0, 32, 0}}, 160, 160, t3, 0);
-  if (!add_c2f(e, ln, ci, {{&t3, 0, 64, 0}}, 80, 80, 64, 2, true, x4, "m4")) return false;
+  if (!add_c2f(e, ln, ci, {{&t3, 0, 64, 0}}, 80, 80, 64, 2, true, x4, "m4", par2 ? 2 : 0)) return false;
   if (!new_tensor(ln, S, 40, 40, 128, t5, "m5")) return false;
   add_conv(e, ln, *e->convs[ci++], {{&x4, 0, 64, 0}}, 80, 80, t5, 0);
   if (!add_c2f(e, ln, ci, {{&t5, 0, 128, 0}}, 40, 40, 128, 2, true, x6, "m6")) return false;
@@ -435,7 +437,7 @@ bool build_lane(irmv_engine *e, Lane &ln) {
   add_conv(e, ln, *e->convs[ci++], {{&sp, 0, 512, 0}}, 20, 20, x9, 0);
   // neck: upsample and concat happen in the consumers' gathers
   if (!add_c2f(e, ln, ci, {{&x9, 0, 256, 1}, {&x6, 0, 128, 0}}, 40, 40, 128, 1, false, x12, "m12")) return false;
-  if (!add_c2f(e, ln, ci, {{&x12, 0, 128, 1}, {&x4, 0, 64, 0}}, 80, 80, 64, 1, false, x15, "m15")) return false;
+  if (!add_c2f(e, ln, ci, {{&x12, 0, 128, 1}, {&x4, 0, 64, 0}}, 80, 80, 64, 1, false, x15, "m15", par2 ? 2 : 0)) return false;
   if (!new_tensor(ln, S, 40, 40, 64, t16, "m16")) return false;
   add_conv(e, ln, *e->convs[ci++], {{&x15, 0, 64, 0}}, 80, 80, t16, 0);
   if (!add_c2f(e, ln, ci, {{&t16, 0, 64, 0}, {&x12, 0, 128, 0}}, 40, 40, 128, 1, false, x18, "m18")) return false;
