@@ -34,6 +34,28 @@ K_CAM = [957.669211, 0.0, 345.943891, 0.0, 969.127115, 284.057302, 0.0, 0.0, 1.0
 D_CAM = [-0.405274, 0.126058, -0.026939, -0.006503, 0.0]
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Libraries (NCCL's version banner, cv2) write to fd 1; the contract is ONE JSON line on stdout,
+    so everything but that line is sent to stderr."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -222,7 +244,7 @@ def run_reference(args):
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------- ours
@@ -420,7 +442,7 @@ def run_ours(args):
     if cpu is not None:
         line["cpu_baseline"] = cpu
     eng.close()
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -436,6 +458,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
