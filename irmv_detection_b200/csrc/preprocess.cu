@@ -292,6 +292,7 @@ stem_kernel(PreprocessParams p, const float *__restrict__ w, const float *__rest
   const float scale_x = __fdiv_rn((float)W, (float)p.new_w), scale_y = __fdiv_rn((float)H, (float)p.new_h);
   const int hp = (p.resize_mode != 0);
   __shared__ float lut[256];
+  __shared__ __half lut_h[256];
   __shared__ Taps ytap[SI], xtap[SI];
   {
     const int nn = threadIdx.x >> 4, k0 = 2 * (threadIdx.x & 15);
@@ -304,6 +305,7 @@ stem_kernel(PreprocessParams p, const float *__restrict__ w, const float *__rest
     }
   }
   lut[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.0f);                       // ST*ST == 256 threads
+  lut_h[threadIdx.x] = __float2half_rn(__fdiv_rn((float)threadIdx.x, 255.0f));
   if (threadIdx.x < SI) ytap[threadIdx.x] = axis_taps_lb(min(max(2 * oy0 - 1 + (int)threadIdx.x, 0), kNet - 1), p.pad_y, p.new_h, scale_y, H, hp);
   else if (threadIdx.x < 2 * SI) xtap[threadIdx.x - SI] = axis_taps_lb(min(max(2 * ox0 - 1 + (int)threadIdx.x - SI, 0), kNet - 1), p.pad_x, p.new_w, scale_x, W, hp);
   // network-input window of this tile: rows 2*oy0-1 .. 2*oy0+2*ST-1 (clipped: outside is conv padding)
@@ -355,21 +357,33 @@ stem_kernel(PreprocessParams p, const float *__restrict__ w, const float *__rest
         load_row(sy + dir, c0, c1, c2);
         cur = sy;
       };
+      // colour-site cases: with an even integer scale the column parity is the same for every
+      // thread, so both branches below are warp-uniform (a warp works on one input row)
       auto demosaic = [&](int sy, int &R, int &G, int &B) {
-        const int cross = (a1 + c1 + b0 + b2 + 2) >> 2, diag = (a0 + a2 + c0 + c2 + 2) >> 2;
-        const int horiz = (b0 + b2 + 1) >> 1, vert = (a1 + c1 + 1) >> 1;
         const bool red_row = ((sy & 1) == red_y);
-        const bool is_r = red_row && red_col, is_b = !red_row && !red_col;
-        G = (is_r || is_b) ? cross : b1;
-        R = is_r ? b1 : (is_b ? diag : (red_row ? horiz : vert));
-        B = is_b ? b1 : (is_r ? diag : (red_row ? vert : horiz));
+        if (red_row == red_col) {            // red or blue site: own colour, green cross, other colour diagonal
+          const int cross = (a1 + c1 + b0 + b2 + 2) >> 2, diag = (a0 + a2 + c0 + c2 + 2) >> 2;
+          G = cross;
+          R = red_row ? b1 : diag;
+          B = red_row ? diag : b1;
+        } else {                             // green site
+          const int horiz = (b0 + b2 + 1) >> 1, vert = (a1 + c1 + 1) >> 1;
+          G = b1;
+          R = red_row ? horiz : vert;
+          B = red_row ? vert : horiz;
+        }
+      };
+      // v is a convex combination of 8-bit values: no clamp needed, floor(v + 0.5) is one F2I
+      auto finish_h = [&](float v) -> __half {
+        if (p.quantize_u8) return lut_h[__float2int_rd(__fadd_rn(v, 0.5f))];
+        return __float2half_rn(__fdiv_rn(v, 255.0f));
       };
 #pragma unroll
       for (int k = 0; k < RG; ++k) {
         const int r = grp * RG + k;
         if (r >= SI) break;
         const int iy = iy_lo + r;
-        float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+        __half h0 = __float2half_rn(0.f), h1 = h0, h2 = h0;
         if (xin && iy >= 0 && iy < kNet) {
           const Taps ty = ytap[r];
           const int sy0 = p.rotate180 ? H - 1 - ty.i0 : ty.i0, sy1 = p.rotate180 ? H - 1 - ty.i1 : ty.i1;
@@ -379,11 +393,11 @@ stem_kernel(PreprocessParams p, const float *__restrict__ w, const float *__rest
           seek(sy1);
           demosaic(sy1, R1, G1, B1);
           const float fy = ty.f, ofy = __fsub_rn(1.0f, fy);
-          v0 = finish(__fadd_rn(__fmul_rn((float)R0, ofy), __fmul_rn((float)R1, fy)), p.quantize_u8, lut);
-          v1 = finish(__fadd_rn(__fmul_rn((float)G0, ofy), __fmul_rn((float)G1, fy)), p.quantize_u8, lut);
-          v2 = finish(__fadd_rn(__fmul_rn((float)B0, ofy), __fmul_rn((float)B1, fy)), p.quantize_u8, lut);
+          h0 = finish_h(__fadd_rn(__fmul_rn((float)R0, ofy), __fmul_rn((float)R1, fy)));
+          h1 = finish_h(__fadd_rn(__fmul_rn((float)G0, ofy), __fmul_rn((float)G1, fy)));
+          h2 = finish_h(__fadd_rn(__fmul_rn((float)B0, ofy), __fmul_rn((float)B1, fy)));
         }
-        tile[0][r][c] = __float2half_rn(v0); tile[1][r][c] = __float2half_rn(v1); tile[2][r][c] = __float2half_rn(v2);
+        tile[0][r][c] = h0; tile[1][r][c] = h1; tile[2][r][c] = h2;
       }
     }
   } else {
