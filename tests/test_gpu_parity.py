@@ -474,6 +474,53 @@ def test_submit_collect_pipelined_matches_sync(base_image, weights_seed0):
     eng.close()
 
 
+def test_ragged_batches_and_empty_results(base_image, weights_seed0):
+    """Edge cases of the batch path: n not a multiple of sub_batch (the last replay is partial),
+    n smaller than one sub_batch, and a score threshold nothing passes (zero detections)."""
+    import irmv_detection_b200 as irmv
+    from irmv_detection_b200 import synth
+    _cuda()
+    fr = synth.frames_from_base(base_image, 7, seed=21)
+    eng = irmv.YoloEngine(weights_seed0, (1280, 1024), max_batch=7, sub_batch=3, num_lanes=2)
+    full = eng.detect_batch(fr)
+    assert sum(len(r) for r in full) > 0
+    for n in (1, 2, 4, 5):
+        part = eng.detect_batch(fr[:n])
+        assert part == full[:n], n
+    eng.close()
+    none = irmv.YoloEngine(weights_seed0, (1280, 1024), max_batch=4, sub_batch=4, score_thr=1.5)
+    assert all(len(r) == 0 for r in none.detect_batch(fr[:4]))
+    none.get_src_image_buffer(0)[...] = fr[0]
+    assert none.detect(0) == []
+    none.close()
+
+
+def test_full_size_batch_has_no_cross_frame_leakage(base_image, weights_seed0):
+    """BASELINE.json configs[3] at full size (256 Bayer frames, sub-batch 128, two lanes, fused
+    PnP): a size-independent property -- the batch is 32 repeats of 8 distinct frames, and every
+    repeat must reproduce the detections and poses of its first occurrence bit for bit."""
+    import irmv_detection_b200 as irmv
+    from irmv_detection_b200 import synth
+    from oracle import pnp_ref as P
+    _cuda()
+    rgb = synth.frames_from_base(base_image, 8, seed=33)[..., ::-1]
+    raw8 = synth.bayer_from_rgb(rgb, "RGGB")
+    raw = np.ascontiguousarray(np.tile(raw8, (32, 1, 1)))
+    eng = irmv.YoloEngine(weights_seed0, (1280, 1024), chan_order=irmv.CH_BAYER_RGGB, max_batch=256,
+                          sub_batch=128, num_lanes=2)
+    eng.enable_pnp(P.K_DEFAULT, P.D_DEFAULT, (0.5, 480 / 1024))
+    counts, dets = eng.detect_batch_arrays(raw)
+    counts, dets = counts.copy(), dets.copy()
+    rv, tv, ok = eng.fetch_poses(256)
+    assert counts[:8].sum() > 0
+    for f in range(8, 256):
+        k = int(counts[f % 8])
+        assert counts[f] == k
+        assert np.array_equal(dets[f, :k], dets[f % 8, :k])
+        assert np.array_equal(rv[f, :k], rv[f % 8, :k]) and np.array_equal(tv[f, :k], tv[f % 8, :k])
+    eng.close()
+
+
 def test_large_sub_batch_matches_single_frames(base_image, weights_seed0):
     """Many tiles per persistent CTA (smem ring wraps, TMEM ping-pong): a 32-frame replay must give
     each frame exactly what it gets alone, and frame 0 must still match the FP32 oracle."""
