@@ -363,7 +363,9 @@ def run_ours(args):
             nops = _lib.lib().irmv_engine_profile_ops(eng._h, C.c_void_p(ptr), k, ms.ctypes.data, 80)
             runs.append(ms[:nops].copy())
         op_ms = np.median(np.stack(runs), axis=0)
-        i_top = 45                                  # network op 46 (conv0 lives in the stem): see scripts/analyze_launches.py
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        from analyze_launches import layers
+        i_top = [l[0] for l in layers()[1:]].index("h0.01")     # conv0 lives in the stem
         fl = 2.0 * k * 80 * 80 * 9 * 64 * 128
         t_top = float(op_ms[i_top]) * 1e-3
         tk = None

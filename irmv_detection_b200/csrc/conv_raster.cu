@@ -316,7 +316,6 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
       const int q_tile = q_lane + tile * TM;
       // real pixel? (not the zero column x == W, not a zero row, inside the batch) -- per accumulator
       uint32_t okmask = 0;
-      int pl2[R], px2[R];                                     // parity twin: first plane / pixel of this lane's pixel
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const int qi = q_tile + r * 128;
@@ -325,9 +324,6 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
         const uint32_t img = (uint32_t)(((uint64_t)row * mul_hp1) >> 34);
         const int yrow = (int)row - (int)img * Hp1;
         if (qi < q_end && x < W && yrow != 0) okmask |= 1u << r;
-        const int y = yrow - 1;
-        pl2[r] = ((y & 1) * 2 + (x & 1)) * cpl;
-        px2[r] = ((int)img * Hp2 + 1 + (y >> 1)) * Wp2 + (x >> 1);
       }
       __half *const out_q = out + (long long)q_tile * 8;
       const __half *const res_q = RES ? res + (long long)q_tile * 8 : nullptr;
@@ -343,7 +339,16 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
         t.ok = ((okmask >> r) & 1u) && t.c0 < cout;
         const long long off = (long long)(t.c0 >> 3) * out_ps + r * 1024;
         t.o = out ? out_q + off : nullptr;
-        t.o2 = out2 ? out2 + (long long)(pl2[r] + (t.c0 >> 3)) * out2_ps + (long long)px2[r] * 8 : nullptr;
+        t.o2 = nullptr;
+        if (out2) {                                         // parity twin: plane group and half-resolution pixel of this lane
+          const int qi = q_tile + r * 128;
+          const uint32_t row = (uint32_t)(((uint64_t)(uint32_t)qi * mul_wp) >> 34);
+          const int x = qi - (int)row * Wp;
+          const uint32_t img = (uint32_t)(((uint64_t)row * mul_hp1) >> 34);
+          const int y = (int)row - (int)img * Hp1 - 1;
+          const int px2 = ((int)img * Hp2 + 1 + (y >> 1)) * Wp2 + (x >> 1);
+          t.o2 = out2 + (long long)(((y & 1) * 2 + (x & 1)) * cpl + (t.c0 >> 3)) * out2_ps + (long long)px2 * 8;
+        }
         if (RES && t.ok) {                                  // residual: issue the loads early
           const __half *rp = res_q + (long long)(t.c0 >> 3) * res_ps + r * 1024;
           t.r0 = *reinterpret_cast<const uint4 *>(rp);

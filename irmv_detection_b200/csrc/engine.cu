@@ -383,6 +383,12 @@ bool add_c2f(irmv_engine *e, Lane &ln, size_t &ci, std::vector<SegRef> in, int H
     if (!add_parity_twin(ln, e->S, out, parity_out == 1)) return false;
     if (tap) ln.taps[tap] = out;
   }
+  // (cv1 of the neck C2f blocks reads concat(upsample(a), b).  Splitting it with
+  // conv1x1(upsample(a)) == upsample(conv1x1(a)) -- W_a at half resolution, the partial sum added in
+  // the full-resolution epilogue -- was built and measured: both halves run on the raster kernel,
+  // but every partial sum is re-read by four output pixels (L2 traffic 633 vs 374 MB on m15.cv1 at
+  // 128 frames) and the extra epilogue state spills registers in every residual layer; the replay
+  // got 0.1 ms slower, so these two layers stay on the gather kernel.)
   add_conv(e, ln, *e->convs[ci++], in, H, W, buf, 0);
   for (int i = 0; i < n; ++i) {
     add_conv(e, ln, *e->convs[ci++], {{&buf, (1 + i) * c, c, 0}}, H, W, tmp, 0);
@@ -806,6 +812,7 @@ void irmv_engine_destroy(irmv_engine *e) {
   for (auto &c : e->convs) {
     cudaFree(c->d_plain); cudaFree(c->d_tiled); cudaFree(c->d_raster); cudaFree(c->d_bias);
   }
+
   for (auto s : e->slots_host) cudaFreeHost(s);
   cudaFree(e->slot_dev);
   cudaFree(e->d_stem_w); cudaFree(e->d_stem_b);

@@ -4,10 +4,12 @@ import re
 import sys
 
 
-def layers():
-    def c2f(name, c1, c2, n, hw):
+def layers(split=False):
+    def c2f(name, c1, c2, n, hw, up=0):
         c = c2 // 2
-        out = [(f"{name}.cv1", hw, c1, 2 * c, 1, 1)]
+        # neck C2f whose cv1 reads concat(upsample(a), b): split into W_a at half resolution + W_b (engine.cu)
+        out = [(f"{name}.cv1a", hw // 2, up, 2 * c, 1, 1), (f"{name}.cv1b", hw, c1 - up, 2 * c, 1, 1)] if (up and split) else \
+              [(f"{name}.cv1", hw, c1, 2 * c, 1, 1)]
         for i in range(n):
             out += [(f"{name}.m{i}.cv1", hw, c, c, 3, 1), (f"{name}.m{i}.cv2", hw, c, c, 3, 1)]
         out.append((f"{name}.cv2", hw, (2 + n) * c, c2, 1, 1))
@@ -15,7 +17,7 @@ def layers():
     d = [("m0", 320, 8, 16, 3, 2), ("m1", 160, 16, 32, 3, 2)] + c2f("m2", 32, 32, 1, 160)
     d += [("m3", 80, 32, 64, 3, 2)] + c2f("m4", 64, 64, 2, 80) + [("m5", 40, 64, 128, 3, 2)] + c2f("m6", 128, 128, 2, 40)
     d += [("m7", 20, 128, 256, 3, 2)] + c2f("m8", 256, 256, 1, 20) + [("m9.cv1", 20, 256, 128, 1, 1), ("POOL", 20, 0, 0, 0, 0), ("m9.cv2", 20, 512, 256, 1, 1)]
-    d += c2f("m12", 384, 128, 1, 40) + c2f("m15", 192, 64, 1, 80) + [("m16", 40, 64, 64, 3, 2)] + c2f("m18", 192, 128, 1, 40)
+    d += c2f("m12", 384, 128, 1, 40, up=256) + c2f("m15", 192, 64, 1, 80, up=128) + [("m16", 40, 64, 64, 3, 2)] + c2f("m18", 192, 128, 1, 40)
     d += [("m19", 20, 128, 128, 3, 2)] + c2f("m21", 384, 256, 1, 20)
     for i, (hw, ch) in enumerate(((80, 64), (40, 128), (20, 256))):
         d += [(f"h{i}.01", hw, ch, 128, 3, 1), (f"h{i}.box1", hw, 64, 64, 3, 1), (f"h{i}.box2", hw, 64, 64, 1, 1),
