@@ -124,7 +124,7 @@ int irmv_engine_fetch_poses(irmv_engine *e, int nframes, double *rvecs, double *
  * from its TripleBuffer (camera thread fills the next slot while detect() runs on the previous one,
  * reference README.md:60-63, src/irm_detector.cpp:68-72).  submit queues H2D copy (dedicated copy
  * stream) + pipeline + D2H of the results and returns; collect waits for that batch and parses it
- * like detect_batch (rvecs/tvecs/ok may be null).  At most two batches in flight; collect in order. */
+ * like detect_batch (rvecs/tvecs/ok may be null).  At most three batches in flight; collect in order. */
 int irmv_engine_submit_batch(irmv_engine *e, const uint8_t *frames_host, int nframes, int *ticket);
 int irmv_engine_collect(irmv_engine *e, int ticket, irmv_bbox *out, int *counts, double *rvecs, double *tvecs,
                         uint8_t *ok);

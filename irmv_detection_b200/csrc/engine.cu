@@ -234,6 +234,8 @@ __global__ void quads_from_dets_kernel(const int32_t *num, const float *boxes, i
 
 using namespace irmv;
 
+constexpr int kSets = 3;    // batches in flight in the pipelined hand-off
+
 struct irmv_engine {
   irmv_engine_config cfg{};
   int nc = IRMV_NUM_CLASSES;
@@ -248,8 +250,8 @@ struct irmv_engine {
   uint8_t *slot_dev = nullptr;            // device copy of the frame being detected
   uint8_t *batch_dev = nullptr;           // staging for host-resident batches
   uint8_t *res_host = nullptr;            // pinned results: max_batch frames (== sets[0].res_host)
-  // Pipelined hand-off (irmv_engine_submit_batch / _collect): two result sets so that the H2D copy
-  // of batch k+1 (copy stream) runs under the kernels of batch k -- the B200 form of the
+  // Pipelined hand-off (irmv_engine_submit_batch / _collect): three result sets so that the H2D copy
+  // of batch k+1 (copy stream) runs under the kernels of batch k while the host still parses batch k-1 -- the B200 form of the
   // reference's camera/detector overlap through its TripleBuffer (reference README.md:60-63).
   struct Set {
     uint8_t *res_host = nullptr;          // pinned results of this set
@@ -257,7 +259,7 @@ struct irmv_engine {
     cudaEvent_t done = nullptr;           // all lanes finished (results in res_host)
     std::vector<cudaEvent_t> h2d;         // per chunk: frames arrived on the device
     int n = 0;
-  } sets[2];
+  } sets[kSets];
   cudaStream_t copy_stream = nullptr;
   long long next_ticket = 0;
   size_t res_bytes = 0;
@@ -818,8 +820,10 @@ void irmv_engine_destroy(irmv_engine *e) {
   cudaFree(e->d_stem_w); cudaFree(e->d_stem_b);
   if (e->batch_dev) cudaFree(e->batch_dev);
   cudaFreeHost(e->res_host);
-  if (e->sets[1].res_host) cudaFreeHost(e->sets[1].res_host);
-  if (e->sets[1].batch_dev) cudaFree(e->sets[1].batch_dev);
+  for (int i = 1; i < kSets; ++i) {
+    if (e->sets[i].res_host) cudaFreeHost(e->sets[i].res_host);
+    if (e->sets[i].batch_dev) cudaFree(e->sets[i].batch_dev);
+  }
   for (auto &st : e->sets) {
     if (st.done) cudaEventDestroy(st.done);
     for (auto ev : st.h2d) cudaEventDestroy(ev);
@@ -900,12 +904,13 @@ int irmv_engine_detect_batch(irmv_engine *e, const uint8_t *frames, int on_devic
 
 // Pipelined form of detect_batch for host-resident frames: submit returns as soon as the work is
 // queued (H2D on the copy stream, kernels on the lanes, D2H of the results); collect waits for
-// that batch and parses it.  Two batches may be in flight: submit(k+1) before collect(k) puts the
-// copy of batch k+1 under the kernels of batch k.  Tickets must be collected in order.
+// that batch and parses it.  Up to three batches may be in flight: submit(k+1) before collect(k) puts
+// the copy of batch k+1 under the kernels of batch k, submit(k+2) keeps the copy engine busy while the
+// host parses.  Tickets must be collected in order.
 int irmv_engine_submit_batch(irmv_engine *e, const uint8_t *frames_host, int nframes, int *ticket) {
   if (!e || !frames_host || !ticket || nframes < 1 || nframes > e->cfg.max_batch) { set_error("bad argument"); return 1; }
   IRMV_CUDA(cudaSetDevice(e->cfg.device));
-  const int set = (int)(e->next_ticket & 1);
+  const int set = (int)(e->next_ticket % kSets);
   irmv_engine::Set &rs = e->sets[set];
   if (!rs.res_host) {
     IRMV_CUDA(cudaHostAlloc((void **)&rs.res_host, e->res_bytes, cudaHostAllocDefault));
@@ -927,7 +932,7 @@ int irmv_engine_collect(irmv_engine *e, int ticket, irmv_bbox *out, int *counts,
                         uint8_t *ok) {
   if (!e || !out) { set_error("bad argument"); return 1; }
   IRMV_CUDA(cudaSetDevice(e->cfg.device));
-  const int set = ticket & 1;
+  const int set = ticket % kSets;
   irmv_engine::Set &rs = e->sets[set];
   if (rs.n < 1) { set_error("nothing was submitted under this ticket"); return 2; }
   IRMV_CUDA(cudaEventSynchronize(rs.done));

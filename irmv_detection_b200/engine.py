@@ -83,7 +83,7 @@ class YoloEngine:
         self._slot = 0
         self._out = (L.Bbox * (max_batch * max_det))()
         self._counts = (C.c_int * max_batch)()
-        self._ticket_n = [0, 0]
+        self._ticket_n = [0, 0, 0]
 
     # -- reference surface ---------------------------------------------------------------
     def get_src_image_buffer(self, slot: int = 0) -> np.ndarray:
@@ -134,7 +134,7 @@ class YoloEngine:
 
     # -- pipelined hand-off (copy of batch k+1 under the kernels of batch k) ---------------
     def submit_batch(self, frames: np.ndarray) -> int:
-        """Queue H2D + pipeline + D2H for host frames and return a ticket; at most two batches in
+        """Queue H2D + pipeline + D2H for host frames and return a ticket; at most three batches in
         flight, collect in order.  `frames` must stay alive and unchanged until collected (pinned
         memory makes the copy asynchronous)."""
         if not frames.flags.c_contiguous or frames.dtype != np.uint8:
@@ -144,14 +144,14 @@ class YoloEngine:
             raise ValueError("frame size does not match the engine's src_image_size")
         t = C.c_int(0)
         L.check(self._lib.irmv_engine_submit_batch(self._h, frames.ctypes.data, n, C.byref(t)), "irmv_engine_submit_batch")
-        self._ticket_n[t.value & 1] = n
+        self._ticket_n[t.value % 3] = n
         return t.value
 
     def collect_arrays(self, ticket: int, poses: bool = False):
         """Wait for a submitted batch: (counts i32[n], dets structured [n, max_det]) and, with
         poses=True, (rvec f64[n,max_det,3], tvec, ok).  The arrays are views that the next collect
         of the same parity overwrites."""
-        n = self._ticket_n[ticket & 1]
+        n = self._ticket_n[ticket % 3]
         rv = tv = ok = None
         if poses:
             rv = np.empty((n, self.max_det, 3)); tv = np.empty((n, self.max_det, 3))

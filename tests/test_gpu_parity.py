@@ -435,7 +435,7 @@ def test_bayer_pipeline_batch_invariance(base_image, weights_seed0):
 
 
 def test_submit_collect_pipelined_matches_sync(base_image, weights_seed0):
-    """Pipelined hand-off (two batches in flight, H2D on the copy stream): each batch gets exactly
+    """Pipelined hand-off (up to three batches in flight, H2D on the copy stream): each batch gets exactly
     the detections and poses of the synchronous call, whatever is queued behind or ahead of it."""
     import torch
     import irmv_detection_b200 as irmv
@@ -459,10 +459,13 @@ def test_submit_collect_pipelined_matches_sync(base_image, weights_seed0):
         want.append((c.copy(), d.copy(), rv, tv, ok))
     t0 = eng.submit_batch(bufs[0])
     t1 = eng.submit_batch(bufs[1])
+    t2 = eng.submit_batch(bufs[2])                      # three batches in flight
     got = [tuple(np.copy(x) for x in eng.collect_arrays(t0, poses=True))]
-    t2 = eng.submit_batch(bufs[2])
+    t3 = eng.submit_batch(bufs[0])                      # reuses the first result set
     got.append(tuple(np.copy(x) for x in eng.collect_arrays(t1, poses=True)))
     got.append(tuple(np.copy(x) for x in eng.collect_arrays(t2, poses=True)))
+    got.append(tuple(np.copy(x) for x in eng.collect_arrays(t3, poses=True)))
+    want.append(want[0])
     assert sum(int(w[0].sum()) for w in want) > 0
     for w, g in zip(want, got):
         assert np.array_equal(w[0], g[0])
