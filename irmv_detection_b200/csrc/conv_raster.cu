@@ -135,7 +135,6 @@ struct RArgs {
   int NCH, NP, taps, Wp, Hp1;             // cin/8, planes per stage, 1 or 9, OW+1, OH+1
   int q_begin, q_end, num_tiles, stages, tmem_cols, ctas_per_sm;
   int b_stream, b_stages;                 // weights streamed chunk by chunk through b_stages ring slots
-  int dbg;                                // debug switches (IRMV_RASTER_DBG)
   int nchunks, chunk_pairs;               // K chunks (a tap, or 64 channels of a wide 1x1) and K16 steps per chunk
   long long npix;                         // raster pixels of the tensors for this batch
   uint32_t idesc, mul_wp, mul_hp1;        // magic dividers (q / Wp, row / (H+1)), >> 34
@@ -147,7 +146,7 @@ struct RArgs {
 // hb: bias / 2 (ACT: folded into the SiLU argument) or the bias itself.
 template <bool ACT, bool RES>
 __device__ __forceinline__ void epi_chunk(const uint32_t (&v32)[16], const float *hb, __half *o, long long out_ps,
-                                          __half *o2, long long out2_ps, const uint4 &r0, const uint4 &r1, int dbg) {
+                                          __half *o2, long long out2_ps, const uint4 &r0, const uint4 &r1) {
   float b[16];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -155,26 +154,7 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v32)[16], const float
     b[4 * j] = t.x; b[4 * j + 1] = t.y; b[4 * j + 2] = t.z; b[4 * j + 3] = t.w;
   }
   float v[16];
-  if (ACT && (dbg & 4)) {
-    // packed variant: tanh.approx.f16x2, one MUFU per two elements
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float h0 = fmaf(__uint_as_float(v32[2 * j]), 0.5f, b[2 * j]);
-      const float h1 = fmaf(__uint_as_float(v32[2 * j + 1]), 0.5f, b[2 * j + 1]);
-      const __half2 hh = __floats2half2_rn(h0, h1);
-      uint32_t t2;
-      asm("tanh.approx.f16x2 %0, %1;" : "=r"(t2) : "r"(*reinterpret_cast<const uint32_t *>(&hh)));
-      const float2 tf = __half22float2(*reinterpret_cast<const __half2 *>(&t2));
-      v[2 * j] = fmaf(h0, tf.x, h0);
-      v[2 * j + 1] = fmaf(h1, tf.y, h1);
-    }
-  } else if (ACT && (dbg & 1)) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float h = fmaf(__uint_as_float(v32[j]), 0.5f, b[j]);
-      v[j] = fmaf(h, h, h);
-    }
-  } else if (ACT) {
+  if (ACT) {
     // SiLU(x) = x * sigmoid(x) = h + h * tanh(h), h = x / 2: one MUFU per element
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
@@ -200,7 +180,6 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v32)[16], const float
   __half2 hv[8];
 #pragma unroll
   for (int t = 0; t < 8; ++t) hv[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
-  if (dbg & 2) return;
   if (o) {
     *reinterpret_cast<uint4 *>(o) = *reinterpret_cast<uint4 *>(&hv[0]);
     *reinterpret_cast<uint4 *>(o + out_ps) = *reinterpret_cast<uint4 *>(&hv[4]);
@@ -298,7 +277,6 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
     const __half *const res = p.res;
     const long long out_ps = p.out_pstride, res_ps = p.res_pstride;
     const int cout = p.cout;
-    const int dbg = a.dbg;
     const int Wp = a.Wp, Hp1 = a.Hp1, W = p.OW, q_end = a.q_end, TM = a.TM;
     __half *const out2 = p.out2;
     const long long out2_ps = p.out2_pstride;
@@ -365,12 +343,12 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
         tc_ld_wait();                                       // va ready
         const bool more_b = w + NSUB < items;
         if (more_b) tc_ld16(setup(w + NSUB, ib), vb);
-        if (ia.ok) epi_chunk<ACT, RES>(va, s_hb + ia.c0, ia.o, out_ps, ia.o2, out2_ps, ia.r0, ia.r1, dbg);
+        if (ia.ok) epi_chunk<ACT, RES>(va, s_hb + ia.c0, ia.o, out_ps, ia.o2, out2_ps, ia.r0, ia.r1);
         if (!more_b) break;
         tc_ld_wait();                                       // vb ready
         const bool more_a = w + 2 * NSUB < items;
         if (more_a) tc_ld16(setup(w + 2 * NSUB, ia), va);
-        if (ib.ok) epi_chunk<ACT, RES>(vb, s_hb + ib.c0, ib.o, out_ps, ib.o2, out2_ps, ib.r0, ib.r1, dbg);
+        if (ib.ok) epi_chunk<ACT, RES>(vb, s_hb + ib.c0, ib.o, out_ps, ib.o2, out2_ps, ib.r0, ib.r1);
         if (!more_a) break;
         w += 2 * NSUB;
       }
@@ -513,10 +491,6 @@ bool plan(const ConvParams &p, int num_sms, RArgs &a) {
   if (p.OW + 2 + 8 > kGuardFront || p.cout % 16 != 0) return false;
   if (p.out2 && ((p.OH & 1) || (p.OW & 1))) return false;
   a.p = p;
-  {
-    static const int dbg = getenv("IRMV_RASTER_DBG") ? atoi(getenv("IRMV_RASTER_DBG")) : 0;
-    a.dbg = dbg;
-  }
   a.NCH = p.cin / 8;
   a.NP = s2 ? 4 * a.NCH : a.NCH;                     // planes per activation stage
   a.taps = p.k * p.k;
