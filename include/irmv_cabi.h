@@ -77,7 +77,9 @@ typedef struct irmv_engine_config {
   float iou_thr;            /* 0.45 */
   int32_t use_graph;        /* 1 = replay captured CUDA graphs (reference behaviour) */
   int32_t reserved[8];      /* reserved[0] != 0: run preprocess and conv0 as separate kernels (the network
-                             * input tensor is then materialised and readable as tap "input") */
+                             * input tensor is then materialised and readable as tap "input");
+                             * reserved[1] != 0: do not fuse 1x1 convs into their producers (every module
+                             * output is then materialised and readable through irmv_engine_read_tensor) */
 } irmv_engine_config;
 
 typedef struct irmv_engine irmv_engine;

@@ -111,6 +111,14 @@ struct ConvParams {
   // raster of the (H/2) x (W/2) pixels of that parity.  A 3x3 / stride-2 / pad-1 tap (ky, kx) then
   // reads parity ((ky != 1), (kx != 1)) at the constant raster offset (ky == 0 ? -Wp : 0) +
   // (kx == 0 ? -1 : 0) of the OUTPUT raster, so stride-2 layers run on the halo-tile kernel too.
+  // Fused 1x1 consumer ("tail", raster kernel only): the epilogue's FP16 output tile stays in
+  // shared memory as the A operand of a second, pointwise GEMM (K = cout of this conv), so the
+  // intermediate tensor never goes to HBM when nobody else reads it (out == null).
+  const __half *tail_w;    // [cout/8][tail_npad][8] = the 1x1 conv's w_raster image; null = no tail
+  const float *tail_bias;  // [tail_npad]
+  int tail_npad, tail_cout, tail_act;
+  __half *tail_out;        // pixel 0 of the first output plane of the tail
+  long long tail_out_pstride;
   int in_parity;           // 1: seg[0].ptr / pstride describe the parity twin of the input
   __half *out2;            // parity twin of the output (written in addition to `out`); may be null
   long long out2_pstride;

@@ -47,6 +47,8 @@ struct Bars {
   uint64_t bw_empty[MAX_BSTAGES];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
+  uint64_t mid_full, mid_empty;           // fused tail: intermediate tile written / consumed
+  uint64_t tail_full[2], tail_empty[2];   // fused tail: second accumulator set
   uint64_t bfull;
   uint32_t tmem_base;
   uint32_t pad;
@@ -140,13 +142,27 @@ struct RArgs {
   uint32_t idesc, mul_wp, mul_hp1;        // magic dividers (q / Wp, row / (H+1)), >> 34
   uint32_t a_stage_bytes, b_bytes, b_tap_bytes, off_b, off_bias, off_bars;
   uint32_t tap_a[9];                      // per chunk: A start offset inside a stage, 16-byte units
+  // fused 1x1 tail (ConvParams::tail_w): intermediate tile [cout/8][TM][8], tail weights, tail bias
+  uint32_t off_mid, off_bt, off_tbias, bt_bytes, tail_idesc;
+  int tmem_tail0;                         // first TMEM column of the tail accumulators
 };
 
 // One 16-column chunk of one accumulator: bias, SiLU, residual, FP16, two 16-byte plane stores.
 // hb: bias / 2 (ACT: folded into the SiLU argument) or the bias itself.
-template <bool ACT, bool RES>
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4 &v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// padding pixels of the intermediate tile of a fused tail: finite values (their output rows are never stored)
+__device__ __forceinline__ void st_shared_zero2(uint32_t addr, uint32_t plane_bytes) {
+  const uint4 z = make_uint4(0, 0, 0, 0);
+  st_shared_v4(addr, z);
+  st_shared_v4(addr + plane_bytes, z);
+}
+
+template <bool ACT, bool RES, bool MID = false>
 __device__ __forceinline__ void epi_chunk(const uint32_t (&v32)[16], const float *hb, __half *o, long long out_ps,
-                                          __half *o2, long long out2_ps, const uint4 &r0, const uint4 &r1) {
+                                          __half *o2, long long out2_ps, const uint4 &r0, const uint4 &r1,
+                                          uint32_t mid = 0, uint32_t mid_plane_bytes = 0) {
   float b[16];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -188,9 +204,14 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v32)[16], const float
     *reinterpret_cast<uint4 *>(o2) = *reinterpret_cast<uint4 *>(&hv[0]);
     *reinterpret_cast<uint4 *>(o2 + out2_ps) = *reinterpret_cast<uint4 *>(&hv[4]);
   }
+  if (MID) {                                                // A operand of the fused 1x1 tail: [plane][pixel][8 channels]
+    st_shared_v4(mid, *reinterpret_cast<uint4 *>(&hv[0]));
+    st_shared_v4(mid + mid_plane_bytes, *reinterpret_cast<uint4 *>(&hv[4]));
+  }
 }
 
-template <int R, int NEPI, bool ACT, bool RES>
+// TAIL: 0 = none, 1 = fused 1x1 consumer without activation, 2 = with SiLU
+template <int R, int NEPI, bool ACT, bool RES, int TAIL>
 __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raster_kernel(const __grid_constant__ RArgs a) {
   constexpr int NTHREADS = (NEPI + 2) * 32;
   constexpr int TMA_WARP = NEPI, MMA_WARP = NEPI + 1;
@@ -199,6 +220,9 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
   uint8_t *sA = smem;
   uint8_t *sB = smem + a.off_b;
   float *s_hb = reinterpret_cast<float *>(smem + a.off_bias);
+  uint8_t *sMid = smem + a.off_mid;
+  uint8_t *sBt = smem + a.off_bt;
+  float *s_tb = reinterpret_cast<float *>(smem + a.off_tbias);
   Bars *bars = reinterpret_cast<Bars *>(smem + a.off_bars);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int npad = p.npad;
@@ -217,6 +241,8 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // act: bias / 2 (folded into the SiLU argument), otherwise the bias itself
   for (int i = tid; i < npad; i += NTHREADS) s_hb[i] = ACT ? 0.5f * p.bias[i] : p.bias[i];
+  if (TAIL)
+    for (int i = tid; i < p.tail_npad; i += NTHREADS) s_tb[i] = TAIL == 2 ? 0.5f * p.tail_bias[i] : p.tail_bias[i];
   if (tid == 0) {
     for (int s = 0; s < a.stages; ++s) {
       mbar_init(&bars->full[s], 1);
@@ -231,6 +257,12 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
       mbar_init(&bars->tmem_empty[i], NEPI);
     }
     mbar_init(&bars->bfull, 1);
+    mbar_init(&bars->mid_full, NEPI);
+    mbar_init(&bars->mid_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->tail_full[i], 1);
+      mbar_init(&bars->tail_empty[i], NEPI);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == MMA_WARP) {
@@ -246,11 +278,12 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
   // Resident weights are constants: start loading them before waiting for the producer kernel.
   if (warp == TMA_WARP && !a.b_stream && elect_one()) {
     const uint32_t bar = smem_u32(&bars->bfull), sB_u = smem_u32(sB);
-    mbar_expect_tx(bar, a.b_bytes);
+    mbar_expect_tx(bar, a.b_bytes + (TAIL ? a.bt_bytes : 0u));
     for (uint32_t off = 0; off < a.b_bytes; off += 65536u) {
       const uint32_t n = a.b_bytes - off < 65536u ? a.b_bytes - off : 65536u;
       bulk_g2s(sB_u + off, reinterpret_cast<const uint8_t *>(p.w_raster) + off, n, bar);
     }
+    if (TAIL) bulk_g2s(smem_u32(sBt), p.tail_w, a.bt_bytes, bar);
   }
   // Everything above overlapped the tail of the previous kernel (PDL); activations, residuals
   // and output buffers may only be touched once it has completed.
@@ -286,14 +319,9 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
     const int num_tiles = a.num_tiles;
     long long *const trace = p.trace;
     const int trace_cap = p.trace_cap;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int buf = it & 1;
-      const uint32_t aph = (uint32_t)(it >> 1) & 1u;
-      const bool tr = trace && blockIdx.x == 0 && tid == 0 && it < trace_cap;
-      const int q_tile = q_lane + tile * TM;
-      // real pixel? (not the zero column x == W, not a zero row, inside the batch) -- per accumulator
-      uint32_t okmask = 0;
+    // real pixel? (not the zero column x == W, not a zero row, inside the batch) -- per accumulator
+    auto valid_mask = [&](int q_tile) -> uint32_t {
+      uint32_t m = 0;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const int qi = q_tile + r * 128;
@@ -301,16 +329,57 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
         const int x = qi - (int)row * Wp;
         const uint32_t img = (uint32_t)(((uint64_t)row * mul_hp1) >> 34);
         const int yrow = (int)row - (int)img * Hp1;
-        if (qi < q_end && x < W && yrow != 0) okmask |= 1u << r;
+        if (qi < q_end && x < W && yrow != 0) m |= 1u << r;
       }
+      return m;
+    };
+    // Fused tail, second epilogue: accumulators of tile number `jt` (TMEM set jt & 1) -> bias,
+    // activation, FP16 -> the tail's output planes.
+    const int tnp = TAIL ? p.tail_npad : 16;
+    const int tshift = 31 - __clz(tnp >> 4), tmask = (tnp >> 4) - 1;
+    __half *const tout = p.tail_out;
+    const long long tout_ps = p.tail_out_pstride;
+    const int tcout = p.tail_cout;
+    auto tail_epilogue = [&](int jt, int tile_j) {
+      const int tb = jt & 1;
+      const int q_tile = q_lane + tile_j * TM;
+      const uint32_t okm = valid_mask(q_tile);
+      mbar_wait_warp(&bars->tail_full[tb], (uint32_t)(jt >> 1) & 1u, lane);
+      tc_fence_after();
+      const uint32_t tcol = lane_base + (uint32_t)(a.tmem_tail0 + tb * R * tnp);
+      const int items2 = R << tshift;
+      const uint4 z = make_uint4(0, 0, 0, 0);
+      for (int w = sub; w < items2; w += NSUB) {
+        const int r = w >> tshift, c0 = (w & tmask) << 4;
+        uint32_t v[16];
+        tc_ld16(tcol + (uint32_t)(r * tnp + c0), v);
+        tc_ld_wait();
+        if (((okm >> r) & 1u) && c0 < tcout)
+          epi_chunk<TAIL == 2, false>(v, s_tb + c0, tout + (long long)(c0 >> 3) * tout_ps + (long long)(q_tile + r * 128) * 8,
+                                      tout_ps, nullptr, 0, z, z);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->tail_empty[tb]);
+    };
+    int it = 0, prev_tile = -1;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+      const bool tr = trace && blockIdx.x == 0 && tid == 0 && it < trace_cap;
+      const int q_tile = q_lane + tile * TM;
+      const uint32_t okmask = valid_mask(q_tile);
       __half *const out_q = out + (long long)q_tile * 8;
       const __half *const res_q = RES ? res + (long long)q_tile * 8 : nullptr;
       mbar_wait_warp(&bars->tmem_full[buf], aph, lane);
+      // fused tail: the intermediate tile is free once the tail MMAs of the previous tile have read it
+      if (TAIL) mbar_wait_warp(&bars->mid_empty, (uint32_t)(it & 1) ^ 1u, lane);
       tc_fence_after();
       if (tr) trace[it * 8 + 6] = clock64();
       const uint32_t tcol0 = lane_base + (uint32_t)(buf * R * npad);
+      const uint32_t mid_lane = smem_u32(sMid) + (uint32_t)(ew * 32 + lane) * 16u;   // + (plane * TM + r * 128) * 16
       // item w -> accumulator r = w / chunks, chunk c = w % chunks; this warp takes w = sub, sub+NSUB, ...
-      struct Item { int c0; bool ok; __half *o, *o2; uint4 r0, r1; };
+      struct Item { int c0; bool ok; __half *o, *o2; uint32_t mid; uint4 r0, r1; };
       auto setup = [&](int w, Item &t) -> uint32_t {
         const int r = w >> chunk_shift;
         t.c0 = (w & chunk_mask) << 4;
@@ -318,6 +387,7 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
         const long long off = (long long)(t.c0 >> 3) * out_ps + r * 1024;
         t.o = out ? out_q + off : nullptr;
         t.o2 = nullptr;
+        t.mid = TAIL ? mid_lane + (uint32_t)((t.c0 >> 3) * TM + r * 128) * 16u : 0u;
         if (out2) {                                         // parity twin: plane group and half-resolution pixel of this lane
           const int qi = q_tile + r * 128;
           const uint32_t row = (uint32_t)(((uint64_t)(uint32_t)qi * mul_wp) >> 34);
@@ -343,21 +413,30 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
         tc_ld_wait();                                       // va ready
         const bool more_b = w + NSUB < items;
         if (more_b) tc_ld16(setup(w + NSUB, ib), vb);
-        if (ia.ok) epi_chunk<ACT, RES>(va, s_hb + ia.c0, ia.o, out_ps, ia.o2, out2_ps, ia.r0, ia.r1);
+        if (ia.ok) epi_chunk<ACT, RES, TAIL != 0>(va, s_hb + ia.c0, ia.o, out_ps, ia.o2, out2_ps, ia.r0, ia.r1, ia.mid, (uint32_t)TM * 16u);
+        else if (TAIL) st_shared_zero2(ia.mid, (uint32_t)TM * 16u);
         if (!more_b) break;
         tc_ld_wait();                                       // vb ready
         const bool more_a = w + 2 * NSUB < items;
         if (more_a) tc_ld16(setup(w + 2 * NSUB, ia), va);
-        if (ib.ok) epi_chunk<ACT, RES>(vb, s_hb + ib.c0, ib.o, out_ps, ib.o2, out2_ps, ib.r0, ib.r1);
+        if (ib.ok) epi_chunk<ACT, RES, TAIL != 0>(vb, s_hb + ib.c0, ib.o, out_ps, ib.o2, out2_ps, ib.r0, ib.r1, ib.mid, (uint32_t)TM * 16u);
+        else if (TAIL) st_shared_zero2(ib.mid, (uint32_t)TM * 16u);
         if (!more_a) break;
         w += 2 * NSUB;
       }
       // all of this warp's TMEM reads of the buffer are done: hand it back to the MMA warp
+      if (TAIL) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // st.shared -> tcgen05.mma operand reads
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->tmem_empty[buf]);
+      if (lane == 0) {
+        mbar_arrive(&bars->tmem_empty[buf]);
+        if (TAIL) mbar_arrive(&bars->mid_full);
+      }
       if (tr) trace[it * 8 + 7] = clock64();
+      if (TAIL && it > 0) tail_epilogue(it - 1, prev_tile);
+      prev_tile = tile;
     }
+    if (TAIL && it > 0) tail_epilogue(it - 1, prev_tile);
   } else if (warp == TMA_WARP) {
     // ===================================================================== TMA producer
     if (elect_one()) {
@@ -408,6 +487,30 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
     const uint32_t b_pair_u = 2u * (uint32_t)npad;
     const uint32_t b_tap_u = a.b_tap_bytes >> 4;
     const int pairs = a.chunk_pairs, nchunks = a.nchunks;
+    // Fused tail: MMAs of the pointwise consumer for tile number j, issued one tile behind the main
+    // MMAs (tile j+1's main MMAs keep the pipe busy while the epilogue produces tile j's operand).
+    const int tnp = TAIL ? p.tail_npad : 16;
+    const uint32_t mid_lo0 = desc_lo(smem_u32(sMid), (uint32_t)a.TM * 16u);
+    const uint32_t bt_lo0 = desc_lo(smem_u32(sBt), (uint32_t)tnp * 16u);
+    auto issue_tail = [&](int j) {
+      const int tb = j & 1;
+      mbar_wait_warp(&bars->mid_full, (uint32_t)j & 1u, lane);
+      mbar_wait_warp(&bars->tail_empty[tb], ((uint32_t)(j >> 1) & 1u) ^ 1u, lane);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t td0 = tmem_base + (uint32_t)(a.tmem_tail0 + tb * R * tnp);
+        const int ksteps = npad >> 4;                       // K of the tail = channels of the intermediate tile
+        uint32_t al = mid_lo0, bl = bt_lo0;
+        for (int kk = 0; kk < ksteps; ++kk, al += 2u * (uint32_t)a.TM, bl += 2u * (uint32_t)tnp) {
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+            tc_mma_f16(td0 + (uint32_t)(r * tnp), al + (uint32_t)(r * 128), kDescHi, bl, kDescHi, a.tail_idesc, kk != 0 ? 1u : 0u);
+        }
+        tc_commit(&bars->tail_full[tb]);
+        tc_commit(&bars->mid_empty);
+      }
+      __syncwarp();
+    };
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       const uint32_t aph = (uint32_t)(it >> 1) & 1u;
@@ -462,7 +565,9 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
       }
       if (tr) p.trace[it * 8 + 5] = clock64();
       if (++s == a.stages) { s = 0; ph ^= 1u; }
+      if (TAIL && it > 0) issue_tail(it - 1);
     }
+    if (TAIL && it > 0) issue_tail(it - 1);
   }
 
   tc_fence_before();
@@ -507,7 +612,13 @@ bool plan(const ConvParams &p, int num_sms, RArgs &a) {
   a.nchunks = a.taps;
   a.chunk_pairs = a.NCH >> 1;
   a.b_tap_bytes = (uint32_t)((size_t)p.cin * p.npad * 2);
-  const size_t misc = (size_t)p.npad * 4 + sizeof(Bars) + 1024 + 256;
+  const bool tail = p.tail_w != nullptr;
+  if (tail && (p.res || p.tail_npad % 16 || p.tail_npad > 256 || p.tail_cout % 16 || p.cout != p.npad || !p.tail_out)) return false;
+  const int tnp = tail ? p.tail_npad : 0;
+  a.bt_bytes = tail ? (uint32_t)((size_t)p.npad * tnp * 2) : 0u;
+  // fused tail: the FP16 intermediate tile [cout/8][TM][8] stays in shared memory
+  auto tail_bytes = [&](int R) { return tail ? (size_t)a.bt_bytes + (size_t)p.npad * 128 * R * 2 + 256 : (size_t)0; };
+  const size_t misc = (size_t)p.npad * 4 + (size_t)tnp * 4 + sizeof(Bars) + 1024 + 256;
   const int halo = p.k == 3 ? (s2 ? a.Wp + 1 : 2 * a.Wp + 2) : 0;
   // Bulk copies run fastest when source, destination and size are multiples of 128 bytes (8
   // pixels): the copied range starts `delta` pixels early so that it begins on an 8-pixel boundary
@@ -520,13 +631,14 @@ bool plan(const ConvParams &p, int num_sms, RArgs &a) {
   int best_R = 0;
   a.b_stream = 0;
   for (int R = 4; R >= 1; R >>= 1) {
-    if (2 * R * p.npad > 512) continue;
-    if (a.b_bytes + 2 * stage_bytes(R) + misc > (size_t)SMEM_BUDGET) continue;
+    if (2 * R * (p.npad + tnp) > 512) continue;
+    if (a.b_bytes + tail_bytes(R) + 2 * stage_bytes(R) + misc > (size_t)SMEM_BUDGET) continue;
     long long tiles = (Mr + 128 * R - 1) / (128 * R);
     if (R > 1 && tiles < 2LL * num_sms) continue;    // keep every SM busy at small batch
     best_R = R;
     break;
   }
+  if (!best_R && tail) return false;                 // a fused tail needs resident weights
   if (!best_R && !getenv("IRMV_NO_BSTREAM")) {
     // weights do not fit next to two activation stages: stream them chunk by chunk.  Larger tiles
     // amortise the weight traffic (all of the weights once per tile), so prefer the largest R that
@@ -554,9 +666,10 @@ bool plan(const ConvParams &p, int num_sms, RArgs &a) {
   a.npix_need = plane_pixels(a.R);
   a.PP = a.npix_need;
   a.a_stage_bytes = (uint32_t)stage_bytes(a.R);
-  int cols = 2 * a.R * p.npad, alloc = 32;
+  int cols = 2 * a.R * (p.npad + tnp), alloc = 32;
   while (alloc < cols) alloc <<= 1;
   a.tmem_cols = alloc;
+  a.tmem_tail0 = 2 * a.R * p.npad;
   a.num_tiles = (int)((Mr + a.TM - 1) / a.TM);
   size_t b_smem = a.b_bytes;
   if (a.b_stream) {
@@ -572,10 +685,11 @@ bool plan(const ConvParams &p, int num_sms, RArgs &a) {
     // The per-tile chain load -> MMA -> epilogue has latency bubbles, so when two CTAs fit on an SM
     // (shared memory and TMEM halves) run two: their phases interleave.
     const size_t half_budget = 112 * 1024;
-    const bool two = !getenv("IRMV_ONE_CTA") && alloc <= 256 && a.b_bytes + 2 * (size_t)a.a_stage_bytes + misc <= half_budget;
+    const size_t fixed = a.b_bytes + tail_bytes(a.R) + misc;
+    const bool two = !getenv("IRMV_ONE_CTA") && alloc <= 256 && fixed + 2 * (size_t)a.a_stage_bytes <= half_budget;
     a.ctas_per_sm = two ? 2 : 1;
     const size_t budget = two ? half_budget : (size_t)SMEM_BUDGET;
-    a.stages = (int)((budget - a.b_bytes - misc) / a.a_stage_bytes);
+    a.stages = (int)((budget - fixed) / a.a_stage_bytes);
     if (a.stages > MAX_STAGES) a.stages = MAX_STAGES;
     a.b_stages = 0;
   }
@@ -583,8 +697,12 @@ bool plan(const ConvParams &p, int num_sms, RArgs &a) {
   a.mul_wp = (uint32_t)(((1ull << 34) + (uint64_t)a.Wp - 1) / (uint64_t)a.Wp);
   a.mul_hp1 = (uint32_t)(((1ull << 34) + (uint64_t)a.Hp1 - 1) / (uint64_t)a.Hp1);
   a.off_b = (uint32_t)((size_t)a.stages * a.a_stage_bytes);
-  a.off_bias = (uint32_t)((a.off_b + b_smem + 127u) & ~(size_t)127u);
-  a.off_bars = (a.off_bias + (uint32_t)p.npad * 4 + 15u) & ~15u;
+  a.off_mid = (uint32_t)((a.off_b + b_smem + 127u) & ~(size_t)127u);
+  a.off_bt = a.off_mid + (tail ? (uint32_t)((size_t)p.npad * a.TM * 2) : 0u);
+  a.off_bias = (uint32_t)((a.off_bt + a.bt_bytes + 127u) & ~(size_t)127u);
+  a.off_tbias = a.off_bias + (uint32_t)p.npad * 4;
+  a.off_bars = (a.off_tbias + (uint32_t)tnp * 4 + 15u) & ~15u;
+  a.tail_idesc = (1u << 4) | ((uint32_t)((tail ? tnp : 16) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   for (int t = 0; t < 9; ++t) {
     const int ky = t / 3, kx = t % 3;
     if (s2) {
@@ -600,11 +718,11 @@ bool plan(const ConvParams &p, int num_sms, RArgs &a) {
   return true;
 }
 
-template <int R, int NEPI, bool ACT, bool RES>
+template <int R, int NEPI, bool ACT, bool RES, int TAIL>
 cudaError_t launch_k(const RArgs &a, int grid, size_t smem, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_raster_kernel<R, NEPI, ACT, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_raster_kernel<R, NEPI, ACT, RES, TAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     configured = true;
   }
@@ -619,14 +737,18 @@ cudaError_t launch_k(const RArgs &a, int grid, size_t smem, cudaStream_t s) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, conv_raster_kernel<R, NEPI, ACT, RES>, a);
+  return cudaLaunchKernelEx(&cfg, conv_raster_kernel<R, NEPI, ACT, RES, TAIL>, a);
 }
 
 template <int R, int NEPI>
 cudaError_t launch_r(const RArgs &a, int grid, size_t smem, cudaStream_t s) {
   const bool act = a.p.act != 0, res = a.p.res != nullptr;
-  if (act) return res ? launch_k<R, NEPI, true, true>(a, grid, smem, s) : launch_k<R, NEPI, true, false>(a, grid, smem, s);
-  return res ? launch_k<R, NEPI, false, true>(a, grid, smem, s) : launch_k<R, NEPI, false, false>(a, grid, smem, s);
+  if (a.p.tail_w) {                                  // fused 1x1 consumer (never together with a residual)
+    if (a.p.tail_act) return act ? launch_k<R, NEPI, true, false, 2>(a, grid, smem, s) : launch_k<R, NEPI, false, false, 2>(a, grid, smem, s);
+    return act ? launch_k<R, NEPI, true, false, 1>(a, grid, smem, s) : launch_k<R, NEPI, false, false, 1>(a, grid, smem, s);
+  }
+  if (act) return res ? launch_k<R, NEPI, true, true, 0>(a, grid, smem, s) : launch_k<R, NEPI, true, false, 0>(a, grid, smem, s);
+  return res ? launch_k<R, NEPI, false, true, 0>(a, grid, smem, s) : launch_k<R, NEPI, false, false, 0>(a, grid, smem, s);
 }
 
 }  // namespace

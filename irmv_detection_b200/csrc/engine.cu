@@ -401,6 +401,50 @@ bool add_c2f(irmv_engine *e, Lane &ln, size_t &ci, std::vector<SegRef> in, int H
   return true;
 }
 
+// Fuse a pointwise (1x1, stride 1) conv into the raster conv that produces its only input: the
+// producer keeps its FP16 output tile in shared memory as the A operand of a second GEMM
+// (ConvParams::tail_*), so the intermediate tensor is neither written nor re-read and one launch
+// disappears (m1 -> m2.cv1 and the Detect towers' 3x3 -> 1x1 pairs).  Only when nobody else reads
+// the intermediate and the fused operands fit (conv_raster_fits decides).
+void fuse_tails(irmv_engine *e, Lane &ln) {
+  if (e->cfg.conv_impl == IRMV_CONV_DIRECT || e->cfg.reserved[1] || getenv("IRMV_NO_TAIL")) return;
+  auto overlaps = [](const __half *a0, const __half *a1, const __half *b0, const __half *b1) { return a0 < b1 && b0 < a1; };
+  for (size_t i = 0; i + 1 < ln.ops.size(); ++i) {
+    Op &m = ln.ops[i];
+    const Op &t = ln.ops[i + 1];
+    if (m.kind != Op::CONV || t.kind != Op::CONV || !m.raster || !t.raster) continue;
+    const ConvParams &tp = t.cp;
+    ConvParams mp = m.cp;
+    if (tp.k != 1 || tp.stride != 1 || tp.nseg != 1 || tp.res || tp.out2 || tp.in_parity || tp.seg[0].up || tp.tail_w) continue;
+    if (mp.res || mp.out2 || mp.tail_w || !mp.out) continue;
+    if (tp.seg[0].ptr != mp.out || tp.seg[0].c != mp.cout || tp.seg[0].pstride != mp.out_pstride) continue;
+    if (tp.H != mp.OH || tp.W != mp.OW) continue;
+    const __half *o0 = mp.out, *o1 = mp.out + (long long)(mp.cout / 8) * mp.out_pstride;
+    bool other = false;
+    for (size_t j = 0; j < ln.ops.size() && !other; ++j) {
+      if (j == i || j == i + 1) continue;
+      const Op &q = ln.ops[j];
+      if (q.kind == Op::POOL) { other = overlaps(o0, o1, q.pool_buf, q.pool_buf + 4LL * (q.pC / 8) * q.pStride); continue; }
+      for (int sgi = 0; sgi < q.cp.nseg; ++sgi) {
+        const ConvSeg &g = q.cp.seg[sgi];
+        if (!q.cp.in_parity && overlaps(o0, o1, g.ptr, g.ptr + (long long)(g.c / 8) * g.pstride)) other = true;
+      }
+      if (q.cp.res && overlaps(o0, o1, q.cp.res, q.cp.res + (long long)(q.cp.cout / 8) * q.cp.res_pstride)) other = true;
+    }
+    for (int h = 0; h < 3 && !other; ++h)
+      if (ln.heads.box[h] == mp.out || ln.heads.cls[h] == mp.out) other = true;
+    if (other) continue;
+    mp.tail_w = tp.w_raster; mp.tail_bias = tp.bias; mp.tail_npad = tp.npad; mp.tail_cout = tp.cout; mp.tail_act = tp.act;
+    mp.tail_out = tp.out; mp.tail_out_pstride = tp.out_pstride;
+    mp.out = nullptr;
+    if (!conv_raster_fits(mp)) continue;
+    m.cp = mp;
+    for (auto it = ln.taps.begin(); it != ln.taps.end();)     // the intermediate is no longer materialised
+      it = (it->second.p == o0) ? ln.taps.erase(it) : std::next(it);
+    ln.ops.erase(ln.ops.begin() + (long)i + 1);
+  }
+}
+
 bool build_lane(irmv_engine *e, Lane &ln) {
   const int S = e->S;
   if (!cuda_ok(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking), "cudaStreamCreate",
@@ -474,6 +518,7 @@ bool build_lane(irmv_engine *e, Lane &ln) {
     ln.heads.padded = 1;
   }
   if (ci != e->convs.size()) { set_error("internal: conv count mismatch"); return false; }
+  fuse_tails(e, ln);
   // decode / NMS scratch and outputs
   if (!lane_alloc(ln, (void **)&ln.nms.boxes, (size_t)S * kNumAnchors * 16) ||
       !lane_alloc(ln, (void **)&ln.nms.keys, (size_t)S * kNumAnchors * e->nc * 8) ||

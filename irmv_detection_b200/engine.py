@@ -52,7 +52,7 @@ class YoloEngine:
                  max_batch: int = 1,
                  sub_batch: int = 0, num_lanes: int = 0, num_slots: int = 3, device: int = 0,
                  conv_impl: int = L.CONV_TCGEN05, score_thr: float = 0.25, iou_thr: float = 0.45,
-                 max_det: int = 100, use_graph: bool = True, fused_stem: bool = True):
+                 max_det: int = 100, use_graph: bool = True, fused_stem: bool = True, fuse_tails: bool = True):
         lib = L.lib()
         wpath = onnx_file_path if onnx_file_path.endswith(".irmw") else weights_path_for(onnx_file_path)
         if not os.path.exists(wpath):
@@ -71,6 +71,7 @@ class YoloEngine:
         cfg.score_thr, cfg.iou_thr, cfg.max_det = score_thr, iou_thr, max_det
         cfg.use_graph = int(use_graph)
         cfg.reserved[0] = 0 if fused_stem else 1
+        cfg.reserved[1] = 0 if fuse_tails else 1
         self._cfg = cfg
         self._h = C.c_void_p()
         self._lib = lib

@@ -4,7 +4,10 @@ import re
 import sys
 
 
-def layers(split=False):
+def layers(split=False, fused=True):
+    """GEMM launches of one replay in issue order (conv0 first; it runs inside the stem kernel).
+    fused=True: the production program, where m2.cv1 and the Detect towers' final 1x1 convs run as
+    fused tails of their producers (engine.cu fuse_tails)."""
     def c2f(name, c1, c2, n, hw, up=0):
         c = c2 // 2
         # neck C2f whose cv1 reads concat(upsample(a), b): split into W_a at half resolution + W_b (engine.cu)
@@ -22,6 +25,12 @@ def layers(split=False):
     for i, (hw, ch) in enumerate(((80, 64), (40, 128), (20, 256))):
         d += [(f"h{i}.01", hw, ch, 128, 3, 1), (f"h{i}.box1", hw, 64, 64, 3, 1), (f"h{i}.box2", hw, 64, 64, 1, 1),
               (f"h{i}.cls1", hw, 64, 64, 3, 1), (f"h{i}.cls2", hw, 64, 16, 1, 1)]
+    if fused:
+        drop = {"m2.cv1": "m1", "m4.cv1": "m3"}
+        for i in range(3):
+            drop[f"h{i}.box2"] = f"h{i}.box1"
+            drop[f"h{i}.cls2"] = f"h{i}.cls1"
+        d = [((n + "+1x1") if n in drop.values() else n, hw, cin, cout, k, s) for (n, hw, cin, cout, k, s) in d if n not in drop]
     return d
 
 

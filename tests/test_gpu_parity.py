@@ -349,26 +349,36 @@ def _oracle_forward(weights, x_nhwc8):
     return taps, outs, boxes.numpy(), scores.numpy()
 
 
-@pytest.mark.parametrize("impl", ["direct", "tcgen05"])
+@pytest.mark.parametrize("impl", ["direct", "tcgen05", "tcgen05_unfused"])
 def test_network_parity(frames, weights_seed0, impl):
     import irmv_detection_b200 as irmv
     from oracle import nms_ref as N
     fr = frames[[0, 2, 3]]                       # rm_test.jpg + two synthetic variants
     n = fr.shape[0]
+    # "tcgen05" is the production program (1x1 consumers fused into their producers: module taps m1 and m3
+    # are then not materialised and is skipped below); "tcgen05_unfused" materialises every module output
     eng = irmv.YoloEngine(weights_seed0, (1280, 1024), max_batch=n, sub_batch=n,
-                          conv_impl=irmv.CONV_DIRECT if impl == "direct" else irmv.CONV_TCGEN05)
+                          conv_impl=irmv.CONV_DIRECT if impl == "direct" else irmv.CONV_TCGEN05,
+                          fuse_tails=(impl != "tcgen05_unfused"))
     dets = eng.detect_batch(fr)
     # the engine's stem kernel fuses preprocess + conv0, so the network input is not materialised;
     # the stand-alone preprocess entry point produces the identical tensor (same device code)
     x = irmv.preprocess(fr)
     taps, outs, rboxes, rscores = _oracle_forward(weights_seed0, x)
     # module taps: FP16 storage vs FP32 oracle
+    seen = 0
     for name, ref in taps.items():
-        got = eng.read_tensor(name).astype(np.float32)
+        try:
+            got = eng.read_tensor(name).astype(np.float32)
+        except RuntimeError:
+            assert impl == "tcgen05" and name in ("m1", "m3"), name   # fused into m2.cv1 / m4.cv1
+            continue
+        seen += 1
         ref = ref.permute(0, 2, 3, 1).numpy()
         err = np.abs(got - ref).max()
         scale = np.abs(ref).max()
         assert err <= 2e-2 * max(scale, 1.0), f"{impl} {name}: max err {err} (scale {scale})"
+    assert seen >= len(taps) - 2
     # head tensors -> decoded boxes/scores through the CUDA decode
     box = np.concatenate([eng.read_tensor(f"box{i}").reshape(n, -1, 64) for i in range(3)], 1)
     cls = np.concatenate([eng.read_tensor(f"cls{i}").reshape(n, -1, 16) for i in range(3)], 1)
