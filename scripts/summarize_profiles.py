@@ -71,7 +71,8 @@ def main():
         agg[k["name"]][1] += k["gpu__time_duration.sum"]
     out += ["## 1. Launch list of `python bench.py --steps 1 --warmup 3 --no-cpu-baseline`",
             f"`profiles/r1_bench_launches.csv` ({len(L)} launches of the engine's kernels, `-s 394 -c 420`; the table is one step = two",
-            f"128-frame replays = {len(step)} launches: set_src + stem + 59 GEMMs + pool + decode + NMS + quads + PnP per replay)", "",
+            f"128-frame replays = {len(step)} launches: set_src + stem + {sum(1 for k in step if k['name'].startswith('conv_')) // 2} GEMM launches + pool + decode + NMS + quads + PnP per replay;",
+            "eight 1x1 convs run as fused tails of their producers, conv0 inside the stem)", "",
             "| kernel | launches | total us | share |", "|---|---|---|---|"]
     for n, (c, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
         out.append(f"| `{n}` | {c} | {t/1e3:.1f} | {100*t/tot:.1f} % |")
@@ -119,7 +120,7 @@ def main():
                        f"{k['sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed']:.1f} | {dm:.0f} | {dm/t:.2f} | {k['lts__t_bytes.sum']/1e6:.0f} | "
                        f"{k['launch__shared_mem_per_block_dynamic']/1e3:.0f} |")
     json.dump({"conv_group_dram_bytes_per_frame": traffic / frames, "frames": frames, "launches": len(conv),
-               "source": "profiles/r1_replay128_metrics.csv (dram__bytes_read.sum + dram__bytes_write.sum of the 59 GEMM launches)"},
+               "source": "profiles/r1_replay128_metrics.csv (dram__bytes_read.sum + dram__bytes_write.sum of the GEMM launches)"},
               open(os.path.join(P, "r1_traffic.json"), "w"), indent=1)
     # ---- full captures
     keys = ["gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum",
