@@ -416,7 +416,7 @@ def run_ours(args):
         try:
             threads = os.cpu_count() or 1
             ref = CpuReference(wpath, threads)
-            fps, n, dt = ref.run(hosts[0][:64], budget_s=args.cpu_budget)
+            fps, n, dt = ref.run(hosts[0], budget_s=args.cpu_budget)
             cpu = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
                    "sample": f"{n} of the step's 256 Bayer frames in {dt:.1f} s; cv2 demosaic+flip+resize, "
                              f"{ref.kind_net} YOLOv8n FP32, numpy NMS, cv2.solvePnP(IPPE)"}
