@@ -193,9 +193,11 @@ __device__ __forceinline__ Region stage_window(const PreprocessParams &p, const 
   auto stage_chunk = [&](int r, int c) {
     const uint8_t *row = frame + (size_t)(sy_lo + r) * src_pitch + col_byte_lo;
     const uint8_t *a = (const uint8_t *)((size_t)row & ~(size_t)15) + (size_t)c * 16;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (a < row + nbytes && a < alloc_end) v = __ldg((const uint4 *)a);
-    *(uint4 *)(smem + (size_t)r * pitch_s + c * 16) = v;
+    // asynchronous copy (zero fill outside the window): the caller overlaps it with its table set-up
+    // and waits with stage_wait()
+    const bool in = a < row + nbytes && a < alloc_end;
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem + (size_t)r * pitch_s + c * 16);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(in ? a : frame), "r"(in ? 16u : 0u) : "memory");
   };
   if (chunks_per_row <= 8) {                    // 8 threads per staged row, no division
     const int c = threadIdx.x & 7;
@@ -210,6 +212,8 @@ __device__ __forceinline__ Region stage_window(const PreprocessParams &p, const 
   const int shift0 = (int)((size_t)(frame + (size_t)sy_lo * src_pitch + col_byte_lo) & 15);
   return Region{frame, smem, sy_lo, pitch_s, col_byte_lo, src_pitch, shift0, src_pitch & 15};
 }
+
+__device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 __global__ void __launch_bounds__(NT)
 preprocess_kernel(PreprocessParams p, int rows_cap, int pitch_s) {
@@ -234,6 +238,7 @@ preprocess_kernel(PreprocessParams p, int rows_cap, int pitch_s) {
   else if (threadIdx.x < TH + TW) xtap[threadIdx.x - TH] = axis_taps_lb(min(ox0 + (int)threadIdx.x - TH, kNet - 1), p.pad_x, p.new_w, scale_x, W, hp);
   Region reg = stage_window(p, base, frame, smem, pitch_s, oy0, min(oy0 + TH, kNet) - 1, ox0, min(ox0 + TW, kNet) - 1,
                             scale_x, scale_y, hp, NT);
+  stage_wait();
   __syncthreads();
   (void)rows_cap;
 
@@ -294,6 +299,11 @@ stem_kernel(PreprocessParams p, const float *__restrict__ w, const float *__rest
   __shared__ float lut[256];
   __shared__ __half lut_h[256];
   __shared__ Taps ytap[SI], xtap[SI];
+  // network-input window of this tile: rows 2*oy0-1 .. 2*oy0+2*ST-1 (clipped: outside is conv padding).
+  // The source window is fetched with cp.async first; the tables below are built while it lands.
+  const int iy_lo = 2 * oy0 - 1, ix_lo = 2 * ox0 - 1;
+  Region reg = stage_window(p, base, frame, smem, pitch_s, max(iy_lo, 0), min(iy_lo + SI - 1, kNet - 1), max(ix_lo, 0),
+                            min(ix_lo + SI - 1, kNet - 1), scale_x, scale_y, hp, ST * ST);
   {
     const int nn = threadIdx.x >> 4, k0 = 2 * (threadIdx.x & 15);
     const __half2 hw = __floats2half2_rn(k0 < 27 ? w[nn * 27 + k0] : 0.f, k0 + 1 < 27 ? w[nn * 27 + k0 + 1] : 0.f);
@@ -308,10 +318,7 @@ stem_kernel(PreprocessParams p, const float *__restrict__ w, const float *__rest
   lut_h[threadIdx.x] = __float2half_rn(__fdiv_rn((float)threadIdx.x, 255.0f));
   if (threadIdx.x < SI) ytap[threadIdx.x] = axis_taps_lb(min(max(2 * oy0 - 1 + (int)threadIdx.x, 0), kNet - 1), p.pad_y, p.new_h, scale_y, H, hp);
   else if (threadIdx.x < 2 * SI) xtap[threadIdx.x - SI] = axis_taps_lb(min(max(2 * ox0 - 1 + (int)threadIdx.x - SI, 0), kNet - 1), p.pad_x, p.new_w, scale_x, W, hp);
-  // network-input window of this tile: rows 2*oy0-1 .. 2*oy0+2*ST-1 (clipped: outside is conv padding)
-  const int iy_lo = 2 * oy0 - 1, ix_lo = 2 * ox0 - 1;
-  Region reg = stage_window(p, base, frame, smem, pitch_s, max(iy_lo, 0), min(iy_lo + SI - 1, kNet - 1), max(ix_lo, 0),
-                            min(ix_lo + SI - 1, kNet - 1), scale_x, scale_y, hp, ST * ST);
+  stage_wait();
   __syncthreads();
   int red_y = 0, red_x = 0;
   if (p.chan_order == 3) { red_y = 1; red_x = 1; }
