@@ -364,8 +364,8 @@ def run_ours(args):
             runs.append(ms[:nops].copy())
         op_ms = np.median(np.stack(runs), axis=0)
         sys.path.insert(0, os.path.join(ROOT, "scripts"))
-        from analyze_launches import layers
-        i_top = [l[0] for l in layers()[1:]].index("h0.01")     # conv0 lives in the stem
+        from analyze_launches import name_ops
+        i_top = [l[0] for l in name_ops(eng.describe_ops())].index("h0.01")     # conv0 lives in the stem
         fl = 2.0 * k * 80 * 80 * 9 * 64 * 128
         t_top = float(op_ms[i_top]) * 1e-3
         tk = None

@@ -135,6 +135,8 @@ int irmv_engine_collect(irmv_engine *e, int ticket, irmv_bbox *out, int *counts,
 int irmv_engine_profile_stages(irmv_engine *e, const uint8_t *frames_dev, int nframes, float ms[5]);
 
 /* Debug/tuning: per-tile clock64 stamps of CTA 0 for GEMM `op_index` (see engine.cu). */
+/* Debug: text description of the network stage's kernels in issue order (one line per launch). */
+int irmv_engine_describe_ops(irmv_engine *e, char *buf, int cap);
 /* Debug: per-kernel CUDA-event times (ms) of the network stage of one eager replay. */
 int irmv_engine_profile_ops(irmv_engine *e, const uint8_t *frames_dev, int nframes, float *ms, int cap);
 int irmv_engine_trace_conv(irmv_engine *e, int op_index, int nframes, long long *out, int cap_tiles,

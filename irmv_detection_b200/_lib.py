@@ -57,6 +57,7 @@ SYMBOLS = {
     "irmv_engine_profile_stages": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_float * 5)]),
     "irmv_engine_submit_batch": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_int)]),
     "irmv_engine_collect": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P]),
+    "irmv_engine_describe_ops": (C.c_int, [_P, _P, C.c_int]),
     "irmv_engine_profile_ops": (C.c_int, [_P, _P, C.c_int, _P, C.c_int]),
     "irmv_engine_trace_conv": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, C.POINTER(C.c_float)]),
     "irmv_engine_read_tensor": (C.c_int, [_P, C.c_char_p, _P, C.c_int64, C.POINTER(C.c_int32 * 5)]),

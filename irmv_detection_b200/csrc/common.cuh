@@ -117,8 +117,12 @@ struct ConvParams {
   const __half *tail_w;    // [cout/8][tail_npad][8] = the 1x1 conv's w_raster image; null = no tail
   const float *tail_bias;  // [tail_npad]
   int tail_npad, tail_cout, tail_act;
-  __half *tail_out;        // pixel 0 of the first output plane of the tail
+  __half *tail_out;        // pixel 0 of the first output plane of the tail (null: only the parity twin)
   long long tail_out_pstride;
+  __half *tail_out2;       // parity twin of the tail's output, or null
+  long long tail_out2_pstride;
+  ConvSeg tail_ext;        // channels that precede the intermediate in the tail's input concat (C2f.cv2 over
+                           // [older chunks | the bottleneck output just computed]); c == 0: none
   int in_parity;           // 1: seg[0].ptr / pstride describe the parity twin of the input
   __half *out2;            // parity twin of the output (written in addition to `out`); may be null
   long long out2_pstride;

@@ -48,6 +48,7 @@ struct Bars {
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint64_t mid_full, mid_empty;           // fused tail: intermediate tile written / consumed
+  uint64_t ext_full, ext_empty;           // fused tail: the tail's other input planes loaded / consumed
   uint64_t tail_full[2], tail_empty[2];   // fused tail: second accumulator set
   uint64_t bfull;
   uint32_t tmem_base;
@@ -143,7 +144,8 @@ struct RArgs {
   uint32_t a_stage_bytes, b_bytes, b_tap_bytes, off_b, off_bias, off_bars;
   uint32_t tap_a[9];                      // per chunk: A start offset inside a stage, 16-byte units
   // fused 1x1 tail (ConvParams::tail_w): intermediate tile [cout/8][TM][8], tail weights, tail bias
-  uint32_t off_mid, off_bt, off_tbias, bt_bytes, tail_idesc;
+  uint32_t off_mid, off_ext, off_bt, off_tbias, bt_bytes, tail_idesc;
+  int ext_planes;                         // tail input planes that come from global memory (ConvParams::tail_ext)
   int tmem_tail0;                         // first TMEM column of the tail accumulators
 };
 
@@ -221,6 +223,7 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
   uint8_t *sB = smem + a.off_b;
   float *s_hb = reinterpret_cast<float *>(smem + a.off_bias);
   uint8_t *sMid = smem + a.off_mid;
+  uint8_t *sExt = smem + a.off_ext;
   uint8_t *sBt = smem + a.off_bt;
   float *s_tb = reinterpret_cast<float *>(smem + a.off_tbias);
   Bars *bars = reinterpret_cast<Bars *>(smem + a.off_bars);
@@ -259,6 +262,8 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
     mbar_init(&bars->bfull, 1);
     mbar_init(&bars->mid_full, NEPI);
     mbar_init(&bars->mid_empty, 1);
+    mbar_init(&bars->ext_full, 1);
+    mbar_init(&bars->ext_empty, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->tail_full[i], 1);
       mbar_init(&bars->tail_empty[i], NEPI);
@@ -339,6 +344,8 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
     const int tshift = 31 - __clz(tnp >> 4), tmask = (tnp >> 4) - 1;
     __half *const tout = p.tail_out;
     const long long tout_ps = p.tail_out_pstride;
+    __half *const tout2 = p.tail_out2;
+    const long long tout2_ps = p.tail_out2_pstride;
     const int tcout = p.tail_cout;
     auto tail_epilogue = [&](int jt, int tile_j) {
       const int tb = jt & 1;
@@ -354,9 +361,20 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
         uint32_t v[16];
         tc_ld16(tcol + (uint32_t)(r * tnp + c0), v);
         tc_ld_wait();
-        if (((okm >> r) & 1u) && c0 < tcout)
-          epi_chunk<TAIL == 2, false>(v, s_tb + c0, tout + (long long)(c0 >> 3) * tout_ps + (long long)(q_tile + r * 128) * 8,
-                                      tout_ps, nullptr, 0, z, z);
+        if (((okm >> r) & 1u) && c0 < tcout) {
+          __half *o = tout ? tout + (long long)(c0 >> 3) * tout_ps + (long long)(q_tile + r * 128) * 8 : nullptr;
+          __half *o2 = nullptr;
+          if (tout2) {                                      // parity twin of the tail's output
+            const int qi = q_tile + r * 128;
+            const uint32_t row = (uint32_t)(((uint64_t)(uint32_t)qi * mul_wp) >> 34);
+            const int x = qi - (int)row * Wp;
+            const uint32_t img = (uint32_t)(((uint64_t)row * mul_hp1) >> 34);
+            const int y = (int)row - (int)img * Hp1 - 1;
+            const int px2 = ((int)img * Hp2 + 1 + (y >> 1)) * Wp2 + (x >> 1);
+            o2 = tout2 + (long long)(((y & 1) * 2 + (x & 1)) * (tcout >> 3) + (c0 >> 3)) * tout2_ps + (long long)px2 * 8;
+          }
+          epi_chunk<TAIL == 2, false>(v, s_tb + c0, o, tout_ps, o2, tout2_ps, z, z);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -448,6 +466,19 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
       const uint32_t tile_tx = plane_bytes * (uint32_t)a.NP;
       const int n0 = p.in_parity ? a.NP : p.seg[0].c >> 3, n1 = p.nseg > 1 ? p.seg[1].c >> 3 : 0;
       const size_t ps0 = (size_t)p.seg[0].pstride * 2, ps1 = (size_t)p.seg[1].pstride * 2;
+      // fused tail over a concat: the tail's other input planes for tile number j (no halo), loaded
+      // one tile behind the main operand (tail(j) runs after main(j+1), see the MMA warp)
+      const uint32_t ext_bytes = (uint32_t)a.TM * 16u;
+      auto load_ext = [&](int j, int tile_j) {
+        mbar_wait(&bars->ext_empty, ((uint32_t)j & 1u) ^ 1u);
+        const uint32_t bar = smem_u32(&bars->ext_full);
+        mbar_expect_tx(bar, ext_bytes * (uint32_t)a.ext_planes);
+        uint32_t dst = smem_u32(sExt);
+        const uint8_t *src = reinterpret_cast<const uint8_t *>(p.tail_ext.ptr) + ((long long)a.q_begin + (long long)tile_j * a.TM) * 16;
+        const size_t pse = (size_t)p.tail_ext.pstride * 2;
+        for (int c = 0; c < a.ext_planes; ++c, dst += ext_bytes, src += pse) bulk_g2s(dst, src, ext_bytes, bar);
+      };
+      int prev_tile = -1;
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++itl) {
         const bool tr = p.trace && blockIdx.x == 0 && itl < p.trace_cap;
         if (tr) p.trace[itl * 8 + 0] = clock64();
@@ -463,6 +494,8 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
         for (int c = 0; c < n1; ++c, dst += pitch_bytes, src += ps1) bulk_g2s(dst, src, plane_bytes, bar);
         if (tr) p.trace[itl * 8 + 2] = clock64();
         if (++s == a.stages) { s = 0; ph ^= 1u; }
+        if (TAIL && a.ext_planes && itl > 0) load_ext(itl - 1, prev_tile);
+        prev_tile = tile;
         if (a.b_stream) {
           const uint8_t *wsrc = reinterpret_cast<const uint8_t *>(p.w_raster);
           for (int t = 0; t < a.nchunks; ++t, wsrc += a.b_tap_bytes) {
@@ -474,6 +507,7 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
           }
         }
       }
+      if (TAIL && a.ext_planes && itl > 0) load_ext(itl - 1, prev_tile);
     }
   } else {
     // ===================================================================== MMA issuer
@@ -491,23 +525,35 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
     // MMAs (tile j+1's main MMAs keep the pipe busy while the epilogue produces tile j's operand).
     const int tnp = TAIL ? p.tail_npad : 16;
     const uint32_t mid_lo0 = desc_lo(smem_u32(sMid), (uint32_t)a.TM * 16u);
+    const uint32_t ext_lo0 = desc_lo(smem_u32(sExt), (uint32_t)a.TM * 16u);
     const uint32_t bt_lo0 = desc_lo(smem_u32(sBt), (uint32_t)tnp * 16u);
     auto issue_tail = [&](int j) {
       const int tb = j & 1;
       mbar_wait_warp(&bars->mid_full, (uint32_t)j & 1u, lane);
+      if (a.ext_planes) mbar_wait_warp(&bars->ext_full, (uint32_t)j & 1u, lane);
       mbar_wait_warp(&bars->tail_empty[tb], ((uint32_t)(j >> 1) & 1u) ^ 1u, lane);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t td0 = tmem_base + (uint32_t)(a.tmem_tail0 + tb * R * tnp);
-        const int ksteps = npad >> 4;                       // K of the tail = channels of the intermediate tile
-        uint32_t al = mid_lo0, bl = bt_lo0;
-        for (int kk = 0; kk < ksteps; ++kk, al += 2u * (uint32_t)a.TM, bl += 2u * (uint32_t)tnp) {
+        // K of the tail = [planes loaded from global (older concat chunks) | the intermediate tile]
+        uint32_t bl = bt_lo0, acc = 0;
+        uint32_t al = ext_lo0;
+        for (int kk = 0; kk < (a.ext_planes >> 1); ++kk, al += 2u * (uint32_t)a.TM, bl += 2u * (uint32_t)tnp) {
 #pragma unroll
           for (int r = 0; r < R; ++r)
-            tc_mma_f16(td0 + (uint32_t)(r * tnp), al + (uint32_t)(r * 128), kDescHi, bl, kDescHi, a.tail_idesc, kk != 0 ? 1u : 0u);
+            tc_mma_f16(td0 + (uint32_t)(r * tnp), al + (uint32_t)(r * 128), kDescHi, bl, kDescHi, a.tail_idesc, acc);
+          acc = 1;
+        }
+        al = mid_lo0;
+        for (int kk = 0; kk < (npad >> 4); ++kk, al += 2u * (uint32_t)a.TM, bl += 2u * (uint32_t)tnp) {
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+            tc_mma_f16(td0 + (uint32_t)(r * tnp), al + (uint32_t)(r * 128), kDescHi, bl, kDescHi, a.tail_idesc, acc);
+          acc = 1;
         }
         tc_commit(&bars->tail_full[tb]);
         tc_commit(&bars->mid_empty);
+        if (a.ext_planes) tc_commit(&bars->ext_empty);
       }
       __syncwarp();
     };
@@ -613,11 +659,15 @@ bool plan(const ConvParams &p, int num_sms, RArgs &a) {
   a.chunk_pairs = a.NCH >> 1;
   a.b_tap_bytes = (uint32_t)((size_t)p.cin * p.npad * 2);
   const bool tail = p.tail_w != nullptr;
-  if (tail && (p.res || p.tail_npad % 16 || p.tail_npad > 256 || p.tail_cout % 16 || p.cout != p.npad || !p.tail_out)) return false;
+  if (tail && (p.tail_npad % 16 || p.tail_npad > 256 || p.tail_cout % 16 || p.cout != p.npad || (!p.tail_out && !p.tail_out2))) return false;
+  if (tail && p.res && !(p.act && p.tail_act)) return false;
   const int tnp = tail ? p.tail_npad : 0;
-  a.bt_bytes = tail ? (uint32_t)((size_t)p.npad * tnp * 2) : 0u;
-  // fused tail: the FP16 intermediate tile [cout/8][TM][8] stays in shared memory
-  auto tail_bytes = [&](int R) { return tail ? (size_t)a.bt_bytes + (size_t)p.npad * 128 * R * 2 + 256 : (size_t)0; };
+  const int ext_c = tail ? p.tail_ext.c : 0;         // tail input channels that come from global memory
+  if (ext_c % 16 || (tail && p.tail_ext.up) || (tail && p.tail_out2 && ((p.OH & 1) || (p.OW & 1)))) return false;
+  a.ext_planes = ext_c / 8;
+  a.bt_bytes = tail ? (uint32_t)((size_t)(p.npad + ext_c) * tnp * 2) : 0u;
+  // fused tail: the FP16 intermediate tile [cout/8][TM][8] (and the tail's other input planes) stay in shared memory
+  auto tail_bytes = [&](int R) { return tail ? (size_t)a.bt_bytes + (size_t)(p.npad + ext_c) * 128 * R * 2 + 256 : (size_t)0; };
   const size_t misc = (size_t)p.npad * 4 + (size_t)tnp * 4 + sizeof(Bars) + 1024 + 256;
   const int halo = p.k == 3 ? (s2 ? a.Wp + 1 : 2 * a.Wp + 2) : 0;
   // Bulk copies run fastest when source, destination and size are multiples of 128 bytes (8
@@ -698,7 +748,8 @@ bool plan(const ConvParams &p, int num_sms, RArgs &a) {
   a.mul_hp1 = (uint32_t)(((1ull << 34) + (uint64_t)a.Hp1 - 1) / (uint64_t)a.Hp1);
   a.off_b = (uint32_t)((size_t)a.stages * a.a_stage_bytes);
   a.off_mid = (uint32_t)((a.off_b + b_smem + 127u) & ~(size_t)127u);
-  a.off_bt = a.off_mid + (tail ? (uint32_t)((size_t)p.npad * a.TM * 2) : 0u);
+  a.off_ext = a.off_mid + (tail ? (uint32_t)((size_t)p.npad * a.TM * 2) : 0u);
+  a.off_bt = a.off_ext + (uint32_t)((size_t)ext_c * a.TM * 2);
   a.off_bias = (uint32_t)((a.off_bt + a.bt_bytes + 127u) & ~(size_t)127u);
   a.off_tbias = a.off_bias + (uint32_t)p.npad * 4;
   a.off_bars = (a.off_tbias + (uint32_t)tnp * 4 + 15u) & ~15u;
@@ -743,7 +794,11 @@ cudaError_t launch_k(const RArgs &a, int grid, size_t smem, cudaStream_t s) {
 template <int R, int NEPI>
 cudaError_t launch_r(const RArgs &a, int grid, size_t smem, cudaStream_t s) {
   const bool act = a.p.act != 0, res = a.p.res != nullptr;
-  if (a.p.tail_w) {                                  // fused 1x1 consumer (never together with a residual)
+  if (a.p.tail_w) {                                  // fused 1x1 consumer
+    if (res) {                                       // bottleneck with shortcut + C2f.cv2: SiLU on both
+      if (!act || !a.p.tail_act) return cudaErrorInvalidValue;
+      return launch_k<R, NEPI, true, true, 2>(a, grid, smem, s);
+    }
     if (a.p.tail_act) return act ? launch_k<R, NEPI, true, false, 2>(a, grid, smem, s) : launch_k<R, NEPI, false, false, 2>(a, grid, smem, s);
     return act ? launch_k<R, NEPI, true, false, 1>(a, grid, smem, s) : launch_k<R, NEPI, false, false, 1>(a, grid, smem, s);
   }

@@ -415,9 +415,13 @@ void fuse_tails(irmv_engine *e, Lane &ln) {
     if (m.kind != Op::CONV || t.kind != Op::CONV || !m.raster || !t.raster) continue;
     const ConvParams &tp = t.cp;
     ConvParams mp = m.cp;
-    if (tp.k != 1 || tp.stride != 1 || tp.nseg != 1 || tp.res || tp.out2 || tp.in_parity || tp.seg[0].up || tp.tail_w) continue;
-    if (mp.res || mp.out2 || mp.tail_w || !mp.out) continue;
-    if (tp.seg[0].ptr != mp.out || tp.seg[0].c != mp.cout || tp.seg[0].pstride != mp.out_pstride) continue;
+    if (tp.k != 1 || tp.stride != 1 || tp.nseg != 1 || tp.res || tp.in_parity || tp.seg[0].up || tp.tail_w) continue;
+    if (mp.out2 || mp.tail_w || !mp.out) continue;
+    // the tail reads [ext channels | this conv's output]: either exactly the output (ext = 0) or a
+    // concat whose LAST chunk it is (C2f.cv2 right after the last bottleneck conv)
+    const int ext = tp.seg[0].c - mp.cout;
+    if (ext < 0 || tp.seg[0].pstride != mp.out_pstride) continue;
+    if (tp.seg[0].ptr + (long long)(ext / 8) * tp.seg[0].pstride != mp.out) continue;
     if (tp.H != mp.OH || tp.W != mp.OW) continue;
     const __half *o0 = mp.out, *o1 = mp.out + (long long)(mp.cout / 8) * mp.out_pstride;
     bool other = false;
@@ -436,6 +440,8 @@ void fuse_tails(irmv_engine *e, Lane &ln) {
     if (other) continue;
     mp.tail_w = tp.w_raster; mp.tail_bias = tp.bias; mp.tail_npad = tp.npad; mp.tail_cout = tp.cout; mp.tail_act = tp.act;
     mp.tail_out = tp.out; mp.tail_out_pstride = tp.out_pstride;
+    mp.tail_out2 = tp.out2; mp.tail_out2_pstride = tp.out2_pstride;
+    mp.tail_ext = tp.seg[0]; mp.tail_ext.c = ext;
     mp.out = nullptr;
     if (!conv_raster_fits(mp)) continue;
     m.cp = mp;
@@ -1151,6 +1157,27 @@ int irmv_engine_profile_ops(irmv_engine *e, const uint8_t *frames_dev, int nfram
   for (size_t i = 1; i < evs.size() && k < cap; ++i, ++k) cudaEventElapsedTime(&ms[k], evs[i - 1], evs[i]);
   for (auto ev : evs) cudaEventDestroy(ev);
   return k;
+}
+
+// Debug: one line per kernel of the network stage of a replay, in issue order:
+// "conv k s cin cout hw raster tail_cout" or "pool".  Returns the number of bytes written.
+int irmv_engine_describe_ops(irmv_engine *e, char *buf, int cap) {
+  if (!e || !buf || cap < 1) return -1;
+  std::string out;
+  bool first = true;
+  const bool fused = e->fused_stem && e->cfg.conv_impl != IRMV_CONV_DIRECT;
+  for (auto &o : e->lanes[0].ops) {
+    if (first && fused) { first = false; continue; }       // conv0 runs inside the stem kernel
+    first = false;
+    char line[160];
+    if (o.kind == Op::POOL) snprintf(line, sizeof line, "pool\n");
+    else snprintf(line, sizeof line, "conv %d %d %d %d %d %d %d\n", o.cp.k, o.cp.stride, o.cp.cin, o.cp.cout, o.cp.OH,
+                  o.raster ? 1 : 0, o.cp.tail_w ? o.cp.tail_cout : 0);
+    out += line;
+  }
+  if ((int)out.size() + 1 > cap) { set_error("buffer too small"); return -1; }
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return (int)out.size();
 }
 
 // Debug: re-run GEMM number `op_index` of lane 0 on whatever its input buffers hold, with CTA 0

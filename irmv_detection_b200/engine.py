@@ -201,6 +201,22 @@ class YoloEngine:
                 "irmv_engine_fetch_poses")
         return rv, tv, ok.astype(bool)
 
+    def describe_ops(self):
+        """Kernels of the network stage in issue order: dicts {kind, k, s, cin, cout, hw, raster, tail_cout}."""
+        buf = C.create_string_buffer(16384)
+        if self._lib.irmv_engine_describe_ops(self._h, buf, 16384) < 0:
+            L.check(1, "irmv_engine_describe_ops")
+        ops = []
+        for line in buf.value.decode().splitlines():
+            f = line.split()
+            if f[0] == "pool":
+                ops.append({"kind": "pool"})
+            else:
+                k, s, cin, cout, hw, raster, tail = (int(v) for v in f[1:])
+                ops.append({"kind": "conv", "k": k, "s": s, "cin": cin, "cout": cout, "hw": hw, "raster": bool(raster),
+                            "tail_cout": tail})
+        return ops
+
     def profile_stages(self, dev_ptr: int, n: int):
         ms = (C.c_float * 5)()
         k = self._lib.irmv_engine_profile_stages(self._h, C.c_void_p(dev_ptr), n, C.byref(ms))

@@ -34,6 +34,30 @@ def layers(split=False, fused=True):
     return d
 
 
+def name_ops(ops):
+    """Names for the engine's launches (YoloEngine.describe_ops()): walks the unfused layer list, a
+    launch with a fused 1x1 tail consumes two entries.  Returns (name, hw, cin, cout, k, s, flop_per_frame)."""
+    L = layers(fused=False)[1:]
+    out, i = [], 0
+    for o in ops:
+        if o["kind"] == "pool":
+            assert L[i][0] == "POOL"
+            out.append(("POOL", 20, 0, 0, 0, 0, 0.0))
+            i += 1
+            continue
+        n, hw, cin, cout, k, s = L[i]
+        fl = 2.0 * hw * hw * k * k * cin * cout
+        i += 1
+        if o["tail_cout"]:
+            n2, hw2, cin2, cout2, k2, s2 = L[i]
+            fl += 2.0 * hw2 * hw2 * cin2 * cout2
+            n = f"{n}+{n2.split('.')[-1]}"
+            i += 1
+        out.append((n, hw, cin, cout, k, s, fl))
+    assert i == len(L), (i, len(L))
+    return out
+
+
 def main():
     path, B = sys.argv[1], int(sys.argv[2])
     with open(path) as f:

@@ -11,7 +11,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name "$KRX" -
 # 2. per-launch counters of one eager 128-frame replay
 scripts/ncu_replay_metrics.sh 128 r1_replay128_metrics
 # 3. full captures: top GEMM (Detect P3 box.0|cls.0, network op 45) and the stem
-OP=$(python -c "import sys; sys.path.insert(0, 'scripts'); from analyze_launches import layers; print([l[0] for l in layers() if l[0] != 'POOL'].index('h0.01'))")
+cp gpurun_out/ops.json gpurun_out/r1_ops.json
+OP=$(python -c "import sys, json; sys.path.insert(0, 'scripts'); from analyze_launches import name_ops; print(1 + [n[0] for n in name_ops(json.load(open('gpurun_out/r1_ops.json'))) if n[0] != 'POOL'].index('h0.01'))")
 scripts/ncu_one_conv.sh $OP 128 r1_raster_h0
 scripts/ncu_stem.sh r1_stem
 rm -f gpurun_out/*.ncu-rep

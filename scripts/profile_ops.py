@@ -14,7 +14,7 @@ def main():
     import torch
     import irmv_detection_b200 as irmv
     from irmv_detection_b200 import weights, _lib
-    from analyze_launches import layers
+    from analyze_launches import name_ops
     import bench
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
     w = "/tmp/profile_seed0.irmw"
@@ -32,19 +32,19 @@ def main():
         k = lib.irmv_engine_profile_ops(eng._h, C.c_void_p(frames.data_ptr()), n, ms.ctypes.data, 80)
         runs.append(ms[:k].copy())
     ms = np.median(np.stack(runs), axis=0) * 1e3
-    L = layers()[1:]                      # op 0 (conv0) lives in the stem kernel
+    L = name_ops(eng.describe_ops())      # conv0 lives in the stem kernel
     assert len(L) == len(ms), (len(L), len(ms))
     tot = ms.sum()
     print(f"network stage: {tot:.1f} us for {n} frames = {tot / n:.2f} us/frame ({8.0956e9 * n / tot / 1e6:.0f} TFLOP/s)")
-    print(f"{'layer':12s} {'hw':>4s} {'cin':>4s} {'cout':>4s} k s {'us':>8s} {'share':>6s} {'TFLOP/s':>8s} {'GB/s(in+out)':>12s}")
-    for (name, hw, cin, cout, k, s), v in zip(L, ms):
+    print(f"{'layer':16s} {'hw':>4s} {'cin':>4s} {'cout':>4s} k s {'us':>8s} {'share':>6s} {'TFLOP/s':>8s} {'GB/s(in+out)':>12s}")
+    for (name, hw, cin, cout, k, s, flf), v in zip(L, ms):
         if name == "POOL":
-            print(f"{name:12s} {'':18s} {v:8.1f} {100 * v / tot:5.1f}%")
+            print(f"{name:16s} {'':18s} {v:8.1f} {100 * v / tot:5.1f}%")
             continue
         M = n * hw * hw
-        fl = 2.0 * M * k * k * cin * cout
+        fl = flf * n
         io = (n * (hw * s) ** 2 * cin + M * cout) * 2.0
-        print(f"{name:12s} {hw:4d} {cin:4d} {cout:4d} {k} {s} {v:8.1f} {100 * v / tot:5.1f}% {fl / v / 1e6:8.1f} {io / v / 1e3:12.1f}")
+        print(f"{name:16s} {hw:4d} {cin:4d} {cout:4d} {k} {s} {v:8.1f} {100 * v / tot:5.1f}% {fl / v / 1e6:8.1f} {io / v / 1e3:12.1f}")
     eng.close()
 
 

@@ -28,6 +28,9 @@ def main():
         eng.enqueue_batch_device(frames.data_ptr(), n)
         ms = eng.sync()
     print("launches per replay", eng.kernel_launches(n), "device ms", ms)
+    import json
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(eng.describe_ops(), open(os.path.join(ROOT, "gpurun_out", "ops.json"), "w"))
     k, st = eng.profile_stages(frames.data_ptr(), n)
     print("stages", k, st)
     eng.close()

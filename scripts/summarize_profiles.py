@@ -10,7 +10,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 P = os.path.join(ROOT, "profiles")
 sys.path.insert(0, os.path.join(ROOT, "scripts"))
-from analyze_launches import layers  # noqa: E402
+from analyze_launches import name_ops  # noqa: E402
 
 
 def short(name):
@@ -104,17 +104,17 @@ def main():
             f"= {traffic / conv_us / 1e6:.2f} TB/s averaged over the conv stage (algorithmic: 42.1 MB of conv inputs + 28.6 MB of conv outputs per frame when",
             "nothing stays in the 126 MB L2; at 128 frames per replay the 160x160 and 80x80 tensors do not fit, so m1-m4 run at the HBM roofline).", ""]
     convs = [k for k in M if k["name"].startswith("conv_") or k["name"].startswith("sppf")]
-    LY = layers()[1:]
+    LY = name_ops(json.load(open(os.path.join(P, "r1_ops.json"))))
     out += ["Per layer (network order; `hw` = output side, tensor % = `sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed`):", "",
             "| layer | kernel | hw | cin | cout | k | s | us | TFLOP/s | tensor % | DRAM MB | DRAM TB/s | L2 MB | smem KB |", "|---|---|---|---|---|---|---|---|---|---|---|---|---|---|"]
     if len(convs) == len(LY):
         for k, d in zip(convs, LY):
-            name, hw, cin, cout, kk, s = d
+            name, hw, cin, cout, kk, s, flf = d
             t = k["gpu__time_duration.sum"] / 1e3
             if name == "POOL":
                 out.append(f"| SPPF pool | `{k['name']}` | 20 | 128 | 384 | 5 | 1 | {t:.1f} | | | | | | |")
                 continue
-            fl = 2.0 * frames * hw * hw * kk * kk * cin * cout
+            fl = flf * frames
             dm = (k["dram__bytes_read.sum"] + k["dram__bytes_write.sum"]) / 1e6
             out.append(f"| {name} | `{k['name'].replace('_kernel', '')}` | {hw} | {cin} | {cout} | {kk} | {s} | {t:.1f} | {fl/t/1e6:.0f} | "
                        f"{k['sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed']:.1f} | {dm:.0f} | {dm/t:.2f} | {k['lts__t_bytes.sum']/1e6:.0f} | "
