@@ -20,6 +20,8 @@
  *   irmv_pnp_create           <- PnPSolver::PnPSolver            src/pnp_solver.cpp:7-34
  *   irmv_pnp_solve            <- PnPSolver::solvePnP             src/pnp_solver.cpp:36-52
  *   irmv_pnp_distance_to_center <- calculateDistanceToCenter     src/pnp_solver.cpp:54-59
+ *   irmv_extract_armors       <- IrmDetector::extract_armors     src/irm_detector.cpp:292-355
+ *                                (+ Light / Armor constructors, include/irmv_detection/armor.hpp:11-77)
  *   irmv_engine_detect_batch / irmv_pnp_solve_batch: batch forms of the same calls for the
  *   multi-frame configs of BASELINE.json (the reference is batch-1 only).
  */
@@ -82,6 +84,31 @@ typedef struct irmv_engine_config {
                              * output is then materialised and readable through irmv_engine_read_tensor) */
 } irmv_engine_config;
 
+/* One armor as IrmDetector::extract_armors builds it (src/irm_detector.cpp:292-355): slot i of a frame
+ * belongs to detection i; valid == 0 when the detection's ROI does not hold two light bars that pass
+ * the filters.  pts = the PnP image points in PnPSolver::solvePnP's order (src/pnp_solver.cpp:41-44):
+ * left.bottom, left.top, right.top, right.bottom, pixels of the rotated source frame. */
+typedef struct irmv_armor {
+  float pts[8];
+  float center[2];   /* Armor::center, include/irmv_detection/armor.hpp:67 */
+  float score;       /* Armor::confidence */
+  int32_t class_id;  /* Armor::armor_class */
+  int32_t size;      /* ArmorSize: 0 SMALL, 1 LARGE */
+  int32_t valid;
+} irmv_armor;
+
+/* Node parameters of the light / armor filters (src/irm_detector.cpp:152,162-173). */
+typedef struct irmv_armor_params {
+  int32_t binary_threshold;            /* 150 */
+  float light_min_ratio;               /* 0.1  (Light::is_light takes floats, armor.hpp:31) */
+  float light_max_ratio;               /* 0.4 */
+  float light_max_angle;               /* 40 degrees */
+  double min_small_center_distance;    /* 0.8 */
+  double max_small_center_distance;    /* 3.2 */
+  double min_large_center_distance;    /* 3.2 */
+  double max_large_center_distance;    /* 5.5 */
+} irmv_armor_params;
+
 typedef struct irmv_engine irmv_engine;
 typedef struct irmv_pnp irmv_pnp;
 
@@ -122,6 +149,23 @@ int irmv_engine_enable_pnp(irmv_engine *e, const double K[9], const double D[5],
                            float corner_sy);
 /* rvecs/tvecs: nframes*max_det*3 doubles; slot i of frame f is valid when i < counts[f]. */
 int irmv_engine_fetch_poses(irmv_engine *e, int nframes, double *rvecs, double *tvecs, uint8_t *ok);
+/* ---- light bars -> armors (IrmDetector::extract_armors, src/irm_detector.cpp:292-355) ---------- */
+int irmv_armor_params_default(irmv_armor_params *p);
+/* Stage entry: nframes frames as the camera wrote them (the kernel reads the rotated view itself),
+ * boxes[nframes*max_det] in source pixels with counts[nframes] valid entries per frame (what detect()
+ * returns); out[nframes*max_det], slot-aligned with boxes.  prm == NULL: defaults. */
+int irmv_extract_armors(const uint8_t *frames, int frames_on_device, int nframes, int src_w, int src_h, int chan_order,
+                        int rotate180, const irmv_bbox *boxes, const int *counts, int max_det,
+                        const irmv_armor_params *prm, int device, irmv_armor *out);
+/* Fuse the stage into the replay, between NMS and PnP: with irmv_engine_enable_pnp the pose stage then
+ * solves on the armor corners (scaled by corner_sx/sy) instead of the box corners, and ok[] is 0 for
+ * detections without an armor -- the whole of message_callback's per-frame work
+ * (src/irm_detector.cpp:181-208) in one graph. */
+int irmv_engine_enable_armors(irmv_engine *e, const irmv_armor_params *prm);
+/* out: nframes*max_det armors of the last detect/detect_batch/sync (ticket < 0) or of a collected
+ * pipelined batch (its ticket). */
+int irmv_engine_fetch_armors(irmv_engine *e, int ticket, int nframes, irmv_armor *out);
+
 /* Pipelined hand-off for host-resident batches -- the B200 form of the overlap the reference gets
  * from its TripleBuffer (camera thread fills the next slot while detect() runs on the previous one,
  * reference README.md:60-63, src/irm_detector.cpp:68-72).  submit queues H2D copy (dedicated copy

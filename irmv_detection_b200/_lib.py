@@ -22,6 +22,18 @@ class Bbox(C.Structure):
     _fields_ = [("xyxy", C.c_float * 4), ("score", C.c_float), ("class_id", C.c_int32)]
 
 
+class Armor(C.Structure):
+    _fields_ = [("pts", C.c_float * 8), ("center", C.c_float * 2), ("score", C.c_float), ("class_id", C.c_int32),
+                ("size", C.c_int32), ("valid", C.c_int32)]
+
+
+class ArmorParams(C.Structure):
+    _fields_ = [("binary_threshold", C.c_int32), ("light_min_ratio", C.c_float), ("light_max_ratio", C.c_float),
+                ("light_max_angle", C.c_float), ("min_small_center_distance", C.c_double),
+                ("max_small_center_distance", C.c_double), ("min_large_center_distance", C.c_double),
+                ("max_large_center_distance", C.c_double)]
+
+
 class EngineConfig(C.Structure):
     _fields_ = [
         ("src_width", C.c_int32), ("src_height", C.c_int32), ("chan_order", C.c_int32),
@@ -54,6 +66,11 @@ SYMBOLS = {
     "irmv_engine_stream": (_P, [_P]),
     "irmv_engine_enable_pnp": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_float, C.c_float]),
     "irmv_engine_fetch_poses": (C.c_int, [_P, C.c_int, _P, _P, _P]),
+    "irmv_armor_params_default": (C.c_int, [C.POINTER(ArmorParams)]),
+    "irmv_extract_armors": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int,
+                                      C.POINTER(ArmorParams), C.c_int, _P]),
+    "irmv_engine_enable_armors": (C.c_int, [_P, C.POINTER(ArmorParams)]),
+    "irmv_engine_fetch_armors": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "irmv_engine_profile_stages": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_float * 5)]),
     "irmv_engine_submit_batch": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_int)]),
     "irmv_engine_collect": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P]),

@@ -177,6 +177,43 @@ cudaError_t launch_score_filter(const float *scores, int B, int A, int nc, float
 cudaError_t launch_nms(NmsScratch sc, int B, int A, int nc, float iou_thr, int max_det, DetOut out,
                        cudaStream_t s);
 
+// ---------------------------------------------------------------- light bars -> armors
+// GPU form of IrmDetector::extract_armors (reference src/irm_detector.cpp:292-355): per detection,
+// ROI of the rotated frame -> gray -> threshold -> top-level outer contours -> minimum-area
+// rectangle -> light filter -> first two lights -> armor.  One CTA per detection.
+struct ArmorOut {            // == irmv_armor (include/irmv_cabi.h)
+  float pts[8];              // left.bottom, left.top, right.top, right.bottom (pixels of the rotated frame)
+  float center[2];
+  float score;
+  int32_t class_id;
+  int32_t size;              // 0 small, 1 large
+  int32_t valid;
+};
+struct ArmorParams {
+  const uint8_t *src;                   // [n] frames as the camera wrote them; used when src_indirect == null
+  const uint8_t *const *src_indirect;   // device word holding the frame base pointer (batch path)
+  int n, src_w, src_h, chan_order, rotate180;
+  const int32_t *num;                   // [n] detections per frame
+  const float *boxes;                   // [n][max_det][4] xyxy
+  const float *scores;                  // [n][max_det]
+  const int32_t *classes;               // [n][max_det]
+  int max_det;
+  float box_sx, box_sy, box_px, box_py; // box -> source pixels: (b - p) * s (engine: network pixels; 1/0 otherwise)
+  int binary_threshold;
+  float min_ratio, max_ratio, max_angle;
+  double min_small, max_small, min_large, max_large;
+  ArmorOut *out;                        // [n][max_det]
+  uint32_t *scratch;                    // bitmaps of ROIs that do not fit in shared memory
+  size_t scratch_words_per_cta;
+  int grid;
+};
+int armors_grid(int num_sms);
+size_t armors_scratch_words_per_cta(int src_w, int src_h);
+cudaError_t launch_extract_armors(const ArmorParams &p, cudaStream_t s);
+// armor corners -> PnP quads in the calibration frame; slots without an armor get a fixed valid quad
+cudaError_t launch_quads_from_armors(const ArmorOut *armors, int total, float sx, float sy, float *pts, cudaStream_t s);
+cudaError_t launch_mask_pose_ok(const ArmorOut *armors, int total, uint8_t *ok, cudaStream_t s);
+
 // ---------------------------------------------------------------- PnP
 struct PnpConsts {
   double fx, fy, cx, cy;

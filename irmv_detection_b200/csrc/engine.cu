@@ -208,6 +208,8 @@ struct Lane {
   float *pnp_pts = nullptr;                // [S*max_det][8]
   double *pnp_rvec = nullptr, *pnp_tvec = nullptr;
   uint8_t *pnp_ok = nullptr;
+  ArmorOut *armors = nullptr;              // [S*max_det], allocated by irmv_engine_enable_armors
+  uint32_t *armor_scratch = nullptr;       // per-CTA bitmaps of ROIs that do not fit in shared memory
   cudaEvent_t stage_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -270,6 +272,9 @@ struct irmv_engine {
   float *d_stem_w = nullptr, *d_stem_b = nullptr;
   PnpConsts pnp_c{};
   float pnp_sx = 1.f, pnp_sy = 1.f, pnp_px = 0.f, pnp_py = 0.f;
+  float corner_sx = 1.f, corner_sy = 1.f;   // source pixels -> calibration frame (irmv_engine_enable_pnp)
+  bool armors_on = false;                   // light-bar extraction between NMS and PnP
+  irmv_armor_params armor_prm{};
   int last_slot = -1;
   int last_n = 0;
 };
@@ -604,7 +609,37 @@ int issue_replay(irmv_engine *e, Lane &ln, int n, cudaStream_t st, int *launches
   DetOut out{ln.det.num(), ln.det.boxes(), ln.det.scores(), ln.det.classes(), ln.det.index()};
   IRMV_CUDA(launch_nms(ln.nms, n, kNumAnchors, e->nc, e->cfg.iou_thr, e->cfg.max_det, out, st)); ++cnt;
   if (mark(3)) return 1;
-  if (e->pnp_on) {
+  if (e->armors_on) {
+    // reference message_callback: extract_armors(get_rotated_image(), bboxes), then solvePnP per armor
+    // (src/irm_detector.cpp:183,204-208)
+    int pad_x, pad_y, new_w, new_h;
+    letterbox_geometry(e->cfg.src_width, e->cfg.src_height, e->cfg.resize_mode, &pad_x, &pad_y, &new_w, &new_h);
+    ArmorParams ap{};
+    ap.src = nullptr; ap.src_indirect = ln.src_word;
+    ap.n = n; ap.src_w = e->cfg.src_width; ap.src_h = e->cfg.src_height;
+    ap.chan_order = e->cfg.chan_order; ap.rotate180 = e->cfg.rotate180;
+    ap.num = ln.det.num(); ap.boxes = ln.det.boxes(); ap.scores = ln.det.scores(); ap.classes = ln.det.classes();
+    ap.max_det = e->cfg.max_det;
+    ap.box_sx = (float)e->cfg.src_width / new_w; ap.box_sy = (float)e->cfg.src_height / new_h;   // parse()'s scale
+    ap.box_px = (float)pad_x; ap.box_py = (float)pad_y;
+    const irmv_armor_params &q = e->armor_prm;
+    ap.binary_threshold = q.binary_threshold;
+    ap.min_ratio = q.light_min_ratio; ap.max_ratio = q.light_max_ratio; ap.max_angle = q.light_max_angle;
+    ap.min_small = q.min_small_center_distance; ap.max_small = q.max_small_center_distance;
+    ap.min_large = q.min_large_center_distance; ap.max_large = q.max_large_center_distance;
+    ap.out = ln.armors; ap.scratch = ln.armor_scratch;
+    ap.scratch_words_per_cta = armors_scratch_words_per_cta(e->cfg.src_width, e->cfg.src_height);
+    ap.grid = armors_grid(e->num_sms);
+    IRMV_CUDA(launch_extract_armors(ap, st)); ++cnt;
+    if (e->pnp_on) {
+      const int total = n * e->cfg.max_det;
+      IRMV_CUDA(launch_quads_from_armors(ln.armors, total, e->corner_sx, e->corner_sy, ln.pnp_pts, st));
+      PnpOut po{ln.pnp_rvec, ln.pnp_tvec, ln.pnp_ok, nullptr, nullptr, nullptr, nullptr};
+      IRMV_CUDA(launch_pnp(e->pnp_c, ln.pnp_pts, total, 0, po, st));
+      IRMV_CUDA(launch_mask_pose_ok(ln.armors, total, ln.pnp_ok, st));
+      cnt += 3;
+    }
+  } else if (e->pnp_on) {
     const int total = n * e->cfg.max_det;
     quads_from_dets_kernel<<<(total + 127) / 128, 128, 0, st>>>(ln.det.num(), ln.det.boxes(), n, e->cfg.max_det,
                                                                e->pnp_sx, e->pnp_sy, e->pnp_px, e->pnp_py, ln.pnp_pts);
@@ -617,6 +652,10 @@ int issue_replay(irmv_engine *e, Lane &ln, int n, cudaStream_t st, int *launches
   if (launches) *launches = cnt;
   return 0;
 }
+
+static_assert(sizeof(ArmorOut) == sizeof(irmv_armor) && sizeof(irmv_armor) == 56, "ArmorOut mirrors irmv_armor");
+// byte offset of the armor block inside a pinned result set (after num, boxes, scores, classes, index, poses)
+size_t armors_offset(size_t B, size_t md) { return (B * 4 + B * md * 28 + B * md * 49 + 63) & ~(size_t)63; }
 
 int run_replay(irmv_engine *e, Lane &ln, int n) {
   if (!e->cfg.use_graph) return issue_replay(e, ln, n, ln.stream, &ln.launches_per_replay);
@@ -698,6 +737,9 @@ int enqueue(irmv_engine *e, const uint8_t *frames_dev, int n, const uint8_t *fra
       o += B * md * 24;
       IRMV_CUDA(cudaMemcpyAsync(h + o + (size_t)f0 * md, ln.pnp_ok, (size_t)nf * md, cudaMemcpyDeviceToHost, ln.stream));
     }
+    if (e->armors_on)
+      IRMV_CUDA(cudaMemcpyAsync(h + armors_offset(B, md) + (size_t)f0 * md * sizeof(ArmorOut), ln.armors,
+                                (size_t)nf * md * sizeof(ArmorOut), cudaMemcpyDeviceToHost, ln.stream));
   }
   for (int l = 0; l < used; ++l) {
     IRMV_CUDA(cudaEventRecord(e->lanes[l].done, e->lanes[l].stream));
@@ -838,7 +880,7 @@ int irmv_engine_create(const char *weights_path, const irmv_engine_config *cfg, 
   }
   IRMV_CUDA(cudaMalloc((void **)&e->slot_dev, e->frame_bytes));
   const size_t md = cfg->max_det, B = cfg->max_batch;
-  size_t res_bytes = B * 4 + B * md * (16 + 4 + 4 + 4) + B * md * (24 + 24 + 1) + 64;
+  size_t res_bytes = armors_offset(B, md) + B * md * sizeof(ArmorOut) + 64;
   IRMV_CUDA(cudaHostAlloc((void **)&e->res_host, res_bytes, cudaHostAllocDefault));
   memset(e->res_host, 0, res_bytes);
   e->res_bytes = res_bytes;
@@ -1101,6 +1143,7 @@ int irmv_engine_enable_pnp(irmv_engine *e, const double K[9], const double D[5],
     e->pnp_sy = corner_sy * (float)e->cfg.src_height / (float)new_h;
     e->pnp_px = (float)pad_x; e->pnp_py = (float)pad_y;
   }
+  e->corner_sx = corner_sx; e->corner_sy = corner_sy;
   e->pnp_on = true;
   IRMV_CUDA(cudaSetDevice(e->cfg.device));
   IRMV_CUDA(cudaDeviceSynchronize());
@@ -1120,6 +1163,106 @@ int irmv_engine_fetch_poses(irmv_engine *e, int nframes, double *rvecs, double *
   memcpy(tvecs, h + B * md * 24, (size_t)nframes * md * 24);
   if (ok) memcpy(ok, h + B * md * 48, (size_t)nframes * md);
   return 0;
+}
+
+int irmv_armor_params_default(irmv_armor_params *p) {
+  if (!p) return 1;
+  // node parameter defaults, reference src/irm_detector.cpp:152,162-173
+  p->binary_threshold = 150;
+  p->light_min_ratio = 0.1f; p->light_max_ratio = 0.4f; p->light_max_angle = 40.0f;
+  p->min_small_center_distance = 0.8; p->max_small_center_distance = 3.2;
+  p->min_large_center_distance = 3.2; p->max_large_center_distance = 5.5;
+  return 0;
+}
+
+int irmv_engine_enable_armors(irmv_engine *e, const irmv_armor_params *prm) {
+  if (!e) { set_error("bad argument"); return 1; }
+  if (prm) e->armor_prm = *prm; else irmv_armor_params_default(&e->armor_prm);
+  IRMV_CUDA(cudaSetDevice(e->cfg.device));
+  IRMV_CUDA(cudaDeviceSynchronize());
+  const size_t slots = (size_t)e->S * e->cfg.max_det;
+  const size_t words = armors_scratch_words_per_cta(e->cfg.src_width, e->cfg.src_height) * (size_t)armors_grid(e->num_sms);
+  for (auto &ln : e->lanes) {
+    if (!ln.armors) {
+      if (!lane_alloc(ln, (void **)&ln.armors, slots * sizeof(ArmorOut)) || !lane_alloc(ln, (void **)&ln.armor_scratch, words * 4)) return 3;
+      IRMV_CUDA(cudaMemset(ln.armors, 0, slots * sizeof(ArmorOut)));
+    }
+    for (auto &g : ln.graphs) cudaGraphExecDestroy(g.second);   // the pipeline changed: drop captured graphs
+    ln.graphs.clear();
+  }
+  e->armors_on = true;
+  return 0;
+}
+
+int irmv_engine_fetch_armors(irmv_engine *e, int ticket, int nframes, irmv_armor *out) {
+  if (!e || !out || nframes < 1 || nframes > e->cfg.max_batch) { set_error("bad argument"); return 1; }
+  if (!e->armors_on) { set_error("armor stage not enabled"); return 2; }
+  const size_t md = e->cfg.max_det, B = e->cfg.max_batch;
+  const uint8_t *h = ticket < 0 ? e->res_host : e->sets[ticket % kSets].res_host;
+  if (!h) { set_error("nothing was submitted under this ticket"); return 2; }
+  memcpy(out, h + armors_offset(B, md), (size_t)nframes * md * sizeof(irmv_armor));
+  return 0;
+}
+
+// Stand-alone stage entry: extract_armors over n frames and their detections (boxes in source pixels).
+int irmv_extract_armors(const uint8_t *frames, int frames_on_device, int nframes, int src_w, int src_h, int chan_order,
+                        int rotate180, const irmv_bbox *boxes, const int *counts, int max_det,
+                        const irmv_armor_params *prm, int device, irmv_armor *out) {
+  if (!frames || !boxes || !counts || !out || nframes < 1 || max_det < 1 || src_w < 2 || src_h < 2) { set_error("bad argument"); return 1; }
+  irmv_armor_params q;
+  if (prm) q = *prm; else irmv_armor_params_default(&q);
+  IRMV_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  IRMV_CUDA(cudaGetDeviceProperties(&prop, device));
+  const size_t fb = (size_t)src_w * src_h * (chan_order >= 2 ? 1 : 3), slots = (size_t)nframes * max_det;
+  uint8_t *d_frames = nullptr;
+  int32_t *d_num = nullptr, *d_cls = nullptr;
+  float *d_boxes = nullptr, *d_scores = nullptr;
+  ArmorOut *d_out = nullptr;
+  uint32_t *d_scratch = nullptr;
+  std::vector<float> hb(slots * 4, 0.f), hs(slots, 0.f);
+  std::vector<int32_t> hc(slots, 0);
+  for (size_t i = 0; i < slots; ++i) {
+    for (int k = 0; k < 4; ++k) hb[i * 4 + k] = boxes[i].xyxy[k];
+    hs[i] = boxes[i].score; hc[i] = boxes[i].class_id;
+  }
+  const int grid = armors_grid(prop.multiProcessorCount);
+  const size_t wpc = armors_scratch_words_per_cta(src_w, src_h);
+  int rc = 0;
+  auto body = [&]() -> int {
+    if (!frames_on_device) {
+      IRMV_CUDA(cudaMalloc((void **)&d_frames, fb * nframes));
+      IRMV_CUDA(cudaMemcpy(d_frames, frames, fb * nframes, cudaMemcpyHostToDevice));
+    }
+    IRMV_CUDA(cudaMalloc((void **)&d_num, (size_t)nframes * 4));
+    IRMV_CUDA(cudaMalloc((void **)&d_cls, slots * 4));
+    IRMV_CUDA(cudaMalloc((void **)&d_boxes, slots * 16));
+    IRMV_CUDA(cudaMalloc((void **)&d_scores, slots * 4));
+    IRMV_CUDA(cudaMalloc((void **)&d_out, slots * sizeof(ArmorOut)));
+    IRMV_CUDA(cudaMalloc((void **)&d_scratch, wpc * grid * 4));
+    IRMV_CUDA(cudaMemcpy(d_num, counts, (size_t)nframes * 4, cudaMemcpyHostToDevice));
+    IRMV_CUDA(cudaMemcpy(d_cls, hc.data(), slots * 4, cudaMemcpyHostToDevice));
+    IRMV_CUDA(cudaMemcpy(d_boxes, hb.data(), slots * 16, cudaMemcpyHostToDevice));
+    IRMV_CUDA(cudaMemcpy(d_scores, hs.data(), slots * 4, cudaMemcpyHostToDevice));
+    IRMV_CUDA(cudaMemset(d_out, 0, slots * sizeof(ArmorOut)));
+    ArmorParams ap{};
+    ap.src = frames_on_device ? frames : d_frames; ap.src_indirect = nullptr;
+    ap.n = nframes; ap.src_w = src_w; ap.src_h = src_h; ap.chan_order = chan_order; ap.rotate180 = rotate180;
+    ap.num = d_num; ap.boxes = d_boxes; ap.scores = d_scores; ap.classes = d_cls; ap.max_det = max_det;
+    ap.box_sx = 1.f; ap.box_sy = 1.f; ap.box_px = 0.f; ap.box_py = 0.f;
+    ap.binary_threshold = q.binary_threshold;
+    ap.min_ratio = q.light_min_ratio; ap.max_ratio = q.light_max_ratio; ap.max_angle = q.light_max_angle;
+    ap.min_small = q.min_small_center_distance; ap.max_small = q.max_small_center_distance;
+    ap.min_large = q.min_large_center_distance; ap.max_large = q.max_large_center_distance;
+    ap.out = d_out; ap.scratch = d_scratch; ap.scratch_words_per_cta = wpc; ap.grid = grid;
+    IRMV_CUDA(launch_extract_armors(ap, nullptr));
+    IRMV_CUDA(cudaDeviceSynchronize());
+    IRMV_CUDA(cudaMemcpy(out, d_out, slots * sizeof(ArmorOut), cudaMemcpyDeviceToHost));
+    return 0;
+  };
+  rc = body();
+  cudaFree(d_frames); cudaFree(d_num); cudaFree(d_cls); cudaFree(d_boxes); cudaFree(d_scores); cudaFree(d_out); cudaFree(d_scratch);
+  return rc;
 }
 
 // One eager (non-graph) replay of up to sub_batch frames on lane 0 with CUDA events between the

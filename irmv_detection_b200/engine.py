@@ -201,6 +201,18 @@ class YoloEngine:
                 "irmv_engine_fetch_poses")
         return rv, tv, ok.astype(bool)
 
+    def enable_armors(self, **params) -> None:
+        """Fuse IrmDetector::extract_armors (light bars -> armors) into every replay, between NMS and
+        PnP; keyword arguments override the node-parameter defaults (see armor_params)."""
+        prm = armor_params(**params)
+        L.check(self._lib.irmv_engine_enable_armors(self._h, C.byref(prm)), "irmv_engine_enable_armors")
+
+    def fetch_armors(self, n: int, ticket: int = -1) -> np.ndarray:
+        """Armors of the last synchronous call (or of a collected ticket): structured [n, max_det]."""
+        out = np.zeros((n, self.max_det), ARMOR_DTYPE)
+        L.check(self._lib.irmv_engine_fetch_armors(self._h, ticket, n, out.ctypes.data), "irmv_engine_fetch_armors")
+        return out
+
     def describe_ops(self):
         """Kernels of the network stage in issue order: dicts {kind, k, s, cin, cout, hw, raster, tail_cout}."""
         buf = C.create_string_buffer(16384)
@@ -326,7 +338,42 @@ class PnPSolver:
             pass
 
 
+ARMOR_DTYPE = np.dtype([("pts", np.float32, (4, 2)), ("center", np.float32, 2), ("score", np.float32),
+                        ("class_id", np.int32), ("size", np.int32), ("valid", np.int32)])
+BBOX_DTYPE = np.dtype([("xyxy", np.float32, 4), ("score", np.float32), ("class_id", np.int32)])
+
+
+def armor_params(**kw) -> "L.ArmorParams":
+    """Node parameters of the light / armor filters (reference src/irm_detector.cpp:152,162-173)."""
+    prm = L.ArmorParams()
+    L.check(L.lib().irmv_armor_params_default(C.byref(prm)), "irmv_armor_params_default")
+    for k, v in kw.items():
+        if not hasattr(prm, k):
+            raise TypeError(f"unknown armor parameter {k}")
+        setattr(prm, k, v)
+    return prm
+
+
 # ---- stage-level wrappers (parity tests) ------------------------------------------------------
+def extract_armors(frames: np.ndarray, boxes: np.ndarray, counts: np.ndarray, chan_order: int = L.CH_PASSTHROUGH,
+                   rotate180: bool = True, device: int = 0, **params) -> np.ndarray:
+    """IrmDetector::extract_armors on the GPU.  frames u8 [n,H,W,3] or [n,H,W] as the camera wrote
+    them; boxes structured BBOX_DTYPE [n, max_det] (source pixels) with counts[n] valid entries.
+    Returns ARMOR_DTYPE [n, max_det], slot-aligned with boxes."""
+    frames = np.ascontiguousarray(frames, np.uint8)
+    boxes = np.ascontiguousarray(boxes, BBOX_DTYPE)
+    counts = np.ascontiguousarray(counts, np.int32)
+    n, H, W = frames.shape[:3]
+    max_det = boxes.shape[1]
+    out = np.zeros((n, max_det), ARMOR_DTYPE)
+    prm = armor_params(**params)
+    L.check(L.lib().irmv_extract_armors(frames.ctypes.data, 0, n, W, H, chan_order, int(rotate180), boxes.ctypes.data,
+                                        counts.ctypes.data, max_det, C.byref(prm), device, out.ctypes.data),
+            "irmv_extract_armors")
+    return out
+
+
+
 def preprocess(frames: np.ndarray, chan_order: int = L.CH_PASSTHROUGH, rotate180: bool = True,
                quantize_u8: bool = True, want_rotated: bool = False, device: int = 0,
                half_pixel: bool = False, letterbox: bool = False):

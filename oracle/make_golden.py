@@ -7,6 +7,8 @@
                    against cv2.dnn.NMSBoxesBatched)
   pre_golden.npz   rm_test.jpg -> sha256 of the FP16 preprocess output per mode + a 16x16 crop
   net_golden.npz   rm_test.jpg, seed-0 weights -> top-32 scores/boxes of the FP32 oracle
+  armor_golden.npz seeded light-bar scenes -> armors of the reference's extract_armors written with
+                   the cv2 calls themselves (oracle/armor_ref.extract_armors_cv2)
 
 Run:  python -m oracle.make_golden
 """
@@ -81,5 +83,24 @@ def main():
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
 
+def armor_golden():
+    """Known answers for the light/armor extraction, produced by the cv2 form of the reference's
+    function (oracle/armor_ref.extract_armors_cv2) on seeded synthetic scenes."""
+    from oracle import armor_ref as A
+    rec = {}
+    for seed in (0, 1, 2):
+        img, boxes, scores, classes = A.synth_armor_scene(8, seed)
+        arms = A.extract_armors_cv2(img, boxes, scores, classes)
+        rec[f"boxes{seed}"] = boxes
+        rec[f"scores{seed}"] = scores
+        rec[f"classes{seed}"] = classes
+        rec[f"index{seed}"] = np.array([a.bbox_index for a in arms], np.int32)
+        rec[f"size{seed}"] = np.array([a.size for a in arms], np.int32)
+        rec[f"pts{seed}"] = np.stack([a.pts for a in arms]).astype(np.float32)
+        rec[f"center{seed}"] = np.stack([a.center for a in arms]).astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "armor_golden.npz"), **rec)
+
+
 if __name__ == "__main__":
     main()
+    armor_golden()

@@ -612,6 +612,159 @@ def test_fused_stem_input_pixels_exact(base_image, tmp_path, chan):
     eng.close()
 
 
+# ------------------------------------------------------------------------- light bars -> armors
+ARMOR_TOL_PX = 1e-2     # corner / centre agreement with cv2 (FP32 rectangle arithmetic on both sides)
+
+
+def _check_armors(got, image, boxes, scores, classes, prm):
+    """got: ARMOR_DTYPE[max_det] of one frame.  Reference = the reference's function written with the
+    cv2 calls; a box may only differ where the restatement reports an ambiguous minimum-area rectangle
+    (two different rectangles of equal area: OpenCV's pick depends on rounding inside its calipers)."""
+    from oracle import armor_ref as A
+    ref = {a.bbox_index: a for a in A.extract_armors_cv2(image, boxes, scores, classes, prm)}
+    bad = []
+    for i in range(len(boxes)):
+        g = got[i]
+        if bool(g["valid"]) != (i in ref):
+            bad.append(i)
+            continue
+        if i in ref:
+            r = ref[i]
+            if (int(g["size"]) != r.size or np.abs(g["pts"] - r.pts).max() > ARMOR_TOL_PX or
+                    np.abs(g["center"] - r.center).max() > ARMOR_TOL_PX):
+                bad.append(i)
+            else:
+                assert int(g["class_id"]) == r.class_id and abs(float(g["score"]) - r.score) < 1e-7
+    assert not got[len(boxes):]["valid"].any()
+    if bad:
+        amb = {}
+        sub = np.asarray(boxes)[bad]
+        A.extract_armors(image, sub, np.asarray(scores)[bad], np.asarray(classes)[bad], prm, ambiguous=amb)
+        not_excused = [bad[k] for k in range(len(bad)) if k not in amb]
+        assert not not_excused, f"armor mismatch on boxes {not_excused}"
+    return len(ref), len(bad)
+
+
+def _boxes_struct(irmv, boxes, scores, classes, max_det):
+    b = np.zeros((1, max_det), irmv.BBOX_DTYPE)
+    b["xyxy"][0, :len(boxes)] = boxes
+    b["score"][0, :len(boxes)] = scores
+    b["class_id"][0, :len(boxes)] = classes
+    return b
+
+
+@pytest.mark.parametrize("seed,rotate", [(0, True), (1, True), (2, False)])
+def test_extract_armors_golden_scenes(seed, rotate):
+    """Seeded light-bar scenes: armors of the CUDA stage vs the cv2 form of the reference's function and
+    the committed golden vectors."""
+    _cuda()
+    import irmv_detection_b200 as irmv
+    from oracle import armor_ref as A, preprocess_ref as PR
+    img, boxes, scores, classes = A.synth_armor_scene(8, seed)
+    frame = PR.rot180(img) if rotate else img                  # what the camera wrote
+    got = irmv.extract_armors(frame[None], _boxes_struct(irmv, boxes, scores, classes, 16), [len(boxes)],
+                              rotate180=rotate)[0]
+    n_ref, n_bad = _check_armors(got, img, boxes, scores, classes, A.ArmorParams())
+    assert n_bad == 0
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "armor_golden.npz"))
+    idx = np.nonzero(got["valid"])[0]
+    assert idx.tolist() == g[f"index{seed}"].tolist()
+    assert got["size"][idx].tolist() == g[f"size{seed}"].tolist()
+    assert np.abs(got["pts"][idx] - g[f"pts{seed}"]).max() < ARMOR_TOL_PX
+
+
+def _blob_scene(seed, h=1024, w=1280, n_blobs=260):
+    import cv2
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    img[rng.random((h, w)) < 0.97] //= 3                        # speckle: sparse bright pixels and tiny components
+    for _ in range(n_blobs):
+        c = (float(rng.uniform(0, w)), float(rng.uniform(0, h)))
+        size = (float(rng.uniform(2, 14)), float(rng.uniform(4, 60)))
+        box = cv2.boxPoints((c, size, float(rng.uniform(-60, 60))))
+        v = int(rng.integers(150, 256))
+        if rng.random() < 0.3:                                  # a ring: components inside it are not external
+            cv2.ellipse(img, (int(c[0]), int(c[1])), (int(size[1]), int(size[1] * 0.6) + 2), 0, 0, 360, (v, v, v), 2)
+        else:
+            cv2.fillConvexPoly(img, np.round(box).astype(np.int32), (v, v, v))
+    return img
+
+
+@pytest.mark.parametrize("seed,chan,rotate", [(3, 0, True), (4, 1, False), (5, 2, True), (6, 4, True)])
+def test_extract_armors_stress_vs_cv2(seed, chan, rotate):
+    """Speckle + blobs + rings with permissive light filters (most contours with >= 5 vertices become
+    lights, so contour order, the vertex count and the external-only rule all decide the answer), boxes
+    of every size including off-frame, degenerate and whole-frame ones (global-scratch bitmaps)."""
+    _cuda()
+    import irmv_detection_b200 as irmv
+    from oracle import armor_ref as A, preprocess_ref as PR
+    rng = np.random.default_rng(100 + seed)
+    scene = _blob_scene(seed)
+    if chan >= 2:
+        frame = PR.mosaic_from_rgb(PR.rot180(scene) if rotate else scene, chan)
+    else:
+        frame = np.ascontiguousarray(PR.rot180(scene) if rotate else scene)
+    image = A.rotated_image(frame, chan, rotate)                # the view the reference thresholds
+    n = 90
+    cx, cy = rng.uniform(0, 1280, n), rng.uniform(0, 1024, n)
+    bw, bh = rng.uniform(4, 260, n), rng.uniform(4, 220, n)
+    boxes = np.stack([cx - bw / 2, cy - bh / 2, cx + bw / 2, cy + bh / 2], 1).astype(np.float32)
+    boxes[0] = [-1e9, -1e9, 1e9, 1e9]                           # whole frame
+    boxes[1] = [-30, -30, 700, 600]
+    boxes[2] = [100, 100, 100.5, 180]                           # zero width after truncation
+    boxes[3] = [300, 300, 200, 400]                             # inverted
+    boxes[4] = [1279.5, 1000, 1400, 1100]
+    scores = rng.uniform(0.25, 1, n).astype(np.float32)
+    classes = rng.integers(0, 16, n).astype(np.int32)          # 14, 15 -> UNKNOWN
+    kw = dict(binary_threshold=140 if chan < 2 else 110, light_min_ratio=0.02, light_max_ratio=0.9, light_max_angle=80.0)
+    prm = A.ArmorParams(binary_threshold=kw["binary_threshold"], light_min_ratio=0.02, light_max_ratio=0.9,
+                        light_max_angle=80.0, min_small_center_distance=0.1, max_small_center_distance=3.2,
+                        min_large_center_distance=3.2, max_large_center_distance=50.0)
+    got = irmv.extract_armors(frame[None], _boxes_struct(irmv, boxes, scores, np.minimum(classes, 14), 100), [n],
+                              chan_order=chan, rotate180=rotate, min_small_center_distance=0.1,
+                              max_large_center_distance=50.0, **kw)[0]
+    n_ref, n_bad = _check_armors(got, image, boxes, scores, np.minimum(classes, 14), prm)
+    assert n_ref >= 20, n_ref
+    assert n_bad <= 6, n_bad                                     # excused (ambiguous rectangle) boxes are rare
+
+
+def test_engine_armor_stage_feeds_pnp(weights_seed0):
+    """enable_armors + enable_pnp: the replay runs detect -> extract_armors -> solvePnP like
+    IrmDetector::message_callback (src/irm_detector.cpp:181-208); armors must equal the stand-alone
+    stage on the engine's own boxes, poses must equal the PnP oracle on the armor corners."""
+    _cuda()
+    import irmv_detection_b200 as irmv
+    from oracle import armor_ref as A, pnp_ref as P, preprocess_ref as PR
+    scenes = [A.synth_armor_scene(10, s)[0] for s in (7, 8, 9)]
+    frames = np.stack([PR.rot180(s) for s in scenes])
+    eng = irmv.YoloEngine(weights_seed0, (1280, 1024), max_batch=3)
+    eng.enable_armors(binary_threshold=150)
+    eng.enable_pnp(P.K_DEFAULT, P.D_DEFAULT, (0.5, 480 / 1024))
+    counts, dets = eng.detect_batch_arrays(frames)
+    counts, dets = counts.copy(), dets.copy()
+    arm = eng.fetch_armors(3)
+    rv, tv, ok = eng.fetch_poses(3)
+    alone = irmv.extract_armors(frames, dets, counts)
+    n_valid = 0
+    for f in range(3):
+        k = int(counts[f])
+        assert np.array_equal(arm[f]["valid"][:k], alone[f]["valid"][:k])
+        v = np.nonzero(arm[f]["valid"][:k])[0]
+        assert np.array_equal(arm[f]["pts"][v], alone[f]["pts"][v])
+        _check_armors(arm[f], scenes[f], dets[f]["xyxy"][:k], dets[f]["score"][:k], dets[f]["class_id"][:k], A.ArmorParams())
+        assert not ok[f, :k][arm[f]["valid"][:k] == 0].any()
+        if len(v):
+            pts = arm[f]["pts"][v] * np.array([0.5, 480 / 1024], np.float32)
+            r1, t1, r2, t2, e1, e2 = P.solve_ippe(pts, both=True)
+            clear = ok[f, v] & np.isfinite(r1).all(1) & (np.abs(e1 - e2) > 1e-6 * np.maximum(e1, e2))
+            rel = np.linalg.norm(rv[f, v][clear] - r1[clear], axis=1) / np.linalg.norm(r1[clear], axis=1)
+            assert rel.size == 0 or rel.max() < PNP_REL_TOL
+            n_valid += len(v)
+    eng.close()
+    # (random-init weights put boxes anywhere; the count only documents how much of the path ran)
+    print("armors from engine boxes:", n_valid)
+
+
 def test_cpp_drop_in_classes(base_image, weights_seed0, tmp_path):
     """The C++ YoloEngine / PnPSolver / TripleBuffer with the reference's class interfaces
     (include/irmv_detection/*.hpp), exercised by a program shaped like the reference's

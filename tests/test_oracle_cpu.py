@@ -205,6 +205,91 @@ def test_network_oracle_vs_opencv_dnn(base_image, weights_seed0, tmp_path):
     assert np.abs(out - ref).max() < 5e-3
 
 
+# ----------------------------------------------------------------------------- light bars / armors
+def test_armor_gray_is_cv2_bgr2gray():
+    import cv2
+    from oracle import armor_ref as A
+    img = np.random.default_rng(3).integers(0, 256, (120, 200, 3), dtype=np.uint8)
+    assert np.array_equal(A.gray_bgr2gray(img), cv2.cvtColor(img, cv2.COLOR_BGR2GRAY))
+
+
+def test_armor_contours_match_cv2_point_for_point():
+    """Top-level outer borders, CHAIN_APPROX_SIMPLE vertices and OpenCV's contour order, on noise,
+    dilated noise, rings with nested blobs, single rows/columns and empty images."""
+    import cv2
+    from oracle import armor_ref as A
+    rng = np.random.default_rng(1)
+    total = 0
+    for t in range(160):
+        h, w = int(rng.integers(1, 40)), int(rng.integers(1, 50))
+        b = rng.random((h, w)) < rng.choice([0.0, 0.1, 0.3, 0.5, 0.7, 0.9, 1.0])
+        if t % 3 == 0:
+            b = cv2.dilate(b.astype(np.uint8), np.ones((3, 3), np.uint8)) > 0
+        if t % 5 == 0 and h > 10 and w > 10:
+            b = np.zeros((h, w), bool)
+            cv2.circle(b.view(np.uint8), (w // 2, h // 2), min(h, w) // 2 - 1, 1, 2)
+            b[h // 2 - 1:h // 2 + 1, w // 2 - 1:w // 2 + 1] = True      # a blob inside the ring: not external
+        ref, _ = cv2.findContours((b * 255).astype(np.uint8), cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
+        mine = A.find_external_contours(b)
+        assert len(ref) == len(mine), t
+        for r, m in zip(ref, mine):
+            assert np.array_equal(r.reshape(-1, 2), m), t
+        total += len(ref)
+    assert total > 500
+
+
+def test_armor_min_area_rect_matches_cv2():
+    import cv2
+    from oracle import armor_ref as A
+    rng = np.random.default_rng(2)
+    n = amb = 0
+    for _ in range(600):
+        pts = rng.integers(0, rng.integers(3, 60), (int(rng.integers(3, 30)), 2)).astype(np.int32)
+        c, cen, a = A.min_area_rect(pts)
+        if a:
+            amb += 1
+            continue
+        rect = cv2.minAreaRect(pts.reshape(-1, 1, 2))
+        bp = cv2.boxPoints(rect)
+        d = np.abs(c[:, None, :] - bp[None, :, :]).sum(-1)
+        assert d.min(1).max() < 1e-3 and np.abs(cen - np.array(rect[0])).max() < 1e-3
+        n += 1
+    assert n > 500 and amb < 100
+
+
+def test_extract_armors_restatement_matches_cv2_and_golden():
+    from oracle import armor_ref as A
+    g = np.load(os.path.join(ROOT, "tests", "golden", "armor_golden.npz"))
+    for seed in (0, 1, 2):
+        img, boxes, scores, classes = A.synth_armor_scene(8, seed)
+        assert np.array_equal(boxes, g[f"boxes{seed}"])
+        a1 = A.extract_armors(img, boxes, scores, classes)
+        a2 = A.extract_armors_cv2(img, boxes, scores, classes)
+        assert [a.bbox_index for a in a1] == [a.bbox_index for a in a2] == g[f"index{seed}"].tolist()
+        assert [a.size for a in a1] == [a.size for a in a2] == g[f"size{seed}"].tolist()
+        for k, (x, y) in enumerate(zip(a1, a2)):
+            assert np.abs(x.pts - y.pts).max() < 1e-3 and np.abs(x.center - y.center).max() < 1e-3
+            assert np.abs(y.pts - g[f"pts{seed}"][k]).max() < 1e-4
+    assert len(g["index2"]) == 7          # one detection of scene 2 holds no valid light pair
+
+
+def test_extract_armors_roi_edge_cases():
+    """Boxes outside / across the frame, empty after truncation, and NaN (src/irm_detector.cpp:299-304)."""
+    from oracle import armor_ref as A
+    img, boxes, scores, classes = A.synth_armor_scene(2, 5)
+    odd = np.array([[-50, -40, 30, 20], [1270, 1000, 1400, 1100], [100, 100, 100.5, 180], [300, 300, 200, 400],
+                    [np.nan, 0, 50, 50], [-1e9, -1e9, 1e9, 1e9]], np.float32)
+    b = np.concatenate([boxes, odd])
+    s = np.concatenate([scores, np.full(len(odd), 0.5, np.float32)])
+    c = np.concatenate([classes, np.zeros(len(odd), np.int32)])
+    a1 = A.extract_armors(img, b, s, c)
+    a2 = A.extract_armors_cv2(img, b, s, c)
+    assert [a.bbox_index for a in a1] == [a.bbox_index for a in a2]
+    assert A.roi_of(odd[2], 1280, 1024) is None and A.roi_of(odd[3], 1280, 1024) is None
+    assert A.roi_of(odd[4], 1280, 1024) is None
+    assert A.roi_of(odd[5], 1280, 1024)[:4] == (0, 0, 1280, 1024)
+
+
 # ----------------------------------------------------------------------------------- boundary
 def test_cabi_exports_every_declared_symbol():
     from irmv_detection_b200 import _lib
@@ -221,7 +306,9 @@ def test_cabi_exports_every_declared_symbol():
     assert lib.irmv_engine_config_default(C.byref(cfg)) == 0
     assert (cfg.src_width, cfg.src_height, cfg.rotate180, cfg.max_det) == (1280, 1024, 1, 100)
     assert abs(cfg.score_thr - 0.25) < 1e-7 and abs(cfg.iou_thr - 0.45) < 1e-7
-    assert C.sizeof(_lib.Bbox) == 24
+    assert C.sizeof(_lib.Bbox) == 24 and C.sizeof(_lib.Armor) == 56 and C.sizeof(_lib.ArmorParams) == 48
+    prm = _lib.ArmorParams()
+    assert lib.irmv_armor_params_default(C.byref(prm)) == 0 and prm.binary_threshold == 150
 
 
 def test_missing_weights_raises(tmp_path):
