@@ -39,6 +39,9 @@ public:
   double get_profiling_time() const { return inference_time_ms_; }
   const cv::Mat & get_rotated_image() const;
   uint8_t * get_src_image_buffer() const { return src_image_buffer_; }
+  // not in the reference class: the C-ABI handle, for the stages that fuse into this engine's replay
+  // (ArmorExtractor::enable, irmv_engine_enable_pnp)
+  irmv_engine * handle() const { return engine_; }
 
 private:
   irmv_engine * engine_ = nullptr;

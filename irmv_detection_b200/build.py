@@ -76,7 +76,8 @@ DROP_IN_TEST = os.path.join(HERE, "drop_in_test")
 def build_host(force: bool = False) -> str:
     """C++ drop-in classes (YoloEngine / PnPSolver with the reference signatures) + their test."""
     inc = os.path.join(os.path.dirname(HERE), "include")
-    srcs = [os.path.join(CSRC, "host", "yolo_engine.cpp"), os.path.join(CSRC, "host", "pnp_solver.cpp")]
+    srcs = [os.path.join(CSRC, "host", "yolo_engine.cpp"), os.path.join(CSRC, "host", "pnp_solver.cpp"),
+            os.path.join(CSRC, "host", "armor_extractor.cpp")]
     test_src = os.path.join(os.path.dirname(HERE), "tests", "cpp", "drop_in_test.cpp")
     deps = srcs + [test_src] + [os.path.join(inc, "irmv_detection", h) for h in os.listdir(os.path.join(inc, "irmv_detection"))]
     if not force and os.path.exists(HOST_LIB) and os.path.exists(DROP_IN_TEST) and \

@@ -32,9 +32,11 @@ namespace irmv {
 namespace {
 
 constexpr int kThreads = 128, kWarps = kThreads / 32;
-constexpr int kSmemWords = 4096;       // per bitmap: ROIs up to ~128 K padded pixels stay in shared memory
-constexpr int kMaxRows = 1088;         // rows of the per-warp row-extreme arrays (ROI height limit)
-constexpr int kHullCap = 768;          // a convex lattice polygon in a 1280 x 1088 box has < 400 vertices
+constexpr int kSmemWords = 2048;       // per bitmap: ROIs up to 64 K padded pixels keep their bitmaps in shared memory
+constexpr int kRows = 256;             // ... and up to this many rows (per-warp row-extreme arrays, hull)
+constexpr int kMaxRows = 1088;         // ROI height limit of the global-scratch path
+constexpr int kHullSmem = 2 * kRows + 2, kHullGlobal = 2 * kMaxRows + 2;   // a row adds at most two hull vertices
+constexpr int kScratchSlots = 64;      // global scratch slots shared by the CTAs that meet a large ROI
 constexpr unsigned kFull = 0xffffffffu;
 
 struct LightRec {
@@ -43,19 +45,31 @@ struct LightRec {
   unsigned key;                        // raster index of the contour's first pixel inside the padded ROI
 };
 
-struct WarpBuf {
-  short rmin[kMaxRows], rmax[kMaxRows];
-  int hull[kHullCap];                  // x | y << 16, ROI coordinates
+struct WarpBuf {                       // per warp: row extremes of the border being examined and its hull
+  short *rmin, *rmax;
+  int *hull;                           // x | y << 16, ROI coordinates
+  int hull_cap;
 };
 
 struct Shared {
   uint32_t fg[kSmemWords];
   uint32_t ext[kSmemWords];
-  WarpBuf wb[kWarps];
+  short rmin[kWarps][kRows], rmax[kWarps][kRows];
+  int hull[kWarps][kHullSmem];
   LightRec best[2];
   int nbest;
   int lock;
+  int slot;
 };
+
+// words of one global scratch slot: two whole-frame bitmaps + the per-warp arrays
+__host__ __device__ inline size_t slot_bitmap_words(int src_w, int src_h) {
+  return (((size_t)src_w + 2 + 31) / 32) * ((size_t)src_h + 2);
+}
+__host__ __device__ inline size_t slot_warp_words() { return (size_t)kMaxRows + kHullGlobal; }   // 2 short arrays + hull
+__host__ __device__ inline size_t slot_words(int src_w, int src_h) {
+  return 2 * slot_bitmap_words(src_w, src_h) + kWarps * slot_warp_words() + 16;
+}
 
 __device__ __forceinline__ int reflect101(int i, int n) {
   if (i < 0) i = -i;
@@ -66,36 +80,58 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 // Gray value of pixel (X, Y) of the rotated frame as cv::cvtColor(COLOR_BGR2GRAY) computes it on the
 // buffer the reference holds (memory channel 0 takes the blue weight, whatever the channel really
 // is: src/irm_detector.cpp:310; a Bayer source is demosaiced to RGB like the vendor ISP does).
-__device__ __forceinline__ int gray_at(const uint8_t *__restrict__ frame, int W, int H, int chan, int rot, int X, int Y) {
+// Branch-free, so that the loads of several pixels can be in flight together.
+template <bool BAYER>
+__device__ __forceinline__ int gray_at(const uint8_t *__restrict__ frame, int W, int H, int red_y, int red_x, int rot, int X, int Y) {
   const int sx = rot ? W - 1 - X : X, sy = rot ? H - 1 - Y : Y;
   int c0, c1, c2;
-  if (chan >= 2) {
-    int red_y = 0, red_x = 0;
-    if (chan == 3) { red_y = 1; red_x = 1; }
-    else if (chan == 4) { red_y = 0; red_x = 1; }
-    else if (chan == 5) { red_y = 1; red_x = 0; }
+  if (BAYER) {
     const int ym = reflect101(sy - 1, H), yp = reflect101(sy + 1, H);
     const int xm = reflect101(sx - 1, W), xp = reflect101(sx + 1, W);
     const uint8_t *r0 = frame + (size_t)ym * W, *r1 = frame + (size_t)sy * W, *r2 = frame + (size_t)yp * W;
-    const int c = r1[sx];
+    const int nw = r0[xm], n = r0[sx], ne = r0[xp], w = r1[xm], c = r1[sx], e = r1[xp], sw = r2[xm], s = r2[sx], se = r2[xp];
+    const int cross = (n + s + w + e + 2) >> 2, diag = (nw + ne + sw + se + 2) >> 2;
+    const int horiz = (w + e + 1) >> 1, vert = (n + s + 1) >> 1;
     const bool red_row = ((sy & 1) == red_y), red_col = ((sx & 1) == red_x);
-    if (red_row == red_col) {            // red or blue site
-      const int cross = (r0[sx] + r2[sx] + r1[xm] + r1[xp] + 2) >> 2;
-      const int diag = (r0[xm] + r0[xp] + r2[xm] + r2[xp] + 2) >> 2;
-      c1 = cross;
-      c0 = red_row ? c : diag;
-      c2 = red_row ? diag : c;
-    } else {                             // green site
-      const int horiz = (r1[xm] + r1[xp] + 1) >> 1, vert = (r0[sx] + r2[sx] + 1) >> 1;
-      c1 = c;
-      c0 = red_row ? horiz : vert;
-      c2 = red_row ? vert : horiz;
-    }
+    const bool is_r = red_row && red_col, is_b = !red_row && !red_col;
+    c1 = (is_r || is_b) ? cross : c;
+    c0 = is_r ? c : (is_b ? diag : (red_row ? horiz : vert));
+    c2 = is_b ? c : (is_r ? diag : (red_row ? vert : horiz));
   } else {
     const uint8_t *s = frame + ((size_t)sy * W + sx) * 3;
     c0 = s[0]; c1 = s[1]; c2 = s[2];
   }
   return (c0 * 3735 + c1 * 19235 + c2 * 9798 + (1 << 14)) >> 15;     // OpenCV BY15, GY15, RY15
+}
+
+// ROI -> 1-bit-per-pixel threshold bitmap, padded by one background pixel all round: a warp builds one
+// word per ballot, eight words per round with their loads issued together (clamped coordinates keep
+// the fetch branch-free).
+template <bool BAYER>
+__device__ __forceinline__ void build_bitmap(uint32_t *fg, const uint8_t *__restrict__ frame, int W, int H, int chan, int rot,
+                                             int rx, int ry, int rw, int rh, int wpr, int words, int thr, int warp, int lane) {
+  int red_y = 0, red_x = 0;
+  if (chan == 3) { red_y = 1; red_x = 1; }
+  else if (chan == 4) { red_y = 0; red_x = 1; }
+  else if (chan == 5) { red_y = 1; red_x = 0; }
+  constexpr int U = BAYER ? 4 : 8;       // a demosaiced pixel is nine loads, a packed one three
+  for (int w0 = warp * U; w0 < words; w0 += kWarps * U) {
+    int g[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int w = min(w0 + u, words - 1);
+      const int row = w / wpr, wi = w - row * wpr;
+      const int x = wi * 32 + lane - 1, y = row - 1;
+      const bool in = x >= 0 && x < rw && y >= 0 && y < rh;
+      g[u] = gray_at<BAYER>(frame, W, H, red_y, red_x, rot, rx + min(max(x, 0), rw - 1), ry + min(max(y, 0), rh - 1));
+      if (!in) g[u] = -1;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t m = __ballot_sync(kFull, g[u] > thr);
+      if (lane == 0 && w0 + u < words) fg[w0 + u] = m;
+    }
+  }
 }
 
 // Seeds `s` (subset of mask `m`) spread along the runs of ones of `m` inside one word.
@@ -107,8 +143,30 @@ __device__ __forceinline__ uint32_t fill_runs(uint32_t s, uint32_t m) {
 }
 
 // chain code of OpenCV: 0 E, 1 NE, 2 N, 3 NW, 4 W, 5 SW, 6 S, 7 SE (y down)
-__device__ __forceinline__ int dir_dx(int s) { return (int)((0x21000122u >> (4 * s)) & 3u) - 1; }
-__device__ __forceinline__ int dir_dy(int s) { return (int)((0x22210001u >> (4 * s)) & 3u) - 1; }
+// (one byte-permute each: byte s of an 8-byte table of signed offsets)
+__device__ __forceinline__ int dir_dx(int s) { return (int)(signed char)__byte_perm(0xFF000101u, 0x0100FFFFu, s); }
+__device__ __forceinline__ int dir_dy(int s) { return (int)(signed char)__byte_perm(0xFFFFFF00u, 0x01010100u, s); }
+
+// 8-neighbour mask of padded pixel (x, y): bit s = neighbour in chain-code direction s is foreground.
+// One word per row covers x-1..x+1 unless x sits on a word boundary.
+__device__ __forceinline__ uint32_t nbr8(const uint32_t *fg, int wpr, int x, int y) {
+  const int b = x & 31;
+  const uint32_t *q = fg + y * wpr + (x >> 5);
+  uint32_t r0, r1, r2;                   // bits 0..2 = x-1, x, x+1 of rows y-1, y, y+1
+  if (b >= 1 && b <= 30) {
+    r0 = (q[-wpr] >> (b - 1)) & 7u; r1 = (q[0] >> (b - 1)) & 7u; r2 = (q[wpr] >> (b - 1)) & 7u;
+  } else if (b == 0) {
+    r0 = ((q[-wpr] & 3u) << 1) | (q[-wpr - 1] >> 31);
+    r1 = ((q[0] & 3u) << 1) | (q[-1] >> 31);
+    r2 = ((q[wpr] & 3u) << 1) | (q[wpr - 1] >> 31);
+  } else {
+    r0 = (q[-wpr] >> 30) | ((q[-wpr + 1] & 1u) << 2);
+    r1 = (q[0] >> 30) | ((q[1] & 1u) << 2);
+    r2 = (q[wpr] >> 30) | ((q[wpr + 1] & 1u) << 2);
+  }
+  return (r1 >> 2) | ((r0 >> 2) << 1) | (((r0 >> 1) & 1u) << 2) | ((r0 & 1u) << 3) | ((r1 & 1u) << 4) | ((r2 & 1u) << 5) |
+         (((r2 >> 1) & 1u) << 6) | ((r2 >> 2) << 7);
+}
 
 // Suzuki-Abe outer-border walk from (x0, y0) (padded ROI coordinates).  Returns false when the
 // border holds a pixel that precedes (x0, y0) in raster order.  npts = CHAIN_APPROX_SIMPLE vertex
@@ -117,20 +175,23 @@ __device__ __forceinline__ int dir_dy(int s) { return (int)((0x22210001u >> (4 *
 template <bool RECORD>
 __device__ bool walk_border(const uint32_t *fg, int wpr, int x0, int y0, long long step_cap, int &npts, int &ymax,
                             short *rmin, short *rmax) {
-  auto bit = [&](int x, int y) -> bool { return (fg[y * wpr + (x >> 5)] >> (x & 31)) & 1u; };
-  int s = 4;
-  do { s = (s - 1) & 7; } while (s != 4 && !bit(x0 + dir_dx(s), y0 + dir_dy(s)));
+  uint32_t nb = nbr8(fg, wpr, x0, y0);
   ymax = y0;
-  if (s == 4) {                          // isolated pixel
+  if (nb == 0) {                         // isolated pixel
     npts = 1;
     if (RECORD) { rmin[0] = (short)x0; rmax[0] = (short)x0; }
     return true;
   }
+  // first neighbour clockwise from W: directions 3, 2, 1, 0, 7, 6, 5 (4 = W itself is background)
+  int s = 3;
+  while (!((nb >> s) & 1u)) s = (s - 1) & 7;
   const int x1 = x0 + dir_dx(s), y1 = y0 + dir_dy(s);
   int x3 = x0, y3 = y0, prev_s = s ^ 4, n = 0;
   for (long long it = 0; it < step_cap; ++it) {
-    int x4, y4;
-    do { s = (s + 1) & 7; x4 = x3 + dir_dx(s); y4 = y3 + dir_dy(s); } while (!bit(x4, y4));
+    // next neighbour counter-clockwise after s: rotate the mask so that direction s + 1 is bit 0
+    const uint32_t rot = ((nb | (nb << 8)) >> ((s + 1) & 7)) & 0xffu;
+    s = (s + __ffs(rot)) & 7;
+    const int x4 = x3 + dir_dx(s), y4 = y3 + dir_dy(s);
     if (y4 < y0 || (y4 == y0 && x4 < x0)) return false;
     if (s != prev_s) ++n;
     if (RECORD) {
@@ -142,6 +203,7 @@ __device__ bool walk_border(const uint32_t *fg, int wpr, int x0, int y0, long lo
     prev_s = s;
     if (x4 == x0 && y4 == y0 && x3 == x1 && y3 == y1) { npts = n; return true; }
     x3 = x4; y3 = y4; s = (s + 4) & 7;
+    nb = nbr8(fg, wpr, x3, y3);
   }
   return false;                          // safety net: never reached on a consistent bitmap
 }
@@ -153,15 +215,20 @@ __device__ __forceinline__ int cross3(int a, int b, int cx, int cy) {
 
 // Kept border -> Light (armor.hpp:15-29) -> filter (armor.hpp:31-38) -> best-two list.
 // Warp-cooperative; (x0, y0) padded ROI coordinates of the first pixel, ymax its last row.
-__device__ void process_border(Shared &sh, WarpBuf &wb, const uint32_t *fg, int wpr, int x0, int y0, int ymax,
-                               long long step_cap, float min_x, float min_y, const ArmorParams &p, int lane) {
+// need_walk: the row extremes are not in wb yet (the ownership walk ran without recording).
+__device__ void process_border(Shared &sh, const WarpBuf &wb, const uint32_t *fg, int wpr, int x0, int y0, int ymax,
+                               bool need_walk, long long step_cap, float min_x, float min_y, const ArmorParams &p, int lane) {
   const int rows = ymax - y0 + 1;
-  for (int r = lane; r < rows; r += 32) { wb.rmin[r] = 32767; wb.rmax[r] = -1; }
-  __syncwarp();
+  if (need_walk) {
+    for (int r = lane; r < rows; r += 32) { wb.rmin[r] = 32767; wb.rmax[r] = -1; }
+    __syncwarp();
+  }
   int nh = 0;
   if (lane == 0) {
-    int npts, ym;
-    walk_border<true>(fg, wpr, x0, y0, step_cap, npts, ym, wb.rmin, wb.rmax);
+    if (need_walk) {
+      int npts, ym;
+      walk_border<true>(fg, wpr, x0, y0, step_cap, npts, ym, wb.rmin, wb.rmax);
+    }
     // convex hull from the row extremes: right side downwards, then left side upwards; both chains
     // turn the same way, end points are hull vertices (extreme rows)
     int n = 0;
@@ -169,14 +236,14 @@ __device__ void process_border(Shared &sh, WarpBuf &wb, const uint32_t *fg, int 
     for (int r = 0; r < rows && !overflow; ++r) {
       const int px = wb.rmax[r] - 1, py = y0 + r - 1;
       while (n >= 2 && cross3(wb.hull[n - 2], wb.hull[n - 1], px, py) <= 0) --n;
-      if (n >= kHullCap) { overflow = true; break; }
+      if (n >= wb.hull_cap) { overflow = true; break; }
       wb.hull[n++] = px | (py << 16);
     }
     const int base = n;
     for (int r = rows - 1; r >= 0 && !overflow; --r) {
       const int px = wb.rmin[r] - 1, py = y0 + r - 1;
       while (n - base >= 2 && cross3(wb.hull[n - 2], wb.hull[n - 1], px, py) <= 0) --n;
-      if (n >= kHullCap) { overflow = true; break; }
+      if (n >= wb.hull_cap) { overflow = true; break; }
       wb.hull[n++] = px | (py << 16);
     }
     if (!overflow) {
@@ -279,7 +346,7 @@ __device__ void process_border(Shared &sh, WarpBuf &wb, const uint32_t *fg, int 
   atomicExch(&sh.lock, 0);
 }
 
-__global__ void __launch_bounds__(kThreads) extract_armors_kernel(ArmorParams p) {
+__global__ void __launch_bounds__(kThreads, 6) extract_armors_kernel(ArmorParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   Shared &sh = *reinterpret_cast<Shared *>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -288,8 +355,11 @@ __global__ void __launch_bounds__(kThreads) extract_armors_kernel(ArmorParams p)
   const size_t frame_bytes = (size_t)W * H * (bayer ? 1 : 3);
   const uint8_t *base = p.src_indirect ? *p.src_indirect : p.src;
   const int total = p.n * p.max_det;
-  for (int item = blockIdx.x; item < total; item += gridDim.x) {
-    const int f = item / p.max_det, k = item - f * p.max_det;
+  // detection-major work order: the real detections (k < num[f]) come first and spread evenly over
+  // the CTAs; the empty slots that follow only clear their flag
+  for (int it = blockIdx.x; it < total; it += gridDim.x) {
+    const int k = it / p.n, f = it - k * p.n;
+    const int item = f * p.max_det + k;
     ArmorOut *out = p.out + item;
     if (k >= p.num[f]) {
       if (tid == 0) out->valid = 0;
@@ -308,72 +378,104 @@ __global__ void __launch_bounds__(kThreads) extract_armors_kernel(ArmorParams p)
       continue;
     }
     const int PW = rw + 2, PH = rh + 2, wpr = (PW + 31) >> 5, words = PH * wpr;
-    uint32_t *fg = sh.fg, *ext = sh.ext;
-    if (words > kSmemWords) {
-      fg = p.scratch + (size_t)blockIdx.x * p.scratch_words_per_cta;
-      ext = fg + p.scratch_words_per_cta / 2;
-    }
-    if (tid == 0) { sh.nbest = 0; sh.lock = 0; }
-    const uint8_t *frame = base + (size_t)f * frame_bytes;
-    // 1. threshold bitmap, padded by one background pixel all round: a warp builds one word per ballot
-    for (int w = warp; w < words; w += kWarps) {
-      const int row = w / wpr, wi = w - row * wpr;
-      const int x = wi * 32 + lane - 1, y = row - 1;
-      bool on = false;
-      if (x >= 0 && x < rw && y >= 0 && y < rh) on = gray_at(frame, W, H, p.chan_order, p.rotate180, rx + x, ry + y) > p.binary_threshold;
-      const uint32_t m = __ballot_sync(kFull, on);
-      if (lane == 0) fg[w] = m;
-    }
-    __syncthreads();
-    // 2. exterior background: seeds on the padding, spread along runs inside each word ...
-    for (int w = tid; w < words; w += kThreads) {
-      const int row = w / wpr, wi = w - row * wpr;
-      const uint32_t m = ~fg[w];
-      uint32_t s = (row == 0 || row == PH - 1) ? kFull : 0u;
-      if (wi == 0) s |= 1u;
-      if (wi == wpr - 1) s |= kFull << ((PW - 1) & 31);
-      ext[w] = fill_runs(s & m, m);
-    }
-    __syncthreads();
-    // ... then row sweeps (down, up) by one warp until nothing changes
-    if (warp == 0) {
-      for (;;) {
-        bool changed = false;
-        for (int pass = 0; pass < 2; ++pass) {
-          for (int i = 1; i <= PH - 2; ++i) {
-            const int r = pass == 0 ? i : PH - 1 - i;
-            uint32_t *er = ext + r * wpr;
-            const uint32_t *fr = fg + r * wpr;
-            bool ch = false;
-            for (int wi = lane; wi < wpr; wi += 32) {
-              const uint32_t m = ~fr[wi], e = er[wi];
-              const uint32_t s = e | (m & (er[wi - wpr] | er[wi + wpr]));
-              if (s != e) { er[wi] = fill_runs(s, m); ch = true; }
-            }
-            ch = __any_sync(kFull, ch);
-            if (wpr > 1) {
-              for (;;) {                          // runs that cross a word boundary
-                __syncwarp();
-                bool c2 = false;
-                for (int wi = lane; wi < wpr; wi += 32) {
-                  const uint32_t m = ~fr[wi], e = er[wi];
-                  const uint32_t lft = wi > 0 ? er[wi - 1] >> 31 : 0u, rgt = wi + 1 < wpr ? er[wi + 1] & 1u : 0u;
-                  const uint32_t s = e | (m & (lft | (rgt << 31)));
-                  if (s != e) { er[wi] = fill_runs(s, m); c2 = true; }
-                }
-                c2 = __any_sync(kFull, c2);
-                if (!c2) break;
-                ch = true;
-              }
-            }
-            __syncwarp();
-            changed |= ch;
-          }
-        }
-        if (!changed) break;
+    // small ROI: bitmaps, row extremes and hull in shared memory; large ROI: everything in one of
+    // the global scratch slots (taken for the duration of this ROI)
+    const bool large = words > kSmemWords || rh > kRows;
+    if (tid == 0) {
+      sh.nbest = 0; sh.lock = 0; sh.slot = -1;
+      if (large) {
+        int sl = blockIdx.x % kScratchSlots;
+        while (atomicCAS(p.slot_locks + sl, 0, 1) != 0) sl = (sl + 1) % kScratchSlots;
+        __threadfence();
+        sh.slot = sl;
       }
     }
     __syncthreads();
+    uint32_t *fg = sh.fg, *ext = sh.ext;
+    WarpBuf wb{sh.rmin[warp], sh.rmax[warp], sh.hull[warp], kHullSmem};
+    if (large) {
+      uint32_t *slot = p.scratch + (size_t)sh.slot * p.scratch_words_per_cta;
+      const size_t bw = slot_bitmap_words(W, H);
+      fg = slot; ext = slot + bw;
+      uint32_t *wbase = slot + 2 * bw + (size_t)warp * slot_warp_words();
+      wb.rmin = reinterpret_cast<short *>(wbase);
+      wb.rmax = wb.rmin + kMaxRows;
+      wb.hull = reinterpret_cast<int *>(wbase + kMaxRows);
+      wb.hull_cap = kHullGlobal;
+    }
+    const uint8_t *frame = base + (size_t)f * frame_bytes;
+    long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+    int rounds = 0;
+    if (p.prof && tid == 0) t0 = clock64();
+    // 1. threshold bitmap
+    if (bayer) build_bitmap<true>(fg, frame, W, H, p.chan_order, p.rotate180, rx, ry, rw, rh, wpr, words, p.binary_threshold, warp, lane);
+    else build_bitmap<false>(fg, frame, W, H, p.chan_order, p.rotate180, rx, ry, rw, rh, wpr, words, p.binary_threshold, warp, lane);
+    __syncthreads();
+    if (p.prof && tid == 0) t1 = clock64();
+    // 2. exterior background.  Seeds on the padding, spread along runs inside each word; then rounds of
+    //    (a) a vertical pass: a warp owns a word column, 32 rows per step, and propagates "exterior"
+    //        down and up the column with a warp scan over (generate = exterior, propagate = background)
+    //        pairs -- all 32 bit lanes at once, any distance in one pass (the space between two light
+    //        bars is open only at its top and bottom);
+    //    (b) a relaxation pass by all threads: a word takes the exterior bits of its four neighbours
+    //        and spreads them along its runs (one word per round horizontally)
+    //    until nothing changes.
+    for (int w = tid; w < words; w += kThreads) {
+      const int row = w / wpr, wi = w - row * wpr;
+      const uint32_t m = ~fg[w];
+      uint32_t sd = (row == 0 || row == PH - 1) ? kFull : 0u;
+      if (wi == 0) sd |= 1u;
+      if (wi == wpr - 1) sd |= kFull << ((PW - 1) & 31);
+      ext[w] = fill_runs(sd & m, m);
+    }
+    __syncthreads();
+    {
+      const int d_row = kThreads / wpr, d_wi = kThreads - d_row * wpr;
+      const int inner = PH - 2;                              // rows 1 .. PH-2
+      for (;;) {
+        bool changed = false;
+        for (int wi = warp; wi < wpr; wi += kWarps) {
+#pragma unroll 1
+          for (int dirn = 0; dirn < 2; ++dirn) {
+            uint32_t carry = ext[(dirn ? PH - 1 : 0) * wpr + wi];
+            for (int c0 = 0; c0 < inner; c0 += 32) {
+              const int i = c0 + lane;
+              const bool valid = i < inner;
+              const int r = dirn ? PH - 2 - i : 1 + i;
+              const uint32_t e_old = valid ? ext[r * wpr + wi] : 0u;
+              const uint32_t m0 = valid ? ~fg[r * wpr + wi] : 0u;
+              uint32_t g = e_old, pm = m0;
+#pragma unroll
+              for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t g2 = __shfl_up_sync(kFull, g, d), p2 = __shfl_up_sync(kFull, pm, d);
+                if (lane >= d) { g |= pm & g2; pm &= p2; }
+              }
+              const uint32_t o = g | (pm & carry);
+              carry = __shfl_sync(kFull, o, 31);
+              // (written run-closed: the relaxation pass only spreads bits that arrive from a neighbour)
+              if (valid && o != e_old) { ext[r * wpr + wi] = fill_runs(o, m0); changed = true; }
+            }
+          }
+        }
+        __syncthreads();
+        int row = tid / wpr, wi = tid - row * wpr;
+        for (int w = tid; w < words; w += kThreads) {
+          if (row >= 1 && row <= PH - 2) {
+            const uint32_t m = ~fg[w], e = ext[w];
+            if (m & ~e) {                                    // background bits not yet exterior
+              const uint32_t lft = wi > 0 ? ext[w - 1] >> 31 : 0u, rgt = wi + 1 < wpr ? ext[w + 1] & 1u : 0u;
+              const uint32_t sd = e | (m & (ext[w - wpr] | ext[w + wpr] | lft | (rgt << 31)));
+              if (sd != e) { ext[w] = fill_runs(sd, m); changed = true; }
+            }
+          }
+          row += d_row; wi += d_wi;
+          if (wi >= wpr) { wi -= wpr; ++row; }
+        }
+        ++rounds;
+        if (!__syncthreads_or(changed)) break;
+      }
+    }
+    if (p.prof && tid == 0) t2 = clock64();
     // 3. border walks from the start candidates, 4. lights
     const long long step_cap = 8ll * PW * PH;
     const int nchunks = (words + 31) >> 5;
@@ -393,27 +495,57 @@ __global__ void __launch_bounds__(kThreads) extract_armors_kernel(ArmorParams p)
           cand = f0 & ext_w & ~above;
         }
       }
-      while (__any_sync(kFull, cand != 0)) {
-        bool acc = false;
-        int x0 = 0, y0 = 0, ymax = 0;
-        if (cand) {
-          const int bpos = __ffs(cand) - 1;
-          cand &= cand - 1;
-          x0 = wi * 32 + bpos; y0 = row;
-          int npts = 0;
-          acc = walk_border<false>(fg, wpr, x0, y0, step_cap, npts, ymax, nullptr, nullptr) && npts >= 5;
-        }
-        uint32_t m = __ballot_sync(kFull, acc);
-        while (m) {
-          const int src = __ffs(m) - 1;
-          m &= m - 1;
-          const int X0 = __shfl_sync(kFull, x0, src), Y0 = __shfl_sync(kFull, y0, src), YM = __shfl_sync(kFull, ymax, src);
-          process_border(sh, sh.wb[warp], fg, wpr, X0, Y0, YM, step_cap, min_x, min_y, p, lane);
+      int ncand = __popc(cand);
+#pragma unroll
+      for (int off = 16; off; off >>= 1) ncand += __shfl_xor_sync(kFull, ncand, off);
+      if (ncand <= 4) {
+        // few candidates (the usual case: a light bar has one): one walk each, recording the row
+        // extremes as it goes, so a kept border is walked once
+        uint32_t have;
+        while ((have = __ballot_sync(kFull, cand != 0)) != 0) {
+          const int src = __ffs(have) - 1;
+          int x0 = 0;
+          if (lane == src) { x0 = wi * 32 + __ffs(cand) - 1; cand &= cand - 1; }
+          const int X0 = __shfl_sync(kFull, x0, src), Y0 = __shfl_sync(kFull, row, src);
+          const int span = PH - 1 - Y0;                      // rows the border can reach
+          for (int r = lane; r < span; r += 32) { wb.rmin[r] = 32767; wb.rmax[r] = -1; }
           __syncwarp();
+          int ok = 0, ymax = 0;
+          if (lane == 0) {
+            int npts = 0;
+            ok = walk_border<true>(fg, wpr, X0, Y0, step_cap, npts, ymax, wb.rmin, wb.rmax) && npts >= 5;
+          }
+          ok = __shfl_sync(kFull, ok, 0);
+          const int YM = __shfl_sync(kFull, ymax, 0);
+          if (ok) process_border(sh, wb, fg, wpr, X0, Y0, YM, false, step_cap, min_x, min_y, p, lane);
+          __syncwarp();
+        }
+      } else {
+        // many candidates (speckle): every lane walks its own candidate for ownership and vertex
+        // count; the few that pass are walked again, recording
+        while (__any_sync(kFull, cand != 0)) {
+          bool acc = false;
+          int x0 = 0, y0 = 0, ymax = 0;
+          if (cand) {
+            const int bpos = __ffs(cand) - 1;
+            cand &= cand - 1;
+            x0 = wi * 32 + bpos; y0 = row;
+            int npts = 0;
+            acc = walk_border<false>(fg, wpr, x0, y0, step_cap, npts, ymax, nullptr, nullptr) && npts >= 5;
+          }
+          uint32_t m = __ballot_sync(kFull, acc);
+          while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const int X0 = __shfl_sync(kFull, x0, src), Y0 = __shfl_sync(kFull, y0, src), YM = __shfl_sync(kFull, ymax, src);
+            process_border(sh, wb, fg, wpr, X0, Y0, YM, true, step_cap, min_x, min_y, p, lane);
+            __syncwarp();
+          }
         }
       }
     }
     __syncthreads();
+    if (p.prof && tid == 0) t3 = clock64();
     // 5. Armor::Armor (armor.hpp:58-68) and the centre-distance filter (src/irm_detector.cpp:333-350)
     if (tid == 0) {
       int valid = 0;
@@ -441,6 +573,16 @@ __global__ void __launch_bounds__(kThreads) extract_armors_kernel(ArmorParams p)
         }
       }
       out->valid = valid;
+      if (large) {
+        __threadfence();
+        atomicExch(p.slot_locks + sh.slot, 0);
+      }
+      if (p.prof) {
+        const long long t4 = clock64();
+        atomicAdd(p.prof + 0, (unsigned long long)(t1 - t0)); atomicAdd(p.prof + 1, (unsigned long long)(t2 - t1));
+        atomicAdd(p.prof + 2, (unsigned long long)(t3 - t2)); atomicAdd(p.prof + 3, (unsigned long long)(t4 - t3));
+        atomicAdd(p.prof + 4, 1ull); atomicAdd(p.prof + 5, (unsigned long long)rounds);
+      }
     }
     __syncthreads();
   }
@@ -469,12 +611,11 @@ __global__ void mask_pose_ok_kernel(const ArmorOut *armors, int total, uint8_t *
 
 }  // namespace
 
-int armors_grid(int num_sms) { return num_sms * 3; }
+int armors_grid(int num_sms) { return num_sms * 6; }
 
-size_t armors_scratch_words_per_cta(int src_w, int src_h) {
-  const size_t wpr = ((size_t)src_w + 2 + 31) / 32;
-  return 2 * wpr * ((size_t)src_h + 2);
-}
+// scratch layout: [kScratchSlots lock words, padded to 64 words][kScratchSlots slots]
+size_t armors_scratch_words_per_cta(int src_w, int src_h) { return slot_words(src_w, src_h); }
+size_t armors_scratch_total_words(int src_w, int src_h) { return 64 + (size_t)kScratchSlots * slot_words(src_w, src_h); }
 
 cudaError_t launch_extract_armors(const ArmorParams &p, cudaStream_t s) {
   if (p.src_h > kMaxRows - 2 || p.src_w > 32766) return cudaErrorInvalidValue;

@@ -627,7 +627,7 @@ int issue_replay(irmv_engine *e, Lane &ln, int n, cudaStream_t st, int *launches
     ap.min_ratio = q.light_min_ratio; ap.max_ratio = q.light_max_ratio; ap.max_angle = q.light_max_angle;
     ap.min_small = q.min_small_center_distance; ap.max_small = q.max_small_center_distance;
     ap.min_large = q.min_large_center_distance; ap.max_large = q.max_large_center_distance;
-    ap.out = ln.armors; ap.scratch = ln.armor_scratch;
+    ap.out = ln.armors; ap.slot_locks = reinterpret_cast<int *>(ln.armor_scratch); ap.scratch = ln.armor_scratch + 64;
     ap.scratch_words_per_cta = armors_scratch_words_per_cta(e->cfg.src_width, e->cfg.src_height);
     ap.grid = armors_grid(e->num_sms);
     IRMV_CUDA(launch_extract_armors(ap, st)); ++cnt;
@@ -1181,11 +1181,12 @@ int irmv_engine_enable_armors(irmv_engine *e, const irmv_armor_params *prm) {
   IRMV_CUDA(cudaSetDevice(e->cfg.device));
   IRMV_CUDA(cudaDeviceSynchronize());
   const size_t slots = (size_t)e->S * e->cfg.max_det;
-  const size_t words = armors_scratch_words_per_cta(e->cfg.src_width, e->cfg.src_height) * (size_t)armors_grid(e->num_sms);
+  const size_t words = armors_scratch_total_words(e->cfg.src_width, e->cfg.src_height);
   for (auto &ln : e->lanes) {
     if (!ln.armors) {
       if (!lane_alloc(ln, (void **)&ln.armors, slots * sizeof(ArmorOut)) || !lane_alloc(ln, (void **)&ln.armor_scratch, words * 4)) return 3;
       IRMV_CUDA(cudaMemset(ln.armors, 0, slots * sizeof(ArmorOut)));
+      IRMV_CUDA(cudaMemset(ln.armor_scratch, 0, 256));         // slot locks
     }
     for (auto &g : ln.graphs) cudaGraphExecDestroy(g.second);   // the pipeline changed: drop captured graphs
     ln.graphs.clear();
@@ -1201,6 +1202,18 @@ int irmv_engine_fetch_armors(irmv_engine *e, int ticket, int nframes, irmv_armor
   const uint8_t *h = ticket < 0 ? e->res_host : e->sets[ticket % kSets].res_host;
   if (!h) { set_error("nothing was submitted under this ticket"); return 2; }
   memcpy(out, h + armors_offset(B, md), (size_t)nframes * md * sizeof(irmv_armor));
+  return 0;
+}
+
+static thread_local double g_armors_ms = 0.0;
+static thread_local unsigned long long g_armors_prof[6] = {0, 0, 0, 0, 0, 0};
+double irmv_extract_armors_last_device_ms(void) { return g_armors_ms; }
+// Debug: per-phase SM cycles of the last stand-alone call, summed over ROIs:
+// {bitmap, flood, walks + lights, armor, ROIs processed, flood rounds}.  Collected only when the
+// environment variable IRMV_ARMOR_PROF is set.
+int irmv_extract_armors_last_profile(unsigned long long out[6]) {
+  if (!out) return 1;
+  for (int i = 0; i < 6; ++i) out[i] = g_armors_prof[i];
   return 0;
 }
 
@@ -1227,7 +1240,7 @@ int irmv_extract_armors(const uint8_t *frames, int frames_on_device, int nframes
     hs[i] = boxes[i].score; hc[i] = boxes[i].class_id;
   }
   const int grid = armors_grid(prop.multiProcessorCount);
-  const size_t wpc = armors_scratch_words_per_cta(src_w, src_h);
+  const size_t wpc = armors_scratch_words_per_cta(src_w, src_h), wtotal = armors_scratch_total_words(src_w, src_h);
   int rc = 0;
   auto body = [&]() -> int {
     if (!frames_on_device) {
@@ -1239,7 +1252,8 @@ int irmv_extract_armors(const uint8_t *frames, int frames_on_device, int nframes
     IRMV_CUDA(cudaMalloc((void **)&d_boxes, slots * 16));
     IRMV_CUDA(cudaMalloc((void **)&d_scores, slots * 4));
     IRMV_CUDA(cudaMalloc((void **)&d_out, slots * sizeof(ArmorOut)));
-    IRMV_CUDA(cudaMalloc((void **)&d_scratch, wpc * grid * 4));
+    IRMV_CUDA(cudaMalloc((void **)&d_scratch, wtotal * 4));
+    IRMV_CUDA(cudaMemset(d_scratch, 0, 256));                  // slot locks
     IRMV_CUDA(cudaMemcpy(d_num, counts, (size_t)nframes * 4, cudaMemcpyHostToDevice));
     IRMV_CUDA(cudaMemcpy(d_cls, hc.data(), slots * 4, cudaMemcpyHostToDevice));
     IRMV_CUDA(cudaMemcpy(d_boxes, hb.data(), slots * 16, cudaMemcpyHostToDevice));
@@ -1254,9 +1268,29 @@ int irmv_extract_armors(const uint8_t *frames, int frames_on_device, int nframes
     ap.min_ratio = q.light_min_ratio; ap.max_ratio = q.light_max_ratio; ap.max_angle = q.light_max_angle;
     ap.min_small = q.min_small_center_distance; ap.max_small = q.max_small_center_distance;
     ap.min_large = q.min_large_center_distance; ap.max_large = q.max_large_center_distance;
-    ap.out = d_out; ap.scratch = d_scratch; ap.scratch_words_per_cta = wpc; ap.grid = grid;
+    ap.out = d_out; ap.slot_locks = reinterpret_cast<int *>(d_scratch); ap.scratch = d_scratch + 64;
+    ap.scratch_words_per_cta = wpc; ap.grid = grid;
+    unsigned long long *d_prof = nullptr;
+    if (getenv("IRMV_ARMOR_PROF")) {
+      IRMV_CUDA(cudaMalloc((void **)&d_prof, 48));
+      IRMV_CUDA(cudaMemset(d_prof, 0, 48));
+    }
+    ap.prof = d_prof;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    IRMV_CUDA(cudaEventCreate(&e0));
+    IRMV_CUDA(cudaEventCreate(&e1));
+    IRMV_CUDA(cudaEventRecord(e0, nullptr));
     IRMV_CUDA(launch_extract_armors(ap, nullptr));
+    IRMV_CUDA(cudaEventRecord(e1, nullptr));
     IRMV_CUDA(cudaDeviceSynchronize());
+    float ms = 0.f;
+    IRMV_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    g_armors_ms = ms;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (d_prof) {
+      IRMV_CUDA(cudaMemcpy(g_armors_prof, d_prof, 48, cudaMemcpyDeviceToHost));
+      cudaFree(d_prof);
+    }
     IRMV_CUDA(cudaMemcpy(out, d_out, slots * sizeof(ArmorOut), cudaMemcpyDeviceToHost));
     return 0;
   };

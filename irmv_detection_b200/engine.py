@@ -361,16 +361,26 @@ def extract_armors(frames: np.ndarray, boxes: np.ndarray, counts: np.ndarray, ch
     them; boxes structured BBOX_DTYPE [n, max_det] (source pixels) with counts[n] valid entries.
     Returns ARMOR_DTYPE [n, max_det], slot-aligned with boxes."""
     frames = np.ascontiguousarray(frames, np.uint8)
+    n, H, W = frames.shape[:3]
+    return extract_armors_ptr(frames.ctypes.data, False, n, W, H, boxes, counts, chan_order, rotate180, device, **params)
+
+
+def extract_armors_ptr(ptr: int, on_device: bool, n: int, W: int, H: int, boxes: np.ndarray, counts: np.ndarray,
+                       chan_order: int = L.CH_PASSTHROUGH, rotate180: bool = True, device: int = 0, **params) -> np.ndarray:
+    """Same stage on n frames at a raw host or device address (device: no copy of the frames)."""
     boxes = np.ascontiguousarray(boxes, BBOX_DTYPE)
     counts = np.ascontiguousarray(counts, np.int32)
-    n, H, W = frames.shape[:3]
     max_det = boxes.shape[1]
     out = np.zeros((n, max_det), ARMOR_DTYPE)
     prm = armor_params(**params)
-    L.check(L.lib().irmv_extract_armors(frames.ctypes.data, 0, n, W, H, chan_order, int(rotate180), boxes.ctypes.data,
-                                        counts.ctypes.data, max_det, C.byref(prm), device, out.ctypes.data),
-            "irmv_extract_armors")
+    L.check(L.lib().irmv_extract_armors(C.c_void_p(ptr), int(on_device), n, W, H, chan_order, int(rotate180),
+                                        boxes.ctypes.data, counts.ctypes.data, max_det, C.byref(prm), device,
+                                        out.ctypes.data), "irmv_extract_armors")
     return out
+
+
+def extract_armors_last_device_ms() -> float:
+    return float(L.lib().irmv_extract_armors_last_device_ms())
 
 
 

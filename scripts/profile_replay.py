@@ -23,6 +23,8 @@ def main():
     torch.cuda.synchronize()
     eng = irmv.YoloEngine(w, (1280, 1024), chan_order=irmv.CH_BAYER_RGGB, max_batch=n, sub_batch=n, num_lanes=1,
                           use_graph=False)
+    if len(sys.argv) > 3 and sys.argv[3] == "armors":      # light-bar extraction between NMS and PnP
+        eng.enable_armors()
     eng.enable_pnp(bench.K_CAM, bench.D_CAM, (0.5, 480 / 1024))
     for _ in range(warm + 1):
         eng.enqueue_batch_device(frames.data_ptr(), n)

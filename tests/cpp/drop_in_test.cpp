@@ -12,6 +12,7 @@
 #include <thread>
 #include <vector>
 
+#include "irmv_detection/armor_extractor.hpp"
 #include "irmv_detection/pnp_solver.hpp"
 #include "irmv_detection/triple_buffer.hpp"
 #include "irmv_detection/yolo_engine.hpp"
@@ -64,6 +65,51 @@ int main(int argc, char ** argv)
   printf("pnp ok %d rvec %.8f %.8f %.8f tvec %.8f %.8f %.8f dist %.4f\n", ok, rvec.at<double>(0), rvec.at<double>(1),
          rvec.at<double>(2), tvec.at<double>(0), tvec.at<double>(1), tvec.at<double>(2),
          pnp.calculateDistanceToCenter(armor.center));
+
+  // extract_armors (reference src/irm_detector.cpp:292-355): two bright bars in a dark rotated image,
+  // one box around them -> one small armor whose corners are the bar ends, then its pose
+  {
+    std::vector<uint8_t> img(1280 * 1024 * 3, 20);
+    auto bar = [&](int x0, int x1, int y0, int y1) {
+      for (int y = y0; y <= y1; y++)
+        for (int x = x0; x <= x1; x++) memset(&img[(static_cast<size_t>(y) * 1280 + x) * 3], 250, 3);
+    };
+    bar(600, 605, 400, 439);      // 6 x 40 pixels, centres 80 px apart: centre distance / length = 2 -> SMALL
+    bar(680, 685, 402, 441);
+    bar(602, 603, 399, 399);      // a rounded cap: an axis-parallel rectangle has only 4 contour vertices and
+    bar(682, 683, 401, 401);      // the reference drops contours with fewer than 5 (src/irm_detector.cpp:320)
+    cv::Mat image(cv::Size(1280, 1024), CV_8UC3, img.data());
+    YoloEngine::bbox box;
+    box.xyxy = {580.5f, 380.25f, 710.f, 460.f};
+    box.score = 0.9f;
+    box.class_id = ArmorClass::R3;
+    ArmorExtractor extractor;
+    std::vector<Armor> armors = extractor.extract_armors(image, {box});
+    printf("armors %zu\n", armors.size());
+    if (armors.size() != 1) { printf("FAIL: extract_armors\n"); return 1; }
+    const Armor & a = armors[0];
+    printf("armor size %d class %s conf %.3f left %.3f %.3f %.3f %.3f right %.3f %.3f %.3f %.3f center %.3f %.3f\n",
+           static_cast<int>(a.size), armor_class_name(a.armor_class), a.confidence, a.left_light.top.x, a.left_light.top.y,
+           a.left_light.bottom.x, a.left_light.bottom.y, a.right_light.top.x, a.right_light.top.y, a.right_light.bottom.x,
+           a.right_light.bottom.y, a.center.x, a.center.y);
+    cv::Mat rv2, tv2;
+    const bool ok2 = pnp.solvePnP(a, rv2, tv2);
+    printf("armor pnp ok %d tvec %.6f %.6f %.6f\n", ok2, tv2.at<double>(0), tv2.at<double>(1), tv2.at<double>(2));
+    // fused form: the engine runs the stage inside its replay; same answer as the image form on the
+    // engine's own boxes and rotated frame
+    if (!extractor.enable(engine)) { printf("FAIL: enable armors\n"); return 1; }
+    for (size_t i = 0; i < img.size(); i++) src[i] = img[img.size() - 3 - (i / 3) * 3 + (i % 3)];   // camera view = rot180
+    std::vector<YoloEngine::bbox> b2 = engine.detect();
+    std::vector<Armor> fused = extractor.extract_armors(engine, b2);
+    std::vector<Armor> staged = extractor.extract_armors(engine.get_rotated_image(), b2);
+    printf("fused armors %zu staged %zu boxes %zu\n", fused.size(), staged.size(), b2.size());
+    if (fused.size() != staged.size()) { printf("FAIL: fused armor stage\n"); return 1; }
+    for (size_t i = 0; i < fused.size(); i++)
+      if (fused[i].left_light.top.x != staged[i].left_light.top.x || fused[i].right_light.bottom.y != staged[i].right_light.bottom.y) {
+        printf("FAIL: fused armor %zu differs\n", i);
+        return 1;
+      }
+  }
 
   // triple buffer: producer at full speed, consumer sees strictly newer frames (drops allowed).
   // The hand-off can lose the wake-up of the very last commit by design (the reference clears its

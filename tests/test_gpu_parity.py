@@ -795,6 +795,23 @@ def test_cpp_drop_in_classes(base_image, weights_seed0, tmp_path):
     np.testing.assert_allclose([float(v) for v in pnp[4:7]], [1.14443091, -0.9268353, 1.21457493], rtol=1e-6)
     np.testing.assert_allclose([float(v) for v in pnp[8:11]], [0.00508322, 0.02282537, 1.30085669], rtol=1e-6)
     eng.close()
+    # ArmorExtractor (IrmDetector::extract_armors): the C++ program's scene through the cv2 form of the reference
+    import cv2
+    from oracle import armor_ref as A
+    img = np.full((1024, 1280, 3), 20, np.uint8)
+    img[400:440, 600:606] = 250
+    img[402:442, 680:686] = 250
+    img[399, 602:604] = 250
+    img[401, 682:684] = 250
+    ref = A.extract_armors_cv2(img, np.array([[580.5, 380.25, 710, 460]], np.float32), [0.9], [9])
+    assert len(ref) == 1 and ref[0].size == A.SMALL
+    arm = [l for l in lines if l.startswith("armor size")][0].split()
+    assert int(arm[2]) == 0 and arm[4] == "R3"
+    got_left = np.array([float(v) for v in arm[8:12]]).reshape(2, 2)       # top, bottom
+    got_right = np.array([float(v) for v in arm[13:17]]).reshape(2, 2)
+    np.testing.assert_allclose(got_left, ref[0].pts[[1, 0]], atol=2e-3)
+    np.testing.assert_allclose(got_right, ref[0].pts[[2, 3]], atol=2e-3)
+    assert [l for l in lines if l.startswith("armor pnp ok 1")]
 
 
 def test_pnp_stress_one_million_properties():
