@@ -160,8 +160,8 @@ int irmv_extract_armors(const uint8_t *frames, int frames_on_device, int nframes
 /* Device time (CUDA events around the kernel) of this thread's last irmv_extract_armors call, ms. */
 double irmv_extract_armors_last_device_ms(void);
 /* Debug (IRMV_ARMOR_PROF set): SM cycles per phase of that call, summed over ROIs:
- * {bitmap, flood, walks + lights, armor, ROIs processed, flood rounds}. */
-int irmv_extract_armors_last_profile(unsigned long long out[6]);
+ * {bitmap, flood, walks + lights, armor, ROIs processed, flood rounds, recording walks, hull + rectangle + light}. */
+int irmv_extract_armors_last_profile(unsigned long long out[8]);
 /* Fuse the stage into the replay, between NMS and PnP: with irmv_engine_enable_pnp the pose stage then
  * solves on the armor corners (scaled by corner_sx/sy) instead of the box corners, and ok[] is 0 for
  * detections without an armor -- the whole of message_callback's per-frame work

@@ -70,7 +70,7 @@ SYMBOLS = {
     "irmv_extract_armors": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int,
                                       C.POINTER(ArmorParams), C.c_int, _P]),
     "irmv_extract_armors_last_device_ms": (C.c_double, []),
-    "irmv_extract_armors_last_profile": (C.c_int, [C.POINTER(C.c_uint64 * 6)]),
+    "irmv_extract_armors_last_profile": (C.c_int, [C.POINTER(C.c_uint64 * 8)]),
     "irmv_engine_enable_armors": (C.c_int, [_P, C.POINTER(ArmorParams)]),
     "irmv_engine_fetch_armors": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "irmv_engine_profile_stages": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_float * 5)]),

@@ -173,8 +173,8 @@ __device__ __forceinline__ uint32_t nbr8(const uint32_t *fg, int wpr, int x, int
 // count, ymax = last row of the border.  RECORD: per-row extreme columns into rmin / rmax (rows
 // relative to y0, which is the component's first row when the walk is the owner's).
 template <bool RECORD>
-__device__ bool walk_border(const uint32_t *fg, int wpr, int x0, int y0, long long step_cap, int &npts, int &ymax,
-                            short *rmin, short *rmax) {
+__device__ __forceinline__ bool walk_border(const uint32_t *fg, int wpr, int x0, int y0, int step_cap, int &npts, int &ymax,
+                                            short *rmin, short *rmax) {
   uint32_t nb = nbr8(fg, wpr, x0, y0);
   ymax = y0;
   if (nb == 0) {                         // isolated pixel
@@ -187,7 +187,7 @@ __device__ bool walk_border(const uint32_t *fg, int wpr, int x0, int y0, long lo
   while (!((nb >> s) & 1u)) s = (s - 1) & 7;
   const int x1 = x0 + dir_dx(s), y1 = y0 + dir_dy(s);
   int x3 = x0, y3 = y0, prev_s = s ^ 4, n = 0;
-  for (long long it = 0; it < step_cap; ++it) {
+  for (int it = 0; it < step_cap; ++it) {
     // next neighbour counter-clockwise after s: rotate the mask so that direction s + 1 is bit 0
     const uint32_t rot = ((nb | (nb << 8)) >> ((s + 1) & 7)) & 0xffu;
     s = (s + __ffs(rot)) & 7;
@@ -216,8 +216,9 @@ __device__ __forceinline__ int cross3(int a, int b, int cx, int cy) {
 // Kept border -> Light (armor.hpp:15-29) -> filter (armor.hpp:31-38) -> best-two list.
 // Warp-cooperative; (x0, y0) padded ROI coordinates of the first pixel, ymax its last row.
 // need_walk: the row extremes are not in wb yet (the ownership walk ran without recording).
-__device__ void process_border(Shared &sh, const WarpBuf &wb, const uint32_t *fg, int wpr, int x0, int y0, int ymax,
-                               bool need_walk, long long step_cap, float min_x, float min_y, const ArmorParams &p, int lane) {
+__device__ __forceinline__ void process_border(Shared &sh, const WarpBuf &wb, const uint32_t *fg, int wpr, int x0, int y0,
+                                               int ymax, bool need_walk, int step_cap, float min_x, float min_y,
+                                               const ArmorParams &p, int lane) {
   const int rows = ymax - y0 + 1;
   if (need_walk) {
     for (int r = lane; r < rows; r += 32) { wb.rmin[r] = 32767; wb.rmax[r] = -1; }
@@ -346,6 +347,214 @@ __device__ void process_border(Shared &sh, const WarpBuf &wb, const uint32_t *fg
   atomicExch(&sh.lock, 0);
 }
 
+// One detection: bitmap -> exterior flood -> border walks -> lights -> armor.  LARGE selects where
+// the per-ROI state lives, so that the small path compiles to shared-memory instructions.
+template <bool LARGE>
+__device__ __forceinline__ void roi_body(Shared &sh, const ArmorParams &p, uint32_t *slot, const uint8_t *frame, int W, int H,
+                                         bool bayer, int rx, int ry, int rw, int rh, float min_x, float min_y, int item,
+                                         ArmorOut *out, int tid, int lane, int warp) {
+  const int PW = rw + 2, PH = rh + 2, wpr = (PW + 31) >> 5, words = PH * wpr;
+  // small ROI: bitmaps, row extremes and hull in shared memory (LDS/STS with 32-bit addresses);
+  // large ROI: everything in the global scratch slot this CTA holds for the duration of the ROI
+  uint32_t *fg, *ext;
+  WarpBuf wb;
+  if (LARGE) {
+    const size_t bw = slot_bitmap_words(W, H);
+    fg = slot; ext = slot + bw;
+    uint32_t *wbase = slot + 2 * bw + (size_t)warp * slot_warp_words();
+    wb.rmin = reinterpret_cast<short *>(wbase);
+    wb.rmax = wb.rmin + kMaxRows;
+    wb.hull = reinterpret_cast<int *>(wbase + kMaxRows);
+    wb.hull_cap = kHullGlobal;
+  } else {
+    fg = sh.fg; ext = sh.ext;
+    wb.rmin = sh.rmin[warp]; wb.rmax = sh.rmax[warp]; wb.hull = sh.hull[warp]; wb.hull_cap = kHullSmem;
+  }
+  long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+  int rounds = 0;
+  if (p.prof && tid == 0) t0 = clock64();
+  // 1. threshold bitmap
+  if (bayer) build_bitmap<true>(fg, frame, W, H, p.chan_order, p.rotate180, rx, ry, rw, rh, wpr, words, p.binary_threshold, warp, lane);
+  else build_bitmap<false>(fg, frame, W, H, p.chan_order, p.rotate180, rx, ry, rw, rh, wpr, words, p.binary_threshold, warp, lane);
+  __syncthreads();
+  if (p.prof && tid == 0) t1 = clock64();
+  // 2. exterior background.  Seeds on the padding, spread along runs inside each word; then rounds of
+  //    (a) a vertical pass: a warp owns a word column, 32 rows per step, and propagates "exterior"
+  //        down and up the column with a warp scan over (generate = exterior, propagate = background)
+  //        pairs -- all 32 bit lanes at once, any distance in one pass (the space between two light
+  //        bars is open only at its top and bottom);
+  //    (b) a relaxation pass by all threads: a word takes the exterior bits of its four neighbours
+  //        and spreads them along its runs (one word per round horizontally)
+  //    until nothing changes.
+  for (int w = tid; w < words; w += kThreads) {
+    const int row = w / wpr, wi = w - row * wpr;
+    const uint32_t m = ~fg[w];
+    uint32_t sd = (row == 0 || row == PH - 1) ? kFull : 0u;
+    if (wi == 0) sd |= 1u;
+    if (wi == wpr - 1) sd |= kFull << ((PW - 1) & 31);
+    ext[w] = fill_runs(sd & m, m);
+  }
+  __syncthreads();
+  {
+    const int d_row = kThreads / wpr, d_wi = kThreads - d_row * wpr;
+    const int inner = PH - 2;                              // rows 1 .. PH-2
+    for (;;) {
+      bool changed = false;
+      for (int wi = warp; wi < wpr; wi += kWarps) {
+#pragma unroll 1
+        for (int dirn = 0; dirn < 2; ++dirn) {
+          uint32_t carry = ext[(dirn ? PH - 1 : 0) * wpr + wi];
+          for (int c0 = 0; c0 < inner; c0 += 32) {
+            const int i = c0 + lane;
+            const bool valid = i < inner;
+            const int r = dirn ? PH - 2 - i : 1 + i;
+            const uint32_t e_old = valid ? ext[r * wpr + wi] : 0u;
+            const uint32_t m0 = valid ? ~fg[r * wpr + wi] : 0u;
+            uint32_t g = e_old, pm = m0;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+              const uint32_t g2 = __shfl_up_sync(kFull, g, d), p2 = __shfl_up_sync(kFull, pm, d);
+              if (lane >= d) { g |= pm & g2; pm &= p2; }
+            }
+            const uint32_t o = g | (pm & carry);
+            carry = __shfl_sync(kFull, o, 31);
+            // (written run-closed: the relaxation pass only spreads bits that arrive from a neighbour)
+            if (valid && o != e_old) { ext[r * wpr + wi] = fill_runs(o, m0); changed = true; }
+          }
+        }
+      }
+      __syncthreads();
+      int row = tid / wpr, wi = tid - row * wpr;
+      for (int w = tid; w < words; w += kThreads) {
+        if (row >= 1 && row <= PH - 2) {
+          const uint32_t m = ~fg[w], e = ext[w];
+          if (m & ~e) {                                    // background bits not yet exterior
+            const uint32_t lft = wi > 0 ? ext[w - 1] >> 31 : 0u, rgt = wi + 1 < wpr ? ext[w + 1] & 1u : 0u;
+            const uint32_t sd = e | (m & (ext[w - wpr] | ext[w + wpr] | lft | (rgt << 31)));
+            if (sd != e) { ext[w] = fill_runs(sd, m); changed = true; }
+          }
+        }
+        row += d_row; wi += d_wi;
+        if (wi >= wpr) { wi -= wpr; ++row; }
+      }
+      ++rounds;
+      if (!__syncthreads_or(changed)) break;
+    }
+  }
+  if (p.prof && tid == 0) t2 = clock64();
+  // 3. border walks from the start candidates, 4. lights
+  const int step_cap = 8 * PW * PH;
+  const int nchunks = (words + 31) >> 5;
+  for (int chunk = warp; chunk < nchunks; chunk += kWarps) {
+    const int w = chunk * 32 + lane;
+    uint32_t cand = 0;
+    int row = 0, wi = 0;
+    if (w < words) {
+      row = w / wpr; wi = w - row * wpr;
+      if (row >= 1 && row <= PH - 2) {
+        const uint32_t f0 = fg[w], e0 = ext[w];
+        const uint32_t ep = wi > 0 ? ext[w - 1] >> 31 : 0u;
+        const uint32_t un = fg[w - wpr];
+        const uint32_t up = wi > 0 ? fg[w - wpr - 1] >> 31 : 0u, ux = wi + 1 < wpr ? fg[w - wpr + 1] << 31 : 0u;
+        const uint32_t ext_w = (e0 << 1) | ep;
+        const uint32_t above = un | (un << 1) | up | (un >> 1) | ux;
+        cand = f0 & ext_w & ~above;
+      }
+    }
+    int ncand = __popc(cand);
+#pragma unroll
+    for (int off = 16; off; off >>= 1) ncand += __shfl_xor_sync(kFull, ncand, off);
+    if (ncand <= 4) {
+      // few candidates (the usual case: a light bar has one): one walk each, recording the row
+      // extremes as it goes, so a kept border is walked once
+      uint32_t have;
+      while ((have = __ballot_sync(kFull, cand != 0)) != 0) {
+        const int src = __ffs(have) - 1;
+        int x0 = 0;
+        if (lane == src) { x0 = wi * 32 + __ffs(cand) - 1; cand &= cand - 1; }
+        const int X0 = __shfl_sync(kFull, x0, src), Y0 = __shfl_sync(kFull, row, src);
+        const int span = PH - 1 - Y0;                      // rows the border can reach
+        for (int r = lane; r < span; r += 32) { wb.rmin[r] = 32767; wb.rmax[r] = -1; }
+        __syncwarp();
+        int ok = 0, ymax = 0;
+        long long c0 = 0, c1 = 0;
+        if (lane == 0) {
+          int npts = 0;
+          if (p.prof) c0 = clock64();
+          ok = walk_border<true>(fg, wpr, X0, Y0, step_cap, npts, ymax, wb.rmin, wb.rmax) && npts >= 5;
+          if (p.prof) c1 = clock64();
+        }
+        ok = __shfl_sync(kFull, ok, 0);
+        const int YM = __shfl_sync(kFull, ymax, 0);
+        if (ok) process_border(sh, wb, fg, wpr, X0, Y0, YM, false, step_cap, min_x, min_y, p, lane);
+        __syncwarp();
+        if (p.prof && lane == 0) {
+          atomicAdd(p.prof + 6, (unsigned long long)(c1 - c0));
+          atomicAdd(p.prof + 7, (unsigned long long)(clock64() - c1));
+        }
+      }
+    } else {
+      // many candidates (speckle): every lane walks its own candidate for ownership and vertex
+      // count; the few that pass are walked again, recording
+      while (__any_sync(kFull, cand != 0)) {
+        bool acc = false;
+        int x0 = 0, y0 = 0, ymax = 0;
+        if (cand) {
+          const int bpos = __ffs(cand) - 1;
+          cand &= cand - 1;
+          x0 = wi * 32 + bpos; y0 = row;
+          int npts = 0;
+          acc = walk_border<false>(fg, wpr, x0, y0, step_cap, npts, ymax, nullptr, nullptr) && npts >= 5;
+        }
+        uint32_t m = __ballot_sync(kFull, acc);
+        while (m) {
+          const int src = __ffs(m) - 1;
+          m &= m - 1;
+          const int X0 = __shfl_sync(kFull, x0, src), Y0 = __shfl_sync(kFull, y0, src), YM = __shfl_sync(kFull, ymax, src);
+          process_border(sh, wb, fg, wpr, X0, Y0, YM, true, step_cap, min_x, min_y, p, lane);
+          __syncwarp();
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (p.prof && tid == 0) t3 = clock64();
+  // 5. Armor::Armor (armor.hpp:58-68) and the centre-distance filter (src/irm_detector.cpp:333-350)
+  if (tid == 0) {
+    int valid = 0;
+    if (sh.nbest >= 2) {
+      const LightRec l0 = sh.best[0], l1 = sh.best[1];
+      const bool first_left = l0.cx < l1.cx;
+      const LightRec L = first_left ? l0 : l1, R = first_left ? l1 : l0;
+      const double avg_len = (l0.length + l1.length) / 2;
+      const float ddx = __fsub_rn(L.cx, R.cx), ddy = __fsub_rn(L.cy, R.cy);
+      const double cd = sqrt((double)ddx * ddx + (double)ddy * ddy) / avg_len;
+      const int size = cd > p.min_large ? 1 : 0;
+      bool ok = true;
+      if (size == 0 && (p.min_small > cd || p.max_small < cd)) ok = false;
+      if (size == 1 && (p.min_large > cd || p.max_large < cd)) ok = false;
+      if (ok) {
+        out->pts[0] = L.bx; out->pts[1] = L.by; out->pts[2] = L.tx; out->pts[3] = L.ty;
+        out->pts[4] = R.tx; out->pts[5] = R.ty; out->pts[6] = R.bx; out->pts[7] = R.by;
+        out->center[0] = __fdiv_rn(__fadd_rn(L.cx, R.cx), 2.f);
+        out->center[1] = __fdiv_rn(__fadd_rn(L.cy, R.cy), 2.f);
+        out->score = p.scores[item];
+        const int c = p.classes[item];
+        out->class_id = (c >= 0 && c < 14) ? c : 14;
+        out->size = size;
+        valid = 1;
+      }
+    }
+    out->valid = valid;
+    if (p.prof) {
+      const long long t4 = clock64();
+      atomicAdd(p.prof + 0, (unsigned long long)(t1 - t0)); atomicAdd(p.prof + 1, (unsigned long long)(t2 - t1));
+      atomicAdd(p.prof + 2, (unsigned long long)(t3 - t2)); atomicAdd(p.prof + 3, (unsigned long long)(t4 - t3));
+      atomicAdd(p.prof + 4, 1ull); atomicAdd(p.prof + 5, (unsigned long long)rounds);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 6) extract_armors_kernel(ArmorParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   Shared &sh = *reinterpret_cast<Shared *>(smem_raw);
@@ -377,13 +586,11 @@ __global__ void __launch_bounds__(kThreads, 6) extract_armors_kernel(ArmorParams
       if (tid == 0) out->valid = 0;
       continue;
     }
-    const int PW = rw + 2, PH = rh + 2, wpr = (PW + 31) >> 5, words = PH * wpr;
-    // small ROI: bitmaps, row extremes and hull in shared memory; large ROI: everything in one of
-    // the global scratch slots (taken for the duration of this ROI)
-    const bool large = words > kSmemWords || rh > kRows;
+    const int words_roi = (rh + 2) * ((rw + 2 + 31) >> 5);
+    const bool large = words_roi > kSmemWords || rh > kRows;
     if (tid == 0) {
       sh.nbest = 0; sh.lock = 0; sh.slot = -1;
-      if (large) {
+      if (large) {                       // take one of the global scratch slots
         int sl = blockIdx.x % kScratchSlots;
         while (atomicCAS(p.slot_locks + sl, 0, 1) != 0) sl = (sl + 1) % kScratchSlots;
         __threadfence();
@@ -391,198 +598,17 @@ __global__ void __launch_bounds__(kThreads, 6) extract_armors_kernel(ArmorParams
       }
     }
     __syncthreads();
-    uint32_t *fg = sh.fg, *ext = sh.ext;
-    WarpBuf wb{sh.rmin[warp], sh.rmax[warp], sh.hull[warp], kHullSmem};
-    if (large) {
-      uint32_t *slot = p.scratch + (size_t)sh.slot * p.scratch_words_per_cta;
-      const size_t bw = slot_bitmap_words(W, H);
-      fg = slot; ext = slot + bw;
-      uint32_t *wbase = slot + 2 * bw + (size_t)warp * slot_warp_words();
-      wb.rmin = reinterpret_cast<short *>(wbase);
-      wb.rmax = wb.rmin + kMaxRows;
-      wb.hull = reinterpret_cast<int *>(wbase + kMaxRows);
-      wb.hull_cap = kHullGlobal;
-    }
     const uint8_t *frame = base + (size_t)f * frame_bytes;
-    long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
-    int rounds = 0;
-    if (p.prof && tid == 0) t0 = clock64();
-    // 1. threshold bitmap
-    if (bayer) build_bitmap<true>(fg, frame, W, H, p.chan_order, p.rotate180, rx, ry, rw, rh, wpr, words, p.binary_threshold, warp, lane);
-    else build_bitmap<false>(fg, frame, W, H, p.chan_order, p.rotate180, rx, ry, rw, rh, wpr, words, p.binary_threshold, warp, lane);
-    __syncthreads();
-    if (p.prof && tid == 0) t1 = clock64();
-    // 2. exterior background.  Seeds on the padding, spread along runs inside each word; then rounds of
-    //    (a) a vertical pass: a warp owns a word column, 32 rows per step, and propagates "exterior"
-    //        down and up the column with a warp scan over (generate = exterior, propagate = background)
-    //        pairs -- all 32 bit lanes at once, any distance in one pass (the space between two light
-    //        bars is open only at its top and bottom);
-    //    (b) a relaxation pass by all threads: a word takes the exterior bits of its four neighbours
-    //        and spreads them along its runs (one word per round horizontally)
-    //    until nothing changes.
-    for (int w = tid; w < words; w += kThreads) {
-      const int row = w / wpr, wi = w - row * wpr;
-      const uint32_t m = ~fg[w];
-      uint32_t sd = (row == 0 || row == PH - 1) ? kFull : 0u;
-      if (wi == 0) sd |= 1u;
-      if (wi == wpr - 1) sd |= kFull << ((PW - 1) & 31);
-      ext[w] = fill_runs(sd & m, m);
-    }
-    __syncthreads();
-    {
-      const int d_row = kThreads / wpr, d_wi = kThreads - d_row * wpr;
-      const int inner = PH - 2;                              // rows 1 .. PH-2
-      for (;;) {
-        bool changed = false;
-        for (int wi = warp; wi < wpr; wi += kWarps) {
-#pragma unroll 1
-          for (int dirn = 0; dirn < 2; ++dirn) {
-            uint32_t carry = ext[(dirn ? PH - 1 : 0) * wpr + wi];
-            for (int c0 = 0; c0 < inner; c0 += 32) {
-              const int i = c0 + lane;
-              const bool valid = i < inner;
-              const int r = dirn ? PH - 2 - i : 1 + i;
-              const uint32_t e_old = valid ? ext[r * wpr + wi] : 0u;
-              const uint32_t m0 = valid ? ~fg[r * wpr + wi] : 0u;
-              uint32_t g = e_old, pm = m0;
-#pragma unroll
-              for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t g2 = __shfl_up_sync(kFull, g, d), p2 = __shfl_up_sync(kFull, pm, d);
-                if (lane >= d) { g |= pm & g2; pm &= p2; }
-              }
-              const uint32_t o = g | (pm & carry);
-              carry = __shfl_sync(kFull, o, 31);
-              // (written run-closed: the relaxation pass only spreads bits that arrive from a neighbour)
-              if (valid && o != e_old) { ext[r * wpr + wi] = fill_runs(o, m0); changed = true; }
-            }
-          }
-        }
-        __syncthreads();
-        int row = tid / wpr, wi = tid - row * wpr;
-        for (int w = tid; w < words; w += kThreads) {
-          if (row >= 1 && row <= PH - 2) {
-            const uint32_t m = ~fg[w], e = ext[w];
-            if (m & ~e) {                                    // background bits not yet exterior
-              const uint32_t lft = wi > 0 ? ext[w - 1] >> 31 : 0u, rgt = wi + 1 < wpr ? ext[w + 1] & 1u : 0u;
-              const uint32_t sd = e | (m & (ext[w - wpr] | ext[w + wpr] | lft | (rgt << 31)));
-              if (sd != e) { ext[w] = fill_runs(sd, m); changed = true; }
-            }
-          }
-          row += d_row; wi += d_wi;
-          if (wi >= wpr) { wi -= wpr; ++row; }
-        }
-        ++rounds;
-        if (!__syncthreads_or(changed)) break;
-      }
-    }
-    if (p.prof && tid == 0) t2 = clock64();
-    // 3. border walks from the start candidates, 4. lights
-    const long long step_cap = 8ll * PW * PH;
-    const int nchunks = (words + 31) >> 5;
-    for (int chunk = warp; chunk < nchunks; chunk += kWarps) {
-      const int w = chunk * 32 + lane;
-      uint32_t cand = 0;
-      int row = 0, wi = 0;
-      if (w < words) {
-        row = w / wpr; wi = w - row * wpr;
-        if (row >= 1 && row <= PH - 2) {
-          const uint32_t f0 = fg[w], e0 = ext[w];
-          const uint32_t ep = wi > 0 ? ext[w - 1] >> 31 : 0u;
-          const uint32_t un = fg[w - wpr];
-          const uint32_t up = wi > 0 ? fg[w - wpr - 1] >> 31 : 0u, ux = wi + 1 < wpr ? fg[w - wpr + 1] << 31 : 0u;
-          const uint32_t ext_w = (e0 << 1) | ep;
-          const uint32_t above = un | (un << 1) | up | (un >> 1) | ux;
-          cand = f0 & ext_w & ~above;
-        }
-      }
-      int ncand = __popc(cand);
-#pragma unroll
-      for (int off = 16; off; off >>= 1) ncand += __shfl_xor_sync(kFull, ncand, off);
-      if (ncand <= 4) {
-        // few candidates (the usual case: a light bar has one): one walk each, recording the row
-        // extremes as it goes, so a kept border is walked once
-        uint32_t have;
-        while ((have = __ballot_sync(kFull, cand != 0)) != 0) {
-          const int src = __ffs(have) - 1;
-          int x0 = 0;
-          if (lane == src) { x0 = wi * 32 + __ffs(cand) - 1; cand &= cand - 1; }
-          const int X0 = __shfl_sync(kFull, x0, src), Y0 = __shfl_sync(kFull, row, src);
-          const int span = PH - 1 - Y0;                      // rows the border can reach
-          for (int r = lane; r < span; r += 32) { wb.rmin[r] = 32767; wb.rmax[r] = -1; }
-          __syncwarp();
-          int ok = 0, ymax = 0;
-          if (lane == 0) {
-            int npts = 0;
-            ok = walk_border<true>(fg, wpr, X0, Y0, step_cap, npts, ymax, wb.rmin, wb.rmax) && npts >= 5;
-          }
-          ok = __shfl_sync(kFull, ok, 0);
-          const int YM = __shfl_sync(kFull, ymax, 0);
-          if (ok) process_border(sh, wb, fg, wpr, X0, Y0, YM, false, step_cap, min_x, min_y, p, lane);
-          __syncwarp();
-        }
-      } else {
-        // many candidates (speckle): every lane walks its own candidate for ownership and vertex
-        // count; the few that pass are walked again, recording
-        while (__any_sync(kFull, cand != 0)) {
-          bool acc = false;
-          int x0 = 0, y0 = 0, ymax = 0;
-          if (cand) {
-            const int bpos = __ffs(cand) - 1;
-            cand &= cand - 1;
-            x0 = wi * 32 + bpos; y0 = row;
-            int npts = 0;
-            acc = walk_border<false>(fg, wpr, x0, y0, step_cap, npts, ymax, nullptr, nullptr) && npts >= 5;
-          }
-          uint32_t m = __ballot_sync(kFull, acc);
-          while (m) {
-            const int src = __ffs(m) - 1;
-            m &= m - 1;
-            const int X0 = __shfl_sync(kFull, x0, src), Y0 = __shfl_sync(kFull, y0, src), YM = __shfl_sync(kFull, ymax, src);
-            process_border(sh, wb, fg, wpr, X0, Y0, YM, true, step_cap, min_x, min_y, p, lane);
-            __syncwarp();
-          }
-        }
-      }
-    }
-    __syncthreads();
-    if (p.prof && tid == 0) t3 = clock64();
-    // 5. Armor::Armor (armor.hpp:58-68) and the centre-distance filter (src/irm_detector.cpp:333-350)
-    if (tid == 0) {
-      int valid = 0;
-      if (sh.nbest >= 2) {
-        const LightRec l0 = sh.best[0], l1 = sh.best[1];
-        const bool first_left = l0.cx < l1.cx;
-        const LightRec L = first_left ? l0 : l1, R = first_left ? l1 : l0;
-        const double avg_len = (l0.length + l1.length) / 2;
-        const float ddx = __fsub_rn(L.cx, R.cx), ddy = __fsub_rn(L.cy, R.cy);
-        const double cd = sqrt((double)ddx * ddx + (double)ddy * ddy) / avg_len;
-        const int size = cd > p.min_large ? 1 : 0;
-        bool ok = true;
-        if (size == 0 && (p.min_small > cd || p.max_small < cd)) ok = false;
-        if (size == 1 && (p.min_large > cd || p.max_large < cd)) ok = false;
-        if (ok) {
-          out->pts[0] = L.bx; out->pts[1] = L.by; out->pts[2] = L.tx; out->pts[3] = L.ty;
-          out->pts[4] = R.tx; out->pts[5] = R.ty; out->pts[6] = R.bx; out->pts[7] = R.by;
-          out->center[0] = __fdiv_rn(__fadd_rn(L.cx, R.cx), 2.f);
-          out->center[1] = __fdiv_rn(__fadd_rn(L.cy, R.cy), 2.f);
-          out->score = p.scores[item];
-          const int c = p.classes[item];
-          out->class_id = (c >= 0 && c < 14) ? c : 14;
-          out->size = size;
-          valid = 1;
-        }
-      }
-      out->valid = valid;
-      if (large) {
+    if (large) {
+      roi_body<true>(sh, p, p.scratch + (size_t)sh.slot * p.scratch_words_per_cta, frame, W, H, bayer, rx, ry, rw, rh, min_x,
+                     min_y, item, out, tid, lane, warp);
+      __syncthreads();
+      if (tid == 0) {
         __threadfence();
         atomicExch(p.slot_locks + sh.slot, 0);
       }
-      if (p.prof) {
-        const long long t4 = clock64();
-        atomicAdd(p.prof + 0, (unsigned long long)(t1 - t0)); atomicAdd(p.prof + 1, (unsigned long long)(t2 - t1));
-        atomicAdd(p.prof + 2, (unsigned long long)(t3 - t2)); atomicAdd(p.prof + 3, (unsigned long long)(t4 - t3));
-        atomicAdd(p.prof + 4, 1ull); atomicAdd(p.prof + 5, (unsigned long long)rounds);
-      }
+    } else {
+      roi_body<false>(sh, p, nullptr, frame, W, H, bayer, rx, ry, rw, rh, min_x, min_y, item, out, tid, lane, warp);
     }
     __syncthreads();
   }

@@ -1206,14 +1206,15 @@ int irmv_engine_fetch_armors(irmv_engine *e, int ticket, int nframes, irmv_armor
 }
 
 static thread_local double g_armors_ms = 0.0;
-static thread_local unsigned long long g_armors_prof[6] = {0, 0, 0, 0, 0, 0};
+static thread_local unsigned long long g_armors_prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 double irmv_extract_armors_last_device_ms(void) { return g_armors_ms; }
 // Debug: per-phase SM cycles of the last stand-alone call, summed over ROIs:
-// {bitmap, flood, walks + lights, armor, ROIs processed, flood rounds}.  Collected only when the
+// {bitmap, flood, walks + lights, armor, ROIs processed, flood rounds, recording walks (warp cycles),
+// hull + rectangle + light (warp cycles)}.  Collected only when the
 // environment variable IRMV_ARMOR_PROF is set.
-int irmv_extract_armors_last_profile(unsigned long long out[6]) {
+int irmv_extract_armors_last_profile(unsigned long long out[8]) {
   if (!out) return 1;
-  for (int i = 0; i < 6; ++i) out[i] = g_armors_prof[i];
+  for (int i = 0; i < 8; ++i) out[i] = g_armors_prof[i];
   return 0;
 }
 
@@ -1272,8 +1273,8 @@ int irmv_extract_armors(const uint8_t *frames, int frames_on_device, int nframes
     ap.scratch_words_per_cta = wpc; ap.grid = grid;
     unsigned long long *d_prof = nullptr;
     if (getenv("IRMV_ARMOR_PROF")) {
-      IRMV_CUDA(cudaMalloc((void **)&d_prof, 48));
-      IRMV_CUDA(cudaMemset(d_prof, 0, 48));
+      IRMV_CUDA(cudaMalloc((void **)&d_prof, 64));
+      IRMV_CUDA(cudaMemset(d_prof, 0, 64));
     }
     ap.prof = d_prof;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -1288,7 +1289,7 @@ int irmv_extract_armors(const uint8_t *frames, int frames_on_device, int nframes
     g_armors_ms = ms;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (d_prof) {
-      IRMV_CUDA(cudaMemcpy(g_armors_prof, d_prof, 48, cudaMemcpyDeviceToHost));
+      IRMV_CUDA(cudaMemcpy(g_armors_prof, d_prof, 64, cudaMemcpyDeviceToHost));
       cudaFree(d_prof);
     }
     IRMV_CUDA(cudaMemcpy(out, d_out, slots * sizeof(ArmorOut), cudaMemcpyDeviceToHost));

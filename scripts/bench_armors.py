@@ -39,12 +39,13 @@ def main():
     if os.environ.get("IRMV_ARMOR_PROF"):
         import ctypes as C
         from irmv_detection_b200 import _lib
-        buf = (C.c_uint64 * 6)()
+        buf = (C.c_uint64 * 8)()
         _lib.lib().irmv_extract_armors_last_profile(C.byref(buf))
         v = [int(x) for x in buf]
         prof = {"rois": v[4], "cycles_per_roi": {"bitmap": v[0] / max(v[4], 1), "flood": v[1] / max(v[4], 1),
                                                  "walks_lights": v[2] / max(v[4], 1), "armor": v[3] / max(v[4], 1)},
-                "flood_rounds_per_roi": v[5] / max(v[4], 1)}
+                "flood_rounds_per_roi": v[5] / max(v[4], 1),
+                "warp_cycles_per_roi": {"recording_walks": v[6] / max(v[4], 1), "hull_rect_light": v[7] / max(v[4], 1)}}
     # ROI bytes the stage has to read (packed u8x3) + one 56-byte armor per detection
     roi_px = 0
     for f in range(n):
