@@ -444,6 +444,16 @@ def run_ours(args):
     if cpu is not None:
         line["cpu_baseline"] = cpu
     eng.close()
+    # ---- light-bar / armor extraction stage, measured on its own workload:
+    #      the random-init network's boxes say nothing about armors, so the stage gets seeded light-bar
+    #      scenes with their boxes; the cv2 chain of the reference runs on the host cores beside it
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "scripts"))
+            import bench_armors
+            line["armor_stage"] = bench_armors.measure(32, 10)
+        except Exception as ex:
+            line["armor_stage"] = {"error": str(ex)}
     emit(line)
 
 

@@ -13,13 +13,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main():
+def measure(n: int = 64, per: int = 10) -> dict:
     import torch
     import irmv_detection_b200 as irmv
     from irmv_detection_b200 import engine as E
     from oracle import armor_ref as A, preprocess_ref as PR
-    n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-    per = int(sys.argv[2]) if len(sys.argv) > 2 else 10
     scenes, boxes = [], np.zeros((n, 100), irmv.BBOX_DTYPE)
     for f in range(n):
         img, b, s, c = A.synth_armor_scene(per, 1000 + f)
@@ -65,7 +63,7 @@ def main():
     cpu(0)
     cpu1_s = time.perf_counter() - t0
     same = all([a.bbox_index for a in ref[f]] == np.nonzero(out[f]["valid"])[0].tolist() for f in range(n))
-    print(json.dumps({
+    return {
         "workload": f"{n} frames 1280x1024x3, {per} detections each (seeded light-bar scenes)",
         "gpu_kernel_ms": k, "gpu_rois_per_s": n * per / (k * 1e-3), "gpu_us_per_frame": k * 1e3 / n,
         "algorithmic_bytes": algo_bytes, "hbm_gbs_achieved": algo_bytes / (k * 1e-3) / 1e9,
@@ -73,7 +71,13 @@ def main():
         "speedup_vs_cpu_all_cores": (n * per / (k * 1e-3)) / (n * per / cpu_s),
         "phase_profile": prof,
         "armors": int(sum(int(o["valid"].sum()) for o in out)), "valid_sets_equal_cv2": bool(same),
-    }))
+    }
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+    per = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+    print(json.dumps(measure(n, per)))
 
 
 if __name__ == "__main__":

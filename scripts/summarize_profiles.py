@@ -70,9 +70,9 @@ def main():
         agg[k["name"]][0] += 1
         agg[k["name"]][1] += k["gpu__time_duration.sum"]
     out += ["## 1. Launch list of `python bench.py --steps 1 --warmup 3 --no-cpu-baseline`",
-            f"`profiles/r1_bench_launches.csv` ({len(L)} launches of the engine's kernels, `-s 394 -c 420`; the table is one step = two",
+            f"`profiles/r1_bench_launches.csv` ({len(L)} launches of the engine's kernels, `-s 374 -c 420`; the table is one step = two",
             f"128-frame replays = {len(step)} launches: set_src + stem + {sum(1 for k in step if k['name'].startswith('conv_')) // 2} GEMM launches + pool + decode + NMS + quads + PnP per replay;",
-            "eight 1x1 convs run as fused tails of their producers, conv0 inside the stem)", "",
+            "eleven 1x1 convs run as fused tails of their producers, conv0 inside the stem)", "",
             "| kernel | launches | total us | share |", "|---|---|---|---|"]
     for n, (c, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
         out.append(f"| `{n}` | {c} | {t/1e3:.1f} | {100*t/tot:.1f} % |")
@@ -138,6 +138,11 @@ def main():
             "`cuobjdump -sass irmv_detection_b200/libirmv_b200.so` contains `UTCHMMA` (tcgen05.mma), `LDTM` (tcgen05.ld), `UBLKCP`",
             "(cp.async.bulk), `UTCBAR` (tcgen05.commit), `SYNCS.*` (mbarrier), `ACQBULK`/`griddepcontrol` (programmatic dependent launch)",
             "and `HMMA.16816` (the stem's conv0).", ""]
+    if os.path.exists(os.path.join(P, "r1_armors_raw.csv")):
+        full_capture(out, "r1_armors", "## 6. `ncu --set full --import-source on` of `extract_armors_kernel` (64 frames x 10 detections, "
+                     "seeded light-bar scenes, `scripts/bench_armors.py`)", keys)
+        out += ["", "One CTA per detection; the border walks are serial per component (one lane), so the kernel is latency bound:",
+                "`scripts/bench_armors.py` with IRMV_ARMOR_PROF=1 gives the cycles per ROI by phase (`gpurun_out/bench_armors_prof.json`).", ""]
     json.dump({"kernel": "conv_raster_kernel (Detect P3 box.0|cls.0, 3x3 64->128)", "frames": 128,
                "dram_bytes_per_launch": (float(h0.get("dram__bytes_read.sum", 0)) + float(h0.get("dram__bytes_write.sum", 0))) * 1e6,
                "gpu_time_us": float(h0.get("gpu__time_duration.sum", 0)),
