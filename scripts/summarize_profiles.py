@@ -142,7 +142,7 @@ def main():
         full_capture(out, "r1_armors", "## 6. `ncu --set full --import-source on` of `extract_armors_kernel` (64 frames x 10 detections, "
                      "seeded light-bar scenes, `scripts/bench_armors.py`)", keys)
         out += ["", "One CTA per detection; the border walks are serial per component (one lane), so the kernel is latency bound:",
-                "`scripts/bench_armors.py` with IRMV_ARMOR_PROF=1 gives the cycles per ROI by phase (`gpurun_out/bench_armors_prof.json`).", ""]
+                "`scripts/bench_armors.py` with IRMV_ARMOR_PROF=1 gives the cycles per ROI by phase (`profiles/r1_armors_phase_profile.json`).", ""]
     json.dump({"kernel": "conv_raster_kernel (Detect P3 box.0|cls.0, 3x3 64->128)", "frames": 128,
                "dram_bytes_per_launch": (float(h0.get("dram__bytes_read.sum", 0)) + float(h0.get("dram__bytes_write.sum", 0))) * 1e6,
                "gpu_time_us": float(h0.get("gpu__time_duration.sum", 0)),
