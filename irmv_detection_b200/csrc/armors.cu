@@ -36,6 +36,7 @@ constexpr int kSmemWords = 2048;       // per bitmap: ROIs up to 64 K padded pix
 constexpr int kRows = 256;             // ... and up to this many rows (per-warp row-extreme arrays, hull)
 constexpr int kMaxRows = 1088;         // ROI height limit of the global-scratch path
 constexpr int kHullSmem = 2 * kRows + 2, kHullGlobal = 2 * kMaxRows + 2;   // a row adds at most two hull vertices
+constexpr int kCandCap = 64;         // ROIs with at most this many start candidates spread them over the warps
 constexpr int kScratchSlots = 64;      // global scratch slots shared by the CTAs that meet a large ROI
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -60,6 +61,8 @@ struct Shared {
   int nbest;
   int lock;
   int slot;
+  int ncand;                           // start candidates of the ROI (may exceed kCandCap)
+  int cand[kCandCap];                  // x | y << 16, padded ROI coordinates
 };
 
 // words of one global scratch slot: two whole-frame bitmaps + the per-warp arrays
@@ -444,58 +447,73 @@ __device__ __forceinline__ void roi_body(Shared &sh, const ArmorParams &p, uint3
   if (p.prof && tid == 0) t2 = clock64();
   // 3. border walks from the start candidates, 4. lights
   const int step_cap = 8 * PW * PH;
-  const int nchunks = (words + 31) >> 5;
-  for (int chunk = warp; chunk < nchunks; chunk += kWarps) {
-    const int w = chunk * 32 + lane;
-    uint32_t cand = 0;
-    int row = 0, wi = 0;
-    if (w < words) {
-      row = w / wpr; wi = w - row * wpr;
-      if (row >= 1 && row <= PH - 2) {
-        const uint32_t f0 = fg[w], e0 = ext[w];
-        const uint32_t ep = wi > 0 ? ext[w - 1] >> 31 : 0u;
-        const uint32_t un = fg[w - wpr];
-        const uint32_t up = wi > 0 ? fg[w - wpr - 1] >> 31 : 0u, ux = wi + 1 < wpr ? fg[w - wpr + 1] << 31 : 0u;
-        const uint32_t ext_w = (e0 << 1) | ep;
-        const uint32_t above = un | (un << 1) | up | (un >> 1) | ux;
-        cand = f0 & ext_w & ~above;
+  // start candidates: foreground, exterior background to the W, background to the NW, N, NE
+  auto candidates_of = [&](int w, int row, int wi) -> uint32_t {
+    if (row < 1 || row > PH - 2) return 0u;
+    const uint32_t f0 = fg[w], e0 = ext[w];
+    if (!f0) return 0u;
+    const uint32_t ep = wi > 0 ? ext[w - 1] >> 31 : 0u;
+    const uint32_t un = fg[w - wpr];
+    const uint32_t up = wi > 0 ? fg[w - wpr - 1] >> 31 : 0u, ux = wi + 1 < wpr ? fg[w - wpr + 1] << 31 : 0u;
+    const uint32_t ext_w = (e0 << 1) | ep;
+    const uint32_t above = un | (un << 1) | up | (un >> 1) | ux;
+    return f0 & ext_w & ~above;
+  };
+  {
+    const int d_row = kThreads / wpr, d_wi = kThreads - d_row * wpr;
+    int row = tid / wpr, wi = tid - row * wpr;
+    for (int w = tid; w < words; w += kThreads) {
+      uint32_t cand = candidates_of(w, row, wi);
+      while (cand) {
+        const int b = __ffs(cand) - 1;
+        cand &= cand - 1;
+        const int idx = atomicAdd(&sh.ncand, 1);
+        if (idx < kCandCap) sh.cand[idx] = (wi * 32 + b) | (row << 16);
+      }
+      row += d_row; wi += d_wi;
+      if (wi >= wpr) { wi -= wpr; ++row; }
+    }
+  }
+  __syncthreads();
+  const int ncand_roi = sh.ncand;
+  if (ncand_roi <= kCandCap) {
+    // few candidates (the usual case: a light bar has one, a number sticker a handful): the warps
+    // take them round-robin, one walk each, recording the row extremes as it goes, so a kept border
+    // is walked once and the borders of one ROI are walked side by side
+    for (int c = warp; c < ncand_roi; c += kWarps) {
+      const int X0 = sh.cand[c] & 0xffff, Y0 = sh.cand[c] >> 16;
+      const int span = PH - 1 - Y0;                        // rows the border can reach
+      for (int r = lane; r < span; r += 32) { wb.rmin[r] = 32767; wb.rmax[r] = -1; }
+      __syncwarp();
+      int ok = 0, ymax = 0;
+      long long c0 = 0, c1 = 0;
+      if (lane == 0) {
+        int npts = 0;
+        if (p.prof) c0 = clock64();
+        ok = walk_border<true>(fg, wpr, X0, Y0, step_cap, npts, ymax, wb.rmin, wb.rmax) && npts >= 5;
+        if (p.prof) c1 = clock64();
+      }
+      ok = __shfl_sync(kFull, ok, 0);
+      const int YM = __shfl_sync(kFull, ymax, 0);
+      if (ok) process_border(sh, wb, fg, wpr, X0, Y0, YM, false, step_cap, min_x, min_y, p, lane);
+      __syncwarp();
+      if (p.prof && lane == 0) {
+        atomicAdd(p.prof + 6, (unsigned long long)(c1 - c0));
+        atomicAdd(p.prof + 7, (unsigned long long)(clock64() - c1));
       }
     }
-    int ncand = __popc(cand);
-#pragma unroll
-    for (int off = 16; off; off >>= 1) ncand += __shfl_xor_sync(kFull, ncand, off);
-    if (ncand <= 4) {
-      // few candidates (the usual case: a light bar has one): one walk each, recording the row
-      // extremes as it goes, so a kept border is walked once
-      uint32_t have;
-      while ((have = __ballot_sync(kFull, cand != 0)) != 0) {
-        const int src = __ffs(have) - 1;
-        int x0 = 0;
-        if (lane == src) { x0 = wi * 32 + __ffs(cand) - 1; cand &= cand - 1; }
-        const int X0 = __shfl_sync(kFull, x0, src), Y0 = __shfl_sync(kFull, row, src);
-        const int span = PH - 1 - Y0;                      // rows the border can reach
-        for (int r = lane; r < span; r += 32) { wb.rmin[r] = 32767; wb.rmax[r] = -1; }
-        __syncwarp();
-        int ok = 0, ymax = 0;
-        long long c0 = 0, c1 = 0;
-        if (lane == 0) {
-          int npts = 0;
-          if (p.prof) c0 = clock64();
-          ok = walk_border<true>(fg, wpr, X0, Y0, step_cap, npts, ymax, wb.rmin, wb.rmax) && npts >= 5;
-          if (p.prof) c1 = clock64();
-        }
-        ok = __shfl_sync(kFull, ok, 0);
-        const int YM = __shfl_sync(kFull, ymax, 0);
-        if (ok) process_border(sh, wb, fg, wpr, X0, Y0, YM, false, step_cap, min_x, min_y, p, lane);
-        __syncwarp();
-        if (p.prof && lane == 0) {
-          atomicAdd(p.prof + 6, (unsigned long long)(c1 - c0));
-          atomicAdd(p.prof + 7, (unsigned long long)(clock64() - c1));
-        }
+  } else {
+    // many candidates (speckle): a warp takes 32 words at a time, every lane walks its own
+    // candidate for ownership and vertex count; the few that pass are walked again, recording
+    const int nchunks = (words + 31) >> 5;
+    for (int chunk = warp; chunk < nchunks; chunk += kWarps) {
+      const int w = chunk * 32 + lane;
+      uint32_t cand = 0;
+      int row = 0, wi = 0;
+      if (w < words) {
+        row = w / wpr; wi = w - row * wpr;
+        cand = candidates_of(w, row, wi);
       }
-    } else {
-      // many candidates (speckle): every lane walks its own candidate for ownership and vertex
-      // count; the few that pass are walked again, recording
       while (__any_sync(kFull, cand != 0)) {
         bool acc = false;
         int x0 = 0, y0 = 0, ymax = 0;
@@ -589,7 +607,7 @@ __global__ void __launch_bounds__(kThreads, 6) extract_armors_kernel(ArmorParams
     const int words_roi = (rh + 2) * ((rw + 2 + 31) >> 5);
     const bool large = words_roi > kSmemWords || rh > kRows;
     if (tid == 0) {
-      sh.nbest = 0; sh.lock = 0; sh.slot = -1;
+      sh.nbest = 0; sh.lock = 0; sh.slot = -1; sh.ncand = 0;
       if (large) {                       // take one of the global scratch slots
         int sl = blockIdx.x % kScratchSlots;
         while (atomicCAS(p.slot_locks + sl, 0, 1) != 0) sl = (sl + 1) % kScratchSlots;
