@@ -149,6 +149,16 @@ int irmv_engine_enable_pnp(irmv_engine *e, const double K[9], const double D[5],
                            float corner_sy);
 /* rvecs/tvecs: nframes*max_det*3 doubles; slot i of frame f is valid when i < counts[f]. */
 int irmv_engine_fetch_poses(irmv_engine *e, int nframes, double *rvecs, double *tvecs, uint8_t *ok);
+/* ---- keypoint variant (BASELINE.json configs[2], north_star "armor-keypoint decode") -------------
+ * A weight file with 72 convolutions carries the ultralytics Pose branch (kpt_shape [4, 2]: the four
+ * armor corners LB, LT, RT, RB per anchor).  The engine then decodes the keypoints of every kept
+ * detection ((raw * 2 + grid) * stride) and, with irmv_engine_enable_pnp, solves the pose on them
+ * instead of the box corners. */
+int irmv_engine_has_keypoints(irmv_engine *e);
+/* kpts: nframes*max_det*8 floats {x, y} x 4, source pixels; slot i of frame f is valid when i < counts[f].
+ * ticket < 0: the last synchronous call; otherwise a collected pipelined batch. */
+int irmv_engine_fetch_keypoints(irmv_engine *e, int ticket, int nframes, float *kpts);
+
 /* ---- light bars -> armors (IrmDetector::extract_armors, src/irm_detector.cpp:292-355) ---------- */
 int irmv_armor_params_default(irmv_armor_params *p);
 /* Stage entry: nframes frames as the camera wrote them (the kernel reads the rotated view itself),

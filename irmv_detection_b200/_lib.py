@@ -66,6 +66,8 @@ SYMBOLS = {
     "irmv_engine_stream": (_P, [_P]),
     "irmv_engine_enable_pnp": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_float, C.c_float]),
     "irmv_engine_fetch_poses": (C.c_int, [_P, C.c_int, _P, _P, _P]),
+    "irmv_engine_has_keypoints": (C.c_int, [_P]),
+    "irmv_engine_fetch_keypoints": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "irmv_armor_params_default": (C.c_int, [C.POINTER(ArmorParams)]),
     "irmv_extract_armors": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int,
                                       C.POINTER(ArmorParams), C.c_int, _P]),

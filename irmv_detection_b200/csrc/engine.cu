@@ -208,6 +208,8 @@ struct Lane {
   float *pnp_pts = nullptr;                // [S*max_det][8]
   double *pnp_rvec = nullptr, *pnp_tvec = nullptr;
   uint8_t *pnp_ok = nullptr;
+  const __half *kpt[3] = {nullptr, nullptr, nullptr};   // keypoint-branch outputs per scale (plane 0 = the 8 raw values)
+  float *kpts = nullptr;                   // [S*max_det][8] decoded keypoints of the kept detections, network pixels
   ArmorOut *armors = nullptr;              // [S*max_det], allocated by irmv_engine_enable_armors
   uint32_t *armor_scratch = nullptr;       // per-CTA bitmaps of ROIs that do not fit in shared memory
   cudaEvent_t stage_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -229,6 +231,59 @@ __global__ void quads_from_dets_kernel(const int32_t *num, const float *boxes, i
   float4 *o = reinterpret_cast<float4 *>(pts + (size_t)i * 8);
   o[0] = make_float4(x1, y2, x1, y1);
   o[1] = make_float4(x2, y1, x2, y2);
+}
+
+// Keypoint branch (ultralytics Pose, kpt_shape [4, 2]): for every kept detection, the 8 raw values at
+// its anchor -> (raw * 2 + grid) * stride, network pixels (oracle/yolov8n_ref.decode_keypoints).
+// index = flat anchor * nc + class, anchors scale-major 80x80 | 40x40 | 20x20.
+__global__ void kpts_from_dets_kernel(const int32_t *num, const int32_t *index, int n, int max_det, int nc,
+                                      const __half *k0, const __half *k1, const __half *k2, float *kpts) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * max_det) return;
+  const int f = i / max_det, k = i - f * max_det;
+  float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+  if (k < num[f]) {
+    int a = index[i] / nc;
+    const __half *base = k0;
+    int hw = 80;
+    float stride = 8.f;
+    if (a >= 8000) { a -= 8000; base = k2; hw = 20; stride = 32.f; }
+    else if (a >= 6400) { a -= 6400; base = k1; hw = 40; stride = 16.f; }
+    const int gy = a / hw, gx = a - gy * hw;
+    const uint4 raw = *reinterpret_cast<const uint4 *>(base + pr_index(f, gy, gx, hw, hw) * 8);
+    const __half2 *h = reinterpret_cast<const __half2 *>(&raw);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 p = __half22float2(h[j]);
+      v[2 * j] = __fmul_rn(__fadd_rn(__fmul_rn(p.x, 2.f), (float)gx), stride);
+      v[2 * j + 1] = __fmul_rn(__fadd_rn(__fmul_rn(p.y, 2.f), (float)gy), stride);
+    }
+    lo = make_float4(v[0], v[1], v[2], v[3]);
+    hi = make_float4(v[4], v[5], v[6], v[7]);
+  }
+  float4 *o = reinterpret_cast<float4 *>(kpts + (size_t)i * 8);
+  o[0] = lo; o[1] = hi;
+}
+
+// Keypoints -> PnP quads (the four keypoints are the armor corners in PnPSolver's order LB, LT, RT, RB,
+// reference src/pnp_solver.cpp:41-44), scaled from network pixels to the calibration frame.
+__global__ void quads_from_kpts_kernel(const int32_t *num, const float *kpts, int n, int max_det, float sx, float sy,
+                                       float px, float py, float *pts) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * max_det) return;
+  const int f = i / max_det, k = i - f * max_det;
+  float q[8] = {150.f, 160.f, 150.f, 140.f, 200.f, 140.f, 200.f, 160.f};    // inactive slots: a fixed valid quad
+  if (k < num[f]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      q[2 * j] = (kpts[(size_t)i * 8 + 2 * j] - px) * sx;
+      q[2 * j + 1] = (kpts[(size_t)i * 8 + 2 * j + 1] - py) * sy;
+    }
+  }
+  float4 *o = reinterpret_cast<float4 *>(pts + (size_t)i * 8);
+  o[0] = make_float4(q[0], q[1], q[2], q[3]);
+  o[1] = make_float4(q[4], q[5], q[6], q[7]);
 }
 
 }  // namespace
@@ -273,6 +328,7 @@ struct irmv_engine {
   PnpConsts pnp_c{};
   float pnp_sx = 1.f, pnp_sy = 1.f, pnp_px = 0.f, pnp_py = 0.f;
   float corner_sx = 1.f, corner_sy = 1.f;   // source pixels -> calibration frame (irmv_engine_enable_pnp)
+  bool pose = false;                        // the weight file holds the keypoint branch (72 convs)
   bool armors_on = false;                   // light-bar extraction between NMS and PnP
   irmv_armor_params armor_prm{};
   int last_slot = -1;
@@ -528,6 +584,19 @@ bool build_lane(irmv_engine *e, Lane &ln) {
     ln.heads.cls[i] = co.p; ln.heads.cls_ps[i] = co.pstride;
     ln.heads.padded = 1;
   }
+  if (e->pose)
+    for (int i = 0; i < 3; ++i) {          // keypoint branch: 3x3 ch->16, 3x3 16->16, 1x1 16->8 (padded to 16 planes-wise)
+      Tensor k0, k1, ko;
+      char nk[8];
+      snprintf(nk, sizeof nk, "kpt%d", i);
+      if (!new_tensor(ln, S, hw[i], hw[i], 16, k0) || !new_tensor(ln, S, hw[i], hw[i], 16, k1) ||
+          !new_tensor(ln, S, hw[i], hw[i], 16, ko, nk))
+        return false;
+      add_conv(e, ln, *e->convs[ci++], {{feat[i], 0, feat[i]->C, 0}}, hw[i], hw[i], k0, 0);
+      add_conv(e, ln, *e->convs[ci++], {{&k0, 0, 16, 0}}, hw[i], hw[i], k1, 0);
+      add_conv(e, ln, *e->convs[ci++], {{&k1, 0, 16, 0}}, hw[i], hw[i], ko, 0);
+      ln.kpt[i] = ko.p;
+    }
   if (ci != e->convs.size()) { set_error("internal: conv count mismatch"); return false; }
   fuse_tails(e, ln);
   // decode / NMS scratch and outputs
@@ -539,6 +608,7 @@ bool build_lane(irmv_engine *e, Lane &ln) {
   if (!lane_alloc(ln, (void **)&ln.det.dev, ln.det.bytes)) return false;
   if (!lane_alloc(ln, (void **)&ln.src_word, sizeof(void *))) return false;
   const size_t slots = (size_t)S * e->cfg.max_det;
+  if (e->pose && !lane_alloc(ln, (void **)&ln.kpts, slots * 32)) return false;
   if (!lane_alloc(ln, (void **)&ln.pnp_pts, slots * 32) || !lane_alloc(ln, (void **)&ln.pnp_rvec, slots * 24) ||
       !lane_alloc(ln, (void **)&ln.pnp_tvec, slots * 24) || !lane_alloc(ln, (void **)&ln.pnp_ok, slots))
     return false;
@@ -608,6 +678,13 @@ int issue_replay(irmv_engine *e, Lane &ln, int n, cudaStream_t st, int *launches
   IRMV_CUDA(launch_decode(ln.heads, n, e->nc, e->cfg.score_thr, ln.nms, nullptr, st)); ++cnt;
   DetOut out{ln.det.num(), ln.det.boxes(), ln.det.scores(), ln.det.classes(), ln.det.index()};
   IRMV_CUDA(launch_nms(ln.nms, n, kNumAnchors, e->nc, e->cfg.iou_thr, e->cfg.max_det, out, st)); ++cnt;
+  if (e->pose) {
+    const int total = n * e->cfg.max_det;
+    kpts_from_dets_kernel<<<(total + 127) / 128, 128, 0, st>>>(ln.det.num(), ln.det.index(), n, e->cfg.max_det, e->nc,
+                                                              ln.kpt[0], ln.kpt[1], ln.kpt[2], ln.kpts);
+    IRMV_CUDA(cudaGetLastError());
+    ++cnt;
+  }
   if (mark(3)) return 1;
   if (e->armors_on) {
     // reference message_callback: extract_armors(get_rotated_image(), bboxes), then solvePnP per armor
@@ -641,8 +718,12 @@ int issue_replay(irmv_engine *e, Lane &ln, int n, cudaStream_t st, int *launches
     }
   } else if (e->pnp_on) {
     const int total = n * e->cfg.max_det;
-    quads_from_dets_kernel<<<(total + 127) / 128, 128, 0, st>>>(ln.det.num(), ln.det.boxes(), n, e->cfg.max_det,
-                                                               e->pnp_sx, e->pnp_sy, e->pnp_px, e->pnp_py, ln.pnp_pts);
+    if (e->pose)    // the keypoints are the armor corners
+      quads_from_kpts_kernel<<<(total + 127) / 128, 128, 0, st>>>(ln.det.num(), ln.kpts, n, e->cfg.max_det, e->pnp_sx,
+                                                                 e->pnp_sy, e->pnp_px, e->pnp_py, ln.pnp_pts);
+    else
+      quads_from_dets_kernel<<<(total + 127) / 128, 128, 0, st>>>(ln.det.num(), ln.det.boxes(), n, e->cfg.max_det,
+                                                                 e->pnp_sx, e->pnp_sy, e->pnp_px, e->pnp_py, ln.pnp_pts);
     IRMV_CUDA(cudaGetLastError());
     PnpOut po{ln.pnp_rvec, ln.pnp_tvec, ln.pnp_ok, nullptr, nullptr, nullptr, nullptr};
     IRMV_CUDA(launch_pnp(e->pnp_c, ln.pnp_pts, total, 0, po, st));
@@ -656,6 +737,7 @@ int issue_replay(irmv_engine *e, Lane &ln, int n, cudaStream_t st, int *launches
 static_assert(sizeof(ArmorOut) == sizeof(irmv_armor) && sizeof(irmv_armor) == 56, "ArmorOut mirrors irmv_armor");
 // byte offset of the armor block inside a pinned result set (after num, boxes, scores, classes, index, poses)
 size_t armors_offset(size_t B, size_t md) { return (B * 4 + B * md * 28 + B * md * 49 + 63) & ~(size_t)63; }
+size_t kpts_offset(size_t B, size_t md) { return armors_offset(B, md) + B * md * sizeof(ArmorOut); }
 
 int run_replay(irmv_engine *e, Lane &ln, int n) {
   if (!e->cfg.use_graph) return issue_replay(e, ln, n, ln.stream, &ln.launches_per_replay);
@@ -740,6 +822,9 @@ int enqueue(irmv_engine *e, const uint8_t *frames_dev, int n, const uint8_t *fra
     if (e->armors_on)
       IRMV_CUDA(cudaMemcpyAsync(h + armors_offset(B, md) + (size_t)f0 * md * sizeof(ArmorOut), ln.armors,
                                 (size_t)nf * md * sizeof(ArmorOut), cudaMemcpyDeviceToHost, ln.stream));
+    if (e->pose)
+      IRMV_CUDA(cudaMemcpyAsync(h + kpts_offset(B, md) + (size_t)f0 * md * 32, ln.kpts, (size_t)nf * md * 32,
+                                cudaMemcpyDeviceToHost, ln.stream));
   }
   for (int l = 0; l < used; ++l) {
     IRMV_CUDA(cudaEventRecord(e->lanes[l].done, e->lanes[l].stream));
@@ -817,7 +902,8 @@ int irmv_engine_create(const char *weights_path, const irmv_engine_config *cfg, 
   e->num_sms = prop.multiProcessorCount;
   std::vector<FileConv> fc;
   if (!read_weights(weights_path, e->nc, fc)) return 4;
-  if (fc.size() != 63 || e->nc != IRMV_NUM_CLASSES) { set_error("weight file is not YOLOv8n nc=14"); return 4; }
+  if ((fc.size() != 63 && fc.size() != 72) || e->nc != IRMV_NUM_CLASSES) { set_error("weight file is not YOLOv8n nc=14"); return 4; }
+  e->pose = fc.size() == 72;                                   // + keypoint branch (kpt_shape [4, 2])
   // 63 reference convs -> 60 GEMMs (Detect box.0|cls.0 merged per scale)
   auto single = [&](size_t i, int cin_pad, std::vector<int> seg) {
     e->convs.emplace_back(new HostConv(make_conv({&fc[i]}, cin_pad, seg)));
@@ -842,6 +928,13 @@ int irmv_engine_create(const char *weights_path, const irmv_engine_config *cfg, 
     single(b + 4, 64, {64});
     single(b + 5, 64, {64});
   }
+  if (e->pose)
+    for (int s = 0; s < 3; ++s) {
+      size_t b = 63 + (size_t)s * 3;
+      single(b + 0, fc[b].cin, {fc[b].cin});
+      single(b + 1, 16, {16});
+      single(b + 2, 16, {16});
+    }
   for (auto &c : e->convs) if (!upload(*c)) return 5;
   {
     // stem weights: conv0 as FP32 [16][9 taps][3] + bias
@@ -880,7 +973,7 @@ int irmv_engine_create(const char *weights_path, const irmv_engine_config *cfg, 
   }
   IRMV_CUDA(cudaMalloc((void **)&e->slot_dev, e->frame_bytes));
   const size_t md = cfg->max_det, B = cfg->max_batch;
-  size_t res_bytes = armors_offset(B, md) + B * md * sizeof(ArmorOut) + 64;
+  size_t res_bytes = kpts_offset(B, md) + B * md * 32 + 64;
   IRMV_CUDA(cudaHostAlloc((void **)&e->res_host, res_bytes, cudaHostAllocDefault));
   memset(e->res_host, 0, res_bytes);
   e->res_bytes = res_bytes;
@@ -1215,6 +1308,28 @@ double irmv_extract_armors_last_device_ms(void) { return g_armors_ms; }
 int irmv_extract_armors_last_profile(unsigned long long out[8]) {
   if (!out) return 1;
   for (int i = 0; i < 8; ++i) out[i] = g_armors_prof[i];
+  return 0;
+}
+
+int irmv_engine_has_keypoints(irmv_engine *e) { return e && e->pose ? 1 : 0; }
+
+// Keypoints of the kept detections in source pixels (the same shift and scale parse() applies to the
+// boxes, reference src/yolo_engine.cpp:211-214): kpts[nframes][max_det][4][2].
+int irmv_engine_fetch_keypoints(irmv_engine *e, int ticket, int nframes, float *kpts) {
+  if (!e || !kpts || nframes < 1 || nframes > e->cfg.max_batch) { set_error("bad argument"); return 1; }
+  if (!e->pose) { set_error("the weight file has no keypoint branch"); return 2; }
+  const size_t md = e->cfg.max_det, B = e->cfg.max_batch;
+  const uint8_t *h = ticket < 0 ? e->res_host : e->sets[ticket % kSets].res_host;
+  if (!h) { set_error("nothing was submitted under this ticket"); return 2; }
+  const float *src = reinterpret_cast<const float *>(h + kpts_offset(B, md));
+  int pad_x, pad_y, new_w, new_h;
+  letterbox_geometry(e->cfg.src_width, e->cfg.src_height, e->cfg.resize_mode, &pad_x, &pad_y, &new_w, &new_h);
+  const float sx = (float)e->cfg.src_width / new_w, sy = (float)e->cfg.src_height / new_h;
+  const float px = (float)pad_x, py = (float)pad_y;
+  for (size_t i = 0; i < (size_t)nframes * md * 4; ++i) {
+    kpts[2 * i] = (src[2 * i] - px) * sx;
+    kpts[2 * i + 1] = (src[2 * i + 1] - py) * sy;
+  }
   return 0;
 }
 

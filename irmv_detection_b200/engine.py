@@ -201,6 +201,16 @@ class YoloEngine:
                 "irmv_engine_fetch_poses")
         return rv, tv, ok.astype(bool)
 
+    def has_keypoints(self) -> bool:
+        """True when the weight file carries the keypoint branch (72 convolutions)."""
+        return bool(self._lib.irmv_engine_has_keypoints(self._h))
+
+    def fetch_keypoints(self, n: int, ticket: int = -1) -> np.ndarray:
+        """Keypoints (armor corners LB, LT, RT, RB) of the kept detections, source pixels: f32[n, max_det, 4, 2]."""
+        out = np.zeros((n, self.max_det, 4, 2), np.float32)
+        L.check(self._lib.irmv_engine_fetch_keypoints(self._h, ticket, n, out.ctypes.data), "irmv_engine_fetch_keypoints")
+        return out
+
     def enable_armors(self, **params) -> None:
         """Fuse IrmDetector::extract_armors (light bars -> armors) into every replay, between NMS and
         PnP; keyword arguments override the node-parameter defaults (see armor_params)."""

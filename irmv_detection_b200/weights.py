@@ -8,7 +8,7 @@ fixed order.  Every stored value is exactly representable in FP16, so the FP32 o
 FP16 tensor-core path start from identical parameters.
 
 File layout (little endian):
-    char[4] "IRMW" | u32 version(=1) | u32 nc | u32 n_convs
+    char[4] "IRMW" | u32 version(=1) | u32 nc | u32 n_convs (63, or 72 with the keypoint branch)
     per conv: u32 cin, cout, k, stride, act | f32 w[cout][cin][k][k] | f32 bias[cout]
 """
 from __future__ import annotations
@@ -48,8 +48,12 @@ def _c2f(prefix: str, c1: int, c2: int, n: int) -> List[ConvSpec]:
     return out
 
 
-def conv_specs(nc: int = NC) -> List[ConvSpec]:
-    """The 63 convolutions in execution order (ultralytics yolov8.yaml, scale n)."""
+NK = 8           # pose variant: kpt_shape = [4, 2], the four armor corners (x, y) per anchor
+
+
+def conv_specs(nc: int = NC, pose: bool = False) -> List[ConvSpec]:
+    """The 63 convolutions in execution order (ultralytics yolov8.yaml, scale n); with pose=True the
+    nine convolutions of the keypoint branch (ultralytics `Pose.cv4`, kpt_shape [4, 2]) follow."""
     s: List[ConvSpec] = []
     s.append(ConvSpec("m0", 3, 16, 3, 2, 1))
     s.append(ConvSpec("m1", 16, 32, 3, 2, 1))
@@ -78,6 +82,12 @@ def conv_specs(nc: int = NC) -> List[ConvSpec]:
         s.append(ConvSpec(f"m22.cls{i}.1", c3, c3, 3, 1, 1))
         s.append(ConvSpec(f"m22.cls{i}.2", c3, nc, 1, 1, 0))
     assert len(s) == 63
+    if pose:
+        c4 = max(64 // 4, NK)
+        for i, ch in enumerate((64, 128, 256)):
+            s.append(ConvSpec(f"m22.kpt{i}.0", ch, c4, 3, 1, 1))
+            s.append(ConvSpec(f"m22.kpt{i}.1", c4, c4, 3, 1, 1))
+            s.append(ConvSpec(f"m22.kpt{i}.2", c4, NK, 1, 1, 0))
     return s
 
 
@@ -133,7 +143,7 @@ INIT_GAIN = {
 CLS_BIAS = -8.0
 
 
-def random_init(seed: int = 0, nc: int = NC, cls_bias: float = CLS_BIAS
+def random_init(seed: int = 0, nc: int = NC, cls_bias: float = CLS_BIAS, pose: bool = False
                 ) -> List[Tuple[np.ndarray, np.ndarray]]:
     """Seeded random-init, FP16-exact, activations kept O(1) through the SiLU chain.
 
@@ -144,11 +154,16 @@ def random_init(seed: int = 0, nc: int = NC, cls_bias: float = CLS_BIAS
     """
     rng = np.random.default_rng(seed)
     out = []
-    for i, c in enumerate(conv_specs(nc)):
+    gains = INIT_GAIN.get(seed, INIT_GAIN[0])
+    for i, c in enumerate(conv_specs(nc, pose)):
         fan_in = c.cin * c.k * c.k
         w = rng.standard_normal((c.cout, c.cin, c.k, c.k)).astype(np.float32) / np.float32(math.sqrt(fan_in))
         b = rng.standard_normal(c.cout).astype(np.float32) * np.float32(0.05)
-        w = w * np.float32(INIT_GAIN.get(seed, INIT_GAIN[0])[i])
+        # (the keypoint branch comes after the 63 calibrated convs and draws from the stream last, so the
+        # box/class network of a seed is the same with and without it; kpt.2 is kept small like box.2:
+        # raw offsets of a few tenths of a cell)
+        w = w * np.float32(gains[i] if i < len(gains) else ((0.05 if c.name.startswith("m22.kpt2") else 0.1)
+                                                              if c.name.endswith(".2") else 1.5))
         if c.name.startswith("m22.cls") and c.name.endswith(".2"):
             b = b + np.float32(cls_bias)
         w = w.astype(np.float16).astype(np.float32)
@@ -158,7 +173,7 @@ def random_init(seed: int = 0, nc: int = NC, cls_bias: float = CLS_BIAS
 
 
 def save(path: str, tensors: List[Tuple[np.ndarray, np.ndarray]], nc: int = NC) -> None:
-    specs = conv_specs(nc)
+    specs = conv_specs(nc, pose=len(tensors) == 72)
     assert len(specs) == len(tensors)
     with open(path, "wb") as f:
         f.write(MAGIC)
@@ -179,7 +194,7 @@ def load(path: str) -> Tuple[int, List[Tuple[ConvSpec, np.ndarray, np.ndarray]]]
     if version != VERSION:
         raise ValueError(f"{path}: unsupported version {version}")
     off = 16
-    specs = conv_specs(nc)
+    specs = conv_specs(nc, pose=n == 72)      # 63 convs: detector; 72: detector + keypoint branch
     if n != len(specs):
         raise ValueError(f"{path}: {n} convs, expected {len(specs)}")
     out = []
@@ -199,6 +214,6 @@ def load(path: str) -> Tuple[int, List[Tuple[ConvSpec, np.ndarray, np.ndarray]]]
     return nc, out
 
 
-def write_random(path: str, seed: int = 0, nc: int = NC) -> str:
-    save(path, random_init(seed, nc), nc)
+def write_random(path: str, seed: int = 0, nc: int = NC, pose: bool = False) -> str:
+    save(path, random_init(seed, nc, pose=pose), nc)
     return path

@@ -79,9 +79,10 @@ class SPPF(nn.Module):
 class YoloV8n(nn.Module):
     """Module order matches irmv_detection_b200.weights.conv_specs()."""
 
-    def __init__(self, nc=14):
+    def __init__(self, nc=14, pose=False):
         super().__init__()
         self.nc = nc
+        self.pose = pose
         self.m0 = Conv(3, 16, 3, 2)
         self.m1 = Conv(16, 32, 3, 2)
         self.m2 = C2f(32, 32, 1, True)
@@ -105,6 +106,10 @@ class YoloV8n(nn.Module):
         self.cls = nn.ModuleList(
             nn.Sequential(Conv(ch, c3, 3), Conv(c3, c3, 3), Conv(c3, nc, 1, 1, act=False))
             for ch in (64, 128, 256))
+        if pose:            # ultralytics `Pose.cv4`, kpt_shape [4, 2]: c4 = max(ch[0] // 4, nk)
+            self.kpt = nn.ModuleList(
+                nn.Sequential(Conv(ch, 16, 3), Conv(16, 16, 3), Conv(16, 8, 1, 1, act=False))
+                for ch in (64, 128, 256))
 
     def convs_in_order(self):
         out = [self.m0.conv, self.m1.conv]
@@ -122,6 +127,9 @@ class YoloV8n(nn.Module):
         for i in range(3):
             out += [self.box[i][0].conv, self.box[i][1].conv, self.box[i][2].conv]
             out += [self.cls[i][0].conv, self.cls[i][1].conv, self.cls[i][2].conv]
+        if self.pose:
+            for i in range(3):
+                out += [self.kpt[i][0].conv, self.kpt[i][1].conv, self.kpt[i][2].conv]
         return out
 
     def load_irmw(self, path):
@@ -163,12 +171,16 @@ class YoloV8n(nn.Module):
         x21 = tap("m21", self.m21(torch.cat((x19, x9), 1)))
         outs = []
         for i, f in enumerate((x15, x18, x21)):
-            outs.append((self.box[i](f), self.cls[i](f)))
+            o = (self.box[i](f), self.cls[i](f))
+            outs.append(o + (self.kpt[i](f),) if self.pose else o)
         return outs
 
     def forward(self, x):
         """x f32[B,3,640,640] -> boxes xyxy f32[B,8400,4] (net px), scores f32[B,8400,nc]."""
-        return decode_heads(self.features(x))
+        outs = self.features(x)
+        if self.pose:
+            return decode_heads(outs) + (decode_keypoints(outs),)
+        return decode_heads(outs)
 
 
 def make_anchors(sizes=(80, 40, 20)):
@@ -203,8 +215,22 @@ def decode_heads(outs):
     return boxes, scores
 
 
+def decode_keypoints(outs):
+    """ultralytics `Pose.kpts_decode` for kpt_shape [4, 2]: (raw * 2 + (anchor - 0.5)) * stride, i.e.
+    (raw * 2 + grid) * stride.  Returns f32[B, A, 4, 2] in network pixels; anchor order as decode_heads."""
+    B = outs[0][2].shape[0]
+    raw = torch.cat([o[2].reshape(B, 8, -1) for o in outs], 2)              # [B,8,A]
+    A = raw.shape[2]
+    anchors, strides = make_anchors(tuple(int(o[0].shape[2]) for o in outs))
+    g = torch.from_numpy(anchors - 0.5).t().unsqueeze(0)                    # [1,2,A] grid x, y
+    s = torch.from_numpy(strides).view(1, 1, 1, A)
+    k = raw.view(B, 4, 2, A)
+    return ((k * 2.0 + g.unsqueeze(1)) * s).permute(0, 3, 1, 2).contiguous()
+
+
 def build(weights_path, nc=14):
+    from irmv_detection_b200 import weights as W
     torch.manual_seed(0)
-    m = YoloV8n(nc).eval()
+    m = YoloV8n(nc, pose=len(W.load(weights_path)[1]) == 72).eval()
     m.load_irmw(weights_path)
     return m

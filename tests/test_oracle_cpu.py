@@ -205,6 +205,32 @@ def test_network_oracle_vs_opencv_dnn(base_image, weights_seed0, tmp_path):
     assert np.abs(out - ref).max() < 5e-3
 
 
+def test_keypoint_variant_weights_and_decode(tmp_path):
+    """72-conv weight file = the 63 detector convs of the same seed + the Pose branch; keypoint decode is
+    (raw * 2 + grid) * stride in anchor order (ultralytics Pose.kpts_decode, kpt_shape [4, 2])."""
+    import torch
+    from irmv_detection_b200 import weights as W
+    from oracle import yolov8n_ref as Y
+    p = str(tmp_path / "pose.irmw")
+    d = str(tmp_path / "det.irmw")
+    W.write_random(p, 0, pose=True)
+    W.write_random(d, 0)
+    a, b = W.load(p)[1], W.load(d)[1]
+    assert len(a) == 72 and len(b) == 63
+    assert all(np.array_equal(x[1], y[1]) and np.array_equal(x[2], y[2]) for x, y in zip(a, b))
+    assert [c.name for c, _, _ in a[63:66]] == ["m22.kpt0.0", "m22.kpt0.1", "m22.kpt0.2"] and a[65][0].cout == 8
+    m = Y.build(p)
+    assert m.pose
+    outs = [(torch.zeros(1, 64, hw, hw), torch.zeros(1, 14, hw, hw), torch.zeros(1, 8, hw, hw)) for hw in (80, 40, 20)]
+    outs[1][2][0, :, 3, 5] = torch.tensor([0.25, -0.5, 0.0, 0.0, 1.0, 1.0, -0.25, 0.125])
+    k = Y.decode_keypoints(outs).numpy()
+    a_idx = 6400 + 3 * 40 + 5
+    np.testing.assert_allclose(k[0, a_idx], [[(0.5 + 5) * 16, (-1.0 + 3) * 16], [5 * 16, 3 * 16], [(2 + 5) * 16, (2 + 3) * 16],
+                                             [(-0.5 + 5) * 16, (0.25 + 3) * 16]])
+    np.testing.assert_allclose(k[0, 0], [[0, 0]] * 4)
+    np.testing.assert_allclose(k[0, 8399], [[19 * 32, 19 * 32]] * 4)
+
+
 # ----------------------------------------------------------------------------- light bars / armors
 def test_armor_gray_is_cv2_bgr2gray():
     import cv2
