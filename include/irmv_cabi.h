@@ -20,6 +20,7 @@
  *   irmv_pnp_create           <- PnPSolver::PnPSolver            src/pnp_solver.cpp:7-34
  *   irmv_pnp_solve            <- PnPSolver::solvePnP             src/pnp_solver.cpp:36-52
  *   irmv_pnp_distance_to_center <- calculateDistanceToCenter     src/pnp_solver.cpp:54-59
+ *   irmv_engine_fetch_keypoints: keypoint variant of the detector (reference README.md:12,16)
  *   irmv_extract_armors       <- IrmDetector::extract_armors     src/irm_detector.cpp:292-355
  *                                (+ Light / Armor constructors, include/irmv_detection/armor.hpp:11-77)
  *   irmv_engine_detect_batch / irmv_pnp_solve_batch: batch forms of the same calls for the
