@@ -4,6 +4,8 @@
 //   candidates (anchor a, class c) with score > thr, ordered by (score desc, a*nc+c asc),
 //   first kMaxCand enter NMS, same-class IoU > iou_thr suppresses, stop at max_det.
 // IoU uses explicitly rounded FP32 ops so kept indices are bit-exact against the oracle.
+#include <math_constants.h>
+
 #include "common.cuh"
 
 namespace irmv {
@@ -19,18 +21,39 @@ __device__ __forceinline__ unsigned long long make_key(float score, uint32_t fla
 // ---- decode: 4 lanes per anchor (one box side each, 16 DFL bins = 32 bytes per lane) --------
 __global__ void __launch_bounds__(256) decode_kernel(HeadPtrs h, int B, int nc, float score_thr,
                                                      NmsScratch sc, float *scores_out) {
+  // grid.y = frame, 64 anchors per CTA: no 64-bit or variable-divisor divisions on the index path
   const int lane4 = threadIdx.x & 3;
-  long long quad = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 2;
-  long long total = (long long)B * kNumAnchors;
-  if (quad >= total) return;   // whole quads exit together (blockDim multiple of 4)
-  const int b = (int)(quad / kNumAnchors);
-  const int a = (int)(quad - (long long)b * kNumAnchors);
-  int scale, local, hw;
+  const int b = blockIdx.y;
+  const int a = blockIdx.x * (blockDim.x >> 2) + (threadIdx.x >> 2);
+  if (a >= kNumAnchors) return;   // whole quads exit together (blockDim multiple of 4)
+  int scale, local, hw, gy;
   float stride;
-  if (a < 6400) { scale = 0; local = a; hw = 80; stride = 8.0f; }
-  else if (a < 8000) { scale = 1; local = a - 6400; hw = 40; stride = 16.0f; }
-  else { scale = 2; local = a - 8000; hw = 20; stride = 32.0f; }
-  const size_t pix = h.padded ? (size_t)pr_index(b, local / hw, local % hw, hw, hw) : (size_t)b * hw * hw + local;
+  if (a < 6400) { scale = 0; local = a; hw = 80; stride = 8.0f; gy = local / 80; }
+  else if (a < 8000) { scale = 1; local = a - 6400; hw = 40; stride = 16.0f; gy = local / 40; }
+  else { scale = 2; local = a - 8000; hw = 20; stride = 32.0f; gy = local / 20; }
+  const int gx = local - gy * hw;
+  const size_t pix = h.padded ? (size_t)pr_index(b, gy, gx, hw, hw) : (size_t)b * hw * hw + local;
+
+  // class logits first: lane handles classes lane4*4 .. +3.  A logit clearly below the threshold's
+  // logit cannot pass (guard band 0.05 in logit space = 0.009 in score, far above the rounding of
+  // the sigmoid below), and an anchor without a candidate needs no box: the quad leaves before the
+  // DFL, so the 64 box logits of almost every anchor are never read.
+  const __half *cp = h.padded ? h.cls[scale] + (size_t)(lane4 >> 1) * h.cls_ps[scale] + pix * 8 + (lane4 & 1) * 4
+                              : h.cls[scale] + pix * kClsPad + lane4 * 4;
+  const uint2 cv = __ldg(reinterpret_cast<const uint2 *>(cp));
+  float lg[4];
+  {
+    const __half2 *ch = reinterpret_cast<const __half2 *>(&cv);
+    float2 f = __half22float2(ch[0]); lg[0] = f.x; lg[1] = f.y;
+    float2 g = __half22float2(ch[1]); lg[2] = g.x; lg[3] = g.y;
+  }
+  const float lthr = !(score_thr > 0.f) ? -CUDART_INF_F : (score_thr >= 1.f ? CUDART_INF_F : __logf(score_thr / (1.f - score_thr)) - 0.05f);
+  bool maybe = false;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) maybe |= (lane4 * 4 + j < nc) && lg[j] > lthr;
+  const int qbase = (threadIdx.x & 31) & ~3;
+  const unsigned qmask = 0xFu << qbase;
+  if (!scores_out && __ballot_sync(qmask, maybe) == 0) return;
 
   // DFL expectation of this lane's side (16 bins = planes 2*side, 2*side+1 in the planar layout)
   uint4 v0, v1;
@@ -64,31 +87,23 @@ __global__ void __launch_bounds__(256) decode_kernel(HeadPtrs h, int B, int nc, 
   }
   float dist = sw / se;
   // gather l,t,r,b in every lane of the quad
-  const unsigned qmask = 0xFu << ((threadIdx.x & 31) & ~3);
-  const int qbase = (threadIdx.x & 31) & ~3;
   float dl = __shfl_sync(qmask, dist, qbase + 0);
   float dt = __shfl_sync(qmask, dist, qbase + 1);
   float dr = __shfl_sync(qmask, dist, qbase + 2);
   float db = __shfl_sync(qmask, dist, qbase + 3);
-  float ax = (float)(local % hw) + 0.5f, ay = (float)(local / hw) + 0.5f;
+  float ax = (float)gx + 0.5f, ay = (float)gy + 0.5f;
   if (lane4 == 0) {
     float4 bx;
     bx.x = (ax - dl) * stride; bx.y = (ay - dt) * stride;
     bx.z = (ax + dr) * stride; bx.w = (ay + db) * stride;
     *reinterpret_cast<float4 *>(sc.boxes + ((size_t)b * kNumAnchors + a) * 4) = bx;
   }
-  // class scores: lane handles classes lane4*4 .. +3
-  const __half *cp = h.padded ? h.cls[scale] + (size_t)(lane4 >> 1) * h.cls_ps[scale] + pix * 8 + (lane4 & 1) * 4
-                              : h.cls[scale] + pix * kClsPad + lane4 * 4;
-  uint2 cv = __ldg(reinterpret_cast<const uint2 *>(cp));
-  const __half2 *ch = reinterpret_cast<const __half2 *>(&cv);
-  float lg[4];
-  { float2 f = __half22float2(ch[0]); lg[0] = f.x; lg[1] = f.y;
-    float2 g = __half22float2(ch[1]); lg[2] = g.x; lg[3] = g.y; }
+  // class scores
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     int c = lane4 * 4 + j;
     if (c >= nc) break;
+    if (!scores_out && !(lg[j] > lthr)) continue;
     float s = sigmoidf_(lg[j]);
     if (scores_out) scores_out[((size_t)b * kNumAnchors + a) * nc + c] = s;
     if (s > score_thr) {
@@ -266,9 +281,9 @@ __global__ void __launch_bounds__(NMS_T) nms_kernel(NmsScratch sc, int A, int nc
 
 cudaError_t launch_decode(const HeadPtrs &h, int B, int nc, float score_thr, NmsScratch sc,
                           float *scores_or_null, cudaStream_t s) {
-  long long threads = (long long)B * kNumAnchors * 4;
-  int blocks = (int)((threads + 255) / 256);
-  decode_kernel<<<blocks, 256, 0, s>>>(h, B, nc, score_thr, sc, scores_or_null);
+  if (B < 1) return cudaSuccess;
+  dim3 grid((kNumAnchors + 63) / 64, B);
+  decode_kernel<<<grid, 256, 0, s>>>(h, B, nc, score_thr, sc, scores_or_null);
   return cudaGetLastError();
 }
 

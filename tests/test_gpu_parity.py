@@ -385,7 +385,10 @@ def test_network_parity(frames, weights_seed0, impl):
     gboxes, gscores = irmv.decode(box, cls)
     assert np.abs(gscores - rscores).max() < SCORE_TOL
     assert np.abs(gboxes - rboxes).max() < BOX_TOL_PX
-    assert np.array_equal(gboxes, eng.read_tensor("boxes").reshape(n, 8400, 4))
+    # the engine decodes a box only for anchors that hold a candidate (a class logit near or above the threshold)
+    cand = (gscores > 0.25).any(-1)
+    assert cand.sum() > 0
+    assert np.array_equal(gboxes[cand], eng.read_tensor("boxes").reshape(n, 8400, 4)[cand])
     for f in range(n):
         # NMS stage: identical inputs (the GPU's own decoded boxes/scores) -> bit-exact indices
         ri, rb, rs, rc = N.nms(gboxes[f], gscores[f])
