@@ -834,6 +834,14 @@ def test_engine_armor_stage_feeds_pnp(weights_seed0):
             rel = np.linalg.norm(rv[f, v][clear] - r1[clear], axis=1) / np.linalg.norm(r1[clear], axis=1)
             assert rel.size == 0 or rel.max() < PNP_REL_TOL
             n_valid += len(v)
+    # pipelined hand-off: the armors travel with their ticket's result set
+    import torch
+    pinned = torch.from_numpy(frames).pin_memory().numpy()
+    t = eng.submit_batch(pinned)
+    c2, d2, rv2, tv2, ok2 = eng.collect_arrays(t, poses=True)
+    arm2 = eng.fetch_armors(3, ticket=t)
+    assert np.array_equal(c2, counts) and np.array_equal(arm2["valid"], arm["valid"]) and np.array_equal(arm2["pts"], arm["pts"])
+    assert np.array_equal(ok2, ok)
     eng.close()
     # (random-init weights put boxes anywhere; the count only documents how much of the path ran)
     print("armors from engine boxes:", n_valid)
