@@ -8,11 +8,13 @@
 #include <chrono>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <numeric>
 #include <thread>
 #include <vector>
 
 #include "irmv_detection/armor_extractor.hpp"
+#include "irmv_detection/camera.hpp"
 #include "irmv_detection/pnp_solver.hpp"
 #include "irmv_detection/triple_buffer.hpp"
 #include "irmv_detection/yolo_engine.hpp"
@@ -109,6 +111,35 @@ int main(int argc, char ** argv)
         printf("FAIL: fused armor %zu differs\n", i);
         return 1;
       }
+  }
+
+  // The node's data path without ROS (reference src/irm_detector.cpp:33-38,68-78,176-183): one engine per
+  // ring slot, a camera streaming into the engines' own source buffers through the TripleBuffer, the
+  // callback running detect() on the engine of the slot it was handed.
+  {
+    std::array<std::unique_ptr<YoloEngine>, 3> engines;
+    Camera::Config ccfg;
+    ccfg.image_size = cv::Size(1280, 1024);
+    for (int i = 0; i < 3; i++) {
+      engines[i] = std::make_unique<YoloEngine>(argv[1], cv::Size(1280, 1024), false);
+      ccfg.image_buffers[i] = engines[i]->get_src_image_buffer();
+    }
+    std::vector<uint8_t> two(frame.size() * 2, 0);                 // frame 0: the test frame, frame 1: black
+    memcpy(two.data(), frame.data(), frame.size());
+    std::atomic<int> n_frame0{0}, n_black{0}, bad{0};
+    const size_t expect0 = boxes.size();
+    auto cb = [&](Camera::StampedImage & img) {
+      const bool black = img.image.data[frame.size() / 2] == 0 && img.image.data[12345] == 0 && img.image.data[7] == 0;
+      const size_t n = engines[img.id]->detect().size();
+      if (black) n_black++; else { n_frame0++; if (n != expect0) bad++; }
+    };
+    {
+      VirtualCamera cam(ccfg, two, cb, 400);
+      std::this_thread::sleep_for(std::chrono::milliseconds(400));
+    }
+    printf("camera loop: %d frames of the test image, %d black frames, %d with a different detection count\n", n_frame0.load(),
+           n_black.load(), bad.load());
+    if (n_frame0 < 5 || n_black < 5 || bad != 0) { printf("FAIL: camera loop\n"); return 1; }
   }
 
   // triple buffer: producer at full speed, consumer sees strictly newer frames (drops allowed).

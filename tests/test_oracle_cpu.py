@@ -396,6 +396,17 @@ def test_triple_buffer_monotonic(tmp_path):
     assert r.returncode == 0 and "FAIL" not in r.stdout, r.stdout[-500:]
 
 
+def test_virtual_camera_handoff(tmp_path):
+    """include/irmv_detection/camera.hpp: VirtualCamera streams into three caller-owned buffers through the
+    TripleBuffer; a slow consumer drops frames but never sees a torn, repeated or reordered one."""
+    import subprocess
+    exe = tmp_path / "vc_test"
+    subprocess.run(["g++", "-std=c++20", "-O2", "-pthread", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cpp", "virtual_camera_test.cpp"), "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "VIRTUAL_CAMERA_OK" in r.stdout, r.stdout[-500:]
+
+
 def test_letterbox_oracle_vs_cv2(base_image):
     """LETTERBOX oracle vs the ultralytics recipe done with cv2 (resize INTER_LINEAR + copyMakeBorder
     114): same geometry, pixels within 1 grey level (cv2 resizes u8 in fixed point)."""
