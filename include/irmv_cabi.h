@@ -51,7 +51,8 @@ enum {
 
 /* STRETCH = the reference: independent x/y scale, NPP's measured corner-aligned bilinear map
  * (src = dst * src_size/640, no half-pixel offset; pinned in tests/golden/npp_rm_golden.npz).
- * STRETCH_HALF_PIXEL = same stretch with OpenCV-style pixel centres.  LETTERBOX: not built yet. */
+ * STRETCH_HALF_PIXEL = same stretch with OpenCV-style pixel centres.  LETTERBOX = ultralytics
+ * LetterBox (aspect-preserving resize, centred, pad 114), not what the reference does. */
 enum { IRMV_RESIZE_STRETCH = 0, IRMV_RESIZE_LETTERBOX = 1, IRMV_RESIZE_STRETCH_HALF_PIXEL = 2 };
 enum { IRMV_CONV_TCGEN05 = 0, IRMV_CONV_DIRECT = 1 /* CUDA-core bring-up kernel */ };
 
