@@ -31,7 +31,7 @@
 namespace irmv {
 namespace {
 
-constexpr int kThreads = 128, kWarps = kThreads / 32;
+constexpr int kThreads = 256, kWarps = kThreads / 32;
 constexpr int kSmemWords = 2048;       // per bitmap: ROIs up to 64 K padded pixels keep their bitmaps in shared memory
 constexpr int kRows = 256;             // ... and up to this many rows (per-warp row-extreme arrays, hull)
 constexpr int kMaxRows = 1088;         // ROI height limit of the global-scratch path
@@ -573,7 +573,7 @@ __device__ __forceinline__ void roi_body(Shared &sh, const ArmorParams &p, uint3
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 6) extract_armors_kernel(ArmorParams p) {
+__global__ void __launch_bounds__(kThreads, 3) extract_armors_kernel(ArmorParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   Shared &sh = *reinterpret_cast<Shared *>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -655,7 +655,7 @@ __global__ void mask_pose_ok_kernel(const ArmorOut *armors, int total, uint8_t *
 
 }  // namespace
 
-int armors_grid(int num_sms) { return num_sms * 6; }
+int armors_grid(int num_sms) { return num_sms * 3; }
 
 // scratch layout: [kScratchSlots lock words, padded to 64 words][kScratchSlots slots]
 size_t armors_scratch_words_per_cta(int src_w, int src_h) { return slot_words(src_w, src_h); }
