@@ -111,6 +111,18 @@ typedef struct irmv_armor_params {
   double max_large_center_distance;    /* 5.5 */
 } irmv_armor_params;
 
+/* Per-armor output of IrmDetector::message_callback (src/irm_detector.cpp:213-230): the
+ * auto_aim_interfaces/Armor fields the node fills -- pose.position = tvec, pose.orientation = the tf2
+ * quaternion (x, y, z, w) of Rodrigues(rvec) (:218-226), distance_to_image_center (:229, the intended
+ * computation of src/pnp_solver.cpp:54-59) -- produced by the fused replay. */
+typedef struct irmv_pose {
+  double position[3];
+  double orientation[4];
+  double rvec[3];                   /* the solver's rotation vector, for callers that want it */
+  float distance_to_image_center;
+  int32_t ok;                       /* 1: slot holds a solved armor (detection present, armor found, PnP ok) */
+} irmv_pose;
+
 typedef struct irmv_engine irmv_engine;
 typedef struct irmv_pnp irmv_pnp;
 
@@ -124,8 +136,17 @@ void irmv_engine_destroy(irmv_engine *e);
 
 /* Borrowed, address-stable pinned-host frame slot the camera writes (src_w*src_h*channels bytes). */
 uint8_t *irmv_engine_src_buffer(irmv_engine *e, int slot);
-/* Rotated frame of `slot` as left by the last detect() on it, copied into dst (packed u8x3). */
+/* get_rotated_image() (include/irmv_detection/yolo_engine.hpp:34; the node calls it every frame,
+ * src/irm_detector.cpp:183): *view = address-stable pinned buffer holding the rotated packed-RGB frame
+ * of `slot` as of the last detect() on it.  The first call turns the feature on (allocates once and
+ * rotates the frame still on the device); afterwards every detect() refreshes the buffer itself and
+ * this call only returns the pointer -- no allocation, no re-upload, no extra preprocess. */
+int irmv_engine_rotated_view(irmv_engine *e, int slot, const uint8_t **view);
+/* Same frame copied into dst (packed u8x3). */
 int irmv_engine_rotated_image(irmv_engine *e, int slot, uint8_t *dst);
+/* Debug: number of device / pinned allocations this library has made in the process so far (tests
+ * assert that per-frame calls make none). */
+long long irmv_debug_alloc_count(void);
 
 /* One frame from pinned slot `slot`: H2D + graph(preprocess, net, decode, NMS) + D2H + parse. */
 int irmv_engine_detect(irmv_engine *e, int slot, irmv_bbox *out, int cap, int *n);
@@ -151,6 +172,9 @@ int irmv_engine_enable_pnp(irmv_engine *e, const double K[9], const double D[5],
                            float corner_sy);
 /* rvecs/tvecs: nframes*max_det*3 doubles; slot i of frame f is valid when i < counts[f]. */
 int irmv_engine_fetch_poses(irmv_engine *e, int nframes, double *rvecs, double *tvecs, uint8_t *ok);
+/* The whole per-armor message payload (see irmv_pose) of the last synchronous call (ticket < 0) or of a
+ * collected pipelined batch: out holds nframes*max_det entries, slot-aligned with the detections. */
+int irmv_engine_fetch_armor_poses(irmv_engine *e, int ticket, int nframes, irmv_pose *out);
 /* ---- keypoint variant (BASELINE.json configs[2], north_star "armor-keypoint decode") -------------
  * A weight file with 72 convolutions carries the ultralytics Pose branch (kpt_shape [4, 2]: the four
  * armor corners LB, LT, RT, RB per anchor).  The engine then decodes the keypoints of every kept
@@ -187,7 +211,10 @@ int irmv_engine_fetch_armors(irmv_engine *e, int ticket, int nframes, irmv_armor
  * from its TripleBuffer (camera thread fills the next slot while detect() runs on the previous one,
  * reference README.md:60-63, src/irm_detector.cpp:68-72).  submit queues H2D copy (dedicated copy
  * stream) + pipeline + D2H of the results and returns; collect waits for that batch and parses it
- * like detect_batch (rvecs/tvecs/ok may be null).  At most three batches in flight; collect in order. */
+ * like detect_batch (rvecs/tvecs/ok may be null).  At most three batches in flight; collect in order.
+ * The hand-off is checked: a fourth submit before a collect, a ticket that is not in flight (stale,
+ * duplicate, never issued), an out-of-order collect, and any synchronous entry point (detect,
+ * detect_batch, enqueue_batch, rotated image) while batches are in flight return an error. */
 int irmv_engine_submit_batch(irmv_engine *e, const uint8_t *frames_host, int nframes, int *ticket);
 int irmv_engine_collect(irmv_engine *e, int ticket, irmv_bbox *out, int *counts, double *rvecs, double *tvecs,
                         uint8_t *ok);
@@ -198,6 +225,8 @@ int irmv_engine_profile_stages(irmv_engine *e, const uint8_t *frames_dev, int nf
 /* Debug/tuning: per-tile clock64 stamps of CTA 0 for GEMM `op_index` (see engine.cu). */
 /* Debug: text description of the network stage's kernels in issue order (one line per launch). */
 int irmv_engine_describe_ops(irmv_engine *e, char *buf, int cap);
+/* Debug: tiling plan / kernel instantiation of every network-stage launch for a replay of nframes frames. */
+int irmv_engine_describe_plans(irmv_engine *e, int nframes, char *buf, int cap);
 /* Debug: per-kernel CUDA-event times (ms) of the network stage of one eager replay. */
 int irmv_engine_profile_ops(irmv_engine *e, const uint8_t *frames_dev, int nframes, float *ms, int cap);
 int irmv_engine_trace_conv(irmv_engine *e, int op_index, int nframes, long long *out, int cap_tiles,

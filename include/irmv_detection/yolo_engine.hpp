@@ -47,8 +47,7 @@ private:
   irmv_engine * engine_ = nullptr;
   cv::Size src_image_size_;
   uint8_t * src_image_buffer_ = nullptr;     // pinned host slot, stable for the object's life
-  mutable cv::Mat rotated_image_;            // filled on demand from the last detected frame
-  mutable std::vector<uint8_t> rotated_store_;
+  mutable cv::Mat rotated_image_;            // header over the engine's pinned rotated-frame buffer
   bool enable_profiling_ = false;
   double inference_time_ms_ = 0.0;
 };

@@ -27,6 +27,11 @@ class Armor(C.Structure):
                 ("size", C.c_int32), ("valid", C.c_int32)]
 
 
+class Pose(C.Structure):
+    _fields_ = [("position", C.c_double * 3), ("orientation", C.c_double * 4), ("rvec", C.c_double * 3),
+                ("distance_to_image_center", C.c_float), ("ok", C.c_int32)]
+
+
 class ArmorParams(C.Structure):
     _fields_ = [("binary_threshold", C.c_int32), ("light_min_ratio", C.c_float), ("light_max_ratio", C.c_float),
                 ("light_max_angle", C.c_float), ("min_small_center_distance", C.c_double),
@@ -55,6 +60,9 @@ SYMBOLS = {
     "irmv_engine_destroy": (None, [_P]),
     "irmv_engine_src_buffer": (_P, [_P, C.c_int]),
     "irmv_engine_rotated_image": (C.c_int, [_P, C.c_int, _P]),
+    "irmv_engine_rotated_view": (C.c_int, [_P, C.c_int, C.POINTER(_P)]),
+    "irmv_debug_alloc_count": (C.c_longlong, []),
+    "irmv_engine_fetch_armor_poses": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "irmv_engine_detect": (C.c_int, [_P, C.c_int, C.POINTER(Bbox), C.c_int, C.POINTER(C.c_int)]),
     "irmv_engine_detect_batch": (C.c_int, [_P, _P, C.c_int, C.c_int, C.POINTER(Bbox), C.POINTER(C.c_int)]),
     "irmv_engine_enqueue_batch": (C.c_int, [_P, _P, C.c_int]),
@@ -79,6 +87,7 @@ SYMBOLS = {
     "irmv_engine_submit_batch": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_int)]),
     "irmv_engine_collect": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P]),
     "irmv_engine_describe_ops": (C.c_int, [_P, _P, C.c_int]),
+    "irmv_engine_describe_plans": (C.c_int, [_P, C.c_int, _P, C.c_int]),
     "irmv_engine_profile_ops": (C.c_int, [_P, _P, C.c_int, _P, C.c_int]),
     "irmv_engine_trace_conv": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, C.POINTER(C.c_float)]),
     "irmv_engine_read_tensor": (C.c_int, [_P, C.c_char_p, _P, C.c_int64, C.POINTER(C.c_int32 * 5)]),

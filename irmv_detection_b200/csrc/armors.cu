@@ -634,7 +634,7 @@ __global__ void __launch_bounds__(kThreads, 3) extract_armors_kernel(ArmorParams
 
 // Armor corners {left.bottom, left.top, right.top, right.bottom} -> PnP quads in the calibration
 // frame (src/pnp_solver.cpp:41-44); slots without an armor get a fixed valid quad and are masked after.
-__global__ void quads_from_armors_kernel(const ArmorOut *armors, int total, float sx, float sy, float *pts) {
+__global__ void quads_from_armors_kernel(const ArmorOut *armors, int total, float sx, float sy, float *pts, float *centers) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const ArmorOut &a = armors[i];
@@ -646,6 +646,8 @@ __global__ void quads_from_armors_kernel(const ArmorOut *armors, int total, floa
   float4 *o = reinterpret_cast<float4 *>(pts + (size_t)i * 8);
   o[0] = make_float4(q[0], q[1], q[2], q[3]);
   o[1] = make_float4(q[4], q[5], q[6], q[7]);
+  // Armor::center in the calibration frame (argument of calculateDistanceToCenter, reference src/irm_detector.cpp:229)
+  if (centers) reinterpret_cast<float2 *>(centers)[i] = a.valid ? make_float2(a.center[0] * sx, a.center[1] * sy) : make_float2(175.f, 150.f);
 }
 
 __global__ void mask_pose_ok_kernel(const ArmorOut *armors, int total, uint8_t *ok) {
@@ -663,11 +665,9 @@ size_t armors_scratch_total_words(int src_w, int src_h) { return 64 + (size_t)kS
 
 cudaError_t launch_extract_armors(const ArmorParams &p, cudaStream_t s) {
   if (p.src_h > kMaxRows - 2 || p.src_w > 32766) return cudaErrorInvalidValue;
-  static bool attr_set = false;
-  if (!attr_set) {
+  {   // per device and cheap: no process-wide "already configured" flag (several engines / devices per process)
     cudaError_t e = cudaFuncSetAttribute(extract_armors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Shared));
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   const int total = p.n * p.max_det;
   if (total <= 0) return cudaSuccess;
@@ -676,9 +676,9 @@ cudaError_t launch_extract_armors(const ArmorParams &p, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_quads_from_armors(const ArmorOut *armors, int total, float sx, float sy, float *pts, cudaStream_t s) {
+cudaError_t launch_quads_from_armors(const ArmorOut *armors, int total, float sx, float sy, float *pts, float *centers, cudaStream_t s) {
   if (total <= 0) return cudaSuccess;
-  quads_from_armors_kernel<<<(total + 127) / 128, 128, 0, s>>>(armors, total, sx, sy, pts);
+  quads_from_armors_kernel<<<(total + 127) / 128, 128, 0, s>>>(armors, total, sx, sy, pts, centers);
   return cudaGetLastError();
 }
 

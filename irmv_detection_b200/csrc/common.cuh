@@ -50,6 +50,7 @@ struct PreprocessParams {
   __half *dst;                 // PR layout of [n][640][640][8]
   uint8_t *rotated;            // optional [n][H][W][3] rotated RGB image, may be null
   int n, src_w, src_h;
+  int frame0;                  // index of the first source frame of this launch (chunked replays)
   int chan_order, rotate180, resize_mode, quantize_u8;
   // filled by letterbox_geometry(): the resized image is new_w x new_h at (pad_x, pad_y) of the
   // 640 x 640 network input (stretch modes: 640 x 640 at (0, 0))
@@ -72,10 +73,16 @@ inline void letterbox_geometry(int src_w, int src_h, int resize_mode, int *pad_x
   if (*pad_y < 0) *pad_y = 0;
 }
 cudaError_t launch_preprocess(const PreprocessParams &p, cudaStream_t s);
+// rotated packed-RGB frame only (what get_rotated_image() exposes, reference include/irmv_detection/yolo_engine.hpp:34)
+cudaError_t launch_rotate(const PreprocessParams &p, cudaStream_t s);
 // Fused preprocess + conv0 (3x3 s2, 3->16, SiLU): w = [16][9 taps][3] FP32, writes two planes.
 // out2 (optional): parity-split twin of the output (see ConvParams).
 cudaError_t launch_stem(const PreprocessParams &p, const float *w, const float *bias, __half *out,
                         long long out_pstride, __half *out2, long long out2_pstride, cudaStream_t s);
+// Camera-case stem (stem_bayer.cu): Bayer source of width 1280, reference resize, 8-bit intermediate.
+bool stem_bayer2x_applies(const PreprocessParams &p);
+cudaError_t launch_stem_bayer2x(const PreprocessParams &p, int frame0, const float *w, const float *bias, __half *out,
+                                long long out_ps, __half *out2, long long out2_ps, cudaStream_t s);
 
 // ---------------------------------------------------------------- convolution
 struct ConvSeg {
@@ -137,6 +144,7 @@ size_t conv_tc_smem_bytes(const ConvParams &p, int *stages, int *b_resident);
 // memory.  w_raster: [tap][cin/8][npad][8] (no swizzle).  Returns false from the fit test when the
 // layer has to take the gather kernel instead.
 bool conv_raster_fits(const ConvParams &p);
+bool conv_raster_plan_info(const ConvParams &p, int num_sms, int out[8]);
 cudaError_t launch_conv_raster(const ConvParams &p, int num_sms, cudaStream_t s);
 
 // ktab meta: bits 0-3 tap index (ky*k+kx), 4 segment, 5 valid, 8.. plane index inside the segment.
@@ -214,7 +222,7 @@ size_t armors_scratch_words_per_cta(int src_w, int src_h);
 size_t armors_scratch_total_words(int src_w, int src_h);   // allocate this many words, zeroed once
 cudaError_t launch_extract_armors(const ArmorParams &p, cudaStream_t s);
 // armor corners -> PnP quads in the calibration frame; slots without an armor get a fixed valid quad
-cudaError_t launch_quads_from_armors(const ArmorOut *armors, int total, float sx, float sy, float *pts, cudaStream_t s);
+cudaError_t launch_quads_from_armors(const ArmorOut *armors, int total, float sx, float sy, float *pts, float *centers, cudaStream_t s);
 cudaError_t launch_mask_pose_ok(const ArmorOut *armors, int total, uint8_t *ok, cudaStream_t s);
 
 // ---------------------------------------------------------------- PnP
@@ -228,6 +236,11 @@ struct PnpOut {
   uint8_t *ok;                   // [n]
   double *quat;                  // [n][4] or null
   double *rvec2, *tvec2, *rmse;  // second solution / [n][2] rmse, or null
+  // distance_to_image_center (reference src/irm_detector.cpp:229, src/pnp_solver.cpp:54-59, the intended
+  // computation): |centre - (cx, cy)| in FP32; centre = centers[i] when given (Armor::center in the
+  // calibration frame), else the mean of the four image points.  dist may be null.
+  float *dist;                   // [n] or null
+  const float *centers;          // [n][2] or null
 };
 cudaError_t launch_pnp(const PnpConsts &c, const float *pts, int n, int large, PnpOut out,
                        cudaStream_t s);

@@ -771,11 +771,9 @@ bool plan(const ConvParams &p, int num_sms, RArgs &a) {
 
 template <int R, int NEPI, bool ACT, bool RES, int TAIL>
 cudaError_t launch_k(const RArgs &a, int grid, size_t smem, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
+  {   // the attribute is per device: no process-wide flag (several engines / devices per process); the call is cheap
     cudaError_t e = cudaFuncSetAttribute(conv_raster_kernel<R, NEPI, ACT, RES, TAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   static const bool pdl = !getenv("IRMV_NO_PDL");
   cudaLaunchConfig_t cfg{};
@@ -807,6 +805,16 @@ cudaError_t launch_r(const RArgs &a, int grid, size_t smem, cudaStream_t s) {
 }
 
 }  // namespace
+
+// Debug: the kernel instantiation and tiling plan() picks for this layer instance:
+// {R, NEPI, b_stream, ctas_per_sm, stages, b_stages, tail (0/1/2), tiles}.
+bool conv_raster_plan_info(const ConvParams &p, int num_sms, int out[8]) {
+  RArgs a;
+  if (!p.w_raster || !plan(p, num_sms, a)) return false;
+  out[0] = a.R; out[1] = a.ctas_per_sm == 2 ? 8 : 16; out[2] = a.b_stream; out[3] = a.ctas_per_sm; out[4] = a.stages;
+  out[5] = a.b_stages; out[6] = p.tail_w ? (p.tail_act ? 2 : 1) : 0; out[7] = a.num_tiles;
+  return true;
+}
 
 bool conv_raster_fits(const ConvParams &p) {
   RArgs a;

@@ -461,12 +461,10 @@ cudaError_t launch_conv_tc(const ConvParams &p, int num_sms, cudaStream_t s) {
   a.mul_ow = (uint32_t)(((1ull << 34) + (uint64_t)p.OW - 1) / (uint64_t)p.OW);
   a.mul_oh = (uint32_t)(((1ull << 34) + (uint64_t)p.OH - 1) / (uint64_t)p.OH);
   a.off_bars = (a.off_bias + (uint32_t)p.npad * 4 + 15u) & ~15u;
-  static size_t configured = 0;
-  if (smem > configured) {
+  {   // per device, cheap: no process-wide flag
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(227 * 1024));
     if (e != cudaSuccess) return e;
-    configured = 227 * 1024;
   }
   int grid = a.num_tiles < num_sms ? a.num_tiles : num_sms;
   conv_tc_kernel<<<grid, NTHREADS, smem, s>>>(a);

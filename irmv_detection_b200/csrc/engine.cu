@@ -7,10 +7,12 @@
 //   :202-220 parse_output(): scale boxes by (W/640, H/640), class id -> ArmorClass/UNKNOWN
 // What changed: unified memory -> pinned host slots + device buffers; TensorRT/NPP -> the kernels
 // in this directory; batch-1 -> sub-batches replayed on several lanes (streams).
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <chrono>
+#include <exception>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -31,6 +33,24 @@ bool cuda_ok(cudaError_t e, const char *what, const char *file, int line) {
   set_error(buf);
   return false;
 }
+
+// Every device / pinned allocation of this file goes through these two, so that a test can assert
+// that the per-frame calls allocate nothing (irmv_debug_alloc_count, include/irmv_cabi.h).
+static std::atomic<long long> g_allocs{0};
+cudaError_t dev_malloc(void **p, size_t bytes) { g_allocs.fetch_add(1); return cudaMalloc(p, bytes); }
+cudaError_t host_malloc(void **p, size_t bytes) { g_allocs.fetch_add(1); return cudaHostAlloc(p, bytes, cudaHostAllocDefault); }
+
+// Nothing may throw across the C ABI: entry points that build std containers from caller data run
+// their body under this guard.
+#define IRMV_ABI_TRY try {
+#define IRMV_ABI_CATCH                                                                   \
+  } catch (const std::exception &ex) {                                                   \
+    ::irmv::set_error(std::string("internal error: ") + ex.what());                      \
+    return 90;                                                                           \
+  } catch (...) {                                                                        \
+    ::irmv::set_error("internal error");                                                 \
+    return 90;                                                                           \
+  }
 
 namespace {
 
@@ -56,28 +76,90 @@ struct FileConv {
 bool read_weights(const char *path, int &nc, std::vector<FileConv> &out) {
   FILE *f = fopen(path, "rb");
   if (!f) { set_error(std::string("cannot open weight file ") + path); return false; }
+  auto fail = [&](const std::string &why) { fclose(f); set_error(std::string(path) + ": " + why); return false; };
+  if (fseek(f, 0, SEEK_END) != 0) return fail("cannot seek");
+  const long long file_bytes = ftell(f);
+  rewind(f);
   char magic[4];
   uint32_t hdr[3];
-  if (fread(magic, 1, 4, f) != 4 || memcmp(magic, "IRMW", 4) != 0 || fread(hdr, 4, 3, f) != 3 ||
-      hdr[0] != 1) {
-    fclose(f);
-    set_error(std::string(path) + ": not an IRMW v1 weight file");
-    return false;
-  }
+  if (fread(magic, 1, 4, f) != 4 || memcmp(magic, "IRMW", 4) != 0 || fread(hdr, 4, 3, f) != 3 || hdr[0] != 1)
+    return fail("not an IRMW v1 weight file");
+  // nothing in the header is trusted: counts and shapes are bounded before anything is allocated
+  if (hdr[2] < 1 || hdr[2] > 512) return fail("implausible convolution count");
   nc = (int)hdr[1];
   out.resize(hdr[2]);
+  long long left = file_bytes - 16;
   for (auto &c : out) {
     uint32_t h[5];
-    if (fread(h, 4, 5, f) != 5) { fclose(f); set_error("truncated weight file"); return false; }
-    c.cin = h[0]; c.cout = h[1]; c.k = h[2]; c.stride = h[3]; c.act = h[4];
-    c.w.resize((size_t)c.cout * c.cin * c.k * c.k);
-    c.b.resize(c.cout);
-    if (fread(c.w.data(), 4, c.w.size(), f) != c.w.size() ||
-        fread(c.b.data(), 4, c.b.size(), f) != c.b.size()) {
-      fclose(f); set_error("truncated weight file"); return false;
-    }
+    if (left < 20 || fread(h, 4, 5, f) != 5) return fail("truncated weight file");
+    left -= 20;
+    if (h[0] < 1 || h[0] > 4096 || h[1] < 1 || h[1] > 4096 || !(h[2] == 1 || h[2] == 3) || !(h[3] == 1 || h[3] == 2) || h[4] > 1)
+      return fail("bad convolution header (cin/cout in 1..4096, k in {1,3}, stride in {1,2}, act in {0,1})");
+    c.cin = (int)h[0]; c.cout = (int)h[1]; c.k = (int)h[2]; c.stride = (int)h[3]; c.act = (int)h[4];
+    const long long nw = (long long)c.cout * c.cin * c.k * c.k, need = (nw + c.cout) * 4;
+    if (need > left) return fail("truncated weight file");
+    c.w.resize((size_t)nw);
+    c.b.resize((size_t)c.cout);
+    if (fread(c.w.data(), 4, c.w.size(), f) != c.w.size() || fread(c.b.data(), 4, c.b.size(), f) != c.b.size())
+      return fail("truncated weight file");
+    left -= need;
   }
   fclose(f);
+  return true;
+}
+
+// The convolutions the engine's layer program expects, in file order (irmv_detection_b200/weights.py
+// conv_specs; ultralytics yolov8.yaml scale n, nc = 14, optional Pose branch kpt_shape [4, 2]).
+struct Spec { int cin, cout, k, stride, act; };
+std::vector<Spec> expected_specs(bool pose) {
+  std::vector<Spec> s;
+  auto c2f = [&](int c1, int c2, int n) {
+    const int c = c2 / 2;
+    s.push_back({c1, 2 * c, 1, 1, 1});
+    for (int i = 0; i < n; ++i) { s.push_back({c, c, 3, 1, 1}); s.push_back({c, c, 3, 1, 1}); }
+    s.push_back({(2 + n) * c, c2, 1, 1, 1});
+  };
+  s.push_back({3, 16, 3, 2, 1});
+  s.push_back({16, 32, 3, 2, 1});
+  c2f(32, 32, 1);
+  s.push_back({32, 64, 3, 2, 1});
+  c2f(64, 64, 2);
+  s.push_back({64, 128, 3, 2, 1});
+  c2f(128, 128, 2);
+  s.push_back({128, 256, 3, 2, 1});
+  c2f(256, 256, 1);
+  s.push_back({256, 128, 1, 1, 1});
+  s.push_back({512, 256, 1, 1, 1});
+  c2f(384, 128, 1);
+  c2f(192, 64, 1);
+  s.push_back({64, 64, 3, 2, 1});
+  c2f(192, 128, 1);
+  s.push_back({128, 128, 3, 2, 1});
+  c2f(384, 256, 1);
+  const int chs[3] = {64, 128, 256};
+  for (int i = 0; i < 3; ++i) {
+    s.push_back({chs[i], 64, 3, 1, 1}); s.push_back({64, 64, 3, 1, 1}); s.push_back({64, 64, 1, 1, 0});
+    s.push_back({chs[i], 64, 3, 1, 1}); s.push_back({64, 64, 3, 1, 1}); s.push_back({64, IRMV_NUM_CLASSES, 1, 1, 0});
+  }
+  if (pose)
+    for (int i = 0; i < 3; ++i) { s.push_back({chs[i], 16, 3, 1, 1}); s.push_back({16, 16, 3, 1, 1}); s.push_back({16, 8, 1, 1, 0}); }
+  return s;
+}
+
+bool check_specs(const std::vector<FileConv> &fc, bool pose) {
+  const std::vector<Spec> want = expected_specs(pose);
+  if (fc.size() != want.size()) { set_error("weight file is not YOLOv8n nc=14"); return false; }
+  for (size_t i = 0; i < fc.size(); ++i) {
+    const FileConv &c = fc[i];
+    const Spec &w = want[i];
+    if (c.cin != w.cin || c.cout != w.cout || c.k != w.k || c.stride != w.stride || c.act != w.act) {
+      char buf[200];
+      snprintf(buf, sizeof buf, "weight file: convolution %zu is %d->%d k%d s%d act%d, the YOLOv8n nc=14 program needs %d->%d k%d s%d act%d",
+               i, c.cin, c.cout, c.k, c.stride, c.act, w.cin, w.cout, w.k, w.stride, w.act);
+      set_error(buf);
+      return false;
+    }
+  }
   return true;
 }
 
@@ -147,7 +229,7 @@ HostConv make_conv(const std::vector<const FileConv *> &parts, int cin_pad,
 
 bool upload(HostConv &h) {
   auto up = [](void **d, const void *src, size_t bytes) {
-    if (!cuda_ok(cudaMalloc(d, bytes), "cudaMalloc(weights)", __FILE__, __LINE__)) return false;
+    if (!cuda_ok(dev_malloc(d, bytes), "dev_malloc(weights)", __FILE__, __LINE__)) return false;
     return cuda_ok(cudaMemcpy(*d, src, bytes, cudaMemcpyHostToDevice), "cudaMemcpy(weights)",
                    __FILE__, __LINE__);
   };
@@ -208,6 +290,9 @@ struct Lane {
   float *pnp_pts = nullptr;                // [S*max_det][8]
   double *pnp_rvec = nullptr, *pnp_tvec = nullptr;
   uint8_t *pnp_ok = nullptr;
+  double *pnp_quat = nullptr;              // [S*max_det][4] tf2 quaternion (x, y, z, w) of the pose
+  float *pnp_dist = nullptr;               // [S*max_det] distance_to_image_center
+  float *pnp_centers = nullptr;            // [S*max_det][2] Armor::center in the calibration frame (armor stage only)
   const __half *kpt[3] = {nullptr, nullptr, nullptr};   // keypoint-branch outputs per scale (plane 0 = the 8 raw values)
   float *kpts = nullptr;                   // [S*max_det][8] decoded keypoints of the kept detections, network pixels
   ArmorOut *armors = nullptr;              // [S*max_det], allocated by irmv_engine_enable_armors
@@ -316,6 +401,8 @@ struct irmv_engine {
     cudaEvent_t done = nullptr;           // all lanes finished (results in res_host)
     std::vector<cudaEvent_t> h2d;         // per chunk: frames arrived on the device
     int n = 0;
+    long long ticket = -1;                // ticket whose results the set holds (-1: a synchronous call / nothing)
+    bool in_flight = false;               // submitted and not yet collected
   } sets[kSets];
   cudaStream_t copy_stream = nullptr;
   long long next_ticket = 0;
@@ -333,12 +420,20 @@ struct irmv_engine {
   irmv_armor_params armor_prm{};
   int last_slot = -1;
   int last_n = 0;
+  // get_rotated_image(): address-stable pinned buffers (one per source slot) refreshed by every
+  // detect() once enabled -- the reference's cv::Mat is a view of the buffer its graph rotates in
+  // place (include/irmv_detection/yolo_engine.hpp:34, src/yolo_engine.cpp:182-184)
+  bool rotated_on = false;
+  uint8_t *rot_dev = nullptr;
+  std::vector<uint8_t *> rot_host;
+  std::vector<char> rot_valid;
+  std::vector<irmv_bbox> parse_tmp;        // detect(): max_det boxes, sized once
 };
 
 namespace {
 
 bool lane_alloc(Lane &ln, void **p, size_t bytes) {
-  if (!cuda_ok(cudaMalloc(p, bytes), "cudaMalloc(activation)", __FILE__, __LINE__)) return false;
+  if (!cuda_ok(dev_malloc(p, bytes), "dev_malloc(activation)", __FILE__, __LINE__)) return false;
   ln.allocs.push_back(*p);
   return cuda_ok(cudaMemset(*p, 0, bytes), "cudaMemset", __FILE__, __LINE__);
 }
@@ -403,7 +498,7 @@ void add_conv(irmv_engine *e, Lane &ln, HostConv &hc, std::vector<SegRef> in, in
       tab[q * 2 + 1] = ktab_meta(tap, sg, 1, off / 8);
     }
     int32_t *d = nullptr;
-    cudaMalloc((void **)&d, tab.size() * 4);
+    dev_malloc((void **)&d, tab.size() * 4);
     cudaMemcpy(d, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice);
     ln.allocs.push_back(d);
     p.ktab = d;
@@ -610,7 +705,9 @@ bool build_lane(irmv_engine *e, Lane &ln) {
   const size_t slots = (size_t)S * e->cfg.max_det;
   if (e->pose && !lane_alloc(ln, (void **)&ln.kpts, slots * 32)) return false;
   if (!lane_alloc(ln, (void **)&ln.pnp_pts, slots * 32) || !lane_alloc(ln, (void **)&ln.pnp_rvec, slots * 24) ||
-      !lane_alloc(ln, (void **)&ln.pnp_tvec, slots * 24) || !lane_alloc(ln, (void **)&ln.pnp_ok, slots))
+      !lane_alloc(ln, (void **)&ln.pnp_tvec, slots * 24) || !lane_alloc(ln, (void **)&ln.pnp_ok, slots) ||
+      !lane_alloc(ln, (void **)&ln.pnp_quat, slots * 32) || !lane_alloc(ln, (void **)&ln.pnp_dist, slots * 4) ||
+      !lane_alloc(ln, (void **)&ln.pnp_centers, slots * 8))
     return false;
   for (auto &ev : ln.stage_ev)
     if (!cuda_ok(cudaEventCreate(&ev), "cudaEventCreate", __FILE__, __LINE__)) return false;
@@ -638,7 +735,7 @@ int issue_replay(irmv_engine *e, Lane &ln, int n, cudaStream_t st, int *launches
   if (mark(0)) return 1;
   PreprocessParams pp{};
   pp.src = nullptr; pp.src_indirect = ln.src_word; pp.dst = ln.in8.p; pp.rotated = ln.rotated;
-  pp.n = n; pp.src_w = e->cfg.src_width; pp.src_h = e->cfg.src_height;
+  pp.n = n; pp.src_w = e->cfg.src_width; pp.src_h = e->cfg.src_height; pp.frame0 = 0;
   pp.chan_order = e->cfg.chan_order; pp.rotate180 = e->cfg.rotate180;
   pp.resize_mode = e->cfg.resize_mode; pp.quantize_u8 = e->cfg.quantize_u8;
   const bool fused = e->fused_stem && e->cfg.conv_impl != IRMV_CONV_DIRECT;
@@ -710,8 +807,8 @@ int issue_replay(irmv_engine *e, Lane &ln, int n, cudaStream_t st, int *launches
     IRMV_CUDA(launch_extract_armors(ap, st)); ++cnt;
     if (e->pnp_on) {
       const int total = n * e->cfg.max_det;
-      IRMV_CUDA(launch_quads_from_armors(ln.armors, total, e->corner_sx, e->corner_sy, ln.pnp_pts, st));
-      PnpOut po{ln.pnp_rvec, ln.pnp_tvec, ln.pnp_ok, nullptr, nullptr, nullptr, nullptr};
+      IRMV_CUDA(launch_quads_from_armors(ln.armors, total, e->corner_sx, e->corner_sy, ln.pnp_pts, ln.pnp_centers, st));
+      PnpOut po{ln.pnp_rvec, ln.pnp_tvec, ln.pnp_ok, ln.pnp_quat, nullptr, nullptr, nullptr, ln.pnp_dist, ln.pnp_centers};
       IRMV_CUDA(launch_pnp(e->pnp_c, ln.pnp_pts, total, 0, po, st));
       IRMV_CUDA(launch_mask_pose_ok(ln.armors, total, ln.pnp_ok, st));
       cnt += 3;
@@ -725,7 +822,7 @@ int issue_replay(irmv_engine *e, Lane &ln, int n, cudaStream_t st, int *launches
       quads_from_dets_kernel<<<(total + 127) / 128, 128, 0, st>>>(ln.det.num(), ln.det.boxes(), n, e->cfg.max_det,
                                                                  e->pnp_sx, e->pnp_sy, e->pnp_px, e->pnp_py, ln.pnp_pts);
     IRMV_CUDA(cudaGetLastError());
-    PnpOut po{ln.pnp_rvec, ln.pnp_tvec, ln.pnp_ok, nullptr, nullptr, nullptr, nullptr};
+    PnpOut po{ln.pnp_rvec, ln.pnp_tvec, ln.pnp_ok, ln.pnp_quat, nullptr, nullptr, nullptr, ln.pnp_dist, nullptr};
     IRMV_CUDA(launch_pnp(e->pnp_c, ln.pnp_pts, total, 0, po, st));
     cnt += 2;
   }
@@ -738,6 +835,9 @@ static_assert(sizeof(ArmorOut) == sizeof(irmv_armor) && sizeof(irmv_armor) == 56
 // byte offset of the armor block inside a pinned result set (after num, boxes, scores, classes, index, poses)
 size_t armors_offset(size_t B, size_t md) { return (B * 4 + B * md * 28 + B * md * 49 + 63) & ~(size_t)63; }
 size_t kpts_offset(size_t B, size_t md) { return armors_offset(B, md) + B * md * sizeof(ArmorOut); }
+// quaternions [B][md][4] f64, then distance_to_image_center [B][md] f32 (fused message_callback outputs)
+size_t quat_offset(size_t B, size_t md) { return (kpts_offset(B, md) + B * md * 32 + 63) & ~(size_t)63; }
+size_t dist_offset(size_t B, size_t md) { return quat_offset(B, md) + B * md * 32; }
 
 int run_replay(irmv_engine *e, Lane &ln, int n) {
   if (!e->cfg.use_graph) return issue_replay(e, ln, n, ln.stream, &ln.launches_per_replay);
@@ -818,6 +918,8 @@ int enqueue(irmv_engine *e, const uint8_t *frames_dev, int n, const uint8_t *fra
       IRMV_CUDA(cudaMemcpyAsync(h + o + (size_t)f0 * md * 24, ln.pnp_tvec, (size_t)nf * md * 24, cudaMemcpyDeviceToHost, ln.stream));
       o += B * md * 24;
       IRMV_CUDA(cudaMemcpyAsync(h + o + (size_t)f0 * md, ln.pnp_ok, (size_t)nf * md, cudaMemcpyDeviceToHost, ln.stream));
+      IRMV_CUDA(cudaMemcpyAsync(h + quat_offset(B, md) + (size_t)f0 * md * 32, ln.pnp_quat, (size_t)nf * md * 32, cudaMemcpyDeviceToHost, ln.stream));
+      IRMV_CUDA(cudaMemcpyAsync(h + dist_offset(B, md) + (size_t)f0 * md * 4, ln.pnp_dist, (size_t)nf * md * 4, cudaMemcpyDeviceToHost, ln.stream));
     }
     if (e->armors_on)
       IRMV_CUDA(cudaMemcpyAsync(h + armors_offset(B, md) + (size_t)f0 * md * sizeof(ArmorOut), ln.armors,
@@ -866,6 +968,27 @@ void parse(irmv_engine *e, int n, irmv_bbox *out, int *counts, int set = 0) {
   }
 }
 
+// The synchronous entry points share set 0, lane 0's buffers and the main stream with the pipelined
+// hand-off: they are refused while a submitted batch has not been collected.
+bool pipeline_busy(irmv_engine *e) {
+  for (auto &st : e->sets)
+    if (st.in_flight) { set_error("pipelined batches are in flight: collect them before a synchronous call"); return true; }
+  return false;
+}
+
+// Refresh the rotated frame of `slot` from the device copy of the frame (slot_dev) on the main stream.
+int refresh_rotated(irmv_engine *e, int slot) {
+  PreprocessParams pp{};
+  pp.src = e->slot_dev; pp.rotated = e->rot_dev; pp.n = 1;
+  pp.src_w = e->cfg.src_width; pp.src_h = e->cfg.src_height; pp.chan_order = e->cfg.chan_order;
+  pp.rotate180 = e->cfg.rotate180;
+  IRMV_CUDA(launch_rotate(pp, e->main_stream));
+  IRMV_CUDA(cudaMemcpyAsync(e->rot_host[slot], e->rot_dev, (size_t)e->cfg.src_width * e->cfg.src_height * 3,
+                            cudaMemcpyDeviceToHost, e->main_stream));
+  e->rot_valid[slot] = 1;
+  return 0;
+}
+
 }  // namespace
 
 // =============================================================================== C ABI
@@ -887,6 +1010,7 @@ int irmv_engine_config_default(irmv_engine_config *c) {
 
 int irmv_engine_create(const char *weights_path, const irmv_engine_config *cfg, irmv_engine **out) {
   if (!weights_path || !cfg || !out) { set_error("null argument"); return 1; }
+  IRMV_ABI_TRY
   if (cfg->max_batch < 1 || cfg->src_width < 2 || cfg->src_height < 2 || cfg->max_det < 1 || cfg->max_det > 1024) {
     set_error("bad engine config"); return 2;
   }
@@ -904,6 +1028,7 @@ int irmv_engine_create(const char *weights_path, const irmv_engine_config *cfg, 
   if (!read_weights(weights_path, e->nc, fc)) return 4;
   if ((fc.size() != 63 && fc.size() != 72) || e->nc != IRMV_NUM_CLASSES) { set_error("weight file is not YOLOv8n nc=14"); return 4; }
   e->pose = fc.size() == 72;                                   // + keypoint branch (kpt_shape [4, 2])
+  if (!check_specs(fc, e->pose)) return 4;                     // make_conv / build_lane index by the expected shapes
   // 63 reference convs -> 60 GEMMs (Detect box.0|cls.0 merged per scale)
   auto single = [&](size_t i, int cin_pad, std::vector<int> seg) {
     e->convs.emplace_back(new HostConv(make_conv({&fc[i]}, cin_pad, seg)));
@@ -945,8 +1070,8 @@ int irmv_engine_create(const char *weights_path, const irmv_engine_config *cfg, 
       for (int t = 0; t < 9; ++t)
         for (int c = 0; c < 3; ++c) w[n * 27 + t * 3 + c] = __half2float(c0.w_plain[(size_t)n * c0.kpad + t * kInC + c]);
     }
-    IRMV_CUDA(cudaMalloc((void **)&e->d_stem_w, w.size() * 4));
-    IRMV_CUDA(cudaMalloc((void **)&e->d_stem_b, b.size() * 4));
+    IRMV_CUDA(dev_malloc((void **)&e->d_stem_w, w.size() * 4));
+    IRMV_CUDA(dev_malloc((void **)&e->d_stem_b, b.size() * 4));
     IRMV_CUDA(cudaMemcpy(e->d_stem_w, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
     IRMV_CUDA(cudaMemcpy(e->d_stem_b, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
     e->fused_stem = cfg->reserved[0] == 0;
@@ -968,21 +1093,24 @@ int irmv_engine_create(const char *weights_path, const irmv_engine_config *cfg, 
   int nslots = cfg->num_slots > 0 ? cfg->num_slots : 1;
   e->slots_host.resize(nslots, nullptr);
   for (auto &s : e->slots_host) {
-    IRMV_CUDA(cudaHostAlloc((void **)&s, e->frame_bytes, cudaHostAllocDefault));
+    IRMV_CUDA(host_malloc((void **)&s, e->frame_bytes));
     memset(s, 0, e->frame_bytes);
   }
-  IRMV_CUDA(cudaMalloc((void **)&e->slot_dev, e->frame_bytes));
+  IRMV_CUDA(dev_malloc((void **)&e->slot_dev, e->frame_bytes));
   const size_t md = cfg->max_det, B = cfg->max_batch;
-  size_t res_bytes = kpts_offset(B, md) + B * md * 32 + 64;
-  IRMV_CUDA(cudaHostAlloc((void **)&e->res_host, res_bytes, cudaHostAllocDefault));
+  size_t res_bytes = dist_offset(B, md) + B * md * 4 + 64;
+  IRMV_CUDA(host_malloc((void **)&e->res_host, res_bytes));
   memset(e->res_host, 0, res_bytes);
   e->res_bytes = res_bytes;
   e->sets[0].res_host = e->res_host;
   IRMV_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
   for (auto &st : e->sets) IRMV_CUDA(cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
+  e->rot_host.assign(nslots, nullptr);
+  e->rot_valid.assign(nslots, 0);
   IRMV_CUDA(cudaDeviceSynchronize());
   *out = e.release();
   return 0;
+  IRMV_ABI_CATCH
 }
 
 void irmv_engine_destroy(irmv_engine *e) {
@@ -1002,6 +1130,8 @@ void irmv_engine_destroy(irmv_engine *e) {
   }
 
   for (auto s : e->slots_host) cudaFreeHost(s);
+  for (auto s : e->rot_host) if (s) cudaFreeHost(s);
+  if (e->rot_dev) cudaFree(e->rot_dev);
   cudaFree(e->slot_dev);
   cudaFree(e->d_stem_w); cudaFree(e->d_stem_b);
   if (e->batch_dev) cudaFree(e->batch_dev);
@@ -1027,18 +1157,20 @@ uint8_t *irmv_engine_src_buffer(irmv_engine *e, int slot) {
 
 int irmv_engine_detect(irmv_engine *e, int slot, irmv_bbox *out, int cap, int *n) {
   if (!e || !n || slot < 0 || slot >= (int)e->slots_host.size()) { set_error("bad argument"); return 1; }
+  if (pipeline_busy(e)) return 5;
   auto t0 = std::chrono::high_resolution_clock::now();
   IRMV_CUDA(cudaSetDevice(e->cfg.device));
-  Lane &ln = e->lanes[0];
   IRMV_CUDA(cudaMemcpyAsync(e->slot_dev, e->slots_host[slot], e->frame_bytes, cudaMemcpyHostToDevice, e->main_stream));
   if (int rc = enqueue(e, e->slot_dev, 1)) return rc;
+  if (e->rotated_on) { if (int rc = refresh_rotated(e, slot)) return rc; }
+  else if (!e->rot_valid.empty()) e->rot_valid[slot] = 0;
   IRMV_CUDA(cudaStreamSynchronize(e->main_stream));
-  (void)ln;
-  std::vector<irmv_bbox> tmp(e->cfg.max_det);
+  e->sets[0].ticket = -1;
+  if ((int)e->parse_tmp.size() < e->cfg.max_det) e->parse_tmp.resize(e->cfg.max_det);   // once
   int k = 0;
-  parse(e, 1, tmp.data(), &k);
+  parse(e, 1, e->parse_tmp.data(), &k);
   *n = k < cap ? k : cap;
-  if (out) memcpy(out, tmp.data(), sizeof(irmv_bbox) * (size_t)*n);
+  if (out) memcpy(out, e->parse_tmp.data(), sizeof(irmv_bbox) * (size_t)*n);
   e->last_slot = slot;
   float ms = 0.f;
   cudaEventElapsedTime(&ms, e->ev_start, e->ev_stop);
@@ -1050,7 +1182,9 @@ int irmv_engine_detect(irmv_engine *e, int slot, irmv_bbox *out, int cap, int *n
 
 int irmv_engine_enqueue_batch(irmv_engine *e, const uint8_t *frames_dev, int nframes) {
   if (!e || !frames_dev || nframes < 1 || nframes > e->cfg.max_batch) { set_error("bad argument"); return 1; }
+  if (pipeline_busy(e)) return 5;
   IRMV_CUDA(cudaSetDevice(e->cfg.device));
+  e->sets[0].ticket = -1;
   return enqueue(e, frames_dev, nframes);
 }
 
@@ -1072,11 +1206,13 @@ int irmv_engine_fetch(irmv_engine *e, int nframes, irmv_bbox *out, int *counts) 
 int irmv_engine_detect_batch(irmv_engine *e, const uint8_t *frames, int on_device, int nframes,
                              irmv_bbox *out, int *counts) {
   if (!e || !frames || !out || nframes < 1 || nframes > e->cfg.max_batch) { set_error("bad argument"); return 1; }
+  if (pipeline_busy(e)) return 5;
   auto t0 = std::chrono::high_resolution_clock::now();
   IRMV_CUDA(cudaSetDevice(e->cfg.device));
+  e->sets[0].ticket = -1;
   const uint8_t *dev = frames;
   if (!on_device) {
-    if (!e->batch_dev) IRMV_CUDA(cudaMalloc((void **)&e->batch_dev, e->frame_bytes * (size_t)e->cfg.max_batch));
+    if (!e->batch_dev) IRMV_CUDA(dev_malloc((void **)&e->batch_dev, e->frame_bytes * (size_t)e->cfg.max_batch));
     e->sets[0].batch_dev = e->batch_dev;
     dev = e->batch_dev;
   }
@@ -1098,18 +1234,26 @@ int irmv_engine_submit_batch(irmv_engine *e, const uint8_t *frames_host, int nfr
   IRMV_CUDA(cudaSetDevice(e->cfg.device));
   const int set = (int)(e->next_ticket % kSets);
   irmv_engine::Set &rs = e->sets[set];
+  if (rs.in_flight) {
+    char buf[128];
+    snprintf(buf, sizeof buf, "three batches are in flight: collect ticket %lld before submitting another", rs.ticket);
+    set_error(buf);
+    return 6;
+  }
   if (!rs.res_host) {
-    IRMV_CUDA(cudaHostAlloc((void **)&rs.res_host, e->res_bytes, cudaHostAllocDefault));
+    IRMV_CUDA(host_malloc((void **)&rs.res_host, e->res_bytes));
     memset(rs.res_host, 0, e->res_bytes);
   }
   if (!rs.batch_dev) {
     if (set == 0 && e->batch_dev) rs.batch_dev = e->batch_dev;
-    else IRMV_CUDA(cudaMalloc((void **)&rs.batch_dev, e->frame_bytes * (size_t)e->cfg.max_batch));
+    else IRMV_CUDA(dev_malloc((void **)&rs.batch_dev, e->frame_bytes * (size_t)e->cfg.max_batch));
     if (set == 0) e->batch_dev = rs.batch_dev;
   }
   // the set's staging buffer and result block are free once its previous batch has finished
   IRMV_CUDA(cudaStreamWaitEvent(e->copy_stream, rs.done, 0));
   if (int rc = enqueue(e, rs.batch_dev, nframes, frames_host, set, true)) return rc;
+  rs.ticket = e->next_ticket & 0x7fffffff;
+  rs.in_flight = true;
   *ticket = (int)(e->next_ticket++ & 0x7fffffff);
   return 0;
 }
@@ -1118,10 +1262,18 @@ int irmv_engine_collect(irmv_engine *e, int ticket, irmv_bbox *out, int *counts,
                         uint8_t *ok) {
   if (!e || !out) { set_error("bad argument"); return 1; }
   IRMV_CUDA(cudaSetDevice(e->cfg.device));
+  if (ticket < 0) { set_error("bad ticket"); return 2; }
   const int set = ticket % kSets;
   irmv_engine::Set &rs = e->sets[set];
-  if (rs.n < 1) { set_error("nothing was submitted under this ticket"); return 2; }
+  if (rs.n < 1 || rs.ticket != ticket || !rs.in_flight) {
+    set_error("this ticket is not in flight (never submitted, already collected, or its result set was reused)");
+    return 2;
+  }
+  // tickets complete in submission order; an older uncollected ticket would be overtaken silently
+  for (auto &o : e->sets)
+    if (o.in_flight && o.ticket < rs.ticket) { set_error("collect tickets in submission order"); return 2; }
   IRMV_CUDA(cudaEventSynchronize(rs.done));
+  rs.in_flight = false;
   parse(e, rs.n, out, counts, set);
   if (rvecs && tvecs && e->pnp_on) {
     const size_t md = e->cfg.max_det, B = e->cfg.max_batch;
@@ -1143,24 +1295,40 @@ int irmv_engine_kernel_launches(irmv_engine *e, int nframes) {
   return chunks * (e->lanes[0].launches_per_replay + 1);
 }
 
-int irmv_engine_rotated_image(irmv_engine *e, int slot, uint8_t *dst) {
-  if (!e || !dst || slot < 0 || slot >= (int)e->slots_host.size()) { set_error("bad argument"); return 1; }
-  IRMV_CUDA(cudaSetDevice(e->cfg.device));
+// get_rotated_image() (reference include/irmv_detection/yolo_engine.hpp:34): the first call switches the
+// engine to "rotated frames on": from then on every detect() also writes the rotated packed-RGB
+// frame of its slot into an address-stable pinned buffer (one rotate kernel + one D2H on the main
+// stream, no allocation, no re-upload), and this call is a pointer return.  The first call itself
+// rotates the frame of the last detect() from the device copy that is still there.
+int irmv_engine_rotated_view(irmv_engine *e, int slot, const uint8_t **view) {
+  if (!e || !view || slot < 0 || slot >= (int)e->slots_host.size()) { set_error("bad argument"); return 1; }
   const size_t bytes = (size_t)e->cfg.src_width * e->cfg.src_height * 3;
-  uint8_t *d = nullptr;
-  IRMV_CUDA(cudaMalloc((void **)&d, bytes));
-  IRMV_CUDA(cudaMemcpyAsync(e->slot_dev, e->slots_host[slot], e->frame_bytes, cudaMemcpyHostToDevice, e->main_stream));
-  PreprocessParams pp{};
-  pp.src = e->slot_dev; pp.dst = e->lanes[0].in8.p; pp.rotated = d; pp.n = 1;
-  pp.src_w = e->cfg.src_width; pp.src_h = e->cfg.src_height; pp.chan_order = e->cfg.chan_order;
-  pp.rotate180 = e->cfg.rotate180; pp.resize_mode = e->cfg.resize_mode; pp.quantize_u8 = e->cfg.quantize_u8;
-  cudaError_t ce = launch_preprocess(pp, e->main_stream);
-  if (ce == cudaSuccess) ce = cudaMemcpyAsync(dst, d, bytes, cudaMemcpyDeviceToHost, e->main_stream);
-  if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->main_stream);
-  cudaFree(d);
-  IRMV_CUDA(ce);
+  if (!e->rotated_on || !e->rot_host[slot] || !e->rot_valid[slot]) {
+    if (pipeline_busy(e)) return 5;
+    IRMV_CUDA(cudaSetDevice(e->cfg.device));
+    if (!e->rot_dev) IRMV_CUDA(dev_malloc((void **)&e->rot_dev, bytes));
+    for (auto &h : e->rot_host)
+      if (!h) { IRMV_CUDA(host_malloc((void **)&h, bytes)); memset(h, 0, bytes); }
+    e->rotated_on = true;
+    if (e->last_slot != slot)      // the device copy holds another slot's frame: bring this one over
+      IRMV_CUDA(cudaMemcpyAsync(e->slot_dev, e->slots_host[slot], e->frame_bytes, cudaMemcpyHostToDevice, e->main_stream));
+    if (int rc = refresh_rotated(e, slot)) return rc;
+    IRMV_CUDA(cudaStreamSynchronize(e->main_stream));
+    e->last_slot = slot;
+  }
+  *view = e->rot_host[slot];
   return 0;
 }
+
+int irmv_engine_rotated_image(irmv_engine *e, int slot, uint8_t *dst) {
+  if (!dst) { set_error("bad argument"); return 1; }
+  const uint8_t *v = nullptr;
+  if (int rc = irmv_engine_rotated_view(e, slot, &v)) return rc;
+  memcpy(dst, v, (size_t)e->cfg.src_width * e->cfg.src_height * 3);
+  return 0;
+}
+
+long long irmv_debug_alloc_count(void) { return g_allocs.load(); }
 
 int irmv_engine_read_tensor(irmv_engine *e, const char *name, void *dst, int64_t cap, int32_t dims[5]) {
   if (!e || !name || !dims) { set_error("bad argument"); return 1; }
@@ -1258,6 +1426,47 @@ int irmv_engine_fetch_poses(irmv_engine *e, int nframes, double *rvecs, double *
   return 0;
 }
 
+// Result block of a finished call: ticket < 0 = the last synchronous call (set 0), else a collected
+// pipelined batch whose set has not been reused yet.
+static const uint8_t *result_block(irmv_engine *e, int ticket) {
+  if (ticket < 0) {
+    if (e->sets[0].ticket != -1) { set_error("set 0 holds a pipelined batch: pass its ticket"); return nullptr; }
+    return e->res_host;
+  }
+  const irmv_engine::Set &rs = e->sets[ticket % kSets];
+  if (!rs.res_host || rs.ticket != ticket) { set_error("this ticket's results are gone (never submitted, or its result set was reused)"); return nullptr; }
+  if (rs.in_flight) { set_error("collect the ticket first"); return nullptr; }
+  return rs.res_host;
+}
+
+static_assert(sizeof(irmv_pose) == 88, "irmv_pose layout");
+// The fields IrmDetector::message_callback fills per armor (reference src/irm_detector.cpp:213-230),
+// straight from the fused replay: position = tvec, orientation = tf2 quaternion of Rodrigues(rvec),
+// distance_to_image_center.  out: nframes*max_det entries, slot-aligned with the detections.
+int irmv_engine_fetch_armor_poses(irmv_engine *e, int ticket, int nframes, irmv_pose *out) {
+  if (!e || !out || nframes < 1 || nframes > e->cfg.max_batch) { set_error("bad argument"); return 1; }
+  if (!e->pnp_on) { set_error("PnP stage not enabled"); return 2; }
+  const uint8_t *h = result_block(e, ticket);
+  if (!h) return 2;
+  const size_t md = e->cfg.max_det, B = e->cfg.max_batch;
+  const double *rv = reinterpret_cast<const double *>(h + B * 4 + B * md * 28);
+  const double *tv = reinterpret_cast<const double *>(h + B * 4 + B * md * 28 + B * md * 24);
+  const uint8_t *ok = h + B * 4 + B * md * 28 + B * md * 48;
+  const double *q = reinterpret_cast<const double *>(h + quat_offset(B, md));
+  const float *d = reinterpret_cast<const float *>(h + dist_offset(B, md));
+  const int32_t *num = reinterpret_cast<const int32_t *>(h);
+  for (size_t f = 0; f < (size_t)nframes; ++f)
+    for (size_t i = 0; i < md; ++i) {
+      const size_t k = f * md + i;
+      irmv_pose &o = out[k];
+      for (int c = 0; c < 3; ++c) { o.position[c] = tv[k * 3 + c]; o.rvec[c] = rv[k * 3 + c]; }
+      for (int c = 0; c < 4; ++c) o.orientation[c] = q[k * 4 + c];
+      o.distance_to_image_center = d[k];
+      o.ok = ((int)i < num[f] && ok[k]) ? 1 : 0;
+    }
+  return 0;
+}
+
 int irmv_armor_params_default(irmv_armor_params *p) {
   if (!p) return 1;
   // node parameter defaults, reference src/irm_detector.cpp:152,162-173
@@ -1292,8 +1501,8 @@ int irmv_engine_fetch_armors(irmv_engine *e, int ticket, int nframes, irmv_armor
   if (!e || !out || nframes < 1 || nframes > e->cfg.max_batch) { set_error("bad argument"); return 1; }
   if (!e->armors_on) { set_error("armor stage not enabled"); return 2; }
   const size_t md = e->cfg.max_det, B = e->cfg.max_batch;
-  const uint8_t *h = ticket < 0 ? e->res_host : e->sets[ticket % kSets].res_host;
-  if (!h) { set_error("nothing was submitted under this ticket"); return 2; }
+  const uint8_t *h = result_block(e, ticket);
+  if (!h) return 2;
   memcpy(out, h + armors_offset(B, md), (size_t)nframes * md * sizeof(irmv_armor));
   return 0;
 }
@@ -1319,8 +1528,8 @@ int irmv_engine_fetch_keypoints(irmv_engine *e, int ticket, int nframes, float *
   if (!e || !kpts || nframes < 1 || nframes > e->cfg.max_batch) { set_error("bad argument"); return 1; }
   if (!e->pose) { set_error("the weight file has no keypoint branch"); return 2; }
   const size_t md = e->cfg.max_det, B = e->cfg.max_batch;
-  const uint8_t *h = ticket < 0 ? e->res_host : e->sets[ticket % kSets].res_host;
-  if (!h) { set_error("nothing was submitted under this ticket"); return 2; }
+  const uint8_t *h = result_block(e, ticket);
+  if (!h) return 2;
   const float *src = reinterpret_cast<const float *>(h + kpts_offset(B, md));
   int pad_x, pad_y, new_w, new_h;
   letterbox_geometry(e->cfg.src_width, e->cfg.src_height, e->cfg.resize_mode, &pad_x, &pad_y, &new_w, &new_h);
@@ -1360,15 +1569,15 @@ int irmv_extract_armors(const uint8_t *frames, int frames_on_device, int nframes
   int rc = 0;
   auto body = [&]() -> int {
     if (!frames_on_device) {
-      IRMV_CUDA(cudaMalloc((void **)&d_frames, fb * nframes));
+      IRMV_CUDA(dev_malloc((void **)&d_frames, fb * nframes));
       IRMV_CUDA(cudaMemcpy(d_frames, frames, fb * nframes, cudaMemcpyHostToDevice));
     }
-    IRMV_CUDA(cudaMalloc((void **)&d_num, (size_t)nframes * 4));
-    IRMV_CUDA(cudaMalloc((void **)&d_cls, slots * 4));
-    IRMV_CUDA(cudaMalloc((void **)&d_boxes, slots * 16));
-    IRMV_CUDA(cudaMalloc((void **)&d_scores, slots * 4));
-    IRMV_CUDA(cudaMalloc((void **)&d_out, slots * sizeof(ArmorOut)));
-    IRMV_CUDA(cudaMalloc((void **)&d_scratch, wtotal * 4));
+    IRMV_CUDA(dev_malloc((void **)&d_num, (size_t)nframes * 4));
+    IRMV_CUDA(dev_malloc((void **)&d_cls, slots * 4));
+    IRMV_CUDA(dev_malloc((void **)&d_boxes, slots * 16));
+    IRMV_CUDA(dev_malloc((void **)&d_scores, slots * 4));
+    IRMV_CUDA(dev_malloc((void **)&d_out, slots * sizeof(ArmorOut)));
+    IRMV_CUDA(dev_malloc((void **)&d_scratch, wtotal * 4));
     IRMV_CUDA(cudaMemset(d_scratch, 0, 256));                  // slot locks
     IRMV_CUDA(cudaMemcpy(d_num, counts, (size_t)nframes * 4, cudaMemcpyHostToDevice));
     IRMV_CUDA(cudaMemcpy(d_cls, hc.data(), slots * 4, cudaMemcpyHostToDevice));
@@ -1388,7 +1597,7 @@ int irmv_extract_armors(const uint8_t *frames, int frames_on_device, int nframes
     ap.scratch_words_per_cta = wpc; ap.grid = grid;
     unsigned long long *d_prof = nullptr;
     if (getenv("IRMV_ARMOR_PROF")) {
-      IRMV_CUDA(cudaMalloc((void **)&d_prof, 64));
+      IRMV_CUDA(dev_malloc((void **)&d_prof, 64));
       IRMV_CUDA(cudaMemset(d_prof, 0, 64));
     }
     ap.prof = d_prof;
@@ -1473,6 +1682,36 @@ int irmv_engine_describe_ops(irmv_engine *e, char *buf, int cap) {
   return (int)out.size();
 }
 
+// Debug: the tiling plan of every network-stage kernel for a replay of `nframes` frames, one line per
+// launch in issue order: "raster k s cin cout hw R nepi b_stream ctas_per_sm stages b_stages tail act res tiles",
+// "gather k s cin cout hw" or "pool".  plan() depends on the tile count, so the kernel instantiations
+// differ between replay sizes; tests use this to show which ones an oracle-compared run covers.
+int irmv_engine_describe_plans(irmv_engine *e, int nframes, char *buf, int cap) {
+  if (!e || !buf || cap < 1 || nframes < 1) return -1;
+  std::string out;
+  bool first = true;
+  const bool fused = e->fused_stem && e->cfg.conv_impl != IRMV_CONV_DIRECT;
+  const int n = nframes < e->S ? nframes : e->S;
+  for (auto &o : e->lanes[0].ops) {
+    if (first && fused) { first = false; continue; }
+    first = false;
+    char line[200];
+    if (o.kind == Op::POOL) { out += "pool\n"; continue; }
+    ConvParams p = o.cp;
+    p.B = n;
+    int info[8];
+    if (o.raster && conv_raster_plan_info(p, e->num_sms, info))
+      snprintf(line, sizeof line, "raster %d %d %d %d %d %d %d %d %d %d %d %d %d %d %d\n", p.k, p.stride, p.cin, p.cout, p.OH,
+               info[0], info[1], info[2], info[3], info[4], info[5], info[6], p.act, p.res ? 1 : 0, info[7]);
+    else
+      snprintf(line, sizeof line, "gather %d %d %d %d %d\n", p.k, p.stride, p.cin, p.cout, p.OH);
+    out += line;
+  }
+  if ((int)out.size() + 1 > cap) { set_error("buffer too small"); return -1; }
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return (int)out.size();
+}
+
 // Debug: re-run GEMM number `op_index` of lane 0 on whatever its input buffers hold, with CTA 0
 // writing clock64 stamps per tile: {tile start, before empty wait, after, last k-block issued,
 // MMA first full, MMA last full, epilogue start, epilogue end}.  Returns tiles traced.
@@ -1485,7 +1724,7 @@ int irmv_engine_trace_conv(irmv_engine *e, int op_index, int nframes, long long 
   for (auto &o : ln.ops) if (o.kind == Op::CONV && ++ci == op_index) { op = &o; break; }
   if (!op) { set_error("no such conv"); return -1; }
   long long *d = nullptr;
-  cudaMalloc((void **)&d, (size_t)(cap_tiles + 16) * 64);
+  dev_malloc((void **)&d, (size_t)(cap_tiles + 16) * 64);
   cudaMemset(d, 0, (size_t)(cap_tiles + 16) * 64);
   ConvParams p = op->cp;
   p.B = nframes < e->S ? nframes : e->S;
@@ -1515,10 +1754,10 @@ int irmv_preprocess(const uint8_t *src, int n, int src_w, int src_h, int chan_or
   const size_t ob = (size_t)pr_pixels(n, kNet, kNet) * kInC * 2;     // kernel writes the PR layout
   uint8_t *ds = nullptr, *dr = nullptr;
   __half *dd = nullptr;
-  IRMV_CUDA(cudaMalloc((void **)&ds, fb * n));
-  IRMV_CUDA(cudaMalloc((void **)&dd, ob));
+  IRMV_CUDA(dev_malloc((void **)&ds, fb * n));
+  IRMV_CUDA(dev_malloc((void **)&dd, ob));
   IRMV_CUDA(cudaMemset(dd, 0, ob));
-  if (rotated) IRMV_CUDA(cudaMalloc((void **)&dr, (size_t)src_w * src_h * 3 * n));
+  if (rotated) IRMV_CUDA(dev_malloc((void **)&dr, (size_t)src_w * src_h * 3 * n));
   IRMV_CUDA(cudaMemcpy(ds, src, fb * n, cudaMemcpyHostToDevice));
   PreprocessParams pp{};
   pp.src = ds; pp.dst = dd; pp.rotated = dr; pp.n = n; pp.src_w = src_w; pp.src_h = src_h;
@@ -1538,12 +1777,12 @@ int irmv_preprocess(const uint8_t *src, int n, int src_w, int src_h, int chan_or
 }
 
 static int alloc_nms(int n, int A, int nc, int max_det, NmsScratch &sc, DetPack &dp) {
-  IRMV_CUDA(cudaMalloc((void **)&sc.boxes, (size_t)n * A * 16));
-  IRMV_CUDA(cudaMalloc((void **)&sc.keys, (size_t)n * A * nc * 8));
-  IRMV_CUDA(cudaMalloc((void **)&sc.counts, (size_t)n * 4));
+  IRMV_CUDA(dev_malloc((void **)&sc.boxes, (size_t)n * A * 16));
+  IRMV_CUDA(dev_malloc((void **)&sc.keys, (size_t)n * A * nc * 8));
+  IRMV_CUDA(dev_malloc((void **)&sc.counts, (size_t)n * 4));
   IRMV_CUDA(cudaMemset(sc.counts, 0, (size_t)n * 4));
   dp.init(n, max_det);
-  IRMV_CUDA(cudaMalloc((void **)&dp.dev, dp.bytes));
+  IRMV_CUDA(dev_malloc((void **)&dp.dev, dp.bytes));
   IRMV_CUDA(cudaMemset(dp.dev, 0, dp.bytes));
   return 0;
 }
@@ -1557,7 +1796,7 @@ int irmv_nms(const float *boxes, const float *scores, int n, int A, int nc, floa
   DetPack dp;
   if (int rc = alloc_nms(n, A, nc, max_det, sc, dp)) return rc;
   float *ds = nullptr;
-  IRMV_CUDA(cudaMalloc((void **)&ds, (size_t)n * A * nc * 4));
+  IRMV_CUDA(dev_malloc((void **)&ds, (size_t)n * A * nc * 4));
   IRMV_CUDA(cudaMemcpy(sc.boxes, boxes, (size_t)n * A * 16, cudaMemcpyHostToDevice));
   IRMV_CUDA(cudaMemcpy(ds, scores, (size_t)n * A * nc * 4, cudaMemcpyHostToDevice));
   cudaError_t ce = launch_score_filter(ds, n, A, nc, score_thr, sc, 0);
@@ -1588,10 +1827,10 @@ int irmv_decode(const uint16_t *box, const uint16_t *cls, int n, float *boxes, f
   HeadPtrs h{};
   __half *db[3], *dc[3];
   float *dscores = nullptr;
-  IRMV_CUDA(cudaMalloc((void **)&dscores, (size_t)n * kNumAnchors * nc * 4));
+  IRMV_CUDA(dev_malloc((void **)&dscores, (size_t)n * kNumAnchors * nc * 4));
   for (int s = 0; s < 3; ++s) {
-    IRMV_CUDA(cudaMalloc((void **)&db[s], (size_t)n * cnt[s] * 64 * 2));
-    IRMV_CUDA(cudaMalloc((void **)&dc[s], (size_t)n * cnt[s] * kClsPad * 2));
+    IRMV_CUDA(dev_malloc((void **)&db[s], (size_t)n * cnt[s] * 64 * 2));
+    IRMV_CUDA(dev_malloc((void **)&dc[s], (size_t)n * cnt[s] * kClsPad * 2));
     for (int f = 0; f < n; ++f) {
       IRMV_CUDA(cudaMemcpy(db[s] + (size_t)f * cnt[s] * 64, box + ((size_t)f * kNumAnchors + off[s]) * 64,
                            (size_t)cnt[s] * 64 * 2, cudaMemcpyHostToDevice));
@@ -1628,7 +1867,37 @@ struct irmv_pnp {
   float *h_pts1 = nullptr;    // pinned
   double *h_out1 = nullptr;
   uint8_t *h_ok1 = nullptr;
+  // grow-only device buffers of the batch call: no allocation per call once they are large enough
+  size_t cap = 0;             // armors the buffers below hold
+  float *d_pts = nullptr;
+  double *d_rv = nullptr, *d_tv = nullptr, *d_q = nullptr, *d_rv2 = nullptr, *d_tv2 = nullptr, *d_e = nullptr;
+  uint8_t *d_ok = nullptr;
 };
+
+static void pnp_free_batch(irmv_pnp *p) {
+  cudaFree(p->d_pts); cudaFree(p->d_rv); cudaFree(p->d_tv); cudaFree(p->d_q); cudaFree(p->d_rv2); cudaFree(p->d_tv2);
+  cudaFree(p->d_e); cudaFree(p->d_ok);
+  p->d_pts = nullptr; p->d_rv = p->d_tv = p->d_q = p->d_rv2 = p->d_tv2 = p->d_e = nullptr; p->d_ok = nullptr;
+  p->cap = 0;
+}
+
+static int pnp_reserve(irmv_pnp *p, size_t n) {
+  if (n <= p->cap) return 0;
+  size_t cap = p->cap ? p->cap : 1024;
+  while (cap < n) cap *= 2;
+  IRMV_CUDA(cudaStreamSynchronize(p->stream));
+  pnp_free_batch(p);
+  IRMV_CUDA(irmv::dev_malloc((void **)&p->d_pts, cap * 32));
+  IRMV_CUDA(irmv::dev_malloc((void **)&p->d_rv, cap * 24));
+  IRMV_CUDA(irmv::dev_malloc((void **)&p->d_tv, cap * 24));
+  IRMV_CUDA(irmv::dev_malloc((void **)&p->d_q, cap * 32));
+  IRMV_CUDA(irmv::dev_malloc((void **)&p->d_rv2, cap * 24));
+  IRMV_CUDA(irmv::dev_malloc((void **)&p->d_tv2, cap * 24));
+  IRMV_CUDA(irmv::dev_malloc((void **)&p->d_e, cap * 16));
+  IRMV_CUDA(irmv::dev_malloc((void **)&p->d_ok, cap));
+  p->cap = cap;
+  return 0;
+}
 
 extern "C" {
 
@@ -1649,12 +1918,12 @@ int irmv_pnp_create(const double K[9], const double D[5], int device, irmv_pnp *
   IRMV_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
   IRMV_CUDA(cudaEventCreate(&p->ev0));
   IRMV_CUDA(cudaEventCreate(&p->ev1));
-  IRMV_CUDA(cudaMalloc((void **)&p->d_pts1, 32));
-  IRMV_CUDA(cudaMalloc((void **)&p->d_out1, 48));
-  IRMV_CUDA(cudaMalloc((void **)&p->d_ok1, 4));
-  IRMV_CUDA(cudaHostAlloc((void **)&p->h_pts1, 32, cudaHostAllocDefault));
-  IRMV_CUDA(cudaHostAlloc((void **)&p->h_out1, 48, cudaHostAllocDefault));
-  IRMV_CUDA(cudaHostAlloc((void **)&p->h_ok1, 4, cudaHostAllocDefault));
+  IRMV_CUDA(dev_malloc((void **)&p->d_pts1, 32));
+  IRMV_CUDA(dev_malloc((void **)&p->d_out1, 48));
+  IRMV_CUDA(dev_malloc((void **)&p->d_ok1, 4));
+  IRMV_CUDA(host_malloc((void **)&p->h_pts1, 32));
+  IRMV_CUDA(host_malloc((void **)&p->h_out1, 48));
+  IRMV_CUDA(host_malloc((void **)&p->h_ok1, 4));
   *out = p.release();
   return 0;
 }
@@ -1663,6 +1932,7 @@ void irmv_pnp_destroy(irmv_pnp *p) {
   if (!p) return;
   cudaSetDevice(p->device);
   cudaStreamSynchronize(p->stream);
+  pnp_free_batch(p);
   cudaFree(p->d_pts1); cudaFree(p->d_out1); cudaFree(p->d_ok1);
   cudaFreeHost(p->h_pts1); cudaFreeHost(p->h_out1); cudaFreeHost(p->h_ok1);
   cudaEventDestroy(p->ev0); cudaEventDestroy(p->ev1);
@@ -1675,7 +1945,7 @@ int irmv_pnp_solve(irmv_pnp *p, const float img_pts[8], double rvec[3], double t
   IRMV_CUDA(cudaSetDevice(p->device));
   memcpy(p->h_pts1, img_pts, 32);
   IRMV_CUDA(cudaMemcpyAsync(p->d_pts1, p->h_pts1, 32, cudaMemcpyHostToDevice, p->stream));
-  PnpOut o{p->d_out1, p->d_out1 + 3, p->d_ok1, nullptr, nullptr, nullptr, nullptr};
+  PnpOut o{p->d_out1, p->d_out1 + 3, p->d_ok1, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   IRMV_CUDA(launch_pnp(p->c, p->d_pts1, 1, 0 /* reference: small_armor = true, src/pnp_solver.cpp:47 */, o, p->stream));
   if (p->lm_iters > 0)
     IRMV_CUDA(launch_pnp_refine_lm(p->c, p->d_pts1, 1, 0, p->lm_iters, p->d_out1, p->d_out1 + 3, nullptr, p->stream));
@@ -1694,45 +1964,32 @@ int irmv_pnp_solve_batch_ex(irmv_pnp *p, const float *img_pts, int n, int on_dev
   if (!p || !img_pts || !rvecs || !tvecs || n < 1) { set_error("bad argument"); return 1; }
   IRMV_CUDA(cudaSetDevice(p->device));
   const bool want2 = rvecs2 && tvecs2 && rmse2;
-  float *dp = nullptr;
-  double *dr = nullptr, *dt = nullptr, *dq = nullptr, *dr2 = nullptr, *dt2 = nullptr, *de = nullptr;
-  uint8_t *dk = nullptr;
-  if (on_device) dp = const_cast<float *>(img_pts);
-  else {
-    IRMV_CUDA(cudaMalloc((void **)&dp, (size_t)n * 32));
-    IRMV_CUDA(cudaMemcpyAsync(dp, img_pts, (size_t)n * 32, cudaMemcpyHostToDevice, p->stream));
+  if (int rc = pnp_reserve(p, (size_t)n)) return rc;
+  const float *dp = img_pts;
+  if (!on_device) {
+    IRMV_CUDA(cudaMemcpyAsync(p->d_pts, img_pts, (size_t)n * 32, cudaMemcpyHostToDevice, p->stream));
+    dp = p->d_pts;
   }
-  IRMV_CUDA(cudaMalloc((void **)&dr, (size_t)n * 24));
-  IRMV_CUDA(cudaMalloc((void **)&dt, (size_t)n * 24));
-  IRMV_CUDA(cudaMalloc((void **)&dk, (size_t)n));
-  if (quats) IRMV_CUDA(cudaMalloc((void **)&dq, (size_t)n * 32));
-  if (want2) {
-    IRMV_CUDA(cudaMalloc((void **)&dr2, (size_t)n * 24));
-    IRMV_CUDA(cudaMalloc((void **)&dt2, (size_t)n * 24));
-    IRMV_CUDA(cudaMalloc((void **)&de, (size_t)n * 16));
-  }
-  PnpOut o{dr, dt, dk, dq, dr2, dt2, de};
+  double *dq = quats ? p->d_q : nullptr;
+  PnpOut o{p->d_rv, p->d_tv, p->d_ok, dq, want2 ? p->d_rv2 : nullptr, want2 ? p->d_tv2 : nullptr, want2 ? p->d_e : nullptr,
+           nullptr, nullptr};
   IRMV_CUDA(cudaEventRecord(p->ev0, p->stream));
   IRMV_CUDA(launch_pnp(p->c, dp, n, large, o, p->stream));
-  if (p->lm_iters > 0) IRMV_CUDA(launch_pnp_refine_lm(p->c, dp, n, large, p->lm_iters, dr, dt, dq, p->stream));
+  if (p->lm_iters > 0) IRMV_CUDA(launch_pnp_refine_lm(p->c, dp, n, large, p->lm_iters, p->d_rv, p->d_tv, dq, p->stream));
   IRMV_CUDA(cudaEventRecord(p->ev1, p->stream));
-  IRMV_CUDA(cudaMemcpyAsync(rvecs, dr, (size_t)n * 24, cudaMemcpyDeviceToHost, p->stream));
-  IRMV_CUDA(cudaMemcpyAsync(tvecs, dt, (size_t)n * 24, cudaMemcpyDeviceToHost, p->stream));
-  if (ok) IRMV_CUDA(cudaMemcpyAsync(ok, dk, (size_t)n, cudaMemcpyDeviceToHost, p->stream));
-  if (quats) IRMV_CUDA(cudaMemcpyAsync(quats, dq, (size_t)n * 32, cudaMemcpyDeviceToHost, p->stream));
+  IRMV_CUDA(cudaMemcpyAsync(rvecs, p->d_rv, (size_t)n * 24, cudaMemcpyDeviceToHost, p->stream));
+  IRMV_CUDA(cudaMemcpyAsync(tvecs, p->d_tv, (size_t)n * 24, cudaMemcpyDeviceToHost, p->stream));
+  if (ok) IRMV_CUDA(cudaMemcpyAsync(ok, p->d_ok, (size_t)n, cudaMemcpyDeviceToHost, p->stream));
+  if (quats) IRMV_CUDA(cudaMemcpyAsync(quats, p->d_q, (size_t)n * 32, cudaMemcpyDeviceToHost, p->stream));
   if (want2) {
-    IRMV_CUDA(cudaMemcpyAsync(rvecs2, dr2, (size_t)n * 24, cudaMemcpyDeviceToHost, p->stream));
-    IRMV_CUDA(cudaMemcpyAsync(tvecs2, dt2, (size_t)n * 24, cudaMemcpyDeviceToHost, p->stream));
-    IRMV_CUDA(cudaMemcpyAsync(rmse2, de, (size_t)n * 16, cudaMemcpyDeviceToHost, p->stream));
+    IRMV_CUDA(cudaMemcpyAsync(rvecs2, p->d_rv2, (size_t)n * 24, cudaMemcpyDeviceToHost, p->stream));
+    IRMV_CUDA(cudaMemcpyAsync(tvecs2, p->d_tv2, (size_t)n * 24, cudaMemcpyDeviceToHost, p->stream));
+    IRMV_CUDA(cudaMemcpyAsync(rmse2, p->d_e, (size_t)n * 16, cudaMemcpyDeviceToHost, p->stream));
   }
   IRMV_CUDA(cudaStreamSynchronize(p->stream));
   float ms = 0.f;
   cudaEventElapsedTime(&ms, p->ev0, p->ev1);
   p->last_ms = ms;
-  if (!on_device) cudaFree(dp);
-  cudaFree(dr); cudaFree(dt); cudaFree(dk);
-  if (dq) cudaFree(dq);
-  if (want2) { cudaFree(dr2); cudaFree(dt2); cudaFree(de); }
   return 0;
 }
 

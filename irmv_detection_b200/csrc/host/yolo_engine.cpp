@@ -67,9 +67,19 @@ std::vector<YoloEngine::bbox> YoloEngine::detect()
 
 const cv::Mat & YoloEngine::get_rotated_image() const
 {
-  rotated_store_.resize(static_cast<size_t>(src_image_size_.width) * src_image_size_.height * 3);
-  irmv_engine_rotated_image(engine_, 0, rotated_store_.data());
-  rotated_image_ = cv::Mat(cv::Size(src_image_size_.width, src_image_size_.height), CV_8UC3, rotated_store_.data());
+  // a view of the engine's pinned, address-stable rotated-frame buffer (the reference's cv::Mat is a
+  // view of the buffer its graph rotates in place, yolo_engine.hpp:34): after the first call every
+  // detect() refreshes the buffer, so the per-frame call of the node (src/irm_detector.cpp:183)
+  // copies nothing and allocates nothing
+  const uint8_t * view = nullptr;
+  if (irmv_engine_rotated_view(engine_, 0, &view) != 0) {
+    std::cerr << "[YoloEngine::get_rotated_image] " << irmv_last_error() << std::endl;
+    return rotated_image_;
+  }
+  if (rotated_image_.data != view) {
+    rotated_image_ = cv::Mat(
+      cv::Size(src_image_size_.width, src_image_size_.height), CV_8UC3, const_cast<uint8_t *>(view));
+  }
   return rotated_image_;
 }
 

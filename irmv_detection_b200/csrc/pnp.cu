@@ -200,6 +200,18 @@ __global__ void __launch_bounds__(128) pnp_kernel(PnpConsts C, const float *__re
 #pragma unroll
     for (int k = 0; k < 4; ++k) out.quat[(size_t)i * 4 + k] = qv[k];
   }
+  if (out.dist) {
+    float cxp, cyp;
+    if (out.centers) { cxp = out.centers[(size_t)i * 2]; cyp = out.centers[(size_t)i * 2 + 1]; }
+    else {
+      const float4 *pq = reinterpret_cast<const float4 *>(pts) + (size_t)i * 2;
+      const float4 qa = __ldg(pq), qb = __ldg(pq + 1);
+      cxp = __fmul_rn(__fadd_rn(__fadd_rn(qa.x, qa.z), __fadd_rn(qb.x, qb.z)), 0.25f);
+      cyp = __fmul_rn(__fadd_rn(__fadd_rn(qa.y, qa.w), __fadd_rn(qb.y, qb.w)), 0.25f);
+    }
+    const float dx = __fsub_rn(cxp, (float)C.cx), dy = __fsub_rn(cyp, (float)C.cy);
+    out.dist[i] = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+  }
   if (out.rvec2) {
     double rv2[3];
     rot2vec(Rm[other], rv2);

@@ -6,6 +6,8 @@
 //
 // Arithmetic is written with explicitly rounded FP32 intrinsics so it is bit-identical to
 // oracle/preprocess_ref.py (no FMA contraction).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace irmv {
@@ -189,7 +191,7 @@ __device__ __forceinline__ Region stage_window(const PreprocessParams &p, const 
   const int col_byte_lo = sx_lo * bpp;
   const int nbytes = (sx_hi - sx_lo + 1) * bpp;
   const int chunks_per_row = pitch_s >> 4;
-  const uint8_t *alloc_end = base + (size_t)p.n * frame_bytes;
+  const uint8_t *alloc_end = base + (size_t)(p.frame0 + p.n) * frame_bytes;
   auto stage_chunk = [&](int r, int c) {
     const uint8_t *row = frame + (size_t)(sy_lo + r) * src_pitch + col_byte_lo;
     const uint8_t *a = (const uint8_t *)((size_t)row & ~(size_t)15) + (size_t)c * 16;
@@ -226,7 +228,7 @@ preprocess_kernel(PreprocessParams p, int rows_cap, int pitch_s) {
   const int src_pitch = W * bpp;
   const size_t frame_bytes = (size_t)H * src_pitch;
   const uint8_t *base = p.src_indirect ? *p.src_indirect : p.src;
-  const uint8_t *frame = base + (size_t)n * frame_bytes;
+  const uint8_t *frame = base + (size_t)(p.frame0 + n) * frame_bytes;
   const float scale_x = __fdiv_rn((float)W, (float)p.new_w);
   const float scale_y = __fdiv_rn((float)H, (float)p.new_h);
   const int hp = (p.resize_mode != 0);
@@ -293,7 +295,7 @@ stem_kernel(PreprocessParams p, const float *__restrict__ w, const float *__rest
   const int H = p.src_h, W = p.src_w;
   const size_t frame_bytes = (size_t)H * W * (bayer ? 1 : 3);
   const uint8_t *base = p.src_indirect ? *p.src_indirect : p.src;
-  const uint8_t *frame = base + (size_t)n * frame_bytes;
+  const uint8_t *frame = base + (size_t)(p.frame0 + n) * frame_bytes;
   const float scale_x = __fdiv_rn((float)W, (float)p.new_w), scale_y = __fdiv_rn((float)H, (float)p.new_h);
   const int hp = (p.resize_mode != 0);
   __shared__ float lut[256];
@@ -501,7 +503,7 @@ __global__ void rotate_kernel(PreprocessParams p) {
     int rem = (int)(i - (size_t)n * H * W);
     int y = rem / W, x = rem - y * W;
     int sy = p.rotate180 ? H - 1 - y : y, sx = p.rotate180 ? W - 1 - x : x;
-    const uint8_t *frame = base + (size_t)n * frame_bytes;
+    const uint8_t *frame = base + (size_t)(p.frame0 + n) * frame_bytes;
     int R, G, B;
     if (bayer) {
       Region reg{frame, frame, 0, W, 0, W, 0, 0};
@@ -540,6 +542,15 @@ __global__ void rotate_kernel(PreprocessParams p) {
 
 }  // namespace
 
+cudaError_t launch_rotate(const PreprocessParams &p, cudaStream_t s) {
+  if (p.n <= 0 || !p.rotated) return cudaSuccess;
+  size_t total = (size_t)p.n * p.src_h * p.src_w;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  rotate_kernel<<<blocks, 256, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_preprocess(const PreprocessParams &p_in, cudaStream_t s) {
   PreprocessParams p = p_in;
   letterbox_geometry(p.src_w, p.src_h, p.resize_mode, &p.pad_x, &p.pad_y, &p.new_w, &p.new_h);
@@ -552,12 +563,10 @@ cudaError_t launch_preprocess(const PreprocessParams &p_in, cudaStream_t s) {
   int pitch_s = ((cols_cap * bpp + 15) / 16 + 2) * 16;   // +1 chunk for the alignment shift
   size_t smem = (size_t)rows_cap * pitch_s;
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  if (smem > 48 * 1024) {                 // per device, cheap: no process-wide flag
     cudaError_t e = cudaFuncSetAttribute(preprocess_kernel,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
   }
   dim3 grid((kNet + TW - 1) / TW, (kNet + TH - 1) / TH, p.n);
   preprocess_kernel<<<grid, NT, smem, s>>>(p, rows_cap, pitch_s);
@@ -579,6 +588,18 @@ cudaError_t launch_stem(const PreprocessParams &p_in, const float *w, const floa
   PreprocessParams p = p_in;
   letterbox_geometry(p.src_w, p.src_h, p.resize_mode, &p.pad_x, &p.pad_y, &p.new_w, &p.new_h);
   if (p.n <= 0) return cudaSuccess;
+  static const bool no_fast = getenv("IRMV_NO_STEM_FAST") != nullptr;
+  if (!no_fast && stem_bayer2x_applies(p)) {
+    cudaError_t e = launch_stem_bayer2x(p, p.frame0, w, bias, out, out_pstride, out2, out2_pstride, s);
+    if (e == cudaSuccess && p.rotated) {
+      size_t total = (size_t)p.n * p.src_h * p.src_w;
+      int blocks = (int)((total + 255) / 256);
+      if (blocks > 148 * 16) blocks = 148 * 16;
+      rotate_kernel<<<blocks, 256, 0, s>>>(p);
+      e = cudaGetLastError();
+    }
+    return e;
+  }
   const bool bayer = p.chan_order >= 2;
   const int bpp = bayer ? 1 : 3;
   const float sx = (float)p.src_w / p.new_w, sy = (float)p.src_h / p.new_h;

@@ -108,6 +108,16 @@ class YoloEngine:
         L.check(self._lib.irmv_engine_rotated_image(self._h, slot, out.ctypes.data), "irmv_engine_rotated_image")
         return out
 
+    def get_rotated_view(self, slot: Optional[int] = None) -> np.ndarray:
+        """Zero-copy form of get_rotated_image(): a read-only view of the engine's pinned, address-stable
+        rotated-frame buffer of `slot`, refreshed by every detect() once this has been called."""
+        slot = self._slot if slot is None else slot
+        p = C.c_void_p()
+        L.check(self._lib.irmv_engine_rotated_view(self._h, slot, C.byref(p)), "irmv_engine_rotated_view")
+        n = self.src_image_size[0] * self.src_image_size[1] * 3
+        buf = (C.c_uint8 * n).from_address(p.value)
+        return np.frombuffer(buf, np.uint8).reshape(self.src_image_size[1], self.src_image_size[0], 3)
+
     def get_profiling_time(self) -> float:
         return float(self._lib.irmv_engine_profile_ms(self._h))
 
@@ -201,6 +211,13 @@ class YoloEngine:
                 "irmv_engine_fetch_poses")
         return rv, tv, ok.astype(bool)
 
+    def fetch_armor_poses(self, n: int, ticket: int = -1) -> np.ndarray:
+        """Per-armor message payload of IrmDetector::message_callback (position, tf2 quaternion x y z w,
+        distance_to_image_center, ok) from the fused replay: structured POSE_DTYPE [n, max_det]."""
+        out = np.zeros((n, self.max_det), POSE_DTYPE)
+        L.check(self._lib.irmv_engine_fetch_armor_poses(self._h, ticket, n, out.ctypes.data), "irmv_engine_fetch_armor_poses")
+        return out
+
     def has_keypoints(self) -> bool:
         """True when the weight file carries the keypoint branch (72 convolutions)."""
         return bool(self._lib.irmv_engine_has_keypoints(self._h))
@@ -238,6 +255,19 @@ class YoloEngine:
                 ops.append({"kind": "conv", "k": k, "s": s, "cin": cin, "cout": cout, "hw": hw, "raster": bool(raster),
                             "tail_cout": tail})
         return ops
+
+    def describe_plans(self, n: int):
+        """Tiling plan / kernel instantiation of every network-stage launch for a replay of n frames:
+        list of tuples ("raster", k, s, cin, cout, hw, R, nepi, b_stream, ctas_per_sm, stages, b_stages, tail,
+        act, res, tiles) | ("gather", k, s, cin, cout, hw) | ("pool",)."""
+        buf = C.create_string_buffer(32768)
+        if self._lib.irmv_engine_describe_plans(self._h, n, buf, 32768) < 0:
+            L.check(1, "irmv_engine_describe_plans")
+        out = []
+        for line in buf.value.decode().splitlines():
+            f = line.split()
+            out.append((f[0],) + tuple(int(v) for v in f[1:]))
+        return out
 
     def profile_stages(self, dev_ptr: int, n: int):
         ms = (C.c_float * 5)()
@@ -350,6 +380,8 @@ class PnPSolver:
 
 ARMOR_DTYPE = np.dtype([("pts", np.float32, (4, 2)), ("center", np.float32, 2), ("score", np.float32),
                         ("class_id", np.int32), ("size", np.int32), ("valid", np.int32)])
+POSE_DTYPE = np.dtype([("position", np.float64, 3), ("orientation", np.float64, 4), ("rvec", np.float64, 3),
+                       ("distance_to_image_center", np.float32), ("ok", np.int32)])
 BBOX_DTYPE = np.dtype([("xyxy", np.float32, 4), ("score", np.float32), ("class_id", np.int32)])
 
 

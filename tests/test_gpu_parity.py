@@ -918,3 +918,362 @@ def test_pnp_stress_one_million_properties():
     r1, t1 = P.solve_ippe(base)
     rel = np.linalg.norm(rv[:5000] - r1, axis=1) / np.linalg.norm(r1, axis=1)
     assert np.quantile(rel, 0.99) < PNP_REL_TOL
+
+
+# ------------------------------------------------------- the configuration bench.py times, pinned
+def _frame_vs_oracle(eng, f, x_nhwc8, wpath):
+    """Frame f of the engine's last run (lane 0) against the FP32 oracle on the same network input:
+    head tensors -> decoded scores within 1e-2, boxes within 0.5 px, kept indices bit-exact on the
+    GPU's own decoded inputs."""
+    import irmv_detection_b200 as irmv
+    from oracle import nms_ref as N
+    _, outs, rboxes, rscores = _oracle_forward(wpath, x_nhwc8)
+    box = np.concatenate([eng.read_tensor(f"box{i}")[f:f + 1].reshape(1, -1, 64) for i in range(3)], 1)
+    cls = np.concatenate([eng.read_tensor(f"cls{i}")[f:f + 1].reshape(1, -1, 16) for i in range(3)], 1)
+    gboxes, gscores = irmv.decode(box, cls)
+    assert np.abs(gscores - rscores).max() < SCORE_TOL
+    assert np.abs(gboxes - rboxes).max() < BOX_TOL_PX
+    ri, _, _, _ = N.nms(gboxes[0], gscores[0])
+    return ri, outs
+
+
+def test_bench_configuration_pinned_to_single_frame_engine_and_oracle(base_image, weights_seed0):
+    """bench.py's engine (BASELINE.json configs[3]: Bayer frames, max_batch 256, sub_batch 128, two
+    lanes, fused PnP) runs kernel instantiations that plan() only picks at large tile counts (R = 4 / 2,
+    streamed weights, other ring depths).  Pin that configuration: frames at the start, middle and end
+    of both lanes must equal a max_batch = 1 engine bit for bit (detections, Detect head tensor, poses),
+    and frame 0 must be within tolerance of the FP32 oracle."""
+    import irmv_detection_b200 as irmv
+    from irmv_detection_b200 import synth
+    from oracle import pnp_ref as P
+    _cuda()
+    rgb = synth.frames_from_base(base_image, 16, seed=77)[..., ::-1]
+    raw16 = synth.bayer_from_rgb(rgb, "RGGB")
+    raw = np.ascontiguousarray(np.tile(raw16[:8], (32, 1, 1)))
+    probe = {0: 0, 1: 1, 2: 2, 3: 3, 5: 4, 64: 5, 126: 6, 127: 7, 128: 8, 129: 9, 200: 10, 254: 11, 255: 12}
+    for pos, src in probe.items():
+        raw[pos] = raw16[src + 3 if src + 3 < 16 else src]
+    big = irmv.YoloEngine(weights_seed0, (1280, 1024), chan_order=irmv.CH_BAYER_RGGB, max_batch=256,
+                          sub_batch=128, num_lanes=2)
+    big.enable_pnp(P.K_DEFAULT, P.D_DEFAULT, (0.5, 480 / 1024))
+    res = big.detect_batch(raw)
+    rv, tv, ok = big.fetch_poses(256)
+    box_big = [big.read_tensor(f"box{i}") for i in range(3)]          # lane 0 = frames 0..127
+    cls_big = [big.read_tensor(f"cls{i}") for i in range(3)]
+    one = irmv.YoloEngine(weights_seed0, (1280, 1024), chan_order=irmv.CH_BAYER_RGGB)
+    one.enable_pnp(P.K_DEFAULT, P.D_DEFAULT, (0.5, 480 / 1024))
+    total = 0
+    for pos in probe:
+        r = one.detect_batch(raw[pos:pos + 1])[0]
+        r1, t1, o1 = one.fetch_poses(1)
+        assert r == res[pos], f"frame {pos}: detections differ from the batch-1 engine"
+        k = len(r)
+        total += k
+        assert np.array_equal(rv[pos, :k], r1[0, :k]) and np.array_equal(tv[pos, :k], t1[0, :k]), f"frame {pos}: poses"
+        assert np.array_equal(ok[pos, :k], o1[0, :k])
+        if pos < 128:
+            for i in range(3):
+                assert np.array_equal(one.read_tensor(f"box{i}")[0], box_big[i][pos]), f"frame {pos} box{i}"
+                assert np.array_equal(one.read_tensor(f"cls{i}")[0], cls_big[i][pos]), f"frame {pos} cls{i}"
+    assert total > 0
+    one.close()
+    # frame 0 of the 128-frame replay against the FP32 oracle
+    x = irmv.preprocess(raw[:1], irmv.CH_BAYER_RGGB)
+    ri, _ = _frame_vs_oracle(big, 0, x, weights_seed0)
+    assert np.array_equal(big.kept_indices(0), ri)
+    big.close()
+
+
+def test_keypoint_variant_batch64_pinned(base_image, tmp_path):
+    """BASELINE.json configs[2]'s shape (keypoint weight file, batch 64, one replay): frames across the
+    replay equal the batch-1 engine bit for bit (detections, keypoints, poses); frame 0 within
+    tolerance of the FP32 oracle, raw keypoint tensors included."""
+    import irmv_detection_b200 as irmv
+    from irmv_detection_b200 import synth, weights as W
+    from oracle import pnp_ref as P
+    _cuda()
+    wp = str(tmp_path / "pose_seed0.irmw")
+    W.write_random(wp, 0, pose=True)
+    fr = synth.frames_from_base(base_image, 64, seed=13)
+    big = irmv.YoloEngine(wp, (1280, 1024), max_batch=64, sub_batch=64, num_lanes=1)
+    big.enable_pnp(P.K_DEFAULT, P.D_DEFAULT, (0.5, 480 / 1024))
+    res = big.detect_batch(fr)
+    kp = big.fetch_keypoints(64)
+    rv, tv, ok = big.fetch_poses(64)
+    raw_k = [big.read_tensor(f"kpt{i}") for i in range(3)]
+    one = irmv.YoloEngine(wp, (1280, 1024))
+    one.enable_pnp(P.K_DEFAULT, P.D_DEFAULT, (0.5, 480 / 1024))
+    for pos in (0, 1, 31, 32, 62, 63):
+        r = one.detect_batch(fr[pos:pos + 1])[0]
+        assert r == res[pos], f"frame {pos}"
+        k = len(r)
+        assert np.array_equal(one.fetch_keypoints(1)[0, :k], kp[pos, :k])
+        r1, t1, _ = one.fetch_poses(1)
+        assert np.array_equal(rv[pos, :k], r1[0, :k]) and np.array_equal(tv[pos, :k], t1[0, :k])
+        for i in range(3):
+            assert np.array_equal(one.read_tensor(f"kpt{i}")[0], raw_k[i][pos])
+    one.close()
+    x = irmv.preprocess(fr[:1])
+    ri, outs = _frame_vs_oracle(big, 0, x, wp)
+    assert np.array_equal(big.kept_indices(0), ri)
+    for i in range(3):
+        ref = outs[i][2].permute(0, 2, 3, 1).numpy()
+        assert np.abs(raw_k[i][:1, ..., :8].astype(np.float32) - ref).max() <= 2e-2 * max(np.abs(ref).max(), 1.0)
+    big.close()
+
+
+def test_plans_of_the_bench_shape_are_covered(weights_seed0, tmp_path):
+    """plan() (csrc/conv_raster.cu) picks R, weight streaming, CTAs per SM and ring depths from the tile
+    count, so different replay sizes run different kernel instantiations.  Replay sizes with a test that
+    compares against the FP32 oracle: 1 and 3 (test_network_parity, the batch-1 engines), 64
+    (test_keypoint_variant_batch64_pinned) and 128 (test_bench_configuration_pinned_...).  Every
+    instantiation (k, stride, R, NEPI, b_stream, CTAs/SM, tail, act, res) that occurs at any replay size
+    up to the bench's 128 must occur at one of those sizes."""
+    import irmv_detection_b200 as irmv
+    from irmv_detection_b200 import weights as W
+    _cuda()
+    wp = str(tmp_path / "pose_seed0.irmw")
+    W.write_random(wp, 0, pose=True)
+
+    def signatures(plans):
+        out = set()
+        for p in plans:
+            if p[0] == "raster":
+                _, k, s, cin, cout, hw, R, nepi, bstream, ctas, stages, bstages, tail, act, res, tiles = p
+                out.add(("raster", k, s, R, nepi, bstream, ctas, tail, act, res))
+            elif p[0] == "gather":
+                out.add(("gather", p[1], p[2]))
+        return out
+
+    for path in (weights_seed0, wp):
+        eng = irmv.YoloEngine(path, (1280, 1024), chan_order=irmv.CH_BAYER_RGGB, max_batch=128, sub_batch=128, num_lanes=1)
+        covered = set()
+        for n in (1, 3, 64, 128):
+            covered |= signatures(eng.describe_plans(n))
+        at128 = signatures(eng.describe_plans(128))
+        assert at128 <= covered
+        for n in (2, 8, 16, 32, 48, 96, 100, 127):
+            missing = signatures(eng.describe_plans(n)) - covered
+            assert not missing, f"replay of {n} frames runs instantiations no oracle-compared test covers: {sorted(missing)}"
+        eng.close()
+
+
+# ------------------------------------------------------- fused message_callback outputs
+def _tf2_quaternion(Rm):
+    """tf2::Matrix3x3::getRotation (x, y, z, w), the call at reference src/irm_detector.cpp:224-225."""
+    tr = Rm[0, 0] + Rm[1, 1] + Rm[2, 2]
+    q = np.zeros(4)
+    if tr > 0:
+        s = np.sqrt(tr + 1.0)
+        q[3] = s * 0.5
+        s = 0.5 / s
+        q[0] = (Rm[2, 1] - Rm[1, 2]) * s; q[1] = (Rm[0, 2] - Rm[2, 0]) * s; q[2] = (Rm[1, 0] - Rm[0, 1]) * s
+    else:
+        i = (2 if Rm[1, 1] < Rm[2, 2] else 1) if Rm[0, 0] < Rm[1, 1] else (2 if Rm[0, 0] < Rm[2, 2] else 0)
+        j, k = (i + 1) % 3, (i + 2) % 3
+        s = np.sqrt(Rm[i, i] - Rm[j, j] - Rm[k, k] + 1.0)
+        q[i] = s * 0.5
+        s = 0.5 / s
+        q[3] = (Rm[k, j] - Rm[j, k]) * s
+        q[j] = (Rm[j, i] + Rm[i, j]) * s
+        q[k] = (Rm[k, i] + Rm[i, k]) * s
+    return q
+
+
+def test_fused_message_callback_outputs(weights_seed0):
+    """detect -> extract_armors -> solvePnP -> Rodrigues -> tf2 quaternion -> distance_to_image_center
+    (reference src/irm_detector.cpp:181-230) as one replay: the per-armor payload of
+    irmv_engine_fetch_armor_poses against cv2.Rodrigues + the tf2 formula + the intended distance, for
+    the armor stage (light-bar scene) and for the box-corner pose stage."""
+    import cv2
+    import irmv_detection_b200 as irmv
+    from oracle import armor_ref as A, pnp_ref as P, preprocess_ref as PR
+    _cuda()
+    cs = (np.float32(0.5), np.float32(480 / 1024))
+    cx, cy = np.float32(P.K_DEFAULT[2]), np.float32(P.K_DEFAULT[5])
+
+    def check(poses, rv, tv, ok, centers):
+        n_ok = 0
+        for i in range(len(poses)):
+            p = poses[i]
+            assert bool(p["ok"]) == bool(ok[i])
+            if not ok[i]:
+                continue
+            n_ok += 1
+            assert np.array_equal(p["position"], tv[i]) and np.array_equal(p["rvec"], rv[i])
+            Rm, _ = cv2.Rodrigues(rv[i].reshape(3, 1))
+            q = _tf2_quaternion(Rm)
+            assert np.abs(p["orientation"] - q).max() < 1e-7, (p["orientation"], q)
+            assert abs(np.linalg.norm(p["orientation"]) - 1.0) < 1e-9
+            dx, dy = np.float32(centers[i][0]) - cx, np.float32(centers[i][1]) - cy
+            want = np.sqrt(np.float32(dx * dx + dy * dy))
+            assert abs(float(p["distance_to_image_center"]) - float(want)) <= 1e-4 * max(1.0, float(want))
+        return n_ok
+
+    # (1) box-corner pose stage on camera frames
+    from irmv_detection_b200 import synth
+    fr = synth.frames_from_base(synth.load_base(), 2, seed=4)
+    eng = irmv.YoloEngine(weights_seed0, (1280, 1024), max_batch=2, sub_batch=2)
+    eng.enable_pnp(P.K_DEFAULT, P.D_DEFAULT, cs)
+    dets = eng.detect_batch(fr)
+    rv, tv, ok = eng.fetch_poses(2)
+    poses = eng.fetch_armor_poses(2)
+    seen = 0
+    for f in range(2):
+        k = len(dets[f])
+        cen = [((np.float32(d.xyxy[0]) * cs[0] + np.float32(d.xyxy[0]) * cs[0] + np.float32(d.xyxy[2]) * cs[0] + np.float32(d.xyxy[2]) * cs[0]) * np.float32(0.25),
+                (np.float32(d.xyxy[3]) * cs[1] + np.float32(d.xyxy[1]) * cs[1] + np.float32(d.xyxy[1]) * cs[1] + np.float32(d.xyxy[3]) * cs[1]) * np.float32(0.25))
+               for d in dets[f]]
+        seen += check(poses[f, :k], rv[f, :k], tv[f, :k], ok[f, :k], cen)
+        assert not poses[f, k:]["ok"].any()
+    assert seen > 0
+    eng.close()
+    # (2) armor stage: seeded light-bar scene, boxes injected through the stand-alone stage + solver
+    img, ab, asc, acl = A.synth_armor_scene(6, 3)
+    boxes = np.zeros((1, 8), irmv.BBOX_DTYPE)
+    boxes["xyxy"][0, :6] = ab; boxes["score"][0, :6] = asc; boxes["class_id"][0, :6] = acl
+    arm = irmv.extract_armors(PR.rot180(img)[None], boxes, [6])[0]
+    valid = np.nonzero(arm["valid"])[0]
+    assert len(valid) > 0
+    s = irmv.PnPSolver(P.K_DEFAULT, P.D_DEFAULT)
+    pts = arm["pts"][valid] * np.array(cs, np.float32)
+    rv, tv, okb, q, _, _, _ = s.solve_batch(pts, extended=True)
+    for i in range(len(valid)):
+        if okb[i]:
+            Rm, _ = cv2.Rodrigues(rv[i].reshape(3, 1))
+            assert np.abs(q[i] - _tf2_quaternion(Rm)).max() < 1e-7
+            c = arm["center"][valid[i]] * np.array(cs, np.float32)
+            d = s.calculateDistanceToCenter(c)
+            assert abs(d - float(np.hypot(np.float32(c[0]) - cx, np.float32(c[1]) - cy))) < 1e-3
+    s.close()
+
+
+def test_engine_armor_stage_payload(weights_seed0):
+    """Engine-fused armor stage: the payload's distance uses Armor::center, ok is 0 without an armor."""
+    import cv2
+    import irmv_detection_b200 as irmv
+    from irmv_detection_b200 import synth
+    from oracle import pnp_ref as P
+    _cuda()
+    cs = (np.float32(0.5), np.float32(480 / 1024))
+    fr = synth.frames_from_base(synth.load_base(), 2, seed=4)
+    eng = irmv.YoloEngine(weights_seed0, (1280, 1024), max_batch=2, sub_batch=2)
+    eng.enable_armors(binary_threshold=20, light_min_ratio=0.01, light_max_ratio=10.0, light_max_angle=90.0,
+                      min_small_center_distance=0.0, max_large_center_distance=1e9)
+    eng.enable_pnp(P.K_DEFAULT, P.D_DEFAULT, cs)
+    dets = eng.detect_batch(fr)
+    arm = eng.fetch_armors(2)
+    rv, tv, ok = eng.fetch_poses(2)
+    poses = eng.fetch_armor_poses(2)
+    cx, cy = np.float32(P.K_DEFAULT[2]), np.float32(P.K_DEFAULT[5])
+    for f in range(2):
+        for i in range(len(dets[f])):
+            assert bool(poses[f, i]["ok"]) == bool(ok[f, i])
+            if ok[f, i]:
+                assert arm[f, i]["valid"]
+                c = arm[f, i]["center"] * np.array(cs, np.float32)
+                want = float(np.sqrt(np.float32((c[0] - cx) * (c[0] - cx) + (c[1] - cy) * (c[1] - cy))))
+                assert abs(float(poses[f, i]["distance_to_image_center"]) - want) <= 1e-4 * max(1.0, want)
+                Rm, _ = cv2.Rodrigues(rv[f, i].reshape(3, 1))
+                assert np.abs(poses[f, i]["orientation"] - _tf2_quaternion(Rm)).max() < 1e-7
+    eng.close()
+
+
+# ------------------------------------------------------- host-path hygiene
+def test_per_frame_calls_do_not_allocate(base_image, weights_seed0):
+    """After construction and one warm call, detect(), get_rotated_image(), detect_batch(), the pipelined
+    hand-off and the PnP batch call make no device or pinned allocation (cudaMalloc inside
+    irmv_pnp_solve_batch_ex and irmv_engine_rotated_image)."""
+    import torch
+    import irmv_detection_b200 as irmv
+    from irmv_detection_b200 import _lib
+    from oracle import pnp_ref as P
+    _cuda()
+    lib = _lib.lib()
+    eng = irmv.YoloEngine(weights_seed0, (1280, 1024), max_batch=4, sub_batch=2, num_lanes=2)
+    eng.enable_pnp(P.K_DEFAULT, P.D_DEFAULT, (0.5, 480 / 1024))
+    eng.get_src_image_buffer(0)[...] = base_image
+    eng.get_src_image_buffer(1)[...] = base_image[::-1]
+    host = torch.empty((4,) + base_image.shape, dtype=torch.uint8, pin_memory=True).numpy()
+    host[...] = base_image
+    s = irmv.PnPSolver(P.K_DEFAULT, P.D_DEFAULT)
+    quads = P.synth_quads(500, seed=1)
+    # warm: lazily created graphs, result sets, staging and rotated buffers
+    eng.detect(0); eng.detect(1)
+    v0 = eng.get_rotated_view(0)
+    eng.detect_batch_arrays(host)
+    for _ in range(3):
+        eng.collect_arrays(eng.submit_batch(host))
+    s.solve_batch(quads, extended=True)
+    before = lib.irmv_debug_alloc_count()
+    for _ in range(3):
+        eng.detect(0)
+        a = eng.get_rotated_view(0)
+        eng.detect(1)
+        b = eng.get_rotated_view(1)
+        eng.detect_batch_arrays(host)
+        eng.fetch_poses(4); eng.fetch_armor_poses(4)
+        t = [eng.submit_batch(host) for _ in range(3)]
+        for x in t:
+            eng.collect_arrays(x, poses=True)
+        s.solve_batch(quads[:300], extended=True)
+        s.solvePnP(quads[0])
+    assert lib.irmv_debug_alloc_count() == before
+    # the view is address-stable and holds the rotated frame of the slot's last detect()
+    assert a.ctypes.data == v0.ctypes.data
+    assert np.array_equal(a, base_image[::-1, ::-1]) and np.array_equal(b, base_image[:, ::-1])
+    assert np.array_equal(eng.get_rotated_image(0), base_image[::-1, ::-1])
+    s.close(); eng.close()
+
+
+def test_pipelined_handoff_state_is_checked(base_image, weights_seed0):
+    """a fourth submit before a collect, stale / duplicate / out-of-order tickets and synchronous
+    calls while batches are in flight are errors, not silent reads of another batch's results."""
+    import torch
+    import irmv_detection_b200 as irmv
+    _cuda()
+    eng = irmv.YoloEngine(weights_seed0, (1280, 1024), max_batch=2, sub_batch=2)
+    host = torch.empty((2,) + base_image.shape, dtype=torch.uint8, pin_memory=True).numpy()
+    host[...] = base_image
+    eng.get_src_image_buffer(0)[...] = base_image
+    with pytest.raises(irmv.IrmvError):
+        eng.collect_arrays(0)                              # never submitted
+    t0, t1, t2 = (eng.submit_batch(host) for _ in range(3))
+    with pytest.raises(irmv.IrmvError):
+        eng.submit_batch(host)                             # a fourth batch would overwrite set 0
+    with pytest.raises(irmv.IrmvError):
+        eng.detect(0)                                      # synchronous call while batches are in flight
+    with pytest.raises(irmv.IrmvError):
+        eng.detect_batch_arrays(host)
+    with pytest.raises(irmv.IrmvError):
+        eng.collect_arrays(t1)                             # out of order
+    c0, d0 = (np.copy(x) for x in eng.collect_arrays(t0))
+    with pytest.raises(irmv.IrmvError):
+        eng.collect_arrays(t0)                             # duplicate
+    eng.collect_arrays(t1); eng.collect_arrays(t2)
+    with pytest.raises(irmv.IrmvError):
+        eng.collect_arrays(t0 + 3)                         # not issued yet
+    ref = eng.detect(0)                                    # everything collected: synchronous calls work again
+    assert len(ref) == int(c0[0])
+    eng.close()
+
+
+def test_weight_file_validation(tmp_path, weights_seed0):
+    """a corrupt or foreign weight file is refused with an error (nothing throws across the
+    ABI, nothing is indexed past its shape)."""
+    import struct
+    import irmv_detection_b200 as irmv
+    _cuda()
+    blob = open(weights_seed0, "rb").read()
+    cases = {
+        "truncated": blob[: len(blob) // 2],
+        "huge_count": blob[:12] + struct.pack("<I", 0x7fffffff) + blob[16:],
+        "bad_k": blob[:16] + struct.pack("<5I", 3, 16, 5, 2, 1) + blob[36:],
+        "huge_cin": blob[:16] + struct.pack("<5I", 0x40000000, 16, 3, 2, 1) + blob[36:],
+        "wrong_shape": blob[:16] + struct.pack("<5I", 3, 16, 3, 1, 1) + blob[36:],     # stride 1 conv0
+    }
+    for name, data in cases.items():
+        p = tmp_path / f"{name}.irmw"
+        p.write_bytes(data)
+        with pytest.raises(irmv.IrmvError):
+            irmv.YoloEngine(str(p), (1280, 1024))

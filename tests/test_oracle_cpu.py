@@ -425,3 +425,114 @@ def test_letterbox_oracle_vs_cv2(base_image):
         assert ref.shape[:2] == (640, 640) and (px, py, nw, nh) == (left, top, new_unpad[0], new_unpad[1])
         got = np.rint(x.transpose(1, 2, 0) * 255).astype(np.int32)
         assert np.abs(got - ref.astype(np.int32)).max() <= 1
+
+
+def test_stem_integer_lerp_equals_float_oracle():
+    """csrc/stem_bayer.cu replaces the reference's FP32 vertical lerp + 8-bit rounding
+    (floor(a*(1-f) + b*f + 0.5), oracle/preprocess_ref.resize_bilinear_u8) by the integer form
+    (2(Q-k)*a + 2k*b + Q) // 2Q with f = k/Q, and the FP32 tap computation by i0 = (dy*P)//Q.
+    Exhaustive over all 640 rows and all byte pairs for the camera height (1024 -> P/Q = 8/5) and
+    sampled for the other heights the fast path accepts."""
+    from math import gcd
+    from oracle import preprocess_ref as PR
+    one = np.float32(1)
+    a = np.arange(256, dtype=np.float32)[:, None, None]
+    b = np.arange(256, dtype=np.float32)[None, :, None]
+    ai, bi = np.arange(256)[:, None, None], np.arange(256)[None, :, None]
+    for H in (1024, 960, 720, 1080, 800, 640):
+        g = gcd(H, 640)
+        P, Q = H // g, 640 // g
+        assert Q <= 16
+        i0, i1, f = PR._axis_taps(640, H, False)
+        dy = np.arange(640)
+        assert np.array_equal((dy * P) // Q, i0) and np.array_equal(np.minimum((dy * P) // Q + 1, H - 1), i1)
+        k = (dy * P) % Q
+        step = 1 if H == 1024 else 7
+        for d0 in range(0, 640, 64):
+            sl = slice(d0, d0 + 64, step)
+            ff = f[sl][None, None, :]
+            v = a * (one - ff) + b * ff
+            qf = np.clip(np.floor(v + np.float32(0.5)), 0, 255).astype(np.int64)
+            kk = k[sl][None, None, :]
+            qi = ((2 * (Q - kk)) * ai + 2 * kk * bi + Q) // (2 * Q)
+            assert np.array_equal(qf, qi), (H, d0)
+
+
+def _stem_fast_path_emulation(raw, chan, rot):
+    """The sampling arithmetic of stem_bayer2x_kernel (csrc/stem_bayer.cu) in numpy, packed 2 x 16-bit
+    lanes included: network-input pixels as 8-bit values [640, 640, 3]."""
+    from math import gcd
+    H, W = raw.shape
+    g = gcd(H, 640)
+    P, Q = H // g, 640 // g
+    red_y = 1 if chan in (3, 5) else 0
+    red_x = 1 if chan in (3, 4) else 0
+    red_col = ((1 if rot else 0) == red_x)
+    M, K1, K2, QQ = 0x00ff00ff, 0x00010001, 0x00020002, Q * 0x10001
+    out = np.zeros((640, 640, 3), np.int64)
+    j = np.arange(320)
+
+    def refl(i):
+        i = -i if i < 0 else i
+        return 2 * H - 2 - i if i >= H else i
+
+    for iy in range(640):
+        tt = iy * P
+        i0, k = tt // Q, tt % Q
+        i1 = min(i0 + 1, H - 1)
+        wA, wB = 2 * (Q - k), 2 * k
+        if i1 == i0:
+            wA, wB = wA + wB, 0
+        sy0, sy1 = (H - 1 - i0, H - 1 - i1) if rot else (i0, i1)
+        lo = min(sy0, sy1)
+        w_lo, w_hi = (wA, wB) if sy0 <= sy1 else (wB, wA)
+        lo_site = (((lo & 1) == red_y) == red_col)
+        rows = []
+        for d in range(-1, 3):
+            r = raw[min(refl(lo + d), H - 1)].astype(np.int64)
+            buf = np.zeros(16 + W + 16, np.int64)
+            buf[16:16 + W] = r; buf[15] = r[1]; buf[16 + W] = r[W - 2]
+            b4 = buf.reshape(-1, 4)
+            w32 = b4[:, 0] | (b4[:, 1] << 8) | (b4[:, 2] << 16) | (b4[:, 3] << 24)
+            C = w32[4 + j]
+            if rot:
+                N = w32[5 + j]
+                rows.append((C & M, (C >> 8) & M, (((C >> 16) | (N << 16)) & 0xffffffff) & M))
+            else:
+                Pw = w32[3 + j]
+                rows.append(((((Pw >> 24) | (C << 8)) & 0xffffffff) & M, C & M, (C >> 8) & M))
+        r0, r1, r2, r3 = rows                      # (w, c, e) per row
+        if lo_site:
+            cross = ((r0[1] + r2[1] + r1[0] + r1[2] + K2) >> 2) & M
+            diag = ((r0[0] + r0[2] + r2[0] + r2[2] + K2) >> 2) & M
+            cS, cG = r1[1], r2[1]
+            horiz = ((r2[0] + r2[2] + K1) >> 1) & M
+            vert = ((r1[1] + r3[1] + K1) >> 1) & M
+            wS, wG = w_lo, w_hi
+        else:
+            horiz = ((r1[0] + r1[2] + K1) >> 1) & M
+            vert = ((r0[1] + r2[1] + K1) >> 1) & M
+            cG, cS = r1[1], r2[1]
+            cross = ((r1[1] + r3[1] + r2[0] + r2[2] + K2) >> 2) & M
+            diag = ((r1[0] + r1[2] + r3[0] + r3[2] + K2) >> 2) & M
+            wG, wS = w_lo, w_hi
+        RS, BS = (cS, diag) if red_col else (diag, cS)
+        RG, BG = (vert, horiz) if red_col else (horiz, vert)
+        for ch, x in enumerate((RS * wS + RG * wG + QQ, cross * wS + cG * wG + QQ, BS * wS + BG * wG + QQ)):
+            lo16, hi16 = (x & 0xffff) // (2 * Q), (x >> 16) // (2 * Q)
+            if rot:
+                out[iy, 638 - 2 * j, ch] = hi16; out[iy, 639 - 2 * j, ch] = lo16
+            else:
+                out[iy, 2 * j, ch] = lo16; out[iy, 2 * j + 1, ch] = hi16
+    return out
+
+
+@pytest.mark.parametrize("H,chan,rot", [(1024, 2, True), (1024, 5, True), (1024, 3, False), (720, 4, True)])
+def test_stem_fast_path_arithmetic_matches_oracle(H, chan, rot):
+    """The camera-case stem's packed-lane demosaic + integer lerp, restated in numpy, equals the oracle's
+    demosaic -> rot180 -> NPP-convention resize -> 8-bit rounding for every pixel."""
+    from oracle import preprocess_ref as PR
+    raw = np.random.default_rng(H + chan).integers(0, 256, (H, 1280), dtype=np.uint8)
+    x, _ = PR.preprocess(raw, chan, rot, True)
+    ref = np.rint(x.transpose(1, 2, 0) * 255).astype(np.int64)
+    assert np.array_equal(_stem_fast_path_emulation(raw, chan, rot), ref)
