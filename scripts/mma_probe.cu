@@ -2,7 +2,8 @@
 // function of operand layout (no swizzle / 128B swizzle), start-address alignment, N, and the number
 // of independent accumulator chains?  Also checks that a ROW-SHIFTED start address works with the
 // 128B swizzle (the raster convolution reads its 9 taps as shifted views of one halo tile).
-//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o scripts/_bin/mma_probe scripts/mma_probe.cu
+//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -cudart shared -o scripts/_bin/mma_probe scripts/mma_probe.cu
+// (-cudart shared: a statically linked runtime would carry the names of API calls this repo must not ship)
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>

@@ -1022,40 +1022,56 @@ def test_keypoint_variant_batch64_pinned(base_image, tmp_path):
     big.close()
 
 
-def test_plans_of_the_bench_shape_are_covered(weights_seed0, tmp_path):
+def _plan_signatures(plans):
+    out = set()
+    for p in plans:
+        if p[0] == "raster":
+            _, k, s, cin, cout, hw, R, nepi, bstream, ctas, stages, bstages, tail, act, res, tiles = p
+            out.add(("raster", k, s, R, nepi, bstream, ctas, min(stages, 2), tail, act, res))
+        elif p[0] == "gather":
+            out.add(("gather", p[1], p[2]))
+    return out
+
+
+def test_every_plan_instantiation_is_oracle_compared(base_image, weights_seed0):
     """plan() (csrc/conv_raster.cu) picks R, weight streaming, CTAs per SM and ring depths from the tile
-    count, so different replay sizes run different kernel instantiations.  Replay sizes with a test that
-    compares against the FP32 oracle: 1 and 3 (test_network_parity, the batch-1 engines), 64
-    (test_keypoint_variant_batch64_pinned) and 128 (test_bench_configuration_pinned_...).  Every
-    instantiation (k, stride, R, NEPI, b_stream, CTAs/SM, tail, act, res) that occurs at any replay size
-    up to the bench's 128 must occur at one of those sizes."""
+    count, so different replay sizes run different kernel instantiations.  Enumerate the instantiations
+    (k, stride, R, NEPI, b_stream, CTAs/SM, >= 2 stages, tail, act, res) over every replay size 1..128,
+    pick replay sizes that cover all of them (greedy, the bench's 128 first), and for each picked size
+    require frames at the start, middle and end of the replay to equal the batch-1 engine bit for bit
+    (detections + all Detect head tensors) and frame 0 to be within tolerance of the FP32 oracle."""
     import irmv_detection_b200 as irmv
-    from irmv_detection_b200 import weights as W
+    from irmv_detection_b200 import synth
     _cuda()
-    wp = str(tmp_path / "pose_seed0.irmw")
-    W.write_random(wp, 0, pose=True)
-
-    def signatures(plans):
-        out = set()
-        for p in plans:
-            if p[0] == "raster":
-                _, k, s, cin, cout, hw, R, nepi, bstream, ctas, stages, bstages, tail, act, res, tiles = p
-                out.add(("raster", k, s, R, nepi, bstream, ctas, tail, act, res))
-            elif p[0] == "gather":
-                out.add(("gather", p[1], p[2]))
-        return out
-
-    for path in (weights_seed0, wp):
-        eng = irmv.YoloEngine(path, (1280, 1024), chan_order=irmv.CH_BAYER_RGGB, max_batch=128, sub_batch=128, num_lanes=1)
-        covered = set()
-        for n in (1, 3, 64, 128):
-            covered |= signatures(eng.describe_plans(n))
-        at128 = signatures(eng.describe_plans(128))
-        assert at128 <= covered
-        for n in (2, 8, 16, 32, 48, 96, 100, 127):
-            missing = signatures(eng.describe_plans(n)) - covered
-            assert not missing, f"replay of {n} frames runs instantiations no oracle-compared test covers: {sorted(missing)}"
-        eng.close()
+    big = irmv.YoloEngine(weights_seed0, (1280, 1024), chan_order=irmv.CH_BAYER_RGGB, max_batch=128, sub_batch=128, num_lanes=1)
+    sig = {n: _plan_signatures(big.describe_plans(n)) for n in range(1, 129)}
+    every = set().union(*sig.values())
+    picked, covered = [128], set(sig[128])
+    while covered != every:
+        n = max(range(1, 129), key=lambda m: (len(sig[m] - covered), m))
+        picked.append(n)
+        covered |= sig[n]
+    assert len(picked) <= 12, picked
+    rgb = synth.frames_from_base(base_image, 128, seed=55)[..., ::-1]
+    raw = synth.bayer_from_rgb(rgb, "RGGB")
+    one = irmv.YoloEngine(weights_seed0, (1280, 1024), chan_order=irmv.CH_BAYER_RGGB)
+    x0 = irmv.preprocess(raw[:1], irmv.CH_BAYER_RGGB)
+    ref = {}
+    for n in picked:
+        res = big.detect_batch(raw[:n])
+        heads = [big.read_tensor(f"{t}{i}") for t in ("box", "cls") for i in range(3)]
+        for pos in sorted({0, n // 2, n - 1}):
+            if pos not in ref:
+                r = one.detect_batch(raw[pos:pos + 1])[0]
+                ref[pos] = (r, [one.read_tensor(f"{t}{i}")[0].copy() for t in ("box", "cls") for i in range(3)])
+            assert res[pos] == ref[pos][0], f"replay of {n}: frame {pos} detections"
+            for h, hr in zip(heads, ref[pos][1]):
+                assert np.array_equal(h[pos], hr), f"replay of {n}: frame {pos} head tensor"
+        ri, _ = _frame_vs_oracle(big, 0, x0, weights_seed0)
+        assert np.array_equal(big.kept_indices(0), ri), f"replay of {n}"
+    assert sum(len(v[0]) for v in ref.values()) > 0
+    print("replay sizes covering every instantiation:", picked, "instantiations:", len(every))
+    one.close(); big.close()
 
 
 # ------------------------------------------------------- fused message_callback outputs
