@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <vector>
 
 namespace irmv {
 
@@ -77,11 +78,14 @@ cudaError_t launch_preprocess(const PreprocessParams &p, cudaStream_t s);
 cudaError_t launch_rotate(const PreprocessParams &p, cudaStream_t s);
 // Fused preprocess + conv0 (3x3 s2, 3->16, SiLU): w = [16][9 taps][3] FP32, writes two planes.
 // out2 (optional): parity-split twin of the output (see ConvParams).
-cudaError_t launch_stem(const PreprocessParams &p, const float *w, const float *bias, __half *out,
+// fast_tab: device table block of stem_bayer2x_tables() (null: always the generic kernel).
+cudaError_t launch_stem(const PreprocessParams &p, const float *w, const float *bias, const uint32_t *fast_tab, __half *out,
                         long long out_pstride, __half *out2, long long out2_pstride, cudaStream_t s);
 // Camera-case stem (stem_bayer.cu): Bayer source of width 1280, reference resize, 8-bit intermediate.
 bool stem_bayer2x_applies(const PreprocessParams &p);
-cudaError_t launch_stem_bayer2x(const PreprocessParams &p, int frame0, const float *w, const float *bias, __half *out,
+// w [16][9 taps][3], bias [16]; the tables depend on the source height, the Bayer pattern and the rotation
+std::vector<uint32_t> stem_bayer2x_tables(const float *w, const float *bias, int src_h, int chan_order, int rotate180);
+cudaError_t launch_stem_bayer2x(const PreprocessParams &p, int frame0, const uint32_t *tab, __half *out,
                                 long long out_ps, __half *out2, long long out2_ps, cudaStream_t s);
 
 // ---------------------------------------------------------------- convolution

@@ -412,6 +412,7 @@ struct irmv_engine {
   bool pnp_on = false;
   bool fused_stem = true;               // preprocess + conv0 in one kernel (input never materialised)
   float *d_stem_w = nullptr, *d_stem_b = nullptr;
+  uint32_t *d_stem_tab = nullptr;        // table block of the camera-case stem (stem_bayer.cu), or null
   PnpConsts pnp_c{};
   float pnp_sx = 1.f, pnp_sy = 1.f, pnp_px = 0.f, pnp_py = 0.f;
   float corner_sx = 1.f, corner_sy = 1.f;   // source pixels -> calibration frame (irmv_engine_enable_pnp)
@@ -739,7 +740,7 @@ int issue_replay(irmv_engine *e, Lane &ln, int n, cudaStream_t st, int *launches
   pp.chan_order = e->cfg.chan_order; pp.rotate180 = e->cfg.rotate180;
   pp.resize_mode = e->cfg.resize_mode; pp.quantize_u8 = e->cfg.quantize_u8;
   const bool fused = e->fused_stem && e->cfg.conv_impl != IRMV_CONV_DIRECT;
-  if (fused) IRMV_CUDA(launch_stem(pp, e->d_stem_w, e->d_stem_b, ln.stem_out.parity_only ? nullptr : ln.stem_out.p, ln.stem_out.pstride, ln.stem_out.pp, ln.stem_out.pp_stride, st));
+  if (fused) IRMV_CUDA(launch_stem(pp, e->d_stem_w, e->d_stem_b, e->d_stem_tab, ln.stem_out.parity_only ? nullptr : ln.stem_out.p, ln.stem_out.pstride, ln.stem_out.pp, ln.stem_out.pp_stride, st));
   else IRMV_CUDA(launch_preprocess(pp, st));
   cnt += 1 + (ln.rotated ? 1 : 0);
   if (mark(1)) return 1;
@@ -1075,6 +1076,14 @@ int irmv_engine_create(const char *weights_path, const irmv_engine_config *cfg, 
     IRMV_CUDA(cudaMemcpy(e->d_stem_w, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
     IRMV_CUDA(cudaMemcpy(e->d_stem_b, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
     e->fused_stem = cfg->reserved[0] == 0;
+    PreprocessParams probe{};
+    probe.src_w = cfg->src_width; probe.src_h = cfg->src_height; probe.chan_order = cfg->chan_order;
+    probe.resize_mode = cfg->resize_mode; probe.quantize_u8 = cfg->quantize_u8;
+    if (stem_bayer2x_applies(probe)) {
+      const std::vector<uint32_t> tab = stem_bayer2x_tables(w.data(), b.data(), cfg->src_height, cfg->chan_order, cfg->rotate180);
+      IRMV_CUDA(dev_malloc((void **)&e->d_stem_tab, tab.size() * 4));
+      IRMV_CUDA(cudaMemcpy(e->d_stem_tab, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+    }
   }
 
   const bool bayer = cfg->chan_order >= 2;
@@ -1133,7 +1142,7 @@ void irmv_engine_destroy(irmv_engine *e) {
   for (auto s : e->rot_host) if (s) cudaFreeHost(s);
   if (e->rot_dev) cudaFree(e->rot_dev);
   cudaFree(e->slot_dev);
-  cudaFree(e->d_stem_w); cudaFree(e->d_stem_b);
+  cudaFree(e->d_stem_w); cudaFree(e->d_stem_b); cudaFree(e->d_stem_tab);
   if (e->batch_dev) cudaFree(e->batch_dev);
   cudaFreeHost(e->res_host);
   for (int i = 1; i < kSets; ++i) {

@@ -583,14 +583,14 @@ cudaError_t launch_preprocess(const PreprocessParams &p_in, cudaStream_t s) {
 }
 
 
-cudaError_t launch_stem(const PreprocessParams &p_in, const float *w, const float *bias, __half *out,
+cudaError_t launch_stem(const PreprocessParams &p_in, const float *w, const float *bias, const uint32_t *fast_tab, __half *out,
                         long long out_pstride, __half *out2, long long out2_pstride, cudaStream_t s) {
   PreprocessParams p = p_in;
   letterbox_geometry(p.src_w, p.src_h, p.resize_mode, &p.pad_x, &p.pad_y, &p.new_w, &p.new_h);
   if (p.n <= 0) return cudaSuccess;
   static const bool no_fast = getenv("IRMV_NO_STEM_FAST") != nullptr;
-  if (!no_fast && stem_bayer2x_applies(p)) {
-    cudaError_t e = launch_stem_bayer2x(p, p.frame0, w, bias, out, out_pstride, out2, out2_pstride, s);
+  if (!no_fast && fast_tab && stem_bayer2x_applies(p)) {
+    cudaError_t e = launch_stem_bayer2x(p, p.frame0, fast_tab, out, out_pstride, out2, out2_pstride, s);
     if (e == cudaSuccess && p.rotated) {
       size_t total = (size_t)p.n * p.src_h * p.src_w;
       int blocks = (int)((total + 255) / 256);

@@ -23,6 +23,9 @@
 // (16-byte cp.async, always aligned), the tile is [2*OROWS+1][641 px][3] halves, conv0 runs as
 // mma.sync m16n8k16 with K ordered (ky, 3 px x 3 ch + 1 pad) so that every A fragment register is one
 // aligned 32-bit shared-memory load.
+#include <cstring>
+#include <vector>
+
 #include "common.cuh"
 
 namespace irmv {
@@ -31,52 +34,58 @@ namespace {
 constexpr int SW = 1280;                 // source width handled by this kernel (2 * kNet)
 constexpr int RP = 16 + SW + 16;         // staged raw row: [16 B apron | row | 16 B apron]
 constexpr int PITCHW = 965;              // tile row pitch in 32-bit words (641 px * 6 B = 3846 B -> 962 words + skew)
-constexpr int NTHREADS = 512;
 constexpr int OWID = kNet / 2;           // conv0 output side, 320
+constexpr int NWARPS = OWID / 16;        // 20: one warp per 16-pixel column block of the conv0 output
+constexpr int NTHREADS = NWARPS * 32;    // 640
+constexpr int OROWS = 8;                 // conv0 output rows per CTA
+constexpr int NIR = 2 * OROWS + 1;       // network-input rows of the strip (one halo row on top)
+
+struct RowTab { int off; uint32_t w_lo, w_hi; int flags; };   // flags: 1 = lo is a site row, 2 = conv padding row
 
 struct StemBayerArgs {
   const uint8_t *src;                    // frames [..][H][1280]; used when src_indirect == null
   const uint8_t *const *src_indirect;
   int n, H, frame0;                      // frame0: first source frame of this launch
-  int P, Q;                              // H / 640 in lowest terms
-  int red_y, red_x;                      // position of the red sample in the 2x2 Bayer tile
-  int nr_max;                            // staged-row capacity (rows of RP bytes)
-  int lut_n;                             // 2*Q*255 + Q + 1
-  const float *w, *bias;                 // conv0: [16][9 taps][3] FP32, [16]
+  int Q, lut_n;                          // H / 640 = P / Q; entries of the lerp table: 2*Q*255 + Q + 1
+  int tab_strip;                         // word offset of the per-strip tables inside tab
+  const uint32_t *tab;                   // device tables built by stem_bayer2x_tables()
   __half *out; long long out_ps;         // normal layout (may be null)
   __half *out2; long long out2_ps;       // parity-split twin (may be null)
 };
 
-__device__ __forceinline__ int reflect101(int i, int n) {
+// Device table block (built once per engine, stem_bayer2x_tables):
+//   TAB_BFRAG  conv0 B fragments per lane [32][8]: weights * 0.5 as FP16 pairs, K ordered (ky, 3 px x 3 ch + pad)
+//   TAB_BIAS   bias * 0.5 [16] FP32   (SiLU(v) = h + h * tanh(h), h = v / 2: the 0.5 is folded into weights
+//              and bias, exact since it is a power of two)
+//   TAB_LUT    lerp table: entry x (the lerp numerator, < lut_n) = FP16(floor(x / 2Q) / 255)
+//   tab_strip  per strip of OROWS output rows: {vlo, nr, 0, 0} + RowTab[NIR] (sampling parameters per
+//              network-input row: byte offset of source row lo-1 in the staged window, the two vertical
+//              weights (doubled, so the numerator is the byte offset into the FP16 table), flags)
+constexpr int TAB_BFRAG = 0, TAB_BIAS = 256, TAB_LUT = 272;   // offsets in 32-bit words
+constexpr int STRIP_WORDS = 4 + 4 * NIR;
+
+__host__ __device__ inline int reflect101(int i, int n) {
   if (i < 0) i = -i;
   if (i >= n) i = 2 * n - 2 - i;
   return i;
 }
 
-__device__ __forceinline__ float silu_fast(float x) {
-  const float h = 0.5f * x;
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
-  return fmaf(h, t, h);
-}
-
 struct Px3 { uint32_t w, c, e; };        // west / centre / east neighbours of the two needed columns, 2 x 16-bit lanes
 
 // Needed columns of unit j.  ROT (needed columns are odd): 4j+1 (low lane), 4j+3 (high lane);
-// otherwise (even): 4j (low), 4j+2 (high).
+// otherwise (even): 4j (low), 4j+2 (high).  rowj = the row's word j.
 template <bool ROT>
-__device__ __forceinline__ Px3 unpack(const uint8_t *row, int j) {
-  const uint32_t *wp = reinterpret_cast<const uint32_t *>(row);
+__device__ __forceinline__ Px3 unpack(const uint32_t *rowj) {
   constexpr uint32_t M = 0x00ff00ffu;
-  const uint32_t C = wp[j];
+  const uint32_t C = rowj[0];
   Px3 o;
   if (ROT) {
-    const uint32_t N = wp[j + 1];
+    const uint32_t N = rowj[1];
     o.c = (C >> 8) & M;
     o.w = C & M;
     o.e = __funnelshift_r(C, N, 16) & M;
   } else {
-    const uint32_t P = wp[j - 1];
+    const uint32_t P = rowj[-1];
     o.c = C & M;
     o.e = (C >> 8) & M;
     o.w = __funnelshift_r(P, C, 24) & M;
@@ -84,141 +93,131 @@ __device__ __forceinline__ Px3 unpack(const uint8_t *row, int j) {
   return o;
 }
 
-template <bool ROT, bool RED_COL, int OROWS>
-__global__ void __launch_bounds__(NTHREADS) stem_bayer2x_kernel(const __grid_constant__ StemBayerArgs a) {
-  constexpr int NIR = 2 * OROWS + 1;     // network-input rows of the strip (one halo row on top)
+// OUT1 / OUT2: write the normal layout / the parity-split twin (at least one of them)
+template <bool ROT, bool RED_COL, bool OUT1, bool OUT2>
+__global__ void __launch_bounds__(NTHREADS, 2) stem_bayer2x_kernel(const __grid_constant__ StemBayerArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
   uint32_t *tile_w = reinterpret_cast<uint32_t *>(smem);                       // [NIR][PITCHW]
-  __half *lut = reinterpret_cast<__half *>(smem + (size_t)NIR * PITCHW * 4);   // [lut_n]
-  uint8_t *raw = smem + (((size_t)NIR * PITCHW * 4 + (size_t)a.lut_n * 2 + 15) & ~(size_t)15);   // [nr_max][RP]
+  uint8_t *lut = smem + (size_t)NIR * PITCHW * 4;                              // [lut_n] halves
+  uint8_t *raw = smem + (((size_t)NIR * PITCHW * 4 + (size_t)a.lut_n * 2 + 15) & ~(size_t)15);   // [nr][RP]
+  __shared__ __align__(16) RowTab rowtab[NIR];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int H = a.H, P = a.P, Q = a.Q;
-  const int n = blockIdx.y, oy0 = blockIdx.x * OROWS, iy0 = 2 * oy0 - 1;
+  const int H = a.H;
+  const int n = blockIdx.y, oy0 = blockIdx.x * OROWS;
   const uint8_t *base = a.src_indirect ? *a.src_indirect : a.src;
   const uint8_t *frame = base + (size_t)(a.frame0 + n) * ((size_t)H * SW);
+  const uint32_t *strip = a.tab + a.tab_strip + blockIdx.x * STRIP_WORDS;
 
   // ---- source rows of the strip: virtual rows [vlo, vlo + nr), slot = v - vlo, content = row reflect101(v)
-  const int ry_min = (max(iy0, 0) * P) / Q;
-  const int ry_max = min(((iy0 + NIR - 1) * P) / Q + 1, H - 1);
-  const int vlo = (ROT ? H - 1 - ry_max : ry_min) - 1;
-  const int nr = ry_max - ry_min + 4;
-  if (((size_t)frame & 15) == 0) {
-    for (int i = tid; i < nr * (SW / 16); i += NTHREADS) {
-      const int r = i / (SW / 16), c = i - r * (SW / 16);
-      const int sy = min(reflect101(vlo + r, H), H - 1);
-      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(raw + (size_t)r * RP + 16 + c * 16);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(frame + (size_t)sy * SW + c * 16) : "memory");
+  const int vlo = (int)strip[0], nr = (int)strip[1];
+  const bool aligned = ((size_t)frame & 15) == 0;
+  for (int r = warp; r < nr; r += NWARPS) {        // a warp stages whole rows: 80 chunks of 16 bytes
+    const uint8_t *g = frame + (size_t)min(reflect101(vlo + r, H), H - 1) * SW;
+    uint8_t *d = raw + (size_t)r * RP + 16;
+    if (aligned) {
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(d);
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        if (c < 2 || lane < SW / 16 - 64)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)(c * 32 + lane) * 16u), "l"(g + (c * 32 + lane) * 16) : "memory");
+    } else {                                        // caller's frames are not 16-byte aligned: plain byte copies
+      for (int c = lane; c < SW; c += 32) d[c] = g[c];
     }
-  } else {                                // caller's frames are not 16-byte aligned: plain byte copies
-    for (int i = tid; i < nr * SW; i += NTHREADS) {
-      const int r = i / SW, c = i - r * SW;
-      raw[(size_t)r * RP + 16 + c] = frame[(size_t)min(reflect101(vlo + r, H), H - 1) * SW + c];
-    }
+    if (lane == 0) { d[-1] = g[1]; d[SW] = g[SW - 2]; }   // mirrored columns -1 and W (reflect-101)
   }
-  if (tid < nr) {                         // mirrored columns -1 and W (reflect-101), read straight from global
-    const uint8_t *g = frame + (size_t)min(reflect101(vlo + tid, H), H - 1) * SW;
-    raw[(size_t)tid * RP + 15] = g[1];
-    raw[(size_t)tid * RP + 16 + SW] = g[SW - 2];
+  {
+    const uint32_t *gl = a.tab + TAB_LUT;
+    uint32_t *sl = reinterpret_cast<uint32_t *>(lut);
+    for (int i = tid; i < (a.lut_n + 1) / 2; i += NTHREADS) sl[i] = gl[i];
   }
-  // table: numerator of the vertical lerp -> FP16(q / 255), q = x / 2Q (the 8-bit intermediate of the reference)
-  for (int x = tid; x < a.lut_n; x += NTHREADS) lut[x] = __float2half_rn(__fdiv_rn((float)(x / (2 * Q)), 255.0f));
-  // conv padding of the tile: column 0 (ix = -1) and the pad half behind the last pixel
   if (tid < NIR) {
+    reinterpret_cast<uint4 *>(rowtab)[tid] = reinterpret_cast<const uint4 *>(strip + 4)[tid];
+    // conv padding of the tile: column 0 (ix = -1) and the pad half behind the last pixel
     uint16_t *row16 = reinterpret_cast<uint16_t *>(tile_w + (size_t)tid * PITCHW);
     row16[0] = row16[1] = row16[2] = 0;
     row16[3 * 641] = 0; row16[3 * 641 + 1] = 0;
   }
-  // conv0 B fragments (constants): k = ky*10 + (kx*3 + c), entry 9 of every ky group and k >= 30 are zero
-  const int g = lane >> 2, t = lane & 3;
-  uint32_t bfrag[2][2][2];
-#pragma unroll
-  for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-    for (int s2 = 0; s2 < 2; ++s2)
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        float v[2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int k = 16 * s2 + 2 * t + 8 * h + e, ky = k / 10, j = k - ky * 10;
-          v[e] = (ky < 3 && j < 9) ? a.w[(nt * 8 + g) * 27 + ky * 9 + j] : 0.f;
-        }
-        const __half2 hv = __floats2half2_rn(v[0], v[1]);
-        bfrag[nt][s2][h] = *reinterpret_cast<const uint32_t *>(&hv);
-      }
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
 
-  // ---- sampling: warp task = (input row r, 32 units); unit = two network-input pixels
-  constexpr uint32_t M = 0x00ff00ffu;
-  const uint32_t K1 = 0x00010001u, K2 = 0x00020002u;
-  for (int task = warp; task < NIR * 10; task += NTHREADS / 32) {
-    const int r = task / 10, j = (task - r * 10) * 32 + lane;
-    const int iy = iy0 + r;
+  // ---- sampling: a warp owns 32 units (= 64 network-input columns) and every second input row
+  {
+    constexpr uint32_t M = 0x00ff00ffu;
+    const uint32_t K1 = 0x00010001u, K2 = 0x00020002u;
+    const uint32_t QQ = 2u * (uint32_t)a.Q * 0x00010001u;   // rounding term in both lanes (doubled like the weights)
+    const uint32_t lut_s = (uint32_t)__cvta_generic_to_shared(lut);
+    auto lut_ld = [&](uint32_t byte_off) -> uint32_t {
+      uint16_t v;
+      asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(lut_s + byte_off));
+      return (uint32_t)v;
+    };
+    const int chunk = warp % 10, j = chunk * 32 + lane;
     // first / second pixel of the unit in ascending ix; tile column = ix + 1
-    const int ix_first = ROT ? 638 - 2 * j : 2 * j;
-    uint8_t *dst = reinterpret_cast<uint8_t *>(tile_w + (size_t)r * PITCHW) + 6 * (ix_first + 1);
-    if (iy < 0) {                         // conv padding row above the image
-      *reinterpret_cast<uint16_t *>(dst) = 0;
-      *reinterpret_cast<uint32_t *>(dst + 2) = 0;
-      *reinterpret_cast<uint32_t *>(dst + 6) = 0;
-      *reinterpret_cast<uint16_t *>(dst + 10) = 0;
-      continue;
+    uint8_t *dst = reinterpret_cast<uint8_t *>(tile_w) + (ROT ? 6 * 639 - 12 * j : 6 + 12 * j) + (size_t)(warp / 10) * (PITCHW * 4);
+    const uint32_t *rawj = reinterpret_cast<const uint32_t *>(raw) + j;
+    for (int r = warp / 10; r < NIR; r += 2, dst += 2 * PITCHW * 4) {
+      const RowTab rt = rowtab[r];
+      if (rt.flags & 2) {                   // conv padding row above the image
+        *reinterpret_cast<uint16_t *>(dst) = 0;
+        *reinterpret_cast<uint32_t *>(dst + 2) = 0;
+        *reinterpret_cast<uint32_t *>(dst + 6) = 0;
+        *reinterpret_cast<uint16_t *>(dst + 10) = 0;
+        continue;
+      }
+      const uint32_t *rp = rawj + (rt.off >> 2);
+      const Px3 r0 = unpack<ROT>(rp), r1 = unpack<ROT>(rp + RP / 4), r2 = unpack<ROT>(rp + 2 * (RP / 4)),
+                r3 = unpack<ROT>(rp + 3 * (RP / 4));
+      uint32_t cross, diag, cS, horiz, vert, cG, wS, wG;
+      if (rt.flags & 1) {                   // site row = lo (r0 r1 r2), green row = lo + 1 (r1 r2 r3)
+        cross = ((r0.c + r2.c + r1.w + r1.e + K2) >> 2) & M;
+        diag = ((r0.w + r0.e + r2.w + r2.e + K2) >> 2) & M;
+        cS = r1.c;
+        horiz = ((r2.w + r2.e + K1) >> 1) & M;
+        vert = ((r1.c + r3.c + K1) >> 1) & M;
+        cG = r2.c;
+        wS = rt.w_lo; wG = rt.w_hi;
+      } else {                              // green row = lo, site row = lo + 1
+        horiz = ((r1.w + r1.e + K1) >> 1) & M;
+        vert = ((r0.c + r2.c + K1) >> 1) & M;
+        cG = r1.c;
+        cross = ((r1.c + r3.c + r2.w + r2.e + K2) >> 2) & M;
+        diag = ((r1.w + r1.e + r3.w + r3.e + K2) >> 2) & M;
+        cS = r2.c;
+        wG = rt.w_lo; wS = rt.w_hi;
+      }
+      // site row: own colour at the centre, green = cross, the other colour = diagonal; green row on a
+      // red row (RED_COL == false): R horizontal, B vertical; on a blue row: R vertical, B horizontal
+      const uint32_t RS = RED_COL ? cS : diag, BS = RED_COL ? diag : cS;
+      const uint32_t RG = RED_COL ? vert : horiz, BG = RED_COL ? horiz : vert;
+      const uint32_t xr = RS * wS + RG * wG + QQ;
+      const uint32_t xg = cross * wS + cG * wG + QQ;
+      const uint32_t xb = BS * wS + BG * wG + QQ;
+      const uint32_t r_l = lut_ld(xr & 0xffffu), r_h = lut_ld(xr >> 16);
+      const uint32_t g_l = lut_ld(xg & 0xffffu), g_h = lut_ld(xg >> 16);
+      const uint32_t b_l = lut_ld(xb & 0xffffu), b_h = lut_ld(xb >> 16);
+      // ROT: the high lane (column 4j+3) is the smaller ix
+      const uint32_t R1 = ROT ? r_h : r_l, G1 = ROT ? g_h : g_l, B1 = ROT ? b_h : b_l;
+      const uint32_t R2 = ROT ? r_l : r_h, G2 = ROT ? g_l : g_h, B2 = ROT ? b_l : b_h;
+      *reinterpret_cast<uint16_t *>(dst) = (uint16_t)R1;
+      *reinterpret_cast<uint32_t *>(dst + 2) = G1 | (B1 << 16);
+      *reinterpret_cast<uint32_t *>(dst + 6) = R2 | (G2 << 16);
+      *reinterpret_cast<uint16_t *>(dst + 10) = (uint16_t)B2;
     }
-    const int tt = iy * P, i0 = tt / Q, k = tt - i0 * Q, i1 = min(i0 + 1, H - 1);
-    int wA = 2 * (Q - k), wB = 2 * k;
-    if (i1 == i0) { wA += wB; wB = 0; }
-    const int sy0 = ROT ? H - 1 - i0 : i0, sy1 = ROT ? H - 1 - i1 : i1;
-    const int lo = min(sy0, sy1);
-    const uint32_t w_lo = (uint32_t)(sy0 <= sy1 ? wA : wB), w_hi = (uint32_t)(sy0 <= sy1 ? wB : wA);
-    // a "site" row holds the red or blue sample at the needed columns, a "green" row the green one
-    const bool lo_site = (((lo & 1) == a.red_y) == RED_COL);
-    const uint8_t *rp = raw + (size_t)(lo - 1 - vlo) * RP + 16;
-    const Px3 r0 = unpack<ROT>(rp, j), r1 = unpack<ROT>(rp + RP, j), r2 = unpack<ROT>(rp + 2 * RP, j),
-              r3 = unpack<ROT>(rp + 3 * RP, j);
-    uint32_t cross, diag, cS, horiz, vert, cG, wS, wG;
-    if (lo_site) {                        // site row = lo (r0 r1 r2), green row = lo + 1 (r1 r2 r3)
-      cross = ((r0.c + r2.c + r1.w + r1.e + K2) >> 2) & M;
-      diag = ((r0.w + r0.e + r2.w + r2.e + K2) >> 2) & M;
-      cS = r1.c;
-      horiz = ((r2.w + r2.e + K1) >> 1) & M;
-      vert = ((r1.c + r3.c + K1) >> 1) & M;
-      cG = r2.c;
-      wS = w_lo; wG = w_hi;
-    } else {                              // green row = lo, site row = lo + 1
-      horiz = ((r1.w + r1.e + K1) >> 1) & M;
-      vert = ((r0.c + r2.c + K1) >> 1) & M;
-      cG = r1.c;
-      cross = ((r1.c + r3.c + r2.w + r2.e + K2) >> 2) & M;
-      diag = ((r1.w + r1.e + r3.w + r3.e + K2) >> 2) & M;
-      cS = r2.c;
-      wG = w_lo; wS = w_hi;
-    }
-    // site row: own colour at the centre, green = cross, the other colour = diagonal; green row on a
-    // red row (RED_COL == false): R horizontal, B vertical; on a blue row: R vertical, B horizontal
-    const uint32_t RS = RED_COL ? cS : diag, BS = RED_COL ? diag : cS;
-    const uint32_t RG = RED_COL ? vert : horiz, BG = RED_COL ? horiz : vert;
-    const uint32_t QQ = (uint32_t)Q * 0x00010001u;     // rounding term in both lanes
-    const uint32_t xr = RS * wS + RG * wG + QQ;
-    const uint32_t xg = cross * wS + cG * wG + QQ;
-    const uint32_t xb = BS * wS + BG * wG + QQ;
-    const uint16_t *lut16 = reinterpret_cast<const uint16_t *>(lut);
-    const uint32_t r_l = lut16[xr & 0xffffu], r_h = lut16[xr >> 16];
-    const uint32_t g_l = lut16[xg & 0xffffu], g_h = lut16[xg >> 16];
-    const uint32_t b_l = lut16[xb & 0xffffu], b_h = lut16[xb >> 16];
-    // ROT: the high lane (column 4j+3) is the smaller ix
-    const uint32_t R1 = ROT ? r_h : r_l, G1 = ROT ? g_h : g_l, B1 = ROT ? b_h : b_l;
-    const uint32_t R2 = ROT ? r_l : r_h, G2 = ROT ? g_l : g_h, B2 = ROT ? b_l : b_h;
-    *reinterpret_cast<uint16_t *>(dst) = (uint16_t)R1;
-    *reinterpret_cast<uint32_t *>(dst + 2) = G1 | (B1 << 16);
-    *reinterpret_cast<uint32_t *>(dst + 6) = R2 | (G2 << 16);
-    *reinterpret_cast<uint16_t *>(dst + 10) = (uint16_t)B2;
   }
   __syncthreads();
 
   // ---- conv0: implicit GEMM on mma.sync m16n8k16 (FP16 operands, FP32 accumulate).  An m-tile is 16
   // consecutive pixels of one output row; A[px][k] = tile[2*orow + ky][2*px + kx][c] = the 10 halves
-  // starting at word 3*px of tile row 2*orow + ky.
+  // starting at word 3*px of tile row 2*orow + ky.  A warp owns one 16-pixel column block and walks
+  // down the OROWS output rows, so every address below advances by a constant.
+  const int g = lane >> 2, t = lane & 3;
+  uint32_t bfrag[2][2][2];                 // [n-tile][k-step][2], constants from the table block
+  {
+    const uint4 b0 = reinterpret_cast<const uint4 *>(a.tab + TAB_BFRAG)[lane * 2];
+    const uint4 b1 = reinterpret_cast<const uint4 *>(a.tab + TAB_BFRAG)[lane * 2 + 1];
+    bfrag[0][0][0] = b0.x; bfrag[0][0][1] = b0.y; bfrag[0][1][0] = b0.z; bfrag[0][1][1] = b0.w;
+    bfrag[1][0][0] = b1.x; bfrag[1][0][1] = b1.y; bfrag[1][1][0] = b1.z; bfrag[1][1][1] = b1.w;
+  }
   int off[2][2];
 #pragma unroll
   for (int s2 = 0; s2 < 2; ++s2)
@@ -227,17 +226,27 @@ __global__ void __launch_bounds__(NTHREADS) stem_bayer2x_kernel(const __grid_con
       const int kw = 8 * s2 + 4 * h + t, ky = kw / 5, tp = kw - ky * 5;
       off[s2][h] = ky < 3 ? ky * PITCHW + tp : 0;
     }
-  float bias_r[2][2];
+  float hbias[2][2];                       // bias / 2
+  {
+    const float *hb = reinterpret_cast<const float *>(a.tab + TAB_BIAS);
 #pragma unroll
-  for (int nt = 0; nt < 2; ++nt) { bias_r[nt][0] = a.bias[nt * 8 + 2 * t]; bias_r[nt][1] = a.bias[nt * 8 + 2 * t + 1]; }
-  for (int mt = warp; mt < OROWS * (OWID / 16); mt += NTHREADS / 32) {
-    const int orow = mt / (OWID / 16), xb = (mt - orow * (OWID / 16)) * 16;
-    const uint32_t *tw = tile_w + (size_t)(2 * orow) * PITCHW + 3 * (xb + g);
+    for (int nt = 0; nt < 2; ++nt) { hbias[nt][0] = hb[nt * 8 + 2 * t]; hbias[nt][1] = hb[nt * 8 + 2 * t + 1]; }
+  }
+  const int xb = warp * 16;
+  const uint32_t *tw = tile_w + 3 * (xb + g);
+  // output pointers for row oy0 (even): normal layout, and the twin's plane group of (y & 1 = 0, x & 1 = g & 1);
+  // lane holds channels {2t, 2t+1} of plane 0 (nt = 0) and plane 1 for pixels xb + g and xb + g + 8
+  __half *o1 = a.out + ((long long)(n * (OWID + 1) + 1 + oy0) * (OWID + 1) + xb + g) * 8 + 2 * t;
+  __half *o2 = a.out2 + (long long)((g & 1) * 2) * a.out2_ps +
+               ((long long)(n * (OWID / 2 + 1) + 1 + (oy0 >> 1)) * (OWID / 2 + 1) + ((xb + g) >> 1)) * 8 + 2 * t;
+  const long long ps1 = a.out_ps, ps2 = a.out2_ps;
+#pragma unroll 1
+  for (int orow = 0; orow < OROWS; ++orow, tw += 2 * PITCHW) {
     float acc[2][4];
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt) {
-      acc[nt][0] = acc[nt][2] = bias_r[nt][0];
-      acc[nt][1] = acc[nt][3] = bias_r[nt][1];
+      acc[nt][0] = acc[nt][2] = hbias[nt][0];
+      acc[nt][1] = acc[nt][3] = hbias[nt][1];
     }
 #pragma unroll
     for (int s2 = 0; s2 < 2; ++s2) {
@@ -248,38 +257,57 @@ __global__ void __launch_bounds__(NTHREADS) stem_bayer2x_kernel(const __grid_con
                      : "+f"(acc[nt][0]), "+f"(acc[nt][1]), "+f"(acc[nt][2]), "+f"(acc[nt][3])
                      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bfrag[nt][s2][0]), "r"(bfrag[nt][s2][1]));
     }
-    // lane holds channels {2t, 2t+1} of plane 0 (nt = 0) and plane 1 for pixels xb + g and xb + g + 8
-    const int y = oy0 + orow;
-    const long long rb = pr_index(n, y, 0, OWID, OWID), rb2 = pr_index(n, y >> 1, 0, OWID / 2, OWID / 2);
+    // acc = v / 2 (folded 0.5): SiLU(v) = h + h * tanh(h)
+    __half2 hv[2][2];
 #pragma unroll
-    for (int hr = 0; hr < 2; ++hr) {
-      const int x = xb + g + 8 * hr;
+    for (int hr = 0; hr < 2; ++hr)
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt) {
-        const __half2 hv = __floats2half2_rn(silu_fast(acc[nt][2 * hr]), silu_fast(acc[nt][2 * hr + 1]));
-        if (a.out) {
-          const long long pix = rb + x;
-          *reinterpret_cast<__half2 *>(a.out + (long long)nt * a.out_ps + pix * 8 + 2 * t) = hv;
-        }
-        if (a.out2) {                     // parity-split twin for the stride-2 consumer (common.cuh, ConvParams)
-          const long long pix2 = rb2 + (x >> 1);
-          *reinterpret_cast<__half2 *>(a.out2 + (long long)(((y & 1) * 2 + (x & 1)) * 2 + nt) * a.out2_ps + pix2 * 8 + 2 * t) = hv;
-        }
+        float t0, t1;
+        const float h0 = acc[nt][2 * hr], h1 = acc[nt][2 * hr + 1];
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+        hv[hr][nt] = __floats2half2_rn(fmaf(h0, t0, h0), fmaf(h1, t1, h1));
       }
+    if (OUT1) {
+#pragma unroll
+      for (int hr = 0; hr < 2; ++hr)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) *reinterpret_cast<__half2 *>(o1 + nt * ps1 + hr * 64) = hv[hr][nt];
+      o1 += (OWID + 1) * 8;
+    }
+    if (OUT2) {                            // parity-split twin for the stride-2 consumer (common.cuh, ConvParams)
+      __half *o = o2 + ((orow & 1) ? 4 * ps2 : 0);     // plane group of row parity y & 1 (oy0 is even)
+#pragma unroll
+      for (int hr = 0; hr < 2; ++hr)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) *reinterpret_cast<__half2 *>(o + nt * ps2 + hr * 32) = hv[hr][nt];
+      if (orow & 1) o2 += (OWID / 2 + 1) * 8;
     }
   }
 }
 
 int gcd_i(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
 
-template <bool ROT, bool RED_COL, int OROWS>
-cudaError_t launch_t(const StemBayerArgs &a, size_t smem, cudaStream_t s) {
-  cudaError_t e = cudaFuncSetAttribute(stem_bayer2x_kernel<ROT, RED_COL, OROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <bool ROT, bool RED_COL, bool OUT1, bool OUT2>
+cudaError_t launch_o(const StemBayerArgs &a, size_t smem, cudaStream_t s) {
+  cudaError_t e = cudaFuncSetAttribute(stem_bayer2x_kernel<ROT, RED_COL, OUT1, OUT2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   dim3 grid(OWID / OROWS, a.n);
-  stem_bayer2x_kernel<ROT, RED_COL, OROWS><<<grid, NTHREADS, smem, s>>>(a);
+  stem_bayer2x_kernel<ROT, RED_COL, OUT1, OUT2><<<grid, NTHREADS, smem, s>>>(a);
   return cudaGetLastError();
 }
+
+template <bool ROT, bool RED_COL>
+cudaError_t launch_t(const StemBayerArgs &a, size_t smem, cudaStream_t s) {
+  if (a.out && a.out2) return launch_o<ROT, RED_COL, true, true>(a, smem, s);
+  if (a.out2) return launch_o<ROT, RED_COL, false, true>(a, smem, s);
+  if (a.out) return launch_o<ROT, RED_COL, true, false>(a, smem, s);
+  return cudaErrorInvalidValue;
+}
+
+// staged-row capacity for a source of height H (H / 640 = P / Q)
+int nr_max_for(int P, int Q) { return (2 * OROWS * P + Q - 1) / Q + 6; }
 
 }  // namespace
 
@@ -291,25 +319,91 @@ bool stem_bayer2x_applies(const PreprocessParams &p) {
   return kNet / g <= 16;
 }
 
-cudaError_t launch_stem_bayer2x(const PreprocessParams &p, int frame0, const float *w, const float *bias, __half *out,
+// Host side of the table block (layout above): conv0 weights w[16][9 taps][3] and bias[16] as the engine
+// keeps them (FP32 values that are FP16-exact), for a source of height src_h, rotated or not, with the
+// red sample on rows of parity red_y and the needed columns on red columns or not.
+std::vector<uint32_t> stem_bayer2x_tables(const float *w, const float *bias, int src_h, int chan_order, int rotate180) {
+  const int g0 = gcd_i(src_h, kNet), P = src_h / g0, Q = kNet / g0, H = src_h;
+  const int lut_n = 2 * Q * 255 + Q + 1;
+  const int tab_strip = TAB_LUT + (lut_n + 7) / 8 * 4;
+  const int nstrips = OWID / OROWS;
+  std::vector<uint32_t> tab(tab_strip + nstrips * STRIP_WORDS, 0u);
+  for (int lane = 0; lane < 32; ++lane) {
+    const int g = lane >> 2, t = lane & 3;
+    for (int nt = 0; nt < 2; ++nt)
+      for (int s2 = 0; s2 < 2; ++s2)
+        for (int h = 0; h < 2; ++h) {
+          uint16_t v[2];
+          for (int e = 0; e < 2; ++e) {
+            const int k = 16 * s2 + 2 * t + 8 * h + e, ky = k / 10, j = k - ky * 10;
+            const float wv = (ky < 3 && j < 9) ? 0.5f * w[(nt * 8 + g) * 27 + ky * 9 + j] : 0.f;
+            const __half hv = __float2half_rn(wv);
+            memcpy(&v[e], &hv, 2);
+          }
+          tab[TAB_BFRAG + lane * 8 + nt * 4 + s2 * 2 + h] = (uint32_t)v[0] | ((uint32_t)v[1] << 16);
+        }
+  }
+  for (int i = 0; i < 16; ++i) {
+    const float hb = 0.5f * bias[i];
+    memcpy(&tab[TAB_BIAS + i], &hb, 4);
+  }
+  uint16_t *lut = reinterpret_cast<uint16_t *>(tab.data() + TAB_LUT);
+  for (int x = 0; x < lut_n; ++x) {
+    const __half hv = __float2half_rn((float)(x / (2 * Q)) / 255.0f);
+    memcpy(&lut[x], &hv, 2);
+  }
+  const bool rot = rotate180 != 0;
+  const int red_y = (chan_order == 3 || chan_order == 5) ? 1 : 0;       // BGGR, GBRG: red on odd rows
+  const int red_x = (chan_order == 3 || chan_order == 4) ? 1 : 0;       // BGGR, GRBG: red on odd columns
+  const bool red_col = ((rot ? 1 : 0) == red_x);                        // needed columns: odd with rot180, even without
+  for (int sidx = 0; sidx < nstrips; ++sidx) {
+    uint32_t *st = tab.data() + tab_strip + sidx * STRIP_WORDS;
+    const int iy0 = 2 * sidx * OROWS - 1;
+    const int ry_min = ((iy0 > 0 ? iy0 : 0) * P) / Q;
+    int ry_max = ((iy0 + NIR - 1) * P) / Q + 1;
+    if (ry_max > H - 1) ry_max = H - 1;
+    const int vlo = (rot ? H - 1 - ry_max : ry_min) - 1;
+    st[0] = (uint32_t)vlo;
+    st[1] = (uint32_t)(ry_max - ry_min + 4);
+    for (int r = 0; r < NIR; ++r) {
+      RowTab rt{0, 0u, 0u, 2};
+      const int iy = iy0 + r;
+      if (iy >= 0) {
+        const int tt = iy * P, i0 = tt / Q, k = tt - i0 * Q, i1 = (i0 + 1 < H - 1) ? i0 + 1 : H - 1;
+        int wA = 2 * (Q - k), wB = 2 * k;
+        if (i1 == i0) { wA += wB; wB = 0; }
+        const int sy0 = rot ? H - 1 - i0 : i0, sy1 = rot ? H - 1 - i1 : i1;
+        const int lo = sy0 < sy1 ? sy0 : sy1;
+        // weights doubled: the lerp numerator then is the BYTE offset into the FP16 table
+        rt.w_lo = 2u * (uint32_t)(sy0 <= sy1 ? wA : wB);
+        rt.w_hi = 2u * (uint32_t)(sy0 <= sy1 ? wB : wA);
+        // a "site" row holds the red or blue sample at the needed columns, a "green" row the green one
+        rt.flags = ((((lo & 1) == red_y) == red_col) ? 1 : 0);
+        rt.off = (lo - 1 - vlo) * RP + 16;
+      }
+      memcpy(st + 4 + 4 * r, &rt, 16);
+    }
+  }
+  return tab;
+}
+
+cudaError_t launch_stem_bayer2x(const PreprocessParams &p, int frame0, const uint32_t *tab, __half *out,
                                 long long out_ps, __half *out2, long long out2_ps, cudaStream_t s) {
-  constexpr int OROWS = 8;
   StemBayerArgs a{};
   a.src = p.src; a.src_indirect = p.src_indirect; a.n = p.n; a.H = p.src_h; a.frame0 = frame0;
   const int g = gcd_i(p.src_h, kNet);
-  a.P = p.src_h / g; a.Q = kNet / g;
-  a.red_y = (p.chan_order == 3 || p.chan_order == 5) ? 1 : 0;      // BGGR, GBRG: red on odd rows
-  a.red_x = (p.chan_order == 3 || p.chan_order == 4) ? 1 : 0;      // BGGR, GRBG: red on odd columns
-  a.nr_max = (2 * OROWS * a.P + a.Q - 1) / a.Q + 6;
-  a.lut_n = 2 * a.Q * 255 + a.Q + 1;
-  a.w = w; a.bias = bias; a.out = out; a.out_ps = out_ps; a.out2 = out2; a.out2_ps = out2_ps;
-  const size_t smem = (((size_t)(2 * OROWS + 1) * PITCHW * 4 + (size_t)a.lut_n * 2 + 15) & ~(size_t)15) + (size_t)a.nr_max * RP;
+  const int P = p.src_h / g, Q = kNet / g;
+  const int red_x = (p.chan_order == 3 || p.chan_order == 4) ? 1 : 0;   // BGGR, GRBG: red on odd columns
+  a.Q = Q; a.lut_n = 2 * Q * 255 + Q + 1;
+  a.tab_strip = TAB_LUT + (a.lut_n + 7) / 8 * 4;
+  a.tab = tab; a.out = out; a.out_ps = out_ps; a.out2 = out2; a.out2_ps = out2_ps;
+  const size_t smem = (((size_t)NIR * PITCHW * 4 + (size_t)a.lut_n * 2 + 15) & ~(size_t)15) + (size_t)nr_max_for(P, Q) * RP;
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   // needed columns: W - 1 - 2*ix (odd) with rot180, 2*ix (even) without
   const bool rot = p.rotate180 != 0;
-  const bool red_col = ((rot ? 1 : 0) == a.red_x);
-  if (rot) return red_col ? launch_t<true, true, OROWS>(a, smem, s) : launch_t<true, false, OROWS>(a, smem, s);
-  return red_col ? launch_t<false, true, OROWS>(a, smem, s) : launch_t<false, false, OROWS>(a, smem, s);
+  const bool red_col = ((rot ? 1 : 0) == red_x);
+  if (rot) return red_col ? launch_t<true, true>(a, smem, s) : launch_t<true, false>(a, smem, s);
+  return red_col ? launch_t<false, true>(a, smem, s) : launch_t<false, false>(a, smem, s);
 }
 
 }  // namespace irmv
