@@ -159,6 +159,8 @@ int irmv_engine_enqueue_batch(irmv_engine *e, const uint8_t *frames_dev, int nfr
 int irmv_engine_sync(irmv_engine *e);
 int irmv_engine_fetch(irmv_engine *e, int nframes, irmv_bbox *out, int *counts);
 double irmv_engine_profile_ms(irmv_engine *e);
+/* Cumulative bytes of the host->device and device->host copies the engine has queued. */
+int irmv_engine_copy_bytes(irmv_engine *e, unsigned long long *h2d, unsigned long long *d2h);
 /* Device time of the last enqueue/detect (CUDA events on the engine's streams), ms. */
 double irmv_engine_last_device_ms(irmv_engine *e);
 int irmv_engine_kernel_launches(irmv_engine *e, int nframes);

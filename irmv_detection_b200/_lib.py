@@ -69,6 +69,7 @@ SYMBOLS = {
     "irmv_engine_sync": (C.c_int, [_P]),
     "irmv_engine_fetch": (C.c_int, [_P, C.c_int, C.POINTER(Bbox), C.POINTER(C.c_int)]),
     "irmv_engine_profile_ms": (C.c_double, [_P]),
+    "irmv_engine_copy_bytes": (C.c_int, [_P, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
     "irmv_engine_last_device_ms": (C.c_double, [_P]),
     "irmv_engine_kernel_launches": (C.c_int, [_P, C.c_int]),
     "irmv_engine_stream": (_P, [_P]),

@@ -52,6 +52,7 @@ struct PreprocessParams {
   uint8_t *rotated;            // optional [n][H][W][3] rotated RGB image, may be null
   int n, src_w, src_h;
   int frame0;                  // index of the first source frame of this launch (chunked replays)
+  int rev_order;               // 1: CTAs walk frames and strips from the last to the first (see ConvParams::rev_tiles)
   int chan_order, rotate180, resize_mode, quantize_u8;
   // filled by letterbox_geometry(): the resized image is new_w x new_h at (pad_x, pad_y) of the
   // 640 x 640 network input (stretch modes: 640 x 640 at (0, 0))
@@ -94,7 +95,14 @@ struct ConvSeg {
   long long pstride;    // halfs between consecutive planes
   int c;                // channels read (multiple of 8)
   int up;               // 1: tensor is half resolution, read with nearest 2x upsampling
+  int runs;             // raster kernel: 0 = the planes are contiguous; k > 0 = they form runs of r = 1 << (k-1)
+                        // planes, one run every 2r planes (plane i of the slice = plane (i / r) * 2r + i % r
+                        // counted from ptr).  The ShuffleNetV2 units process every second run of a stage
+                        // buffer in place (channel split + shuffle cost zero bytes).
 };
+__host__ __device__ inline int run_plane(int i, int runs) {
+  return runs == 0 ? i : (((i >> (runs - 1)) << runs) + (i & ((1 << (runs - 1)) - 1)));
+}
 
 struct ConvParams {
   ConvSeg seg[2];
@@ -115,6 +123,7 @@ struct ConvParams {
   const float *bias;       // [npad]
   __half *out;             // pixel 0 of the first output plane (raster kernel: null = only the parity twin is written)
   long long out_pstride;
+  int out_runs;            // output planes in runs like ConvSeg::runs (raster kernel, no tail / twin / residual)
   const __half *res;       // residual added after the activation (same grid as out); may be null
   long long res_pstride;
   // Parity-split twin tensors (raster kernel only).  A tensor of C channels on an H x W grid is
@@ -137,6 +146,9 @@ struct ConvParams {
   int in_parity;           // 1: seg[0].ptr / pstride describe the parity twin of the input
   __half *out2;            // parity twin of the output (written in addition to `out`); may be null
   long long out2_pstride;
+  int rev_tiles;           // 1: process the tiles from the last to the first.  Consecutive layers alternate the
+                           // direction, so a layer starts with the part of its input the producer wrote last --
+                           // the part that is still in the 126 MB L2 (tensors of a 128-frame replay are 100-400 MB)
   int sync_mode;           // tcgen05 producer hand-off: 0 = cp.async-tracked mbarrier, 1 = wait+fence
   long long *trace;        // debug: CTA 0 writes per-tile clock64 stamps [tile][8]; null in production
   int trace_cap;
@@ -157,6 +169,20 @@ cudaError_t launch_conv_raster(const ConvParams &p, int num_sms, cudaStream_t s)
 __host__ __device__ inline int32_t ktab_meta(int tap, int seg, int valid, int plane) {
   return tap | (seg << 4) | (valid << 5) | (plane << 8);
 }
+
+// ---------------------------------------------------------------- depthwise 3x3 (ShuffleNetV2 units)
+struct DwParams {
+  const __half *in;        // pixel 0 of the first input plane (padded raster layout)
+  long long in_ps;         // halfs between planes
+  __half *out;             // pixel 0 of the first output plane
+  long long out_ps;
+  const __half *w;         // [planes][9 taps][8 channels]
+  const float *bias;       // [planes][8]
+  int planes, B, H, W;     // input grid
+  int stride;              // 1 or 2 (pad 1)
+  int rev;                 // walk blocks from the last to the first (see ConvParams::rev_tiles)
+};
+cudaError_t launch_dwconv3x3(const DwParams &p, cudaStream_t s);
 
 // ---------------------------------------------------------------- SPPF pooling
 // in: planes [0, c/8) of `buf`; writes maxpool5, maxpool5^2, maxpool5^3 to the three following

@@ -146,6 +146,7 @@ struct RArgs {
   // fused 1x1 tail (ConvParams::tail_w): intermediate tile [cout/8][TM][8], tail weights, tail bias
   uint32_t off_mid, off_ext, off_bt, off_tbias, bt_bytes, tail_idesc;
   int ext_planes;                         // tail input planes that come from global memory (ConvParams::tail_ext)
+  int rev;                                // walk the tiles from the last to the first (ConvParams::rev_tiles)
   int tmem_tail0;                         // first TMEM column of the tail accumulators
 };
 
@@ -314,6 +315,8 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
     __half *const out = p.out;
     const __half *const res = p.res;
     const long long out_ps = p.out_pstride, res_ps = p.res_pstride;
+    const int orl = p.out_runs;
+    const long long out_ps_pair = orl == 1 ? 2 * out_ps : out_ps;   // distance between the two planes of a 16-channel chunk
     const int cout = p.cout;
     const int Wp = a.Wp, Hp1 = a.Hp1, W = p.OW, q_end = a.q_end, TM = a.TM;
     __half *const out2 = p.out2;
@@ -381,7 +384,8 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
       if (lane == 0) mbar_arrive(&bars->tail_empty[tb]);
     };
     int it = 0, prev_tile = -1;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tseq = blockIdx.x; tseq < num_tiles; tseq += gridDim.x, ++it) {
+      const int tile = a.rev ? num_tiles - 1 - tseq : tseq;
       const int buf = it & 1;
       const uint32_t aph = (uint32_t)(it >> 1) & 1u;
       const bool tr = trace && blockIdx.x == 0 && tid == 0 && it < trace_cap;
@@ -402,7 +406,7 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
         const int r = w >> chunk_shift;
         t.c0 = (w & chunk_mask) << 4;
         t.ok = ((okmask >> r) & 1u) && t.c0 < cout;
-        const long long off = (long long)(t.c0 >> 3) * out_ps + r * 1024;
+        const long long off = (long long)run_plane(t.c0 >> 3, orl) * out_ps + r * 1024;
         t.o = out ? out_q + off : nullptr;
         t.o2 = nullptr;
         t.mid = TAIL ? mid_lane + (uint32_t)((t.c0 >> 3) * TM + r * 128) * 16u : 0u;
@@ -431,13 +435,13 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
         tc_ld_wait();                                       // va ready
         const bool more_b = w + NSUB < items;
         if (more_b) tc_ld16(setup(w + NSUB, ib), vb);
-        if (ia.ok) epi_chunk<ACT, RES, TAIL != 0>(va, s_hb + ia.c0, ia.o, out_ps, ia.o2, out2_ps, ia.r0, ia.r1, ia.mid, (uint32_t)TM * 16u);
+        if (ia.ok) epi_chunk<ACT, RES, TAIL != 0>(va, s_hb + ia.c0, ia.o, out_ps_pair, ia.o2, out2_ps, ia.r0, ia.r1, ia.mid, (uint32_t)TM * 16u);
         else if (TAIL) st_shared_zero2(ia.mid, (uint32_t)TM * 16u);
         if (!more_b) break;
         tc_ld_wait();                                       // vb ready
         const bool more_a = w + 2 * NSUB < items;
         if (more_a) tc_ld16(setup(w + 2 * NSUB, ia), va);
-        if (ib.ok) epi_chunk<ACT, RES, TAIL != 0>(vb, s_hb + ib.c0, ib.o, out_ps, ib.o2, out2_ps, ib.r0, ib.r1, ib.mid, (uint32_t)TM * 16u);
+        if (ib.ok) epi_chunk<ACT, RES, TAIL != 0>(vb, s_hb + ib.c0, ib.o, out_ps_pair, ib.o2, out2_ps, ib.r0, ib.r1, ib.mid, (uint32_t)TM * 16u);
         else if (TAIL) st_shared_zero2(ib.mid, (uint32_t)TM * 16u);
         if (!more_a) break;
         w += 2 * NSUB;
@@ -466,6 +470,7 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
       const uint32_t tile_tx = plane_bytes * (uint32_t)a.NP;
       const int n0 = p.in_parity ? a.NP : p.seg[0].c >> 3, n1 = p.nseg > 1 ? p.seg[1].c >> 3 : 0;
       const size_t ps0 = (size_t)p.seg[0].pstride * 2, ps1 = (size_t)p.seg[1].pstride * 2;
+      const int rl0 = p.in_parity ? 0 : p.seg[0].runs;
       // fused tail over a concat: the tail's other input planes for tile number j (no halo), loaded
       // one tile behind the main operand (tail(j) runs after main(j+1), see the MMA warp)
       const uint32_t ext_bytes = (uint32_t)a.TM * 16u;
@@ -479,7 +484,8 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
         for (int c = 0; c < a.ext_planes; ++c, dst += ext_bytes, src += pse) bulk_g2s(dst, src, ext_bytes, bar);
       };
       int prev_tile = -1;
-      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++itl) {
+      for (int tseq = blockIdx.x; tseq < a.num_tiles; tseq += gridDim.x, ++itl) {
+        const int tile = a.rev ? a.num_tiles - 1 - tseq : tseq;
         const bool tr = p.trace && blockIdx.x == 0 && itl < p.trace_cap;
         if (tr) p.trace[itl * 8 + 0] = clock64();
         const long long qlo = (long long)a.q_begin + (long long)tile * a.TM - a.halo_front;
@@ -489,7 +495,11 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
         mbar_expect_tx(bar, tile_tx);
         uint32_t dst = sA_u + (uint32_t)s * a.a_stage_bytes;
         const uint8_t *src = reinterpret_cast<const uint8_t *>(p.seg[0].ptr) + qlo * 16;
-        for (int c = 0; c < n0; ++c, dst += pitch_bytes, src += ps0) bulk_g2s(dst, src, plane_bytes, bar);
+        if (rl0 == 0) {
+          for (int c = 0; c < n0; ++c, dst += pitch_bytes, src += ps0) bulk_g2s(dst, src, plane_bytes, bar);
+        } else {                                            // planes in runs (ConvSeg::runs)
+          for (int c = 0; c < n0; ++c, dst += pitch_bytes) bulk_g2s(dst, src + (size_t)run_plane(c, rl0) * ps0, plane_bytes, bar);
+        }
         src = reinterpret_cast<const uint8_t *>(p.seg[1].ptr) + qlo * 16;
         for (int c = 0; c < n1; ++c, dst += pitch_bytes, src += ps1) bulk_g2s(dst, src, plane_bytes, bar);
         if (tr) p.trace[itl * 8 + 2] = clock64();
@@ -641,7 +651,10 @@ bool plan(const ConvParams &p, int num_sms, RArgs &a) {
   for (int i = 0; i < p.nseg; ++i) if (p.seg[i].up || p.seg[i].c % 8) return false;
   if (p.OW + 2 + 8 > kGuardFront || p.cout % 16 != 0) return false;
   if (p.out2 && ((p.OH & 1) || (p.OW & 1))) return false;
+  // planes in runs: plain 1x1 / 3x3 convs only (no twin, residual, tail or second segment)
+  if ((p.out_runs || p.seg[0].runs) && (p.out2 || p.res || p.tail_w || p.in_parity || p.nseg != 1)) return false;
   a.p = p;
+  a.rev = p.rev_tiles;
   a.NCH = p.cin / 8;
   a.NP = s2 ? 4 * a.NCH : a.NCH;                     // planes per activation stage
   a.taps = p.k * p.k;
@@ -680,7 +693,9 @@ bool plan(const ConvParams &p, int num_sms, RArgs &a) {
   auto stage_bytes = [&](int R) { return (size_t)a.NP * plane_pixels(R) * 16; };
   int best_R = 0;
   a.b_stream = 0;
+  static const int rmax_env = getenv("IRMV_RMAX") ? atoi(getenv("IRMV_RMAX")) : 4;   // tuning knob
   for (int R = 4; R >= 1; R >>= 1) {
+    if (R > rmax_env) continue;
     if (2 * R * (p.npad + tnp) > 512) continue;
     if (a.b_bytes + tail_bytes(R) + 2 * stage_bytes(R) + misc > (size_t)SMEM_BUDGET) continue;
     long long tiles = (Mr + 128 * R - 1) / (128 * R);

@@ -161,7 +161,7 @@ __device__ __forceinline__ float silu(float x) {
 
 struct TcArgs {
   ConvParams p;
-  int M, num_tiles, KB, ksteps_last, stages, b_resident, tmem_cols;
+  int M, num_tiles, KB, ksteps_last, stages, b_resident, tmem_cols, rev;
   uint32_t idesc;
   uint32_t mul_ow, mul_oh;      // ceil(2^34 / OW), ceil(2^34 / OH): q = (n * mul) >> 34, exact for n < 2^25
   uint32_t off_b, off_ktab, off_bias, off_bars;
@@ -235,7 +235,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
     int own = 0;               // k-blocks this group has issued
     int s_pub = grp % stages;  // ring slot of the next k-block this group publishes
     int itp = 0;
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++itp) {
+    for (int tseq = blockIdx.x; tseq < a.num_tiles; tseq += gridDim.x, ++itp) {
+      const int tile = a.rev ? a.num_tiles - 1 - tseq : tseq; (void)tile;
       const bool tr = p.trace && blockIdx.x == 0 && tid == 0 && itp < p.trace_cap;
       if (tr) p.trace[itp * 8 + 0] = clock64();
       int off0[8], off1[8];
@@ -290,7 +291,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
     const int ew = warp - EPI_WARP0;
     const int row = ew * 32 + lane;
     int it = 0;
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+    for (int tseq = blockIdx.x; tseq < a.num_tiles; tseq += gridDim.x, ++it) {
+      const int tile = a.rev ? a.num_tiles - 1 - tseq : tseq; (void)tile;
       const int acc = it & 1;
       const uint32_t aph = (uint32_t)(it >> 1) & 1u;
       const bool tr = p.trace && blockIdx.x == 0 && tid == EPI_WARP0 * 32 && it < p.trace_cap;
@@ -353,7 +355,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
     int it = 0, s = 0;
     uint32_t ph = 0;
     const int stages = a.stages, KB = a.KB;
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+    for (int tseq = blockIdx.x; tseq < a.num_tiles; tseq += gridDim.x, ++it) {
+      const int tile = a.rev ? a.num_tiles - 1 - tseq : tseq; (void)tile;
       const int acc = it & 1;
       const uint32_t aph = (uint32_t)(it >> 1) & 1u;
       mbar_wait_warp(&bars->tmem_empty[acc], aph ^ 1u, lane);
@@ -396,7 +399,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
       } else {
         int s = 0;
         uint32_t ph = 0;
-        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+        for (int tseq = blockIdx.x; tseq < a.num_tiles; tseq += gridDim.x) {
+      const int tile = a.rev ? a.num_tiles - 1 - tseq : tseq; (void)tile;
           for (int kb = 0; kb < a.KB; ++kb) {
             mbar_wait(&bars->empty[s], ph ^ 1u);
             mbar_expect_tx(&bars->full[s], b_block_bytes);
@@ -443,6 +447,7 @@ cudaError_t launch_conv_tc(const ConvParams &p, int num_sms, cudaStream_t s) {
   a.p = p;
   a.M = p.B * p.OH * p.OW;
   a.num_tiles = (a.M + BM - 1) / BM;
+  a.rev = p.rev_tiles;
   a.KB = p.kpad / BK;
   const int ksteps_total = (p.K + 15) / 16;
   a.ksteps_last = ksteps_total - (a.KB - 1) * 4;

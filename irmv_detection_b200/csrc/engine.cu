@@ -7,6 +7,7 @@
 //   :202-220 parse_output(): scale boxes by (W/640, H/640), class id -> ArmorClass/UNKNOWN
 // What changed: unified memory -> pinned host slots + device buffers; TensorRT/NPP -> the kernels
 // in this directory; batch-1 -> sub-batches replayed on several lanes (streams).
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -69,11 +70,13 @@ struct HostConv {   // one GEMM as the kernels see it (possibly several referenc
 };
 
 struct FileConv {
-  int cin, cout, k, stride, act;
-  std::vector<float> w, b;   // w [cout][cin][k][k]
+  int cin, cout, k, stride, act, groups = 1;
+  std::vector<float> w, b;   // w [cout][cin / groups][k][k]
 };
 
-bool read_weights(const char *path, int &nc, std::vector<FileConv> &out) {
+constexpr int kArchYolov8n = 0, kArchShuffleKpt = 1;   // irmv_detection_b200/weights.py ARCH_*
+
+bool read_weights(const char *path, int &nc, int &arch, std::vector<FileConv> &out) {
   FILE *f = fopen(path, "rb");
   if (!f) { set_error(std::string("cannot open weight file ") + path); return false; }
   auto fail = [&](const std::string &why) { fclose(f); set_error(std::string(path) + ": " + why); return false; };
@@ -82,21 +85,30 @@ bool read_weights(const char *path, int &nc, std::vector<FileConv> &out) {
   rewind(f);
   char magic[4];
   uint32_t hdr[3];
-  if (fread(magic, 1, 4, f) != 4 || memcmp(magic, "IRMW", 4) != 0 || fread(hdr, 4, 3, f) != 3 || hdr[0] != 1)
-    return fail("not an IRMW v1 weight file");
+  if (fread(magic, 1, 4, f) != 4 || memcmp(magic, "IRMW", 4) != 0 || fread(hdr, 4, 3, f) != 3 || (hdr[0] != 1 && hdr[0] != 2))
+    return fail("not an IRMW v1/v2 weight file");
+  const bool v2 = hdr[0] == 2;          // v2: + architecture id in the header, + groups per convolution
+  arch = kArchYolov8n;
+  if (v2) {
+    uint32_t a = 0;
+    if (fread(&a, 4, 1, f) != 1 || a > 1) return fail("unknown architecture id");
+    arch = (int)a;
+  }
   // nothing in the header is trusted: counts and shapes are bounded before anything is allocated
   if (hdr[2] < 1 || hdr[2] > 512) return fail("implausible convolution count");
   nc = (int)hdr[1];
   out.resize(hdr[2]);
-  long long left = file_bytes - 16;
+  long long left = file_bytes - (v2 ? 20 : 16);
   for (auto &c : out) {
-    uint32_t h[5];
-    if (left < 20 || fread(h, 4, 5, f) != 5) return fail("truncated weight file");
-    left -= 20;
-    if (h[0] < 1 || h[0] > 4096 || h[1] < 1 || h[1] > 4096 || !(h[2] == 1 || h[2] == 3) || !(h[3] == 1 || h[3] == 2) || h[4] > 1)
-      return fail("bad convolution header (cin/cout in 1..4096, k in {1,3}, stride in {1,2}, act in {0,1})");
-    c.cin = (int)h[0]; c.cout = (int)h[1]; c.k = (int)h[2]; c.stride = (int)h[3]; c.act = (int)h[4];
-    const long long nw = (long long)c.cout * c.cin * c.k * c.k, need = (nw + c.cout) * 4;
+    uint32_t h[6] = {0, 0, 0, 0, 0, 1};
+    const size_t nh = v2 ? 6 : 5;
+    if (left < (long long)nh * 4 || fread(h, 4, nh, f) != nh) return fail("truncated weight file");
+    left -= (long long)nh * 4;
+    if (h[0] < 1 || h[0] > 4096 || h[1] < 1 || h[1] > 4096 || !(h[2] == 1 || h[2] == 3) || !(h[3] == 1 || h[3] == 2) || h[4] > 1 ||
+        !(h[5] == 1 || (h[5] == h[0] && h[0] == h[1])))
+      return fail("bad convolution header (cin/cout in 1..4096, k in {1,3}, stride in {1,2}, act in {0,1}, groups 1 or depthwise)");
+    c.cin = (int)h[0]; c.cout = (int)h[1]; c.k = (int)h[2]; c.stride = (int)h[3]; c.act = (int)h[4]; c.groups = (int)h[5];
+    const long long nw = (long long)c.cout * (c.cin / c.groups) * c.k * c.k, need = (nw + c.cout) * 4;
     if (need > left) return fail("truncated weight file");
     c.w.resize((size_t)nw);
     c.b.resize((size_t)c.cout);
@@ -110,9 +122,34 @@ bool read_weights(const char *path, int &nc, std::vector<FileConv> &out) {
 
 // The convolutions the engine's layer program expects, in file order (irmv_detection_b200/weights.py
 // conv_specs; ultralytics yolov8.yaml scale n, nc = 14, optional Pose branch kpt_shape [4, 2]).
-struct Spec { int cin, cout, k, stride, act; };
-std::vector<Spec> expected_specs(bool pose) {
+struct Spec { int cin, cout, k, stride, act, groups = 1; };
+struct ShuffleStage { int cin, cout, units; };
+// the four stride-2 stages of the ShuffleNetV2-style backbone (irmv_detection_b200/weights.py shuffle_stage_plan)
+const ShuffleStage kShuffleStages[4] = {{16, 32, 0}, {32, 64, 1}, {64, 128, 3}, {128, 256, 1}};
+
+std::vector<Spec> expected_specs(bool pose, int arch = kArchYolov8n) {
   std::vector<Spec> s;
+  if (arch == kArchShuffleKpt) {
+    // weights.py shuffle_conv_specs: stem, per stage a down unit {b1.dw, b1.pw, b2.pw1, b2.dw, b2.pw2} and
+    // basic units {pw1, dw, pw2}, then everything of YOLOv8n-pose from m9.cv1 on
+    s.push_back({3, 16, 3, 2, 1});
+    for (const ShuffleStage &st : kShuffleStages) {
+      const int h = st.cout / 2;
+      s.push_back({st.cin, st.cin, 3, 2, 0, st.cin});
+      s.push_back({st.cin, h, 1, 1, 1});
+      s.push_back({st.cin, h, 1, 1, 1});
+      s.push_back({h, h, 3, 2, 0, h});
+      s.push_back({h, h, 1, 1, 1});
+      for (int u = 0; u < st.units; ++u) {
+        s.push_back({h, h, 1, 1, 1});
+        s.push_back({h, h, 3, 1, 0, h});
+        s.push_back({h, h, 1, 1, 1});
+      }
+    }
+    const std::vector<Spec> y = expected_specs(true, kArchYolov8n);
+    s.insert(s.end(), y.begin() + 25, y.end());
+    return s;
+  }
   auto c2f = [&](int c1, int c2, int n) {
     const int c = c2 / 2;
     s.push_back({c1, 2 * c, 1, 1, 1});
@@ -146,15 +183,15 @@ std::vector<Spec> expected_specs(bool pose) {
   return s;
 }
 
-bool check_specs(const std::vector<FileConv> &fc, bool pose) {
-  const std::vector<Spec> want = expected_specs(pose);
-  if (fc.size() != want.size()) { set_error("weight file is not YOLOv8n nc=14"); return false; }
+bool check_specs(const std::vector<FileConv> &fc, bool pose, int arch) {
+  const std::vector<Spec> want = expected_specs(pose, arch);
+  if (fc.size() != want.size()) { set_error("weight file does not hold the convolutions of its architecture"); return false; }
   for (size_t i = 0; i < fc.size(); ++i) {
     const FileConv &c = fc[i];
     const Spec &w = want[i];
-    if (c.cin != w.cin || c.cout != w.cout || c.k != w.k || c.stride != w.stride || c.act != w.act) {
+    if (c.cin != w.cin || c.cout != w.cout || c.k != w.k || c.stride != w.stride || c.act != w.act || c.groups != w.groups) {
       char buf[200];
-      snprintf(buf, sizeof buf, "weight file: convolution %zu is %d->%d k%d s%d act%d, the YOLOv8n nc=14 program needs %d->%d k%d s%d act%d",
+      snprintf(buf, sizeof buf, "weight file: convolution %zu is %d->%d k%d s%d act%d, the layer program needs %d->%d k%d s%d act%d",
                i, c.cin, c.cout, c.k, c.stride, c.act, w.cin, w.cout, w.k, w.stride, w.act);
       set_error(buf);
       return false;
@@ -227,6 +264,45 @@ HostConv make_conv(const std::vector<const FileConv *> &parts, int cin_pad,
   return h;
 }
 
+// The ShuffleNetV2 units never move channels: a stage lives in one buffer, a unit rewrites every second
+// run of its planes in place, and channel split / concat / shuffle become a logical -> physical channel
+// map that is folded into the weights of whoever reads or writes the buffer.
+// in_map[k] = logical input channel held by physical input channel k; out_map[n] likewise for outputs.
+FileConv permuted(const FileConv &f, const std::vector<int> &in_map, const std::vector<int> &out_map) {
+  FileConv r = f;
+  const int kk = f.k * f.k;
+  for (int n = 0; n < f.cout; ++n) {
+    const int ln = out_map.empty() ? n : out_map[n];
+    r.b[n] = f.b[ln];
+    for (int c = 0; c < f.cin; ++c) {
+      const int lc = in_map.empty() ? c : in_map[c];
+      for (int t = 0; t < kk; ++t) r.w[((size_t)n * f.cin + c) * kk + t] = f.w[((size_t)ln * f.cin + lc) * kk + t];
+    }
+  }
+  return r;
+}
+
+struct HostDw {              // depthwise 3x3: [planes][9 taps][8] FP16 + [planes][8] FP32 bias, physical channel order
+  int c = 0, stride = 1;
+  std::vector<__half> w;
+  std::vector<float> b;
+  __half *d_w = nullptr;
+  float *d_b = nullptr;
+};
+
+HostDw make_dw(const FileConv &f, const std::vector<int> &map) {   // map[physical channel] = logical channel
+  HostDw h;
+  h.c = f.cout; h.stride = f.stride;
+  h.w.assign((size_t)f.cout * 9, __float2half(0.f));
+  h.b.assign(f.cout, 0.f);
+  for (int pc = 0; pc < f.cout; ++pc) {
+    const int lc = map.empty() ? pc : map[pc];
+    h.b[pc] = f.b[lc];
+    for (int t = 0; t < 9; ++t) h.w[((size_t)(pc / 8) * 9 + t) * 8 + pc % 8] = __float2half(f.w[(size_t)lc * 9 + t]);
+  }
+  return h;
+}
+
 bool upload(HostConv &h) {
   auto up = [](void **d, const void *src, size_t bytes) {
     if (!cuda_ok(dev_malloc(d, bytes), "dev_malloc(weights)", __FILE__, __LINE__)) return false;
@@ -246,10 +322,12 @@ struct Tensor {            // channel-blocked planar PR layout (common.cuh)
   __half *pp = nullptr;    // parity-split twin (4 * C/8 planes of (H/2) x (W/2) rasters), or null
   long long pp_stride = 0;
   bool parity_only = false;  // the producer writes only the twin (every consumer reads the twin)
+  std::vector<int> cmap;     // logical -> physical channel (ShuffleNetV2 stage buffers); empty = identity
 };
 
 struct Op {
-  enum Kind { CONV, POOL } kind = CONV;
+  enum Kind { CONV, POOL, DW } kind = CONV;
+  DwParams dw{};
   ConvParams cp{};
   bool raster = false;       // raster (halo-tile) kernel, else the per-tap gather kernel
   __half *pool_buf = nullptr;
@@ -385,6 +463,11 @@ struct irmv_engine {
   int S = 1, L = 1;
   size_t frame_bytes = 0;
   std::vector<std::unique_ptr<HostConv>> convs;
+  int arch = kArchYolov8n;
+  std::vector<std::unique_ptr<HostDw>> dws;       // depthwise convs of the ShuffleNetV2 backbone, execution order
+  struct ShuffleUnit { int first_plane, runs; };  // planes a basic unit rewrites in place (ConvSeg::runs)
+  std::vector<std::vector<ShuffleUnit>> sh_units; // per stage
+  std::vector<std::vector<int>> sh_map;           // per stage: logical -> physical channel of the stage output
   std::vector<Lane> lanes;
   cudaStream_t main_stream = nullptr;
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
@@ -429,6 +512,7 @@ struct irmv_engine {
   std::vector<uint8_t *> rot_host;
   std::vector<char> rot_valid;
   std::vector<irmv_bbox> parse_tmp;        // detect(): max_det boxes, sized once
+  unsigned long long h2d_bytes = 0, d2h_bytes = 0;   // bytes of every host<->device copy queued so far
 };
 
 namespace {
@@ -574,6 +658,7 @@ void fuse_tails(irmv_engine *e, Lane &ln) {
     ConvParams mp = m.cp;
     if (tp.k != 1 || tp.stride != 1 || tp.nseg != 1 || tp.res || tp.in_parity || tp.seg[0].up || tp.tail_w) continue;
     if (mp.out2 || mp.tail_w || !mp.out) continue;
+    if (tp.seg[0].runs || tp.out_runs || mp.seg[0].runs || mp.out_runs) continue;   // ShuffleNetV2 in-place units
     // the tail reads [ext channels | this conv's output]: either exactly the output (ext = 0) or a
     // concat whose LAST chunk it is (C2f.cv2 right after the last bottleneck conv)
     const int ext = tp.seg[0].c - mp.cout;
@@ -586,6 +671,7 @@ void fuse_tails(irmv_engine *e, Lane &ln) {
       if (j == i || j == i + 1) continue;
       const Op &q = ln.ops[j];
       if (q.kind == Op::POOL) { other = overlaps(o0, o1, q.pool_buf, q.pool_buf + 4LL * (q.pC / 8) * q.pStride); continue; }
+      if (q.kind == Op::DW) { other = overlaps(o0, o1, q.dw.in, q.dw.in + (long long)q.dw.planes * q.dw.in_ps); continue; }
       for (int sgi = 0; sgi < q.cp.nseg; ++sgi) {
         const ConvSeg &g = q.cp.seg[sgi];
         if (!q.cp.in_parity && overlaps(o0, o1, g.ptr, g.ptr + (long long)(g.c / 8) * g.pstride)) other = true;
@@ -624,12 +710,66 @@ bool build_lane(irmv_engine *e, Lane &ln) {
   const bool fused = e->fused_stem && e->cfg.conv_impl != IRMV_CONV_DIRECT;
   // x4 / x15 also feed stride-1 consumers, so their producers would write both layouts (m5, m16)
   const bool par2 = par && getenv("IRMV_S2_DUAL");
+  const bool shuffle = e->arch == kArchShuffleKpt;
   if (!new_tensor(ln, S, 320, 320, 16, t0, "m0")) return false;
-  if (par && fused && !add_parity_twin(ln, S, t0, true)) return false;
+  if (!shuffle && par && fused && !add_parity_twin(ln, S, t0, true)) return false;
   ln.taps["m0"] = t0;
   add_conv(e, ln, *e->convs[ci++], {{&ln.in8, 0, kInC, 0}}, 640, 640, t0, 0);
   ln.ops.back().cp.out2 = nullptr;                 // conv0 as a stand-alone op never writes the twin
   ln.stem_out = t0;
+  if (shuffle) {
+    // ShuffleNetV2-style backbone (weights.py shuffle_conv_specs).  A stage is ONE buffer X of cout channels:
+    // the down unit writes its two branches into the two halves, every basic unit rewrites the planes of
+    // its "right half" in place (engine->sh_units: runs of planes), and split / concat / shuffle are the
+    // channel map folded into the weights at load time (irmv_engine_create).
+    size_t di = 0;
+    const Tensor *prev = &ln.stem_out;
+    Tensor stage_out[4];
+    int hw = 320;
+    auto add_dw = [&](const HostDw &d, const Tensor &in, int in_plane0, int H, const Tensor &out) {
+      Op op;
+      op.kind = Op::DW;
+      op.dw.in = in.p + (long long)in_plane0 * in.pstride; op.dw.in_ps = in.pstride;
+      op.dw.out = out.p; op.dw.out_ps = out.pstride;
+      op.dw.w = d.d_w; op.dw.bias = d.d_b;
+      op.dw.planes = d.c / 8; op.dw.B = e->S; op.dw.H = H; op.dw.W = H; op.dw.stride = d.stride; op.dw.rev = 0;
+      ln.ops.push_back(op);
+    };
+    for (int sgi = 0; sgi < 4; ++sgi) {
+      const ShuffleStage &st = kShuffleStages[sgi];
+      const int h = st.cout / 2, oh = hw / 2;
+      Tensor X, Ta, Tb, Tc, T1, T2;
+      char nm[8];
+      snprintf(nm, sizeof nm, "d%d", sgi + 1);
+      if (!new_tensor(ln, S, oh, oh, st.cout, X) || !new_tensor(ln, S, oh, oh, st.cin, Ta) ||
+          !new_tensor(ln, S, hw, hw, h, Tb) || !new_tensor(ln, S, oh, oh, h, Tc))
+        return false;
+      X.cmap = e->sh_map[sgi];
+      ln.taps[nm] = X;
+      add_dw(*e->dws[di++], *prev, 0, hw, Ta);                                              // b1.dw  (stride 2)
+      add_conv(e, ln, *e->convs[ci++], {{&Ta, 0, st.cin, 0}}, oh, oh, X, 0);                // b1.pw  -> X[0, h)
+      add_conv(e, ln, *e->convs[ci++], {{prev, 0, st.cin, 0}}, hw, hw, Tb, 0);              // b2.pw1
+      add_dw(*e->dws[di++], Tb, 0, hw, Tc);                                                 // b2.dw  (stride 2)
+      add_conv(e, ln, *e->convs[ci++], {{&Tc, 0, h, 0}}, oh, oh, X, h);                     // b2.pw2 -> X[h, 2h)
+      if (st.units && (!new_tensor(ln, S, oh, oh, h, T1) || !new_tensor(ln, S, oh, oh, h, T2))) return false;
+      for (int u = 0; u < st.units; ++u) {
+        const irmv_engine::ShuffleUnit &su = e->sh_units[sgi][u];
+        add_conv(e, ln, *e->convs[ci++], {{&X, su.first_plane * 8, h, 0}}, oh, oh, T1, 0);  // pw1: the unit's planes -> T1
+        ln.ops.back().cp.seg[0].runs = su.runs; ln.ops.back().cp.seg[1].runs = su.runs;
+        add_dw(*e->dws[di++], T1, 0, oh, T2);                                               // dw
+        add_conv(e, ln, *e->convs[ci++], {{&T2, 0, h, 0}}, oh, oh, X, su.first_plane * 8);  // pw2: T2 -> the same planes
+        ln.ops.back().cp.out_runs = su.runs;
+      }
+      stage_out[sgi] = X;
+      ln.taps[nm] = X;
+      prev = &stage_out[sgi];
+      hw = oh;
+    }
+    for (size_t k = 1; k < ln.ops.size(); ++k)
+      if (ln.ops[k].kind == Op::CONV && !ln.ops[k].raster) { set_error("internal: a ShuffleNetV2 1x1 conv does not fit the raster kernel"); return false; }
+    if (di != e->dws.size()) { set_error("internal: depthwise conv count mismatch"); return false; }
+    x4 = stage_out[1]; x6 = stage_out[2]; x8 = stage_out[3];
+  } else {
   if (!new_tensor(ln, S, 160, 160, 32, t1, "m1")) return false;
   add_conv(e, ln, *e->convs[ci++], {{&t0, 0, 16, 0}}, 320, 320, t1, 0);
   if (!add_c2f(e, ln, ci, {{&t1, 0, 32, 0}}, 160, 160, 32, 1, true, x2, "m2", par ? 1 : 0)) return false;
@@ -642,6 +782,7 @@ bool build_lane(irmv_engine *e, Lane &ln) {
   if (!new_tensor(ln, S, 20, 20, 256, t7, "m7")) return false;
   add_conv(e, ln, *e->convs[ci++], {{&x6, 0, 128, 0}}, 40, 40, t7, 0);
   if (!add_c2f(e, ln, ci, {{&t7, 0, 256, 0}}, 20, 20, 256, 1, true, x8, "m8")) return false;
+  }
   // SPPF: cv1 -> [pool x3 into the next slices] -> cv2
   if (!new_tensor(ln, S, 20, 20, 512, sp) || !new_tensor(ln, S, 20, 20, 256, x9, "m9")) return false;
   add_conv(e, ln, *e->convs[ci++], {{&x8, 0, 256, 0}}, 20, 20, sp, 0);
@@ -745,16 +886,27 @@ int issue_replay(irmv_engine *e, Lane &ln, int n, cudaStream_t st, int *launches
   cnt += 1 + (ln.rotated ? 1 : 0);
   if (mark(1)) return 1;
   op_mark();
+  // Consecutive kernels walk their tiles in opposite directions (ConvParams::rev_tiles): a layer then
+  // starts with the end of the tensor its producer has just finished writing, which is what the L2 still holds.
+  static const bool pingpong = !getenv("IRMV_NO_PINGPONG");
+  int seq = 0;
   bool first = true;
   for (auto &op : ln.ops) {
     if (first && fused) { first = false; continue; }        // conv0 ran inside the stem kernel
     first = false;
+    ++seq;
     if (op.kind == Op::CONV) {
       ConvParams p = op.cp;
       p.B = n;
+      p.rev_tiles = pingpong ? (seq & 1) : 0;
       if (e->cfg.conv_impl == IRMV_CONV_DIRECT) IRMV_CUDA(launch_conv_direct(p, st));
       else if (op.raster) IRMV_CUDA(launch_conv_raster(p, e->num_sms, st));
       else IRMV_CUDA(launch_conv_tc(p, e->num_sms, st));
+    } else if (op.kind == Op::DW) {
+      DwParams d = op.dw;
+      d.B = n;
+      d.rev = pingpong ? (seq & 1) : 0;
+      IRMV_CUDA(launch_dwconv3x3(d, st));
     } else {
       IRMV_CUDA(launch_sppf_pool(op.pool_buf, n, op.pH, op.pW, op.pStride, op.pC, st));
     }
@@ -765,7 +917,7 @@ int issue_replay(irmv_engine *e, Lane &ln, int n, cudaStream_t st, int *launches
       if (ce != cudaSuccess) {
         char buf[256];
         snprintf(buf, sizeof buf, "op %d (%s k=%d s=%d cin=%d cout=%d H=%d) failed: %s", cnt - 2,
-                 op.kind == Op::POOL ? "pool" : (op.raster ? "raster" : "gather"), op.cp.k, op.cp.stride, op.cp.cin,
+                 op.kind == Op::POOL ? "pool" : (op.kind == Op::DW ? "dw" : (op.raster ? "raster" : "gather")), op.cp.k, op.cp.stride, op.cp.cin,
                  op.cp.cout, op.cp.H, cudaGetErrorString(ce));
         set_error(buf);
         return 1;
@@ -888,12 +1040,14 @@ int enqueue(irmv_engine *e, const uint8_t *frames_dev, int n, const uint8_t *fra
       IRMV_CUDA(cudaMemcpyAsync(const_cast<uint8_t *>(frames_dev) + (size_t)f0 * e->frame_bytes,
                                 frames_host + (size_t)f0 * e->frame_bytes, (size_t)nf * e->frame_bytes,
                                 cudaMemcpyHostToDevice, e->copy_stream));
+      e->h2d_bytes += (size_t)nf * e->frame_bytes;
       IRMV_CUDA(cudaEventRecord(rs.h2d[c], e->copy_stream));
       IRMV_CUDA(cudaStreamWaitEvent(ln.stream, rs.h2d[c], 0));
     } else if (frames_host) {
       IRMV_CUDA(cudaMemcpyAsync(const_cast<uint8_t *>(frames_dev) + (size_t)f0 * e->frame_bytes,
                                 frames_host + (size_t)f0 * e->frame_bytes, (size_t)nf * e->frame_bytes,
                                 cudaMemcpyHostToDevice, ln.stream));
+      e->h2d_bytes += (size_t)nf * e->frame_bytes;
     }
     set_src_kernel<<<1, 1, 0, ln.stream>>>(ln.src_word, frames_dev + (size_t)f0 * e->frame_bytes);
     IRMV_CUDA(cudaGetLastError());
@@ -903,31 +1057,33 @@ int enqueue(irmv_engine *e, const uint8_t *frames_dev, int n, const uint8_t *fra
     uint8_t *h = rs.res_host;
     const int md = e->cfg.max_det;
     const size_t B = e->cfg.max_batch;
-    IRMV_CUDA(cudaMemcpyAsync(h + (size_t)f0 * 4, ln.det.num(), (size_t)nf * 4, cudaMemcpyDeviceToHost, ln.stream));
+    auto d2h = [&](size_t host_off, const void *src, size_t bytes) -> cudaError_t {
+      e->d2h_bytes += bytes;
+      return cudaMemcpyAsync(h + host_off, src, bytes, cudaMemcpyDeviceToHost, ln.stream);
+    };
+    IRMV_CUDA(d2h((size_t)f0 * 4, ln.det.num(), (size_t)nf * 4));
     size_t o = B * 4;
-    IRMV_CUDA(cudaMemcpyAsync(h + o + (size_t)f0 * md * 16, ln.det.boxes(), (size_t)nf * md * 16, cudaMemcpyDeviceToHost, ln.stream));
+    IRMV_CUDA(d2h(o + (size_t)f0 * md * 16, ln.det.boxes(), (size_t)nf * md * 16));
     o += B * md * 16;
-    IRMV_CUDA(cudaMemcpyAsync(h + o + (size_t)f0 * md * 4, ln.det.scores(), (size_t)nf * md * 4, cudaMemcpyDeviceToHost, ln.stream));
+    IRMV_CUDA(d2h(o + (size_t)f0 * md * 4, ln.det.scores(), (size_t)nf * md * 4));
     o += B * md * 4;
-    IRMV_CUDA(cudaMemcpyAsync(h + o + (size_t)f0 * md * 4, ln.det.classes(), (size_t)nf * md * 4, cudaMemcpyDeviceToHost, ln.stream));
+    IRMV_CUDA(d2h(o + (size_t)f0 * md * 4, ln.det.classes(), (size_t)nf * md * 4));
     o += B * md * 4;
-    IRMV_CUDA(cudaMemcpyAsync(h + o + (size_t)f0 * md * 4, ln.det.index(), (size_t)nf * md * 4, cudaMemcpyDeviceToHost, ln.stream));
+    IRMV_CUDA(d2h(o + (size_t)f0 * md * 4, ln.det.index(), (size_t)nf * md * 4));
     o += B * md * 4;
     if (e->pnp_on) {
-      IRMV_CUDA(cudaMemcpyAsync(h + o + (size_t)f0 * md * 24, ln.pnp_rvec, (size_t)nf * md * 24, cudaMemcpyDeviceToHost, ln.stream));
+      IRMV_CUDA(d2h(o + (size_t)f0 * md * 24, ln.pnp_rvec, (size_t)nf * md * 24));
       o += B * md * 24;
-      IRMV_CUDA(cudaMemcpyAsync(h + o + (size_t)f0 * md * 24, ln.pnp_tvec, (size_t)nf * md * 24, cudaMemcpyDeviceToHost, ln.stream));
+      IRMV_CUDA(d2h(o + (size_t)f0 * md * 24, ln.pnp_tvec, (size_t)nf * md * 24));
       o += B * md * 24;
-      IRMV_CUDA(cudaMemcpyAsync(h + o + (size_t)f0 * md, ln.pnp_ok, (size_t)nf * md, cudaMemcpyDeviceToHost, ln.stream));
-      IRMV_CUDA(cudaMemcpyAsync(h + quat_offset(B, md) + (size_t)f0 * md * 32, ln.pnp_quat, (size_t)nf * md * 32, cudaMemcpyDeviceToHost, ln.stream));
-      IRMV_CUDA(cudaMemcpyAsync(h + dist_offset(B, md) + (size_t)f0 * md * 4, ln.pnp_dist, (size_t)nf * md * 4, cudaMemcpyDeviceToHost, ln.stream));
+      IRMV_CUDA(d2h(o + (size_t)f0 * md, ln.pnp_ok, (size_t)nf * md));
+      IRMV_CUDA(d2h(quat_offset(B, md) + (size_t)f0 * md * 32, ln.pnp_quat, (size_t)nf * md * 32));
+      IRMV_CUDA(d2h(dist_offset(B, md) + (size_t)f0 * md * 4, ln.pnp_dist, (size_t)nf * md * 4));
     }
     if (e->armors_on)
-      IRMV_CUDA(cudaMemcpyAsync(h + armors_offset(B, md) + (size_t)f0 * md * sizeof(ArmorOut), ln.armors,
-                                (size_t)nf * md * sizeof(ArmorOut), cudaMemcpyDeviceToHost, ln.stream));
+      IRMV_CUDA(d2h(armors_offset(B, md) + (size_t)f0 * md * sizeof(ArmorOut), ln.armors, (size_t)nf * md * sizeof(ArmorOut)));
     if (e->pose)
-      IRMV_CUDA(cudaMemcpyAsync(h + kpts_offset(B, md) + (size_t)f0 * md * 32, ln.kpts, (size_t)nf * md * 32,
-                                cudaMemcpyDeviceToHost, ln.stream));
+      IRMV_CUDA(d2h(kpts_offset(B, md) + (size_t)f0 * md * 32, ln.kpts, (size_t)nf * md * 32));
   }
   for (int l = 0; l < used; ++l) {
     IRMV_CUDA(cudaEventRecord(e->lanes[l].done, e->lanes[l].stream));
@@ -986,6 +1142,7 @@ int refresh_rotated(irmv_engine *e, int slot) {
   IRMV_CUDA(launch_rotate(pp, e->main_stream));
   IRMV_CUDA(cudaMemcpyAsync(e->rot_host[slot], e->rot_dev, (size_t)e->cfg.src_width * e->cfg.src_height * 3,
                             cudaMemcpyDeviceToHost, e->main_stream));
+  e->d2h_bytes += (size_t)e->cfg.src_width * e->cfg.src_height * 3;
   e->rot_valid[slot] = 1;
   return 0;
 }
@@ -1026,28 +1183,99 @@ int irmv_engine_create(const char *weights_path, const irmv_engine_config *cfg, 
   e->cfg = *cfg;
   e->num_sms = prop.multiProcessorCount;
   std::vector<FileConv> fc;
-  if (!read_weights(weights_path, e->nc, fc)) return 4;
-  if ((fc.size() != 63 && fc.size() != 72) || e->nc != IRMV_NUM_CLASSES) { set_error("weight file is not YOLOv8n nc=14"); return 4; }
-  e->pose = fc.size() == 72;                                   // + keypoint branch (kpt_shape [4, 2])
-  if (!check_specs(fc, e->pose)) return 4;                     // make_conv / build_lane index by the expected shapes
+  if (!read_weights(weights_path, e->nc, e->arch, fc)) return 4;
+  if (e->nc != IRMV_NUM_CLASSES) { set_error("weight file is not an nc=14 detector"); return 4; }
+  if (e->arch == kArchYolov8n && fc.size() != 63 && fc.size() != 72) { set_error("weight file is not YOLOv8n nc=14"); return 4; }
+  e->pose = e->arch == kArchShuffleKpt || fc.size() == 72;    // + keypoint branch (kpt_shape [4, 2])
+  if (!check_specs(fc, e->pose, e->arch)) return 4;            // make_conv / build_lane index by the expected shapes
+  if (e->arch == kArchShuffleKpt && (cfg->conv_impl == IRMV_CONV_DIRECT || getenv("IRMV_NO_RASTER"))) {
+    set_error("the ShuffleNetV2 variant runs on the tcgen05 raster kernel only"); return 2;
+  }
   // 63 reference convs -> 60 GEMMs (Detect box.0|cls.0 merged per scale)
   auto single = [&](size_t i, int cin_pad, std::vector<int> seg) {
     e->convs.emplace_back(new HostConv(make_conv({&fc[i]}, cin_pad, seg)));
   };
+  auto single_p = [&](const FileConv &f, int cin_pad, std::vector<int> seg) {
+    e->convs.emplace_back(new HostConv(make_conv({&f}, cin_pad, seg)));
+  };
   size_t i = 0;
   single(i++, kInC, {kInC});                                   // m0: 3 -> 8 input channels
-  for (; i < 45; ++i) {
-    int cin = fc[i].cin;
-    std::vector<int> seg{cin};
-    // concat-on-read layers: first conv of m12, m15, m18, m21 (cv1 over two sources)
-    if (i == 27) seg = {256, 128};
-    if (i == 31) seg = {128, 64};
-    if (i == 36) seg = {64, 128};
-    if (i == 41) seg = {128, 256};
-    single(i, cin, seg);
+  size_t neck0 = 27;                                           // first neck conv (m12.cv1) in file order
+  std::vector<int> inv4, inv6, inv8;                           // physical -> logical channel of x4 / x6 / x8 (empty: identity)
+  if (e->arch == kArchYolov8n) {
+    for (; i < 25; ++i) single(i, fc[i].cin, {fc[i].cin});     // m1 .. m8.cv2
+  } else {
+    // ShuffleNetV2 backbone: build every conv with the channel maps folded in (see permuted())
+    neck0 = 38;
+    std::vector<int> Lp;                                       // logical -> physical of the stage input (stem: identity)
+    for (int c = 0; c < 16; ++c) Lp.push_back(c);
+    auto inverse = [](const std::vector<int> &L) { std::vector<int> r(L.size()); for (size_t j = 0; j < L.size(); ++j) r[L[j]] = (int)j; return r; };
+    for (const ShuffleStage &st : kShuffleStages) {
+      const int h = st.cout / 2;
+      const std::vector<int> pinv = inverse(Lp);               // physical -> logical of the stage input
+      e->dws.emplace_back(new HostDw(make_dw(fc[i++], pinv)));                              // b1.dw on the input
+      single_p(permuted(fc[i], pinv, {}), st.cin, {st.cin}); ++i;                           // b1.pw  -> X[0, h)
+      single_p(permuted(fc[i], pinv, {}), st.cin, {st.cin}); ++i;                           // b2.pw1 -> Tb
+      e->dws.emplace_back(new HostDw(make_dw(fc[i++], {})));                                // b2.dw
+      single(i, h, {h}); ++i;                                                               // b2.pw2 -> X[h, 2h)
+      std::vector<int> L(2 * h);                               // shuffle of concat(b1, b2)
+      for (int j = 0; j < h; ++j) { L[2 * j] = j; L[2 * j + 1] = h + j; }
+      std::vector<irmv_engine::ShuffleUnit> units;
+      for (int u = 0; u < st.units; ++u) {
+        // x2 = logical [h, 2h): the physical planes it occupies, ascending
+        std::vector<int> phys(L.begin() + h, L.end());
+        std::sort(phys.begin(), phys.end());
+        std::vector<int> planes;
+        for (int j = 0; j < h; j += 8) {
+          for (int q = 1; q < 8; ++q)
+            if (phys[j + q] != phys[j] + q || phys[j] % 8) { set_error("internal: shuffle unit is not plane aligned"); return 6; }
+          planes.push_back(phys[j] / 8);
+        }
+        int run = 1;
+        while (run < (int)planes.size() && planes[run] == planes[0] + run) ++run;
+        int runs = 0;
+        if (run < (int)planes.size()) { runs = 1; while ((1 << (runs - 1)) < run) ++runs; }
+        for (size_t q = 0; q < planes.size(); ++q)
+          if (planes[q] != planes[0] + run_plane((int)q, runs)) { set_error("internal: shuffle unit planes are not regular runs"); return 6; }
+        units.push_back({planes[0], runs});
+        const std::vector<int> Linv = inverse(L);
+        std::vector<int> m(h);                                 // physical position in the slice -> logical index inside x2 / b
+        for (int j = 0; j < h; ++j) m[j] = Linv[planes[j / 8] * 8 + j % 8] - h;
+        single_p(permuted(fc[i], m, {}), h, {h}); ++i;                                      // pw1: x2 -> T1
+        e->dws.emplace_back(new HostDw(make_dw(fc[i++], {})));                              // dw:  T1 -> T2
+        single_p(permuted(fc[i], {}, m), h, {h}); ++i;                                      // pw2: T2 -> x2's planes
+        std::vector<int> Ln(2 * h);                            // b[j] sits where x2[j] was; shuffle(concat(x1, b))
+        for (int j = 0; j < h; ++j) { Ln[2 * j] = L[j]; Ln[2 * j + 1] = L[h + j]; }
+        L = Ln;
+      }
+      e->sh_units.push_back(units);
+      e->sh_map.push_back(L);
+      Lp = L;
+    }
+    inv4 = inverse(e->sh_map[1]); inv6 = inverse(e->sh_map[2]); inv8 = inverse(e->sh_map[3]);
   }
-  for (int s = 0; s < 3; ++s) {
-    size_t b = 45 + (size_t)s * 6;
+  if (i != neck0 - 2) { set_error("internal: backbone conv count mismatch"); return 6; }
+  // SPPF + neck (file order from m9.cv1 on is the same for both architectures)
+  {
+    const size_t b9 = neck0 - 2;
+    if (inv8.empty()) single(b9, fc[b9].cin, {fc[b9].cin}); else single_p(permuted(fc[b9], inv8, {}), fc[b9].cin, {fc[b9].cin});
+    single(b9 + 1, fc[b9 + 1].cin, {fc[b9 + 1].cin});
+    for (size_t k = 0; k < 18; ++k) {
+      const size_t fi = neck0 + k;
+      int cin = fc[fi].cin;
+      std::vector<int> seg{cin};
+      std::vector<int> in_map;
+      // concat-on-read layers: first conv of m12, m15, m18, m21 (cv1 over two sources)
+      if (k == 0) { seg = {256, 128}; if (!inv6.empty()) { for (int c = 0; c < 256; ++c) in_map.push_back(c); for (int c : inv6) in_map.push_back(256 + c); } }
+      if (k == 4) { seg = {128, 64}; if (!inv4.empty()) { for (int c = 0; c < 128; ++c) in_map.push_back(c); for (int c : inv4) in_map.push_back(128 + c); } }
+      if (k == 9) seg = {64, 128};
+      if (k == 14) seg = {128, 256};
+      if (in_map.empty()) single(fi, cin, seg); else single_p(permuted(fc[fi], in_map, {}), cin, seg);
+    }
+  }
+  const size_t head0 = neck0 + 18;
+  for (int sc = 0; sc < 3; ++sc) {
+    size_t b = head0 + (size_t)sc * 6;
     e->convs.emplace_back(new HostConv(make_conv({&fc[b + 0], &fc[b + 3]}, fc[b].cin, {fc[b].cin})));
     single(b + 1, 64, {64});
     single(b + 2, 64, {64});
@@ -1055,12 +1283,18 @@ int irmv_engine_create(const char *weights_path, const irmv_engine_config *cfg, 
     single(b + 5, 64, {64});
   }
   if (e->pose)
-    for (int s = 0; s < 3; ++s) {
-      size_t b = 63 + (size_t)s * 3;
+    for (int sc = 0; sc < 3; ++sc) {
+      size_t b = head0 + 18 + (size_t)sc * 3;
       single(b + 0, fc[b].cin, {fc[b].cin});
       single(b + 1, 16, {16});
       single(b + 2, 16, {16});
     }
+  for (auto &d : e->dws) {
+    IRMV_CUDA(dev_malloc((void **)&d->d_w, d->w.size() * 2));
+    IRMV_CUDA(dev_malloc((void **)&d->d_b, d->b.size() * 4));
+    IRMV_CUDA(cudaMemcpy(d->d_w, d->w.data(), d->w.size() * 2, cudaMemcpyHostToDevice));
+    IRMV_CUDA(cudaMemcpy(d->d_b, d->b.data(), d->b.size() * 4, cudaMemcpyHostToDevice));
+  }
   for (auto &c : e->convs) if (!upload(*c)) return 5;
   {
     // stem weights: conv0 as FP32 [16][9 taps][3] + bias
@@ -1137,6 +1371,7 @@ void irmv_engine_destroy(irmv_engine *e) {
   for (auto &c : e->convs) {
     cudaFree(c->d_plain); cudaFree(c->d_tiled); cudaFree(c->d_raster); cudaFree(c->d_bias);
   }
+  for (auto &d : e->dws) { cudaFree(d->d_w); cudaFree(d->d_b); }
 
   for (auto s : e->slots_host) cudaFreeHost(s);
   for (auto s : e->rot_host) if (s) cudaFreeHost(s);
@@ -1170,6 +1405,7 @@ int irmv_engine_detect(irmv_engine *e, int slot, irmv_bbox *out, int cap, int *n
   auto t0 = std::chrono::high_resolution_clock::now();
   IRMV_CUDA(cudaSetDevice(e->cfg.device));
   IRMV_CUDA(cudaMemcpyAsync(e->slot_dev, e->slots_host[slot], e->frame_bytes, cudaMemcpyHostToDevice, e->main_stream));
+  e->h2d_bytes += e->frame_bytes;
   if (int rc = enqueue(e, e->slot_dev, 1)) return rc;
   if (e->rotated_on) { if (int rc = refresh_rotated(e, slot)) return rc; }
   else if (!e->rot_valid.empty()) e->rot_valid[slot] = 0;
@@ -1294,6 +1530,15 @@ int irmv_engine_collect(irmv_engine *e, int ticket, irmv_bbox *out, int *counts,
   return 0;
 }
 
+// Bytes of every host->device / device->host copy the engine has queued since it was created (bench.py
+// reports the per-step difference as e2e.h2d_bytes_per_step / d2h_bytes_per_step).
+int irmv_engine_copy_bytes(irmv_engine *e, unsigned long long *h2d, unsigned long long *d2h) {
+  if (!e) return 1;
+  if (h2d) *h2d = e->h2d_bytes;
+  if (d2h) *d2h = e->d2h_bytes;
+  return 0;
+}
+
 double irmv_engine_profile_ms(irmv_engine *e) { return e ? e->profile_ms : 0.0; }
 double irmv_engine_last_device_ms(irmv_engine *e) { return e ? e->device_ms : 0.0; }
 void *irmv_engine_stream(irmv_engine *e) { return e ? (void *)e->main_stream : nullptr; }
@@ -1369,6 +1614,13 @@ int irmv_engine_read_tensor(irmv_engine *e, const char *name, void *dst, int64_t
             for (int x = 0; x < t.W; ++x)
               memcpy(o + ((((size_t)b * t.H + y) * t.W + x) * t.C + pl * 8),
                      tmp.data() + (size_t)pr_index(b, y, x, t.H, t.W) * 8, 16);
+      }
+      if (!t.cmap.empty()) {             // ShuffleNetV2 stage buffer: physical channel order -> logical
+        std::vector<uint16_t> px(t.C);
+        for (size_t q = 0; q < (size_t)nb * t.H * t.W; ++q) {
+          memcpy(px.data(), o + q * t.C, (size_t)t.C * 2);
+          for (int c = 0; c < t.C; ++c) o[q * t.C + c] = px[t.cmap[c]];
+        }
       }
       if (t.parity_only) {               // only the parity-split twin exists: planes [g][C/8] of (H/2) x (W/2)
         const size_t px2 = (size_t)pr_pixels(nb, t.H / 2, t.W / 2);
@@ -1682,6 +1934,7 @@ int irmv_engine_describe_ops(irmv_engine *e, char *buf, int cap) {
     first = false;
     char line[160];
     if (o.kind == Op::POOL) snprintf(line, sizeof line, "pool\n");
+    else if (o.kind == Op::DW) snprintf(line, sizeof line, "dw %d %d %d\n", o.dw.stride, o.dw.planes * 8, o.dw.H / o.dw.stride);
     else snprintf(line, sizeof line, "conv %d %d %d %d %d %d %d\n", o.cp.k, o.cp.stride, o.cp.cin, o.cp.cout, o.cp.OH,
                   o.raster ? 1 : 0, o.cp.tail_w ? o.cp.tail_cout : 0);
     out += line;
@@ -1706,6 +1959,7 @@ int irmv_engine_describe_plans(irmv_engine *e, int nframes, char *buf, int cap) 
     first = false;
     char line[200];
     if (o.kind == Op::POOL) { out += "pool\n"; continue; }
+    if (o.kind == Op::DW) { snprintf(line, sizeof line, "dw %d %d %d\n", o.dw.stride, o.dw.planes * 8, o.dw.H / o.dw.stride); out += line; continue; }
     ConvParams p = o.cp;
     p.B = n;
     int info[8];

@@ -46,6 +46,7 @@ struct StemBayerArgs {
   const uint8_t *src;                    // frames [..][H][1280]; used when src_indirect == null
   const uint8_t *const *src_indirect;
   int n, H, frame0;                      // frame0: first source frame of this launch
+  int rev;                               // walk frames and strips from the last to the first
   int Q, lut_n;                          // H / 640 = P / Q; entries of the lerp table: 2*Q*255 + Q + 1
   int tab_strip;                         // word offset of the per-strip tables inside tab
   const uint32_t *tab;                   // device tables built by stem_bayer2x_tables()
@@ -103,10 +104,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) stem_bayer2x_kernel(const __grid_
   __shared__ __align__(16) RowTab rowtab[NIR];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int H = a.H;
-  const int n = blockIdx.y, oy0 = blockIdx.x * OROWS;
+  // blockIdx.x walks the strips of a frame, blockIdx.y the frames: the launch order follows memory order
+  const int sidx = a.rev ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
+  const int n = a.rev ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y, oy0 = sidx * OROWS;
   const uint8_t *base = a.src_indirect ? *a.src_indirect : a.src;
   const uint8_t *frame = base + (size_t)(a.frame0 + n) * ((size_t)H * SW);
-  const uint32_t *strip = a.tab + a.tab_strip + blockIdx.x * STRIP_WORDS;
+  const uint32_t *strip = a.tab + a.tab_strip + sidx * STRIP_WORDS;
 
   // ---- source rows of the strip: virtual rows [vlo, vlo + nr), slot = v - vlo, content = row reflect101(v)
   const int vlo = (int)strip[0], nr = (int)strip[1];
@@ -390,7 +393,7 @@ std::vector<uint32_t> stem_bayer2x_tables(const float *w, const float *bias, int
 cudaError_t launch_stem_bayer2x(const PreprocessParams &p, int frame0, const uint32_t *tab, __half *out,
                                 long long out_ps, __half *out2, long long out2_ps, cudaStream_t s) {
   StemBayerArgs a{};
-  a.src = p.src; a.src_indirect = p.src_indirect; a.n = p.n; a.H = p.src_h; a.frame0 = frame0;
+  a.src = p.src; a.src_indirect = p.src_indirect; a.n = p.n; a.H = p.src_h; a.frame0 = frame0; a.rev = p.rev_order;
   const int g = gcd_i(p.src_h, kNet);
   const int P = p.src_h / g, Q = kNet / g;
   const int red_x = (p.chan_order == 3 || p.chan_order == 4) ? 1 : 0;   // BGGR, GRBG: red on odd columns

@@ -194,6 +194,12 @@ class YoloEngine:
     def last_device_ms(self) -> float:
         return float(self._lib.irmv_engine_last_device_ms(self._h))
 
+    def copy_bytes(self) -> Tuple[int, int]:
+        """(host->device, device->host) bytes of every copy the engine has queued since creation."""
+        a, b = C.c_ulonglong(0), C.c_ulonglong(0)
+        L.check(self._lib.irmv_engine_copy_bytes(self._h, C.byref(a), C.byref(b)), "irmv_engine_copy_bytes")
+        return int(a.value), int(b.value)
+
     def kernel_launches(self, n: int) -> int:
         return int(self._lib.irmv_engine_kernel_launches(self._h, n))
 
@@ -250,6 +256,8 @@ class YoloEngine:
             f = line.split()
             if f[0] == "pool":
                 ops.append({"kind": "pool"})
+            elif f[0] == "dw":
+                ops.append({"kind": "dw", "s": int(f[1]), "c": int(f[2]), "hw": int(f[3])})
             else:
                 k, s, cin, cout, hw, raster, tail = (int(v) for v in f[1:])
                 ops.append({"kind": "conv", "k": k, "s": s, "cin": cin, "cout": cout, "hw": hw, "raster": bool(raster),

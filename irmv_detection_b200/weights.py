@@ -8,8 +8,12 @@ fixed order.  Every stored value is exactly representable in FP16, so the FP32 o
 FP16 tensor-core path start from identical parameters.
 
 File layout (little endian):
-    char[4] "IRMW" | u32 version(=1) | u32 nc | u32 n_convs (63, or 72 with the keypoint branch)
-    per conv: u32 cin, cout, k, stride, act | f32 w[cout][cin][k][k] | f32 bias[cout]
+    version 1 (YOLOv8n body):
+        char[4] "IRMW" | u32 version(=1) | u32 nc | u32 n_convs (63, or 72 with the keypoint branch)
+        per conv: u32 cin, cout, k, stride, act | f32 w[cout][cin][k][k] | f32 bias[cout]
+    version 2 (other backbones; today: the ShuffleNetV2-backbone keypoint detector, arch id 1):
+        char[4] "IRMW" | u32 version(=2) | u32 nc | u32 n_convs | u32 arch
+        per conv: u32 cin, cout, k, stride, act, groups | f32 w[cout][cin/groups][k][k] | f32 bias[cout]
 """
 from __future__ import annotations
 
@@ -35,7 +39,13 @@ class ConvSpec:
     cout: int
     k: int
     stride: int
-    act: int  # 1 = SiLU (Conv-BN-SiLU folded), 0 = plain conv2d with bias (Detect heads)
+    act: int  # 1 = SiLU (Conv-BN-SiLU folded), 0 = plain conv2d with bias (Detect heads, depthwise convs)
+    groups: int = 1   # cin for a depthwise conv
+
+
+ARCH_YOLOV8N = 0
+ARCH_SHUFFLE_KPT = 1      # ShuffleNetV2-style backbone + YOLOv8n neck + Detect + Pose(kpt_shape [4, 2])
+KPT_ARCHS = ("yolov8n-pose", "shufflenetv2-pose")      # the keypoint detectors bench.py times at batch 64
 
 
 def _c2f(prefix: str, c1: int, c2: int, n: int) -> List[ConvSpec]:
@@ -91,6 +101,49 @@ def conv_specs(nc: int = NC, pose: bool = False) -> List[ConvSpec]:
     return s
 
 
+def shuffle_stage_plan():
+    """(name, cin, cout, basic units) of the four stride-2 stages of the ShuffleNetV2-style backbone."""
+    return (("d1", 16, 32, 0), ("d2", 32, 64, 1), ("d3", 64, 128, 3), ("d4", 128, 256, 1))
+
+
+def shuffle_conv_specs(nc: int = NC) -> List[ConvSpec]:
+    """Keypoint detector on a ShuffleNetV2-style backbone (BASELINE.json configs[2]; the reference names the
+    model in its benchmark table, README.md:12,16, but ships neither file nor definition, so the backbone
+    is self-defined -- SURVEY.md section 8d item 3):
+
+        stem   Conv 3x3 s2 3->16 + SiLU                                               320 x 320
+        d1     down unit 16->32                                                       160 x 160
+        d2     down unit 32->64,   1 basic unit            -> P3 (64 ch)               80 x 80
+        d3     down unit 64->128,  3 basic units           -> P4 (128 ch)              40 x 40
+        d4     down unit 128->256, 1 basic unit, SPPF(256) -> P5 (256 ch)              20 x 20
+        YOLOv8n neck (m12 .. m21), Detect, Pose(kpt_shape [4, 2]) unchanged.
+
+    Down unit (cin -> cout, ShuffleNetV2 fig. 3d): branch 1 = depthwise 3x3 s2 -> 1x1 (cin -> cout/2);
+    branch 2 = 1x1 (cin -> cout/2) -> depthwise 3x3 s2 -> 1x1; concat, channel shuffle (groups = 2).
+    Basic unit (fig. 3c): split in halves, right half through 1x1 -> depthwise 3x3 -> 1x1, concat with the
+    untouched left half, channel shuffle.  1x1 convs carry SiLU, depthwise convs only their (BN-folded)
+    bias."""
+    s: List[ConvSpec] = [ConvSpec("m0", 3, 16, 3, 2, 1)]
+    for name, cin, cout, units in shuffle_stage_plan():
+        h = cout // 2
+        s.append(ConvSpec(f"{name}.b1.dw", cin, cin, 3, 2, 0, cin))
+        s.append(ConvSpec(f"{name}.b1.pw", cin, h, 1, 1, 1))
+        s.append(ConvSpec(f"{name}.b2.pw1", cin, h, 1, 1, 1))
+        s.append(ConvSpec(f"{name}.b2.dw", h, h, 3, 2, 0, h))
+        s.append(ConvSpec(f"{name}.b2.pw2", h, h, 1, 1, 1))
+        for u in range(units):
+            s.append(ConvSpec(f"{name}.u{u}.pw1", h, h, 1, 1, 1))
+            s.append(ConvSpec(f"{name}.u{u}.dw", h, h, 3, 1, 0, h))
+            s.append(ConvSpec(f"{name}.u{u}.pw2", h, h, 1, 1, 1))
+    full = conv_specs(nc, pose=True)
+    s += full[25:]                       # m9.cv1, m9.cv2, neck, Detect, Pose
+    return s
+
+
+def specs_for(arch: int, nc: int = NC, pose: bool = False) -> List[ConvSpec]:
+    return shuffle_conv_specs(nc) if arch == ARCH_SHUFFLE_KPT else conv_specs(nc, pose)
+
+
 def total_flops(nc: int = NC) -> float:
     """2*MAC over the 63 convs at 640x640 (8.0956 GFLOP)."""
     hw = {}
@@ -141,10 +194,25 @@ INIT_GAIN = {
     ),
 }
 CLS_BIAS = -8.0
+# ShuffleNetV2-backbone keypoint detector: gains from `python -m oracle.calibrate_init 0 shuffle`
+# (box.2 gains are 0.2x the calibrated value, like the YOLOv8n table above)
+INIT_GAIN_SHUFFLE = {0: (
+    14.7, 3.07, 1.054, 1.973, 1.07, 0.7047, 2.278, 1.211,
+    2.151, 1.273, 1.262, 1.67, 1.229, 0.9991, 1.408, 0.9903,
+    1.821, 1.835, 1.009, 1.827, 1.407, 0.9733, 1.415, 1.379,
+    1.095, 1.539, 1.219, 0.9222, 1.425, 1.016, 1.465, 1.68,
+    1.016, 1.355, 1.308, 0.9648, 1.427, 0.3457, 1.533, 1.634,
+    1.541, 1.529, 1.591, 1.76, 1.968, 1.46, 1.536, 1.617,
+    1.625, 1.715, 1.554, 1.447, 1.535, 1.495, 1.485, 1.526,
+    1.648, 1.677, 0.7202, 1.593, 1.671, 1.329, 1.392, 1.437,
+    0.6148, 1.558, 1.523, 1.653, 1.681, 1.55, 0.6508, 1.74,
+    1.44, 1.711, 1.763, 2.363, 0.2423, 1.352, 1.565, 0.1022,
+    1.656, 1.404, 0.2159,
+)}
 
 
-def random_init(seed: int = 0, nc: int = NC, cls_bias: float = CLS_BIAS, pose: bool = False
-                ) -> List[Tuple[np.ndarray, np.ndarray]]:
+def random_init(seed: int = 0, nc: int = NC, cls_bias: float = CLS_BIAS, pose: bool = False,
+                arch: int = ARCH_YOLOV8N) -> List[Tuple[np.ndarray, np.ndarray]]:
     """Seeded random-init, FP16-exact, activations kept O(1) through the SiLU chain.
 
     The class-logit bias plays the role of the ultralytics prior log(5/nc/(640/s)^2): with
@@ -154,10 +222,14 @@ def random_init(seed: int = 0, nc: int = NC, cls_bias: float = CLS_BIAS, pose: b
     """
     rng = np.random.default_rng(seed)
     out = []
-    gains = INIT_GAIN.get(seed, INIT_GAIN[0])
-    for i, c in enumerate(conv_specs(nc, pose)):
-        fan_in = c.cin * c.k * c.k
-        w = rng.standard_normal((c.cout, c.cin, c.k, c.k)).astype(np.float32) / np.float32(math.sqrt(fan_in))
+    if arch == ARCH_SHUFFLE_KPT:
+        gains = INIT_GAIN_SHUFFLE.get(seed, INIT_GAIN_SHUFFLE[0])
+    else:
+        gains = INIT_GAIN.get(seed, INIT_GAIN[0])
+    for i, c in enumerate(specs_for(arch, nc, pose)):
+        cg = c.cin // c.groups
+        fan_in = cg * c.k * c.k
+        w = rng.standard_normal((c.cout, cg, c.k, c.k)).astype(np.float32) / np.float32(math.sqrt(fan_in))
         b = rng.standard_normal(c.cout).astype(np.float32) * np.float32(0.05)
         # (the keypoint branch comes after the 63 calibrated convs and draws from the stream last, so the
         # box/class network of a seed is the same with and without it; kpt.2 is kept small like box.2:
@@ -172,17 +244,32 @@ def random_init(seed: int = 0, nc: int = NC, cls_bias: float = CLS_BIAS, pose: b
     return out
 
 
-def save(path: str, tensors: List[Tuple[np.ndarray, np.ndarray]], nc: int = NC) -> None:
-    specs = conv_specs(nc, pose=len(tensors) == 72)
+def save(path: str, tensors: List[Tuple[np.ndarray, np.ndarray]], nc: int = NC, arch: int = ARCH_YOLOV8N) -> None:
+    specs = specs_for(arch, nc, pose=len(tensors) == 72)
     assert len(specs) == len(tensors)
     with open(path, "wb") as f:
         f.write(MAGIC)
-        f.write(struct.pack("<III", VERSION, nc, len(specs)))
+        if arch == ARCH_YOLOV8N:
+            f.write(struct.pack("<III", VERSION, nc, len(specs)))
+        else:
+            f.write(struct.pack("<IIII", 2, nc, len(specs), arch))
         for c, (w, b) in zip(specs, tensors):
-            assert w.shape == (c.cout, c.cin, c.k, c.k) and b.shape == (c.cout,)
-            f.write(struct.pack("<IIIII", c.cin, c.cout, c.k, c.stride, c.act))
+            assert w.shape == (c.cout, c.cin // c.groups, c.k, c.k) and b.shape == (c.cout,), c.name
+            if arch == ARCH_YOLOV8N:
+                f.write(struct.pack("<IIIII", c.cin, c.cout, c.k, c.stride, c.act))
+            else:
+                f.write(struct.pack("<IIIIII", c.cin, c.cout, c.k, c.stride, c.act, c.groups))
             f.write(np.ascontiguousarray(w, dtype="<f4").tobytes())
             f.write(np.ascontiguousarray(b, dtype="<f4").tobytes())
+
+
+def file_arch(path: str) -> int:
+    with open(path, "rb") as f:
+        head = f.read(20)
+    if head[:4] != MAGIC:
+        raise ValueError(f"{path}: not an IRMW weight file")
+    version = struct.unpack_from("<I", head, 4)[0]
+    return struct.unpack_from("<I", head, 16)[0] if version == 2 else ARCH_YOLOV8N
 
 
 def load(path: str) -> Tuple[int, List[Tuple[ConvSpec, np.ndarray, np.ndarray]]]:
@@ -191,20 +278,26 @@ def load(path: str) -> Tuple[int, List[Tuple[ConvSpec, np.ndarray, np.ndarray]]]
     if data[:4] != MAGIC:
         raise ValueError(f"{path}: not an IRMW weight file")
     version, nc, n = struct.unpack_from("<III", data, 4)
-    if version != VERSION:
+    if version not in (1, 2):
         raise ValueError(f"{path}: unsupported version {version}")
-    off = 16
-    specs = conv_specs(nc, pose=n == 72)      # 63 convs: detector; 72: detector + keypoint branch
+    arch = struct.unpack_from("<I", data, 16)[0] if version == 2 else ARCH_YOLOV8N
+    off = 16 if version == 1 else 20
+    specs = specs_for(arch, nc, pose=n == 72)      # v1, 63 convs: detector; 72: detector + keypoint branch
     if n != len(specs):
         raise ValueError(f"{path}: {n} convs, expected {len(specs)}")
     out = []
     for c in specs:
-        cin, cout, k, stride, act = struct.unpack_from("<IIIII", data, off)
-        off += 20
-        if (cin, cout, k, stride, act) != (c.cin, c.cout, c.k, c.stride, c.act):
+        if version == 1:
+            cin, cout, k, stride, act = struct.unpack_from("<IIIII", data, off)
+            groups = 1
+            off += 20
+        else:
+            cin, cout, k, stride, act, groups = struct.unpack_from("<IIIIII", data, off)
+            off += 24
+        if (cin, cout, k, stride, act, groups) != (c.cin, c.cout, c.k, c.stride, c.act, c.groups):
             raise ValueError(f"{path}: conv {c.name} header mismatch")
-        nw = cout * cin * k * k
-        w = np.frombuffer(data, "<f4", nw, off).reshape(cout, cin, k, k).copy()
+        nw = cout * (cin // groups) * k * k
+        w = np.frombuffer(data, "<f4", nw, off).reshape(cout, cin // groups, k, k).copy()
         off += 4 * nw
         b = np.frombuffer(data, "<f4", cout, off).copy()
         off += 4 * cout
@@ -214,6 +307,8 @@ def load(path: str) -> Tuple[int, List[Tuple[ConvSpec, np.ndarray, np.ndarray]]]
     return nc, out
 
 
-def write_random(path: str, seed: int = 0, nc: int = NC, pose: bool = False) -> str:
-    save(path, random_init(seed, nc, pose=pose), nc)
+def write_random(path: str, seed: int = 0, nc: int = NC, pose: bool = False, arch=ARCH_YOLOV8N) -> str:
+    if isinstance(arch, str):
+        arch = {"yolov8n": ARCH_YOLOV8N, "yolov8n-pose": ARCH_YOLOV8N, "shufflenetv2-pose": ARCH_SHUFFLE_KPT}[arch]
+    save(path, random_init(seed, nc, pose=pose, arch=arch), nc, arch)
     return path

@@ -403,28 +403,6 @@ def extract_armors_cv2(image: np.ndarray, boxes: np.ndarray, scores, classes, pr
 
 def synth_armor_scene(n_armors: int = 6, seed: int = 0, w: int = 1280, h: int = 1024, noise: bool = True):
     """A dark arena frame (rotated view) with bright light-bar pairs and the boxes a detector would put
-    around them; returns (image u8[h,w,3], boxes[n,4], scores[n], classes[n])."""
-    import cv2
-    rng = np.random.default_rng(seed)
-    img = rng.integers(0, 60, (h, w, 3), dtype=np.uint8) if noise else np.zeros((h, w, 3), np.uint8)
-    boxes, scores, classes = [], [], []
-    for k in range(n_armors):
-        cx, cy = rng.uniform(120, w - 120), rng.uniform(100, h - 100)
-        L = rng.uniform(18, 70)                       # light length, px
-        large = rng.random() < 0.3
-        sep = L * (rng.uniform(3.5, 5.0) if large else rng.uniform(1.2, 2.8))
-        tilt = rng.uniform(-20, 20)
-        wd = L * rng.uniform(0.15, 0.3)
-        for sgn in (-1, 1):
-            c = (cx + sgn * sep / 2, cy + rng.uniform(-2, 2))
-            box = cv2.boxPoints((c, (wd, L), tilt + rng.uniform(-4, 4)))
-            cv2.fillConvexPoly(img, np.round(box).astype(np.int32), (int(rng.integers(200, 256)),) * 3)
-        if rng.random() < 0.5:                        # a number sticker between the lights (dim or bright)
-            v = int(rng.integers(100, 256))
-            cv2.putText(img, str(int(rng.integers(1, 6))), (int(cx - L / 4), int(cy + L / 4)), cv2.FONT_HERSHEY_SIMPLEX,
-                        L / 40, (v, v, v), max(1, int(L / 15)))
-        m = rng.uniform(0.05, 0.3)
-        boxes.append([cx - sep / 2 - wd - m * sep, cy - L * (0.6 + m), cx + sep / 2 + wd + m * sep, cy + L * (0.6 + m)])
-        scores.append(rng.uniform(0.3, 0.95))
-        classes.append(int(rng.integers(0, 14)))
-    return img, np.array(boxes, np.float32), np.array(scores, np.float32), np.array(classes, np.int32)
+    around them (generator: irmv_detection_b200/synth.py armor_scene)."""
+    from irmv_detection_b200 import synth
+    return synth.armor_scene(n_armors, seed, w, h, noise)

@@ -18,15 +18,17 @@ def main():
     import cv2
     from irmv_detection_b200 import weights as W
     from oracle import yolov8n_ref as Y, preprocess_ref as PR
-    specs = W.conv_specs()
     seed = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+    arch = W.ARCH_SHUFFLE_KPT if (len(sys.argv) > 2 and sys.argv[2] == "shuffle") else W.ARCH_YOLOV8N
+    specs = W.specs_for(arch)
     rng = np.random.default_rng(seed)
     tens = []
     for c in specs:
-        w = rng.standard_normal((c.cout, c.cin, c.k, c.k)).astype(np.float32) / math.sqrt(c.cin * c.k * c.k)
+        cg = c.cin // c.groups
+        w = rng.standard_normal((c.cout, cg, c.k, c.k)).astype(np.float32) / math.sqrt(cg * c.k * c.k)
         b = rng.standard_normal(c.cout).astype(np.float32) * 0.05
         tens.append((w, b))
-    W.save("/tmp/_calib.irmw", tens)
+    W.save("/tmp/_calib.irmw", tens, arch=arch)
     m = Y.build("/tmp/_calib.irmw")
     img = cv2.imread("tests/golden/rm_test.jpg")
     from irmv_detection_b200 import synth
@@ -43,6 +45,8 @@ def main():
             target = 2.0
         if c.name.startswith("m22.cls") and c.name.endswith(".2"):
             target = 1.0
+        if c.name.startswith("m22.kpt"):
+            target = 0.1 if c.name.endswith(".2") else 1.0
         got = {}
         h = conv.register_forward_hook(lambda mod, i, o: got.__setitem__("s", float(o.std())))
         with torch.no_grad():

@@ -11,8 +11,8 @@ class _Wrapper(torch.nn.Module):
         self.m = m
 
     def forward(self, x):
-        boxes, scores = self.m(x)
-        return torch.cat((boxes, scores), 2)
+        out = self.m(x)                       # (boxes, scores) or (boxes, scores, keypoints)
+        return torch.cat((out[0], out[1]), 2)
 
 
 def export(model, path, batch=1):

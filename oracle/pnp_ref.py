@@ -261,41 +261,10 @@ def project(rvec, tvec, K=K_DEFAULT, D=D_DEFAULT, large=False):
 
 def synth_quads(n: int, seed: int = 0, noise_px: float = 0.5, K=K_DEFAULT, D=D_DEFAULT,
                 img_w: int = 640, img_h: int = 480):
-    """seeded armor poses projected through K/D (+ pixel noise).
-
-    Model frame is x-forward/y-left/z-up; the camera looks along +z, so the base rotation
-    maps model x -> camera z, model y -> camera -x, model z -> camera -y.
-    """
-    import cv2
-    rng = np.random.default_rng(seed)
-    Km = np.asarray(K, np.float64).reshape(3, 3)
-    Dm = np.asarray(D, np.float64).reshape(1, 5)
-    base = np.array([[0.0, -1.0, 0.0], [0.0, 0.0, -1.0], [1.0, 0.0, 0.0]])
-    obj = object_points(False)
-    out = np.empty((n, 4, 2), np.float32)
-    i = 0
-    while i < n:
-        dist = rng.uniform(0.5, 8.0)
-        yaw, pitch, roll = np.deg2rad(rng.uniform(-60, 60)), np.deg2rad(rng.uniform(-30, 30)), np.deg2rad(rng.uniform(-15, 15))
-        cy, sy = np.cos(yaw), np.sin(yaw)
-        cp, sp = np.cos(pitch), np.sin(pitch)
-        cr, sr = np.cos(roll), np.sin(roll)
-        Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
-        Rx = np.array([[1, 0, 0], [0, cp, -sp], [0, sp, cp]])
-        Rz = np.array([[cr, -sr, 0], [sr, cr, 0], [0, 0, 1]])
-        R = Rz @ Rx @ Ry @ base
-        # centre somewhere in view
-        u = rng.uniform(0.15, 0.85) * img_w
-        v = rng.uniform(0.15, 0.85) * img_h
-        t = np.array([(u - Km[0, 2]) / Km[0, 0] * dist, (v - Km[1, 2]) / Km[1, 1] * dist, dist])
-        rvec, _ = cv2.Rodrigues(R)
-        p, _ = cv2.projectPoints(obj, rvec, t, Km, Dm)
-        p = p.reshape(4, 2) + rng.normal(0.0, noise_px, (4, 2))
-        if (p[:, 0].min() < 0 or p[:, 0].max() >= img_w or p[:, 1].min() < 0 or p[:, 1].max() >= img_h):
-            continue
-        out[i] = p.astype(np.float32)
-        i += 1
-    return out
+    """seeded armor poses projected through K/D (+ pixel noise).  The
+    generator lives with the other synthetic inputs (irmv_detection_b200/synth.py: armor_quads)."""
+    from irmv_detection_b200 import synth
+    return synth.armor_quads(n, seed, noise_px, K, D, img_w, img_h)
 
 
 def refine_lm_cv2(img_pts: np.ndarray, rvecs: np.ndarray, tvecs: np.ndarray, K=K_DEFAULT, D=D_DEFAULT,

@@ -183,6 +183,113 @@ class YoloV8n(nn.Module):
         return decode_heads(outs)
 
 
+class DWConv(nn.Module):
+    """Depthwise 3x3 conv with (BN-folded) bias, no activation (ShuffleNetV2 units)."""
+
+    def __init__(self, c, s):
+        super().__init__()
+        self.conv = nn.Conv2d(c, c, 3, s, 1, groups=c, bias=True)
+
+    def forward(self, x):
+        return self.conv(x)
+
+
+def channel_shuffle(x, groups=2):
+    b, c, h, w = x.shape
+    return x.view(b, groups, c // groups, h, w).transpose(1, 2).reshape(b, c, h, w)
+
+
+class ShuffleDown(nn.Module):
+    """ShuffleNetV2 spatial down-sampling unit (Ma et al. 2018, fig. 3d), SiLU after the 1x1 convs."""
+
+    def __init__(self, cin, cout):
+        super().__init__()
+        h = cout // 2
+        self.b1_dw, self.b1_pw = DWConv(cin, 2), Conv(cin, h, 1, 1)
+        self.b2_pw1, self.b2_dw, self.b2_pw2 = Conv(cin, h, 1, 1), DWConv(h, 2), Conv(h, h, 1, 1)
+
+    def convs(self):
+        return [self.b1_dw.conv, self.b1_pw.conv, self.b2_pw1.conv, self.b2_dw.conv, self.b2_pw2.conv]
+
+    def forward(self, x):
+        return channel_shuffle(torch.cat((self.b1_pw(self.b1_dw(x)), self.b2_pw2(self.b2_dw(self.b2_pw1(x)))), 1))
+
+
+class ShuffleBasic(nn.Module):
+    """ShuffleNetV2 basic unit (fig. 3c): channel split, right half 1x1 -> depthwise 3x3 -> 1x1, concat, shuffle."""
+
+    def __init__(self, c):
+        super().__init__()
+        h = c // 2
+        self.pw1, self.dw, self.pw2 = Conv(h, h, 1, 1), DWConv(h, 1), Conv(h, h, 1, 1)
+
+    def convs(self):
+        return [self.pw1.conv, self.dw.conv, self.pw2.conv]
+
+    def forward(self, x):
+        x1, x2 = x.chunk(2, 1)
+        return channel_shuffle(torch.cat((x1, self.pw2(self.dw(self.pw1(x2)))), 1))
+
+
+class ShuffleV2Kpt(YoloV8n):
+    """The keypoint detector on a ShuffleNetV2-style backbone (irmv_detection_b200.weights.shuffle_conv_specs):
+    stem + four down units (+ 0/1/3/1 basic units) produce P3/P4/P5-in, then SPPF, the YOLOv8n neck, Detect
+    and the Pose branch.  Parity unpinned by the reference (the model is only named, README.md:12,16)."""
+
+    def __init__(self, nc=14):
+        super().__init__(nc, pose=True)
+        from irmv_detection_b200 import weights as W
+        for n in ("m1", "m2", "m3", "m4", "m5", "m6", "m7", "m8"):
+            delattr(self, n)
+        self.stages = nn.ModuleList()
+        for name, cin, cout, units in W.shuffle_stage_plan():
+            self.stages.append(nn.ModuleList([ShuffleDown(cin, cout)] + [ShuffleBasic(cout) for _ in range(units)]))
+
+    def convs_in_order(self):
+        out = [self.m0.conv]
+        for st in self.stages:
+            for u in st:
+                out += u.convs()
+        out += [self.m9.cv1.conv, self.m9.cv2.conv]
+
+        def c2f(m):
+            r = [m.cv1.conv]
+            for b in m.m:
+                r += [b.cv1.conv, b.cv2.conv]
+            return r + [m.cv2.conv]
+
+        out += c2f(self.m12) + c2f(self.m15) + [self.m16.conv] + c2f(self.m18) + [self.m19.conv] + c2f(self.m21)
+        for i in range(3):
+            out += [self.box[i][0].conv, self.box[i][1].conv, self.box[i][2].conv]
+            out += [self.cls[i][0].conv, self.cls[i][1].conv, self.cls[i][2].conv]
+        for i in range(3):
+            out += [self.kpt[i][0].conv, self.kpt[i][1].conv, self.kpt[i][2].conv]
+        return out
+
+    def features(self, x, taps=None):
+        def tap(name, t):
+            if taps is not None:
+                taps[name] = t
+            return t
+        x = tap("m0", self.m0(x))
+        feats = []
+        for i, st in enumerate(self.stages):
+            for u in st:
+                x = u(x)
+            feats.append(tap(f"d{i + 1}", x))
+        x4, x6 = feats[1], feats[2]
+        x9 = tap("m9", self.m9(feats[3]))
+        u = F.interpolate(x9, scale_factor=2, mode="nearest")
+        x12 = tap("m12", self.m12(torch.cat((u, x6), 1)))
+        u = F.interpolate(x12, scale_factor=2, mode="nearest")
+        x15 = tap("m15", self.m15(torch.cat((u, x4), 1)))
+        x16 = tap("m16", self.m16(x15))
+        x18 = tap("m18", self.m18(torch.cat((x16, x12), 1)))
+        x19 = tap("m19", self.m19(x18))
+        x21 = tap("m21", self.m21(torch.cat((x19, x9), 1)))
+        return [(self.box[i](f), self.cls[i](f), self.kpt[i](f)) for i, f in enumerate((x15, x18, x21))]
+
+
 def make_anchors(sizes=(80, 40, 20)):
     pts, strides = [], []
     for hw, s in zip(sizes, STRIDES):
@@ -231,6 +338,9 @@ def decode_keypoints(outs):
 def build(weights_path, nc=14):
     from irmv_detection_b200 import weights as W
     torch.manual_seed(0)
-    m = YoloV8n(nc, pose=len(W.load(weights_path)[1]) == 72).eval()
+    if W.file_arch(weights_path) == W.ARCH_SHUFFLE_KPT:
+        m = ShuffleV2Kpt(nc).eval()
+    else:
+        m = YoloV8n(nc, pose=len(W.load(weights_path)[1]) == 72).eval()
     m.load_irmw(weights_path)
     return m

@@ -17,14 +17,15 @@ def measure(n: int = 64, per: int = 10) -> dict:
     import torch
     import irmv_detection_b200 as irmv
     from irmv_detection_b200 import engine as E
-    from oracle import armor_ref as A, preprocess_ref as PR
+    from irmv_detection_b200 import synth
+    from oracle import armor_ref as A                          # CPU-baseline leg: the reference's cv2 chain
     scenes, boxes = [], np.zeros((n, 100), irmv.BBOX_DTYPE)
     for f in range(n):
-        img, b, s, c = A.synth_armor_scene(per, 1000 + f)
+        img, b, s, c = synth.armor_scene(per, 1000 + f)
         scenes.append(img)
         boxes["xyxy"][f, :per] = b; boxes["score"][f, :per] = s; boxes["class_id"][f, :per] = c
     counts = np.full(n, per, np.int32)
-    frames = np.stack([PR.rot180(s) for s in scenes])              # camera view
+    frames = np.stack([np.ascontiguousarray(s[::-1, ::-1]) for s in scenes])              # camera view
     dev = torch.from_numpy(frames).cuda()
     torch.cuda.synchronize()
     ms = []

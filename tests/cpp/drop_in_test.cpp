@@ -52,7 +52,12 @@ int main(int argc, char ** argv)
   for (size_t i = 0; i < boxes.size() && i < 3; i++)
     printf("box %.3f %.3f %.3f %.3f score %.4f class %s\n", boxes[i].xyxy[0], boxes[i].xyxy[1], boxes[i].xyxy[2],
            boxes[i].xyxy[3], boxes[i].score, armor_class_name(boxes[i].class_id));
+  const double mn = *std::min_element(avg.begin(), avg.end());
   printf("avg_ms %.4f max_ms %.4f profiling_ms %.4f\n", mean, mx, engine.get_profiling_time());
+  // the reference's benchmark protocol as a record (test/yolo_test.cpp:68-103): 100 warm-ups, `runs` runs of
+  // 10 x {memcpy of the 3.9 MB frame into the source buffer + detect()}, avg / min / max of the per-run means
+  printf("protocol runs %d avg_ms %.4f min_ms %.4f max_ms %.4f\n", runs, mean, mn, mx);
+  if (argc > 4 && std::string(argv[4]) == "protocol") return mx < 30.0 ? 0 : 1;
   if (!(mx < 30.0)) { printf("FAIL: max detection time\n"); return 1; }   // reference bound, test/yolo_test.cpp:106
   const cv::Mat & rot = engine.get_rotated_image();
   printf("rotated %dx%d first_byte %d expect %d\n", rot.cols, rot.rows, rot.data[0], frame[frame.size() - 3]);

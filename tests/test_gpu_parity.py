@@ -1293,3 +1293,111 @@ def test_weight_file_validation(tmp_path, weights_seed0):
         p.write_bytes(data)
         with pytest.raises(irmv.IrmvError):
             irmv.YoloEngine(str(p), (1280, 1024))
+
+
+# ------------------------------------------------------- ShuffleNetV2-backbone keypoint detector (configs[2])
+@pytest.fixture(scope="module")
+def weights_shuffle(tmp_path_factory):
+    from irmv_detection_b200 import weights as W
+    p = tmp_path_factory.mktemp("ws") / "shufflenetv2_pose_seed0.irmw"
+    W.write_random(str(p), 0, arch="shufflenetv2-pose")
+    return str(p)
+
+
+def test_shufflenet_variant_parity(frames, weights_shuffle):
+    """BASELINE.json configs[2], north_star "depthwise and elementwise layers are fused bandwidth-bound
+    kernels": the keypoint detector on the ShuffleNetV2-style backbone.  Depthwise 3x3 kernel + 1x1 convs on
+    the tcgen05 raster kernel, channel split / concat / shuffle folded into plane runs and weight
+    permutations (zero bytes moved).  Every stage output (un-permuted by read_tensor), the neck taps and the
+    three head tensors against the FP32 oracle; decoded scores / boxes / keypoints within the north_star
+    tolerances; kept indices bit-exact on the GPU's own decoded inputs."""
+    import torch
+    import irmv_detection_b200 as irmv
+    from oracle import nms_ref as N, pnp_ref as P, yolov8n_ref as Y
+    _cuda()
+    fr = frames[[0, 2, 3]]
+    n = fr.shape[0]
+    eng = irmv.YoloEngine(weights_shuffle, (1280, 1024), max_batch=n, sub_batch=n)
+    assert eng.has_keypoints()
+    assert sum(1 for o in eng.describe_ops() if o["kind"] == "dw") == 13
+    assert all(o["raster"] for o in eng.describe_ops() if o["kind"] == "conv" and o["k"] == 1)
+    eng.enable_pnp(P.K_DEFAULT, P.D_DEFAULT, (0.5, 480 / 1024))
+    dets = eng.detect_batch(fr)
+    kp = eng.fetch_keypoints(n)
+    x = irmv.preprocess(fr)
+    m = Y.build(weights_shuffle)
+    taps = {}
+    with torch.no_grad():
+        outs = m.features(torch.from_numpy(x[..., :3].astype(np.float32)).permute(0, 3, 1, 2).contiguous(), taps)
+        rboxes, rscores = Y.decode_heads(outs)
+        rk = Y.decode_keypoints(outs).numpy()
+    rboxes, rscores = rboxes.numpy(), rscores.numpy()
+    seen = 0
+    for name, ref in taps.items():
+        try:
+            got = eng.read_tensor(name).astype(np.float32)
+        except RuntimeError:
+            continue
+        seen += 1
+        ref = ref.permute(0, 2, 3, 1).numpy()
+        err, scale = np.abs(got - ref).max(), np.abs(ref).max()
+        assert err <= 2e-2 * max(scale, 1.0), f"{name}: max err {err} (scale {scale})"
+    assert seen >= 9 and all(k in taps for k in ("d1", "d2", "d3", "d4"))
+    box = np.concatenate([eng.read_tensor(f"box{i}").reshape(n, -1, 64) for i in range(3)], 1)
+    cls = np.concatenate([eng.read_tensor(f"cls{i}").reshape(n, -1, 16) for i in range(3)], 1)
+    gboxes, gscores = irmv.decode(box, cls)
+    assert np.abs(gscores - rscores).max() < SCORE_TOL
+    assert np.abs(gboxes - rboxes).max() < BOX_TOL_PX
+    for i in range(3):
+        got = eng.read_tensor(f"kpt{i}").astype(np.float32)[..., :8]
+        ref = outs[i][2].permute(0, 2, 3, 1).numpy()
+        assert np.abs(got - ref).max() <= 2e-2 * max(np.abs(ref).max(), 1.0), f"kpt{i}"
+    scale = np.array([1280 / 640, 1024 / 640], np.float32)
+    total = 0
+    for f in range(n):
+        ri, rb, rs, rc = N.nms(gboxes[f], gscores[f])
+        assert np.array_equal(eng.kept_indices(f), ri), f"frame {f}"
+        assert len(dets[f]) == len(ri)
+        total += len(ri)
+        if len(ri):
+            assert np.abs(kp[f, :len(ri)] - rk[f, ri // 14] * scale).max() < BOX_TOL_PX * 2.0     # 0.5 px at network scale
+        oi, ob, os_, oc = N.nms(rboxes[f], rscores[f])
+        confident = [k for k in range(len(oi)) if os_[k] > 0.25 + 2 * SCORE_TOL]
+        missing = [k for k in confident if int(oi[k]) not in set(ri.tolist())]
+        assert len(missing) <= max(1, len(confident) // 20)
+    assert total > 0
+    eng.close()
+
+
+def test_shufflenet_variant_batch64_pinned(base_image, weights_shuffle):
+    """configs[2]'s own shape: batch 64 in one replay.  Frames across the replay equal the batch-1 engine bit
+    for bit (detections, keypoints, poses, raw keypoint tensors); frame 0 within tolerance of the FP32 oracle."""
+    import irmv_detection_b200 as irmv
+    from irmv_detection_b200 import synth
+    from oracle import pnp_ref as P
+    _cuda()
+    fr = synth.frames_from_base(base_image, 64, seed=29)
+    big = irmv.YoloEngine(weights_shuffle, (1280, 1024), max_batch=64, sub_batch=64, num_lanes=1)
+    big.enable_pnp(P.K_DEFAULT, P.D_DEFAULT, (0.5, 480 / 1024))
+    res = big.detect_batch(fr)
+    kp = big.fetch_keypoints(64)
+    rv, tv, ok = big.fetch_poses(64)
+    raw_k = [big.read_tensor(f"kpt{i}") for i in range(3)]
+    d3 = big.read_tensor("d3")
+    one = irmv.YoloEngine(weights_shuffle, (1280, 1024))
+    one.enable_pnp(P.K_DEFAULT, P.D_DEFAULT, (0.5, 480 / 1024))
+    for pos in (0, 1, 31, 32, 62, 63):
+        r = one.detect_batch(fr[pos:pos + 1])[0]
+        assert r == res[pos], f"frame {pos}"
+        k = len(r)
+        assert np.array_equal(one.fetch_keypoints(1)[0, :k], kp[pos, :k])
+        r1, t1, _ = one.fetch_poses(1)
+        assert np.array_equal(rv[pos, :k], r1[0, :k]) and np.array_equal(tv[pos, :k], t1[0, :k])
+        for i in range(3):
+            assert np.array_equal(one.read_tensor(f"kpt{i}")[0], raw_k[i][pos])
+        assert np.array_equal(one.read_tensor("d3")[0], d3[pos])
+    one.close()
+    x = irmv.preprocess(fr[:1])
+    ri, outs = _frame_vs_oracle(big, 0, x, weights_shuffle)
+    assert np.array_equal(big.kept_indices(0), ri)
+    big.close()

@@ -536,3 +536,46 @@ def test_stem_fast_path_arithmetic_matches_oracle(H, chan, rot):
     x, _ = PR.preprocess(raw, chan, rot, True)
     ref = np.rint(x.transpose(1, 2, 0) * 255).astype(np.int64)
     assert np.array_equal(_stem_fast_path_emulation(raw, chan, rot), ref)
+
+
+def test_shufflenet_variant_weights_and_oracle(base_image, tmp_path):
+    """BASELINE.json configs[2]: the keypoint detector on the ShuffleNetV2-style backbone.  The weight file
+    (IRMW v2: architecture id + groups per conv) round-trips, the inventory is what weights.py documents
+    (83 convs, 13 of them depthwise), the units are the published ShuffleNetV2 ones (channel shuffle checked
+    against its definition), and OpenCV-DNN running the ONNX export agrees with the torch oracle."""
+    import cv2
+    import torch
+    from irmv_detection_b200 import weights as W
+    from oracle import export_onnx, preprocess_ref as PR, yolov8n_ref as Y
+    specs = W.shuffle_conv_specs()
+    assert len(specs) == 83 and sum(1 for c in specs if c.groups > 1) == 13
+    assert all(c.groups in (1, c.cin) and (c.groups == 1 or (c.k == 3 and c.act == 0 and c.cin == c.cout)) for c in specs)
+    assert [c.name for c in specs[36:40]] == ["m9.cv1", "m9.cv2", "m12.cv1", "m12.m0.cv1"]
+    p = str(tmp_path / "shuffle.irmw")
+    W.write_random(p, 0, arch="shufflenetv2-pose")
+    assert W.file_arch(p) == W.ARCH_SHUFFLE_KPT
+    nc, t = W.load(p)
+    assert nc == 14 and len(t) == 83
+    assert all(np.array_equal(w.astype(np.float16).astype(np.float32), w) for _, w, _ in t)   # FP16-exact
+    x = torch.arange(2 * 8 * 1 * 1, dtype=torch.float32).view(2, 8, 1, 1)
+    assert Y.channel_shuffle(x)[0, :, 0, 0].tolist() == [0, 4, 1, 5, 2, 6, 3, 7]              # y[2i] = a[i], y[2i+1] = b[i]
+    m = Y.build(p)
+    assert isinstance(m, Y.ShuffleV2Kpt) and len(m.convs_in_order()) == 83
+    xin, _ = PR.preprocess(base_image)
+    taps = {}
+    with torch.no_grad():
+        outs = m.features(torch.from_numpy(xin)[None], taps)
+        boxes, scores = Y.decode_heads(outs)
+    assert [tuple(taps[k].shape[1:]) for k in ("d1", "d2", "d3", "d4")] == [(32, 160, 160), (64, 80, 80), (128, 40, 40), (256, 20, 20)]
+    assert all(0.2 < float(taps[k].std()) < 3.0 for k in taps)            # calibrated init keeps activations O(1)
+    assert outs[0][2].shape == (1, 8, 80, 80)
+    path = str(tmp_path / "shuffle.onnx")
+    try:
+        export_onnx.export(m, path)
+        net = cv2.dnn.readNetFromONNX(path)
+    except Exception as e:          # exporter internals differ between torch builds
+        pytest.skip(f"ONNX export / import unavailable: {e}")
+    net.setInput(xin[None])
+    out = net.forward()
+    ref = torch.cat((boxes, scores), 2).numpy()
+    assert out.shape == ref.shape and np.abs(out - ref).max() < 5e-3
