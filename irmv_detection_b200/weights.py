@@ -195,7 +195,8 @@ INIT_GAIN = {
 }
 CLS_BIAS = -8.0
 # ShuffleNetV2-backbone keypoint detector: gains from `python -m oracle.calibrate_init 0 shuffle`
-# (box.2 gains are 0.2x the calibrated value, like the YOLOv8n table above)
+# (box.2 gains are 0.12x the calibrated value: DFL logits of std ~0.25 keep the FP16-vs-FP32 box drift at
+# stride 32 under the 0.5 px bar; at 0.2x, the YOLOv8n table's factor, it measured 0.53 px on this backbone)
 INIT_GAIN_SHUFFLE = {0: (
     14.7, 3.07, 1.054, 1.973, 1.07, 0.7047, 2.278, 1.211,
     2.151, 1.273, 1.262, 1.67, 1.229, 0.9991, 1.408, 0.9903,
@@ -204,8 +205,8 @@ INIT_GAIN_SHUFFLE = {0: (
     1.016, 1.355, 1.308, 0.9648, 1.427, 0.3457, 1.533, 1.634,
     1.541, 1.529, 1.591, 1.76, 1.968, 1.46, 1.536, 1.617,
     1.625, 1.715, 1.554, 1.447, 1.535, 1.495, 1.485, 1.526,
-    1.648, 1.677, 0.7202, 1.593, 1.671, 1.329, 1.392, 1.437,
-    0.6148, 1.558, 1.523, 1.653, 1.681, 1.55, 0.6508, 1.74,
+    1.648, 1.677, 0.4321, 1.593, 1.671, 1.329, 1.392, 1.437,
+    0.3689, 1.558, 1.523, 1.653, 1.681, 1.55, 0.3905, 1.74,
     1.44, 1.711, 1.763, 2.363, 0.2423, 1.352, 1.565, 0.1022,
     1.656, 1.404, 0.2159,
 )}
