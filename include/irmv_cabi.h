@@ -49,6 +49,19 @@ enum {
   IRMV_CH_BAYER_GBRG = 5
 };
 
+/* MindVision frame header field tSdkFrameHead.uiMediaType (reference mvsdk/include/CameraDefine.h:609-627;
+ * 8-bit Bayer codes :733-736, packed RGB8 / BGR8 :771-772) -> IRMV_CH_* for a raw sensor frame handed to the
+ * engine instead of the vendor ISP's RGB8 output (reference src/mv_camera.cpp:64,96).  The vendor names a
+ * pattern by the first two pixels of the first row: BAYRG = R G / G B = RGGB, BAYGR = GRBG, BAYGB = GBRG,
+ * BAYBG = BGGR.  Returns -1 for formats the engine does not ingest (10/12/16-bit Bayer, mono, YUV, planar). */
+#define IRMV_MV_MEDIA_TYPE_BAYGR8 0x01080008u
+#define IRMV_MV_MEDIA_TYPE_BAYRG8 0x01080009u
+#define IRMV_MV_MEDIA_TYPE_BAYGB8 0x0108000Au
+#define IRMV_MV_MEDIA_TYPE_BAYBG8 0x0108000Bu
+#define IRMV_MV_MEDIA_TYPE_RGB8 0x02180014u
+#define IRMV_MV_MEDIA_TYPE_BGR8 0x02180015u
+int irmv_chan_order_from_media_type(uint32_t mv_media_type);
+
 /* STRETCH = the reference: independent x/y scale, NPP's measured corner-aligned bilinear map
  * (src = dst * src_size/640, no half-pixel offset; pinned in tests/golden/npp_rm_golden.npz).
  * STRETCH_HALF_PIXEL = same stretch with OpenCV-style pixel centres.  LETTERBOX = ultralytics

@@ -55,6 +55,7 @@ _P = C.c_void_p
 SYMBOLS = {
     "irmv_last_error": (C.c_char_p, []),
     "irmv_version": (C.c_int, []),
+    "irmv_chan_order_from_media_type": (C.c_int, [C.c_uint32]),
     "irmv_engine_config_default": (C.c_int, [C.POINTER(EngineConfig)]),
     "irmv_engine_create": (C.c_int, [C.c_char_p, C.POINTER(EngineConfig), C.POINTER(_P)]),
     "irmv_engine_destroy": (None, [_P]),

@@ -1153,6 +1153,18 @@ int refresh_rotated(irmv_engine *e, int slot) {
 extern "C" {
 
 const char *irmv_last_error(void) { return g_err.c_str(); }
+
+int irmv_chan_order_from_media_type(uint32_t t) {
+  switch (t) {
+    case IRMV_MV_MEDIA_TYPE_BAYRG8: return IRMV_CH_BAYER_RGGB;
+    case IRMV_MV_MEDIA_TYPE_BAYGR8: return IRMV_CH_BAYER_GRBG;
+    case IRMV_MV_MEDIA_TYPE_BAYGB8: return IRMV_CH_BAYER_GBRG;
+    case IRMV_MV_MEDIA_TYPE_BAYBG8: return IRMV_CH_BAYER_BGGR;
+    case IRMV_MV_MEDIA_TYPE_RGB8: return IRMV_CH_PASSTHROUGH;     // the reference feeds the ISP's RGB8 as is
+    case IRMV_MV_MEDIA_TYPE_BGR8: return IRMV_CH_SWAP_RB;
+    default: return -1;
+  }
+}
 int irmv_version(void) { return 100; }
 
 int irmv_engine_config_default(irmv_engine_config *c) {

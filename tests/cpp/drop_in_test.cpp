@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <memory>
@@ -14,6 +15,7 @@
 #include <vector>
 
 #include "irmv_detection/armor_extractor.hpp"
+#include "irmv_detection/irm_detector.hpp"
 #include "irmv_detection/camera.hpp"
 #include "irmv_detection/pnp_solver.hpp"
 #include "irmv_detection/triple_buffer.hpp"
@@ -116,6 +118,34 @@ int main(int argc, char ** argv)
         printf("FAIL: fused armor %zu differs\n", i);
         return 1;
       }
+    // IrmDetectorCore (include/irmv_detection/irm_detector.hpp): the node's message_callback data path --
+    // detect -> extract_armors -> solvePnP -> quaternion -> distance in one replay -- on the same frame:
+    // every returned armor carries a unit quaternion and the pose PnPSolver gives for that armor
+    {
+      IrmDetectorCore core(argv[1], cv::Size(1280, 1024), {957.669211, 0, 345.943891, 0, 969.127115, 284.057302, 0, 0, 1},
+                           {-0.405274, 0.126058, -0.026939, -0.006503, 0});
+      memcpy(core.image_buffers()[1], src, img.size());
+      Camera::StampedImage si;
+      si.id = 1;
+      std::vector<ArmorPose> poses = core.message_callback(si);
+      printf("core armors %zu of %zu fused\n", poses.size(), fused.size());
+      if (poses.size() > fused.size()) { printf("FAIL: IrmDetectorCore armor count\n"); return 1; }
+      size_t fi = 0;
+      for (const ArmorPose & ap : poses) {
+        const double n2 = ap.orientation[0] * ap.orientation[0] + ap.orientation[1] * ap.orientation[1] +
+                          ap.orientation[2] * ap.orientation[2] + ap.orientation[3] * ap.orientation[3];
+        if (!(n2 > 1.0 - 1e-9 && n2 < 1.0 + 1e-9)) { printf("FAIL: IrmDetectorCore quaternion\n"); return 1; }
+        // the same armor through the stand-alone solver (armors without a pose are skipped, reference :207-209)
+        bool matched = false;
+        for (; fi < fused.size() && !matched; fi++) {
+          cv::Mat rv3, tv3;
+          if (!pnp.solvePnP(fused[fi], rv3, tv3)) continue;
+          matched = std::fabs(tv3.at<double>(2) - ap.position[2]) < 1e-9 * std::fabs(ap.position[2]) + 1e-12;
+          if (!matched) { printf("FAIL: IrmDetectorCore pose %f vs %f\n", ap.position[2], tv3.at<double>(2)); return 1; }
+        }
+        if (!matched) { printf("FAIL: IrmDetectorCore armor without a stand-alone match\n"); return 1; }
+      }
+    }
   }
 
   // The node's data path without ROS (reference src/irm_detector.cpp:33-38,68-78,176-183): one engine per

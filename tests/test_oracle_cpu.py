@@ -579,3 +579,19 @@ def test_shufflenet_variant_weights_and_oracle(base_image, tmp_path):
     out = net.forward()
     ref = torch.cat((boxes, scores), 2).numpy()
     assert out.shape == ref.shape and np.abs(out - ref).max() < 5e-3
+
+
+def test_media_type_to_channel_order():
+    """tSdkFrameHead.uiMediaType -> IRMV_CH_* (reference mvsdk/include/CameraDefine.h:693-705,733-736,771-772).
+    The codes are rebuilt here from the vendor header's formula (MONO|COLOR base | bit occupancy | id)."""
+    from irmv_detection_b200 import _lib as L
+    MONO, COLOR, O8, O24, O16 = 0x01000000, 0x02000000, 0x00080000, 0x00180000, 0x00100000
+    f = L.lib().irmv_chan_order_from_media_type
+    assert f(MONO | O8 | 0x0009) == L.CH_BAYER_RGGB      # BAYRG8: R G / G B
+    assert f(MONO | O8 | 0x0008) == L.CH_BAYER_GRBG      # BAYGR8
+    assert f(MONO | O8 | 0x000A) == L.CH_BAYER_GBRG      # BAYGB8
+    assert f(MONO | O8 | 0x000B) == L.CH_BAYER_BGGR      # BAYBG8
+    assert f(COLOR | O24 | 0x0014) == L.CH_PASSTHROUGH   # RGB8: what CameraImageProcess emits (src/mv_camera.cpp:64)
+    assert f(COLOR | O24 | 0x0015) == L.CH_SWAP_RB       # BGR8
+    assert f(MONO | O8 | 0x0001) == -1                   # MONO8
+    assert f(MONO | O16 | 0x000D) == -1                  # BAYRG10: not ingested
