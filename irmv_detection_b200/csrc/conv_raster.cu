@@ -48,7 +48,7 @@ struct Bars {
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint64_t mid_full, mid_empty;           // fused tail: intermediate tile written / consumed
-  uint64_t ext_full, ext_empty;           // fused tail: the tail's other input planes loaded / consumed
+  uint64_t ext_full[2], ext_empty[2];     // fused tail: the tail's other input planes loaded / consumed (1 or 2 buffers)
   uint64_t tail_full[2], tail_empty[2];   // fused tail: second accumulator set
   uint64_t bfull;
   uint32_t tmem_base;
@@ -69,6 +69,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
       "bra LAB_WAIT;\n"
       "DONE:\n"
       "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
+}
+// non-blocking probe: has the phase with this parity completed?
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, uint32_t parity, int lane) {
   if (lane == 0) mbar_wait(bar, parity);
@@ -146,6 +157,7 @@ struct RArgs {
   // fused 1x1 tail (ConvParams::tail_w): intermediate tile [cout/8][TM][8], tail weights, tail bias
   uint32_t off_mid, off_ext, off_bt, off_tbias, bt_bytes, tail_idesc;
   int ext_planes;                         // tail input planes that come from global memory (ConvParams::tail_ext)
+  int ext_stages;                         // buffers for them (2 when shared memory allows: the load of tile j+1 runs under tail(j))
   int rev;                                // walk the tiles from the last to the first (ConvParams::rev_tiles)
   int tmem_tail0;                         // first TMEM column of the tail accumulators
 };
@@ -263,8 +275,10 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
     mbar_init(&bars->bfull, 1);
     mbar_init(&bars->mid_full, NEPI);
     mbar_init(&bars->mid_empty, 1);
-    mbar_init(&bars->ext_full, 1);
-    mbar_init(&bars->ext_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->ext_full[i], 1);
+      mbar_init(&bars->ext_empty[i], 1);
+    }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->tail_full[i], 1);
       mbar_init(&bars->tail_empty[i], NEPI);
@@ -471,25 +485,22 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
       const int n0 = p.in_parity ? a.NP : p.seg[0].c >> 3, n1 = p.nseg > 1 ? p.seg[1].c >> 3 : 0;
       const size_t ps0 = (size_t)p.seg[0].pstride * 2, ps1 = (size_t)p.seg[1].pstride * 2;
       const int rl0 = p.in_parity ? 0 : p.seg[0].runs;
-      // fused tail over a concat: the tail's other input planes for tile number j (no halo), loaded
-      // one tile behind the main operand (tail(j) runs after main(j+1), see the MMA warp)
+      // fused tail over a concat: the tail's other input planes for tile number j (no halo).  They do not
+      // depend on this kernel's own progress, so they are loaded as early as their buffer is free.
       const uint32_t ext_bytes = (uint32_t)a.TM * 16u;
-      auto load_ext = [&](int j, int tile_j) {
-        mbar_wait(&bars->ext_empty, ((uint32_t)j & 1u) ^ 1u);
-        const uint32_t bar = smem_u32(&bars->ext_full);
-        mbar_expect_tx(bar, ext_bytes * (uint32_t)a.ext_planes);
-        uint32_t dst = smem_u32(sExt);
+      const uint32_t ext_buf_bytes = ext_bytes * (uint32_t)a.ext_planes;
+      auto issue_ext = [&](int j, int tile_j) {
+        const int eb = a.ext_stages == 2 ? (j & 1) : 0;
+        const uint32_t bar = smem_u32(&bars->ext_full[eb]);
+        mbar_expect_tx(bar, ext_buf_bytes);
+        uint32_t dst = smem_u32(sExt) + (uint32_t)eb * ext_buf_bytes;
         const uint8_t *src = reinterpret_cast<const uint8_t *>(p.tail_ext.ptr) + ((long long)a.q_begin + (long long)tile_j * a.TM) * 16;
         const size_t pse = (size_t)p.tail_ext.pstride * 2;
         for (int c = 0; c < a.ext_planes; ++c, dst += ext_bytes, src += pse) bulk_g2s(dst, src, ext_bytes, bar);
       };
-      int prev_tile = -1;
-      for (int tseq = blockIdx.x; tseq < a.num_tiles; tseq += gridDim.x, ++itl) {
-        const int tile = a.rev ? a.num_tiles - 1 - tseq : tseq;
+      auto issue_main = [&](int tile, int itl) {
         const bool tr = p.trace && blockIdx.x == 0 && itl < p.trace_cap;
-        if (tr) p.trace[itl * 8 + 0] = clock64();
         const long long qlo = (long long)a.q_begin + (long long)tile * a.TM - a.halo_front;
-        mbar_wait(&bars->empty[s], ph ^ 1u);
         if (tr) p.trace[itl * 8 + 1] = clock64();
         const uint32_t bar = smem_u32(&bars->full[s]);
         mbar_expect_tx(bar, tile_tx);
@@ -504,20 +515,52 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
         for (int c = 0; c < n1; ++c, dst += pitch_bytes, src += ps1) bulk_g2s(dst, src, plane_bytes, bar);
         if (tr) p.trace[itl * 8 + 2] = clock64();
         if (++s == a.stages) { s = 0; ph ^= 1u; }
-        if (TAIL && a.ext_planes && itl > 0) load_ext(itl - 1, prev_tile);
-        prev_tile = tile;
-        if (a.b_stream) {
-          const uint8_t *wsrc = reinterpret_cast<const uint8_t *>(p.w_raster);
-          for (int t = 0; t < a.nchunks; ++t, wsrc += a.b_tap_bytes) {
-            mbar_wait(&bars->bw_empty[bs], bph ^ 1u);
-            const uint32_t bbar = smem_u32(&bars->bw_full[bs]);
-            mbar_expect_tx(bbar, a.b_tap_bytes);
-            bulk_g2s(sB_u + (uint32_t)bs * a.b_tap_bytes, wsrc, a.b_tap_bytes, bbar);
-            if (++bs == a.b_stages) { bs = 0; bph ^= 1u; }
+      };
+      auto tile_of = [&](int seq) { return a.rev ? a.num_tiles - 1 - seq : seq; };
+      if (TAIL && a.ext_planes) {
+        // Two independent streams of loads (main tiles, ext tiles) issued by one thread: poll both
+        // barriers without blocking, so a full ext buffer never holds back the next main tile (the
+        // blocking order main(j+1) -> ext(j) serialised the loads: one main tile in flight at a time,
+        // its DRAM latency exposed on every tile -- scripts/trace_conv.py, profiles/r2_summary.md).
+        const int mine = a.num_tiles > (int)blockIdx.x ? (a.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+        int mi = 0, ei = 0;
+        while (mi < mine || ei < mine) {
+          bool progressed = false;
+          if (mi < mine && mbar_test(&bars->empty[s], ph ^ 1u)) {
+            if (p.trace && blockIdx.x == 0 && mi < p.trace_cap) p.trace[mi * 8 + 0] = clock64();
+            issue_main(tile_of((int)blockIdx.x + mi * (int)gridDim.x), mi);
+            ++mi;
+            progressed = true;
+          }
+          if (ei < mine) {
+            const int eb = a.ext_stages == 2 ? (ei & 1) : 0;
+            const uint32_t eph = a.ext_stages == 2 ? ((uint32_t)(ei >> 1) & 1u) : ((uint32_t)ei & 1u);
+            if (mbar_test(&bars->ext_empty[eb], eph ^ 1u)) {
+              issue_ext(ei, tile_of((int)blockIdx.x + ei * (int)gridDim.x));
+              ++ei;
+              progressed = true;
+            }
+          }
+          if (!progressed) __nanosleep(64);
+        }
+      } else {
+        for (int tseq = blockIdx.x; tseq < a.num_tiles; tseq += gridDim.x, ++itl) {
+          const int tile = tile_of(tseq);
+          if (p.trace && blockIdx.x == 0 && itl < p.trace_cap) p.trace[itl * 8 + 0] = clock64();
+          mbar_wait(&bars->empty[s], ph ^ 1u);
+          issue_main(tile, itl);
+          if (a.b_stream) {
+            const uint8_t *wsrc = reinterpret_cast<const uint8_t *>(p.w_raster);
+            for (int t = 0; t < a.nchunks; ++t, wsrc += a.b_tap_bytes) {
+              mbar_wait(&bars->bw_empty[bs], bph ^ 1u);
+              const uint32_t bbar = smem_u32(&bars->bw_full[bs]);
+              mbar_expect_tx(bbar, a.b_tap_bytes);
+              bulk_g2s(sB_u + (uint32_t)bs * a.b_tap_bytes, wsrc, a.b_tap_bytes, bbar);
+              if (++bs == a.b_stages) { bs = 0; bph ^= 1u; }
+            }
           }
         }
       }
-      if (TAIL && a.ext_planes && itl > 0) load_ext(itl - 1, prev_tile);
     }
   } else {
     // ===================================================================== MMA issuer
@@ -539,15 +582,17 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
     const uint32_t bt_lo0 = desc_lo(smem_u32(sBt), (uint32_t)tnp * 16u);
     auto issue_tail = [&](int j) {
       const int tb = j & 1;
+      const int eb = a.ext_stages == 2 ? (j & 1) : 0;
+      const uint32_t eph = a.ext_stages == 2 ? ((uint32_t)(j >> 1) & 1u) : ((uint32_t)j & 1u);
       mbar_wait_warp(&bars->mid_full, (uint32_t)j & 1u, lane);
-      if (a.ext_planes) mbar_wait_warp(&bars->ext_full, (uint32_t)j & 1u, lane);
+      if (a.ext_planes) mbar_wait_warp(&bars->ext_full[eb], eph, lane);
       mbar_wait_warp(&bars->tail_empty[tb], ((uint32_t)(j >> 1) & 1u) ^ 1u, lane);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t td0 = tmem_base + (uint32_t)(a.tmem_tail0 + tb * R * tnp);
         // K of the tail = [planes loaded from global (older concat chunks) | the intermediate tile]
         uint32_t bl = bt_lo0, acc = 0;
-        uint32_t al = ext_lo0;
+        uint32_t al = ext_lo0 + (uint32_t)eb * (uint32_t)(a.ext_planes * a.TM);     // 16-byte units: planes x TM pixels per buffer
         for (int kk = 0; kk < (a.ext_planes >> 1); ++kk, al += 2u * (uint32_t)a.TM, bl += 2u * (uint32_t)tnp) {
 #pragma unroll
           for (int r = 0; r < R; ++r)
@@ -563,7 +608,7 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
         }
         tc_commit(&bars->tail_full[tb]);
         tc_commit(&bars->mid_empty);
-        if (a.ext_planes) tc_commit(&bars->ext_empty);
+        if (a.ext_planes) tc_commit(&bars->ext_empty[eb]);
       }
       __syncwarp();
     };
@@ -680,7 +725,9 @@ bool plan(const ConvParams &p, int num_sms, RArgs &a) {
   a.ext_planes = ext_c / 8;
   a.bt_bytes = tail ? (uint32_t)((size_t)(p.npad + ext_c) * tnp * 2) : 0u;
   // fused tail: the FP16 intermediate tile [cout/8][TM][8] (and the tail's other input planes) stay in shared memory
-  auto tail_bytes = [&](int R) { return tail ? (size_t)a.bt_bytes + (size_t)(p.npad + ext_c) * 128 * R * 2 + 256 : (size_t)0; };
+  // (two buffers for the tail's other input planes when they fit: their load then runs a tile ahead)
+  int ext_stages = 1;
+  auto tail_bytes = [&](int R) { return tail ? (size_t)a.bt_bytes + (size_t)(p.npad + ext_c * ext_stages) * 128 * R * 2 + 256 : (size_t)0; };
   const size_t misc = (size_t)p.npad * 4 + (size_t)tnp * 4 + sizeof(Bars) + 1024 + 256;
   const int halo = p.k == 3 ? (s2 ? a.Wp + 1 : 2 * a.Wp + 2) : 0;
   // Bulk copies run fastest when source, destination and size are multiples of 128 bytes (8
@@ -694,15 +741,20 @@ bool plan(const ConvParams &p, int num_sms, RArgs &a) {
   int best_R = 0;
   a.b_stream = 0;
   static const int rmax_env = getenv("IRMV_RMAX") ? atoi(getenv("IRMV_RMAX")) : 4;   // tuning knob
-  for (int R = 4; R >= 1; R >>= 1) {
+  static const bool ext2_env = !getenv("IRMV_EXT1");
+  for (int R = 4; R >= 1 && !best_R; R >>= 1) {
     if (R > rmax_env) continue;
     if (2 * R * (p.npad + tnp) > 512) continue;
-    if (a.b_bytes + tail_bytes(R) + 2 * stage_bytes(R) + misc > (size_t)SMEM_BUDGET) continue;
     long long tiles = (Mr + 128 * R - 1) / (128 * R);
     if (R > 1 && tiles < 2LL * num_sms) continue;    // keep every SM busy at small batch
-    best_R = R;
-    break;
+    for (ext_stages = (ext_c && ext2_env) ? 2 : 1; ext_stages >= 1; --ext_stages) {
+      if (a.b_bytes + tail_bytes(R) + 2 * stage_bytes(R) + misc > (size_t)SMEM_BUDGET) continue;
+      best_R = R;
+      break;
+    }
   }
+  if (ext_stages < 1) ext_stages = 1;
+  a.ext_stages = ext_stages;
   if (!best_R && tail) return false;                 // a fused tail needs resident weights
   if (!best_R && !getenv("IRMV_NO_BSTREAM")) {
     // weights do not fit next to two activation stages: stream them chunk by chunk.  Larger tiles
@@ -764,7 +816,7 @@ bool plan(const ConvParams &p, int num_sms, RArgs &a) {
   a.off_b = (uint32_t)((size_t)a.stages * a.a_stage_bytes);
   a.off_mid = (uint32_t)((a.off_b + b_smem + 127u) & ~(size_t)127u);
   a.off_ext = a.off_mid + (tail ? (uint32_t)((size_t)p.npad * a.TM * 2) : 0u);
-  a.off_bt = a.off_ext + (uint32_t)((size_t)ext_c * a.TM * 2);
+  a.off_bt = a.off_ext + (uint32_t)((size_t)ext_c * a.ext_stages * a.TM * 2);
   a.off_bias = (uint32_t)((a.off_bt + a.bt_bytes + 127u) & ~(size_t)127u);
   a.off_tbias = a.off_bias + (uint32_t)p.npad * 4;
   a.off_bars = (a.off_tbias + (uint32_t)tnp * 4 + 15u) & ~15u;
