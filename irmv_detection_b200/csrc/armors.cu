@@ -37,7 +37,8 @@ constexpr int kRows = 256;             // ... and up to this many rows (per-warp
 constexpr int kMaxRows = 1088;         // ROI height limit of the global-scratch path
 constexpr int kHullSmem = 2 * kRows + 2, kHullGlobal = 2 * kMaxRows + 2;   // a row adds at most two hull vertices
 constexpr int kCandCap = 64;         // ROIs with at most this many start candidates spread them over the warps
-constexpr int kScratchSlots = 64;      // global scratch slots shared by the CTAs that meet a large ROI
+// (large ROIs use a global scratch slot per CTA: with 64 shared slots behind locks the slots, not the SMs,
+// limited the stage when most boxes are large -- 15 ms per 6400 random-init boxes)
 constexpr unsigned kFull = 0xffffffffu;
 
 struct LightRec {
@@ -608,23 +609,13 @@ __global__ void __launch_bounds__(kThreads, 3) extract_armors_kernel(ArmorParams
     const bool large = words_roi > kSmemWords || rh > kRows;
     if (tid == 0) {
       sh.nbest = 0; sh.lock = 0; sh.slot = -1; sh.ncand = 0;
-      if (large) {                       // take one of the global scratch slots
-        int sl = blockIdx.x % kScratchSlots;
-        while (atomicCAS(p.slot_locks + sl, 0, 1) != 0) sl = (sl + 1) % kScratchSlots;
-        __threadfence();
-        sh.slot = sl;
-      }
+      if (large) sh.slot = blockIdx.x;   // this CTA's own global scratch slot
     }
     __syncthreads();
     const uint8_t *frame = base + (size_t)f * frame_bytes;
     if (large) {
       roi_body<true>(sh, p, p.scratch + (size_t)sh.slot * p.scratch_words_per_cta, frame, W, H, bayer, rx, ry, rw, rh, min_x,
                      min_y, item, out, tid, lane, warp);
-      __syncthreads();
-      if (tid == 0) {
-        __threadfence();
-        atomicExch(p.slot_locks + sh.slot, 0);
-      }
     } else {
       roi_body<false>(sh, p, nullptr, frame, W, H, bayer, rx, ry, rw, rh, min_x, min_y, item, out, tid, lane, warp);
     }
@@ -659,9 +650,9 @@ __global__ void mask_pose_ok_kernel(const ArmorOut *armors, int total, uint8_t *
 
 int armors_grid(int num_sms) { return num_sms * 3; }
 
-// scratch layout: [kScratchSlots lock words, padded to 64 words][kScratchSlots slots]
+// scratch layout: [64 words, unused][one slot per CTA of the grid]
 size_t armors_scratch_words_per_cta(int src_w, int src_h) { return slot_words(src_w, src_h); }
-size_t armors_scratch_total_words(int src_w, int src_h) { return 64 + (size_t)kScratchSlots * slot_words(src_w, src_h); }
+size_t armors_scratch_total_words(int src_w, int src_h, int grid) { return 64 + (size_t)grid * slot_words(src_w, src_h); }
 
 cudaError_t launch_extract_armors(const ArmorParams &p, cudaStream_t s) {
   if (p.src_h > kMaxRows - 2 || p.src_w > 32766) return cudaErrorInvalidValue;

@@ -241,7 +241,7 @@ struct ArmorParams {
   float min_ratio, max_ratio, max_angle;
   double min_small, max_small, min_large, max_large;
   ArmorOut *out;                        // [n][max_det]
-  int *slot_locks;                      // kScratchSlots lock words (zero = free): the head of the scratch allocation
+  int *slot_locks;                      // head of the scratch allocation (64 words, unused since every CTA owns a slot)
   uint32_t *scratch;                    // slots for ROIs that do not fit in shared memory (scratch allocation + 64 words)
   size_t scratch_words_per_cta;         // words per slot
   int grid;
@@ -249,7 +249,7 @@ struct ArmorParams {
 };
 int armors_grid(int num_sms);
 size_t armors_scratch_words_per_cta(int src_w, int src_h);
-size_t armors_scratch_total_words(int src_w, int src_h);   // allocate this many words, zeroed once
+size_t armors_scratch_total_words(int src_w, int src_h, int grid);   // allocate this many words (one slot per CTA of the grid)
 cudaError_t launch_extract_armors(const ArmorParams &p, cudaStream_t s);
 // armor corners -> PnP quads in the calibration frame; slots without an armor get a fixed valid quad
 cudaError_t launch_quads_from_armors(const ArmorOut *armors, int total, float sx, float sy, float *pts, float *centers, cudaStream_t s);

@@ -1759,7 +1759,7 @@ int irmv_engine_enable_armors(irmv_engine *e, const irmv_armor_params *prm) {
   IRMV_CUDA(cudaSetDevice(e->cfg.device));
   IRMV_CUDA(cudaDeviceSynchronize());
   const size_t slots = (size_t)e->S * e->cfg.max_det;
-  const size_t words = armors_scratch_total_words(e->cfg.src_width, e->cfg.src_height);
+  const size_t words = armors_scratch_total_words(e->cfg.src_width, e->cfg.src_height, armors_grid(e->num_sms));
   for (auto &ln : e->lanes) {
     if (!ln.armors) {
       if (!lane_alloc(ln, (void **)&ln.armors, slots * sizeof(ArmorOut)) || !lane_alloc(ln, (void **)&ln.armor_scratch, words * 4)) return 3;
@@ -1841,7 +1841,7 @@ int irmv_extract_armors(const uint8_t *frames, int frames_on_device, int nframes
     hs[i] = boxes[i].score; hc[i] = boxes[i].class_id;
   }
   const int grid = armors_grid(prop.multiProcessorCount);
-  const size_t wpc = armors_scratch_words_per_cta(src_w, src_h), wtotal = armors_scratch_total_words(src_w, src_h);
+  const size_t wpc = armors_scratch_words_per_cta(src_w, src_h), wtotal = armors_scratch_total_words(src_w, src_h, grid);
   int rc = 0;
   auto body = [&]() -> int {
     if (!frames_on_device) {
