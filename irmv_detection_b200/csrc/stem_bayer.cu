@@ -32,13 +32,18 @@ namespace irmv {
 namespace {
 
 constexpr int SW = 1280;                 // source width handled by this kernel (2 * kNet)
-constexpr int RP = 16 + SW + 16;         // staged raw row: [16 B apron | row | 16 B apron]
+constexpr int FMT_BAYER = 0, FMT_BAYER_REDCOL = 1, FMT_RGB = 2, FMT_BGR = 3;
+constexpr int row_pitch(int fmt) { return 16 + (fmt >= FMT_RGB ? 3 * SW : SW) + 16; }   // staged raw row: [16 B apron | row | 16 B apron]
 constexpr int PITCHW = 965;              // tile row pitch in 32-bit words (641 px * 6 B = 3846 B -> 962 words + skew)
 constexpr int OWID = kNet / 2;           // conv0 output side, 320
 constexpr int NWARPS = OWID / 16;        // 20: one warp per 16-pixel column block of the conv0 output
 constexpr int NTHREADS = NWARPS * 32;    // 640
-constexpr int OROWS = 8;                 // conv0 output rows per CTA
-constexpr int NIR = 2 * OROWS + 1;       // network-input rows of the strip (one halo row on top)
+// conv0 output rows per CTA (template parameter OROWS): 8 for Bayer sources (2 CTAs per SM), 4 for packed
+// 3-byte sources (their staged rows are three times as long); network-input rows of a strip = 2*OROWS + 1
+// (one halo row on top).
+// FMT: 0 / 1 = Bayer with the needed columns on non-red / red columns, 2 = packed u8x3 passed through (the
+// reference: whatever byte order is in the buffer goes to the net, src/yolo_engine.cpp:186-199), 3 = packed with R and B swapped.
+constexpr int orows_for(int fmt) { return fmt >= FMT_RGB ? 4 : 8; }
 
 struct RowTab { int off; uint32_t w_lo, w_hi; int flags; };   // flags: 1 = lo is a site row, 2 = conv padding row
 
@@ -60,10 +65,10 @@ struct StemBayerArgs {
 //              and bias, exact since it is a power of two)
 //   TAB_LUT    lerp table: entry x (the lerp numerator, < lut_n) = FP16(floor(x / 2Q) / 255)
 //   tab_strip  per strip of OROWS output rows: {vlo, nr, 0, 0} + RowTab[NIR] (sampling parameters per
-//              network-input row: byte offset of source row lo-1 in the staged window, the two vertical
-//              weights (doubled, so the numerator is the byte offset into the FP16 table), flags)
+//              network-input row: byte offset of source row lo-1 (Bayer) / lo (packed) in the staged window, the
+//              two vertical weights (doubled, so the numerator is the byte offset into the FP16 table), flags)
 constexpr int TAB_BFRAG = 0, TAB_BIAS = 256, TAB_LUT = 272;   // offsets in 32-bit words
-constexpr int STRIP_WORDS = 4 + 4 * NIR;
+constexpr int strip_words(int orows) { return 4 + 4 * (2 * orows + 1); }
 
 __host__ __device__ inline int reflect101(int i, int n) {
   if (i < 0) i = -i;
@@ -95,8 +100,11 @@ __device__ __forceinline__ Px3 unpack(const uint32_t *rowj) {
 }
 
 // OUT1 / OUT2: write the normal layout / the parity-split twin (at least one of them)
-template <bool ROT, bool RED_COL, bool OUT1, bool OUT2>
+template <bool ROT, int FMT, bool OUT1, bool OUT2>
 __global__ void __launch_bounds__(NTHREADS, 2) stem_bayer2x_kernel(const __grid_constant__ StemBayerArgs a) {
+  constexpr int OROWS = orows_for(FMT), NIR = 2 * OROWS + 1, RP = row_pitch(FMT), STRIP_WORDS = strip_words(OROWS);
+  constexpr bool PACKED = FMT >= FMT_RGB, RED_COL = FMT == FMT_BAYER_REDCOL;
+  constexpr int SROW = PACKED ? 3 * SW : SW;          // bytes of a source row
   extern __shared__ __align__(16) uint8_t smem[];
   uint32_t *tile_w = reinterpret_cast<uint32_t *>(smem);                       // [NIR][PITCHW]
   uint8_t *lut = smem + (size_t)NIR * PITCHW * 4;                              // [lut_n] halves
@@ -108,25 +116,25 @@ __global__ void __launch_bounds__(NTHREADS, 2) stem_bayer2x_kernel(const __grid_
   const int sidx = a.rev ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
   const int n = a.rev ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y, oy0 = sidx * OROWS;
   const uint8_t *base = a.src_indirect ? *a.src_indirect : a.src;
-  const uint8_t *frame = base + (size_t)(a.frame0 + n) * ((size_t)H * SW);
+  const uint8_t *frame = base + (size_t)(a.frame0 + n) * ((size_t)H * SROW);
   const uint32_t *strip = a.tab + a.tab_strip + sidx * STRIP_WORDS;
 
   // ---- source rows of the strip: virtual rows [vlo, vlo + nr), slot = v - vlo, content = row reflect101(v)
   const int vlo = (int)strip[0], nr = (int)strip[1];
   const bool aligned = ((size_t)frame & 15) == 0;
-  for (int r = warp; r < nr; r += NWARPS) {        // a warp stages whole rows: 80 chunks of 16 bytes
-    const uint8_t *g = frame + (size_t)min(reflect101(vlo + r, H), H - 1) * SW;
+  for (int r = warp; r < nr; r += NWARPS) {        // a warp stages whole rows in 16-byte chunks
+    const uint8_t *g = frame + (size_t)min(reflect101(vlo + r, H), H - 1) * SROW;
     uint8_t *d = raw + (size_t)r * RP + 16;
     if (aligned) {
       const uint32_t dst = (uint32_t)__cvta_generic_to_shared(d);
 #pragma unroll
-      for (int c = 0; c < 3; ++c)
-        if (c < 2 || lane < SW / 16 - 64)
+      for (int c = 0; c < (SROW / 16 + 31) / 32; ++c)
+        if ((c + 1) * 32 <= SROW / 16 || c * 32 + lane < SROW / 16)
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)(c * 32 + lane) * 16u), "l"(g + (c * 32 + lane) * 16) : "memory");
     } else {                                        // caller's frames are not 16-byte aligned: plain byte copies
-      for (int c = lane; c < SW; c += 32) d[c] = g[c];
+      for (int c = lane; c < SROW; c += 32) d[c] = g[c];
     }
-    if (lane == 0) { d[-1] = g[1]; d[SW] = g[SW - 2]; }   // mirrored columns -1 and W (reflect-101)
+    if (!PACKED && lane == 0) { d[-1] = g[1]; d[SW] = g[SW - 2]; }   // mirrored columns -1 and W (reflect-101) for the demosaic
   }
   {
     const uint32_t *gl = a.tab + TAB_LUT;
@@ -167,6 +175,31 @@ __global__ void __launch_bounds__(NTHREADS, 2) stem_bayer2x_kernel(const __grid_
         *reinterpret_cast<uint16_t *>(dst + 10) = 0;
         continue;
       }
+      uint32_t xr, xg, xb;
+      if (PACKED) {
+        // packed u8x3: the two needed pixels of unit j sit in the 12-byte group [12j, 12j + 12) of the row:
+        // ROT pixels 4j+1 (low lane) and 4j+3 (high lane), otherwise 4j and 4j+2.  No demosaic: a
+        // network-input value is the vertical lerp of the two source rows lo and lo + 1.
+        const uint32_t *ra = reinterpret_cast<const uint32_t *>(raw + rt.off) + 3 * j;
+        uint32_t v[2][3];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const uint32_t W0 = ra[q * (RP / 4)], W1 = ra[q * (RP / 4) + 1], W2 = ra[q * (RP / 4) + 2];
+          if (ROT) {
+            v[q][0] = (W0 >> 24) | ((W2 << 8) & 0x00ff0000u);
+            v[q][1] = (W1 & 0xffu) | (W2 & 0x00ff0000u);
+            v[q][2] = ((W1 >> 8) & 0xffu) | ((W2 >> 8) & 0x00ff0000u);
+          } else {
+            v[q][0] = (W0 & 0xffu) | (W1 & 0x00ff0000u);
+            v[q][1] = ((W0 >> 8) & 0xffu) | ((W1 >> 8) & 0x00ff0000u);
+            v[q][2] = ((W0 >> 16) & 0xffu) | ((W2 << 16) & 0x00ff0000u);
+          }
+        }
+        const uint32_t x0 = v[0][0] * rt.w_lo + v[1][0] * rt.w_hi + QQ;
+        const uint32_t x1 = v[0][1] * rt.w_lo + v[1][1] * rt.w_hi + QQ;
+        const uint32_t x2 = v[0][2] * rt.w_lo + v[1][2] * rt.w_hi + QQ;
+        xr = FMT == FMT_BGR ? x2 : x0; xg = x1; xb = FMT == FMT_BGR ? x0 : x2;
+      } else {
       const uint32_t *rp = rawj + (rt.off >> 2);
       const Px3 r0 = unpack<ROT>(rp), r1 = unpack<ROT>(rp + RP / 4), r2 = unpack<ROT>(rp + 2 * (RP / 4)),
                 r3 = unpack<ROT>(rp + 3 * (RP / 4));
@@ -192,9 +225,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) stem_bayer2x_kernel(const __grid_
       // red row (RED_COL == false): R horizontal, B vertical; on a blue row: R vertical, B horizontal
       const uint32_t RS = RED_COL ? cS : diag, BS = RED_COL ? diag : cS;
       const uint32_t RG = RED_COL ? vert : horiz, BG = RED_COL ? horiz : vert;
-      const uint32_t xr = RS * wS + RG * wG + QQ;
-      const uint32_t xg = cross * wS + cG * wG + QQ;
-      const uint32_t xb = BS * wS + BG * wG + QQ;
+      xr = RS * wS + RG * wG + QQ;
+      xg = cross * wS + cG * wG + QQ;
+      xb = BS * wS + BG * wG + QQ;
+      }
       const uint32_t r_l = lut_ld(xr & 0xffffu), r_h = lut_ld(xr >> 16);
       const uint32_t g_l = lut_ld(xg & 0xffffu), g_h = lut_ld(xg >> 16);
       const uint32_t b_l = lut_ld(xb & 0xffffu), b_h = lut_ld(xb >> 16);
@@ -290,43 +324,64 @@ __global__ void __launch_bounds__(NTHREADS, 2) stem_bayer2x_kernel(const __grid_
   }
 }
 
-int gcd_i(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
 
-template <bool ROT, bool RED_COL, bool OUT1, bool OUT2>
+template <bool ROT, int FMT, bool OUT1, bool OUT2>
 cudaError_t launch_o(const StemBayerArgs &a, size_t smem, cudaStream_t s) {
-  cudaError_t e = cudaFuncSetAttribute(stem_bayer2x_kernel<ROT, RED_COL, OUT1, OUT2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(stem_bayer2x_kernel<ROT, FMT, OUT1, OUT2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  dim3 grid(OWID / OROWS, a.n);
-  stem_bayer2x_kernel<ROT, RED_COL, OUT1, OUT2><<<grid, NTHREADS, smem, s>>>(a);
+  dim3 grid(OWID / orows_for(FMT), a.n);
+  stem_bayer2x_kernel<ROT, FMT, OUT1, OUT2><<<grid, NTHREADS, smem, s>>>(a);
   return cudaGetLastError();
 }
 
-template <bool ROT, bool RED_COL>
+template <bool ROT, int FMT>
 cudaError_t launch_t(const StemBayerArgs &a, size_t smem, cudaStream_t s) {
-  if (a.out && a.out2) return launch_o<ROT, RED_COL, true, true>(a, smem, s);
-  if (a.out2) return launch_o<ROT, RED_COL, false, true>(a, smem, s);
-  if (a.out) return launch_o<ROT, RED_COL, true, false>(a, smem, s);
+  if (a.out && a.out2) return launch_o<ROT, FMT, true, true>(a, smem, s);
+  if (a.out2) return launch_o<ROT, FMT, false, true>(a, smem, s);
+  if (a.out) return launch_o<ROT, FMT, true, false>(a, smem, s);
   return cudaErrorInvalidValue;
 }
 
-// staged-row capacity for a source of height H (H / 640 = P / Q)
-int nr_max_for(int P, int Q) { return (2 * OROWS * P + Q - 1) / Q + 6; }
+template <bool ROT>
+cudaError_t launch_f(int fmt, const StemBayerArgs &a, size_t smem, cudaStream_t s) {
+  switch (fmt) {
+    case FMT_BAYER: return launch_t<ROT, FMT_BAYER>(a, smem, s);
+    case FMT_BAYER_REDCOL: return launch_t<ROT, FMT_BAYER_REDCOL>(a, smem, s);
+    case FMT_RGB: return launch_t<ROT, FMT_RGB>(a, smem, s);
+    default: return launch_t<ROT, FMT_BGR>(a, smem, s);
+  }
+}
+
+int gcd_i(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
+
+// kernel format of a source (chan_order: IRMV_CH_*; needed columns are odd with rot180, even without)
+int format_of(int chan_order, int rotate180) {
+  if (chan_order == 0) return FMT_RGB;
+  if (chan_order == 1) return FMT_BGR;
+  const int red_x = (chan_order == 3 || chan_order == 4) ? 1 : 0;       // BGGR, GRBG: red on odd columns
+  return ((rotate180 ? 1 : 0) == red_x) ? FMT_BAYER_REDCOL : FMT_BAYER;
+}
+
+// staged-row capacity of a strip for a source of height H (H / 640 = P / Q)
+int nr_max_for(int P, int Q, int fmt) { return (2 * orows_for(fmt) * P + Q - 1) / Q + (fmt >= FMT_RGB ? 4 : 6); }
 
 }  // namespace
 
-// The fast path applies to: Bayer source, width 1280, height >= 640 with H/640 = P/Q, Q <= 16,
-// reference resize (corner-aligned stretch) and the 8-bit intermediate.
+// The fast path applies to: 8-bit Bayer or packed u8x3 source of width 1280, height >= 640 with
+// H/640 = P/Q, Q <= 16, reference resize (corner-aligned stretch) and the 8-bit intermediate.
 bool stem_bayer2x_applies(const PreprocessParams &p) {
-  if (p.chan_order < 2 || p.src_w != SW || p.resize_mode != 0 || !p.quantize_u8 || p.src_h < kNet || p.src_h > 4096) return false;
+  if (p.chan_order < 0 || p.chan_order > 5 || p.src_w != SW || p.resize_mode != 0 || !p.quantize_u8 || p.src_h < kNet || p.src_h > 4096) return false;
   const int g = gcd_i(p.src_h, kNet);
   return kNet / g <= 16;
 }
 
 // Host side of the table block (layout above): conv0 weights w[16][9 taps][3] and bias[16] as the engine
-// keeps them (FP32 values that are FP16-exact), for a source of height src_h, rotated or not, with the
-// red sample on rows of parity red_y and the needed columns on red columns or not.
+// keeps them (FP32 values that are FP16-exact), for a source of height src_h in the given format and rotation.
 std::vector<uint32_t> stem_bayer2x_tables(const float *w, const float *bias, int src_h, int chan_order, int rotate180) {
   const int g0 = gcd_i(src_h, kNet), P = src_h / g0, Q = kNet / g0, H = src_h;
+  const int fmt = format_of(chan_order, rotate180);
+  const bool packed = fmt >= FMT_RGB;
+  const int OROWS = orows_for(fmt), NIR = 2 * OROWS + 1, RP = row_pitch(fmt), STRIP_WORDS = strip_words(OROWS);
   const int lut_n = 2 * Q * 255 + Q + 1;
   const int tab_strip = TAB_LUT + (lut_n + 7) / 8 * 4;
   const int nstrips = OWID / OROWS;
@@ -357,17 +412,17 @@ std::vector<uint32_t> stem_bayer2x_tables(const float *w, const float *bias, int
   }
   const bool rot = rotate180 != 0;
   const int red_y = (chan_order == 3 || chan_order == 5) ? 1 : 0;       // BGGR, GBRG: red on odd rows
-  const int red_x = (chan_order == 3 || chan_order == 4) ? 1 : 0;       // BGGR, GRBG: red on odd columns
-  const bool red_col = ((rot ? 1 : 0) == red_x);                        // needed columns: odd with rot180, even without
+  const bool red_col = fmt == FMT_BAYER_REDCOL;
+  const int halo = packed ? 0 : 1;                                      // demosaic reads one row above / below
   for (int sidx = 0; sidx < nstrips; ++sidx) {
     uint32_t *st = tab.data() + tab_strip + sidx * STRIP_WORDS;
     const int iy0 = 2 * sidx * OROWS - 1;
     const int ry_min = ((iy0 > 0 ? iy0 : 0) * P) / Q;
     int ry_max = ((iy0 + NIR - 1) * P) / Q + 1;
     if (ry_max > H - 1) ry_max = H - 1;
-    const int vlo = (rot ? H - 1 - ry_max : ry_min) - 1;
+    const int vlo = (rot ? H - 1 - ry_max : ry_min) - halo;
     st[0] = (uint32_t)vlo;
-    st[1] = (uint32_t)(ry_max - ry_min + 4);
+    st[1] = (uint32_t)(ry_max - ry_min + 2 + 2 * halo);             // rows lo - halo .. lo + 1 + halo of every input row
     for (int r = 0; r < NIR; ++r) {
       RowTab rt{0, 0u, 0u, 2};
       const int iy = iy0 + r;
@@ -381,8 +436,8 @@ std::vector<uint32_t> stem_bayer2x_tables(const float *w, const float *bias, int
         rt.w_lo = 2u * (uint32_t)(sy0 <= sy1 ? wA : wB);
         rt.w_hi = 2u * (uint32_t)(sy0 <= sy1 ? wB : wA);
         // a "site" row holds the red or blue sample at the needed columns, a "green" row the green one
-        rt.flags = ((((lo & 1) == red_y) == red_col) ? 1 : 0);
-        rt.off = (lo - 1 - vlo) * RP + 16;
+        rt.flags = (!packed && (((lo & 1) == red_y) == red_col)) ? 1 : 0;
+        rt.off = (lo - halo - vlo) * RP + 16;
       }
       memcpy(st + 4 + 4 * r, &rt, 16);
     }
@@ -396,17 +451,14 @@ cudaError_t launch_stem_bayer2x(const PreprocessParams &p, int frame0, const uin
   a.src = p.src; a.src_indirect = p.src_indirect; a.n = p.n; a.H = p.src_h; a.frame0 = frame0; a.rev = p.rev_order;
   const int g = gcd_i(p.src_h, kNet);
   const int P = p.src_h / g, Q = kNet / g;
-  const int red_x = (p.chan_order == 3 || p.chan_order == 4) ? 1 : 0;   // BGGR, GRBG: red on odd columns
+  const int fmt = format_of(p.chan_order, p.rotate180);
   a.Q = Q; a.lut_n = 2 * Q * 255 + Q + 1;
   a.tab_strip = TAB_LUT + (a.lut_n + 7) / 8 * 4;
   a.tab = tab; a.out = out; a.out_ps = out_ps; a.out2 = out2; a.out2_ps = out2_ps;
-  const size_t smem = (((size_t)NIR * PITCHW * 4 + (size_t)a.lut_n * 2 + 15) & ~(size_t)15) + (size_t)nr_max_for(P, Q) * RP;
+  const size_t smem = (((size_t)(2 * orows_for(fmt) + 1) * PITCHW * 4 + (size_t)a.lut_n * 2 + 15) & ~(size_t)15) +
+                      (size_t)nr_max_for(P, Q, fmt) * row_pitch(fmt);
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
-  // needed columns: W - 1 - 2*ix (odd) with rot180, 2*ix (even) without
-  const bool rot = p.rotate180 != 0;
-  const bool red_col = ((rot ? 1 : 0) == red_x);
-  if (rot) return red_col ? launch_t<true, true>(a, smem, s) : launch_t<true, false>(a, smem, s);
-  return red_col ? launch_t<false, true>(a, smem, s) : launch_t<false, false>(a, smem, s);
+  return p.rotate180 ? launch_f<true>(fmt, a, smem, s) : launch_f<false>(fmt, a, smem, s);
 }
 
 }  // namespace irmv

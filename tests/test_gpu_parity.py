@@ -646,13 +646,15 @@ def test_fused_stem_matches_unfused(frames, weights_seed0):
     a.close(); b.close()
 
 
-@pytest.mark.parametrize("chan", [0, 2, 3, 4, 5])
-def test_fused_stem_input_pixels_exact(base_image, tmp_path, chan):
+@pytest.mark.parametrize("chan,rotate", [(0, True), (1, True), (2, True), (3, True), (4, True), (5, True),
+                                         (0, False), (1, False), (2, False), (5, False)])
+def test_fused_stem_input_pixels_exact(base_image, tmp_path, chan, rotate):
     """The fused stem never materialises the network input, so probe it through conv0: with
     one-hot weights output channel 3*t + c is SiLU(input[c] at tap t) for the four taps
     (ky, kx) in {1,2}^2, which together visit every input pixel.  A single 8-bit step of the
     preprocess (1/255 = 3.9e-3) would move the output by >= 2e-3; tanh.approx + FP16 rounding
-    stay below 1.5e-3.  Covers the Bayer fast path (integer horizontal scale) and packed RGB."""
+    stay below 1.5e-3.  Covers the camera-case stem (csrc/stem_bayer.cu) for all four Bayer patterns, packed RGB
+    and BGR, with and without the 180-degree rotation."""
     import irmv_detection_b200 as irmv
     from irmv_detection_b200 import synth, weights
     from oracle import preprocess_ref as PR
@@ -672,11 +674,11 @@ def test_fused_stem_input_pixels_exact(base_image, tmp_path, chan):
         src = synth.bayer_from_rgb(rgb, {2: "RGGB", 3: "BGGR", 4: "GRBG", 5: "GBRG"}[chan])
     else:
         src = rgb
-    eng = irmv.YoloEngine(wp, (1280, 1024), chan_order=chan, max_batch=2, sub_batch=2)
+    eng = irmv.YoloEngine(wp, (1280, 1024), chan_order=chan, rotate180=rotate, max_batch=2, sub_batch=2)
     eng.detect_batch(src)
     m0 = eng.read_tensor("m0").astype(np.float64)                  # [2, 320, 320, 16]
     for f in range(2):
-        ref, _ = PR.preprocess_fp16(src[f], chan)                   # [3, 640, 640] fp16
+        ref, _ = PR.preprocess_fp16(src[f], chan, rotate)           # [3, 640, 640] fp16
         x = np.pad(ref.astype(np.float64), ((0, 0), (1, 1), (1, 1)))
         for t, (ky, kx) in enumerate(taps):
             want = x[:, ky:ky + 640:2, kx:kx + 640:2]                # input (2y + ky - 1, 2x + kx - 1)
