@@ -22,7 +22,7 @@
 // A CTA owns a full-width strip of OROWS conv0 output rows: staging is whole 1280-byte rows
 // (16-byte cp.async, always aligned), the tile is [2*OROWS+1][641 px][3] halves, conv0 runs as
 // mma.sync m16n8k16 with K ordered (ky, 3 px x 3 ch + 1 pad) so that every A fragment register is one
-// aligned 32-bit shared-memory load.
+// aligned, bank-conflict-free 32-bit shared-memory load.
 #include <cstring>
 #include <vector>
 
@@ -260,8 +260,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) stem_bayer2x_kernel(const __grid_
   for (int s2 = 0; s2 < 2; ++s2)
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const int kw = 8 * s2 + 4 * h + t, ky = kw / 5, tp = kw - ky * 5;
-      off[s2][h] = ky < 3 ? ky * PITCHW + tp : 0;
+      // K slot (s2, h, t) -> tile word: the four lanes t of one load read ONE tile row (a load that mixes rows
+      // ky and ky+1 is a 2-way bank conflict for any row pitch): slots (0,0) (0,1) (1,0) = words 0..3 of rows
+      // ky = 0, 1, 2; slot (1,1) = word 4 of rows 0, 1, 2 (banks of different residues mod 3) + one pad lane
+      const int ky = (s2 == 1 && h == 1) ? (t < 3 ? t : 0) : 2 * s2 + h, tp = (s2 == 1 && h == 1) ? 4 : t;
+      off[s2][h] = ky * PITCHW + tp;
     }
   float hbias[2][2];                       // bias / 2
   {
@@ -393,7 +396,9 @@ std::vector<uint32_t> stem_bayer2x_tables(const float *w, const float *bias, int
         for (int h = 0; h < 2; ++h) {
           uint16_t v[2];
           for (int e = 0; e < 2; ++e) {
-            const int k = 16 * s2 + 2 * t + 8 * h + e, ky = k / 10, j = k - ky * 10;
+            // same K slot -> (ky, j) map as the kernel's `off` table; j = 9 and the pad lane carry zero weights
+            const bool last = s2 == 1 && h == 1;
+            const int ky = last ? t : 2 * s2 + h, j = last ? 8 + e : 2 * t + e;
             const float wv = (ky < 3 && j < 9) ? 0.5f * w[(nt * 8 + g) * 27 + ky * 9 + j] : 0.f;
             const __half hv = __float2half_rn(wv);
             memcpy(&v[e], &hv, 2);
