@@ -96,7 +96,9 @@ typedef struct irmv_engine_config {
   int32_t reserved[8];      /* reserved[0] != 0: run preprocess and conv0 as separate kernels (the network
                              * input tensor is then materialised and readable as tap "input");
                              * reserved[1] != 0: do not fuse 1x1 convs into their producers (every module
-                             * output is then materialised and readable through irmv_engine_read_tensor) */
+                             * output is then materialised and readable through irmv_engine_read_tensor);
+                             * reserved[2] != 0: ShuffleNetV2 variant: one launch per convolution instead of one fused
+                             * kernel per unit */
 } irmv_engine_config;
 
 /* One armor as IrmDetector::extract_armors builds it (src/irm_detector.cpp:292-355): slot i of a frame

@@ -184,6 +184,41 @@ struct DwParams {
 };
 cudaError_t launch_dwconv3x3(const DwParams &p, cudaStream_t s);
 
+// ---------------------------------------------------------------- fused ShuffleNetV2 units (shuffle_unit.cu)
+// The unit's constants as ONE blob the kernel fetches with a single bulk copy (byte offsets, all 16-byte
+// aligned): 1x1 weights as [h][K + 8] halves (pw1: cin -> h, pw2: h -> h, down only: branch-1 1x1 cin -> h),
+// depthwise weights as FP32 [planes][9][8] (dw on the 1x1 -> dw -> 1x1 path, down only: dwa on the input),
+// FP32 biases b1[h] b2[h] ba[h] dwb[h] dwab[cin].
+struct ShuffleBlobLayout { int w1, w2, wa, dw, dwa, bias, bytes; };
+__host__ __device__ inline ShuffleBlobLayout shuffle_blob_layout(int down, int cin, int h) {
+  ShuffleBlobLayout L;
+  L.w1 = 0;
+  L.w2 = L.w1 + h * (cin + 8) * 2;
+  L.wa = L.w2 + h * (h + 8) * 2;
+  L.dw = L.wa + (down ? h * (cin + 8) * 2 : 0);
+  L.dwa = L.dw + (h / 8) * 72 * 4;
+  L.bias = L.dwa + (down ? (cin / 8) * 72 * 4 : 0);
+  L.bytes = L.bias + (4 * h + cin) * 4;
+  return L;
+}
+struct ShuffleUnitParams {
+  int down;                      // 1: down unit (input grid 2H x 2W), 0: basic unit
+  const __half *in;              // plane 0 of the input (down: the previous stage / stem output; basic: the stage buffer read)
+  long long in_ps;
+  __half *out;                   // plane 0 of the stage buffer written
+  long long out_ps;
+  int B, H, W;                   // output grid
+  int cin, h;                    // input channels of the 1x1 convs on the input (basic: = h), half of the stage's channels
+  int first_plane, runs;         // basic: the planes of the right half (ConvSeg::runs); the left half lies one run before
+  const uint8_t *blob;           // shuffle_blob_layout(down, cin, h)
+  int TH;                        // output rows per tile (divides H)
+  int rev;
+  int num_sms;
+};
+size_t shuffle_unit_smem(const ShuffleUnitParams &p);
+int shuffle_unit_ctas_per_sm(const ShuffleUnitParams &p);
+cudaError_t launch_shuffle_unit(const ShuffleUnitParams &p, cudaStream_t s);
+
 // ---------------------------------------------------------------- SPPF pooling
 // in: planes [0, c/8) of `buf`; writes maxpool5, maxpool5^2, maxpool5^3 to the three following
 // groups of c/8 planes of the same tensor (ultralytics SPPF).

@@ -126,6 +126,9 @@ struct Spec { int cin, cout, k, stride, act, groups = 1; };
 struct ShuffleStage { int cin, cout, units; };
 // the four stride-2 stages of the ShuffleNetV2-style backbone (irmv_detection_b200/weights.py shuffle_stage_plan)
 const ShuffleStage kShuffleStages[4] = {{16, 32, 0}, {32, 64, 1}, {64, 128, 3}, {128, 256, 1}};
+// stages with half-width <= this run as one fused kernel per unit (shuffle_unit.cu); the last stage (h = 128 on
+// 20 x 20 maps) is weight-heavy and keeps one tcgen05 launch per convolution
+constexpr int kShuffleFuseMaxH = 64;
 
 std::vector<Spec> expected_specs(bool pose, int arch = kArchYolov8n) {
   std::vector<Spec> s;
@@ -326,8 +329,9 @@ struct Tensor {            // channel-blocked planar PR layout (common.cuh)
 };
 
 struct Op {
-  enum Kind { CONV, POOL, DW } kind = CONV;
+  enum Kind { CONV, POOL, DW, SHUF } kind = CONV;
   DwParams dw{};
+  ShuffleUnitParams su{};
   ConvParams cp{};
   bool raster = false;       // raster (halo-tile) kernel, else the per-tap gather kernel
   __half *pool_buf = nullptr;
@@ -468,6 +472,9 @@ struct irmv_engine {
   struct ShuffleUnit { int first_plane, runs; };  // planes a basic unit rewrites in place (ConvSeg::runs)
   std::vector<std::vector<ShuffleUnit>> sh_units; // per stage
   std::vector<std::vector<int>> sh_map;           // per stage: logical -> physical channel of the stage output
+  // fused units (shuffle_unit.cu): one constant blob (shuffle_blob_layout) per unit of the stages it serves, in execution order
+  std::vector<uint8_t *> sh_blobs;
+  bool sh_fused = true;                           // cfg.reserved[2] != 0: one launch per conv instead (unfused reference path)
   std::vector<Lane> lanes;
   cudaStream_t main_stream = nullptr;
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
@@ -672,6 +679,7 @@ void fuse_tails(irmv_engine *e, Lane &ln) {
       const Op &q = ln.ops[j];
       if (q.kind == Op::POOL) { other = overlaps(o0, o1, q.pool_buf, q.pool_buf + 4LL * (q.pC / 8) * q.pStride); continue; }
       if (q.kind == Op::DW) { other = overlaps(o0, o1, q.dw.in, q.dw.in + (long long)q.dw.planes * q.dw.in_ps); continue; }
+      if (q.kind == Op::SHUF) { other = overlaps(o0, o1, q.su.in, q.su.in + (long long)(q.su.down ? q.su.cin / 8 : q.su.h / 4) * q.su.in_ps); continue; }
       for (int sgi = 0; sgi < q.cp.nseg; ++sgi) {
         const ConvSeg &g = q.cp.seg[sgi];
         if (!q.cp.in_parity && overlaps(o0, o1, g.ptr, g.ptr + (long long)(g.c / 8) * g.pstride)) other = true;
@@ -722,7 +730,7 @@ bool build_lane(irmv_engine *e, Lane &ln) {
     // the down unit writes its two branches into the two halves, every basic unit rewrites the planes of
     // its "right half" in place (engine->sh_units: runs of planes), and split / concat / shuffle are the
     // channel map folded into the weights at load time (irmv_engine_create).
-    size_t di = 0;
+    size_t di = 0, bi = 0;
     const Tensor *prev = &ln.stem_out;
     Tensor stage_out[4];
     int hw = 320;
@@ -741,6 +749,51 @@ bool build_lane(irmv_engine *e, Lane &ln) {
       Tensor X, Ta, Tb, Tc, T1, T2;
       char nm[8];
       snprintf(nm, sizeof nm, "d%d", sgi + 1);
+      if (e->sh_fused && h <= kShuffleFuseMaxH) {
+        // one kernel per unit (shuffle_unit.cu); basic units ping-pong between two stage buffers (their
+        // depthwise conv reads a halo other CTAs may already have rewritten, so not in place)
+        Tensor XB;
+        if (!new_tensor(ln, S, oh, oh, st.cout, X) || (st.units && !new_tensor(ln, S, oh, oh, st.cout, XB))) return false;
+        static const int th_force = getenv("IRMV_UNIT_TH") ? atoi(getenv("IRMV_UNIT_TH")) : 0;
+        auto pick_th = [&](ShuffleUnitParams q) {                          // most rows per tile that still leave two CTAs per SM
+          for (int th : {8, 4, 2}) {
+            if (oh % th) continue;
+            q.TH = th;
+            if (th == th_force || (!th_force && shuffle_unit_ctas_per_sm(q) >= 2)) return th;
+          }
+          return 1;
+        };
+        Op op;
+        op.kind = Op::SHUF;
+        ShuffleUnitParams &q = op.su;
+        q.down = 1; q.in = prev->p; q.in_ps = prev->pstride; q.out = X.p; q.out_ps = X.pstride;
+        q.B = S; q.H = oh; q.W = oh; q.cin = st.cin; q.h = h; q.first_plane = 0; q.runs = 0;
+        q.blob = e->sh_blobs[bi++];
+        q.rev = 0; q.num_sms = e->num_sms;
+        q.TH = pick_th(q);
+        ln.ops.push_back(op);
+        ci += 3; di += 2;
+        Tensor *cur = &X, *oth = &XB;
+        for (int u = 0; u < st.units; ++u) {
+          const irmv_engine::ShuffleUnit &su = e->sh_units[sgi][u];
+          const int run_planes = su.runs ? (1 << (su.runs - 1)) : h / 8;
+          if (su.first_plane != run_planes) { set_error("internal: shuffle unit planes do not start one run in"); return false; }
+          Op ob;
+          ob.kind = Op::SHUF;
+          ShuffleUnitParams &r = ob.su;
+          r.down = 0; r.in = cur->p; r.in_ps = cur->pstride; r.out = oth->p; r.out_ps = oth->pstride;
+          r.B = S; r.H = oh; r.W = oh; r.cin = h; r.h = h; r.first_plane = su.first_plane; r.runs = su.runs;
+          r.blob = e->sh_blobs[bi++];
+          r.rev = 0; r.num_sms = e->num_sms;
+          r.TH = pick_th(r);
+          ln.ops.push_back(ob);
+          ci += 2; di += 1;
+          std::swap(cur, oth);
+        }
+        X = *cur;                                                          // the buffer that holds the stage output
+        X.cmap = e->sh_map[sgi];
+        ln.taps[nm] = X;
+      } else {
       if (!new_tensor(ln, S, oh, oh, st.cout, X) || !new_tensor(ln, S, oh, oh, st.cin, Ta) ||
           !new_tensor(ln, S, hw, hw, h, Tb) || !new_tensor(ln, S, oh, oh, h, Tc))
         return false;
@@ -760,6 +813,7 @@ bool build_lane(irmv_engine *e, Lane &ln) {
         add_conv(e, ln, *e->convs[ci++], {{&T2, 0, h, 0}}, oh, oh, X, su.first_plane * 8);  // pw2: T2 -> the same planes
         ln.ops.back().cp.out_runs = su.runs;
       }
+      }
       stage_out[sgi] = X;
       ln.taps[nm] = X;
       prev = &stage_out[sgi];
@@ -767,7 +821,7 @@ bool build_lane(irmv_engine *e, Lane &ln) {
     }
     for (size_t k = 1; k < ln.ops.size(); ++k)
       if (ln.ops[k].kind == Op::CONV && !ln.ops[k].raster) { set_error("internal: a ShuffleNetV2 1x1 conv does not fit the raster kernel"); return false; }
-    if (di != e->dws.size()) { set_error("internal: depthwise conv count mismatch"); return false; }
+    if (di != e->dws.size() || ci != 23) { set_error("internal: backbone conv count mismatch"); return false; }
     x4 = stage_out[1]; x6 = stage_out[2]; x8 = stage_out[3];
   } else {
   if (!new_tensor(ln, S, 160, 160, 32, t1, "m1")) return false;
@@ -902,6 +956,11 @@ int issue_replay(irmv_engine *e, Lane &ln, int n, cudaStream_t st, int *launches
       if (e->cfg.conv_impl == IRMV_CONV_DIRECT) IRMV_CUDA(launch_conv_direct(p, st));
       else if (op.raster) IRMV_CUDA(launch_conv_raster(p, e->num_sms, st));
       else IRMV_CUDA(launch_conv_tc(p, e->num_sms, st));
+    } else if (op.kind == Op::SHUF) {
+      ShuffleUnitParams q = op.su;
+      q.B = n;
+      q.rev = pingpong ? (seq & 1) : 0;
+      IRMV_CUDA(launch_shuffle_unit(q, st));
     } else if (op.kind == Op::DW) {
       DwParams d = op.dw;
       d.B = n;
@@ -917,7 +976,7 @@ int issue_replay(irmv_engine *e, Lane &ln, int n, cudaStream_t st, int *launches
       if (ce != cudaSuccess) {
         char buf[256];
         snprintf(buf, sizeof buf, "op %d (%s k=%d s=%d cin=%d cout=%d H=%d) failed: %s", cnt - 2,
-                 op.kind == Op::POOL ? "pool" : (op.kind == Op::DW ? "dw" : (op.raster ? "raster" : "gather")), op.cp.k, op.cp.stride, op.cp.cin,
+                 op.kind == Op::POOL ? "pool" : (op.kind == Op::DW ? "dw" : (op.kind == Op::SHUF ? "shuffle-unit" : (op.raster ? "raster" : "gather"))), op.cp.k, op.cp.stride, op.cp.cin,
                  op.cp.cout, op.cp.H, cudaGetErrorString(ce));
         set_error(buf);
         return 1;
@@ -1304,6 +1363,54 @@ int irmv_engine_create(const char *weights_path, const irmv_engine_config *cfg, 
       single(b + 1, 16, {16});
       single(b + 2, 16, {16});
     }
+  e->sh_fused = e->arch == kArchShuffleKpt && cfg->reserved[2] == 0 && !getenv("IRMV_NO_SHUFFLE_FUSE");
+  if (e->sh_fused) {
+    // convs[1 .. 22] are the backbone's 1x1 convs (3 per down unit: b1.pw, b2.pw1, b2.pw2; 2 per basic unit),
+    // dws[] its depthwise convs (2 per down unit: b1.dw, b2.dw; 1 per basic unit), both in execution order
+    size_t ci = 1, di = 0;
+    auto put_pw = [&](std::vector<uint8_t> &blob, int off, const HostConv &hc, int boff, int h) {
+      const int K = hc.cin_eff;
+      __half *w = reinterpret_cast<__half *>(blob.data() + off);
+      for (int n = 0; n < h; ++n)
+        for (int c = 0; c < K; ++c) w[(size_t)n * (K + 8) + c] = hc.w_plain[(size_t)n * hc.kpad + c];
+      memcpy(blob.data() + boff, hc.bias.data(), (size_t)h * 4);
+    };
+    auto put_dw = [&](std::vector<uint8_t> &blob, int off, const HostDw &d, int boff) {
+      float *w = reinterpret_cast<float *>(blob.data() + off);
+      for (size_t i = 0; i < d.w.size(); ++i) w[i] = __half2float(d.w[i]);
+      memcpy(blob.data() + boff, d.b.data(), d.b.size() * 4);
+    };
+    for (int sgi = 0; sgi < 4; ++sgi) {
+      const ShuffleStage &st = kShuffleStages[sgi];
+      const int h = st.cout / 2;
+      const bool fuse = h <= kShuffleFuseMaxH;
+      for (int u = -1; u < st.units; ++u) {
+        const bool down = u < 0;
+        if (fuse) {
+          const int cin = down ? st.cin : h;
+          const ShuffleBlobLayout L = shuffle_blob_layout(down, cin, h);
+          std::vector<uint8_t> blob(L.bytes, 0);
+          if (down) {
+            put_pw(blob, L.wa, *e->convs[ci], L.bias + 2 * h * 4, h);
+            put_pw(blob, L.w1, *e->convs[ci + 1], L.bias, h);
+            put_pw(blob, L.w2, *e->convs[ci + 2], L.bias + h * 4, h);
+            put_dw(blob, L.dwa, *e->dws[di], L.bias + 4 * h * 4);
+            put_dw(blob, L.dw, *e->dws[di + 1], L.bias + 3 * h * 4);
+          } else {
+            put_pw(blob, L.w1, *e->convs[ci], L.bias, h);
+            put_pw(blob, L.w2, *e->convs[ci + 1], L.bias + h * 4, h);
+            put_dw(blob, L.dw, *e->dws[di], L.bias + 3 * h * 4);
+          }
+          uint8_t *d = nullptr;
+          IRMV_CUDA(dev_malloc((void **)&d, blob.size()));
+          IRMV_CUDA(cudaMemcpy(d, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+          e->sh_blobs.push_back(d);
+        }
+        ci += down ? 3 : 2;
+        di += down ? 2 : 1;
+      }
+    }
+  }
   for (auto &d : e->dws) {
     IRMV_CUDA(dev_malloc((void **)&d->d_w, d->w.size() * 2));
     IRMV_CUDA(dev_malloc((void **)&d->d_b, d->b.size() * 4));
@@ -1387,6 +1494,7 @@ void irmv_engine_destroy(irmv_engine *e) {
     cudaFree(c->d_plain); cudaFree(c->d_tiled); cudaFree(c->d_raster); cudaFree(c->d_bias);
   }
   for (auto &d : e->dws) { cudaFree(d->d_w); cudaFree(d->d_b); }
+  for (uint8_t *b : e->sh_blobs) cudaFree(b);
 
   for (auto s : e->slots_host) cudaFreeHost(s);
   for (auto s : e->rot_host) if (s) cudaFreeHost(s);
@@ -1950,6 +2058,7 @@ int irmv_engine_describe_ops(irmv_engine *e, char *buf, int cap) {
     char line[160];
     if (o.kind == Op::POOL) snprintf(line, sizeof line, "pool\n");
     else if (o.kind == Op::DW) snprintf(line, sizeof line, "dw %d %d %d\n", o.dw.stride, o.dw.planes * 8, o.dw.H / o.dw.stride);
+    else if (o.kind == Op::SHUF) snprintf(line, sizeof line, "unit %d %d %d %d %d\n", o.su.down, o.su.cin, o.su.h, o.su.H, o.su.TH);
     else snprintf(line, sizeof line, "conv %d %d %d %d %d %d %d\n", o.cp.k, o.cp.stride, o.cp.cin, o.cp.cout, o.cp.OH,
                   o.raster ? 1 : 0, o.cp.tail_w ? o.cp.tail_cout : 0);
     out += line;
@@ -1975,6 +2084,7 @@ int irmv_engine_describe_plans(irmv_engine *e, int nframes, char *buf, int cap) 
     char line[200];
     if (o.kind == Op::POOL) { out += "pool\n"; continue; }
     if (o.kind == Op::DW) { snprintf(line, sizeof line, "dw %d %d %d\n", o.dw.stride, o.dw.planes * 8, o.dw.H / o.dw.stride); out += line; continue; }
+    if (o.kind == Op::SHUF) { snprintf(line, sizeof line, "unit %d %d %d %d %d\n", o.su.down, o.su.cin, o.su.h, o.su.H, o.su.TH); out += line; continue; }
     ConvParams p = o.cp;
     p.B = n;
     int info[8];

@@ -1,0 +1,299 @@
+// Fused ShuffleNetV2 units (sm_100a): one kernel per unit instead of three to five launches that
+// each stream the tensors through HBM / L2.  BASELINE.json configs[2] (the keypoint detector on a
+// ShuffleNetV2-style backbone; the reference names the model, README.md:12,16) and the north_star's
+// "depthwise and elementwise layers are fused bandwidth-bound kernels".
+//
+//   basic unit  (Ma et al. 2018, fig. 3c):  x1 | x2 -> x1 | pw2(dw3x3(pw1(x2)))        -> shuffle
+//   down unit   (fig. 3d):  pwA(dwA_s2(x)) | pw2(dwB_s2(pw1(x)))                       -> shuffle
+//
+// Persistent CTAs: the unit's weights (one packed blob, shuffle_blob_layout) are fetched once per CTA with
+// one bulk copy and stay in shared memory; the CTA then walks tiles of TH full-width output rows of one
+// image.  A tile's input is ONE contiguous run of raster pixels per plane (the zero-padded raster layout,
+// common.cuh: row pitch W + 1, so the left / right / top / bottom padding the depthwise conv wants is
+// already in the run) -> one cp.async.bulk per plane onto an mbarrier, and the next tile's copy is issued
+// as soon as the last reader of the input tile (the first 1x1) is done, i.e. it lands under the depthwise
+// conv, the second 1x1 and the output stores of the current tile.  The 1x1 convolutions run on
+// mma.sync.m16n8k16 straight from the tile (rows = pixels, [plane][pixel][8 channels] -> every A fragment
+// register is one conflict-free 32-bit load); the intermediates stay in shared memory as FP16 (exactly the
+// values the unfused path stores in HBM), the depthwise convs run from there and only the unit's output is
+// written.  HBM traffic of a unit = its input + its output (a basic unit also copies its pass-through half
+// into the other buffer of the stage's ping-pong pair: reading a halo that another CTA may already have
+// rewritten rules out updating in place).
+// Channel split / concat / shuffle stay the logical -> physical channel map folded into the weights
+// (engine.cu), so the unit reads and writes plane runs of the stage buffer (ConvSeg::runs).
+//
+// Bound: HBM (2 B in + 2 B out per value against ~3 h MACs); used for the stages with h <= 64, whose 1x1
+// GEMMs (K, N <= 64) are far too small for a tcgen05 tile to pay for its TMEM round trip, hence mma.sync.
+// The last stage (h = 128, 20 x 20 maps) is weight-heavy and stays one tcgen05 launch per convolution.
+#include "common.cuh"
+
+namespace irmv {
+namespace {
+
+constexpr int NT = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// floor(m / d) for m < 65536 through the reciprocal inv = recip_u16(d) (a 32-bit integer division costs ~25 issue slots)
+__device__ __forceinline__ uint32_t recip_u16(int d) { return 0xFFFFFFFFu / (uint32_t)d + 1u; }
+__device__ __forceinline__ int fast_div(int m, uint32_t inv) { return (int)__umulhi((uint32_t)m, inv); }
+
+__device__ __forceinline__ float silu_f(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+
+// Pointwise conv as a GEMM over a shared-memory tile: out[m][n] = silu(sum_k A[m][k] * W[n][k] + bias[n]),
+// K = N = C (every unit of the backbone has cin == h on the fused stages).
+//   sA: [C/8][Mp][8] halves (plane-major, Mp = M rounded up to 16); sW: [C][C + 8] halves; bias: [C] floats.
+// A warp takes m-tiles round-robin and holds all C/8 n-tile accumulators of an m-tile at once (the A fragments
+// are loaded once, the B fragments stream from shared memory, C/8 independent HMMA chains).
+// row(m) -> a per-row cookie, computed once per m-tile for the lane's two rows (m0 + g, m0 + g + 8);
+// epi(cookie, nt, packed): nt-th n-tile, packed = the two activated FP16 values of channels nt*8 + 2t, + 1.
+template <int C, typename Row, typename Epi>
+__device__ __forceinline__ void pw_gemm(const __half *sA, int M, int Mp, const __half *sW, const float *bias,
+                                        int warp, int lane, Row row, Epi epi) {
+  constexpr int KS = C / 16, NTL = C / 8, WP2 = (C + 8) / 2;                   // k-steps, n-tiles, weight row pitch in 32-bit words
+  const int g = lane >> 2, t = lane & 3;
+  const uint32_t *A32 = reinterpret_cast<const uint32_t *>(sA);
+  const uint32_t *W32 = reinterpret_cast<const uint32_t *>(sW) + g * WP2 + t;
+  const float2 *b2 = reinterpret_cast<const float2 *>(bias) + t;
+  for (int m0 = warp * 16; m0 < M; m0 += (NT / 32) * 16) {
+    const auto r0 = row(m0 + g), r1 = row(m0 + g + 8);
+    uint32_t a[KS][4];
+    const uint32_t *ap = A32 + (m0 + g) * 4 + t;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {                                          // plane 2ks / 2ks+1, pixel m0+g (+8), channels 2t..2t+1
+      a[ks][0] = ap[(2 * ks) * Mp * 4]; a[ks][1] = ap[(2 * ks) * Mp * 4 + 32];
+      a[ks][2] = ap[(2 * ks + 1) * Mp * 4]; a[ks][3] = ap[(2 * ks + 1) * Mp * 4 + 32];
+    }
+    float c[NTL][4];
+#pragma unroll
+    for (int nt = 0; nt < NTL; ++nt) {
+      const float2 bv = b2[nt * 4];
+      c[nt][0] = bv.x; c[nt][1] = bv.y; c[nt][2] = bv.x; c[nt][3] = bv.y;
+    }
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+      for (int nt = 0; nt < NTL; ++nt) {
+        const uint32_t b0 = W32[nt * 8 * WP2 + ks * 8], b1 = W32[nt * 8 * WP2 + ks * 8 + 4];
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[nt][0]), "+f"(c[nt][1]), "+f"(c[nt][2]), "+f"(c[nt][3])
+                     : "r"(a[ks][0]), "r"(a[ks][1]), "r"(a[ks][2]), "r"(a[ks][3]), "r"(b0), "r"(b1));
+      }
+#pragma unroll
+    for (int nt = 0; nt < NTL; ++nt) {
+      const __half2 h0 = __floats2half2_rn(silu_f(c[nt][0]), silu_f(c[nt][1])), h1 = __floats2half2_rn(silu_f(c[nt][2]), silu_f(c[nt][3]));
+      epi(r0, nt, *reinterpret_cast<const uint32_t *>(&h0));
+      epi(r1, nt, *reinterpret_cast<const uint32_t *>(&h1));
+    }
+  }
+}
+
+// Depthwise 3x3 (+ bias) from a shared-memory tile [PL][inMp][8] whose pixels form rows of pitch inW
+// to [PL][outMp][8]: output pixel (r, c), r < outH, c < outW, reads tile pixels
+// (S*r + ky) * inW + S*c + kx.  w: FP32 [PL][9][8].  A thread takes one output pixel and walks its planes.
+template <int PL, int S>
+__device__ __forceinline__ void dw_tile(const __half *sIn, int inMp, int inW, const float *w, const float *bias,
+                                        __half *sOut, int outMp, int outH, int outW, uint32_t inv_outW, int tid) {
+  const int npx = outH * outW;
+  for (int px = tid; px < npx; px += NT) {
+    const int r = fast_div(px, inv_outW), c = px - r * outW;
+    const __half *in = sIn + ((size_t)(S * r) * inW + S * c) * 8;
+    __half *out = sOut + (size_t)px * 8;
+#pragma unroll 2
+    for (int p = 0; p < PL; ++p) {
+      float acc[8];
+      {
+        const float4 b0 = *reinterpret_cast<const float4 *>(bias + p * 8), b1 = *reinterpret_cast<const float4 *>(bias + p * 8 + 4);
+        acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+      }
+      const __half *ip = in + (size_t)p * inMp * 8;
+      const float *wp = w + p * 72;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const uint4 v = *reinterpret_cast<const uint4 *>(ip + (ky * inW + kx) * 8);
+          const float4 w0 = *reinterpret_cast<const float4 *>(wp + (ky * 3 + kx) * 8), w1 = *reinterpret_cast<const float4 *>(wp + (ky * 3 + kx) * 8 + 4);
+          const __half2 *hv = reinterpret_cast<const __half2 *>(&v);
+          const float2 f0 = __half22float2(hv[0]), f1 = __half22float2(hv[1]), f2 = __half22float2(hv[2]), f3 = __half22float2(hv[3]);
+          acc[0] = fmaf(f0.x, w0.x, acc[0]); acc[1] = fmaf(f0.y, w0.y, acc[1]);
+          acc[2] = fmaf(f1.x, w0.z, acc[2]); acc[3] = fmaf(f1.y, w0.w, acc[3]);
+          acc[4] = fmaf(f2.x, w1.x, acc[4]); acc[5] = fmaf(f2.y, w1.y, acc[5]);
+          acc[6] = fmaf(f3.x, w1.z, acc[6]); acc[7] = fmaf(f3.y, w1.w, acc[7]);
+        }
+      __half2 o[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) o[q] = __floats2half2_rn(acc[2 * q], acc[2 * q + 1]);
+      *reinterpret_cast<uint4 *>(out + (size_t)p * outMp * 8) = *reinterpret_cast<uint4 *>(o);
+    }
+  }
+}
+
+// C = the unit's half width h = its input width cin (16 / 32 / 64), DOWN = down unit
+template <int C, bool DOWN>
+__global__ void __launch_bounds__(NT, 2) shuffle_unit_kernel(const __grid_constant__ ShuffleUnitParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  constexpr int PL = C / 8, S = DOWN ? 2 : 1;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int H = p.H, W = p.W, TH = p.TH;
+  const int Hin = S * H, Win = S * W;
+  // input tile of one plane: rows S*y0 - 1 .. S*(y0 + TH - 1) + 1 as one run of raster pixels starting at
+  // column -1 (pitch WC = Win + 1), plus the pixel after it (the right neighbour of the last pixel)
+  const int HR = S * TH + (DOWN ? 1 : 2), WC = Win + 1;
+  const int HP = HR * WC + 1, HPp = (HP + 15) & ~15;
+  const int TP = TH * W, TPp = (TP + 15) & ~15;
+  const ShuffleBlobLayout L = shuffle_blob_layout(DOWN, C, C);
+  // shared memory: blob | sX [PL][HPp][8] | sT1 [PL][HPp][8] | sU [PL][TPp][8] | output plane offsets | 2 mbarriers
+  const __half *sW1 = reinterpret_cast<const __half *>(smem + L.w1), *sW2 = reinterpret_cast<const __half *>(smem + L.w2);
+  const __half *sWa = reinterpret_cast<const __half *>(smem + L.wa);
+  const float *sDw = reinterpret_cast<const float *>(smem + L.dw), *sDwa = reinterpret_cast<const float *>(smem + L.dwa);
+  const float *sB = reinterpret_cast<const float *>(smem + L.bias);         // b1[C] b2[C] ba[C] dwb[C] dwab[C]
+  __half *sX = reinterpret_cast<__half *>(smem + L.bytes);
+  __half *sT1 = sX + (size_t)PL * HPp * 8;
+  __half *sU = sT1 + (size_t)PL * HPp * 8;
+  long long *sOff = reinterpret_cast<long long *>(sU + (size_t)PL * TPp * 8);   // [PL]: half offset of the plane the nt-th n-tile of the second 1x1 writes
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sOff + PL);
+  const int tiles_per_img = H / TH, tiles = p.B * tiles_per_img;
+  const uint32_t plane_bytes = (uint32_t)HP * 16;
+  auto issue = [&](int tile) {                                              // one thread
+    const int t = p.rev ? tiles - 1 - tile : tile;
+    const int b = t / tiles_per_img, y0 = (t - b * tiles_per_img) * TH;
+    const __half *src = p.in + pr_index(b, S * y0 - 1, -1, Hin, Win) * 8;
+    mbar_expect_tx(&bars[0], plane_bytes * PL);
+#pragma unroll 1
+    for (int pl = 0; pl < PL; ++pl) {
+      const int plane = DOWN ? pl : p.first_plane + run_plane(pl, p.runs);
+      bulk_g2s(sX + (size_t)pl * HPp * 8, src + (long long)plane * p.in_ps, plane_bytes, &bars[0]);
+    }
+  };
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(&bars[1], (uint32_t)L.bytes);
+    bulk_g2s(smem, p.blob, (uint32_t)L.bytes, &bars[1]);
+    if ((int)blockIdx.x < tiles) issue(blockIdx.x);
+  }
+  if (tid < PL) sOff[tid] = (long long)(DOWN ? PL + tid : p.first_plane + run_plane(tid, p.runs)) * p.out_ps;
+  __syncthreads();
+  mbar_wait(&bars[1], 0);
+  const int t2 = 2 * (lane & 3);
+  const uint32_t invW = recip_u16(W), invWC = recip_u16(WC);
+  uint32_t it = 0;
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+    const int t = p.rev ? tiles - 1 - tile : tile;
+    const int b = t / tiles_per_img, y0 = (t - b * tiles_per_img) * TH;
+    const long long out0 = pr_index(b, y0, 0, H, W) * 8;                    // output pixel (y0, 0); the TH rows follow with pitch W + 1
+    if (!DOWN) {
+      // pass-through half: the planes one run before the unit's, copied to the other buffer of the ping-pong pair
+      const int rp = p.runs ? (1 << (p.runs - 1)) : PL;
+      const int run_px = TP + TH - 1;                                       // the TH rows of a plane are one contiguous run (pads included)
+#pragma unroll 1
+      for (int pl = 0; pl < PL; ++pl) {
+        const int plane = p.first_plane + run_plane(pl, p.runs) - rp;
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.in + (long long)plane * p.in_ps + out0);
+        uint4 *dst = reinterpret_cast<uint4 *>(p.out + (long long)plane * p.out_ps + out0);
+#pragma unroll 2
+        for (int px = tid; px < run_px; px += NT) dst[px] = __ldg(src + px);
+      }
+    }
+    mbar_wait(&bars[0], it & 1);
+    // pixels outside the image must be ZERO in T1 (the depthwise conv pads T1, not the first 1x1's input)
+    const int ylo = 1 - S * y0, yhi = Hin + 1 - S * y0;                     // tile rows [ylo, yhi) are image rows
+    auto t1_row = [&](int m) -> int {
+      const int r = fast_div(m, invWC), c = m - r * WC;
+      return (c != 0 && r >= ylo && r < yhi) ? m : -1 - m;
+    };
+    auto t1_store = [&](int ck, int nt, uint32_t v) {
+      const bool in = ck >= 0;
+      const int m = in ? ck : -1 - ck;
+      *reinterpret_cast<uint32_t *>(sT1 + ((size_t)nt * HPp + m) * 8 + t2) = in ? v : 0u;
+    };
+    auto out_row = [&](int m) -> __half * {
+      if (m >= TP) return nullptr;
+      return p.out + out0 + (long long)(m + fast_div(m, invW)) * 8 + t2;               // pixel (r, c) sits r pad pixels further along the raster
+    };
+    if (DOWN) {
+      // branch 1, first half: depthwise s2 on the input tile
+      dw_tile<PL, 2>(sX, HPp, WC, sDwa, sB + 4 * C, sU, TPp, TH, W, invW, tid);
+    }
+    // branch 2 / basic unit: first 1x1 over the whole input tile
+    pw_gemm<C>(sX, HP, HPp, sW1, sB, warp, lane, t1_row, t1_store);
+    __syncthreads();                                                        // sX is free, sT1 (and sU) complete
+    if (tid == 0 && tile + (int)gridDim.x < tiles) issue(tile + gridDim.x);
+    if (DOWN) {
+      // branch 1, second half: 1x1 C -> C into output planes [0, C/8)
+      pw_gemm<C>(sU, TP, TPp, sWa, sB + 2 * C, warp, lane, out_row, [&](__half *o, int nt, uint32_t v) {
+        if (o) *reinterpret_cast<uint32_t *>(o + (long long)nt * p.out_ps) = v;
+      });
+      __syncthreads();
+    }
+    dw_tile<PL, S>(sT1, HPp, WC, sDw, sB + 3 * C, sU, TPp, TH, W, invW, tid);
+    __syncthreads();
+    pw_gemm<C>(sU, TP, TPp, sW2, sB + C, warp, lane, out_row, [&](__half *o, int nt, uint32_t v) {
+      if (o) *reinterpret_cast<uint32_t *>(o + sOff[nt]) = v;
+    });
+    __syncthreads();                                                        // sU / sT1 are rewritten by the next tile
+  }
+}
+
+}  // namespace
+
+size_t shuffle_unit_smem(const ShuffleUnitParams &p) {
+  const int s = p.down ? 2 : 1;
+  const int HR = s * p.TH + (p.down ? 1 : 2), WC = s * p.W + 1;
+  const size_t HPp = ((size_t)HR * WC + 1 + 15) & ~(size_t)15, TPp = ((size_t)p.TH * p.W + 15) & ~(size_t)15;
+  const size_t pl = p.h / 8;
+  return (size_t)shuffle_blob_layout(p.down, p.cin, p.h).bytes + (2 * pl * HPp + pl * TPp) * 16 + pl * 8 + 16;
+}
+
+int shuffle_unit_ctas_per_sm(const ShuffleUnitParams &p) {
+  const size_t smem = shuffle_unit_smem(p) + 1024;                          // + the per-CTA reservation
+  const int by_smem = (int)((size_t)228 * 1024 / smem);
+  return by_smem < 1 ? 0 : (by_smem > 2 ? 2 : by_smem);                    // __launch_bounds__(256, 2): 128 registers per thread
+}
+
+cudaError_t launch_shuffle_unit(const ShuffleUnitParams &p, cudaStream_t s) {
+  if (p.B <= 0) return cudaSuccess;
+  if (p.TH < 1 || p.H % p.TH || p.cin != p.h || !(p.h == 16 || p.h == 32 || p.h == 64)) return cudaErrorInvalidValue;
+  const size_t smem = shuffle_unit_smem(p);
+  const int per_sm = shuffle_unit_ctas_per_sm(p);
+  if (per_sm < 1) return cudaErrorInvalidValue;
+  void (*k)(const ShuffleUnitParams) = nullptr;
+  if (p.down) k = p.h == 16 ? shuffle_unit_kernel<16, true> : (p.h == 32 ? shuffle_unit_kernel<32, true> : shuffle_unit_kernel<64, true>);
+  else k = p.h == 16 ? shuffle_unit_kernel<16, false> : (p.h == 32 ? shuffle_unit_kernel<32, false> : shuffle_unit_kernel<64, false>);
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int tiles = p.B * (p.H / p.TH);
+  const int grid = std::min(tiles, (p.num_sms > 0 ? p.num_sms : 148) * per_sm);
+  k<<<grid, NT, smem, s>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace irmv

@@ -52,7 +52,8 @@ class YoloEngine:
                  max_batch: int = 1,
                  sub_batch: int = 0, num_lanes: int = 0, num_slots: int = 3, device: int = 0,
                  conv_impl: int = L.CONV_TCGEN05, score_thr: float = 0.25, iou_thr: float = 0.45,
-                 max_det: int = 100, use_graph: bool = True, fused_stem: bool = True, fuse_tails: bool = True):
+                 max_det: int = 100, use_graph: bool = True, fused_stem: bool = True, fuse_tails: bool = True,
+                 fuse_units: bool = True):
         lib = L.lib()
         wpath = onnx_file_path if onnx_file_path.endswith(".irmw") else weights_path_for(onnx_file_path)
         if not os.path.exists(wpath):
@@ -72,6 +73,7 @@ class YoloEngine:
         cfg.use_graph = int(use_graph)
         cfg.reserved[0] = 0 if fused_stem else 1
         cfg.reserved[1] = 0 if fuse_tails else 1
+        cfg.reserved[2] = 0 if fuse_units else 1          # ShuffleNetV2 variant: one kernel per unit (default) or one per conv
         self._cfg = cfg
         self._h = C.c_void_p()
         self._lib = lib
@@ -258,6 +260,8 @@ class YoloEngine:
                 ops.append({"kind": "pool"})
             elif f[0] == "dw":
                 ops.append({"kind": "dw", "s": int(f[1]), "c": int(f[2]), "hw": int(f[3])})
+            elif f[0] == "unit":
+                ops.append({"kind": "unit", "down": bool(int(f[1])), "cin": int(f[2]), "h": int(f[3]), "hw": int(f[4]), "rows_per_cta": int(f[5])})
             else:
                 k, s, cin, cout, hw, raster, tail = (int(v) for v in f[1:])
                 ops.append({"kind": "conv", "k": k, "s": s, "cin": cin, "cout": cout, "hw": hw, "raster": bool(raster),

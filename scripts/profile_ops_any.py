@@ -1,5 +1,5 @@
 """Per-kernel CUDA-event times of one eager replay for any weight file / architecture:
-`python scripts/profile_ops_any.py [frames] [yolov8n|yolov8n-pose|shufflenetv2-pose]`."""
+`python scripts/profile_ops_any.py [frames] [yolov8n|yolov8n-pose|shufflenetv2-pose] [unfused]`."""
 import ctypes as C
 import os
 import sys
@@ -19,7 +19,8 @@ def main():
     w = f"/tmp/profile_{arch}.irmw"
     weights.write_random(w, 0, pose=(arch == "yolov8n-pose"), arch=arch)
     frames = torch.from_numpy(synth.frames_from_base(synth.load_base(), n, seed=2)).cuda()
-    eng = irmv.YoloEngine(w, (1280, 1024), max_batch=n, sub_batch=n, num_lanes=1, use_graph=False)
+    fuse = not (len(sys.argv) > 3 and sys.argv[3] == "unfused")
+    eng = irmv.YoloEngine(w, (1280, 1024), max_batch=n, sub_batch=n, num_lanes=1, use_graph=False, fuse_units=fuse)
     for _ in range(3):
         eng.enqueue_batch_device(frames.data_ptr(), n)
         eng.sync()
@@ -40,6 +41,10 @@ def main():
         elif o["kind"] == "dw":
             io = n * ((o["hw"] * o["s"]) ** 2 + o["hw"] ** 2) * o["c"] * 2.0
             print(f"dw   k3 s{o['s']} {o['c']:4d}         hw {o['hw']:3d}                 {v:8.1f} us {io / v / 1e3:8.1f} GB/s(in+out)")
+        elif o["kind"] == "unit":
+            s_ = 2 if o["down"] else 1
+            io = n * ((o["hw"] * s_) ** 2 * o["cin"] * (1 if o["down"] else 2) + o["hw"] ** 2 * 2 * o["h"]) * 2.0
+            print(f"unit {'down ' if o['down'] else 'basic'} {o['cin']:4d}->{2 * o['h']:4d} hw {o['hw']:3d} rows/cta {o['rows_per_cta']} {v:8.1f} us {io / v / 1e3:8.1f} GB/s(in+out)")
         else:
             print(f"pool {v:8.1f} us")
     eng.close()

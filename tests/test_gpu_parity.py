@@ -1306,22 +1306,36 @@ def weights_shuffle(tmp_path_factory):
     return str(p)
 
 
-def test_shufflenet_variant_parity(frames, weights_shuffle):
+@pytest.mark.parametrize("fuse_units", [True, False])
+def test_shufflenet_variant_parity(frames, weights_shuffle, fuse_units):
     """BASELINE.json configs[2], north_star "depthwise and elementwise layers are fused bandwidth-bound
     kernels": the keypoint detector on the ShuffleNetV2-style backbone.  Depthwise 3x3 kernel + 1x1 convs on
     the tcgen05 raster kernel, channel split / concat / shuffle folded into plane runs and weight
     permutations (zero bytes moved).  Every stage output (un-permuted by read_tensor), the neck taps and the
     three head tensors against the FP32 oracle; decoded scores / boxes / keypoints within the north_star
-    tolerances; kept indices bit-exact on the GPU's own decoded inputs."""
+    tolerances; kept indices bit-exact on the GPU's own decoded inputs.  fuse_units: each ShuffleNetV2 unit
+    as ONE kernel (shuffle_unit.cu; intermediates in shared memory) or one launch per convolution -- the two
+    store the same FP16 intermediates and differ only in the tensor cores' accumulation order."""
     import torch
     import irmv_detection_b200 as irmv
     from oracle import nms_ref as N, pnp_ref as P, yolov8n_ref as Y
     _cuda()
     fr = frames[[0, 2, 3]]
     n = fr.shape[0]
-    eng = irmv.YoloEngine(weights_shuffle, (1280, 1024), max_batch=n, sub_batch=n)
+    eng = irmv.YoloEngine(weights_shuffle, (1280, 1024), max_batch=n, sub_batch=n, fuse_units=fuse_units)
     assert eng.has_keypoints()
-    assert sum(1 for o in eng.describe_ops() if o["kind"] == "dw") == 13
+    kinds = [o["kind"] for o in eng.describe_ops()]
+    if fuse_units:
+        assert kinds.count("unit") == 7 and kinds.count("dw") == 3       # the h = 128 stage stays one launch per conv
+        other = irmv.YoloEngine(weights_shuffle, (1280, 1024), max_batch=n, sub_batch=n, fuse_units=False)
+        other.detect_batch(fr)
+        eng.detect_batch(fr)
+        for name in ("d1", "d2", "d3", "d4", "box0", "cls2", "kpt1"):
+            a, b = eng.read_tensor(name).astype(np.float32), other.read_tensor(name).astype(np.float32)
+            assert np.abs(a - b).max() <= 4e-3 * max(np.abs(b).max(), 1.0), name     # mma.sync vs tcgen05 accumulation order
+        other.close()
+    else:
+        assert kinds.count("dw") == 13 and kinds.count("unit") == 0
     # (the engine refuses to build unless every backbone 1x1 runs on the tcgen05 raster kernel; the two
     # neck convs over concat(upsample, skip) are the only gather-kernel launches left)
     assert sum(1 for o in eng.describe_ops() if o["kind"] == "conv" and not o["raster"]) <= 4
