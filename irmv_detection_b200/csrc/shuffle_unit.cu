@@ -81,6 +81,7 @@ __device__ __forceinline__ void pw_gemm(const __half *sA, int M, int Mp, const _
   const uint32_t *A32 = reinterpret_cast<const uint32_t *>(sA);
   const uint32_t *W32 = reinterpret_cast<const uint32_t *>(sW) + g * WP2 + t;
   const float2 *b2 = reinterpret_cast<const float2 *>(bias) + t;
+#pragma unroll(C <= 32 ? 2 : 1)
   for (int m0 = warp * 16; m0 < M; m0 += (NT / 32) * 16) {
     const auto r0 = row(m0 + g), r1 = row(m0 + g + 8);
     uint32_t a[KS][4];
@@ -157,7 +158,7 @@ __device__ __forceinline__ void dw_tile(const __half *sIn, int inMp, int inW, co
 
 // C = the unit's half width h = its input width cin (16 / 32 / 64), DOWN = down unit
 template <int C, bool DOWN>
-__global__ void __launch_bounds__(NT, 2) shuffle_unit_kernel(const __grid_constant__ ShuffleUnitParams p) {
+__global__ void __launch_bounds__(NT, C == 16 ? 3 : 2) shuffle_unit_kernel(const __grid_constant__ ShuffleUnitParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int PL = C / 8, S = DOWN ? 2 : 1;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -276,7 +277,8 @@ size_t shuffle_unit_smem(const ShuffleUnitParams &p) {
 int shuffle_unit_ctas_per_sm(const ShuffleUnitParams &p) {
   const size_t smem = shuffle_unit_smem(p) + 1024;                          // + the per-CTA reservation
   const int by_smem = (int)((size_t)228 * 1024 / smem);
-  return by_smem < 1 ? 0 : (by_smem > 2 ? 2 : by_smem);                    // __launch_bounds__(256, 2): 128 registers per thread
+  const int by_regs = p.h == 16 ? 3 : 2;                                    // __launch_bounds__(256, 3 / 2): 85 / 128 registers per thread
+  return by_smem < 1 ? 0 : (by_smem > by_regs ? by_regs : by_smem);
 }
 
 cudaError_t launch_shuffle_unit(const ShuffleUnitParams &p, cudaStream_t s) {
