@@ -241,9 +241,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
       if (tr) p.trace[itp * 8 + 0] = clock64();
       int off0[8], off1[8];
       uint32_t mask[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int m = tile * BM + rbase + 16 * i;
+      {
+        // The eight lanes that share rbase (chunk = lane & 7) need the same eight rows rbase + 16*i: lane
+        // `chunk` decodes row i = chunk only and the octet exchanges the results by shuffle (the decode was
+        // 29 % of the kernel's instructions when every thread decoded all eight rows itself).
+        const int m = tile * BM + rbase + 16 * chunk;
         const uint32_t t = (uint32_t)(((uint64_t)(uint32_t)m * mul_ow) >> 34);      // m / OW
         const int ox = m - (int)t * OW;
         const uint32_t bimg = (uint32_t)(((uint64_t)t * mul_oh) >> 34);             // t / OH
@@ -251,10 +253,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
         const int iy0 = oy * cstr, ix0 = ox * cstr;
         const int full = ((int)bimg * (H + 1) + 1 + iy0) * (W + 1) + ix0;                       // PR layout
         const int half = ((int)bimg * (Hh + 1) + 1 + (iy0 >> 1)) * (Wh + 1) + (ix0 >> 1);
-        off0[i] = (up0 ? half : full) * 8;                 // halfs inside a plane
-        off1[i] = two ? (up1 ? half : full) * 8 : 0;
+        const int my0 = (up0 ? half : full) * 8;           // halfs inside a plane
+        const int my1 = two ? (up1 ? half : full) * 8 : 0;
         // the PR layout's zero row/column make every tap of a real output pixel readable
-        mask[i] = (m < M && nozero) ? (k3 ? 0x1FFu : 1u) : 0u;
+        const uint32_t vb = __ballot_sync(0xffffffffu, m < M && nozero) >> (lane & 24);
+        const uint32_t mfull = k3 ? 0x1FFu : 1u;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          off0[i] = __shfl_sync(0xffffffffu, my0, (lane & 24) | i);
+          off1[i] = two ? __shfl_sync(0xffffffffu, my1, (lane & 24) | i) : 0;
+          mask[i] = ((vb >> i) & 1u) ? mfull : 0u;
+        }
       }
       if (tr) p.trace[itp * 8 + 1] = clock64();
       for (int kb = 0; kb < KB; ++kb) {
