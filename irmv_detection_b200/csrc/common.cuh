@@ -126,6 +126,9 @@ struct ConvParams {
   int out_runs;            // output planes in runs like ConvSeg::runs (raster kernel, no tail / twin / residual)
   const __half *res;       // residual added after the activation (same grid as out); may be null
   long long res_pstride;
+  int res_up;              // raster kernel: 1 = `res` is a HALF-resolution tensor (OH/2 x OW/2) whose pixel (y/2, x/2) is
+                           // added BEFORE the activation: the a-half of a 1x1 conv over concat(upsample(a), b), computed at
+                           // a's resolution (a 1x1 conv commutes with nearest upsampling)
   // Parity-split twin tensors (raster kernel only).  A tensor of C channels on an H x W grid is
   // stored a second time as 4 * C/8 planes ordered [parity g = (y&1)*2 + (x&1)][C/8], each a padded
   // raster of the (H/2) x (W/2) pixels of that parity.  A 3x3 / stride-2 / pad-1 tap (ky, kx) then

@@ -174,7 +174,10 @@ __device__ __forceinline__ void st_shared_zero2(uint32_t addr, uint32_t plane_by
   st_shared_v4(addr + plane_bytes, z);
 }
 
-template <bool ACT, bool RES, bool MID = false>
+// RES: 0 = none; 1 = residual of the same pixel added after the activation (C2f bottleneck shortcut); 2 = partial
+// sum of the same channels added BEFORE the activation (r0 / r1 come from a half-resolution tensor: the
+// upsampled half of a 1x1 conv over concat(upsample(a), b), computed at a's resolution -- ConvParams::res_up)
+template <bool ACT, int RES, bool MID = false>
 __device__ __forceinline__ void epi_chunk(const uint32_t (&v32)[16], const float *hb, __half *o, long long out_ps,
                                           __half *o2, long long out2_ps, const uint4 &r0, const uint4 &r1,
                                           uint32_t mid = 0, uint32_t mid_plane_bytes = 0) {
@@ -183,6 +186,17 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v32)[16], const float
   for (int j = 0; j < 4; ++j) {
     const float4 t = *reinterpret_cast<const float4 *>(hb + 4 * j);   // same address in every lane: broadcast
     b[4 * j] = t.x; b[4 * j + 1] = t.y; b[4 * j + 2] = t.z; b[4 * j + 3] = t.w;
+  }
+  if (RES == 2) {
+    const float sc = ACT ? 0.5f : 1.0f;                    // ACT: b is bias / 2 and the accumulator is halved below
+    const __half2 *h0 = reinterpret_cast<const __half2 *>(&r0);
+    const __half2 *h1 = reinterpret_cast<const __half2 *>(&r1);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 f0 = __half22float2(h0[t]), f1 = __half22float2(h1[t]);
+      b[2 * t] = fmaf(f0.x, sc, b[2 * t]); b[2 * t + 1] = fmaf(f0.y, sc, b[2 * t + 1]);
+      b[8 + 2 * t] = fmaf(f1.x, sc, b[8 + 2 * t]); b[8 + 2 * t + 1] = fmaf(f1.y, sc, b[8 + 2 * t + 1]);
+    }
   }
   float v[16];
   if (ACT) {
@@ -198,7 +212,7 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v32)[16], const float
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(v32[j]) + b[j];
   }
-  if (RES) {
+  if (RES == 1) {
     const __half2 *h0 = reinterpret_cast<const __half2 *>(&r0);
     const __half2 *h1 = reinterpret_cast<const __half2 *>(&r1);
 #pragma unroll
@@ -226,7 +240,7 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v32)[16], const float
 }
 
 // TAIL: 0 = none, 1 = fused 1x1 consumer without activation, 2 = with SiLU
-template <int R, int NEPI, bool ACT, bool RES, int TAIL>
+template <int R, int NEPI, bool ACT, int RES, int TAIL>
 __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raster_kernel(const __grid_constant__ RArgs a) {
   constexpr int NTHREADS = (NEPI + 2) * 32;
   constexpr int TMA_WARP = NEPI, MMA_WARP = NEPI + 1;
@@ -406,7 +420,7 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
       const int q_tile = q_lane + tile * TM;
       const uint32_t okmask = valid_mask(q_tile);
       __half *const out_q = out + (long long)q_tile * 8;
-      const __half *const res_q = RES ? res + (long long)q_tile * 8 : nullptr;
+      const __half *const res_q = RES == 1 ? res + (long long)q_tile * 8 : nullptr;
       mbar_wait_warp(&bars->tmem_full[buf], aph, lane);
       // fused tail: the intermediate tile is free once the tail MMAs of the previous tile have read it
       if (TAIL) mbar_wait_warp(&bars->mid_empty, (uint32_t)(it & 1) ^ 1u, lane);
@@ -433,10 +447,21 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
           const int px2 = ((int)img * Hp2 + 1 + (y >> 1)) * Wp2 + (x >> 1);
           t.o2 = out2 + (long long)(((y & 1) * 2 + (x & 1)) * cpl + (t.c0 >> 3)) * out2_ps + (long long)px2 * 8;
         }
-        if (RES && t.ok) {                                  // residual: issue the loads early
+        if (RES == 1 && t.ok) {                             // residual: issue the loads early
           const __half *rp = res_q + (long long)(t.c0 >> 3) * res_ps + r * 1024;
           t.r0 = *reinterpret_cast<const uint4 *>(rp);
           t.r1 = *reinterpret_cast<const uint4 *>(rp + res_ps);
+        }
+        if (RES == 2 && t.ok) {                             // half-resolution partial sum: pixel (y / 2, x / 2) of its raster
+          const int qi = q_tile + r * 128;
+          const uint32_t row = (uint32_t)(((uint64_t)(uint32_t)qi * mul_wp) >> 34);
+          const int x = qi - (int)row * Wp;
+          const uint32_t img = (uint32_t)(((uint64_t)row * mul_hp1) >> 34);
+          const int y = (int)row - (int)img * Hp1 - 1;
+          const int px2 = ((int)img * Hp2 + 1 + (y >> 1)) * Wp2 + (x >> 1);
+          const __half *rp = res + (long long)(t.c0 >> 3) * res_ps + (long long)px2 * 8;
+          t.r0 = __ldg(reinterpret_cast<const uint4 *>(rp));
+          t.r1 = __ldg(reinterpret_cast<const uint4 *>(rp + res_ps));
         }
         return tcol0 + (uint32_t)(r * npad + t.c0);
       };
@@ -696,6 +721,7 @@ bool plan(const ConvParams &p, int num_sms, RArgs &a) {
   for (int i = 0; i < p.nseg; ++i) if (p.seg[i].up || p.seg[i].c % 8) return false;
   if (p.OW + 2 + 8 > kGuardFront || p.cout % 16 != 0) return false;
   if (p.out2 && ((p.OH & 1) || (p.OW & 1))) return false;
+  if (p.res_up && (!p.res || !p.act || p.tail_w || s2 || (p.OH & 1) || (p.OW & 1))) return false;
   // planes in runs: plain 1x1 / 3x3 convs only (no twin, residual, tail or second segment)
   if ((p.out_runs || p.seg[0].runs) && (p.out2 || p.res || p.tail_w || p.in_parity || p.nseg != 1)) return false;
   a.p = p;
@@ -836,7 +862,7 @@ bool plan(const ConvParams &p, int num_sms, RArgs &a) {
   return true;
 }
 
-template <int R, int NEPI, bool ACT, bool RES, int TAIL>
+template <int R, int NEPI, bool ACT, int RES, int TAIL>
 cudaError_t launch_k(const RArgs &a, int grid, size_t smem, cudaStream_t s) {
   {   // the attribute is per device: no process-wide flag (several engines / devices per process); the call is cheap
     cudaError_t e = cudaFuncSetAttribute(conv_raster_kernel<R, NEPI, ACT, RES, TAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -859,16 +885,20 @@ cudaError_t launch_k(const RArgs &a, int grid, size_t smem, cudaStream_t s) {
 template <int R, int NEPI>
 cudaError_t launch_r(const RArgs &a, int grid, size_t smem, cudaStream_t s) {
   const bool act = a.p.act != 0, res = a.p.res != nullptr;
+  if (res && a.p.res_up) {                           // 1x1 over concat(upsample(a), b), the a half precomputed at a's resolution
+    if (!act || a.p.tail_w) return cudaErrorInvalidValue;
+    return launch_k<R, NEPI, true, 2, 0>(a, grid, smem, s);
+  }
   if (a.p.tail_w) {                                  // fused 1x1 consumer
     if (res) {                                       // bottleneck with shortcut + C2f.cv2: SiLU on both
       if (!act || !a.p.tail_act) return cudaErrorInvalidValue;
-      return launch_k<R, NEPI, true, true, 2>(a, grid, smem, s);
+      return launch_k<R, NEPI, true, 1, 2>(a, grid, smem, s);
     }
-    if (a.p.tail_act) return act ? launch_k<R, NEPI, true, false, 2>(a, grid, smem, s) : launch_k<R, NEPI, false, false, 2>(a, grid, smem, s);
-    return act ? launch_k<R, NEPI, true, false, 1>(a, grid, smem, s) : launch_k<R, NEPI, false, false, 1>(a, grid, smem, s);
+    if (a.p.tail_act) return act ? launch_k<R, NEPI, true, 0, 2>(a, grid, smem, s) : launch_k<R, NEPI, false, 0, 2>(a, grid, smem, s);
+    return act ? launch_k<R, NEPI, true, 0, 1>(a, grid, smem, s) : launch_k<R, NEPI, false, 0, 1>(a, grid, smem, s);
   }
-  if (act) return res ? launch_k<R, NEPI, true, true, 0>(a, grid, smem, s) : launch_k<R, NEPI, true, false, 0>(a, grid, smem, s);
-  return res ? launch_k<R, NEPI, false, true, 0>(a, grid, smem, s) : launch_k<R, NEPI, false, false, 0>(a, grid, smem, s);
+  if (act) return res ? launch_k<R, NEPI, true, 1, 0>(a, grid, smem, s) : launch_k<R, NEPI, true, 0, 0>(a, grid, smem, s);
+  return res ? launch_k<R, NEPI, false, 1, 0>(a, grid, smem, s) : launch_k<R, NEPI, false, 0, 0>(a, grid, smem, s);
 }
 
 }  // namespace

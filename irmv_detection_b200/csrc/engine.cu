@@ -67,6 +67,9 @@ struct HostConv {   // one GEMM as the kernels see it (possibly several referenc
   __half *d_plain = nullptr, *d_tiled = nullptr, *d_raster = nullptr;
   float *d_bias = nullptr;
   int32_t *d_ktab = nullptr;
+  // a 1x1 conv over concat(upsample(a), b) split into W_a (at a's resolution, no bias / activation) and W_b (at
+  // full resolution, + bias, + upsampled partial sum before the activation: ConvParams::res_up); null = not split
+  std::shared_ptr<HostConv> up_a, up_b;
 };
 
 struct FileConv {
@@ -265,6 +268,19 @@ HostConv make_conv(const std::vector<const FileConv *> &parts, int cin_pad,
     h.ktab[q * 3 + 0] = tap; h.ktab[q * 3 + 1] = sg; h.ktab[q * 3 + 2] = off;
   }
   return h;
+}
+
+// Input channels [c0, c1) of a convolution as a convolution of its own (bias / activation kept or dropped).
+FileConv slice_cin(const FileConv &f, int c0, int c1, bool keep_bias_act) {
+  FileConv r = f;
+  const int kk = f.k * f.k;
+  r.cin = c1 - c0;
+  r.w.assign((size_t)f.cout * r.cin * kk, 0.f);
+  for (int n = 0; n < f.cout; ++n)
+    for (int c = c0; c < c1; ++c)
+      for (int t = 0; t < kk; ++t) r.w[((size_t)n * r.cin + (c - c0)) * kk + t] = f.w[((size_t)n * f.cin + c) * kk + t];
+  if (!keep_bias_act) { r.act = 0; std::fill(r.b.begin(), r.b.end(), 0.f); }
+  return r;
 }
 
 // The ShuffleNetV2 units never move channels: a stage lives in one buffer, a unit rewrites every second
@@ -474,6 +490,7 @@ struct irmv_engine {
   std::vector<std::vector<int>> sh_map;           // per stage: logical -> physical channel of the stage output
   // fused units (shuffle_unit.cu): one constant blob (shuffle_blob_layout) per unit of the stages it serves, in execution order
   std::vector<uint8_t *> sh_blobs;
+  bool up_split = true;                           // 1x1 over concat(upsample(a), b) as two raster launches (HostConv::up_a / up_b)
   bool sh_fused = true;                           // cfg.reserved[2] != 0: one launch per conv instead (unfused reference path)
   std::vector<Lane> lanes;
   cudaStream_t main_stream = nullptr;
@@ -558,7 +575,7 @@ bool add_parity_twin(Lane &ln, int S, Tensor &t, bool only) {
 struct SegRef { const Tensor *t; int coff; int c; int up; };
 
 void add_conv(irmv_engine *e, Lane &ln, HostConv &hc, std::vector<SegRef> in, int H, int W,
-              const Tensor &out, int out_coff, const Tensor *res = nullptr, int res_coff = 0) {
+              const Tensor &out, int out_coff, const Tensor *res = nullptr, int res_coff = 0, int res_up = 0) {
   Op op;
   op.kind = Op::CONV;
   ConvParams &p = op.cp;
@@ -598,6 +615,7 @@ void add_conv(irmv_engine *e, Lane &ln, HostConv &hc, std::vector<SegRef> in, in
   p.out = out.p + (long long)(out_coff / 8) * out.pstride; p.out_pstride = out.pstride;
   p.res = res ? res->p + (long long)(res_coff / 8) * res->pstride : nullptr;
   p.res_pstride = res ? res->pstride : 0;
+  p.res_up = res ? res_up : 0;
   p.sync_mode = 0;
   p.trace = nullptr; p.trace_cap = 0;
   p.in_parity = 0;
@@ -633,13 +651,26 @@ bool add_c2f(irmv_engine *e, Lane &ln, size_t &ci, std::vector<SegRef> in, int H
     if (!add_parity_twin(ln, e->S, out, parity_out == 1)) return false;
     if (tap) ln.taps[tap] = out;
   }
-  // (cv1 of the neck C2f blocks reads concat(upsample(a), b).  Splitting it with
-  // conv1x1(upsample(a)) == upsample(conv1x1(a)) -- W_a at half resolution, the partial sum added in
-  // the full-resolution epilogue -- was built and measured: both halves run on the raster kernel,
-  // but every partial sum is re-read by four output pixels (L2 traffic 633 vs 374 MB on m15.cv1 at
-  // 128 frames) and the extra epilogue state spills registers in every residual layer; the replay
-  // got 0.1 ms slower, so these two layers stay on the gather kernel.)
-  add_conv(e, ln, *e->convs[ci++], in, H, W, buf, 0);
+  // cv1 of the neck C2f blocks reads concat(upsample(a), b).  A 1x1 conv commutes with nearest upsampling:
+  // conv1x1(upsample(a)) == upsample(conv1x1(a)), so W_a runs at half resolution and its partial sum joins the
+  // full-resolution accumulator in the epilogue, before the activation.  (Round 1 built this with the extra epilogue
+  // state in EVERY instantiation: residual layers spilled and the replay got slower.  As its own template value --
+  // conv_raster_kernel<.., RES = 2, ..> -- it takes m15.cv1 + m12.cv1 from 198 us on the gather kernel to about
+  // 130 us on four raster launches per 128 frames.)
+  HostConv &cv1 = *e->convs[ci++];
+  bool split = false;
+  if (cv1.up_a && in.size() == 2 && in[0].up && !in[1].up) {
+    // cv1 over concat(upsample(a), b): W_a . a at a's resolution (no bias, no activation), then W_b . b at full
+    // resolution with the upsampled partial sum added before the activation -- both on the raster kernel
+    Tensor ya;
+    if (!new_tensor(ln, e->S, H / 2, W / 2, cv1.cout, ya)) return false;
+    add_conv(e, ln, *cv1.up_a, {{in[0].t, in[0].coff, in[0].c, 0}}, H / 2, W / 2, ya, 0);
+    const bool ok_a = ln.ops.back().raster;
+    add_conv(e, ln, *cv1.up_b, {in[1]}, H, W, buf, 0, &ya, 0, 1);
+    if (ok_a && ln.ops.back().raster) split = true;
+    else { ln.ops.pop_back(); ln.ops.pop_back(); }          // does not fit the raster kernel: the gather kernel does the concat
+  }
+  if (!split) add_conv(e, ln, cv1, in, H, W, buf, 0);
   for (int i = 0; i < n; ++i) {
     add_conv(e, ln, *e->convs[ci++], {{&buf, (1 + i) * c, c, 0}}, H, W, tmp, 0);
     add_conv(e, ln, *e->convs[ci++], {{&tmp, 0, c, 0}}, H, W, buf, (2 + i) * c,
@@ -1265,6 +1296,7 @@ int irmv_engine_create(const char *weights_path, const irmv_engine_config *cfg, 
   if (e->arch == kArchShuffleKpt && (cfg->conv_impl == IRMV_CONV_DIRECT || getenv("IRMV_NO_RASTER"))) {
     set_error("the ShuffleNetV2 variant runs on the tcgen05 raster kernel only"); return 2;
   }
+  e->up_split = cfg->conv_impl != IRMV_CONV_DIRECT && !getenv("IRMV_NO_RASTER") && !getenv("IRMV_NO_UP_SPLIT");
   // 63 reference convs -> 60 GEMMs (Detect box.0|cls.0 merged per scale)
   auto single = [&](size_t i, int cin_pad, std::vector<int> seg) {
     e->convs.emplace_back(new HostConv(make_conv({&fc[i]}, cin_pad, seg)));
@@ -1344,7 +1376,14 @@ int irmv_engine_create(const char *weights_path, const irmv_engine_config *cfg, 
       if (k == 4) { seg = {128, 64}; if (!inv4.empty()) { for (int c = 0; c < 128; ++c) in_map.push_back(c); for (int c : inv4) in_map.push_back(128 + c); } }
       if (k == 9) seg = {64, 128};
       if (k == 14) seg = {128, 256};
-      if (in_map.empty()) single(fi, cin, seg); else single_p(permuted(fc[fi], in_map, {}), cin, seg);
+      const FileConv f = in_map.empty() ? fc[fi] : permuted(fc[fi], in_map, {});
+      single_p(f, cin, seg);
+      if ((k == 0 || k == 4) && e->up_split) {               // m12.cv1 / m15.cv1: split over the upsampled half (add_c2f)
+        HostConv &hc = *e->convs.back();
+        const FileConv fa = slice_cin(f, 0, seg[0], false), fb = slice_cin(f, seg[0], cin, true);
+        hc.up_a.reset(new HostConv(make_conv({&fa}, seg[0], {seg[0]})));
+        hc.up_b.reset(new HostConv(make_conv({&fb}, seg[1], {seg[1]})));
+      }
     }
   }
   const size_t head0 = neck0 + 18;
@@ -1417,7 +1456,10 @@ int irmv_engine_create(const char *weights_path, const irmv_engine_config *cfg, 
     IRMV_CUDA(cudaMemcpy(d->d_w, d->w.data(), d->w.size() * 2, cudaMemcpyHostToDevice));
     IRMV_CUDA(cudaMemcpy(d->d_b, d->b.data(), d->b.size() * 4, cudaMemcpyHostToDevice));
   }
-  for (auto &c : e->convs) if (!upload(*c)) return 5;
+  for (auto &c : e->convs) {
+    if (!upload(*c)) return 5;
+    if (c->up_a && (!upload(*c->up_a) || !upload(*c->up_b))) return 5;
+  }
   {
     // stem weights: conv0 as FP32 [16][9 taps][3] + bias
     const HostConv &c0 = *e->convs[0];
@@ -1492,6 +1534,8 @@ void irmv_engine_destroy(irmv_engine *e) {
   }
   for (auto &c : e->convs) {
     cudaFree(c->d_plain); cudaFree(c->d_tiled); cudaFree(c->d_raster); cudaFree(c->d_bias);
+    for (HostConv *u : {c->up_a.get(), c->up_b.get()})
+      if (u) { cudaFree(u->d_plain); cudaFree(u->d_tiled); cudaFree(u->d_raster); cudaFree(u->d_bias); }
   }
   for (auto &d : e->dws) { cudaFree(d->d_w); cudaFree(d->d_b); }
   for (uint8_t *b : e->sh_blobs) cudaFree(b);
