@@ -39,15 +39,26 @@ def name_ops(ops):
     launch with a fused 1x1 tail consumes two entries.  Returns (name, hw, cin, cout, k, s, flop_per_frame)."""
     L = layers(fused=False)[1:]
     out, i = [], 0
+    split_b = None
     for o in ops:
         if o["kind"] == "pool":
             assert L[i][0] == "POOL"
             out.append(("POOL", 20, 0, 0, 0, 0, 0.0))
             i += 1
             continue
+        if split_b:                       # second launch of a 1x1 over concat(upsample(a), b): W_b at full resolution
+            n, hw, cin, cout, k, s = split_b
+            split_b = None
+            out.append((n + "b", hw, o["cin"], cout, k, s, 2.0 * hw * hw * o["cin"] * cout))
+            continue
         n, hw, cin, cout, k, s = L[i]
-        fl = 2.0 * hw * hw * k * k * cin * cout
         i += 1
+        if n in ("m12.cv1", "m15.cv1") and o["cin"] != cin:
+            # first launch: W_a at the upsampled input's own (half) resolution, no bias / activation
+            split_b = (n, hw, cin, cout, k, s)
+            out.append((n + "a", hw // 2, o["cin"], cout, k, s, 2.0 * (hw // 2) ** 2 * o["cin"] * cout))
+            continue
+        fl = 2.0 * hw * hw * k * k * cin * cout
         if o["tail_cout"]:
             n2, hw2, cin2, cout2, k2, s2 = L[i]
             fl += 2.0 * hw2 * hw2 * cin2 * cout2

@@ -3,7 +3,7 @@
 # only after the same command has exited 0 without ncu.  usage: scripts/collect_profiles.sh [tag]
 set -u
 T=${1:-r2}
-KRX='regex:^(conv_raster_kernel|conv_tc_kernel|decode_kernel|nms_kernel|pnp_kernel|quads_from_dets_kernel|set_src_kernel|sppf_pool_kernel|stem_kernel|stem_bayer2x_kernel|dwconv3x3_kernel|kpts_from_dets_kernel|quads_from_kpts_kernel)$'
+KRX='regex:^(conv_raster_kernel|conv_tc_kernel|decode_kernel|nms_kernel|pnp_kernel|quads_from_dets_kernel|set_src_kernel|sppf_pool_kernel|stem_kernel|stem_bayer2x_kernel|dwconv3x3_kernel|shuffle_unit_kernel|kpts_from_dets_kernel|quads_from_kpts_kernel)$'
 mkdir -p gpurun_out
 BENCH="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extras --clock-warmup-s 0"
 # 1. launch list of the bench command: 3 warm-up steps + the timed step (= replays 7 and 8), then the end-to-end loop
@@ -13,12 +13,12 @@ ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name "$KRX" -
 # 2. per-launch counters of one eager 128-frame replay
 scripts/ncu_replay_metrics.sh 128 ${T}_replay128_metrics
 cp gpurun_out/ops.json gpurun_out/${T}_ops.json
-# 3. full captures: top GEMM (Detect P3 box.0|cls.0), the gather kernel's largest launch (m15.cv1), the stem,
+# 3. full captures: top GEMM (Detect P3 box.0|cls.0), the gather kernel's largest launch (m5), the stem,
 #    decode, NMS, PnP
 OP=$(python -c "import sys, json; sys.path.insert(0, 'scripts'); from analyze_launches import name_ops; print(1 + [n[0] for n in name_ops(json.load(open('gpurun_out/${T}_ops.json'))) if n[0] != 'POOL'].index('h0.01'))")
 scripts/ncu_one_conv.sh $OP 128 ${T}_raster_h0
-OP2=$(python -c "import sys, json; sys.path.insert(0, 'scripts'); from analyze_launches import name_ops; print(1 + [n[0] for n in name_ops(json.load(open('gpurun_out/${T}_ops.json'))) if n[0] != 'POOL'].index('m15.cv1'))")
-RASTER= scripts/ncu_one_conv.sh $OP2 128 ${T}_gather_m15 conv_tc_kernel
+OP2=$(python -c "import sys, json; sys.path.insert(0, 'scripts'); from analyze_launches import name_ops; print(1 + [n[0] for n in name_ops(json.load(open('gpurun_out/${T}_ops.json'))) if n[0] != 'POOL'].index('m5'))")
+RASTER= scripts/ncu_one_conv.sh $OP2 128 ${T}_gather_m5 conv_tc_kernel
 scripts/ncu_stem.sh ${T}_stem
 for k in decode_kernel nms_kernel pnp_kernel; do
   ncu --set full --clock-control none --import-source on --kernel-name regex:^${k}$ --launch-skip 2 --launch-count 1 \
@@ -26,10 +26,14 @@ for k in decode_kernel nms_kernel pnp_kernel; do
   ncu -i gpurun_out/${T}_${k}.ncu-rep --page raw --csv > gpurun_out/${T}_${k}_raw.csv 2>/dev/null
   ncu -i gpurun_out/${T}_${k}.ncu-rep --page source --csv > gpurun_out/${T}_${k}_source.csv 2>/dev/null
 done
-# 4. depthwise 3x3 kernel of the ShuffleNetV2 variant (largest launch: d1.b1.dw, 16 channels, 320x320 -> 160x160, 64 frames)
+# 4. ShuffleNetV2 variant at 64 frames: per-op times fused / unfused, the fused unit kernels (seven launches of one
+#    replay), and the depthwise 3x3 kernel of the one-launch-per-conv path (largest launch: d1.b1.dw, 16 channels,
+#    320x320 -> 160x160)
 python scripts/profile_ops_any.py 64 shufflenetv2-pose > gpurun_out/${T}_ops_shuffle64.log 2>&1 || exit 1
+python scripts/profile_ops_any.py 64 shufflenetv2-pose unfused > gpurun_out/${T}_ops_shuffle64_unfused.log 2>&1 || exit 1
+scripts/ncu_shuffle_unit.sh ${T}_shuffle_unit
 ncu --set full --clock-control none --import-source on --kernel-name regex:dwconv3x3_kernel --launch-skip 39 --launch-count 1 \
-  -o gpurun_out/${T}_dwconv -f python scripts/profile_ops_any.py 64 shufflenetv2-pose > gpurun_out/${T}_dwconv.log 2>&1
+  -o gpurun_out/${T}_dwconv -f python scripts/profile_ops_any.py 64 shufflenetv2-pose unfused > gpurun_out/${T}_dwconv.log 2>&1
 ncu -i gpurun_out/${T}_dwconv.ncu-rep --page raw --csv > gpurun_out/${T}_dwconv_raw.csv 2>/dev/null
 ncu -i gpurun_out/${T}_dwconv.ncu-rep --page source --csv > gpurun_out/${T}_dwconv_source.csv 2>/dev/null
 # 5. light-bar / armor extraction on its own workload
