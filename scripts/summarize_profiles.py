@@ -73,7 +73,8 @@ def main():
            "compare SHARES, not absolutes.", ""]
     # ---- launch list of the bench command
     L = read_long(os.path.join(P, f"{TAG}_bench_launches.csv"))
-    starts = [i for i, k in enumerate(L) if k["name"] == "set_src_kernel"]
+    # a replay = [set_src (only when the source pointer of the lane changed)] + stem + ...: split at the stem launches
+    starts = [i - 1 if i and L[i - 1]["name"] == "set_src_kernel" else i for i, k in enumerate(L) if k["name"].startswith("stem_")]
     # launches 0..: three warm-up steps, then the timed step = replays 7 and 8 (two 128-frame replays per 256-frame step)
     step = L[starts[6]:starts[8]]
     tot = sum(k["gpu__time_duration.sum"] for k in step)
@@ -83,8 +84,8 @@ def main():
         agg[k["name"]][1] += k["gpu__time_duration.sum"]
     out += ["## 1. Launch list of `python bench.py --steps 1 --warmup 3 --no-cpu-baseline`",
             f"`profiles/{TAG}_bench_launches.csv` (the first {len(L)} launches of the engine's kernels: three warm-up steps, the timed step, the start of the end-to-end loop; the table is the timed step = two",
-            f"128-frame replays = {len(step)} launches: set_src + stem + {sum(1 for k in step if k['name'].startswith('conv_')) // 2} GEMM launches + pool + decode + NMS + quads + PnP per replay;",
-            "eleven 1x1 convs run as fused tails of their producers, conv0 inside the stem)", "",
+            f"128-frame replays = {len(step)} launches: [set_src] + stem + {sum(1 for k in step if k['name'].startswith('conv_')) // 2} GEMM launches + pool + decode + NMS + quads + PnP per replay;",
+            "eleven 1x1 convs run as fused tails of their producers, conv0 inside the stem, the two neck convs over concat(upsample(a), b) as two raster launches each)", "",
             "| kernel | launches | total us | share |", "|---|---|---|---|"]
     for n, (c, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
         out.append(f"| `{n}` | {c} | {t/1e3:.1f} | {100*t/tot:.1f} % |")
