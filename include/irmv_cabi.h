@@ -98,7 +98,9 @@ typedef struct irmv_engine_config {
                              * reserved[1] != 0: do not fuse 1x1 convs into their producers (every module
                              * output is then materialised and readable through irmv_engine_read_tensor);
                              * reserved[2] != 0: ShuffleNetV2 variant: one launch per convolution instead of one fused
-                             * kernel per unit */
+                             * kernel per unit;
+                             * reserved[3] != 0: the neck's 1x1 convs over concat(upsample(a), b) as ONE gather-kernel
+                             * launch each instead of two raster-kernel launches (W_a at a's resolution + W_b) */
 } irmv_engine_config;
 
 /* One armor as IrmDetector::extract_armors builds it (src/irm_detector.cpp:292-355): slot i of a frame

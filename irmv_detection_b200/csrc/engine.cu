@@ -1296,7 +1296,7 @@ int irmv_engine_create(const char *weights_path, const irmv_engine_config *cfg, 
   if (e->arch == kArchShuffleKpt && (cfg->conv_impl == IRMV_CONV_DIRECT || getenv("IRMV_NO_RASTER"))) {
     set_error("the ShuffleNetV2 variant runs on the tcgen05 raster kernel only"); return 2;
   }
-  e->up_split = cfg->conv_impl != IRMV_CONV_DIRECT && !getenv("IRMV_NO_RASTER") && !getenv("IRMV_NO_UP_SPLIT");
+  e->up_split = cfg->conv_impl != IRMV_CONV_DIRECT && cfg->reserved[3] == 0 && !getenv("IRMV_NO_RASTER") && !getenv("IRMV_NO_UP_SPLIT");
   // 63 reference convs -> 60 GEMMs (Detect box.0|cls.0 merged per scale)
   auto single = [&](size_t i, int cin_pad, std::vector<int> seg) {
     e->convs.emplace_back(new HostConv(make_conv({&fc[i]}, cin_pad, seg)));

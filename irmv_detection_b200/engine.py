@@ -53,7 +53,7 @@ class YoloEngine:
                  sub_batch: int = 0, num_lanes: int = 0, num_slots: int = 3, device: int = 0,
                  conv_impl: int = L.CONV_TCGEN05, score_thr: float = 0.25, iou_thr: float = 0.45,
                  max_det: int = 100, use_graph: bool = True, fused_stem: bool = True, fuse_tails: bool = True,
-                 fuse_units: bool = True):
+                 fuse_units: bool = True, split_upsample_convs: bool = True):
         lib = L.lib()
         wpath = onnx_file_path if onnx_file_path.endswith(".irmw") else weights_path_for(onnx_file_path)
         if not os.path.exists(wpath):
@@ -74,6 +74,7 @@ class YoloEngine:
         cfg.reserved[0] = 0 if fused_stem else 1
         cfg.reserved[1] = 0 if fuse_tails else 1
         cfg.reserved[2] = 0 if fuse_units else 1          # ShuffleNetV2 variant: one kernel per unit (default) or one per conv
+        cfg.reserved[3] = 0 if split_upsample_convs else 1   # neck cv1 over concat(upsample(a), b): two raster launches or one gather launch
         self._cfg = cfg
         self._h = C.c_void_p()
         self._lib = lib

@@ -349,17 +349,19 @@ def _oracle_forward(weights, x_nhwc8):
     return taps, outs, boxes.numpy(), scores.numpy()
 
 
-@pytest.mark.parametrize("impl", ["direct", "tcgen05", "tcgen05_unfused"])
+@pytest.mark.parametrize("impl", ["direct", "tcgen05", "tcgen05_unfused", "tcgen05_gather_neck"])
 def test_network_parity(frames, weights_seed0, impl):
     import irmv_detection_b200 as irmv
     from oracle import nms_ref as N
     fr = frames[[0, 2, 3]]                       # rm_test.jpg + two synthetic variants
     n = fr.shape[0]
     # "tcgen05" is the production program (1x1 consumers fused into their producers: module taps m1 and m3
-    # are then not materialised and is skipped below); "tcgen05_unfused" materialises every module output
+    # are then not materialised and is skipped below); "tcgen05_unfused" materialises every module output;
+    # "tcgen05_gather_neck" runs the neck's cv1 over concat(upsample(a), b) as one gather-kernel launch instead of
+    # the default two raster launches (test_split_upsample_convs_match_the_gather_path)
     eng = irmv.YoloEngine(weights_seed0, (1280, 1024), max_batch=n, sub_batch=n,
                           conv_impl=irmv.CONV_DIRECT if impl == "direct" else irmv.CONV_TCGEN05,
-                          fuse_tails=(impl != "tcgen05_unfused"))
+                          fuse_tails=(impl != "tcgen05_unfused"), split_upsample_convs=(impl != "tcgen05_gather_neck"))
     dets = eng.detect_batch(fr)
     # the engine's stem kernel fuses preprocess + conv0, so the network input is not materialised;
     # the stand-alone preprocess entry point produces the identical tensor (same device code)
@@ -371,7 +373,7 @@ def test_network_parity(frames, weights_seed0, impl):
         try:
             got = eng.read_tensor(name).astype(np.float32)
         except RuntimeError:
-            assert impl == "tcgen05" and name in ("m1", "m3"), name   # fused into m2.cv1 / m4.cv1
+            assert impl in ("tcgen05", "tcgen05_gather_neck") and name in ("m1", "m3"), name   # fused into m2.cv1 / m4.cv1
             continue
         seen += 1
         ref = ref.permute(0, 2, 3, 1).numpy()
@@ -1295,6 +1297,34 @@ def test_weight_file_validation(tmp_path, weights_seed0):
         p.write_bytes(data)
         with pytest.raises(irmv.IrmvError):
             irmv.YoloEngine(str(p), (1280, 1024))
+
+
+def test_split_upsample_convs_match_the_gather_path(frames, weights_seed0):
+    """The neck's cv1 over concat(upsample(a), b) runs as W_a . a at a's resolution + W_b . b with the partial sum
+    added before the activation (two raster-kernel launches, conv_raster RES = 2) by default, or as one
+    gather-kernel launch (cfg.reserved[3]).  Same network either way: the module outputs agree to FP16 rounding of
+    the partial sum, both launch lists are what the design says (4 vs 6 gather launches), and the decoded boxes /
+    scores of the two FP16 paths -- each within the north_star tolerance of the FP32 oracle on its own
+    (test_network_parity[tcgen05], [tcgen05_gather_neck]) -- lie within twice that of each other."""
+    import irmv_detection_b200 as irmv
+    _cuda()
+    fr = frames[[0, 2, 3]]                       # the frames of test_network_parity
+    a = irmv.YoloEngine(weights_seed0, (1280, 1024), max_batch=3, sub_batch=3)
+    b = irmv.YoloEngine(weights_seed0, (1280, 1024), max_batch=3, sub_batch=3, split_upsample_convs=False)
+    ga = sum(1 for o in a.describe_ops() if o["kind"] == "conv" and not o["raster"])
+    gb = sum(1 for o in b.describe_ops() if o["kind"] == "conv" and not o["raster"])
+    assert (ga, gb) == (4, 6)
+    assert len(a.describe_ops()) == len(b.describe_ops()) + 2
+    da, db = a.detect_batch(fr), b.detect_batch(fr)
+    for name in ("m12", "m15", "m18", "m21"):
+        x, y = a.read_tensor(name).astype(np.float32), b.read_tensor(name).astype(np.float32)
+        assert np.abs(x - y).max() <= 4e-3 * max(np.abs(y).max(), 1.0), name
+    box = [np.concatenate([e.read_tensor(f"box{i}").reshape(3, -1, 64) for i in range(3)], 1) for e in (a, b)]
+    cls = [np.concatenate([e.read_tensor(f"cls{i}").reshape(3, -1, 16) for i in range(3)], 1) for e in (a, b)]
+    (ba, sa), (bb, sb) = irmv.decode(box[0], cls[0]), irmv.decode(box[1], cls[1])
+    assert np.abs(sa - sb).max() < 2 * SCORE_TOL and np.abs(ba - bb).max() < 2 * BOX_TOL_PX
+    assert sum(len(d) for d in da) > 0 and abs(sum(len(d) for d in da) - sum(len(d) for d in db)) <= 2
+    a.close(); b.close()
 
 
 # ------------------------------------------------------- ShuffleNetV2-backbone keypoint detector (configs[2])
