@@ -189,9 +189,10 @@ cudaError_t launch_dwconv3x3(const DwParams &p, cudaStream_t s);
 
 // ---------------------------------------------------------------- fused ShuffleNetV2 units (shuffle_unit.cu)
 // The unit's constants as ONE blob the kernel fetches with a single bulk copy (byte offsets, all 16-byte
-// aligned): 1x1 weights as [h][K + 8] halves (pw1: cin -> h, pw2: h -> h, down only: branch-1 1x1 cin -> h),
-// depthwise weights as FP32 [planes][9][8] (dw on the 1x1 -> dw -> 1x1 path, down only: dwa on the input),
-// FP32 biases b1[h] b2[h] ba[h] dwb[h] dwab[cin].
+// aligned): 1x1 weights as [h][K + 8] halves (pw1: cin -> h, pw2: h -> h, down only: branch-1 1x1 cin -> h);
+// depthwise weights as the B-operand table of the block-diagonal GEMM the kernel runs them as,
+// [planes][10 taps (9 + a zero tap)][8 channels] 32-bit words = the FP16 weight in the half its channel parity
+// selects (dw on the 1x1 -> dw -> 1x1 path, down only: dwa on the input); FP32 biases b1[h] b2[h] ba[h] dwb[h] dwab[cin].
 struct ShuffleBlobLayout { int w1, w2, wa, dw, dwa, bias, bytes; };
 __host__ __device__ inline ShuffleBlobLayout shuffle_blob_layout(int down, int cin, int h) {
   ShuffleBlobLayout L;
@@ -199,8 +200,8 @@ __host__ __device__ inline ShuffleBlobLayout shuffle_blob_layout(int down, int c
   L.w2 = L.w1 + h * (cin + 8) * 2;
   L.wa = L.w2 + h * (h + 8) * 2;
   L.dw = L.wa + (down ? h * (cin + 8) * 2 : 0);
-  L.dwa = L.dw + (h / 8) * 72 * 4;
-  L.bias = L.dwa + (down ? (cin / 8) * 72 * 4 : 0);
+  L.dwa = L.dw + (h / 8) * 80 * 4;
+  L.bias = L.dwa + (down ? (cin / 8) * 80 * 4 : 0);
   L.bytes = L.bias + (4 * h + cin) * 4;
   return L;
 }

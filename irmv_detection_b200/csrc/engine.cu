@@ -1415,8 +1415,17 @@ int irmv_engine_create(const char *weights_path, const irmv_engine_config *cfg, 
       memcpy(blob.data() + boff, hc.bias.data(), (size_t)h * 4);
     };
     auto put_dw = [&](std::vector<uint8_t> &blob, int off, const HostDw &d, int boff) {
-      float *w = reinterpret_cast<float *>(blob.data() + off);
-      for (size_t i = 0; i < d.w.size(); ++i) w[i] = __half2float(d.w[i]);
+      // d.w is [planes][9 taps][8 channels] FP16 -> [planes][10][8] words, the weight in the half of its channel parity
+      uint32_t *w = reinterpret_cast<uint32_t *>(blob.data() + off);
+      const int planes = d.c / 8;
+      for (int p = 0; p < planes; ++p)
+        for (int t = 0; t < 9; ++t)
+          for (int c = 0; c < 8; ++c) {
+            uint16_t bits;
+            const __half hv = d.w[((size_t)p * 9 + t) * 8 + c];
+            memcpy(&bits, &hv, 2);
+            w[(p * 10 + t) * 8 + c] = (c & 1) ? ((uint32_t)bits << 16) : (uint32_t)bits;
+          }
       memcpy(blob.data() + boff, d.b.data(), d.b.size() * 4);
     };
     for (int sgi = 0; sgi < 4; ++sgi) {

@@ -66,91 +66,88 @@ __device__ __forceinline__ float silu_f(float x) {
   return fmaf(h, t, h);
 }
 
-// Pointwise conv as a GEMM over a shared-memory tile: out[m][n] = silu(sum_k A[m][k] * W[n][k] + bias[n]),
-// K = N = C (every unit of the backbone has cin == h on the fused stages).
-//   sA: [C/8][Mp][8] halves (plane-major, Mp = M rounded up to 16); sW: [C][C + 8] halves; bias: [C] floats.
-// A warp takes m-tiles round-robin and holds all C/8 n-tile accumulators of an m-tile at once (the A fragments
-// are loaded once, the B fragments stream from shared memory, C/8 independent HMMA chains).
-// row(m) -> a per-row cookie, computed once per m-tile for the lane's two rows (m0 + g, m0 + g + 8);
-// epi(cookie, nt, packed): nt-th n-tile, packed = the two activated FP16 values of channels nt*8 + 2t, + 1.
-template <int C, typename Row, typename Epi>
-__device__ __forceinline__ void pw_gemm(const __half *sA, int M, int Mp, const __half *sW, const float *bias,
-                                        int warp, int lane, Row row, Epi epi) {
+__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+  const __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t *>(&h);
+}
+
+// Pointwise conv of one 16-pixel m-tile: out[m][n] = silu(sum_k A[m][k] * W[n][k] + bias[n]), K = N = C (every unit of
+// the backbone has cin == h on the fused stages).  a: the m-tile's A fragments (a[ks] = k-step ks: planes 2ks, 2ks+1);
+// sW: [C][C + 8] halves; bias: [C] floats.  All C/8 n-tile accumulators are live at once (C/8 independent HMMA
+// chains, the B fragments stream from shared memory).  epi(cookie, nt, packed): row cookie r0 = row m0 + g,
+// r1 = row m0 + g + 8; packed = the two activated FP16 values of channels nt*8 + 2t, + 1.
+template <int C, typename Cookie, typename Epi>
+__device__ __forceinline__ void pw_tile(const uint32_t (&a)[C / 16][4], const __half *sW, const float *bias, int g, int t,
+                                        Cookie r0, Cookie r1, Epi epi) {
   constexpr int KS = C / 16, NTL = C / 8, WP2 = (C + 8) / 2;                   // k-steps, n-tiles, weight row pitch in 32-bit words
-  const int g = lane >> 2, t = lane & 3;
-  const uint32_t *A32 = reinterpret_cast<const uint32_t *>(sA);
   const uint32_t *W32 = reinterpret_cast<const uint32_t *>(sW) + g * WP2 + t;
   const float2 *b2 = reinterpret_cast<const float2 *>(bias) + t;
-#pragma unroll(C <= 32 ? 2 : 1)
-  for (int m0 = warp * 16; m0 < M; m0 += (NT / 32) * 16) {
-    const auto r0 = row(m0 + g), r1 = row(m0 + g + 8);
-    uint32_t a[KS][4];
-    const uint32_t *ap = A32 + (m0 + g) * 4 + t;
+  float c[NTL][4];
 #pragma unroll
-    for (int ks = 0; ks < KS; ++ks) {                                          // plane 2ks / 2ks+1, pixel m0+g (+8), channels 2t..2t+1
-      a[ks][0] = ap[(2 * ks) * Mp * 4]; a[ks][1] = ap[(2 * ks) * Mp * 4 + 32];
-      a[ks][2] = ap[(2 * ks + 1) * Mp * 4]; a[ks][3] = ap[(2 * ks + 1) * Mp * 4 + 32];
-    }
-    float c[NTL][4];
+  for (int nt = 0; nt < NTL; ++nt) {
+    const float2 bv = b2[nt * 4];
+    c[nt][0] = bv.x; c[nt][1] = bv.y; c[nt][2] = bv.x; c[nt][3] = bv.y;
+  }
 #pragma unroll
-    for (int nt = 0; nt < NTL; ++nt) {
-      const float2 bv = b2[nt * 4];
-      c[nt][0] = bv.x; c[nt][1] = bv.y; c[nt][2] = bv.x; c[nt][3] = bv.y;
-    }
+  for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
-    for (int ks = 0; ks < KS; ++ks)
+    for (int nt = 0; nt < NTL; ++nt)
+      mma16816(c[nt], a[ks][0], a[ks][1], a[ks][2], a[ks][3], W32[nt * 8 * WP2 + ks * 8], W32[nt * 8 * WP2 + ks * 8 + 4]);
 #pragma unroll
-      for (int nt = 0; nt < NTL; ++nt) {
-        const uint32_t b0 = W32[nt * 8 * WP2 + ks * 8], b1 = W32[nt * 8 * WP2 + ks * 8 + 4];
-        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                     : "+f"(c[nt][0]), "+f"(c[nt][1]), "+f"(c[nt][2]), "+f"(c[nt][3])
-                     : "r"(a[ks][0]), "r"(a[ks][1]), "r"(a[ks][2]), "r"(a[ks][3]), "r"(b0), "r"(b1));
-      }
-#pragma unroll
-    for (int nt = 0; nt < NTL; ++nt) {
-      const __half2 h0 = __floats2half2_rn(silu_f(c[nt][0]), silu_f(c[nt][1])), h1 = __floats2half2_rn(silu_f(c[nt][2]), silu_f(c[nt][3]));
-      epi(r0, nt, *reinterpret_cast<const uint32_t *>(&h0));
-      epi(r1, nt, *reinterpret_cast<const uint32_t *>(&h1));
-    }
+  for (int nt = 0; nt < NTL; ++nt) {
+    epi(r0, nt, pack_h2(silu_f(c[nt][0]), silu_f(c[nt][1])));
+    epi(r1, nt, pack_h2(silu_f(c[nt][2]), silu_f(c[nt][3])));
   }
 }
 
-// Depthwise 3x3 (+ bias) from a shared-memory tile [PL][inMp][8] whose pixels form rows of pitch inW
-// to [PL][outMp][8]: output pixel (r, c), r < outH, c < outW, reads tile pixels
-// (S*r + ky) * inW + S*c + kx.  w: FP32 [PL][9][8].  Work item = (plane, output pixel), pixel fastest, so
-// small tiles (40 .. 160 pixels) still fill the CTA's 256 threads.
-template <int PL, int S>
-__device__ __forceinline__ void dw_tile(const __half *sIn, int inMp, int inW, const float *w, const float *bias,
-                                        __half *sOut, int outMp, int outH, int outW, uint32_t inv_outW, int tid) {
-  const int npx = outH * outW;
-  const uint32_t inv_npx = recip_u16(npx);
-  for (int i = tid; i < npx * PL; i += NT) {
-    const int p = fast_div(i, inv_npx), px = i - p * npx;
-    const int r = fast_div(px, inv_outW), c = px - r * outW;
-    float acc[8];
-    {
-      const float4 b0 = *reinterpret_cast<const float4 *>(bias + p * 8), b1 = *reinterpret_cast<const float4 *>(bias + p * 8 + 4);
-      acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+// A fragments of the m-tile starting at pixel m0 of a shared-memory tile [C/8][Mp][8] halves (plane-major): every
+// register is one conflict-free 32-bit load (plane 2ks / 2ks+1, pixel m0+g / m0+g+8, channels 2t, 2t+1).
+template <int C>
+__device__ __forceinline__ void load_frags(const __half *sA, int Mp, int m0, int g, int t, uint32_t (&a)[C / 16][4]) {
+  const uint32_t *ap = reinterpret_cast<const uint32_t *>(sA) + (m0 + g) * 4 + t;
+#pragma unroll
+  for (int ks = 0; ks < C / 16; ++ks) {
+    a[ks][0] = ap[(2 * ks) * Mp * 4]; a[ks][1] = ap[(2 * ks) * Mp * 4 + 32];
+    a[ks][2] = ap[(2 * ks + 1) * Mp * 4]; a[ks][3] = ap[(2 * ks + 1) * Mp * 4 + 32];
+  }
+}
+
+// Depthwise 3x3 (+ bias) of one 16-pixel m-tile ON THE TENSOR CORES, result delivered as the A fragments of the 1x1 conv
+// that follows.  Per 8-channel plane the depthwise conv is the GEMM
+//     out[px][n] = sum_{k = (tap, c')} in[px + off(tap)][c'] * (c' == n ? w[tap][n] : 0),
+// K = 9 taps x 8 channels padded to 80 = five m16n8k16 steps of two taps each: an A register is one 32-bit load from the
+// tile at the tap's pixel offset, a B register is the lane's table word (blob layout) or zero.  Seven eighths of the MACs
+// multiply by zero, which the tensor pipe has to spare; the CUDA-core form costs ~17 issue slots per output value
+// (convert + FMA per tap), this one 0.3.  The accumulator fragment of plane p (rows g / g+8, channels 2t, 2t+1) IS the A
+// fragment register pair of plane p in the following 1x1 GEMM, so the depthwise output never touches shared memory.
+//   sIn: [PL][inMp][8] halves, pixels in rows of pitch inW; base0 / base1: tile pixel of the window's corner for rows
+//   g / g+8; tab: [PL][10][8] words; bias: [PL * 8]; keep: all-ones in the lanes with t == g / 2, else zero.
+template <int PL>
+__device__ __forceinline__ void dw_frags(const __half *sIn, int inMp, int inW, int base0, int base1, const uint32_t *tab,
+                                         const float *bias, int g, int t, uint32_t keep, uint32_t (&a)[PL / 2][4]) {
+  const uint32_t *i0 = reinterpret_cast<const uint32_t *>(sIn) + base0 * 4 + t;
+  const uint32_t *i1 = reinterpret_cast<const uint32_t *>(sIn) + base1 * 4 + t;
+  const float2 *b2 = reinterpret_cast<const float2 *>(bias) + t;
+#pragma unroll
+  for (int p = 0; p < PL; ++p) {
+    const float2 bv = b2[p * 4];
+    float c[4] = {bv.x, bv.y, bv.x, bv.y};
+    const uint32_t *tp = tab + p * 80 + g;
+#pragma unroll
+    for (int ks = 0; ks < 5; ++ks) {
+      constexpr int dummy = 0; (void)dummy;
+      const int ta = 2 * ks, tb = ks < 4 ? 2 * ks + 1 : 8;                     // the pad tap re-reads tap 8's pixel (finite) against zero weights
+      const int oa = ((ta / 3) * inW + ta % 3) * 4, ob = ((tb / 3) * inW + tb % 3) * 4;
+      mma16816(c, i0[p * inMp * 4 + oa], i1[p * inMp * 4 + oa], i0[p * inMp * 4 + ob], i1[p * inMp * 4 + ob],
+               tp[(2 * ks) * 8] & keep, tp[(2 * ks + 1) * 8] & keep);
     }
-    const __half *ip = sIn + ((size_t)p * inMp + (size_t)(S * r) * inW + S * c) * 8;
-    const float *wp = w + p * 72;
-#pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const uint4 v = *reinterpret_cast<const uint4 *>(ip + (ky * inW + kx) * 8);
-        const float4 w0 = *reinterpret_cast<const float4 *>(wp + (ky * 3 + kx) * 8), w1 = *reinterpret_cast<const float4 *>(wp + (ky * 3 + kx) * 8 + 4);
-        const __half2 *hv = reinterpret_cast<const __half2 *>(&v);
-        const float2 f0 = __half22float2(hv[0]), f1 = __half22float2(hv[1]), f2 = __half22float2(hv[2]), f3 = __half22float2(hv[3]);
-        acc[0] = fmaf(f0.x, w0.x, acc[0]); acc[1] = fmaf(f0.y, w0.y, acc[1]);
-        acc[2] = fmaf(f1.x, w0.z, acc[2]); acc[3] = fmaf(f1.y, w0.w, acc[3]);
-        acc[4] = fmaf(f2.x, w1.x, acc[4]); acc[5] = fmaf(f2.y, w1.y, acc[5]);
-        acc[6] = fmaf(f3.x, w1.z, acc[6]); acc[7] = fmaf(f3.y, w1.w, acc[7]);
-      }
-    __half2 o[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) o[q] = __floats2half2_rn(acc[2 * q], acc[2 * q + 1]);
-    *reinterpret_cast<uint4 *>(sOut + ((size_t)p * outMp + px) * 8) = *reinterpret_cast<uint4 *>(o);
+    a[p >> 1][(p & 1) * 2] = pack_h2(c[0], c[1]);
+    a[p >> 1][(p & 1) * 2 + 1] = pack_h2(c[2], c[3]);
   }
 }
 
@@ -160,29 +157,29 @@ __global__ void __launch_bounds__(NT, C == 16 ? 3 : 2) shuffle_unit_kernel(const
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int PL = C / 8, S = DOWN ? 2 : 1;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
   const int H = p.H, W = p.W, TH = p.TH;
   const int Hin = S * H, Win = S * W;
   // input tile of one plane: rows S*y0 - 1 .. S*(y0 + TH - 1) + 1 as one run of raster pixels starting at
   // column -1 (pitch WC = Win + 1), plus the pixel after it (the right neighbour of the last pixel)
   const int HR = S * TH + (DOWN ? 1 : 2), WC = Win + 1;
   const int HP = HR * WC + 1, HPp = (HP + 15) & ~15;
-  const int TP = TH * W, TPp = (TP + 15) & ~15;
+  const int TP = TH * W;
   const ShuffleBlobLayout L = shuffle_blob_layout(DOWN, C, C);
-  // shared memory: blob | sX [PL][HPp][8] | sT1 [PL][HPp][8] | sU [PL][TPp][8] | output plane offsets | 2 mbarriers
+  // shared memory: blob | sX [PL][HPp][8] | sT1 [PL][HPp][8] | output plane offsets | 2 mbarriers
   const __half *sW1 = reinterpret_cast<const __half *>(smem + L.w1), *sW2 = reinterpret_cast<const __half *>(smem + L.w2);
   const __half *sWa = reinterpret_cast<const __half *>(smem + L.wa);
-  const float *sDw = reinterpret_cast<const float *>(smem + L.dw), *sDwa = reinterpret_cast<const float *>(smem + L.dwa);
+  const uint32_t *sDw = reinterpret_cast<const uint32_t *>(smem + L.dw), *sDwa = reinterpret_cast<const uint32_t *>(smem + L.dwa);
   const float *sB = reinterpret_cast<const float *>(smem + L.bias);         // b1[C] b2[C] ba[C] dwb[C] dwab[C]
   __half *sX = reinterpret_cast<__half *>(smem + L.bytes);
   __half *sT1 = sX + (size_t)PL * HPp * 8;
-  __half *sU = sT1 + (size_t)PL * HPp * 8;
-  long long *sOff = reinterpret_cast<long long *>(sU + (size_t)PL * TPp * 8);   // [PL]: half offset of the plane the nt-th n-tile of the second 1x1 writes
+  long long *sOff = reinterpret_cast<long long *>(sT1 + (size_t)PL * HPp * 8);   // [PL]: half offset of the plane the nt-th n-tile of the second 1x1 writes
   uint64_t *bars = reinterpret_cast<uint64_t *>(sOff + PL);
   const int tiles_per_img = H / TH, tiles = p.B * tiles_per_img;
   const uint32_t plane_bytes = (uint32_t)HP * 16;
   auto issue = [&](int tile) {                                              // one thread
-    const int t = p.rev ? tiles - 1 - tile : tile;
-    const int b = t / tiles_per_img, y0 = (t - b * tiles_per_img) * TH;
+    const int tt = p.rev ? tiles - 1 - tile : tile;
+    const int b = tt / tiles_per_img, y0 = (tt - b * tiles_per_img) * TH;
     const __half *src = p.in + pr_index(b, S * y0 - 1, -1, Hin, Win) * 8;
     mbar_expect_tx(&bars[0], plane_bytes * PL);
 #pragma unroll 1
@@ -202,12 +199,20 @@ __global__ void __launch_bounds__(NT, C == 16 ? 3 : 2) shuffle_unit_kernel(const
   if (tid < PL) sOff[tid] = (long long)(DOWN ? PL + tid : p.first_plane + run_plane(tid, p.runs)) * p.out_ps;
   __syncthreads();
   mbar_wait(&bars[1], 0);
-  const int t2 = 2 * (lane & 3);
+  const int t2 = 2 * t;
+  const uint32_t keep = (t == (g >> 1)) ? 0xffffffffu : 0u;
   const uint32_t invW = recip_u16(W), invWC = recip_u16(WC);
+  const int n_pw1 = (HP + 15) >> 4, n_out = (TP + 15) >> 4;                 // m-tiles of the first 1x1 / of the unit's output
+  // corner (tile pixel index) of the depthwise window of output pixel m; pixels past the tile re-read its last pixel
+  auto window = [&](int m) -> int {
+    m = m < TP ? m : TP - 1;
+    const int r = fast_div(m, invW), c = m - r * W;
+    return (S * r) * WC + S * c;
+  };
   uint32_t it = 0;
   for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-    const int t = p.rev ? tiles - 1 - tile : tile;
-    const int b = t / tiles_per_img, y0 = (t - b * tiles_per_img) * TH;
+    const int tt = p.rev ? tiles - 1 - tile : tile;
+    const int b = tt / tiles_per_img, y0 = (tt - b * tiles_per_img) * TH;
     const long long out0 = pr_index(b, y0, 0, H, W) * 8;                    // output pixel (y0, 0); the TH rows follow with pitch W + 1
     if (!DOWN) {
       // pass-through half: the planes one run before the unit's, copied to the other buffer of the ping-pong pair
@@ -223,42 +228,49 @@ __global__ void __launch_bounds__(NT, C == 16 ? 3 : 2) shuffle_unit_kernel(const
       }
     }
     mbar_wait(&bars[0], it & 1);
-    // pixels outside the image must be ZERO in T1 (the depthwise conv pads T1, not the first 1x1's input)
     const int ylo = 1 - S * y0, yhi = Hin + 1 - S * y0;                     // tile rows [ylo, yhi) are image rows
-    auto t1_row = [&](int m) -> int {
-      const int r = fast_div(m, invWC), c = m - r * WC;
-      return (c != 0 && r >= ylo && r < yhi) ? m : -1 - m;
-    };
-    auto t1_store = [&](int ck, int nt, uint32_t v) {
-      const bool in = ck >= 0;
-      const int m = in ? ck : -1 - ck;
-      *reinterpret_cast<uint32_t *>(sT1 + ((size_t)nt * HPp + m) * 8 + t2) = in ? v : 0u;
-    };
+    // row cookie of an output pixel: where its channels 2t, 2t+1 of plane 0 go (null: past the tile)
     auto out_row = [&](int m) -> __half * {
       if (m >= TP) return nullptr;
-      return p.out + out0 + (long long)(m + fast_div(m, invW)) * 8 + t2;               // pixel (r, c) sits r pad pixels further along the raster
+      return p.out + out0 + (long long)(m + fast_div(m, invW)) * 8 + t2;    // pixel (r, c) sits r pad pixels further along the raster
     };
-    if (DOWN) {
-      // branch 1, first half: depthwise s2 on the input tile
-      dw_tile<PL, 2>(sX, HPp, WC, sDwa, sB + 4 * C, sU, TPp, TH, W, invW, tid);
+    // ---- phase 1: first 1x1 over the whole input tile -> T1; down units also run their branch 1 (depthwise s2 on the
+    //      input, 1x1 into output planes [0, C/8)), which reads the input tile only
+    for (int item = warp; item < n_pw1 + (DOWN ? n_out : 0); item += NT / 32) {
+      uint32_t a[C / 16][4];
+      if (item < n_pw1) {
+        const int m0 = item * 16;
+        load_frags<C>(sX, HPp, m0, g, t, a);
+        // pixels outside the image must be ZERO in T1 (the depthwise conv pads T1, not the first 1x1's input)
+        auto t1_row = [&](int m) -> int {
+          const int r = fast_div(m, invWC), c = m - r * WC;
+          return (c != 0 && r >= ylo && r < yhi) ? m : -1 - m;
+        };
+        pw_tile<C>(a, sW1, sB, g, t, t1_row(m0 + g), t1_row(m0 + g + 8), [&](int ck, int nt, uint32_t v) {
+          const bool in = ck >= 0;
+          const int m = in ? ck : -1 - ck;
+          *reinterpret_cast<uint32_t *>(sT1 + ((size_t)nt * HPp + m) * 8 + t2) = in ? v : 0u;
+        });
+      } else {
+        const int m0 = (item - n_pw1) * 16;
+        dw_frags<PL>(sX, HPp, WC, window(m0 + g), window(m0 + g + 8), sDwa, sB + 4 * C, g, t, keep, a);
+        pw_tile<C>(a, sWa, sB + 2 * C, g, t, out_row(m0 + g), out_row(m0 + g + 8), [&](__half *o, int nt, uint32_t v) {
+          if (o) *reinterpret_cast<uint32_t *>(o + (long long)nt * p.out_ps) = v;
+        });
+      }
     }
-    // branch 2 / basic unit: first 1x1 over the whole input tile
-    pw_gemm<C>(sX, HP, HPp, sW1, sB, warp, lane, t1_row, t1_store);
-    __syncthreads();                                                        // sX is free, sT1 (and sU) complete
+    __syncthreads();                                                        // sX is free, sT1 complete
     if (tid == 0 && tile + (int)gridDim.x < tiles) issue(tile + gridDim.x);
-    if (DOWN) {
-      // branch 1, second half: 1x1 C -> C into output planes [0, C/8)
-      pw_gemm<C>(sU, TP, TPp, sWa, sB + 2 * C, warp, lane, out_row, [&](__half *o, int nt, uint32_t v) {
-        if (o) *reinterpret_cast<uint32_t *>(o + (long long)nt * p.out_ps) = v;
+    // ---- phase 2: depthwise on T1 -> second 1x1 -> the unit's planes of the output
+    for (int item = warp; item < n_out; item += NT / 32) {
+      const int m0 = item * 16;
+      uint32_t a[C / 16][4];
+      dw_frags<PL>(sT1, HPp, WC, window(m0 + g), window(m0 + g + 8), sDw, sB + 3 * C, g, t, keep, a);
+      pw_tile<C>(a, sW2, sB + C, g, t, out_row(m0 + g), out_row(m0 + g + 8), [&](__half *o, int nt, uint32_t v) {
+        if (o) *reinterpret_cast<uint32_t *>(o + sOff[nt]) = v;
       });
-      __syncthreads();
     }
-    dw_tile<PL, S>(sT1, HPp, WC, sDw, sB + 3 * C, sU, TPp, TH, W, invW, tid);
-    __syncthreads();
-    pw_gemm<C>(sU, TP, TPp, sW2, sB + C, warp, lane, out_row, [&](__half *o, int nt, uint32_t v) {
-      if (o) *reinterpret_cast<uint32_t *>(o + sOff[nt]) = v;
-    });
-    __syncthreads();                                                        // sU / sT1 are rewritten by the next tile
+    __syncthreads();                                                        // sT1 is rewritten by the next tile
   }
 }
 
@@ -267,9 +279,9 @@ __global__ void __launch_bounds__(NT, C == 16 ? 3 : 2) shuffle_unit_kernel(const
 size_t shuffle_unit_smem(const ShuffleUnitParams &p) {
   const int s = p.down ? 2 : 1;
   const int HR = s * p.TH + (p.down ? 1 : 2), WC = s * p.W + 1;
-  const size_t HPp = ((size_t)HR * WC + 1 + 15) & ~(size_t)15, TPp = ((size_t)p.TH * p.W + 15) & ~(size_t)15;
+  const size_t HPp = ((size_t)HR * WC + 1 + 15) & ~(size_t)15;
   const size_t pl = p.h / 8;
-  return (size_t)shuffle_blob_layout(p.down, p.cin, p.h).bytes + (2 * pl * HPp + pl * TPp) * 16 + pl * 8 + 16;
+  return (size_t)shuffle_blob_layout(p.down, p.cin, p.h).bytes + 2 * pl * HPp * 16 + pl * 8 + 16;
 }
 
 int shuffle_unit_ctas_per_sm(const ShuffleUnitParams &p) {
