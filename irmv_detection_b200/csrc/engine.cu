@@ -1410,9 +1410,12 @@ int irmv_engine_create(const char *weights_path, const irmv_engine_config *cfg, 
     auto put_pw = [&](std::vector<uint8_t> &blob, int off, const HostConv &hc, int boff, int h) {
       const int K = hc.cin_eff;
       __half *w = reinterpret_cast<__half *>(blob.data() + off);
+      // every 1x1 of a unit ends in SiLU(x) = x/2 + x/2 * tanh(x/2): the 1/2 is folded into weights and bias (exact in FP16
+      // short of subnormals), so the kernel's accumulator is x/2 already
       for (int n = 0; n < h; ++n)
-        for (int c = 0; c < K; ++c) w[(size_t)n * (K + 8) + c] = hc.w_plain[(size_t)n * hc.kpad + c];
-      memcpy(blob.data() + boff, hc.bias.data(), (size_t)h * 4);
+        for (int c = 0; c < K; ++c) w[(size_t)n * (K + 8) + c] = __float2half(0.5f * __half2float(hc.w_plain[(size_t)n * hc.kpad + c]));
+      float *bb = reinterpret_cast<float *>(blob.data() + boff);
+      for (int n = 0; n < h; ++n) bb[n] = 0.5f * hc.bias[n];
     };
     auto put_dw = [&](std::vector<uint8_t> &blob, int off, const HostDw &d, int boff) {
       // d.w is [planes][9 taps][8 channels] FP16 -> [planes][10][8] words, the weight in the half of its channel parity

@@ -59,8 +59,8 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 __device__ __forceinline__ uint32_t recip_u16(int d) { return 0xFFFFFFFFu / (uint32_t)d + 1u; }
 __device__ __forceinline__ int fast_div(int m, uint32_t inv) { return (int)__umulhi((uint32_t)m, inv); }
 
-__device__ __forceinline__ float silu_f(float x) {
-  const float h = 0.5f * x;
+// SiLU(x) from h = x / 2 (the 1/2 is folded into the 1x1 weights and biases of the blob): h + h * tanh(h), one MUFU
+__device__ __forceinline__ float silu_f(float h) {
   float t;
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
   return fmaf(h, t, h);
@@ -76,7 +76,8 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
   return *reinterpret_cast<const uint32_t *>(&h);
 }
 
-// Pointwise conv of one 16-pixel m-tile: out[m][n] = silu(sum_k A[m][k] * W[n][k] + bias[n]), K = N = C (every unit of
+// Pointwise conv of one 16-pixel m-tile: out[m][n] = silu(2 * (sum_k A[m][k] * W[n][k] + bias[n])) with W, bias = half the
+// layer's (blob), K = N = C (every unit of
 // the backbone has cin == h on the fused stages).  a: the m-tile's A fragments (a[ks] = k-step ks: planes 2ks, 2ks+1);
 // sW: [C][C + 8] halves; bias: [C] floats.  All C/8 n-tile accumulators are live at once (C/8 independent HMMA
 // chains, the B fragments stream from shared memory).  epi(cookie, nt, packed): row cookie r0 = row m0 + g,
@@ -133,17 +134,18 @@ __device__ __forceinline__ void dw_frags(const __half *sIn, int inMp, int inW, i
   const uint32_t *i0 = reinterpret_cast<const uint32_t *>(sIn) + base0 * 4 + t;
   const uint32_t *i1 = reinterpret_cast<const uint32_t *>(sIn) + base1 * 4 + t;
   const float2 *b2 = reinterpret_cast<const float2 *>(bias) + t;
+  const uint32_t *tp = tab + g;
+  const int rw = inW * 4, pw = inMp * 4;                                       // words per tile row / per plane
 #pragma unroll
-  for (int p = 0; p < PL; ++p) {
+  for (int p = 0; p < PL; ++p, i0 += pw, i1 += pw, tp += 80) {
     const float2 bv = b2[p * 4];
     float c[4] = {bv.x, bv.y, bv.x, bv.y};
-    const uint32_t *tp = tab + p * 80 + g;
+    // one pointer per window row: every tap is then [row pointer + constant]
+    const uint32_t *q0[3] = {i0, i0 + rw, i0 + 2 * rw}, *q1[3] = {i1, i1 + rw, i1 + 2 * rw};
 #pragma unroll
     for (int ks = 0; ks < 5; ++ks) {
-      constexpr int dummy = 0; (void)dummy;
       const int ta = 2 * ks, tb = ks < 4 ? 2 * ks + 1 : 8;                     // the pad tap re-reads tap 8's pixel (finite) against zero weights
-      const int oa = ((ta / 3) * inW + ta % 3) * 4, ob = ((tb / 3) * inW + tb % 3) * 4;
-      mma16816(c, i0[p * inMp * 4 + oa], i1[p * inMp * 4 + oa], i0[p * inMp * 4 + ob], i1[p * inMp * 4 + ob],
+      mma16816(c, q0[ta / 3][(ta % 3) * 4], q1[ta / 3][(ta % 3) * 4], q0[tb / 3][(tb % 3) * 4], q1[tb / 3][(tb % 3) * 4],
                tp[(2 * ks) * 8] & keep, tp[(2 * ks + 1) * 8] & keep);
     }
     a[p >> 1][(p & 1) * 2] = pack_h2(c[0], c[1]);
@@ -218,13 +220,27 @@ __global__ void __launch_bounds__(NT, C == 16 ? 3 : 2) shuffle_unit_kernel(const
       // pass-through half: the planes one run before the unit's, copied to the other buffer of the ping-pong pair
       const int rp = p.runs ? (1 << (p.runs - 1)) : PL;
       const int run_px = TP + TH - 1;                                       // the TH rows of a plane are one contiguous run (pads included)
-#pragma unroll 1
-      for (int pl = 0; pl < PL; ++pl) {
-        const int plane = p.first_plane + run_plane(pl, p.runs) - rp;
-        const uint4 *src = reinterpret_cast<const uint4 *>(p.in + (long long)plane * p.in_ps + out0);
-        uint4 *dst = reinterpret_cast<uint4 *>(p.out + (long long)plane * p.out_ps + out0);
-#pragma unroll 2
-        for (int px = tid; px < run_px; px += NT) dst[px] = __ldg(src + px);
+      // four loads in flight per thread before the first store: the copy is latency, not bandwidth
+      const int total = PL * run_px;
+      const uint32_t inv_run = recip_u16(run_px);
+      for (int i0 = tid; i0 < total; i0 += 4 * NT) {
+        uint4 v[4];
+        long long off[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int i = i0 + k * NT;
+          off[k] = -1;
+          if (i < total) {
+            const int pl = fast_div(i, inv_run), px = i - pl * run_px;
+            const int plane = p.first_plane + run_plane(pl, p.runs) - rp;
+            off[k] = out0 + (long long)px * 8;
+            v[k] = __ldg(reinterpret_cast<const uint4 *>(p.in + (long long)plane * p.in_ps + off[k]));
+            off[k] += (long long)plane * p.out_ps;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (off[k] >= 0) *reinterpret_cast<uint4 *>(p.out + off[k]) = v[k];
       }
     }
     mbar_wait(&bars[0], it & 1);
