@@ -11,19 +11,26 @@
 // image.  A tile's input is ONE contiguous run of raster pixels per plane (the zero-padded raster layout,
 // common.cuh: row pitch W + 1, so the left / right / top / bottom padding the depthwise conv wants is
 // already in the run) -> one cp.async.bulk per plane onto an mbarrier, and the next tile's copy is issued
-// as soon as the last reader of the input tile (the first 1x1) is done, i.e. it lands under the depthwise
-// conv, the second 1x1 and the output stores of the current tile.  The 1x1 convolutions run on
-// mma.sync.m16n8k16 straight from the tile (rows = pixels, [plane][pixel][8 channels] -> every A fragment
-// register is one conflict-free 32-bit load); the intermediates stay in shared memory as FP16 (exactly the
-// values the unfused path stores in HBM), the depthwise convs run from there and only the unit's output is
-// written.  HBM traffic of a unit = its input + its output (a basic unit also copies its pass-through half
-// into the other buffer of the stage's ping-pong pair: reading a halo that another CTA may already have
-// rewritten rules out updating in place).
+// as soon as the last reader of the input tile is done, i.e. it lands under the second half of the current
+// tile.  Everything runs on the tensor cores with mma.sync.m16n8k16:
+//   * the 1x1 convolutions straight from the tile (rows = pixels, [plane][pixel][8 channels] -> every A
+//     fragment register is one conflict-free 32-bit load);
+//   * the depthwise 3x3 convs as a block-diagonal GEMM per 8-channel plane (K = 9 taps x 8 channels, see
+//     dw_frags), whose accumulator fragment IS the A fragment of the 1x1 that follows -- the depthwise output
+//     never leaves registers.  (The CUDA-core form, FP16 -> FP32 convert + FMA per tap, cost 17 issue slots
+//     per output value and made the unit issue bound at half the speed.)
+// Per tile: phase 1 = first 1x1 over the input tile -> T1 in shared memory as FP16 (exactly the values the
+// unfused path stores in HBM; zero outside the image, which is the depthwise conv's padding), and for down
+// units branch 1 (depthwise s2 on the input -> 1x1 -> output); barrier; phase 2 = depthwise on T1 -> second
+// 1x1 -> output; barrier.  HBM traffic of a unit = its input + its output (a basic unit also copies its
+// pass-through half into the other buffer of the stage's ping-pong pair: reading a halo that another CTA may
+// already have rewritten rules out updating in place).
 // Channel split / concat / shuffle stay the logical -> physical channel map folded into the weights
 // (engine.cu), so the unit reads and writes plane runs of the stage buffer (ConvSeg::runs).
 //
-// Bound: HBM (2 B in + 2 B out per value against ~3 h MACs); used for the stages with h <= 64, whose 1x1
-// GEMMs (K, N <= 64) are far too small for a tcgen05 tile to pay for its TMEM round trip, hence mma.sync.
+// Bound: HBM by bytes (2 B in + 2 B out per value against ~3 h MACs), issue / shared-memory pipe in practice
+// (profiles/r2_summary.md section 12); used for the stages with h <= 64, whose 1x1 GEMMs (K, N <= 64) are far
+// too small for a tcgen05 tile to pay for its TMEM round trip, hence mma.sync.
 // The last stage (h = 128, 20 x 20 maps) is weight-heavy and stays one tcgen05 launch per convolution.
 #include "common.cuh"
 

@@ -201,9 +201,9 @@ def main():
             out.append(f"| {nm} | {t:.1f} | {ab * 64 / 1e6:.0f} | {(dr + dw) / 1e6:.0f} | {ab * 64 / t / 1e6:.2f} | {ab * 64 / t / 1e6 / 6.5494:.2f} | "
                        f"{float(r[ix['smsp__issue_active.avg.pct_of_peak_sustained_active']]):.0f} | {float(r[ix['sm__warps_active.avg.pct_of_peak_sustained_active']]):.0f} | "
                        f"{r[ix['launch__registers_per_thread']]} | {float(r[ix['launch__shared_mem_per_block_dynamic']]):.0f} |")
-        out += ["", "The units are instruction-issue bound, not HBM bound: the depthwise convs cost ~15 issue slots per output value on the CUDA cores",
-                "(FP16 -> FP32 convert + FMA per tap) and the 1x1 GEMMs have K = N = 16..64, i.e. mostly epilogue (SiLU, pack, store).",
-                "See DESIGN.md section 3 for the comparison with the one-launch-per-convolution path."]
+        out += ["", "The units are bound by instruction issue and the shared-memory pipe, not by HBM: with K = N = 16..64 the 1x1 GEMMs are mostly",
+                "epilogue (SiLU, pack, store) and fragment loads; the depthwise convs run on the tensor cores as block-diagonal GEMMs (17 -> 0.3 issue",
+                "slots per output value).  See DESIGN.md section 3 for the comparison with the one-launch-per-convolution path."]
     json.dump({"src_hash": src_hash, "kernel": "conv_raster_kernel (Detect P3 box.0|cls.0, 3x3 64->128)", "frames": 128,
                "dram_bytes_per_launch": h0.get("dram__bytes_read.sum:bytes", 0.0) + h0.get("dram__bytes_write.sum:bytes", 0.0),
                "gpu_time_us": h0.get("time_us", 0.0),
