@@ -164,6 +164,10 @@ int irmv_engine_rotated_image(irmv_engine *e, int slot, uint8_t *dst);
 /* Debug: number of device / pinned allocations this library has made in the process so far (tests
  * assert that per-frame calls make none). */
 long long irmv_debug_alloc_count(void);
+/* Debug: every activation tensor is a zero-padded raster (guard pixels, a zero row per image, a zero column) and every
+ * kernel relies on that padding staying zero.  Counts the padding pixels of all activation tensors of the engine that
+ * are not zero: 0 after any sequence of calls, anything else is a stray store (the memory check this pool allows). */
+int irmv_debug_check_padding(irmv_engine *e, long long *bad_pixels);
 
 /* One frame from pinned slot `slot`: H2D + graph(preprocess, net, decode, NMS) + D2H + parse. */
 int irmv_engine_detect(irmv_engine *e, int slot, irmv_bbox *out, int cap, int *n);

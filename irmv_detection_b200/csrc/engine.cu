@@ -375,6 +375,8 @@ struct Lane {
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;
   std::vector<void *> allocs;
+  struct Raster { const __half *p; long long pstride; int planes, H, W; };   // every padded raster of the lane (normal layouts and parity twins)
+  std::vector<Raster> rasters;
   std::map<std::string, Tensor> taps;
   std::vector<Op> ops;
   Tensor in8, stem_out;
@@ -399,6 +401,32 @@ struct Lane {
 };
 
 __global__ void set_src_kernel(const uint8_t **word, const uint8_t *ptr) { *word = ptr; }
+
+// Debug (irmv_debug_check_padding): counts the pixels of one padded raster plane set that must be zero -- guard
+// pixels, the zero row before every image and after the last, the zero column -- and are not.  Every kernel that
+// writes activations relies on that padding being intact, so a stray store shows up here.
+__global__ void __launch_bounds__(256) check_padding_kernel(const __half *p, long long pstride, int planes, int S, int H, int W,
+                                                            unsigned long long *bad) {
+  const long long real = pr_pixels(S, H, W), total = (long long)kGuardFront + real + kGuardBack;
+  const int plane = blockIdx.y;
+  const uint4 *base = reinterpret_cast<const uint4 *>(p + (long long)plane * pstride) - kGuardFront;
+  unsigned long long n = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long q = i - kGuardFront;
+    bool must_be_zero = q < 0 || q >= real;
+    if (!must_be_zero) {
+      const long long row = q / (W + 1);
+      const int x = (int)(q - row * (W + 1));
+      must_be_zero = x == W || row % (H + 1) == 0;
+    }
+    if (must_be_zero) {
+      const uint4 v = base[i];
+      n += (v.x | v.y | v.z | v.w) != 0u;
+    }
+  }
+  if (n) atomicAdd(bad, n);
+  (void)planes;
+}
 
 // Detections -> PnP corner quads {LB, LT, RT, RB} (reference order, src/pnp_solver.cpp:41-44).
 // Until the light-bar extractor (reference src/irm_detector.cpp:292-355) is on the GPU the four
@@ -556,6 +584,7 @@ bool new_tensor(Lane &ln, int S, int H, int W, int C, Tensor &t, const char *tap
   __half *base = nullptr;
   if (!lane_alloc(ln, (void **)&base, (size_t)(C / 8) * plane_px * 16)) return false;
   t.p = base + (size_t)kGuardFront * 8;
+  ln.rasters.push_back({t.p, t.pstride, C / 8, H, W});
   if (tap) ln.taps[tap] = t;
   return true;
 }
@@ -569,6 +598,7 @@ bool add_parity_twin(Lane &ln, int S, Tensor &t, bool only) {
   __half *base = nullptr;
   if (!lane_alloc(ln, (void **)&base, (size_t)(4 * (t.C / 8)) * plane_px * 16)) return false;
   t.pp = base + (size_t)kGuardFront * 8;
+  ln.rasters.push_back({t.pp, t.pp_stride, 4 * (t.C / 8), t.H / 2, t.W / 2});
   return true;
 }
 
@@ -1762,6 +1792,26 @@ int irmv_engine_rotated_image(irmv_engine *e, int slot, uint8_t *dst) {
 }
 
 long long irmv_debug_alloc_count(void) { return g_allocs.load(); }
+
+int irmv_debug_check_padding(irmv_engine *e, long long *bad_pixels) {
+  IRMV_ABI_TRY
+  if (!e || !bad_pixels) { set_error("null argument"); return 1; }
+  IRMV_CUDA(cudaSetDevice(e->cfg.device));
+  IRMV_CUDA(cudaDeviceSynchronize());
+  unsigned long long *d = nullptr;
+  IRMV_CUDA(cudaMalloc((void **)&d, 8));
+  IRMV_CUDA(cudaMemset(d, 0, 8));
+  for (const Lane &ln : e->lanes)
+    for (const Lane::Raster &r : ln.rasters)
+      check_padding_kernel<<<dim3(64, (unsigned)r.planes), 256>>>(r.p, r.pstride, r.planes, e->S, r.H, r.W, d);
+  unsigned long long h = 0;
+  const cudaError_t err = cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  IRMV_CUDA(err);
+  *bad_pixels = (long long)h;
+  return 0;
+  IRMV_ABI_CATCH
+}
 
 int irmv_engine_read_tensor(irmv_engine *e, const char *name, void *dst, int64_t cap, int32_t dims[5]) {
   if (!e || !name || !dims) { set_error("bad argument"); return 1; }

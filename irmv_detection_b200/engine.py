@@ -249,6 +249,12 @@ class YoloEngine:
         L.check(self._lib.irmv_engine_fetch_armors(self._h, ticket, n, out.ctypes.data), "irmv_engine_fetch_armors")
         return out
 
+    def check_padding(self) -> int:
+        """Debug: number of padding pixels of the activation tensors that are not zero (0 unless a kernel stored out of bounds)."""
+        bad = C.c_longlong(-1)
+        L.check(self._lib.irmv_debug_check_padding(self._h, C.byref(bad)), "irmv_debug_check_padding")
+        return int(bad.value)
+
     def describe_ops(self):
         """Kernels of the network stage in issue order: dicts {kind, k, s, cin, cout, hw, raster, tail_cout}."""
         buf = C.create_string_buffer(16384)

@@ -1449,3 +1449,37 @@ def test_shufflenet_variant_batch64_pinned(base_image, weights_shuffle):
     ri, outs = _frame_vs_oracle(big, 0, x, weights_shuffle)
     assert np.array_equal(big.kept_indices(0), ri)
     big.close()
+
+
+@pytest.mark.parametrize("arch,n,chan", [("yolov8n", 1, "rgb"), ("yolov8n", 5, "bayer"), ("yolov8n", 32, "bayer"),
+                                         ("shuffle", 2, "rgb"), ("shuffle", 5, "bayer"), ("shuffle", 64, "bayer")])
+def test_activation_padding_stays_zero(base_image, weights_seed0, weights_shuffle, arch, n, chan):
+    """Memory check in place of a sanitizer run: every activation tensor is a zero-padded raster (guard pixels,
+    a zero row per image, a zero column) and every kernel relies on the padding staying zero, so a store
+    outside a kernel's own pixels lands either in the padding or in another frame.  After full runs (armor and
+    pose stages on, ragged sub-batches, repeated replays) no padding pixel of any tensor of any lane may be
+    non-zero, and repeating the batch gives identical detections (no stray store into a neighbour's pixels)."""
+    import irmv_detection_b200 as irmv
+    from irmv_detection_b200 import synth
+    from oracle import pnp_ref as P
+    _cuda()
+    fr = synth.frames_from_base(base_image, n, seed=41)
+    if chan == "bayer":
+        fr, order = synth.bayer_from_rgb(fr[..., ::-1], "RGGB"), irmv.CH_BAYER_RGGB
+    else:
+        order = irmv.CH_PASSTHROUGH
+    w = weights_seed0 if arch == "yolov8n" else weights_shuffle
+    sub = max(1, min(n, 32) if n != 5 else 2)          # n = 5, sub-batch 2: ragged last sub-batch
+    eng = irmv.YoloEngine(w, (1280, 1024), chan_order=order, max_batch=n, sub_batch=sub, num_lanes=2 if n > sub else 1)
+    assert eng.check_padding() == 0, "padding not zero after construction"
+    eng.enable_armors()
+    eng.enable_pnp(P.K_DEFAULT, P.D_DEFAULT, (0.5, 480 / 1024))
+    first = eng.detect_batch(fr)
+    assert eng.check_padding() == 0, "a kernel stored into the padding"
+    for _ in range(2):
+        assert eng.detect_batch(fr) == first
+    if n > 1:
+        eng.detect_batch(fr[:1])
+        assert eng.detect_batch(fr) == first
+    assert eng.check_padding() == 0
+    eng.close()
