@@ -84,7 +84,7 @@ typedef struct irmv_engine_config {
   int32_t resize_mode;      /* IRMV_RESIZE_* */
   int32_t quantize_u8;      /* 1 = keep the reference's 8-bit intermediate after the resize */
   int32_t max_batch;        /* frames per detect_batch call; 1 = reference */
-  int32_t sub_batch;        /* frames per graph replay (<= max_batch); 0 = pick */
+  int32_t sub_batch;        /* frames per graph replay (<= max_batch); 0 = pick (min(max_batch, 256)) */
   int32_t num_lanes;        /* concurrent streams replaying sub-batches; 0 = pick */
   int32_t num_slots;        /* pinned source slots for detect(); 3 = the reference's triple buffer */
   int32_t device;           /* CUDA device ordinal */

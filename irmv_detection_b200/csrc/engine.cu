@@ -957,15 +957,30 @@ bool build_lane(irmv_engine *e, Lane &ln) {
       !lane_alloc(ln, (void **)&ln.nms.counts, (size_t)S * 4))
     return false;
   ln.det.init(S, e->cfg.max_det);
-  if (!lane_alloc(ln, (void **)&ln.det.dev, ln.det.bytes)) return false;
   if (!lane_alloc(ln, (void **)&ln.src_word, sizeof(void *))) return false;
   const size_t slots = (size_t)S * e->cfg.max_det;
-  if (e->pose && !lane_alloc(ln, (void **)&ln.kpts, slots * 32)) return false;
-  if (!lane_alloc(ln, (void **)&ln.pnp_pts, slots * 32) || !lane_alloc(ln, (void **)&ln.pnp_rvec, slots * 24) ||
-      !lane_alloc(ln, (void **)&ln.pnp_tvec, slots * 24) || !lane_alloc(ln, (void **)&ln.pnp_ok, slots) ||
-      !lane_alloc(ln, (void **)&ln.pnp_quat, slots * 32) || !lane_alloc(ln, (void **)&ln.pnp_dist, slots * 4) ||
-      !lane_alloc(ln, (void **)&ln.pnp_centers, slots * 8))
-    return false;
+  {
+    // Everything a replay hands back lives in ONE device block per lane, in the order of the pinned result block
+    // (enqueue()): detections | rvec | tvec | ok | armors | keypoints | quaternion | distance.  When a replay
+    // covers the whole batch the two layouts coincide and the copies back merge into two or three
+    // cudaMemcpyAsync calls instead of ten (each costs 5-10 us of stream time: 0.1 ms of a 4.6 ms step, and a
+    // tenth of the batch-1 detect() latency).
+    auto up = [](size_t v, size_t a) { return (v + a - 1) & ~(a - 1); };
+    const size_t o_rvec = up(ln.det.bytes, 16), o_tvec = o_rvec + slots * 24, o_ok = o_tvec + slots * 24;
+    const size_t o_arm = up(o_ok + slots, 64), o_kpt = o_arm + slots * sizeof(ArmorOut);
+    const size_t o_quat = up(o_kpt + slots * 32, 64), o_dist = o_quat + slots * 32;
+    uint8_t *blk = nullptr;
+    if (!lane_alloc(ln, (void **)&blk, o_dist + slots * 4)) return false;
+    ln.det.dev = blk;
+    ln.pnp_rvec = reinterpret_cast<double *>(blk + o_rvec);
+    ln.pnp_tvec = reinterpret_cast<double *>(blk + o_tvec);
+    ln.pnp_ok = blk + o_ok;
+    ln.armors = reinterpret_cast<ArmorOut *>(blk + o_arm);
+    ln.kpts = reinterpret_cast<float *>(blk + o_kpt);
+    ln.pnp_quat = reinterpret_cast<double *>(blk + o_quat);
+    ln.pnp_dist = reinterpret_cast<float *>(blk + o_dist);
+  }
+  if (!lane_alloc(ln, (void **)&ln.pnp_pts, slots * 32) || !lane_alloc(ln, (void **)&ln.pnp_centers, slots * 8)) return false;
   for (auto &ev : ln.stage_ev)
     if (!cuda_ok(cudaEventCreate(&ev), "cudaEventCreate", __FILE__, __LINE__)) return false;
   Tensor bt; bt.p = reinterpret_cast<__half *>(ln.nms.boxes); bt.H = 1; bt.W = kNumAnchors; bt.C = 4; bt.pstride = 0;
@@ -1175,38 +1190,49 @@ int enqueue(irmv_engine *e, const uint8_t *frames_dev, int n, const uint8_t *fra
     set_src_kernel<<<1, 1, 0, ln.stream>>>(ln.src_word, frames_dev + (size_t)f0 * e->frame_bytes);
     IRMV_CUDA(cudaGetLastError());
     if (int rc = run_replay(e, ln, nf)) return rc;
-    // results: the lane's packed block -> pinned host, one copy per array so a partial replay
-    // still lands at the frame's slot
+    // results: the lane's block -> pinned host.  One range per array (a partial replay still lands at the
+    // frame's slot); ranges that are adjacent on both sides -- a replay of the whole batch -- go as one copy.
     uint8_t *h = rs.res_host;
     const int md = e->cfg.max_det;
     const size_t B = e->cfg.max_batch;
-    auto d2h = [&](size_t host_off, const void *src, size_t bytes) -> cudaError_t {
-      e->d2h_bytes += bytes;
-      return cudaMemcpyAsync(h + host_off, src, bytes, cudaMemcpyDeviceToHost, ln.stream);
+    struct Range { size_t host_off; const uint8_t *src; size_t bytes; };
+    Range rg[12];
+    int nr = 0;
+    auto d2h = [&](size_t host_off, const void *src, size_t bytes) {
+      const uint8_t *sp = static_cast<const uint8_t *>(src);
+      static const bool merge = !getenv("IRMV_NO_D2H_MERGE");   // A/B knob
+      if (merge && nr && rg[nr - 1].host_off + rg[nr - 1].bytes == host_off && rg[nr - 1].src + rg[nr - 1].bytes == sp) rg[nr - 1].bytes += bytes;
+      else rg[nr++] = {host_off, sp, bytes};
     };
-    IRMV_CUDA(d2h((size_t)f0 * 4, ln.det.num(), (size_t)nf * 4));
+    d2h((size_t)f0 * 4, ln.det.num(), (size_t)nf * 4);
     size_t o = B * 4;
-    IRMV_CUDA(d2h(o + (size_t)f0 * md * 16, ln.det.boxes(), (size_t)nf * md * 16));
+    d2h(o + (size_t)f0 * md * 16, ln.det.boxes(), (size_t)nf * md * 16);
     o += B * md * 16;
-    IRMV_CUDA(d2h(o + (size_t)f0 * md * 4, ln.det.scores(), (size_t)nf * md * 4));
+    d2h(o + (size_t)f0 * md * 4, ln.det.scores(), (size_t)nf * md * 4);
     o += B * md * 4;
-    IRMV_CUDA(d2h(o + (size_t)f0 * md * 4, ln.det.classes(), (size_t)nf * md * 4));
+    d2h(o + (size_t)f0 * md * 4, ln.det.classes(), (size_t)nf * md * 4);
     o += B * md * 4;
-    IRMV_CUDA(d2h(o + (size_t)f0 * md * 4, ln.det.index(), (size_t)nf * md * 4));
+    d2h(o + (size_t)f0 * md * 4, ln.det.index(), (size_t)nf * md * 4);
     o += B * md * 4;
     if (e->pnp_on) {
-      IRMV_CUDA(d2h(o + (size_t)f0 * md * 24, ln.pnp_rvec, (size_t)nf * md * 24));
+      d2h(o + (size_t)f0 * md * 24, ln.pnp_rvec, (size_t)nf * md * 24);
       o += B * md * 24;
-      IRMV_CUDA(d2h(o + (size_t)f0 * md * 24, ln.pnp_tvec, (size_t)nf * md * 24));
+      d2h(o + (size_t)f0 * md * 24, ln.pnp_tvec, (size_t)nf * md * 24);
       o += B * md * 24;
-      IRMV_CUDA(d2h(o + (size_t)f0 * md, ln.pnp_ok, (size_t)nf * md));
-      IRMV_CUDA(d2h(quat_offset(B, md) + (size_t)f0 * md * 32, ln.pnp_quat, (size_t)nf * md * 32));
-      IRMV_CUDA(d2h(dist_offset(B, md) + (size_t)f0 * md * 4, ln.pnp_dist, (size_t)nf * md * 4));
+      d2h(o + (size_t)f0 * md, ln.pnp_ok, (size_t)nf * md);
     }
     if (e->armors_on)
-      IRMV_CUDA(d2h(armors_offset(B, md) + (size_t)f0 * md * sizeof(ArmorOut), ln.armors, (size_t)nf * md * sizeof(ArmorOut)));
+      d2h(armors_offset(B, md) + (size_t)f0 * md * sizeof(ArmorOut), ln.armors, (size_t)nf * md * sizeof(ArmorOut));
     if (e->pose)
-      IRMV_CUDA(d2h(kpts_offset(B, md) + (size_t)f0 * md * 32, ln.kpts, (size_t)nf * md * 32));
+      d2h(kpts_offset(B, md) + (size_t)f0 * md * 32, ln.kpts, (size_t)nf * md * 32);
+    if (e->pnp_on) {
+      d2h(quat_offset(B, md) + (size_t)f0 * md * 32, ln.pnp_quat, (size_t)nf * md * 32);
+      d2h(dist_offset(B, md) + (size_t)f0 * md * 4, ln.pnp_dist, (size_t)nf * md * 4);
+    }
+    for (int i = 0; i < nr; ++i) {
+      e->d2h_bytes += rg[i].bytes;
+      IRMV_CUDA(cudaMemcpyAsync(h + rg[i].host_off, rg[i].src, rg[i].bytes, cudaMemcpyDeviceToHost, ln.stream));
+    }
   }
   for (int l = 0; l < used; ++l) {
     IRMV_CUDA(cudaEventRecord(e->lanes[l].done, e->lanes[l].stream));
@@ -1528,8 +1554,9 @@ int irmv_engine_create(const char *weights_path, const irmv_engine_config *cfg, 
 
   const bool bayer = cfg->chan_order >= 2;
   e->frame_bytes = (size_t)cfg->src_width * cfg->src_height * (bayer ? 1 : 3);
-  // defaults from the bench sweeps: replays of up to 128 frames on 2 lanes
-  e->S = cfg->sub_batch > 0 ? cfg->sub_batch : (cfg->max_batch < 128 ? cfg->max_batch : 128);
+  // defaults from the bench sweeps: replays of up to 256 frames (a launch carries ~7 us of fixed cost whatever
+  // its size, so one 256-frame replay beats two of 128 by 3 %); two lanes when the batch needs several replays
+  e->S = cfg->sub_batch > 0 ? cfg->sub_batch : (cfg->max_batch < 256 ? cfg->max_batch : 256);
   if (e->S > cfg->max_batch) e->S = cfg->max_batch;
   int chunks = (cfg->max_batch + e->S - 1) / e->S;
   e->L = cfg->num_lanes > 0 ? cfg->num_lanes : (chunks < 2 ? chunks : 2);
@@ -1975,8 +2002,8 @@ int irmv_engine_enable_armors(irmv_engine *e, const irmv_armor_params *prm) {
   const size_t slots = (size_t)e->S * e->cfg.max_det;
   const size_t words = armors_scratch_total_words(e->cfg.src_width, e->cfg.src_height, armors_grid(e->num_sms));
   for (auto &ln : e->lanes) {
-    if (!ln.armors) {
-      if (!lane_alloc(ln, (void **)&ln.armors, slots * sizeof(ArmorOut)) || !lane_alloc(ln, (void **)&ln.armor_scratch, words * 4)) return 3;
+    if (!ln.armor_scratch) {                                    // (the armor slots are part of the lane's result block)
+      if (!lane_alloc(ln, (void **)&ln.armor_scratch, words * 4)) return 3;
       IRMV_CUDA(cudaMemset(ln.armors, 0, slots * sizeof(ArmorOut)));
       IRMV_CUDA(cudaMemset(ln.armor_scratch, 0, 256));         // slot locks
     }

@@ -941,12 +941,13 @@ def _frame_vs_oracle(eng, f, x_nhwc8, wpath):
     return ri, outs
 
 
-def test_bench_configuration_pinned_to_single_frame_engine_and_oracle(base_image, weights_seed0):
-    """bench.py's engine (BASELINE.json configs[3]: Bayer frames, max_batch 256, sub_batch 128, two
-    lanes, fused PnP) runs kernel instantiations that plan() only picks at large tile counts (R = 4 / 2,
-    streamed weights, other ring depths).  Pin that configuration: frames at the start, middle and end
-    of both lanes must equal a max_batch = 1 engine bit for bit (detections, Detect head tensor, poses),
-    and frame 0 must be within tolerance of the FP32 oracle."""
+@pytest.mark.parametrize("sub,lanes", [(256, 1), (128, 2)])
+def test_bench_configuration_pinned_to_single_frame_engine_and_oracle(base_image, weights_seed0, sub, lanes):
+    """bench.py's engine (BASELINE.json configs[3]: Bayer frames, max_batch 256, one 256-frame replay --
+    and the round-1 split, two lanes of 128 -- fused PnP) runs kernel instantiations that plan() only
+    picks at large tile counts (R = 4 / 2, streamed weights, other ring depths).  Pin that configuration:
+    frames at the start, middle and end of every replay must equal a max_batch = 1 engine bit for bit
+    (detections, Detect head tensor, poses), and frame 0 must be within tolerance of the FP32 oracle."""
     import irmv_detection_b200 as irmv
     from irmv_detection_b200 import synth
     from oracle import pnp_ref as P
@@ -958,11 +959,11 @@ def test_bench_configuration_pinned_to_single_frame_engine_and_oracle(base_image
     for pos, src in probe.items():
         raw[pos] = raw16[src + 3 if src + 3 < 16 else src]
     big = irmv.YoloEngine(weights_seed0, (1280, 1024), chan_order=irmv.CH_BAYER_RGGB, max_batch=256,
-                          sub_batch=128, num_lanes=2)
+                          sub_batch=sub, num_lanes=lanes)
     big.enable_pnp(P.K_DEFAULT, P.D_DEFAULT, (0.5, 480 / 1024))
     res = big.detect_batch(raw)
     rv, tv, ok = big.fetch_poses(256)
-    box_big = [big.read_tensor(f"box{i}") for i in range(3)]          # lane 0 = frames 0..127
+    box_big = [big.read_tensor(f"box{i}") for i in range(3)]          # lane 0 = frames 0..sub-1
     cls_big = [big.read_tensor(f"cls{i}") for i in range(3)]
     one = irmv.YoloEngine(weights_seed0, (1280, 1024), chan_order=irmv.CH_BAYER_RGGB)
     one.enable_pnp(P.K_DEFAULT, P.D_DEFAULT, (0.5, 480 / 1024))
@@ -975,13 +976,13 @@ def test_bench_configuration_pinned_to_single_frame_engine_and_oracle(base_image
         total += k
         assert np.array_equal(rv[pos, :k], r1[0, :k]) and np.array_equal(tv[pos, :k], t1[0, :k]), f"frame {pos}: poses"
         assert np.array_equal(ok[pos, :k], o1[0, :k])
-        if pos < 128:
+        if pos < sub:
             for i in range(3):
                 assert np.array_equal(one.read_tensor(f"box{i}")[0], box_big[i][pos]), f"frame {pos} box{i}"
                 assert np.array_equal(one.read_tensor(f"cls{i}")[0], cls_big[i][pos]), f"frame {pos} cls{i}"
     assert total > 0
     one.close()
-    # frame 0 of the 128-frame replay against the FP32 oracle
+    # frame 0 of the replay against the FP32 oracle
     x = irmv.preprocess(raw[:1], irmv.CH_BAYER_RGGB)
     ri, _ = _frame_vs_oracle(big, 0, x, weights_seed0)
     assert np.array_equal(big.kept_indices(0), ri)
@@ -1040,24 +1041,26 @@ def _plan_signatures(plans):
 def test_every_plan_instantiation_is_oracle_compared(base_image, weights_seed0):
     """plan() (csrc/conv_raster.cu) picks R, weight streaming, CTAs per SM and ring depths from the tile
     count, so different replay sizes run different kernel instantiations.  Enumerate the instantiations
-    (k, stride, R, NEPI, b_stream, CTAs/SM, >= 2 stages, tail, act, res) over every replay size 1..128,
-    pick replay sizes that cover all of them (greedy, the bench's 128 first), and for each picked size
+    (k, stride, R, NEPI, b_stream, CTAs/SM, >= 2 stages, tail, act, res) over every replay size 1..256,
+    pick replay sizes that cover all of them (greedy, the bench's 256 first), and for each picked size
     require frames at the start, middle and end of the replay to equal the batch-1 engine bit for bit
     (detections + all Detect head tensors) and frame 0 to be within tolerance of the FP32 oracle."""
     import irmv_detection_b200 as irmv
     from irmv_detection_b200 import synth
     _cuda()
-    big = irmv.YoloEngine(weights_seed0, (1280, 1024), chan_order=irmv.CH_BAYER_RGGB, max_batch=128, sub_batch=128, num_lanes=1)
-    sig = {n: _plan_signatures(big.describe_plans(n)) for n in range(1, 129)}
+    NMAX = 256
+    big = irmv.YoloEngine(weights_seed0, (1280, 1024), chan_order=irmv.CH_BAYER_RGGB, max_batch=NMAX, sub_batch=NMAX, num_lanes=1)
+    sig = {n: _plan_signatures(big.describe_plans(n)) for n in range(1, NMAX + 1)}
     every = set().union(*sig.values())
-    picked, covered = [128], set(sig[128])
+    picked, covered = [NMAX], set(sig[NMAX])
     while covered != every:
-        n = max(range(1, 129), key=lambda m: (len(sig[m] - covered), m))
+        n = max(range(1, NMAX + 1), key=lambda m: (len(sig[m] - covered), m))
         picked.append(n)
         covered |= sig[n]
     assert len(picked) <= 12, picked
     rgb = synth.frames_from_base(base_image, 128, seed=55)[..., ::-1]
     raw = synth.bayer_from_rgb(rgb, "RGGB")
+    raw = np.ascontiguousarray(np.concatenate([raw, raw[::-1]]))          # 256 frames, no two neighbours alike
     one = irmv.YoloEngine(weights_seed0, (1280, 1024), chan_order=irmv.CH_BAYER_RGGB)
     x0 = irmv.preprocess(raw[:1], irmv.CH_BAYER_RGGB)
     ref = {}
