@@ -350,6 +350,9 @@ struct Op {
   ShuffleUnitParams su{};
   ConvParams cp{};
   bool raster = false;       // raster (halo-tile) kernel, else the per-tap gather kernel
+  // Small replays (issue_replay): independent sub-graphs run on side streams.  `stream` 0 is the lane's own
+  // stream; before the op its stream waits for event `wait`, after it the stream records event `signal`.
+  int stream = 0, wait = -1, signal = -1;
   __half *pool_buf = nullptr;
   int pH = 0, pW = 0, pC = 0;
   long long pStride = 0;
@@ -386,6 +389,9 @@ struct Lane {
   const uint8_t **src_word = nullptr;      // device word: base pointer of the frames of this replay
   uint8_t *rotated = nullptr;
   std::map<int, cudaGraphExec_t> graphs;   // keyed by frames in the replay
+  static constexpr int kSide = 9, kSig = 6;
+  cudaStream_t side[kSide] = {};           // side streams of the branched schedule (index 0 unused)
+  cudaEvent_t side_done[kSide] = {}, sig[kSig] = {};
   int launches_per_replay = 0;
   float *pnp_pts = nullptr;                // [S*max_det][8]
   double *pnp_rvec = nullptr, *pnp_tvec = nullptr;
@@ -757,6 +763,7 @@ void fuse_tails(irmv_engine *e, Lane &ln) {
     mp.out = nullptr;
     if (!conv_raster_fits(mp)) continue;
     m.cp = mp;
+    if (t.signal >= 0) m.signal = t.signal;                   // the fused launch now produces what the tail produced
     for (auto it = ln.taps.begin(); it != ln.taps.end();)     // the intermediate is no longer materialised
       it = (it->second.p == o0) ? ln.taps.erase(it) : std::next(it);
     ln.ops.erase(ln.ops.begin() + (long)i + 1);
@@ -770,6 +777,12 @@ bool build_lane(irmv_engine *e, Lane &ln) {
       !cuda_ok(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming), "cudaEventCreate",
                __FILE__, __LINE__))
     return false;
+  for (int i = 1; i < Lane::kSide; ++i)
+    if (!cuda_ok(cudaStreamCreateWithFlags(&ln.side[i], cudaStreamNonBlocking), "cudaStreamCreate", __FILE__, __LINE__) ||
+        !cuda_ok(cudaEventCreateWithFlags(&ln.side_done[i], cudaEventDisableTiming), "cudaEventCreate", __FILE__, __LINE__))
+      return false;
+  for (auto &ev : ln.sig)
+    if (!cuda_ok(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "cudaEventCreate", __FILE__, __LINE__)) return false;
   if (!new_tensor(ln, S, kNet, kNet, kInC, ln.in8, "input")) return false;
   size_t ci = 0;
   Tensor t0, t1, x2, t3, x4, t5, x6, t7, x8, sp, x9, x12, x15, t16, x18, t19, x21;
@@ -909,12 +922,15 @@ bool build_lane(irmv_engine *e, Lane &ln) {
   // neck: upsample and concat happen in the consumers' gathers
   if (!add_c2f(e, ln, ci, {{&x9, 0, 256, 1}, {&x6, 0, 128, 0}}, 40, 40, 128, 1, false, x12, "m12")) return false;
   if (!add_c2f(e, ln, ci, {{&x12, 0, 128, 1}, {&x4, 0, 64, 0}}, 80, 80, 64, 1, false, x15, "m15", par2 ? 2 : 0)) return false;
+  ln.ops.back().signal = 0;                        // P3 feature ready: its Detect / keypoint towers may start
   if (!new_tensor(ln, S, 40, 40, 64, t16, "m16")) return false;
   add_conv(e, ln, *e->convs[ci++], {{&x15, 0, 64, 0}}, 80, 80, t16, 0);
   if (!add_c2f(e, ln, ci, {{&t16, 0, 64, 0}, {&x12, 0, 128, 0}}, 40, 40, 128, 1, false, x18, "m18")) return false;
+  ln.ops.back().signal = 1;                        // P4
   if (!new_tensor(ln, S, 20, 20, 128, t19, "m19")) return false;
   add_conv(e, ln, *e->convs[ci++], {{&x18, 0, 128, 0}}, 40, 40, t19, 0);
   if (!add_c2f(e, ln, ci, {{&t19, 0, 128, 0}, {&x9, 0, 256, 0}}, 20, 20, 256, 1, false, x21, "m21")) return false;
+  ln.ops.back().signal = 2;                        // P5
   // Detect head: box.0|cls.0 merged (N=128), then the two towers
   const Tensor *feat[3] = {&x15, &x18, &x21};
   const int hw[3] = {80, 40, 20};
@@ -927,11 +943,19 @@ bool build_lane(irmv_engine *e, Lane &ln) {
         !new_tensor(ln, S, hw[i], hw[i], 64, hc) || !new_tensor(ln, S, hw[i], hw[i], 64, bo, nb) ||
         !new_tensor(ln, S, hw[i], hw[i], kClsPad, co, ncn))
       return false;
+    // branched schedule: scale i's towers start as soon as its feature exists (the P3 towers run beside the
+    // rest of the neck); box and cls towers of a scale run side by side; P5's first conv stays on the trunk
+    const int s_box = i < 2 ? 1 + 2 * i : 0, s_cls = i < 2 ? 2 + 2 * i : 5;
     add_conv(e, ln, *e->convs[ci++], {{feat[i], 0, feat[i]->C, 0}}, hw[i], hw[i], h0, 0);
+    ln.ops.back().stream = s_box; ln.ops.back().wait = i; ln.ops.back().signal = 3 + i;
     add_conv(e, ln, *e->convs[ci++], {{&h0, 0, 64, 0}}, hw[i], hw[i], hb, 0);
+    ln.ops.back().stream = s_box;
     add_conv(e, ln, *e->convs[ci++], {{&hb, 0, 64, 0}}, hw[i], hw[i], bo, 0);
+    ln.ops.back().stream = s_box;
     add_conv(e, ln, *e->convs[ci++], {{&h0, 64, 64, 0}}, hw[i], hw[i], hc, 0);
+    ln.ops.back().stream = s_cls; ln.ops.back().wait = 3 + i;
     add_conv(e, ln, *e->convs[ci++], {{&hc, 0, 64, 0}}, hw[i], hw[i], co, 0);
+    ln.ops.back().stream = s_cls;
     ln.heads.box[i] = bo.p; ln.heads.box_ps[i] = bo.pstride;
     ln.heads.cls[i] = co.p; ln.heads.cls_ps[i] = co.pstride;
     ln.heads.padded = 1;
@@ -945,8 +969,11 @@ bool build_lane(irmv_engine *e, Lane &ln) {
           !new_tensor(ln, S, hw[i], hw[i], 16, ko, nk))
         return false;
       add_conv(e, ln, *e->convs[ci++], {{feat[i], 0, feat[i]->C, 0}}, hw[i], hw[i], k0, 0);
+      ln.ops.back().stream = 6 + i; ln.ops.back().wait = i;
       add_conv(e, ln, *e->convs[ci++], {{&k0, 0, 16, 0}}, hw[i], hw[i], k1, 0);
+      ln.ops.back().stream = 6 + i;
       add_conv(e, ln, *e->convs[ci++], {{&k1, 0, 16, 0}}, hw[i], hw[i], ko, 0);
+      ln.ops.back().stream = 6 + i;
       ln.kpt[i] = ko.p;
     }
   if (ci != e->convs.size()) { set_error("internal: conv count mismatch"); return false; }
@@ -1019,12 +1046,25 @@ int issue_replay(irmv_engine *e, Lane &ln, int n, cudaStream_t st, int *launches
   // Consecutive kernels walk their tiles in opposite directions (ConvParams::rev_tiles): a layer then
   // starts with the end of the tensor its producer has just finished writing, which is what the L2 still holds.
   static const bool pingpong = !getenv("IRMV_NO_PINGPONG");
+  // Branched schedule for small replays: at batch 1 a Detect tower launch occupies 4-52 of the 148 SMs and the
+  // replay is a chain of ~57 launch latencies, so the towers of a scale run on side streams next to the rest of the
+  // neck and next to each other (fork / join by events; inside a CUDA graph these become parallel branches).  Large
+  // replays fill the machine with every launch and stay on one stream.
+  static const int branch_max = getenv("IRMV_BRANCH_MAX") ? atoi(getenv("IRMV_BRANCH_MAX")) : 4;
+  const bool branched = n <= branch_max && !stage_events && !op_events && e->cfg.conv_impl != IRMV_CONV_DIRECT;
+  unsigned side_used = 0;
+  const cudaStream_t trunk = st;
   int seq = 0;
   bool first = true;
   for (auto &op : ln.ops) {
     if (first && fused) { first = false; continue; }        // conv0 ran inside the stem kernel
     first = false;
     ++seq;
+    st = trunk;
+    if (branched) {
+      if (op.stream > 0) { st = ln.side[op.stream]; side_used |= 1u << op.stream; }
+      if (op.wait >= 0) IRMV_CUDA(cudaStreamWaitEvent(st, ln.sig[op.wait], 0));
+    }
     if (op.kind == Op::CONV) {
       ConvParams p = op.cp;
       p.B = n;
@@ -1046,6 +1086,7 @@ int issue_replay(irmv_engine *e, Lane &ln, int n, cudaStream_t st, int *launches
       IRMV_CUDA(launch_sppf_pool(op.pool_buf, n, op.pH, op.pW, op.pStride, op.pC, st));
     }
     ++cnt;
+    if (branched && op.signal >= 0) IRMV_CUDA(cudaEventRecord(ln.sig[op.signal], st));
     op_mark();
     if (getenv("IRMV_SYNC_EACH")) {
       cudaError_t ce = cudaStreamSynchronize(st);
@@ -1059,6 +1100,12 @@ int issue_replay(irmv_engine *e, Lane &ln, int n, cudaStream_t st, int *launches
       }
     }
   }
+  st = trunk;
+  for (int i = 1; i < Lane::kSide; ++i)                      // join the side streams
+    if (side_used & (1u << i)) {
+      IRMV_CUDA(cudaEventRecord(ln.side_done[i], ln.side[i]));
+      IRMV_CUDA(cudaStreamWaitEvent(st, ln.side_done[i], 0));
+    }
   if (mark(2)) return 1;
   IRMV_CUDA(launch_decode(ln.heads, n, e->nc, e->cfg.score_thr, ln.nms, nullptr, st)); ++cnt;
   DetOut out{ln.det.num(), ln.det.boxes(), ln.det.scores(), ln.det.classes(), ln.det.index()};
@@ -1600,6 +1647,9 @@ void irmv_engine_destroy(irmv_engine *e) {
     if (ln.stream) cudaStreamDestroy(ln.stream);
     if (ln.done) cudaEventDestroy(ln.done);
     for (auto ev : ln.stage_ev) if (ev) cudaEventDestroy(ev);
+    for (auto st : ln.side) if (st) cudaStreamDestroy(st);
+    for (auto ev : ln.side_done) if (ev) cudaEventDestroy(ev);
+    for (auto ev : ln.sig) if (ev) cudaEventDestroy(ev);
   }
   for (auto &c : e->convs) {
     cudaFree(c->d_plain); cudaFree(c->d_tiled); cudaFree(c->d_raster); cudaFree(c->d_bias);
