@@ -155,6 +155,12 @@ struct ConvParams {
   int sync_mode;           // tcgen05 producer hand-off: 0 = cp.async-tracked mbarrier, 1 = wait+fence
   long long *trace;        // debug: CTA 0 writes per-tile clock64 stamps [tile][8]; null in production
   int trace_cap;
+  // Raster kernel, small replays: the same weights as `split_ways` slices of npad / split_ways output channels,
+  // [slice][k*k][cin/8][npad / split_ways][8].  When a launch has fewer tiles than SMs / split_ways (the 20x20 layers
+  // of a batch-1 replay are 4 tiles), each tile is computed by split_ways CTAs, one per slice: a CTA then pulls a
+  // quarter of the weights through its SM and issues N/4-wide MMAs.  Null = never split.
+  const __half *w_raster_split;
+  int split_ways;
 };
 cudaError_t launch_conv_direct(const ConvParams &p, cudaStream_t s);
 cudaError_t launch_conv_tc(const ConvParams &p, int num_sms, cudaStream_t s);

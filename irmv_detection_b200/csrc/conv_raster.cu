@@ -160,6 +160,8 @@ struct RArgs {
   int ext_stages;                         // buffers for them (2 when shared memory allows: the load of tile j+1 runs under tail(j))
   int rev;                                // walk the tiles from the last to the first (ConvParams::rev_tiles)
   int tmem_tail0;                         // first TMEM column of the tail accumulators
+  int nsplit;                             // > 1: CTA b computes output-channel slice b % nsplit of tile b / nsplit (ConvParams::w_raster_split);
+                                          // p.cout / p.npad are then the slice's, b_bytes the slice's weight bytes
 };
 
 // One 16-column chunk of one accumulator: bias, SiLU, residual, FP16, two 16-byte plane stores.
@@ -256,6 +258,13 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
   Bars *bars = reinterpret_cast<Bars *>(smem + a.off_bars);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int npad = p.npad;
+  // output-channel split (small replays): CTA -> (tile stream bid of gsz, slice)
+  const int nsplit = a.nsplit;
+  const int bid = nsplit > 1 ? (int)(blockIdx.x / (unsigned)nsplit) : (int)blockIdx.x;
+  const int gsz = nsplit > 1 ? (int)(gridDim.x / (unsigned)nsplit) : (int)gridDim.x;
+  const int split = nsplit > 1 ? (int)(blockIdx.x % (unsigned)nsplit) : 0;
+  const float *const bias_g = p.bias + split * npad;
+  const uint8_t *const w_g = reinterpret_cast<const uint8_t *>(p.w_raster) + (size_t)split * a.b_bytes;
   // debug trace rows cap+15 (CTA 0) / cap+14 (last CTA): {entry, setup done, exit} clocks + globaltimer ns
   long long *trow = (p.trace && tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))
                         ? p.trace + (size_t)(p.trace_cap + (blockIdx.x == 0 ? 15 : 14)) * 8 : nullptr;
@@ -270,7 +279,7 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
   // own griddepcontrol.wait still blocks until this grid has completed and flushed.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // act: bias / 2 (folded into the SiLU argument), otherwise the bias itself
-  for (int i = tid; i < npad; i += NTHREADS) s_hb[i] = ACT ? 0.5f * p.bias[i] : p.bias[i];
+  for (int i = tid; i < npad; i += NTHREADS) s_hb[i] = ACT ? 0.5f * bias_g[i] : bias_g[i];
   if (TAIL)
     for (int i = tid; i < p.tail_npad; i += NTHREADS) s_tb[i] = TAIL == 2 ? 0.5f * p.tail_bias[i] : p.tail_bias[i];
   if (tid == 0) {
@@ -315,7 +324,7 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
     mbar_expect_tx(bar, a.b_bytes + (TAIL ? a.bt_bytes : 0u));
     for (uint32_t off = 0; off < a.b_bytes; off += 65536u) {
       const uint32_t n = a.b_bytes - off < 65536u ? a.b_bytes - off : 65536u;
-      bulk_g2s(sB_u + off, reinterpret_cast<const uint8_t *>(p.w_raster) + off, n, bar);
+      bulk_g2s(sB_u + off, w_g + off, n, bar);
     }
     if (TAIL) bulk_g2s(smem_u32(sBt), p.tail_w, a.bt_bytes, bar);
   }
@@ -340,8 +349,8 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
     const int chunk_mask = (npad >> 4) - 1;
     const int items = R << chunk_shift;
     const uint32_t lane_base = tmem_base + ((uint32_t)(ew * 32) << 16);
-    __half *const out = p.out;
-    const __half *const res = p.res;
+    __half *const out = p.out ? p.out + (long long)(split * (npad >> 3)) * p.out_pstride : nullptr;
+    const __half *const res = p.res ? p.res + (long long)(split * (npad >> 3)) * p.res_pstride : nullptr;
     const long long out_ps = p.out_pstride, res_ps = p.res_pstride;
     const int orl = p.out_runs;
     const long long out_ps_pair = orl == 1 ? 2 * out_ps : out_ps;   // distance between the two planes of a 16-channel chunk
@@ -412,7 +421,7 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
       if (lane == 0) mbar_arrive(&bars->tail_empty[tb]);
     };
     int it = 0, prev_tile = -1;
-    for (int tseq = blockIdx.x; tseq < num_tiles; tseq += gridDim.x, ++it) {
+    for (int tseq = bid; tseq < num_tiles; tseq += gsz, ++it) {
       const int tile = a.rev ? num_tiles - 1 - tseq : tseq;
       const int buf = it & 1;
       const uint32_t aph = (uint32_t)(it >> 1) & 1u;
@@ -547,13 +556,13 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
         // barriers without blocking, so a full ext buffer never holds back the next main tile (the
         // blocking order main(j+1) -> ext(j) serialised the loads: one main tile in flight at a time,
         // its DRAM latency exposed on every tile -- scripts/trace_conv.py, profiles/r2_summary.md).
-        const int mine = a.num_tiles > (int)blockIdx.x ? (a.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+        const int mine = a.num_tiles > bid ? (a.num_tiles - 1 - bid) / gsz + 1 : 0;
         int mi = 0, ei = 0;
         while (mi < mine || ei < mine) {
           bool progressed = false;
           if (mi < mine && mbar_test(&bars->empty[s], ph ^ 1u)) {
             if (p.trace && blockIdx.x == 0 && mi < p.trace_cap) p.trace[mi * 8 + 0] = clock64();
-            issue_main(tile_of((int)blockIdx.x + mi * (int)gridDim.x), mi);
+            issue_main(tile_of(bid + mi * gsz), mi);
             ++mi;
             progressed = true;
           }
@@ -561,7 +570,7 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
             const int eb = a.ext_stages == 2 ? (ei & 1) : 0;
             const uint32_t eph = a.ext_stages == 2 ? ((uint32_t)(ei >> 1) & 1u) : ((uint32_t)ei & 1u);
             if (mbar_test(&bars->ext_empty[eb], eph ^ 1u)) {
-              issue_ext(ei, tile_of((int)blockIdx.x + ei * (int)gridDim.x));
+              issue_ext(ei, tile_of(bid + ei * gsz));
               ++ei;
               progressed = true;
             }
@@ -569,13 +578,13 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
           if (!progressed) __nanosleep(64);
         }
       } else {
-        for (int tseq = blockIdx.x; tseq < a.num_tiles; tseq += gridDim.x, ++itl) {
+        for (int tseq = bid; tseq < a.num_tiles; tseq += gsz, ++itl) {
           const int tile = tile_of(tseq);
           if (p.trace && blockIdx.x == 0 && itl < p.trace_cap) p.trace[itl * 8 + 0] = clock64();
           mbar_wait(&bars->empty[s], ph ^ 1u);
           issue_main(tile, itl);
           if (a.b_stream) {
-            const uint8_t *wsrc = reinterpret_cast<const uint8_t *>(p.w_raster);
+            const uint8_t *wsrc = w_g;
             for (int t = 0; t < a.nchunks; ++t, wsrc += a.b_tap_bytes) {
               mbar_wait(&bars->bw_empty[bs], bph ^ 1u);
               const uint32_t bbar = smem_u32(&bars->bw_full[bs]);
@@ -637,7 +646,7 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
       }
       __syncwarp();
     };
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = bid; tile < a.num_tiles; tile += gsz, ++it) {
       const int buf = it & 1;
       const uint32_t aph = (uint32_t)(it >> 1) & 1u;
       const bool tr = p.trace && blockIdx.x == 0 && lane == 0 && it < p.trace_cap;
@@ -709,7 +718,22 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
   }
 }
 
-bool plan(const ConvParams &p, int num_sms, RArgs &a) {
+bool plan(const ConvParams &p_in, int num_sms, RArgs &a) {
+  ConvParams p = p_in;
+  // Small replays: a launch with fewer 128-pixel tiles than a quarter of the SMs gives every tile to `split_ways`
+  // CTAs, one per slice of output channels (ConvParams::w_raster_split).
+  a.nsplit = 1;
+  static const bool split_env = !getenv("IRMV_NO_NSPLIT");
+  if (split_env && p.w_raster_split && p.split_ways > 1 && p.stride == 1 && !p.in_parity && !p.tail_w && !p.out2 && !p.out_runs &&
+      !p.seg[0].runs && !p.res_up && p.out && p.cout == p.npad && p.npad % (16 * p.split_ways) == 0) {
+    const long long m = (long long)p.B * (p.OH + 1) * (p.OW + 1) - (p.OW + 1);
+    if ((m + 127) / 128 * p.split_ways <= num_sms) {
+      a.nsplit = p.split_ways;
+      p.w_raster = p.w_raster_split;
+      p.cout /= a.nsplit;
+      p.npad /= a.nsplit;
+    }
+  }
   const bool s2 = p.stride == 2;
   if (s2) {
     // stride 2: 3x3 / pad 1 over the parity-split twin of the input (common.cuh)
@@ -922,8 +946,8 @@ cudaError_t launch_conv_raster(const ConvParams &p, int num_sms, cudaStream_t s)
   RArgs a;
   if (!plan(p, num_sms, a)) return cudaErrorInvalidValue;
   const size_t smem = (size_t)a.off_bars + sizeof(Bars) + 64;
-  const int slots = num_sms * a.ctas_per_sm;
-  const int grid = a.num_tiles < slots ? a.num_tiles : slots;
+  const int slots = num_sms * a.ctas_per_sm / a.nsplit;
+  const int grid = (a.num_tiles < slots ? a.num_tiles : slots) * a.nsplit;
   if (a.ctas_per_sm == 2) {
     switch (a.R) {
       case 4: return launch_r<4, 8>(a, grid, smem, s);

@@ -65,6 +65,8 @@ struct HostConv {   // one GEMM as the kernels see it (possibly several referenc
   std::vector<float> bias;           // [npad]
   std::vector<int32_t> ktab;         // [kpad/8]
   __half *d_plain = nullptr, *d_tiled = nullptr, *d_raster = nullptr;
+  __half *d_raster_split = nullptr;  // [split_ways][k*k][cin/8][npad / split_ways][8] (ConvParams::w_raster_split)
+  int split_ways = 0;
   float *d_bias = nullptr;
   int32_t *d_ktab = nullptr;
   // a 1x1 conv over concat(upsample(a), b) split into W_a (at a's resolution, no bias / activation) and W_b (at
@@ -328,6 +330,19 @@ bool upload(HostConv &h) {
     return cuda_ok(cudaMemcpy(*d, src, bytes, cudaMemcpyHostToDevice), "cudaMemcpy(weights)",
                    __FILE__, __LINE__);
   };
+  // output-channel slices for the small-replay split (layers with at least 128 output channels)
+  if (h.npad >= 128 && h.npad % 64 == 0 && !h.w_raster.empty() && h.w_raster.size() % ((size_t)h.npad * 8) == 0) {
+    const int ways = 4, ns = h.npad / ways;
+    const size_t rows = h.w_raster.size() / ((size_t)h.npad * 8);          // k*k * cin/8
+    std::vector<__half> sp(h.w_raster.size());
+    for (int sl = 0; sl < ways; ++sl)
+      for (size_t r = 0; r < rows; ++r)
+        for (int n = 0; n < ns; ++n)
+          for (int j = 0; j < 8; ++j)
+            sp[(((size_t)sl * rows + r) * ns + n) * 8 + j] = h.w_raster[(r * h.npad + (size_t)sl * ns + n) * 8 + j];
+    if (!up((void **)&h.d_raster_split, sp.data(), sp.size() * 2)) return false;
+    h.split_ways = ways;
+  }
   return up((void **)&h.d_plain, h.w_plain.data(), h.w_plain.size() * 2) &&
          up((void **)&h.d_tiled, h.w_tiled.data(), h.w_tiled.size() * 2) &&
          up((void **)&h.d_raster, h.w_raster.data(), h.w_raster.size() * 2) &&
@@ -630,6 +645,7 @@ void add_conv(irmv_engine *e, Lane &ln, HostConv &hc, std::vector<SegRef> in, in
   p.OW = (W + 2 * p.pad - hc.k) / hc.stride + 1;
   p.cin = cin; p.cout = hc.cout; p.npad = hc.npad; p.K = hc.K; p.kpad = hc.kpad; p.act = hc.act;
   p.w_plain = hc.d_plain; p.w_tiled = hc.d_tiled; p.w_raster = hc.d_raster; p.bias = hc.d_bias;
+  p.w_raster_split = hc.d_raster_split; p.split_ways = hc.split_ways;
   {
     // device tap table for this layer instance
     const int nq = hc.kpad / 8;
@@ -1652,9 +1668,9 @@ void irmv_engine_destroy(irmv_engine *e) {
     for (auto ev : ln.sig) if (ev) cudaEventDestroy(ev);
   }
   for (auto &c : e->convs) {
-    cudaFree(c->d_plain); cudaFree(c->d_tiled); cudaFree(c->d_raster); cudaFree(c->d_bias);
+    cudaFree(c->d_plain); cudaFree(c->d_tiled); cudaFree(c->d_raster); cudaFree(c->d_bias); cudaFree(c->d_raster_split);
     for (HostConv *u : {c->up_a.get(), c->up_b.get()})
-      if (u) { cudaFree(u->d_plain); cudaFree(u->d_tiled); cudaFree(u->d_raster); cudaFree(u->d_bias); }
+      if (u) { cudaFree(u->d_plain); cudaFree(u->d_tiled); cudaFree(u->d_raster); cudaFree(u->d_bias); cudaFree(u->d_raster_split); }
   }
   for (auto &d : e->dws) { cudaFree(d->d_w); cudaFree(d->d_b); }
   for (uint8_t *b : e->sh_blobs) cudaFree(b);

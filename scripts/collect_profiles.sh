@@ -3,26 +3,27 @@
 # only after the same command has exited 0 without ncu.  usage: scripts/collect_profiles.sh [tag]
 set -u
 T=${1:-r2}
+FR=${FR:-256}            # frames per replay = the bench's (bench.py replay_split)
 KRX='regex:^(conv_raster_kernel|conv_tc_kernel|decode_kernel|nms_kernel|pnp_kernel|quads_from_dets_kernel|set_src_kernel|sppf_pool_kernel|stem_kernel|stem_bayer2x_kernel|dwconv3x3_kernel|shuffle_unit_kernel|kpts_from_dets_kernel|quads_from_kpts_kernel)$'
 mkdir -p gpurun_out
 BENCH="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extras --clock-warmup-s 0"
-# 1. launch list of the bench command: 3 warm-up steps + the timed step (= replays 7 and 8), then the end-to-end loop
+# 1. launch list of the bench command: 3 warm-up steps + the timed step (one replay each), then the end-to-end loop
 $BENCH > gpurun_out/${T}_bench_plain.json 2> gpurun_out/${T}_bench_plain.err || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name "$KRX" -c 560 --csv \
     --log-file gpurun_out/${T}_bench_launches.csv $BENCH > gpurun_out/${T}_bench_ncu.log 2>&1
-# 2. per-launch counters of one eager 128-frame replay
-scripts/ncu_replay_metrics.sh 128 ${T}_replay128_metrics
+# 2. per-launch counters of one eager replay of the bench's size
+scripts/ncu_replay_metrics.sh $FR ${T}_replay${FR}_metrics
 cp gpurun_out/ops.json gpurun_out/${T}_ops.json
 # 3. full captures: top GEMM (Detect P3 box.0|cls.0), the gather kernel's largest launch (m5), the stem,
 #    decode, NMS, PnP
 OP=$(python -c "import sys, json; sys.path.insert(0, 'scripts'); from analyze_launches import name_ops; print(1 + [n[0] for n in name_ops(json.load(open('gpurun_out/${T}_ops.json'))) if n[0] != 'POOL'].index('h0.01'))")
-scripts/ncu_one_conv.sh $OP 128 ${T}_raster_h0
+scripts/ncu_one_conv.sh $OP $FR ${T}_raster_h0
 OP2=$(python -c "import sys, json; sys.path.insert(0, 'scripts'); from analyze_launches import name_ops; print(1 + [n[0] for n in name_ops(json.load(open('gpurun_out/${T}_ops.json'))) if n[0] != 'POOL'].index('m5'))")
-RASTER= scripts/ncu_one_conv.sh $OP2 128 ${T}_gather_m5 conv_tc_kernel
-scripts/ncu_stem.sh ${T}_stem
+RASTER= scripts/ncu_one_conv.sh $OP2 $FR ${T}_gather_m5 conv_tc_kernel
+FR=$FR scripts/ncu_stem.sh ${T}_stem
 for k in decode_kernel nms_kernel pnp_kernel; do
   ncu --set full --clock-control none --import-source on --kernel-name regex:^${k}$ --launch-skip 2 --launch-count 1 \
-    -o gpurun_out/${T}_${k} -f python scripts/profile_replay.py 128 1 > gpurun_out/${T}_${k}.log 2>&1
+    -o gpurun_out/${T}_${k} -f python scripts/profile_replay.py $FR 1 > gpurun_out/${T}_${k}.log 2>&1
   ncu -i gpurun_out/${T}_${k}.ncu-rep --page raw --csv > gpurun_out/${T}_${k}_raw.csv 2>/dev/null
   ncu -i gpurun_out/${T}_${k}.ncu-rep --page source --csv > gpurun_out/${T}_${k}_source.csv 2>/dev/null
 done

@@ -2,7 +2,8 @@
 # Copies the artefacts scripts/collect_profiles.sh left in gpurun_out/ into profiles/ (only the files that script
 # writes) and rebuilds the summary: scripts/import_profiles.sh [tag]
 T=${1:-r2}
-for n in bench_launches replay128_metrics raster_h0_raw raster_h0_source gather_m5_raw gather_m5_source stem_raw stem_source \
+FR=${FR:-256}
+for n in bench_launches replay${FR}_metrics raster_h0_raw raster_h0_source gather_m5_raw gather_m5_source stem_raw stem_source \
          decode_kernel_raw decode_kernel_source nms_kernel_raw nms_kernel_source pnp_kernel_raw pnp_kernel_source \
          dwconv_raw dwconv_source armors_raw armors_source shuffle_unit_raw shuffle_unit_source; do
   cp gpurun_out/${T}_${n}.csv profiles/ || exit 1

@@ -11,6 +11,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 P = os.path.join(ROOT, "profiles")
 TAG = sys.argv[1] if len(sys.argv) > 1 else "r2"
+FR = int(os.environ.get("FR", "256"))          # frames per replay of the captures (= bench.py replay_split)
 sys.path.insert(0, os.path.join(ROOT, "scripts"))
 from analyze_launches import name_ops  # noqa: E402
 
@@ -75,16 +76,17 @@ def main():
     L = read_long(os.path.join(P, f"{TAG}_bench_launches.csv"))
     # a replay = [set_src (only when the source pointer of the lane changed)] + stem + ...: split at the stem launches
     starts = [i - 1 if i and L[i - 1]["name"] == "set_src_kernel" else i for i, k in enumerate(L) if k["name"].startswith("stem_")]
-    # launches 0..: three warm-up steps, then the timed step = replays 7 and 8 (two 128-frame replays per 256-frame step)
-    step = L[starts[6]:starts[8]]
+    # launches 0..: three warm-up steps, then the timed step; a step is 256 // FR replays
+    rps = max(1, 256 // FR)
+    step = L[starts[3 * rps]:starts[4 * rps]]
     tot = sum(k["gpu__time_duration.sum"] for k in step)
     agg = collections.defaultdict(lambda: [0, 0.0])
     for k in step:
         agg[k["name"]][0] += 1
         agg[k["name"]][1] += k["gpu__time_duration.sum"]
     out += ["## 1. Launch list of `python bench.py --steps 1 --warmup 3 --no-cpu-baseline`",
-            f"`profiles/{TAG}_bench_launches.csv` (the first {len(L)} launches of the engine's kernels: three warm-up steps, the timed step, the start of the end-to-end loop; the table is the timed step = two",
-            f"128-frame replays = {len(step)} launches: [set_src] + stem + {sum(1 for k in step if k['name'].startswith('conv_')) // 2} GEMM launches + pool + decode + NMS + quads + PnP per replay;",
+            f"`profiles/{TAG}_bench_launches.csv` (the first {len(L)} launches of the engine's kernels: three warm-up steps, the timed step, the start of the end-to-end loop; the table is the timed step = {rps}",
+            f"replay(s) of {FR} frames = {len(step)} launches: [set_src] + stem + {sum(1 for k in step if k['name'].startswith('conv_')) // rps} GEMM launches + pool + decode + NMS + quads + PnP per replay;",
             "eleven 1x1 convs run as fused tails of their producers, conv0 inside the stem, the two neck convs over concat(upsample(a), b) as two raster launches each)", "",
             "| kernel | launches | total us | share |", "|---|---|---|---|"]
     for n, (c, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
@@ -92,9 +94,9 @@ def main():
     conv_share = sum(t for n, (c, t) in agg.items() if n.startswith("conv_")) / tot
     out += ["", f"Convolution kernels (`conv_raster_kernel` + `conv_tc_kernel`) = {100*conv_share:.1f} % of the step's kernel time;",
             "`bench.py` measures the same group live with CUDA events (`roofline.stage_ms.conv / total`).", ""]
-    # ---- per-launch metrics of one 128-frame replay
-    frames = 128
-    M = read_long(os.path.join(P, f"{TAG}_replay128_metrics.csv"))
+    # ---- per-launch metrics of one replay of the bench's size
+    frames = FR
+    M = read_long(os.path.join(P, f"{TAG}_replay{FR}_metrics.csv"))
     tot = sum(k["gpu__time_duration.sum"] for k in M)
     agg = collections.defaultdict(lambda: [0, 0.0, 0.0, 0.0, 0.0, 0.0])
     for k in M:
@@ -104,8 +106,8 @@ def main():
         a[2] += k["dram__bytes_read.sum"]; a[3] += k["dram__bytes_write.sum"]
         a[4] += k["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"] * t
         a[5] += k["lts__t_bytes.sum"]
-    out += [f"## 2. Per-launch counters, one eager replay of {frames} Bayer frames (`scripts/ncu_replay_metrics.sh 128`)",
-            f"`profiles/{TAG}_replay128_metrics.csv` ({len(M)} launches = the whole replay)", "",
+    out += [f"## 2. Per-launch counters, one eager replay of {frames} Bayer frames (`scripts/ncu_replay_metrics.sh {FR}`)",
+            f"`profiles/{TAG}_replay{FR}_metrics.csv` ({len(M)} launches = the whole replay)", "",
             "| kernel | launches | us | share | DRAM read MB | DRAM write MB | L2 bytes MB | tensor pipe active (time-weighted) |",
             "|---|---|---|---|---|---|---|---|"]
     for n, a in sorted(agg.items(), key=lambda x: -x[1][1]):
@@ -115,7 +117,7 @@ def main():
     conv_us = sum(k["gpu__time_duration.sum"] for k in conv) / 1e3
     out += ["", f"DRAM traffic of the {len(conv)} GEMM launches: {traffic/1e6:.1f} MB for {frames} frames = {traffic/frames/1e6:.2f} MB per frame in {conv_us:.0f} us",
             f"= {traffic / conv_us / 1e6:.2f} TB/s averaged over the conv stage (algorithmic: 42.1 MB of conv inputs + 28.6 MB of conv outputs per frame when",
-            "nothing stays in the 126 MB L2; at 128 frames per replay the 160x160 and 80x80 tensors do not fit, so m1-m4 run at the HBM roofline).", ""]
+            f"nothing stays in the 126 MB L2; at {FR} frames per replay the 160x160 and 80x80 tensors do not fit, so m1-m4 run at the HBM roofline).", ""]
     convs = [k for k in M if k["name"].startswith("conv_") or k["name"].startswith("sppf")]
     LY = name_ops(json.load(open(os.path.join(P, f"{TAG}_ops.json"))))
     out += ["Per layer (network order; `hw` = output side, tensor % = `sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed`):", "",
@@ -134,24 +136,24 @@ def main():
                        f"{k['launch__shared_mem_per_block_dynamic']/1e3:.0f} |")
     src_hash = open(os.path.join(P, f"{TAG}_src_hash.txt")).read().strip() if os.path.exists(os.path.join(P, f"{TAG}_src_hash.txt")) else None
     json.dump({"src_hash": src_hash, "conv_group_dram_bytes_per_frame": traffic / frames, "frames": frames, "launches": len(conv),
-               "source": f"profiles/{TAG}_replay128_metrics.csv (dram__bytes_read.sum + dram__bytes_write.sum of the GEMM launches)"},
+               "source": f"profiles/{TAG}_replay{FR}_metrics.csv (dram__bytes_read.sum + dram__bytes_write.sum of the GEMM launches)"},
               open(os.path.join(P, f"{TAG}_traffic.json"), "w"), indent=1)
     # ---- full captures
     keys = ["gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum",
             "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
             "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
             "launch__shared_mem_per_block_dynamic", "launch__grid_size", "launch__block_size", "sm__warps_active.avg.pct_of_peak_sustained_active"]
-    h0 = full_capture(out, f"{TAG}_raster_h0", "## 3. `ncu --set full --import-source on` of the top GEMM (Detect P3 box.0|cls.0: 3x3, 64 -> 128, 128 frames)", keys)
+    h0 = full_capture(out, f"{TAG}_raster_h0", "## 3. `ncu --set full --import-source on` of the top GEMM (Detect P3 box.0|cls.0: 3x3, 64 -> 128, " + str(FR) + " frames)", keys)
     out += ["", "The MMA issue loop now runs at the tensor pipe's own rate (scripts/mma_probe.cu: max(N/2, 32 + N/4) cycles per M128 x N x K16 MMA,",
             "the 32 + N/4 term being the shared-memory operand fetch); what is left is the per-tile hand-off (a two-stage activation ring next to",
             "147 KB of resident weights) and the epilogue's TMEM round trip."]
-    st = full_capture(out, f"{TAG}_stem", "## 4. `ncu --set full --import-source on` of `stem_bayer2x_kernel` (demosaic + rot180 + resize + /255 + conv0, 128 Bayer frames)", keys)
+    st = full_capture(out, f"{TAG}_stem", "## 4. `ncu --set full --import-source on` of `stem_bayer2x_kernel` (demosaic + rot180 + resize + /255 + conv0, " + str(FR) + " Bayer frames)", keys)
     try:
         t_us = st["time_us"]
-        alg = (1310720 + 16 * 320 * 320 * 2) * 128
+        alg = (1310720 + 16 * 320 * 320 * 2) * FR
         out += ["", f"Algorithmic bytes: 1.31 MB Bayer in + 3.28 MB conv0 out per frame = {alg/1e6:.0f} MB per launch -> {alg/t_us/1e6:.2f} TB/s achieved",
                 f"({100*alg/t_us/1e6/6.5494:.0f} % of the measured 6549 GB/s); DRAM traffic {(st['dram__bytes_read.sum:bytes']+st['dram__bytes_write.sum:bytes'])/1e6:.0f} MB "
-                "(nothing is re-read).  Round 1's generic stem took 741 us for the same launch (630 M warp instructions); this kernel executes",
+                "(nothing is re-read).  Round 1's generic stem took 741 us per 128 frames (630 M warp instructions); this kernel executes",
                 f"{float(st['smsp__inst_executed.sum'])/1e6:.0f} M.  It is still issue / shared-memory-pipe bound, not HBM bound (see DESIGN.md section 3)."]
     except Exception:
         pass
@@ -166,10 +168,10 @@ def main():
                      "seeded light-bar scenes, `scripts/bench_armors.py`)", keys)
         out += ["", "One CTA per detection; the border walks are serial per component (one lane), so the kernel is latency bound:",
                 "`scripts/bench_armors.py` with IRMV_ARMOR_PROF=1 gives the cycles per ROI by phase (`profiles/{TAG}_armors_phase_profile.json`).", ""]
-    extra = [("gather_m5", "## 7. `conv_tc_kernel`, its largest launch (m5: 3x3 stride 2, 64 -> 128, 80x80 -> 40x40, 128 frames)"),
-             ("decode_kernel", "## 8. `decode_kernel` (DFL decode + candidate keys, 128 frames)"),
-             ("nms_kernel", "## 9. `nms_kernel` (top-k, sort, class-aware greedy NMS; one CTA per frame, 128 frames)"),
-             ("pnp_kernel", "## 10. `pnp_kernel` (IPPE, 12800 quads = 128 frames x 100 slots)"),
+    extra = [("gather_m5", "## 7. `conv_tc_kernel`, its largest launch (m5: 3x3 stride 2, 64 -> 128, 80x80 -> 40x40, " + str(FR) + " frames)"),
+             ("decode_kernel", "## 8. `decode_kernel` (DFL decode + candidate keys, " + str(FR) + " frames)"),
+             ("nms_kernel", "## 9. `nms_kernel` (top-k, sort, class-aware greedy NMS; one CTA per frame, " + str(FR) + " frames)"),
+             ("pnp_kernel", "## 10. `pnp_kernel` (IPPE, " + str(FR * 100) + " quads = " + str(FR) + " frames x 100 slots)"),
              ("dwconv", "## 11. `dwconv3x3_kernel` (ShuffleNetV2 variant, d1.b1.dw: 16 channels, 320x320 -> 160x160, stride 2, 64 frames)")]
     for tag, title in extra:
         if os.path.exists(os.path.join(P, f"{TAG}_{tag}_raw.csv")):
@@ -204,7 +206,7 @@ def main():
         out += ["", "The units are bound by instruction issue and the shared-memory pipe, not by HBM: with K = N = 16..64 the 1x1 GEMMs are mostly",
                 "epilogue (SiLU, pack, store) and fragment loads; the depthwise convs run on the tensor cores as block-diagonal GEMMs (17 -> 0.3 issue",
                 "slots per output value).  See DESIGN.md section 3 for the comparison with the one-launch-per-convolution path."]
-    json.dump({"src_hash": src_hash, "kernel": "conv_raster_kernel (Detect P3 box.0|cls.0, 3x3 64->128)", "frames": 128,
+    json.dump({"src_hash": src_hash, "kernel": "conv_raster_kernel (Detect P3 box.0|cls.0, 3x3 64->128)", "frames": FR,
                "dram_bytes_per_launch": h0.get("dram__bytes_read.sum:bytes", 0.0) + h0.get("dram__bytes_write.sum:bytes", 0.0),
                "gpu_time_us": h0.get("time_us", 0.0),
                "tensor_pipe_pct": float(h0.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", 0)),
