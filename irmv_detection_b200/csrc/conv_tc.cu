@@ -15,6 +15,8 @@
 //               descriptors; tcgen05.commit releases ring slots and publishes accumulators.
 //   warps 8-11  epilogue: tcgen05.ld accumulator rows out of TMEM (double-buffered, 2*N columns),
 //               + bias, SiLU, residual, FP16 pack, channel-slice store.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace irmv {
@@ -162,6 +164,8 @@ __device__ __forceinline__ float silu(float x) {
 struct TcArgs {
   ConvParams p;
   int M, num_tiles, KB, ksteps_last, stages, b_resident, tmem_cols, rev;
+  int nsplit, npad_full;        // nsplit > 1: CTA b computes output channels [slice * p.npad, +p.npad) of tile b / nsplit, slice = b % nsplit
+                                // (p.npad / p.cout are the slice's; npad_full is the row count of a k-block of w_tiled)
   uint32_t idesc;
   uint32_t mul_ow, mul_oh;      // ceil(2^34 / OW), ceil(2^34 / OH): q = (n * mul) >> 34, exact for n < 2^25
   uint32_t off_b, off_ktab, off_bias, off_bars;
@@ -178,9 +182,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int npad = p.npad;
   const uint32_t b_block_bytes = (uint32_t)npad * 128u;
+  // output-channel split for small replays (same idea as the raster kernel's, conv_raster.cu): a k-block of the
+  // pre-swizzled weights is [npad_full rows][128 B], so a slice of rows (a multiple of 8) is a contiguous range
+  // with the same swizzle phase
+  const int nsplit = a.nsplit;
+  const int bid = nsplit > 1 ? (int)(blockIdx.x / (unsigned)nsplit) : (int)blockIdx.x;
+  const int gsz = nsplit > 1 ? (int)(gridDim.x / (unsigned)nsplit) : (int)gridDim.x;
+  const int split = nsplit > 1 ? (int)(blockIdx.x % (unsigned)nsplit) : 0;
+  const __half *const w_g = p.w_tiled + (size_t)split * npad * BK;
+  const size_t w_kb_stride = (size_t)a.npad_full * BK;
 
+  // Programmatic dependent launch: the next kernel may start its prologue now; this kernel's own prologue (tables,
+  // barriers, TMEM, resident weights) runs under the previous kernel's tail and only the warps that touch
+  // activations wait for it (griddepcontrol.wait below).
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   for (int i = tid; i < a.KB * 16; i += NTHREADS) s_ktab[i] = p.ktab[i];
-  for (int i = tid; i < npad; i += NTHREADS) s_bias[i] = p.bias[i];
+  for (int i = tid; i < npad; i += NTHREADS) s_bias[i] = p.bias[split * npad + i];
   if (tid == 0) {
     for (int s = 0; s < a.stages; ++s) {
       mbar_init(&bars->full[s], 128 + (a.b_resident ? 0 : 1));   // the 128 threads of the owning producer group
@@ -202,6 +219,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  if (warp != BLD_WARP) asm volatile("griddepcontrol.wait;" ::: "memory");   // weights are constants: their loader runs ahead
 
   if (warp < EPI_WARP0) {
     // ===================================================================== A producers
@@ -235,7 +253,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
     int own = 0;               // k-blocks this group has issued
     int s_pub = grp % stages;  // ring slot of the next k-block this group publishes
     int itp = 0;
-    for (int tseq = blockIdx.x; tseq < a.num_tiles; tseq += gridDim.x, ++itp) {
+    for (int tseq = bid; tseq < a.num_tiles; tseq += gsz, ++itp) {
       const int tile = a.rev ? a.num_tiles - 1 - tseq : tseq; (void)tile;
       const bool tr = p.trace && blockIdx.x == 0 && tid == 0 && itp < p.trace_cap;
       if (tr) p.trace[itp * 8 + 0] = clock64();
@@ -300,7 +318,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
     const int ew = warp - EPI_WARP0;
     const int row = ew * 32 + lane;
     int it = 0;
-    for (int tseq = blockIdx.x; tseq < a.num_tiles; tseq += gridDim.x, ++it) {
+    for (int tseq = bid; tseq < a.num_tiles; tseq += gsz, ++it) {
       const int tile = a.rev ? a.num_tiles - 1 - tseq : tseq; (void)tile;
       const int acc = it & 1;
       const uint32_t aph = (uint32_t)(it >> 1) & 1u;
@@ -316,8 +334,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
         const uint32_t bimg = (uint32_t)(((uint64_t)t * a.mul_oh) >> 34);
         opix = (size_t)pr_index((int)bimg, (int)t - (int)bimg * p.OH, m - (int)t * p.OW, p.OH, p.OW);
       }
-      __half *orow = p.out + opix * 8;                      // + plane * out_pstride
-      const __half *rrow = p.res ? p.res + opix * 8 : nullptr;
+      __half *orow = p.out + (size_t)(split * (npad >> 3)) * p.out_pstride + opix * 8;                      // + plane * out_pstride
+      const __half *rrow = p.res ? p.res + (size_t)(split * (npad >> 3)) * p.res_pstride + opix * 8 : nullptr;
       const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * npad);
       for (int c0 = 0; c0 < npad; c0 += 16) {
         uint32_t r[16];
@@ -364,7 +382,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
     int it = 0, s = 0;
     uint32_t ph = 0;
     const int stages = a.stages, KB = a.KB;
-    for (int tseq = blockIdx.x; tseq < a.num_tiles; tseq += gridDim.x, ++it) {
+    for (int tseq = bid; tseq < a.num_tiles; tseq += gsz, ++it) {
       const int tile = a.rev ? a.num_tiles - 1 - tseq : tseq; (void)tile;
       const int acc = it & 1;
       const uint32_t aph = (uint32_t)(it >> 1) & 1u;
@@ -403,17 +421,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
       if (a.b_resident) {
         mbar_expect_tx(&bars->bfull, (uint32_t)a.KB * b_block_bytes);
         for (int kb = 0; kb < a.KB; ++kb)
-          bulk_g2s(sB + (size_t)kb * b_block_bytes, p.w_tiled + (size_t)kb * npad * BK,
+          bulk_g2s(sB + (size_t)kb * b_block_bytes, w_g + (size_t)kb * w_kb_stride,
                    b_block_bytes, &bars->bfull);
       } else {
         int s = 0;
         uint32_t ph = 0;
-        for (int tseq = blockIdx.x; tseq < a.num_tiles; tseq += gridDim.x) {
+        for (int tseq = bid; tseq < a.num_tiles; tseq += gsz) {
       const int tile = a.rev ? a.num_tiles - 1 - tseq : tseq; (void)tile;
           for (int kb = 0; kb < a.KB; ++kb) {
             mbar_wait(&bars->empty[s], ph ^ 1u);
             mbar_expect_tx(&bars->full[s], b_block_bytes);
-            bulk_g2s(sB + (size_t)s * b_block_bytes, p.w_tiled + (size_t)kb * npad * BK,
+            bulk_g2s(sB + (size_t)s * b_block_bytes, w_g + (size_t)kb * w_kb_stride,
                      b_block_bytes, &bars->full[s]);
             if (++s == a.stages) { s = 0; ph ^= 1u; }
           }
@@ -451,11 +469,20 @@ size_t conv_tc_smem_bytes(const ConvParams &p, int *stages_out, int *b_resident_
   return (size_t)stages * A_STAGE + b_bytes + misc + 1024;
 }
 
-cudaError_t launch_conv_tc(const ConvParams &p, int num_sms, cudaStream_t s) {
+cudaError_t launch_conv_tc(const ConvParams &p_in, int num_sms, cudaStream_t s) {
   TcArgs a;
-  a.p = p;
+  ConvParams p = p_in;
   a.M = p.B * p.OH * p.OW;
   a.num_tiles = (a.M + BM - 1) / BM;
+  a.nsplit = 1;
+  a.npad_full = p.npad;
+  static const bool split_env = !getenv("IRMV_NO_NSPLIT");
+  if (split_env && p.npad >= 128 && p.npad % 64 == 0 && p.cout == p.npad && a.num_tiles * 4 <= num_sms) {
+    a.nsplit = 4;
+    p.npad /= 4;
+    p.cout /= 4;
+  }
+  a.p = p;
   a.rev = p.rev_tiles;
   a.KB = p.kpad / BK;
   const int ksteps_total = (p.K + 15) / 16;
@@ -480,9 +507,20 @@ cudaError_t launch_conv_tc(const ConvParams &p, int num_sms, cudaStream_t s) {
                                          (int)(227 * 1024));
     if (e != cudaSuccess) return e;
   }
-  int grid = a.num_tiles < num_sms ? a.num_tiles : num_sms;
-  conv_tc_kernel<<<grid, NTHREADS, smem, s>>>(a);
-  return cudaGetLastError();
+  const int slots = num_sms / a.nsplit;
+  const int grid = (a.num_tiles < slots ? a.num_tiles : slots) * a.nsplit;
+  static const bool pdl = !getenv("IRMV_NO_PDL") && !getenv("IRMV_TC_NO_PDL");
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, conv_tc_kernel, a);
 }
 
 }  // namespace irmv
