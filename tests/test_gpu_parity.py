@@ -982,6 +982,17 @@ def test_bench_configuration_pinned_to_single_frame_engine_and_oracle(base_image
                 assert np.array_equal(one.read_tensor(f"cls{i}")[0], cls_big[i][pos]), f"frame {pos} cls{i}"
     assert total > 0
     one.close()
+    # the pipelined host path of the same engine (submit_batch replays a 256-frame batch in host chunks of 128
+    # frames while the copy of the next chunk runs): same detections and poses as the synchronous call
+    cs, ds = big.detect_batch_arrays(raw)
+    cs, ds = cs.copy(), ds.copy()
+    cp, dp, rvp, tvp, okp = big.collect_arrays(big.submit_batch(raw), poses=True)
+    assert np.array_equal(cs, cp)
+    for f in range(256):
+        k = int(cs[f])
+        assert np.array_equal(ds[f, :k], dp[f, :k]), f"pipelined frame {f}"
+        assert np.array_equal(rv[f, :k], rvp[f, :k]) and np.array_equal(tv[f, :k], tvp[f, :k]) and np.array_equal(ok[f, :k], okp[f, :k])
+    big.detect_batch(raw)                                             # lane 0 holds frames 0.. again
     # frame 0 of the replay against the FP32 oracle
     x = irmv.preprocess(raw[:1], irmv.CH_BAYER_RGGB)
     ri, _ = _frame_vs_oracle(big, 0, x, weights_seed0)
