@@ -18,8 +18,9 @@ def main():
     fr = bench.make_bayer_frames_device(n, seed=0, device=torch.device("cuda:0"))
     eng = irmv.YoloEngine(w, (1280, 1024), chan_order=irmv.CH_BAYER_RGGB, max_batch=n, sub_batch=n, num_lanes=1)
     eng.enable_pnp(bench.K_CAM, bench.D_CAM, (0.5, 480 / 1024))
-    for _ in range(30):
-        eng.detect_batch_device(fr.data_ptr(), n) if hasattr(eng, "detect_batch_device") else eng.profile_stages(fr.data_ptr(), n)
+    for _ in range(30):                                   # clock ramp
+        eng.enqueue_batch_device(fr.data_ptr(), n)
+        eng.sync()
     conv, tot = [], []
     for _ in range(7):
         k, st = eng.profile_stages(fr.data_ptr(), n)
