@@ -1064,9 +1064,11 @@ int issue_replay(irmv_engine *e, Lane &ln, int n, cudaStream_t st, int *launches
   static const bool pingpong = !getenv("IRMV_NO_PINGPONG");
   // Branched schedule for small replays: at batch 1 a Detect tower launch occupies 4-52 of the 148 SMs and the
   // replay is a chain of ~57 launch latencies, so the towers of a scale run on side streams next to the rest of the
-  // neck and next to each other (fork / join by events; inside a CUDA graph these become parallel branches).  Large
-  // replays fill the machine with every launch and stay on one stream.
-  static const int branch_max = getenv("IRMV_BRANCH_MAX") ? atoi(getenv("IRMV_BRANCH_MAX")) : 4;
+  // neck and next to each other (fork / join by events; inside a CUDA graph these become parallel branches).  Measured
+  // (scripts/ab_small.py, device time of a replay, one stream -> branched): 1 frame 392 -> 346 us, 8 frames 548 -> 525,
+  // 64 frames 1438 -> 1411 (the towers fill the other launches' partial last waves); at 128 / 256 frames every launch
+  // fills the machine and the two schedules time the same, so those stay on one stream.
+  static const int branch_max = getenv("IRMV_BRANCH_MAX") ? atoi(getenv("IRMV_BRANCH_MAX")) : 64;
   const bool branched = n <= branch_max && !stage_events && !op_events && e->cfg.conv_impl != IRMV_CONV_DIRECT;
   unsigned side_used = 0;
   const cudaStream_t trunk = st;

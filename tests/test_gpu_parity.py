@@ -961,7 +961,11 @@ def test_bench_configuration_pinned_to_single_frame_engine_and_oracle(base_image
     big = irmv.YoloEngine(weights_seed0, (1280, 1024), chan_order=irmv.CH_BAYER_RGGB, max_batch=256,
                           sub_batch=sub, num_lanes=lanes)
     big.enable_pnp(P.K_DEFAULT, P.D_DEFAULT, (0.5, 480 / 1024))
-    res = big.detect_batch(raw)
+    import torch
+    raw_dev = torch.from_numpy(raw).cuda()
+    res_host = big.detect_batch(raw)           # host frames: 128-frame chunks through the copy stream when sub = 256
+    res = big.detect_batch_device(raw_dev.data_ptr(), 256)            # the bench's timed path: device-resident frames
+    assert res == res_host
     rv, tv, ok = big.fetch_poses(256)
     box_big = [big.read_tensor(f"box{i}") for i in range(3)]          # lane 0 = frames 0..sub-1
     cls_big = [big.read_tensor(f"cls{i}") for i in range(3)]
@@ -992,7 +996,7 @@ def test_bench_configuration_pinned_to_single_frame_engine_and_oracle(base_image
         k = int(cs[f])
         assert np.array_equal(ds[f, :k], dp[f, :k]), f"pipelined frame {f}"
         assert np.array_equal(rv[f, :k], rvp[f, :k]) and np.array_equal(tv[f, :k], tvp[f, :k]) and np.array_equal(ok[f, :k], okp[f, :k])
-    big.detect_batch(raw)                                             # lane 0 holds frames 0.. again
+    big.detect_batch_device(raw_dev.data_ptr(), 256)                  # lane 0 holds frames 0.. again
     # frame 0 of the replay against the FP32 oracle
     x = irmv.preprocess(raw[:1], irmv.CH_BAYER_RGGB)
     ri, _ = _frame_vs_oracle(big, 0, x, weights_seed0)
@@ -1075,8 +1079,10 @@ def test_every_plan_instantiation_is_oracle_compared(base_image, weights_seed0):
     one = irmv.YoloEngine(weights_seed0, (1280, 1024), chan_order=irmv.CH_BAYER_RGGB)
     x0 = irmv.preprocess(raw[:1], irmv.CH_BAYER_RGGB)
     ref = {}
+    import torch
+    raw_dev = torch.from_numpy(raw).cuda()
     for n in picked:
-        res = big.detect_batch(raw[:n])
+        res = big.detect_batch_device(raw_dev.data_ptr(), n)       # one replay of n device-resident frames (host batches of > 128 frames are chunked)
         heads = [big.read_tensor(f"{t}{i}") for t in ("box", "cls") for i in range(3)]
         for pos in sorted({0, n // 2, n - 1}):
             if pos not in ref:
