@@ -161,11 +161,6 @@ struct ConvParams {
   // quarter of the weights through its SM and issues N/4-wide MMAs.  Null = never split.
   const __half *w_raster_split;
   int split_ways;
-  // Raster kernel, small replays: 1 = `out2` is the NORMAL layout of a half-resolution tensor and only the pixels with
-  // even y and even x are stored there (out == null): a 3x3 / stride-2 / pad-1 convolution computed at stride 1,
-  // out_s2[oy][ox] = out_s1[2 oy][2 ox].  Four times the MMAs, but a one-frame replay is a chain of launch latencies
-  // and the halo-tile kernel starts in half the time of the gather kernel (engine.cu, Op::cp_small).
-  int out2_sub;
 };
 cudaError_t launch_conv_direct(const ConvParams &p, cudaStream_t s);
 cudaError_t launch_conv_tc(const ConvParams &p, int num_sms, cudaStream_t s);

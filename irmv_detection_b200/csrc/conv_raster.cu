@@ -356,9 +356,8 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
     const long long out_ps_pair = orl == 1 ? 2 * out_ps : out_ps;   // distance between the two planes of a 16-channel chunk
     const int cout = p.cout;
     const int Wp = a.Wp, Hp1 = a.Hp1, W = p.OW, q_end = a.q_end, TM = a.TM;
-    const int sub2 = p.out2_sub;                            // out2 = even pixels only, normal half-resolution layout
+    __half *const out2 = p.out2;
     const long long out2_ps = p.out2_pstride;
-    __half *const out2 = (p.out2 && sub2) ? p.out2 + (long long)(split * (npad >> 3)) * out2_ps : p.out2;
     const int Wp2 = (p.OW >> 1) + 1, Hp2 = (p.OH >> 1) + 1, cpl = cout >> 3;
     const uint32_t mul_wp = a.mul_wp, mul_hp1 = a.mul_hp1;
     const int q_lane = a.q_begin + ew * 32 + lane;
@@ -455,8 +454,7 @@ __global__ void __launch_bounds__((NEPI + 2) * 32, NEPI == 8 ? 2 : 1) conv_raste
           const uint32_t img = (uint32_t)(((uint64_t)row * mul_hp1) >> 34);
           const int y = (int)row - (int)img * Hp1 - 1;
           const int px2 = ((int)img * Hp2 + 1 + (y >> 1)) * Wp2 + (x >> 1);
-          if (sub2) t.o2 = ((x | y) & 1) ? nullptr : out2 + (long long)(t.c0 >> 3) * out2_ps + (long long)px2 * 8;
-          else t.o2 = out2 + (long long)(((y & 1) * 2 + (x & 1)) * cpl + (t.c0 >> 3)) * out2_ps + (long long)px2 * 8;
+          t.o2 = out2 + (long long)(((y & 1) * 2 + (x & 1)) * cpl + (t.c0 >> 3)) * out2_ps + (long long)px2 * 8;
         }
         if (RES == 1 && t.ok) {                             // residual: issue the loads early
           const __half *rp = res_q + (long long)(t.c0 >> 3) * res_ps + r * 1024;
@@ -726,9 +724,8 @@ bool plan(const ConvParams &p_in, int num_sms, RArgs &a) {
   // CTAs, one per slice of output channels (ConvParams::w_raster_split).
   a.nsplit = 1;
   static const bool split_env = !getenv("IRMV_NO_NSPLIT");
-  if (split_env && p.w_raster_split && p.split_ways > 1 && p.stride == 1 && !p.in_parity && !p.tail_w && !p.out_runs &&
-      ((p.out && !p.out2) || (!p.out && p.out2 && p.out2_sub)) &&
-      !p.seg[0].runs && !p.res_up && p.cout == p.npad && p.npad % (16 * p.split_ways) == 0) {
+  if (split_env && p.w_raster_split && p.split_ways > 1 && p.stride == 1 && !p.in_parity && !p.tail_w && !p.out2 && !p.out_runs &&
+      !p.seg[0].runs && !p.res_up && p.out && p.cout == p.npad && p.npad % (16 * p.split_ways) == 0) {
     const long long m = (long long)p.B * (p.OH + 1) * (p.OW + 1) - (p.OW + 1);
     if ((m + 127) / 128 * p.split_ways <= num_sms) {
       a.nsplit = p.split_ways;

@@ -368,10 +368,6 @@ struct Op {
   // Small replays (issue_replay): independent sub-graphs run on side streams.  `stream` 0 is the lane's own
   // stream; before the op its stream waits for event `wait`, after it the stream records event `signal`.
   int stream = 0, wait = -1, signal = -1;
-  // 3x3 / stride-2 layers of the gather kernel: the same convolution as a stride-1 launch of the raster kernel that
-  // stores the even pixels only (ConvParams::out2_sub), used when that launch is at most one wave of tiles
-  ConvParams cp_small{};
-  bool has_small = false;
   __half *pool_buf = nullptr;
   int pH = 0, pW = 0, pC = 0;
   long long pStride = 0;
@@ -691,13 +687,6 @@ void add_conv(irmv_engine *e, Lane &ln, HostConv &hc, std::vector<SegRef> in, in
   }
   op.raster = conv_raster_fits(p) && !getenv("IRMV_NO_RASTER");
   if (p.out2 && !op.raster) { p.out2 = nullptr; p.out = out.p; }   // conv0 as a stand-alone op: the stem kernel writes the twin
-  if (!op.raster && hc.stride == 2 && hc.k == 3 && p.nseg == 1 && !p.seg[0].up && !p.res && !p.out2 && !p.in_parity && p.out &&
-      !(p.H & 1) && !(p.W & 1) && hc.d_raster && !getenv("IRMV_NO_RASTER")) {
-    ConvParams q = p;                       // small replays: stride 1 on the raster kernel, even output pixels only (Op::cp_small)
-    q.stride = 1; q.OH = p.H; q.OW = p.W;
-    q.out = nullptr; q.out2 = p.out; q.out2_pstride = p.out_pstride; q.out2_sub = 1;
-    if (conv_raster_fits(q)) { op.cp_small = q; op.has_small = true; }
-  }
   ln.ops.push_back(op);
 }
 
@@ -1098,15 +1087,9 @@ int issue_replay(irmv_engine *e, Lane &ln, int n, cudaStream_t st, int *launches
       ConvParams p = op.cp;
       p.B = n;
       p.rev_tiles = pingpong ? (seq & 1) : 0;
-      static const bool s1sub = !getenv("IRMV_NO_S1SUB");
       if (e->cfg.conv_impl == IRMV_CONV_DIRECT) IRMV_CUDA(launch_conv_direct(p, st));
       else if (op.raster) IRMV_CUDA(launch_conv_raster(p, e->num_sms, st));
-      else if (op.has_small && s1sub && ((long long)n * (p.H + 1) * (p.W + 1) + 127) / 128 <= e->num_sms) {
-        ConvParams q = op.cp_small;                       // small replay: stride 1 on the raster kernel, even pixels stored
-        q.B = n;
-        q.rev_tiles = p.rev_tiles;
-        IRMV_CUDA(launch_conv_raster(q, e->num_sms, st));
-      } else IRMV_CUDA(launch_conv_tc(p, e->num_sms, st));
+      else IRMV_CUDA(launch_conv_tc(p, e->num_sms, st));
     } else if (op.kind == Op::SHUF) {
       ShuffleUnitParams q = op.su;
       q.B = n;
