@@ -237,7 +237,10 @@ int irmv_engine_fetch_armors(irmv_engine *e, int ticket, int nframes, irmv_armor
  * like detect_batch (rvecs/tvecs/ok may be null).  At most three batches in flight; collect in order.
  * The hand-off is checked: a fourth submit before a collect, a ticket that is not in flight (stale,
  * duplicate, never issued), an out-of-order collect, and any synchronous entry point (detect,
- * detect_batch, enqueue_batch, rotated image) while batches are in flight return an error. */
+ * detect_batch, enqueue_batch, rotated image) while batches are in flight return an error.
+ * Host batches are replayed in chunks of at most 128 frames whatever sub_batch is (a chunk starts as soon as its
+ * own frames have landed, under the copy of the next one); synchronous detect_batch calls with more than 128 host
+ * frames take the same route.  Results do not depend on the chunking. */
 int irmv_engine_submit_batch(irmv_engine *e, const uint8_t *frames_host, int nframes, int *ticket);
 int irmv_engine_collect(irmv_engine *e, int ticket, irmv_bbox *out, int *counts, double *rvecs, double *tvecs,
                         uint8_t *ok);

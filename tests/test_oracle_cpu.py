@@ -595,3 +595,20 @@ def test_media_type_to_channel_order():
     assert f(COLOR | O24 | 0x0015) == L.CH_SWAP_RB       # BGR8
     assert f(MONO | O8 | 0x0001) == -1                   # MONO8
     assert f(MONO | O16 | 0x000D) == -1                  # BAYRG10: not ingested
+
+
+def test_bench_replay_split_and_config_are_shared_by_both_arms():
+    """bench.py: the engine runs the 256-frame step as one replay on one lane by default; explicit flags win; the
+    reference arm prints the same `config` object as the repo's arm (the driver compares them)."""
+    import argparse
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    a = argparse.Namespace(batch=256, sub_batch=0, lanes=0)
+    assert bench.replay_split(a) == (256, 1)
+    assert bench.replay_split(argparse.Namespace(batch=512, sub_batch=0, lanes=0)) == (256, 2)
+    assert bench.replay_split(argparse.Namespace(batch=64, sub_batch=0, lanes=0)) == (64, 1)
+    assert bench.replay_split(argparse.Namespace(batch=256, sub_batch=128, lanes=2)) == (128, 2)
+    cfg = bench.workload_config(256, *bench.replay_split(a))
+    assert cfg["frames_per_gpu_per_step"] == 256 and cfg["sub_batch"] == 256 and cfg["lanes"] == 1
+    assert "workload" in cfg and "model" not in cfg
